@@ -1,0 +1,196 @@
+/*
+ * TEST INFRASTRUCTURE ONLY -- C entry points around the UNMODIFIED reference.
+ *
+ * Compiles patflick/psac's own headers where they lie under /root/reference
+ * (nothing is copied into this repo) against oracle/mpi_shim/mpi.h and runs
+ * them at np=1.  Output: oracle/_ref/libpsacref.so (git-ignored).  Only
+ * tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may load it.
+ *
+ * Reference entry points wrapped here:
+ *   suffix_array<char,index_t,LCP>::construct      include/suffix_array.hpp:469-486
+ *   suffix_array<...>::construct_arr<L>            include/suffix_array.hpp:490-641
+ *   alphabet<char>::from_sequence / encode          include/alphabet.hpp:213-218, 274-278
+ *   kmer_generation                                 include/kmer.hpp:204-224
+ *   lcp_bitwise                                     include/bitops.hpp:169-183
+ *   lcp_from_sa (Kasai checker)                     include/lcp.hpp:46-77
+ *   ansv / ansv_sequential                          include/ansv.hpp:47-65, 2042-2051
+ *   construct_suffix_tree                           include/suffix_tree.hpp:413-499
+ */
+#include <mpi.h>
+
+#include <cstdint>
+#include <cstring>
+#include <iostream>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include <mxx/env.hpp>
+#include <mxx/comm.hpp>
+
+#include <suffix_array.hpp>
+#include <alphabet.hpp>
+#include <kmer.hpp>
+#include <bitops.hpp>
+#include <lcp.hpp>
+#include <ansv.hpp>
+#include <suffix_tree.hpp>
+
+namespace {
+
+/* the reference logs to std::cerr unconditionally (suffix_array.hpp:49); mute it */
+struct cerr_mute {
+    std::streambuf* old;
+    std::ostringstream sink;
+    bool on;
+    explicit cerr_mute(bool enable) : old(nullptr), on(enable) { if (on) old = std::cerr.rdbuf(sink.rdbuf()); }
+    ~cerr_mute() { if (on) std::cerr.rdbuf(old); }
+};
+
+bool g_verbose = false;
+
+template <typename index_t, bool LCP>
+int run_construct(const char* text, size_t n, unsigned k, int fast, int arr_L, void* sa_out, void* isa_out, void* lcp_out) {
+    cerr_mute mute(!g_verbose);
+    mxx::comm c;
+    suffix_array<char, index_t, LCP> sa(c);
+    switch (arr_L) {
+        case 0: sa.construct(text, text + n, fast != 0, k); break;
+        case 2: sa.template construct_arr<2>(text, text + n, fast != 0); break;
+        case 3: sa.template construct_arr<3>(text, text + n, fast != 0); break;
+        case 4: sa.template construct_arr<4>(text, text + n, fast != 0); break;
+        default: return -2;
+    }
+    if (sa.local_SA.size() != n || sa.local_B.size() != n) return -3;
+    if (sa_out) std::memcpy(sa_out, sa.local_SA.data(), n * sizeof(index_t));
+    if (isa_out) std::memcpy(isa_out, sa.local_B.data(), n * sizeof(index_t));
+    if (LCP && lcp_out) {
+        if (sa.local_LCP.size() != n) return -4;
+        std::memcpy(lcp_out, sa.local_LCP.data(), n * sizeof(index_t));
+    }
+    return 0;
+}
+
+} // namespace
+
+extern "C" {
+
+void psacref_set_verbose(int v) { g_verbose = v != 0; }
+
+/* suffix_array<char,index_t,LCP>::construct / construct_arr<L> at np=1.
+ * index_bytes 4|8; want_lcp 0|1 (ignored for arr_L != 0: the reference builds no LCP there);
+ * arr_L = 0 -> construct(begin,end,fast,k); 2..4 -> construct_arr<L>(begin,end,fast). */
+int psacref_construct(const char* text, size_t n, int index_bytes, int want_lcp, unsigned k, int fast, int arr_L,
+                      void* sa_out, void* isa_out, void* lcp_out) {
+    try {
+        if (index_bytes == 4) {
+            return want_lcp && arr_L == 0 ? run_construct<uint32_t, true>(text, n, k, fast, arr_L, sa_out, isa_out, lcp_out)
+                                          : run_construct<uint32_t, false>(text, n, k, fast, arr_L, sa_out, isa_out, lcp_out);
+        } else if (index_bytes == 8) {
+            return want_lcp && arr_L == 0 ? run_construct<uint64_t, true>(text, n, k, fast, arr_L, sa_out, isa_out, lcp_out)
+                                          : run_construct<uint64_t, false>(text, n, k, fast, arr_L, sa_out, isa_out, lcp_out);
+        }
+        return -1;
+    } catch (const std::exception& e) {
+        std::fprintf(stderr, "psacref_construct: %s\n", e.what());
+        return -10;
+    }
+}
+
+/* alphabet<char>::from_sequence: lut[c] = encode(c) (uchar, wraps at 256), sigma, bits_per_char */
+int psacref_alphabet(const char* text, size_t n, uint8_t* lut256, unsigned* sigma, unsigned* bits_per_char) {
+    alphabet<char> a = alphabet<char>::from_sequence(text, text + n);
+    for (int ch = 0; ch < 256; ++ch) lut256[ch] = a.encode((char)ch);
+    *sigma = a.sigma();
+    *bits_per_char = a.bits_per_char();
+    return 0;
+}
+
+/* get_optimal_k at np=1 (kmer.hpp:25-40) */
+unsigned psacref_optimal_k(const char* text, size_t n, int index_bytes, unsigned k) {
+    mxx::comm c;
+    alphabet<char> a = alphabet<char>::from_sequence(text, text + n);
+    return index_bytes == 4 ? get_optimal_k<uint32_t>(a, n, c, k) : get_optimal_k<uint64_t>(a, n, c, k);
+}
+
+/* kmer_generation at np=1 (kmer.hpp:204-224), k as given (caller clamps) */
+int psacref_kmer_generation(const char* text, size_t n, int index_bytes, unsigned k, void* out) {
+    mxx::comm c;
+    alphabet<char> a = alphabet<char>::from_sequence(text, text + n);
+    if (index_bytes == 4) {
+        std::vector<uint32_t> v = kmer_generation<uint32_t>(text, text + n, k, a, c);
+        std::memcpy(out, v.data(), n * 4);
+    } else {
+        std::vector<uint64_t> v = kmer_generation<uint64_t>(text, text + n, k, a, c);
+        std::memcpy(out, v.data(), n * 8);
+    }
+    return 0;
+}
+
+unsigned psacref_lcp_bitwise32(uint32_t x, uint32_t y, unsigned k, unsigned l) { return lcp_bitwise<uint32_t>(x, y, k, l); }
+unsigned psacref_lcp_bitwise64(uint64_t x, uint64_t y, unsigned k, unsigned l) { return lcp_bitwise<uint64_t>(x, y, k, l); }
+
+/* Kasai checker (lcp.hpp:46-77), 64-bit indices */
+int psacref_lcp_from_sa(const char* text, size_t n, const uint64_t* sa, const uint64_t* isa, uint64_t* lcp) {
+    std::string s(text, n);
+    std::vector<uint64_t> SA(sa, sa + n), ISA(isa, isa + n), LCP;
+    lcp_from_sa(s, SA, ISA, LCP);
+    std::memcpy(lcp, LCP.data(), n * 8);
+    return 0;
+}
+
+/* ansv_sequential (ansv.hpp:47-65) */
+int psacref_ansv_sequential(const uint64_t* in, size_t n, int left, uint64_t nonsv, uint64_t* out) {
+    std::vector<uint64_t> v(in, in + n);
+    std::vector<size_t> r = ansv_sequential(v, left != 0, (size_t)nonsv);
+    for (size_t i = 0; i < n; ++i) out[i] = r[i];
+    return 0;
+}
+
+/* ansv<T,left_type,right_type,global_indexing> at np=1 (ansv.hpp:2042-2045); modes: 0 nearest_sm, 1 nearest_eq, 2 furthest_eq */
+int psacref_ansv(const uint64_t* in, size_t n, int left_type, int right_type, uint64_t nonsv, uint64_t* left_out, uint64_t* right_out) {
+    cerr_mute mute(!g_verbose);
+    mxx::comm c;
+    std::vector<uint64_t> v(in, in + n);
+    std::vector<size_t> l, r;
+    std::vector<std::pair<uint64_t, size_t>> lr;
+#define PSACREF_ANSV_CASE(LT, RT) \
+    if (left_type == LT && right_type == RT) { ansv<uint64_t, LT, RT, global_indexing>(v, l, r, lr, c, (size_t)nonsv); }
+    PSACREF_ANSV_CASE(nearest_sm, nearest_sm) else PSACREF_ANSV_CASE(nearest_sm, nearest_eq) else PSACREF_ANSV_CASE(nearest_sm, furthest_eq)
+    else PSACREF_ANSV_CASE(nearest_eq, nearest_sm) else PSACREF_ANSV_CASE(nearest_eq, nearest_eq) else PSACREF_ANSV_CASE(nearest_eq, furthest_eq)
+    else PSACREF_ANSV_CASE(furthest_eq, nearest_sm) else PSACREF_ANSV_CASE(furthest_eq, nearest_eq) else PSACREF_ANSV_CASE(furthest_eq, furthest_eq)
+    else return -1;
+#undef PSACREF_ANSV_CASE
+    for (size_t i = 0; i < n; ++i) { left_out[i] = l[i]; right_out[i] = r[i]; }
+    return 0;
+}
+
+/* construct (u64, LCP) + construct_suffix_tree (suffix_tree.hpp:413-499) at np=1.
+ * nodes_out must hold (sigma+1)*n entries; returns sigma+1 (row width) or <0. */
+long psacref_suffix_tree(const char* text, size_t n, uint64_t* nodes_out, size_t nodes_cap) {
+    try {
+        cerr_mute mute(!g_verbose);
+        mxx::comm c;
+        suffix_array<char, size_t, true> sa(c);
+        sa.construct(text, text + n);
+        std::vector<size_t> nodes = construct_suffix_tree(sa, text, text + n, c);
+        if (nodes.size() > nodes_cap) return -2;
+        for (size_t i = 0; i < nodes.size(); ++i) nodes_out[i] = nodes[i];
+        return (long)(sa.alpha.sigma() + 1);
+    } catch (const std::exception& e) {
+        std::fprintf(stderr, "psacref_suffix_tree: %s\n", e.what());
+        return -10;
+    }
+}
+
+/* rand_dna(size, seed) exactly as the reference's tests generate inputs (alphabet.hpp:37-45; glibc rand) */
+int psacref_rand_dna(size_t n, int seed, char* out) {
+    std::string s = rand_dna(n, seed);
+    std::memcpy(out, s.data(), n);
+    return 0;
+}
+
+} // extern "C"
+
+namespace { struct env_holder { mxx::env e; }; env_holder* g_env = nullptr; }
+extern "C" void psacref_init() { if (!g_env) g_env = new env_holder(); }

@@ -1,0 +1,77 @@
+"""Deterministic synthetic texts for parity tests and the benchmark.
+
+A counter-based generator (splitmix64 of seed + block index), so any shard can generate
+its own block and the same bytes are reproducible on any machine -- the reference's own
+``rand_dna`` depends on glibc ``rand()`` (include/alphabet.hpp:32-45).
+"""
+import numpy as np
+
+_GOLDEN = np.uint64(0x9E3779B97F4A7C15)
+_M1 = np.uint64(0xBF58476D1CE4E5B9)
+_M2 = np.uint64(0x94D049BB133111EB)
+
+
+def splitmix64(seed, idx):
+    """splitmix64 output for counters ``idx`` (uint64 array) and stream ``seed``."""
+    with np.errstate(over="ignore"):
+        z = (idx.astype(np.uint64) + np.uint64(1)) * _GOLDEN + np.uint64(seed) * _M1
+        z = (z ^ (z >> np.uint64(30))) * _M1
+        z = (z ^ (z >> np.uint64(27))) * _M2
+        z = z ^ (z >> np.uint64(31))
+    return z
+
+
+def random_bytes(n, seed, start=0, chunk=1 << 24):
+    """n uniform bytes: byte i = byte (i % 8) of splitmix64(seed, i // 8)."""
+    out = np.empty(n, np.uint8)
+    pos = 0
+    while pos < n:
+        m = min(chunk, n - pos)
+        g0 = start + pos
+        w0 = g0 // 8
+        w1 = (g0 + m + 7) // 8
+        words = splitmix64(seed, np.arange(w0, w1, dtype=np.uint64))
+        b = words.view(np.uint8)  # little-endian host
+        off = g0 - w0 * 8
+        out[pos:pos + m] = b[off:off + m]
+        pos += m
+    return out
+
+
+def random_dna(n, seed, start=0, chunk=1 << 24):
+    """n uniform characters over ACGT: char i = "ACGT"[(splitmix64(seed, i // 32) >> 2*(i % 32)) & 3]."""
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    out = np.empty(n, np.uint8)
+    pos = 0
+    shifts = (np.arange(32, dtype=np.uint64) * np.uint64(2))[None, :]
+    while pos < n:
+        m = min(chunk, n - pos)
+        g0 = start + pos
+        w0 = g0 // 32
+        w1 = (g0 + m + 31) // 32
+        words = splitmix64(seed, np.arange(w0, w1, dtype=np.uint64))
+        codes = ((words[:, None] >> shifts) & np.uint64(3)).astype(np.uint8).reshape(-1)
+        off = g0 - w0 * 32
+        out[pos:pos + m] = acgt[codes[off:off + m]]
+        pos += m
+    return out
+
+
+def random_bytes_config4(n, seed):
+    """BASELINE config 4 text: uniform bytes with the last byte forced != 0xFF."""
+    t = random_bytes(n, seed)
+    if n and t[-1] == 0xFF:
+        t[-1] = 0xFE
+    return t
+
+
+def repeats_text(nwords, seed):
+    """Highly repetitive text in the spirit of test/test_psac.cpp:178-190 (own PRNG instead of std::rand)."""
+    words = [b"helloworld", b"blahlablah", b"ellow", b"worldblah", b"rld", b"hello"]
+    pick = splitmix64(seed, np.arange(nwords, dtype=np.uint64)) % np.uint64(len(words))
+    return np.frombuffer(b"".join(words[int(i)] for i in pick), np.uint8).copy()
+
+
+def periodic_text(unit, reps):
+    """(unit)^reps, e.g. (abc)^n of test/test_suffixtree.cpp:131-162."""
+    return np.frombuffer(bytes(unit) * reps, np.uint8).copy()

@@ -1,0 +1,195 @@
+"""Pins the CPU oracle (oracle/psac_oracle.c) before anything is compared against it.
+
+Sources of truth, in order: the reference's own golden vectors / KATs,
+fixtures generated from the unmodified reference (tests/golden/, make_golden.py), and -- where
+oracle/_ref/libpsacref.so exists -- the unmodified reference itself run here at np=1.
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as O
+from psac_b200 import textgen as G
+
+NONE = 0
+
+
+def test_mississippi_golden_sa():
+    # test/test_psac.cpp:105, README.md:85-101
+    exp = np.array([10, 7, 4, 1, 0, 9, 8, 6, 3, 5, 2], np.uint64)
+    for bits in (32, 64):
+        r = O.construct(b"mississippi", bits, 0, True)
+        assert r["rc"] == 0
+        assert (r["sa"] == exp).all()
+        assert (r["sa"][r["isa"].astype(np.int64)] == np.arange(11)).all()
+    assert (O.sa_naive(b"mississippi") == exp).all()
+
+
+def test_lcp_bitwise_kats():
+    # test/test_bitops.cpp:76-83
+    kats = [
+        (0xFECF0123, 0xFECDCCCE, 16, 2, 32, 7),
+        (0x01234567, 0x01234566, 10, 3, 32, 9),
+        (0x00001234, 0x00002234, 4, 4, 32, 0),
+        (0xBEEFBEEFBEEFADAD, 0xBEEFBEEFBEACADAD, 21, 3, 64, 13),
+        (0xBEEFBEEFBEEFADAD, 0xBEEFBEEFBEEFADAD, 21, 3, 64, 21),
+        (0x8EEFBEEFBEEFADAD, 0xBEEFBEEFBEEFADAD, 21, 3, 64, 0),
+    ]
+    for x, y, k, l, wb, exp in kats:
+        assert O.lcp_bitwise(x, y, k, l, wb) == exp
+
+
+def test_alphabet_lut_and_overflow():
+    lut, sigma, l = O.alphabet(b"mississippi")
+    assert sigma == 4 and l == 3
+    assert [lut[c] for c in b"imps"] == [1, 2, 3, 4]
+    # all 256 byte values: 0xFF would get code 256 -> wraps to 0 in the uint8 table (alphabet.hpp:136,160)
+    lut, sigma, l = O.alphabet(np.arange(256, dtype=np.uint8))
+    assert sigma == 256 and l == 9
+    assert lut[0xFF] == 0 and lut[0] == 1 and lut[0xFE] == 255
+
+
+def test_optimal_k():
+    # kmer.hpp:25-40 with alphabet.hpp:254-262
+    assert O.optimal_k(3, 32, 1 << 20) == 10
+    assert O.optimal_k(3, 64, 1 << 20) == 21
+    assert O.optimal_k(9, 32, 1 << 20) == 3
+    assert O.optimal_k(9, 64, 1 << 20) == 7
+    assert O.optimal_k(3, 64, 11) == 10  # k >= n -> n, then -1 at p == 1
+    assert O.optimal_k(3, 64, 1 << 20, k=3) == 3
+    assert O.optimal_k(3, 64, 1 << 20, k=99) == 21
+    assert O.optimal_k(3, 64, 5, p=4) == 5
+
+
+def _golden_cases(golden_dir):
+    for f in sorted(glob.glob(os.path.join(golden_dir, "*.npz"))):
+        d = np.load(f)
+        if "sa" in d.files:
+            yield os.path.basename(f), d
+
+
+def test_port_matches_golden_fixtures(golden_dir):
+    n_cases = 0
+    for name, d in _golden_cases(golden_dir):
+        text = d["text"]
+        ib = int(d["index_bytes"])
+        want_lcp = "lcp" in d.files
+        r = O.construct(text, ib * 8, int(d["k"]), want_lcp)
+        assert (r["sa"] == d["sa"].astype(np.uint64)).all(), name
+        assert (r["isa"] == d["isa"].astype(np.uint64)).all(), name
+        if want_lcp:
+            assert (r["lcp"] == d["lcp"].astype(np.uint64)).all(), name
+        # independent definitions
+        assert (O.sa_naive(text) == r["sa"]).all(), name
+        assert O.check_sa(text, r["sa"], r["isa"]) == 0, name
+        if want_lcp and text.size > 2:
+            assert (O.lcp_from_sa(text, r["sa"], r["isa"]) == r["lcp"]).all(), name
+        n_cases += 1
+    assert n_cases >= 14
+
+
+def test_port_kmers_match_golden(golden_dir):
+    d = np.load(os.path.join(golden_dir, "kmers_dna300.npz"))
+    text = d["text"]
+    lut, sigma, l = O.alphabet(text)
+    assert (sigma, l) == (4, 3)
+    assert (O.kmer_generation(text, lut, l, 10, 32) == d["k10_u32"]).all()
+    assert (O.kmer_generation(text, lut, l, 21, 64) == d["k21_u64"]).all()
+    assert (O.kmer_generation(text, lut, l, 3, 32) == d["k3_u32"]).all()
+    assert (O.kmer_generation(text, lut, l, 1, 64) == d["k1_u64"]).all()
+
+
+def test_construct_arr_port(golden_dir):
+    d = np.load(os.path.join(golden_dir, "dna4096_u32.npz"))
+    for L in (2, 3, 4):
+        r = O.construct_arr(d["text"], L, 32)
+        assert r["rc"] == 0
+        assert (r["sa"] == d["sa"]).all() and (r["isa"] == d["isa"]).all()
+
+
+def test_phase_functions_compose_to_construct():
+    """The per-phase oracle functions (used to check individual kernels) reproduce construct()."""
+    text = G.random_dna(3000, 5)
+    lut, sigma, l = O.alphabet(text)
+    k = O.optimal_k(l, 32, text.size, 1, 3)
+    b = O.kmer_generation(text, lut, l, k, 32)
+    n = text.size
+    h = k
+    lcp = None
+    while h < n:
+        b2 = O.shift(b, h)
+        b1s, b2s, sa = O.idxsort(b, b2)
+        lcp = O.initial_kmer_lcp(b1s, b2s, k, l, 32) if h == k else O.resolve_next_lcp(b1s, b2s, h, lcp)
+        ids, ub, ue = O.rebucket(b1s, b2s)
+        b = O.bulk_permute(ids, sa)
+        h *= 2
+        if ub == 0:
+            break
+    full = O.construct(text, 32, 3, True)
+    assert (sa == full["sa"]).all() and (b - 1 == full["isa"]).all() and (lcp == full["lcp"]).all()
+
+
+def test_check_sa_rejects_wrong_arrays():
+    text = G.random_dna(500, 9)
+    r = O.construct(text, 64)
+    assert O.check_sa(text, r["sa"], r["isa"]) == 0
+    bad = r["sa"].copy()
+    bad[[10, 11]] = bad[[11, 10]]
+    bad_isa = np.empty_like(bad)
+    bad_isa[bad.astype(np.int64)] = np.arange(bad.size, dtype=np.uint64)
+    assert O.check_sa(text, bad, bad_isa) != 0
+    assert O.check_sa(text, r["sa"], np.roll(r["isa"], 1)) != 0
+
+
+def test_ansv_port_matches_golden(golden_dir):
+    d = np.load(os.path.join(golden_dir, "ansv137.npz"))
+    vals = d["vals"]
+    nonsv = 2 ** 64 - 1
+    for lt in range(3):
+        for rt in range(3):
+            l, r = O.ansv(vals, lt, rt, nonsv)
+            assert (l == d["l_%d_%d" % (lt, rt)]).all(), (lt, rt)
+            assert (r == d["r_%d_%d" % (lt, rt)]).all(), (lt, rt)
+    assert (O.ansv_sequential(vals, True, nonsv) == d["l_0_0"]).all()
+    assert (O.ansv_sequential(vals, False, nonsv) == d["r_0_0"]).all()
+
+
+def test_suffix_tree_golden_vector(golden_dir):
+    # test/test_suffixtree.cpp:66-79 (55-entry child table of "mississippi"); the fixture was produced by
+    # the unmodified reference and must equal the literal from the reference's test.
+    solution = [0, 1, 15, 6, 9, 11, NONE, NONE, 12, 3, NONE, NONE, NONE, NONE, NONE, NONE, NONE, NONE, 13, 14,
+                NONE, NONE, NONE, NONE, NONE, NONE, NONE, NONE, NONE, NONE, NONE, 16, NONE, 17, NONE,
+                NONE, NONE, NONE, NONE, NONE, NONE, NONE, NONE, 18, 19, NONE, 8, NONE, NONE, 10,
+                NONE, NONE, NONE, 20, 21]
+    d = np.load(os.path.join(golden_dir, "stree_mississippi.npz"))
+    assert d["nodes"].reshape(-1).tolist() == solution
+
+
+@pytest.mark.skipif(not O.have_ref(), reason="oracle/_ref not built (needs /root/reference)")
+def test_port_matches_live_reference():
+    cases = [
+        (G.random_dna(130370, 7), 4, False, 0),     # RandAll shape, test_psac.cpp:131-176
+        (G.random_dna(130370, 7), 4, False, 3),
+        (G.random_dna(66763, 23), 8, True, 0),      # Lcp1 shape, test_psac.cpp:250-274
+        (G.random_dna(66763, 23), 8, True, 3),
+        (G.repeats_text(15000, 1), 8, True, 0),     # RepeatsAll shape, test_psac.cpp:178-224
+        (G.periodic_text(b"abc", 14681), 8, True, 0),
+        (G.random_bytes_config4(200000, 4), 8, False, 0),
+        (O.ref_rand_dna(9, 13), 4, False, 0),       # SmallStrings, test_psac.cpp:226-248
+    ]
+    for text, ib, want_lcp, k in cases:
+        ref = O.ref_construct(text, ib, want_lcp, k, True)
+        r = O.construct(text, ib * 8, k, want_lcp)
+        assert (r["sa"] == ref["sa"]).all() and (r["isa"] == ref["isa"]).all()
+        if want_lcp:
+            assert (r["lcp"] == ref["lcp"]).all()
+    lut_p = O.alphabet(G.random_bytes(5000, 1))
+    lut_r = O.ref_alphabet(G.random_bytes(5000, 1))
+    assert (lut_p[0] == lut_r[0]).all() and lut_p[1:] == lut_r[1:]
+    for L in (2, 3, 4):
+        text = G.random_dna(20000, 3)
+        ref = O.ref_construct(text, 4, False, 0, L != 4, L)
+        r = O.construct_arr(text, L, 32)
+        assert (r["sa"] == ref["sa"]).all() and (r["isa"] == ref["isa"]).all()
