@@ -1,0 +1,102 @@
+/*
+ * psacb200 -- C ABI of the B200-native suffix-array / LCP construction engine.
+ *
+ * Drop-in boundary for ONE path of patflick/psac: suffix_array<char_t,index_t,_LCP>::construct() /
+ * construct_arr<L>() (reference include/suffix_array.hpp:365-486, 490-641).  The reference has no FFI for this
+ * path (it is a header-only class template); these are the entry points a C++/cgo/ctypes binding of that class
+ * would bind, see INTEGRATION.md.  Plain pointers and sizes only; every function returns 0 on success or a
+ * negative psacb200_status, and psacb200_last_error() gives the message (the C++ shim in
+ * include/psacb200/suffix_array.hpp rethrows it as std::runtime_error like the reference, suffix_array.hpp:226).
+ *
+ * There is NO CPU fallback: every entry point fails with PSACB200_ERR_CUDA when no sm_100a device is usable.
+ */
+#ifndef PSACB200_H
+#define PSACB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct psacb200_engine psacb200_engine;
+
+enum psacb200_status {
+    PSACB200_OK = 0,
+    PSACB200_ERR_ARG = -1,   /* bad argument (index width too small for n, null pointer, ...) */
+    PSACB200_ERR_CUDA = -2,  /* CUDA runtime failure, including "no device" */
+    PSACB200_ERR_OOM = -3,   /* device memory exhausted */
+    PSACB200_ERR_INTERNAL = -4
+};
+
+/* flags of psacb200_construct* */
+enum {
+    PSACB200_LCP = 1u,          /* also build the LCP array (template parameter _CONSTRUCT_LCP, suffix_array.hpp:170) */
+    PSACB200_FAST_RESOLVAL = 2u /* reference's fast_resolval argument (suffix_array.hpp:470); accepted for signature
+                                   parity -- the engine always restricts later rounds to unresolved buckets */
+};
+
+/* Per-call statistics (the reference prints these as TIMER / "unfinished buckets" lines, suffix_array.hpp:52-63, 415). */
+typedef struct psacb200_stats {
+    uint64_t n;
+    uint32_t sigma;           /* distinct characters */
+    uint32_t bits_per_char;   /* reference's l = ceil(log2(sigma+1)), alphabet.hpp:153 */
+    uint32_t pack_bits;       /* bits per character in the engine's packed text */
+    uint32_t key_chars;       /* characters in the first sort key */
+    uint32_t rounds;          /* sorting rounds executed (1 = the first sort resolved everything) */
+    uint32_t sort_passes;     /* radix digit passes of the first sort */
+    uint32_t internal_index_bytes;
+    uint32_t reserved;
+    uint64_t unresolved_after_first; /* suffixes still sharing a bucket after the first sort */
+    uint64_t device_bytes;    /* device memory held by the engine */
+    float ms_total;           /* device time of the whole call (CUDA events) */
+    float ms_h2d, ms_alphabet, ms_pack, ms_keygen, ms_hist, ms_sort, ms_resolve, ms_rounds, ms_output, ms_d2h;
+    float ms_sort_pass_avg;   /* average duration of one radix digit pass of the first sort */
+    float reserved_f[3];
+} psacb200_stats;
+
+/* ---- lifetime ---------------------------------------------------------------------------------------------- */
+/* One engine = one GPU (cudaSetDevice(device)) + one stream + reusable device buffers.  Not thread-safe per engine. */
+int psacb200_create(int device, psacb200_engine** out);
+void psacb200_destroy(psacb200_engine* e);
+const char* psacb200_last_error(void);
+/* Number of CUDA kernel launches issued by this engine since creation (bench.py's gpu_launches). */
+uint64_t psacb200_launch_count(const psacb200_engine* e);
+int psacb200_get_stats(const psacb200_engine* e, psacb200_stats* out);
+/* Pre-size the device buffers for texts up to n characters (optional; avoids cudaMalloc inside a timed call). */
+int psacb200_reserve(psacb200_engine* e, size_t n, int index_bytes, unsigned flags);
+
+/* ---- alphabet (reference alphabet<char>::from_sequence, include/alphabet.hpp:147-164, 213-218) --------------- */
+/* lut[c] = 1 + rank of byte c among the bytes that occur, truncated to 8 bits exactly like the reference
+ * (0xFF wraps to 0 when all 256 values occur).  text is a HOST pointer. */
+int psacb200_alphabet(psacb200_engine* e, const uint8_t* text, size_t n, uint8_t lut[256], uint32_t* sigma, uint32_t* bits_per_char);
+
+/* ---- construct (reference suffix_array::construct, include/suffix_array.hpp:469-486) ------------------------- */
+/* HOST buffers in and out.  index_bytes = sizeof(index_t) (4 or 8).  sa_out / isa_out: n elements each, 0-based
+ * (the reference's local_SA / local_B at p = 1); lcp_out: n elements, LCP[0] = 0, required iff flags & PSACB200_LCP.
+ * isa_out may be NULL.  k = reference's k argument (0 = automatic).  Equivalent to construct_arr<L> for SA/ISA
+ * (suffix_array.hpp:490-641 produces the same final arrays). */
+int psacb200_construct(psacb200_engine* e, const uint8_t* text, size_t n, int index_bytes, unsigned flags, unsigned k, void* sa_out,
+                       void* isa_out, void* lcp_out);
+/* Same with the alphabet supplied by the caller (reference overload suffix_array.hpp:365-366).  lut = 256 codes as
+ * produced by psacb200_alphabet; only their ORDER matters. */
+int psacb200_construct_alphabet(psacb200_engine* e, const uint8_t* text, size_t n, int index_bytes, unsigned flags, unsigned k,
+                                const uint8_t lut[256], void* sa_out, void* isa_out, void* lcp_out);
+/* DEVICE buffers in and out (text already resident in HBM; outputs stay there). */
+int psacb200_construct_device(psacb200_engine* e, const uint8_t* d_text, size_t n, int index_bytes, unsigned flags, unsigned k, void* d_sa,
+                              void* d_isa, void* d_lcp);
+
+/* ---- building blocks on DEVICE pointers (used by the parity tests and by the sharded multi-GPU driver) ------ */
+/* Stable LSD radix sort of n (key, value) pairs by key bits [begin_bit, end_bit); key_bytes in {4,8}, val_bytes in
+ * {0,4,8}.  Sorted data is returned in keys/vals (keys_alt/vals_alt are scratch of the same size).
+ * Replaces idxsort_vectors -> mxx::sort (include/idxsort.hpp:22-83). */
+int psacb200_sort_pairs(psacb200_engine* e, void* d_keys, void* d_keys_alt, void* d_vals, void* d_vals_alt, size_t n, int key_bytes,
+                        int val_bytes, int begin_bit, int end_bit);
+/* Host-buffer wrapper of the above for tests. */
+int psacb200_sort_pairs_host(psacb200_engine* e, void* keys, void* vals, size_t n, int key_bytes, int val_bytes, int begin_bit, int end_bit);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PSACB200_H */

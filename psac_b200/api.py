@@ -1,0 +1,217 @@
+"""ctypes binding of the psacb200 C ABI (include/psacb200.h) and a Python mirror of the reference class.
+
+``SuffixArray`` mirrors ``suffix_array<char_t, index_t, _CONSTRUCT_LCP>`` of the reference
+(include/suffix_array.hpp:170-213): same method names (``construct``, ``construct_arr``), same argument meaning
+(``fast_resolval``, ``k``) and the same post-conditions (``n``, ``local_size``, ``local_SA``, ``local_B`` = ISA,
+``local_LCP``), at p = 1.  There is no CPU fallback: if the CUDA library or a GPU is missing every call raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libpsacb200.so")
+
+LCP = 1
+FAST_RESOLVAL = 2
+
+_lib = None
+
+
+class PsacError(RuntimeError):
+    """Mirrors the reference's std::runtime_error (suffix_array.hpp:226-227)."""
+
+
+class Stats(C.Structure):
+    _fields_ = [
+        ("n", C.c_uint64),
+        ("sigma", C.c_uint32),
+        ("bits_per_char", C.c_uint32),
+        ("pack_bits", C.c_uint32),
+        ("key_chars", C.c_uint32),
+        ("rounds", C.c_uint32),
+        ("sort_passes", C.c_uint32),
+        ("internal_index_bytes", C.c_uint32),
+        ("reserved", C.c_uint32),
+        ("unresolved_after_first", C.c_uint64),
+        ("device_bytes", C.c_uint64),
+        ("ms_total", C.c_float),
+        ("ms_h2d", C.c_float),
+        ("ms_alphabet", C.c_float),
+        ("ms_pack", C.c_float),
+        ("ms_keygen", C.c_float),
+        ("ms_hist", C.c_float),
+        ("ms_sort", C.c_float),
+        ("ms_resolve", C.c_float),
+        ("ms_rounds", C.c_float),
+        ("ms_output", C.c_float),
+        ("ms_d2h", C.c_float),
+        ("ms_sort_pass_avg", C.c_float),
+        ("reserved_f", C.c_float * 3),
+    ]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_ if not k.startswith("reserved")}
+
+
+def lib():
+    """Load libpsacb200.so (built in-tree by ``make`` / ``__graft_entry__.build``).  Raises if it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise PsacError("psac_b200/libpsacb200.so is missing: run `make` (or __graft_entry__.build()); there is no CPU fallback")
+        L = C.CDLL(LIB_PATH)
+        L.psacb200_last_error.restype = C.c_char_p
+        L.psacb200_launch_count.restype = C.c_uint64
+        L.psacb200_launch_count.argtypes = [C.c_void_p]
+        L.psacb200_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+        L.psacb200_destroy.argtypes = [C.c_void_p]
+        L.psacb200_destroy.restype = None
+        L.psacb200_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
+        L.psacb200_reserve.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_uint]
+        L.psacb200_alphabet.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+        cargs = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_uint, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.psacb200_construct.argtypes = cargs
+        L.psacb200_construct_device.argtypes = cargs
+        L.psacb200_construct_alphabet.argtypes = cargs[:6] + [C.c_void_p] + cargs[6:]
+        L.psacb200_sort_pairs.argtypes = [C.c_void_p] * 5 + [C.c_size_t] + [C.c_int] * 4
+        L.psacb200_sort_pairs_host.argtypes = [C.c_void_p] * 3 + [C.c_size_t] + [C.c_int] * 4
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise PsacError("psacb200 status %d: %s" % (rc, lib().psacb200_last_error().decode()))
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    return C.c_void_p(a.ctypes.data)
+
+
+class Engine:
+    """One GPU, one stream, reusable device buffers (psacb200_create / psacb200_destroy)."""
+
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        _check(lib().psacb200_create(int(device), C.byref(self._h)))
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            lib().psacb200_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launches(self):
+        return int(lib().psacb200_launch_count(self._h))
+
+    def stats(self):
+        s = Stats()
+        _check(lib().psacb200_get_stats(self._h, C.byref(s)))
+        return s.as_dict()
+
+    def reserve(self, n, index_bytes=4, flags=0):
+        _check(lib().psacb200_reserve(self._h, n, index_bytes, flags))
+
+    def alphabet(self, text):
+        t = _as_text(text)
+        lut = np.zeros(256, np.uint8)
+        sigma = C.c_uint32()
+        bpc = C.c_uint32()
+        _check(lib().psacb200_alphabet(self._h, _ptr(t), t.size, _ptr(lut), C.byref(sigma), C.byref(bpc)))
+        return lut, sigma.value, bpc.value
+
+    def construct(self, text, index_bytes=8, want_lcp=False, k=0, fast_resolval=True, want_isa=True, lut=None, out=None):
+        """Host buffers in, numpy arrays out: dict(sa, isa, lcp)."""
+        t = _as_text(text)
+        n = t.size
+        dt = np.uint32 if index_bytes == 4 else np.uint64
+        if out is None:
+            sa = np.empty(n, dt)
+            isa = np.empty(n, dt) if want_isa else None
+            lcp = np.empty(n, dt) if want_lcp else None
+        else:
+            sa, isa, lcp = out
+        flags = (LCP if want_lcp else 0) | (FAST_RESOLVAL if fast_resolval else 0)
+        if lut is None:
+            _check(lib().psacb200_construct(self._h, _ptr(t), n, index_bytes, flags, k, _ptr(sa), _ptr(isa), _ptr(lcp)))
+        else:
+            lut = np.ascontiguousarray(lut, np.uint8)
+            _check(lib().psacb200_construct_alphabet(self._h, _ptr(t), n, index_bytes, flags, k, _ptr(lut), _ptr(sa), _ptr(isa), _ptr(lcp)))
+        return dict(sa=sa, isa=isa, lcp=lcp)
+
+    def construct_ptr(self, text_ptr, n, index_bytes, flags, k, sa_ptr, isa_ptr, lcp_ptr, device=False):
+        """Raw-pointer form (pinned host buffers or device buffers owned by the caller, e.g. torch tensors)."""
+        f = lib().psacb200_construct_device if device else lib().psacb200_construct
+        _check(f(self._h, _ptr(text_ptr), n, index_bytes, flags, k, _ptr(sa_ptr), _ptr(isa_ptr), _ptr(lcp_ptr)))
+
+    def sort_pairs_host(self, keys, vals, begin_bit, end_bit):
+        """In-place stable radix sort of numpy keys (uint32/uint64) and optional values by key bits [begin_bit, end_bit)."""
+        assert keys.flags.c_contiguous and keys.dtype in (np.uint32, np.uint64)
+        vb = 0 if vals is None else vals.dtype.itemsize
+        _check(lib().psacb200_sort_pairs_host(self._h, _ptr(keys), _ptr(vals), keys.size, keys.dtype.itemsize, vb, begin_bit, end_bit))
+
+
+def _as_text(t):
+    if isinstance(t, (bytes, bytearray)):
+        t = np.frombuffer(bytes(t), dtype=np.uint8)
+    return np.ascontiguousarray(t, dtype=np.uint8)
+
+
+_default_engine = None
+
+
+def default_engine():
+    global _default_engine
+    if _default_engine is None:
+        _default_engine = Engine(int(os.environ.get("LOCAL_RANK", "0")))
+    return _default_engine
+
+
+class SuffixArray:
+    """Python mirror of ``suffix_array<char, index_t, _CONSTRUCT_LCP>`` at p = 1 (reference suffix_array.hpp:170-213)."""
+
+    def __init__(self, index_bytes=8, construct_lcp=False, engine=None):
+        self.index_bytes = index_bytes
+        self.construct_lcp = construct_lcp
+        self.engine = engine
+        self.n = 0
+        self.local_size = 0
+        self.p = 1
+        self.local_SA = None
+        self.local_B = None
+        self.local_LCP = None
+        self.alpha = None
+
+    def _eng(self):
+        return self.engine if self.engine is not None else default_engine()
+
+    def construct(self, text, fast_resolval=True, k=0):
+        """reference: construct(begin, end, fast_resolval = true, k = 0), suffix_array.hpp:469-486"""
+        t = _as_text(text)
+        r = self._eng().construct(t, self.index_bytes, self.construct_lcp, k, fast_resolval)
+        self.n = self.local_size = t.size
+        self.local_SA, self.local_B, self.local_LCP = r["sa"], r["isa"], r["lcp"]
+        return self
+
+    def construct_arr(self, text, L=2, fast_resolval=True):
+        """reference: construct_arr<L>(begin, end, fast_resolval), suffix_array.hpp:490-641 -- SA/ISA only, no LCP (:555-567)"""
+        if L < 2:
+            raise PsacError("construct_arr: L must be >= 2")
+        t = _as_text(text)
+        r = self._eng().construct(t, self.index_bytes, False, 0, fast_resolval)
+        self.n = self.local_size = t.size
+        self.local_SA, self.local_B, self.local_LCP = r["sa"], r["isa"], None
+        return self

@@ -1,0 +1,140 @@
+// psac-b200: shared device/host helpers for the sm_100a suffix-array engine.
+//
+// Everything on this path is unsigned-integer indexing work bounded by HBM bandwidth
+// (SURVEY.md section 8d): no tensor cores, no floating point.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+typedef uint8_t u8;
+typedef uint16_t u16;
+typedef uint32_t u32;
+typedef uint64_t u64;
+
+namespace psacb200 {
+
+// ---------------------------------------------------------------- error plumbing
+void set_last_error(const std::string& msg);
+
+struct cuda_failure {
+    cudaError_t err;
+    const char* what;
+    const char* file;
+    int line;
+};
+
+#define PSAC_CUDA(call)                                                            \
+    do {                                                                           \
+        cudaError_t _e = (call);                                                   \
+        if (_e != cudaSuccess) throw psacb200::cuda_failure{_e, #call, __FILE__, __LINE__}; \
+    } while (0)
+
+// ---------------------------------------------------------------- small device helpers
+__device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
+__device__ __forceinline__ unsigned lanemask_lt() {
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+// 64-bit entries shared between CTAs for the decoupled look-back: one aligned 8-byte word carries
+// payload + epoch + state, so a single relaxed load observes a consistent triple.
+__device__ __forceinline__ u64 ld_relaxed(const u64* p) {
+    u64 v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed(u64* p, u64 v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// streaming (evict-first) accessors for arrays that are touched exactly once per kernel
+template <typename T>
+__device__ __forceinline__ T ld_stream(const T* p) {
+    return __ldcs(p);
+}
+template <typename T>
+__device__ __forceinline__ void st_stream(T* p, T v) {
+    __stcs(p, v);
+}
+
+__host__ __device__ __forceinline__ unsigned bits_for(u64 x) {  // number of bits needed to store x (0 -> 0)
+    unsigned b = 0;
+    while (x) {
+        ++b;
+        x >>= 1;
+    }
+    return b;
+}
+
+static inline size_t div_up(size_t a, size_t b) { return (a + b - 1) / b; }
+static inline size_t align_up(size_t a, size_t b) { return div_up(a, b) * b; }
+
+// ---------------------------------------------------------------- decoupled look-back channel
+// One u64 per tile: [63:10] payload (54 bits), [9:2] epoch, [1:0] state.  The epoch makes entries of a
+// previous use of the same buffer read as "not yet written" without a memset between uses.
+enum : u64 { LB_NONE = 0, LB_AGGREGATE = 1, LB_INCLUSIVE = 2 };
+
+__device__ __forceinline__ u64 lb_pack(u64 payload, u32 epoch, u64 state) { return (payload << 10) | ((u64)(epoch & 0xffu) << 2) | state; }
+__device__ __forceinline__ u64 lb_payload(u64 w) { return w >> 10; }
+__device__ __forceinline__ u64 lb_state(u64 w, u32 epoch) { return (((w >> 2) & 0xffu) == (epoch & 0xffu)) ? (w & 3u) : (u64)LB_NONE; }
+
+struct OpSum {
+    __device__ __forceinline__ u64 operator()(u64 a, u64 b) const { return a + b; }
+    static __device__ __forceinline__ u64 identity() { return 0; }
+};
+struct OpMax {
+    __device__ __forceinline__ u64 operator()(u64 a, u64 b) const { return a > b ? a : b; }
+    static __device__ __forceinline__ u64 identity() { return 0; }
+};
+
+// Called by ONE thread per channel.  Publishes this tile's aggregate, walks back over the predecessors
+// until an inclusive prefix is found, publishes this tile's inclusive prefix and returns the EXCLUSIVE one.
+// Tiles must be numbered in launch order (dynamic tile ids) so every predecessor is already running.
+template <typename Op>
+__device__ __forceinline__ u64 lookback_exclusive(u64* chan, size_t stride, size_t tile, u64 aggregate, u32 epoch, Op op) {
+    if (tile == 0) {
+        st_relaxed(chan, lb_pack(aggregate, epoch, LB_INCLUSIVE));
+        return Op::identity();
+    }
+    st_relaxed(chan + tile * stride, lb_pack(aggregate, epoch, LB_AGGREGATE));
+    u64 excl = Op::identity();
+    size_t t = tile;
+    while (true) {
+        --t;
+        u64 w, st;
+        do {
+            w = ld_relaxed(chan + t * stride);
+            st = lb_state(w, epoch);
+        } while (st == LB_NONE);
+        excl = op(lb_payload(w), excl);
+        if (st == LB_INCLUSIVE) break;
+    }
+    st_relaxed(chan + tile * stride, lb_pack(op(excl, aggregate), epoch, LB_INCLUSIVE));
+    return excl;
+}
+
+// ---------------------------------------------------------------- warp scans (shuffle based)
+template <typename Op>
+__device__ __forceinline__ u64 warp_inclusive_scan(u64 v, Op op) {
+    unsigned lane = lane_id();
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        u64 o = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= (unsigned)d) v = op(o, v);
+    }
+    return v;
+}
+__device__ __forceinline__ u32 warp_inclusive_sum_u32(u32 v) {
+    unsigned lane = lane_id();
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        u32 o = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= (unsigned)d) v += o;
+    }
+    return v;
+}
+
+}  // namespace psacb200

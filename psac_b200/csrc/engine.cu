@@ -1,0 +1,669 @@
+// psac-b200: host orchestration of the suffix-array / LCP construction and the C ABI (include/psacb200.h).
+//
+// Path restated: suffix_array<char_t,index_t,_LCP>::construct (reference include/suffix_array.hpp:365-486) at p = 1.
+// Loop structure here (see sa_kernels.cuh for how each step maps to the reference's):
+//   alphabet -> pack text -> first key (C characters per suffix, one word) -> radix sort -> resolve (buckets, ISA,
+//   LCP, compaction of unresolved suffixes) -> while unresolved: keys (bucket, ISA[SA+h]) -> sort -> resolve; h *= 2.
+// Output SA / ISA / LCP are the unique arrays of the 0-padded suffix order, hence bit-identical to the reference's
+// (SURVEY.md section 0, items 1-2).
+#include <algorithm>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/psacb200.h"
+#include "radix_sort.cuh"
+#include "sa_kernels.cuh"
+
+using namespace psacb200;
+
+static_assert(sizeof(psacb200_stats) == 120, "psacb200_stats layout is mirrored by psac_b200/api.py");
+
+static thread_local std::string g_last_error;
+void psacb200::set_last_error(const std::string& msg) { g_last_error = msg; }
+
+namespace {
+
+struct oom_failure {
+    size_t bytes;
+};
+struct arg_failure {
+    std::string what;
+};
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    // grow-only; contents are NOT preserved across a growth
+    void reserve(size_t bytes, size_t* total) {
+        if (bytes <= cap) return;
+        if (p) {
+            cudaFree(p);
+            *total -= cap;
+            p = nullptr;
+            cap = 0;
+        }
+        bytes = align_up(bytes, 1 << 20);
+        cudaError_t err = cudaMalloc(&p, bytes);
+        if (err != cudaSuccess) {
+            cudaGetLastError();
+            p = nullptr;
+            throw oom_failure{bytes};
+        }
+        cap = bytes;
+        *total += bytes;
+    }
+    void release(size_t* total) {
+        if (p) cudaFree(p);
+        if (total) *total -= cap;
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T>
+    T* as() const {
+        return reinterpret_cast<T*>(p);
+    }
+};
+
+enum Phase { PH_H2D, PH_ALPHABET, PH_PACK, PH_KEYGEN, PH_HIST, PH_SORT, PH_RESOLVE, PH_ROUNDS, PH_OUTPUT, PH_D2H, PH_TOTAL, PH_COUNT };
+
+}  // namespace
+
+struct psacb200_engine {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    size_t device_bytes = 0;
+    uint64_t launches = 0;
+    DevBuf text, packed, keys[2], vals[2], isa, lcp, small, lookback, rk[2], rv[2], rp[2], rh[2], scratch;
+    u64* h_pinned = nullptr;  // 512 u64 of pinned host memory for small read-backs
+    cudaEvent_t ev_begin[PH_COUNT], ev_end[PH_COUNT];
+    bool ev_used[PH_COUNT];
+    psacb200_stats stats;
+
+    // layout of `small`
+    u64* ghist() const { return small.as<u64>(); }
+    u64* gbase() const { return small.as<u64>() + MAX_PASSES * RADIX; }
+    u64* byte_hist() const { return small.as<u64>() + 2 * MAX_PASSES * RADIX; }
+    u64* counts() const { return byte_hist() + 256; }
+    u32* counters() const { return reinterpret_cast<u32*>(counts() + 8); }
+    static size_t small_bytes() { return (2 * MAX_PASSES * RADIX + 256 + 8) * sizeof(u64) + 64 * sizeof(u32); }
+
+    RadixWorkspace radix_ws() const {
+        RadixWorkspace ws;
+        ws.ghist = ghist();
+        ws.gbase = gbase();
+        ws.counters = counters();
+        ws.lookback = lookback.as<u64>();
+        ws.lookback_bytes = lookback.cap;
+        return ws;
+    }
+    void begin(Phase p) {
+        cudaEventRecord(ev_begin[p], stream);
+        ev_used[p] = true;
+    }
+    void end(Phase p) { cudaEventRecord(ev_end[p], stream); }
+    float ms(Phase p) {
+        if (!ev_used[p]) return 0.f;
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, ev_begin[p], ev_end[p]) != cudaSuccess) {
+            cudaGetLastError();
+            return 0.f;
+        }
+        return t;
+    }
+};
+
+namespace {
+
+int grid_for(const psacb200_engine* e, size_t work_items, int threads, int per_sm) {
+    size_t want = div_up(work_items ? work_items : 1, (size_t)threads);
+    size_t cap = (size_t)e->sm_count * per_sm;
+    return (int)(want < cap ? want : cap);
+}
+
+struct Alphabet {
+    uint8_t lut[256];   // reference mapping table (alphabet.hpp:157-164)
+    CodeTable dense;    // order-preserving dense codes 0..D-1 used by the packed text
+    unsigned sigma = 0;
+    unsigned ref_bits = 0;
+    int lbits = 1;
+};
+
+// reference alphabet<char>::init_mapping_table: codes 1..sigma in byte order, stored in an 8-bit table
+void alphabet_from_hist(const u64* hist, Alphabet& a) {
+    uint16_t mapped = 1;
+    a.sigma = 0;
+    for (int c = 0; c < 256; ++c) {
+        a.lut[c] = 0;
+        if (hist[c]) {
+            a.lut[c] = (uint8_t)mapped;  // uchar truncation: 256 -> 0 when every byte value occurs
+            ++mapped;
+            ++a.sigma;
+        }
+    }
+    a.ref_bits = 0;
+    while ((1u << a.ref_bits) < a.sigma + 1) ++a.ref_bits;
+}
+
+// dense, order-preserving codes of the characters that occur (order = order of their lut codes)
+void dense_codes(const u64* hist, Alphabet& a) {
+    bool used[256] = {false};
+    for (int c = 0; c < 256; ++c)
+        if (hist[c]) used[a.lut[c]] = true;
+    int rank[256];
+    int d = 0;
+    for (int v = 0; v < 256; ++v) rank[v] = used[v] ? d++ : 0;
+    for (int c = 0; c < 256; ++c) a.dense.code[c] = hist[c] ? (u8)rank[a.lut[c]] : 0;
+    a.lbits = d <= 2 ? 1 : d <= 4 ? 2 : d <= 16 ? 4 : 8;
+}
+
+template <typename IdxT>
+void launch_resolve(psacb200_engine* e, bool first, const ResolveArgs& A) {
+    const u64 ntiles = div_up(A.m, (size_t)RES_TILE);
+    PSAC_CUDA(cudaMemsetAsync(A.lb_max, 0, 2 * ntiles * sizeof(u64), e->stream));  // lb_sum follows lb_max
+    PSAC_CUDA(cudaMemsetAsync(A.counts, 0, 2 * sizeof(u64), e->stream));
+    PSAC_CUDA(cudaMemsetAsync(A.tile_counter, 0, sizeof(u32), e->stream));
+    if (first)
+        resolve_kernel<IdxT, true><<<(unsigned)ntiles, RES_THREADS, 0, e->stream>>>(A);
+    else
+        resolve_kernel<IdxT, false><<<(unsigned)ntiles, RES_THREADS, 0, e->stream>>>(A);
+    e->launches += 1;
+    PSAC_CUDA(cudaGetLastError());
+}
+
+void read_counts(psacb200_engine* e, u64* m, u64* nb) {
+    PSAC_CUDA(cudaMemcpyAsync(e->h_pinned, e->counts(), 2 * sizeof(u64), cudaMemcpyDeviceToHost, e->stream));
+    PSAC_CUDA(cudaStreamSynchronize(e->stream));
+    *m = e->h_pinned[0];
+    *nb = e->h_pinned[1];
+}
+
+template <typename SrcT>
+void emit(psacb200_engine* e, const SrcT* src, void* dst, u64 n, int index_bytes, bool dst_is_host) {
+    if (dst == nullptr) return;
+    if ((int)sizeof(SrcT) == index_bytes) {
+        PSAC_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(SrcT), dst_is_host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, e->stream));
+        return;
+    }
+    // widen / narrow on the device, then move
+    void* target = dst;
+    if (dst_is_host) {
+        e->scratch.reserve(n * (size_t)index_bytes, &e->device_bytes);
+        target = e->scratch.p;
+    }
+    const int grid = grid_for(e, n, 256, 16);
+    if (index_bytes == 8)
+        convert_kernel<SrcT, u64><<<grid, 256, 0, e->stream>>>(src, reinterpret_cast<u64*>(target), n);
+    else
+        convert_kernel<SrcT, u32><<<grid, 256, 0, e->stream>>>(src, reinterpret_cast<u32*>(target), n);
+    e->launches += 1;
+    PSAC_CUDA(cudaGetLastError());
+    if (dst_is_host) PSAC_CUDA(cudaMemcpyAsync(dst, target, n * (size_t)index_bytes, cudaMemcpyDeviceToHost, e->stream));
+}
+
+unsigned choose_key_chars(u64 n, int lbits, unsigned k) {
+    const unsigned maxC = 64u / (unsigned)lbits;
+    if (k != 0) {
+        // the reference's first sort key is (kmer_k[i], kmer_k[i+k]) = 2k characters (suffix_array.hpp:381-394)
+        u64 c = 2ull * k;
+        return (unsigned)std::max<u64>(1, std::min<u64>(c, maxC));
+    }
+    // enough characters that random text leaves well under 1 % of the suffixes unresolved, rounded so that every
+    // 8-bit digit pass is fully used
+    unsigned want = bits_for(n) + 8;
+    unsigned nbits = std::min(64u, (want + 7u) / 8u * 8u);
+    return std::max(1u, nbits / (unsigned)lbits);
+}
+
+template <typename IdxT>
+void reserve_buffers(psacb200_engine* e, u64 n, bool want_lcp) {
+    size_t* tot = &e->device_bytes;
+    e->small.reserve(psacb200_engine::small_bytes(), tot);
+    e->packed.reserve((n / 8 + 4) * sizeof(u64) + 64, tot);  // worst case 8 bits per character
+    for (int b = 0; b < 2; ++b) {
+        e->keys[b].reserve(n * sizeof(u64), tot);
+        e->vals[b].reserve(n * sizeof(IdxT), tot);
+    }
+    e->isa.reserve(n * sizeof(IdxT), tot);
+    if (want_lcp) e->lcp.reserve(n * sizeof(IdxT), tot);
+    size_t lb = std::max(RadixWorkspace::lookback_bytes_for<u64, IdxT>(n), (size_t)(2 * div_up(n, (size_t)RES_TILE) * sizeof(u64)));
+    e->lookback.reserve(lb, tot);
+}
+
+template <typename IdxT>
+void construct_core(psacb200_engine* e, const u8* d_text, u64 n, int index_bytes, unsigned flags, unsigned k, const uint8_t* user_lut, void* sa_out,
+                    void* isa_out, void* lcp_out, bool out_is_host) {
+    const bool want_lcp = (flags & PSACB200_LCP) != 0;
+    cudaStream_t st = e->stream;
+    psacb200_stats& S = e->stats;
+    S.internal_index_bytes = sizeof(IdxT);
+    reserve_buffers<IdxT>(e, n, want_lcp);
+
+    // ---- alphabet (a2)
+    e->begin(PH_ALPHABET);
+    PSAC_CUDA(cudaMemsetAsync(e->byte_hist(), 0, 256 * sizeof(u64), st));
+    byte_hist_kernel<<<grid_for(e, n / 16 + 1, 512, 4), 512, 0, st>>>(d_text, n, e->byte_hist());
+    e->launches += 1;
+    PSAC_CUDA(cudaGetLastError());
+    PSAC_CUDA(cudaMemcpyAsync(e->h_pinned + 16, e->byte_hist(), 256 * sizeof(u64), cudaMemcpyDeviceToHost, st));
+    e->end(PH_ALPHABET);
+    PSAC_CUDA(cudaStreamSynchronize(st));
+    Alphabet alpha;
+    alphabet_from_hist(e->h_pinned + 16, alpha);
+    if (user_lut) memcpy(alpha.lut, user_lut, 256);
+    dense_codes(e->h_pinned + 16, alpha);
+    S.sigma = alpha.sigma;
+    S.bits_per_char = alpha.ref_bits;
+    S.pack_bits = alpha.lbits;
+    const int lbits = alpha.lbits;
+
+    // ---- packed text
+    e->begin(PH_PACK);
+    const int cpw = 64 / lbits;
+    const size_t nwords = div_up(n, (size_t)cpw) + 2;
+    pack_text_kernel<<<grid_for(e, nwords, 256, 8), 256, 0, st>>>(d_text, n, alpha.dense, lbits, e->packed.as<u64>(), nwords);
+    e->launches += 1;
+    PSAC_CUDA(cudaGetLastError());
+    e->end(PH_PACK);
+
+    // ---- first key (a4) + sort (a6)
+    const unsigned C = choose_key_chars(n, lbits, k);
+    S.key_chars = C;
+    e->begin(PH_KEYGEN);
+    keygen_kernel<IdxT><<<grid_for(e, n, 256, 16), 256, 0, st>>>(e->packed.as<u64>(), n, lbits, (int)C, e->keys[0].as<u64>(), e->vals[0].as<IdxT>());
+    e->launches += 1;
+    PSAC_CUDA(cudaGetLastError());
+    e->end(PH_KEYGEN);
+
+    RadixPlan plan;
+    uint64_t sort_launches = 0;
+    e->begin(PH_HIST);
+    const bool in_alt = radix_sort_pairs<u64, IdxT>(e->radix_ws(), e->keys[0].as<u64>(), e->keys[1].as<u64>(), e->vals[0].as<IdxT>(),
+                                                   e->vals[1].as<IdxT>(), n, 0, (int)(C * lbits), st, e->sm_count, &plan, &sort_launches,
+                                                   e->ev_end[PH_HIST], e->ev_begin[PH_SORT]);
+    e->ev_used[PH_SORT] = true;
+    e->end(PH_SORT);
+    e->launches += sort_launches;
+    S.sort_passes = plan.npass;
+    const int x = in_alt ? 1 : 0, y = 1 - x;
+    IdxT* SA = e->vals[x].as<IdxT>();
+    IdxT* ISA = e->isa.as<IdxT>();
+    IdxT* LCP = want_lcp ? e->lcp.as<IdxT>() : nullptr;
+
+    // ---- resolve round 0 (a7, a9, a10)
+    e->begin(PH_RESOLVE);
+    ResolveArgs R{};
+    R.keys = e->keys[x].as<u64>();
+    R.vals = SA;
+    R.pos_in = nullptr;
+    R.m = n;
+    R.n = n;
+    R.sa = SA;
+    R.isa = ISA;
+    R.lcp = LCP;
+    R.pos_out = e->vals[y].p;
+    R.head_out = e->keys[y].as<u8>();
+    R.counts = e->counts();
+    R.lb_max = e->lookback.as<u64>();
+    R.lb_sum = R.lb_max + div_up(n, (size_t)RES_TILE);
+    R.tile_counter = e->counters() + 16;
+    R.stream = e->packed.as<u64>();
+    R.lbits = lbits;
+    R.C = (int)C;
+    R.kbits = 0;
+    R.h = 0;
+    launch_resolve<IdxT>(e, true, R);
+    e->end(PH_RESOLVE);
+    u64 m = 0, nb = 0;
+    read_counts(e, &m, &nb);
+    S.unresolved_after_first = m;
+    S.rounds = 1;
+
+    // ---- later rounds on the unresolved suffixes only (a5, a6, a8, a9, a10, a12)
+    if (m > 0) {
+        e->begin(PH_ROUNDS);
+        size_t* tot = &e->device_bytes;
+        for (int b = 0; b < 2; ++b) {
+            e->rk[b].reserve(m * sizeof(u64), tot);
+            e->rv[b].reserve(m * sizeof(IdxT), tot);
+            e->rp[b].reserve(m * sizeof(IdxT), tot);
+            e->rh[b].reserve(m, tot);
+        }
+        const void* pos_in = e->vals[y].p;
+        const u8* head_in = e->keys[y].as<u8>();
+        const int kbits = (int)bits_for(n);
+        u64 h = C;
+        int t = 0;
+        while (m > 0) {
+            const int mbits = (int)bits_for(m - 1);
+            if (kbits + mbits > 64) throw arg_failure{"text too repetitive for a 64-bit round key (n >= 2^32 with > 2^30 unresolved suffixes)"};
+            const u64 ntiles = div_up(m, (size_t)RES_TILE);
+            RoundKeyArgs K{};
+            K.pos = pos_in;
+            K.head = head_in;
+            K.sa = SA;
+            K.isa = ISA;
+            K.m = m;
+            K.n = n;
+            K.h = h;
+            K.kbits = kbits;
+            K.keys = e->rk[0].as<u64>();
+            K.vals = e->rv[0].p;
+            K.lb_max = e->lookback.as<u64>();
+            K.tile_counter = e->counters() + 17;
+            PSAC_CUDA(cudaMemsetAsync(K.lb_max, 0, ntiles * sizeof(u64), st));
+            PSAC_CUDA(cudaMemsetAsync(K.tile_counter, 0, sizeof(u32), st));
+            round_keys_kernel<IdxT><<<(unsigned)ntiles, RES_THREADS, 0, st>>>(K);
+            e->launches += 1;
+            PSAC_CUDA(cudaGetLastError());
+            uint64_t sl = 0;
+            const bool alt = radix_sort_pairs<u64, IdxT>(e->radix_ws(), e->rk[0].as<u64>(), e->rk[1].as<u64>(), e->rv[0].as<IdxT>(),
+                                                        e->rv[1].as<IdxT>(), m, 0, kbits + mbits, st, e->sm_count, nullptr, &sl);
+            e->launches += sl;
+            ResolveArgs Q = R;
+            Q.keys = e->rk[alt ? 1 : 0].as<u64>();
+            Q.vals = e->rv[alt ? 1 : 0].p;
+            Q.pos_in = pos_in;
+            Q.m = m;
+            Q.pos_out = e->rp[t].p;
+            Q.head_out = e->rh[t].as<u8>();
+            Q.lb_sum = Q.lb_max + ntiles;
+            Q.kbits = kbits;
+            Q.h = h;
+            launch_resolve<IdxT>(e, false, Q);
+            read_counts(e, &m, &nb);
+            pos_in = e->rp[t].p;
+            head_in = e->rh[t].as<u8>();
+            t ^= 1;
+            h *= 2;
+            S.rounds += 1;
+            if (h > 4 * n + 64 && m > 0) throw std::string("prefix doubling did not converge");
+        }
+        e->end(PH_ROUNDS);
+    }
+
+    // ---- outputs: SA and ISA (= final bucket ids, 0-based) and LCP in the caller's index width
+    e->begin(out_is_host ? PH_D2H : PH_OUTPUT);
+    emit<IdxT>(e, SA, sa_out, n, index_bytes, out_is_host);
+    emit<IdxT>(e, ISA, isa_out, n, index_bytes, out_is_host);
+    if (want_lcp) emit<IdxT>(e, LCP, lcp_out, n, index_bytes, out_is_host);
+    e->end(out_is_host ? PH_D2H : PH_OUTPUT);
+}
+
+int construct_entry(psacb200_engine* e, const u8* text, bool text_is_host, size_t n, int index_bytes, unsigned flags, unsigned k, const uint8_t* lut,
+                    void* sa_out, void* isa_out, void* lcp_out) {
+    if (!e) {
+        set_last_error("null engine");
+        return PSACB200_ERR_ARG;
+    }
+    try {
+        if (index_bytes != 4 && index_bytes != 8) throw arg_failure{"index_bytes must be 4 or 8"};
+        if (n > 0 && (!text || !sa_out)) throw arg_failure{"null text / sa_out"};
+        if ((flags & PSACB200_LCP) && n > 0 && !lcp_out) throw arg_failure{"PSACB200_LCP set but lcp_out is null"};
+        if (index_bytes == 4 && (u64)n >= (1ull << 32)) throw arg_failure{"32-bit index too small for this text (reference asserts the same)"};
+        if ((u64)n >= (1ull << 40)) throw arg_failure{"n too large"};
+        PSAC_CUDA(cudaSetDevice(e->device));
+        memset(&e->stats, 0, sizeof(e->stats));
+        memset(e->ev_used, 0, sizeof(e->ev_used));
+        e->stats.n = n;
+        if (n == 0) return PSACB200_OK;
+        e->begin(PH_TOTAL);
+        const u8* d_text = text;
+        if (text_is_host) {
+            e->begin(PH_H2D);
+            e->text.reserve(n + 64, &e->device_bytes);
+            PSAC_CUDA(cudaMemcpyAsync(e->text.p, text, n, cudaMemcpyHostToDevice, e->stream));
+            e->end(PH_H2D);
+            d_text = e->text.as<u8>();
+        }
+        if ((u64)n <= (1ull << 32))
+            construct_core<u32>(e, d_text, n, index_bytes, flags, k, lut, sa_out, isa_out, lcp_out, text_is_host);
+        else
+            construct_core<u64>(e, d_text, n, index_bytes, flags, k, lut, sa_out, isa_out, lcp_out, text_is_host);
+        e->end(PH_TOTAL);
+        PSAC_CUDA(cudaStreamSynchronize(e->stream));
+        psacb200_stats& S = e->stats;
+        S.device_bytes = e->device_bytes;
+        S.ms_total = e->ms(PH_TOTAL);
+        S.ms_h2d = e->ms(PH_H2D);
+        S.ms_alphabet = e->ms(PH_ALPHABET);
+        S.ms_pack = e->ms(PH_PACK);
+        S.ms_keygen = e->ms(PH_KEYGEN);
+        S.ms_hist = e->ms(PH_HIST);
+        S.ms_sort = e->ms(PH_SORT);
+        S.ms_resolve = e->ms(PH_RESOLVE);
+        S.ms_rounds = e->ms(PH_ROUNDS);
+        S.ms_output = e->ms(PH_OUTPUT);
+        S.ms_d2h = e->ms(PH_D2H);
+        S.ms_sort_pass_avg = S.sort_passes ? S.ms_sort / (float)S.sort_passes : 0.f;
+        return PSACB200_OK;
+    } catch (const cuda_failure& f) {
+        set_last_error(std::string("CUDA error: ") + cudaGetErrorString(f.err) + " in " + f.what + " at " + f.file + ":" + std::to_string(f.line));
+        cudaGetLastError();
+        return PSACB200_ERR_CUDA;
+    } catch (const oom_failure& f) {
+        set_last_error("out of device memory allocating " + std::to_string(f.bytes) + " bytes");
+        return PSACB200_ERR_OOM;
+    } catch (const arg_failure& f) {
+        set_last_error(f.what);
+        return PSACB200_ERR_ARG;
+    } catch (const std::string& s) {
+        set_last_error(s);
+        return PSACB200_ERR_INTERNAL;
+    } catch (const std::bad_alloc&) {
+        set_last_error("host allocation failed");
+        return PSACB200_ERR_INTERNAL;
+    }
+}
+
+template <typename F>
+int guarded(F&& f) {
+    try {
+        return f();
+    } catch (const cuda_failure& x) {
+        set_last_error(std::string("CUDA error: ") + cudaGetErrorString(x.err) + " in " + x.what + " at " + x.file + ":" + std::to_string(x.line));
+        cudaGetLastError();
+        return PSACB200_ERR_CUDA;
+    } catch (const oom_failure& x) {
+        set_last_error("out of device memory allocating " + std::to_string(x.bytes) + " bytes");
+        return PSACB200_ERR_OOM;
+    } catch (const arg_failure& x) {
+        set_last_error(x.what);
+        return PSACB200_ERR_ARG;
+    } catch (const std::string& s) {
+        set_last_error(s);
+        return PSACB200_ERR_INTERNAL;
+    }
+}
+
+template <typename KeyT>
+bool sort_dispatch_val(psacb200_engine* e, void* k, void* ka, void* v, void* va, size_t n, int val_bytes, int b0, int b1, uint64_t* sl) {
+    RadixWorkspace ws = e->radix_ws();
+    if (val_bytes == 0)
+        return radix_sort_pairs<KeyT, NoVal>(ws, (KeyT*)k, (KeyT*)ka, (NoVal*)nullptr, (NoVal*)nullptr, n, b0, b1, e->stream, e->sm_count, nullptr, sl);
+    if (val_bytes == 4) return radix_sort_pairs<KeyT, u32>(ws, (KeyT*)k, (KeyT*)ka, (u32*)v, (u32*)va, n, b0, b1, e->stream, e->sm_count, nullptr, sl);
+    return radix_sort_pairs<KeyT, u64>(ws, (KeyT*)k, (KeyT*)ka, (u64*)v, (u64*)va, n, b0, b1, e->stream, e->sm_count, nullptr, sl);
+}
+
+}  // namespace
+
+// ================================================================================================ C ABI
+extern "C" {
+
+const char* psacb200_last_error(void) { return g_last_error.c_str(); }
+
+int psacb200_create(int device, psacb200_engine** out) {
+    if (!out) {
+        set_last_error("null out pointer");
+        return PSACB200_ERR_ARG;
+    }
+    *out = nullptr;
+    return guarded([&]() -> int {
+        int count = 0;
+        cudaError_t err = cudaGetDeviceCount(&count);
+        if (err != cudaSuccess || count == 0) {
+            cudaGetLastError();
+            set_last_error(std::string("no CUDA device available (") + cudaGetErrorString(err) + "); psacb200 has no CPU fallback");
+            return PSACB200_ERR_CUDA;
+        }
+        if (device < 0 || device >= count) throw arg_failure{"device ordinal out of range"};
+        PSAC_CUDA(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        PSAC_CUDA(cudaGetDeviceProperties(&prop, device));
+        if (prop.major < 10) throw arg_failure{std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) + "; this library is built for sm_100a only"};
+        psacb200_engine* e = new psacb200_engine();
+        e->device = device;
+        e->sm_count = prop.multiProcessorCount;
+        PSAC_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+        PSAC_CUDA(cudaMallocHost((void**)&e->h_pinned, 512 * sizeof(u64)));
+        for (int i = 0; i < PH_COUNT; ++i) {
+            PSAC_CUDA(cudaEventCreate(&e->ev_begin[i]));
+            PSAC_CUDA(cudaEventCreate(&e->ev_end[i]));
+            e->ev_used[i] = false;
+        }
+        memset(&e->stats, 0, sizeof(e->stats));
+        e->small.reserve(psacb200_engine::small_bytes(), &e->device_bytes);
+        *out = e;
+        return PSACB200_OK;
+    });
+}
+
+void psacb200_destroy(psacb200_engine* e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    cudaStreamSynchronize(e->stream);
+    DevBuf* all[] = {&e->text, &e->packed, &e->keys[0], &e->keys[1], &e->vals[0], &e->vals[1], &e->isa, &e->lcp, &e->small, &e->lookback,
+                     &e->rk[0], &e->rk[1], &e->rv[0], &e->rv[1], &e->rp[0], &e->rp[1], &e->rh[0], &e->rh[1], &e->scratch};
+    for (DevBuf* b : all) b->release(nullptr);
+    for (int i = 0; i < PH_COUNT; ++i) {
+        cudaEventDestroy(e->ev_begin[i]);
+        cudaEventDestroy(e->ev_end[i]);
+    }
+    if (e->h_pinned) cudaFreeHost(e->h_pinned);
+    cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+uint64_t psacb200_launch_count(const psacb200_engine* e) { return e ? e->launches : 0; }
+
+int psacb200_get_stats(const psacb200_engine* e, psacb200_stats* out) {
+    if (!e || !out) {
+        set_last_error("null argument");
+        return PSACB200_ERR_ARG;
+    }
+    *out = e->stats;
+    return PSACB200_OK;
+}
+
+int psacb200_reserve(psacb200_engine* e, size_t n, int index_bytes, unsigned flags) {
+    if (!e) {
+        set_last_error("null engine");
+        return PSACB200_ERR_ARG;
+    }
+    return guarded([&]() -> int {
+        PSAC_CUDA(cudaSetDevice(e->device));
+        const bool lcp = (flags & PSACB200_LCP) != 0;
+        if ((u64)n <= (1ull << 32))
+            reserve_buffers<u32>(e, n, lcp);
+        else
+            reserve_buffers<u64>(e, n, lcp);
+        e->text.reserve(n + 64, &e->device_bytes);
+        if ((u64)n <= (1ull << 32) && index_bytes == 8) e->scratch.reserve(n * 8, &e->device_bytes);
+        return PSACB200_OK;
+    });
+}
+
+int psacb200_alphabet(psacb200_engine* e, const uint8_t* text, size_t n, uint8_t lut[256], uint32_t* sigma, uint32_t* bits_per_char) {
+    if (!e || (!text && n) || !lut) {
+        set_last_error("null argument");
+        return PSACB200_ERR_ARG;
+    }
+    return guarded([&]() -> int {
+        PSAC_CUDA(cudaSetDevice(e->device));
+        e->text.reserve(n + 64, &e->device_bytes);
+        PSAC_CUDA(cudaMemcpyAsync(e->text.p, text, n, cudaMemcpyHostToDevice, e->stream));
+        PSAC_CUDA(cudaMemsetAsync(e->byte_hist(), 0, 256 * sizeof(u64), e->stream));
+        if (n) {
+            byte_hist_kernel<<<grid_for(e, n / 16 + 1, 512, 4), 512, 0, e->stream>>>(e->text.as<u8>(), n, e->byte_hist());
+            e->launches += 1;
+        }
+        PSAC_CUDA(cudaMemcpyAsync(e->h_pinned + 16, e->byte_hist(), 256 * sizeof(u64), cudaMemcpyDeviceToHost, e->stream));
+        PSAC_CUDA(cudaStreamSynchronize(e->stream));
+        Alphabet a;
+        alphabet_from_hist(e->h_pinned + 16, a);
+        memcpy(lut, a.lut, 256);
+        if (sigma) *sigma = a.sigma;
+        if (bits_per_char) *bits_per_char = a.ref_bits;
+        return PSACB200_OK;
+    });
+}
+
+int psacb200_construct(psacb200_engine* e, const uint8_t* text, size_t n, int index_bytes, unsigned flags, unsigned k, void* sa_out, void* isa_out,
+                       void* lcp_out) {
+    return construct_entry(e, text, true, n, index_bytes, flags, k, nullptr, sa_out, isa_out, lcp_out);
+}
+
+int psacb200_construct_alphabet(psacb200_engine* e, const uint8_t* text, size_t n, int index_bytes, unsigned flags, unsigned k, const uint8_t lut[256],
+                                void* sa_out, void* isa_out, void* lcp_out) {
+    return construct_entry(e, text, true, n, index_bytes, flags, k, lut, sa_out, isa_out, lcp_out);
+}
+
+int psacb200_construct_device(psacb200_engine* e, const uint8_t* d_text, size_t n, int index_bytes, unsigned flags, unsigned k, void* d_sa, void* d_isa,
+                              void* d_lcp) {
+    return construct_entry(e, d_text, false, n, index_bytes, flags, k, nullptr, d_sa, d_isa, d_lcp);
+}
+
+int psacb200_sort_pairs(psacb200_engine* e, void* d_keys, void* d_keys_alt, void* d_vals, void* d_vals_alt, size_t n, int key_bytes, int val_bytes,
+                        int begin_bit, int end_bit) {
+    if (!e) {
+        set_last_error("null engine");
+        return PSACB200_ERR_ARG;
+    }
+    return guarded([&]() -> int {
+        if ((key_bytes != 4 && key_bytes != 8) || (val_bytes != 0 && val_bytes != 4 && val_bytes != 8)) throw arg_failure{"unsupported key/value width"};
+        if (begin_bit < 0 || end_bit > key_bytes * 8 || begin_bit > end_bit) throw arg_failure{"bad bit range"};
+        PSAC_CUDA(cudaSetDevice(e->device));
+        e->lookback.reserve(div_up(n ? n : 1, (size_t)2048) * RADIX * sizeof(u64), &e->device_bytes);
+        uint64_t sl = 0;
+        bool alt = key_bytes == 8 ? sort_dispatch_val<u64>(e, d_keys, d_keys_alt, d_vals, d_vals_alt, n, val_bytes, begin_bit, end_bit, &sl)
+                                  : sort_dispatch_val<u32>(e, d_keys, d_keys_alt, d_vals, d_vals_alt, n, val_bytes, begin_bit, end_bit, &sl);
+        e->launches += sl;
+        if (alt) {
+            PSAC_CUDA(cudaMemcpyAsync(d_keys, d_keys_alt, n * (size_t)key_bytes, cudaMemcpyDeviceToDevice, e->stream));
+            if (val_bytes) PSAC_CUDA(cudaMemcpyAsync(d_vals, d_vals_alt, n * (size_t)val_bytes, cudaMemcpyDeviceToDevice, e->stream));
+        }
+        PSAC_CUDA(cudaStreamSynchronize(e->stream));
+        return PSACB200_OK;
+    });
+}
+
+int psacb200_sort_pairs_host(psacb200_engine* e, void* keys, void* vals, size_t n, int key_bytes, int val_bytes, int begin_bit, int end_bit) {
+    if (!e) {
+        set_last_error("null engine");
+        return PSACB200_ERR_ARG;
+    }
+    if (n == 0) return PSACB200_OK;
+    int rc = guarded([&]() -> int {
+        PSAC_CUDA(cudaSetDevice(e->device));
+        size_t* tot = &e->device_bytes;
+        e->rk[0].reserve(n * 8, tot);
+        e->rk[1].reserve(n * 8, tot);
+        e->rv[0].reserve(n * 8, tot);
+        e->rv[1].reserve(n * 8, tot);
+        PSAC_CUDA(cudaMemcpyAsync(e->rk[0].p, keys, n * (size_t)key_bytes, cudaMemcpyHostToDevice, e->stream));
+        if (val_bytes) PSAC_CUDA(cudaMemcpyAsync(e->rv[0].p, vals, n * (size_t)val_bytes, cudaMemcpyHostToDevice, e->stream));
+        return PSACB200_OK;
+    });
+    if (rc) return rc;
+    rc = psacb200_sort_pairs(e, e->rk[0].p, e->rk[1].p, e->rv[0].p, e->rv[1].p, n, key_bytes, val_bytes, begin_bit, end_bit);
+    if (rc) return rc;
+    return guarded([&]() -> int {
+        PSAC_CUDA(cudaMemcpyAsync(keys, e->rk[0].p, n * (size_t)key_bytes, cudaMemcpyDeviceToHost, e->stream));
+        if (val_bytes) PSAC_CUDA(cudaMemcpyAsync(vals, e->rv[0].p, n * (size_t)val_bytes, cudaMemcpyDeviceToHost, e->stream));
+        PSAC_CUDA(cudaStreamSynchronize(e->stream));
+        return PSACB200_OK;
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,392 @@
+// psac-b200: device kernels of the prefix-doubling loop other than the radix sort.
+//
+// Reference stages restated here as kernels:
+//   a2  alphabet histogram            include/alphabet.hpp:48-59          -> byte_hist_kernel
+//   a4  k-mer generation              include/kmer.hpp:119-224            -> pack_text_kernel + keygen_kernel
+//   a5  rank shift B2[i] = B[i+h]     include/shifting.hpp:32-122         -> fused into round_keys_kernel (gathers ISA[SA+h])
+//   a7  initial k-mer LCP             include/suffix_array.hpp:1353-1396  -> resolve_kernel<FIRST=true>
+//   a8  LCP of later rounds           include/suffix_array.hpp:1444-1508  -> resolve_kernel<FIRST=false> (direct compare on packed text)
+//   a9  rebucket (head flags + scan)  include/bucketing.hpp:57-123        -> resolve_kernel (warp-shuffle max-scan + look-back)
+//   a10 SA->ISA bulk permute          include/bulk_permute.hpp:14-73      -> resolve_kernel (ISA[SA[j]] = bucket)
+// The engine is not a port: text is packed densely (no sentinel code; suffixes that run past the end are
+// ordered by a stable-sort trick, see keygen_kernel), the first sort key is ONE word read from the packed
+// text instead of a materialised (B1,B2) pair, bucket ids are 0-based head positions (so the final ids ARE the
+// ISA and no fix-up pass exists) and later rounds touch only the suffixes that are still in a shared bucket.
+#pragma once
+#include "common.cuh"
+
+namespace psacb200 {
+
+// ------------------------------------------------------------------ a2: byte histogram
+__global__ void __launch_bounds__(512) byte_hist_kernel(const u8* __restrict__ text, size_t n, u64* __restrict__ hist) {
+    __shared__ u32 sh[8][256];  // one private histogram per pair of warps cuts same-address contention
+    for (int e = threadIdx.x; e < 8 * 256; e += blockDim.x) (&sh[0][0])[e] = 0;
+    __syncthreads();
+    u32* my = sh[(threadIdx.x >> 6) & 7];
+    const size_t head = (16 - ((size_t)text & 15)) & 15;  // bytes before the first 16-byte boundary
+    const size_t pre = head < n ? head : n;
+    const size_t nvec = (n - pre) / 16;
+    const uint4* tv = reinterpret_cast<const uint4*>(text + pre);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
+        uint4 q = __ldcs(tv + i);
+        u32 w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+#pragma unroll
+            for (int b = 0; b < 4; ++b) atomicAdd(&my[(w[a] >> (8 * b)) & 0xffu], 1u);
+        }
+    }
+    if (blockIdx.x == 0) {
+        for (size_t i = threadIdx.x; i < pre; i += blockDim.x) atomicAdd(&my[text[i]], 1u);
+        for (size_t i = pre + nvec * 16 + threadIdx.x; i < n; i += blockDim.x) atomicAdd(&my[text[i]], 1u);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < 256; c += blockDim.x) {
+        u64 s = 0;
+        for (int r = 0; r < 8; ++r) s += sh[r][c];
+        if (s) atomicAdd((unsigned long long*)&hist[c], (unsigned long long)s);
+    }
+}
+
+// ------------------------------------------------------------------ packed text
+// The text is stored as a big-endian bit stream of dense codes, lbits in {1,2,4,8} per character, character i
+// at stream bits [i*lbits, (i+1)*lbits).  Word w holds characters [w*cpw, (w+1)*cpw), first character in the
+// most significant bits, zero past the end; the stream has two zero words of padding.
+struct CodeTable {
+    u8 code[256];
+};
+
+__global__ void __launch_bounds__(256) pack_text_kernel(const u8* __restrict__ text, size_t n, CodeTable tab, int lbits, u64* __restrict__ stream,
+                                                        size_t nwords) {
+    __shared__ u8 lut[256];
+    lut[threadIdx.x] = tab.code[threadIdx.x];
+    __syncthreads();
+    const int cpw = 64 / lbits;
+    const bool aligned = (((size_t)text) & 15) == 0;
+    for (size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x; w < nwords; w += (size_t)gridDim.x * blockDim.x) {
+        const size_t c0 = w * (size_t)cpw;
+        u64 acc = 0;
+        if (c0 + cpw <= n && aligned && cpw >= 16) {
+            const uint4* tv = reinterpret_cast<const uint4*>(text + c0);
+            for (int v = 0; v < cpw / 16; ++v) {
+                uint4 q = __ldcs(tv + v);
+                u32 ww[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) acc = (acc << lbits) | lut[(ww[a] >> (8 * b)) & 0xffu];
+                }
+            }
+        } else {
+            for (int c = 0; c < cpw; ++c) {
+                const size_t i = c0 + c;
+                acc = (acc << lbits) | (u64)(i < n ? lut[text[i]] : 0);
+            }
+        }
+        stream[w] = acc;
+    }
+}
+
+// nbits (<= 64) stream bits starting at character position i, right-aligned
+__device__ __forceinline__ u64 stream_extract(const u64* __restrict__ stream, u64 i, int lbits, int nbits) {
+    const u64 bit = i * (u64)lbits;
+    const u64 w = bit >> 6;
+    const unsigned o = (unsigned)(bit & 63);
+    const u64 hi = __ldg(stream + w), lo = __ldg(stream + w + 1);
+    const u64 v = o ? ((hi << o) | (lo >> (64 - o))) : hi;
+    return v >> (64 - nbits);
+}
+
+// ------------------------------------------------------------------ a4: first sort key
+// keys[j] = the first C characters of suffix idx(j), packed; vals[j] = idx(j).
+// Initial order: the T = min(n, C-1) suffixes that run past the end of the text come FIRST, shortest first,
+// then suffixes 0..n-T-1.  The radix sort is stable, so among equal keys the suffixes that hit the end sort
+// in front and by increasing length -- exactly the order the reference obtains from its 0 sentinel code
+// (include/alphabet.hpp:157-164: code 0 is reserved for "past the end").
+template <typename IdxT>
+__global__ void __launch_bounds__(256) keygen_kernel(const u64* __restrict__ stream, u64 n, int lbits, int C, u64* __restrict__ keys,
+                                                     IdxT* __restrict__ vals) {
+    const u64 T = (n < (u64)(C - 1)) ? n : (u64)(C - 1);
+    const int nbits = C * lbits;
+    for (u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (u64)gridDim.x * blockDim.x) {
+        const u64 idx = (j < T) ? (n - 1 - j) : (j - T);
+        st_stream(keys + j, stream_extract(stream, idx, lbits, nbits));
+        st_stream(vals + j, (IdxT)idx);
+    }
+}
+
+// common characters of two suffixes starting at a+off / b+off in the packed text (used only for the few
+// boundaries that are split in rounds >= 1; all the others get their LCP from the sort keys)
+__device__ __forceinline__ u64 stream_lcp(const u64* __restrict__ stream, u64 n, int lbits, u64 a, u64 b, u64 off) {
+    const int cpw = 64 / lbits;
+    u64 l = off;
+    while (a + l < n && b + l < n) {
+        const u64 x = stream_extract(stream, a + l, lbits, 64) ^ stream_extract(stream, b + l, lbits, 64);
+        if (x) {
+            l += (u64)(__clzll((long long)x) / lbits);
+            break;
+        }
+        l += cpw;
+    }
+    const u64 la = n - a, lb = n - b;
+    const u64 cap = la < lb ? la : lb;
+    return l < cap ? l : cap;
+}
+
+// ------------------------------------------------------------------ a7/a8/a9/a10: resolve one round
+// Works on the m suffixes that were just sorted (round 0: all n of them, position q; later rounds: the
+// unresolved ones, compacted, at SA positions pos[q]).
+//   head[q]   = first element of a bucket (sort key differs from the predecessor)
+//   bucket[q] = SA position of its head            (inclusive max-scan, warp shuffles + look-back)
+//   ISA[suffix[q]] = bucket[q]                      (SA -> ISA permute)
+//   LCP at every new bucket boundary
+//   unresolved' = elements whose bucket still has >= 2 members; their positions and head flags are
+//                 compacted in order (exclusive sum-scan, look-back) for the next round.
+struct ResolveArgs {
+    const u64* keys;      // sorted keys
+    const void* vals;     // sorted suffix indices (IdxT)
+    const void* pos_in;   // SA position of element q (rounds >= 1)
+    u64 m;                // elements this round
+    u64 n;                // text length
+    void* sa;             // rounds >= 1: SA[pos[q]] = vals[q]
+    void* isa;
+    void* lcp;            // may be null
+    void* pos_out;        // compacted positions of the still unresolved elements
+    u8* head_out;         // their head flags
+    u64* counts;          // [0] unresolved elements, [1] unresolved buckets (atomic)
+    u64* lb_max;          // look-back channels, one u64 per tile each
+    u64* lb_sum;
+    u32* tile_counter;
+    const u64* stream;    // packed text
+    int lbits;
+    int C;                // round 0: characters in the key
+    int kbits;            // rounds >= 1: bits of the low key field (rank of suffix+h); the rest is the bucket
+    u64 h;                // rounds >= 1: characters already known equal inside a bucket
+};
+
+constexpr int RES_THREADS = 256;
+constexpr int RES_ITEMS = 4;
+constexpr int RES_TILE = RES_THREADS * RES_ITEMS;
+
+template <typename IdxT, bool FIRST>
+__global__ void __launch_bounds__(RES_THREADS) resolve_kernel(ResolveArgs A) {
+    __shared__ u64 s_wmax[RES_THREADS / 32];
+    __shared__ u32 s_wsum[RES_THREADS / 32];
+    __shared__ u64 s_excl_max;
+    __shared__ u64 s_excl_sum;
+    __shared__ u32 s_tile;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_tile = atomicAdd(A.tile_counter, 1u);
+    __syncthreads();
+    const u64 tile = s_tile;
+    const u64 ntiles = (A.m + RES_TILE - 1) / RES_TILE;
+    const u64 q0 = tile * RES_TILE + (u64)tid * RES_ITEMS;
+    const IdxT* vals = reinterpret_cast<const IdxT*>(A.vals);
+    const IdxT* pos_in = reinterpret_cast<const IdxT*>(A.pos_in);
+    const u64 m = A.m, n = A.n;
+
+    // elements q0-1 .. q0+ITEMS (one neighbour on each side)
+    u64 key[RES_ITEMS + 2];
+    u64 suf[RES_ITEMS + 2];
+    u64 pos[RES_ITEMS];
+#pragma unroll
+    for (int i = 0; i < RES_ITEMS + 2; ++i) {
+        const u64 q = q0 + i - 1;
+        const bool in = (q0 + i >= 1) && q < m;
+        key[i] = in ? A.keys[q] : 0;
+        suf[i] = in ? (u64)vals[q] : 0;
+    }
+#pragma unroll
+    for (int i = 0; i < RES_ITEMS; ++i) {
+        const u64 q = q0 + i;
+        pos[i] = FIRST ? q : ((q < m) ? (u64)pos_in[q] : 0);
+    }
+    // head flags for q0 .. q0+ITEMS (the last one only feeds the "unresolved" test); head[m] = true
+    bool head[RES_ITEMS + 1];
+    const u64 tail_from = (n >= (u64)A.C) ? (n - (u64)A.C) : 0;  // suffix s runs past the end iff s > tail_from (or n < C)
+    const bool all_tail = n < (u64)A.C;
+#pragma unroll
+    for (int i = 0; i < RES_ITEMS + 1; ++i) {
+        const u64 q = q0 + i;
+        bool hd;
+        if (q >= m || q == 0) {
+            hd = true;
+        } else {
+            hd = key[i + 1] != key[i];
+            if (FIRST) hd = hd || all_tail || suf[i + 1] > tail_from || suf[i] > tail_from;
+        }
+        head[i] = hd;
+    }
+    // thread-local scans
+    u64 mx[RES_ITEMS];
+    u32 un[RES_ITEMS];
+    u64 run_max = 0;
+    u32 run_sum = 0, nbuckets = 0;
+#pragma unroll
+    for (int i = 0; i < RES_ITEMS; ++i) {
+        const bool valid = (q0 + i) < m;
+        if (valid && head[i]) run_max = pos[i] > run_max ? pos[i] : run_max;
+        mx[i] = run_max;
+        const u32 u = (valid && !(head[i] && head[i + 1])) ? 1u : 0u;
+        un[i] = run_sum;  // exclusive
+        run_sum += u;
+        nbuckets += (u && head[i]) ? 1u : 0u;
+    }
+    // warp + CTA scans
+    const u64 wincl_max = warp_inclusive_scan(run_max, OpMax());
+    const u32 wincl_sum = warp_inclusive_sum_u32(run_sum);
+    u32 wb = nbuckets;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) wb += __shfl_xor_sync(0xffffffffu, wb, d);
+    if (lane == 31) {
+        s_wmax[warp] = wincl_max;
+        s_wsum[warp] = wincl_sum;
+    }
+    u64 texcl_max = __shfl_up_sync(0xffffffffu, wincl_max, 1);
+    if (lane == 0) texcl_max = 0;
+    const u32 texcl_sum = wincl_sum - run_sum;
+    __syncthreads();
+    u64 cta_max = 0;
+    u32 cta_sum = 0;
+    u64 wpre_max = 0;
+    u32 wpre_sum = 0;
+#pragma unroll
+    for (int w = 0; w < RES_THREADS / 32; ++w) {
+        if (w == warp) {
+            wpre_max = cta_max;
+            wpre_sum = cta_sum;
+        }
+        cta_max = s_wmax[w] > cta_max ? s_wmax[w] : cta_max;
+        cta_sum += s_wsum[w];
+    }
+    if (tid == 0) s_excl_max = lookback_exclusive(A.lb_max, 1, tile, cta_max, 1u, OpMax());
+    if (tid == 32) {
+        const u64 e = lookback_exclusive(A.lb_sum, 1, tile, (u64)cta_sum, 1u, OpSum());
+        s_excl_sum = e;
+        if (tile == ntiles - 1) atomicAdd((unsigned long long*)&A.counts[0], (unsigned long long)(e + cta_sum));
+    }
+    if (lane == 0 && wb) atomicAdd((unsigned long long*)&A.counts[1], (unsigned long long)wb);
+    __syncthreads();
+    u64 pre_max = s_excl_max;
+    pre_max = wpre_max > pre_max ? wpre_max : pre_max;
+    pre_max = texcl_max > pre_max ? texcl_max : pre_max;
+    const u64 pre_sum = s_excl_sum + wpre_sum + texcl_sum;
+
+    IdxT* sa = reinterpret_cast<IdxT*>(A.sa);
+    IdxT* isa = reinterpret_cast<IdxT*>(A.isa);
+    IdxT* lcp = reinterpret_cast<IdxT*>(A.lcp);
+    IdxT* pos_out = reinterpret_cast<IdxT*>(A.pos_out);
+    const int nbits = A.C * A.lbits;
+#pragma unroll
+    for (int i = 0; i < RES_ITEMS; ++i) {
+        const u64 q = q0 + i;
+        if (q >= m) break;
+        const u64 bucket = mx[i] > pre_max ? mx[i] : pre_max;
+        const u64 s = suf[i + 1];
+        isa[s] = (IdxT)bucket;
+        if (!FIRST) sa[pos[i]] = (IdxT)s;
+        if (lcp != nullptr && head[i]) {
+            if (q == 0) {
+                if (FIRST) lcp[0] = 0;
+            } else if (FIRST) {
+                const u64 sp = suf[i];
+                const u64 x = key[i] ^ key[i + 1];
+                u64 c = x ? (u64)(__clzll((long long)(x << (64 - nbits))) / A.lbits) : (u64)A.C;
+                const u64 la = n - sp, lb = n - s;
+                c = c < la ? c : la;
+                c = c < lb ? c : lb;
+                lcp[q] = (IdxT)c;
+            } else if ((key[i] >> A.kbits) == (key[i + 1] >> A.kbits)) {
+                // same old bucket, different rank of suffix+h: the first h characters agree
+                lcp[pos[i]] = (IdxT)stream_lcp(A.stream, n, A.lbits, suf[i], s, A.h);
+            }
+        }
+        const bool unresolved = !(head[i] && head[i + 1]);
+        if (unresolved) {
+            const u64 o = pre_sum + un[i];
+            pos_out[o] = (IdxT)pos[i];
+            A.head_out[o] = head[i] ? 1 : 0;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ a5 + key assembly for rounds >= 1
+// For unresolved element q (SA position pos[q], suffix s = SA[pos[q]]):
+//   key = (index of its bucket's head in the compacted array) << kbits  |  (s+h < n ? ISA[s+h] + 1 : 0)
+// so one radix sort orders every bucket by the rank of the suffix h characters further on while keeping
+// the buckets where they are.
+struct RoundKeyArgs {
+    const void* pos;
+    const u8* head;
+    const void* sa;
+    const void* isa;
+    u64 m, n, h;
+    int kbits;
+    u64* keys;
+    void* vals;
+    u64* lb_max;
+    u32* tile_counter;
+};
+
+template <typename IdxT>
+__global__ void __launch_bounds__(RES_THREADS) round_keys_kernel(RoundKeyArgs A) {
+    __shared__ u64 s_wmax[RES_THREADS / 32];
+    __shared__ u64 s_excl_max;
+    __shared__ u32 s_tile;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_tile = atomicAdd(A.tile_counter, 1u);
+    __syncthreads();
+    const u64 tile = s_tile;
+    const u64 q0 = tile * RES_TILE + (u64)tid * RES_ITEMS;
+    const IdxT* pos = reinterpret_cast<const IdxT*>(A.pos);
+    const IdxT* sa = reinterpret_cast<const IdxT*>(A.sa);
+    const IdxT* isa = reinterpret_cast<const IdxT*>(A.isa);
+    IdxT* vals = reinterpret_cast<IdxT*>(A.vals);
+    u64 mx[RES_ITEMS], suf[RES_ITEMS], k2[RES_ITEMS];
+    u64 run_max = 0;
+#pragma unroll
+    for (int i = 0; i < RES_ITEMS; ++i) {
+        const u64 q = q0 + i;
+        suf[i] = 0;
+        k2[i] = 0;
+        if (q < A.m) {
+            if (A.head[q]) run_max = q;  // q increases, so "max" is simply the latest head
+            const u64 s = (u64)sa[pos[q]];
+            suf[i] = s;
+            k2[i] = (s + A.h < A.n) ? (u64)isa[s + A.h] + 1 : 0;
+        }
+        mx[i] = run_max;
+    }
+    const u64 wincl = warp_inclusive_scan(run_max, OpMax());
+    if (lane == 31) s_wmax[warp] = wincl;
+    u64 texcl = __shfl_up_sync(0xffffffffu, wincl, 1);
+    if (lane == 0) texcl = 0;
+    __syncthreads();
+    u64 cta_max = 0, wpre = 0;
+#pragma unroll
+    for (int w = 0; w < RES_THREADS / 32; ++w) {
+        if (w == warp) wpre = cta_max;
+        cta_max = s_wmax[w] > cta_max ? s_wmax[w] : cta_max;
+    }
+    if (tid == 0) s_excl_max = lookback_exclusive(A.lb_max, 1, tile, cta_max, 1u, OpMax());
+    __syncthreads();
+    u64 pre = s_excl_max;
+    pre = wpre > pre ? wpre : pre;
+    pre = texcl > pre ? texcl : pre;
+#pragma unroll
+    for (int i = 0; i < RES_ITEMS; ++i) {
+        const u64 q = q0 + i;
+        if (q >= A.m) break;
+        const u64 b = mx[i] > pre ? mx[i] : pre;
+        A.keys[q] = (b << A.kbits) | k2[i];
+        vals[q] = (IdxT)suf[i];
+    }
+}
+
+// ------------------------------------------------------------------ output conversion (internal IdxT -> reference index_t)
+template <typename SrcT, typename DstT>
+__global__ void __launch_bounds__(256) convert_kernel(const SrcT* __restrict__ src, DstT* __restrict__ dst, u64 n) {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) st_stream(dst + i, (DstT)ld_stream(src + i));
+}
+
+}  // namespace psacb200

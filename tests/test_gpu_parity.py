@@ -1,0 +1,190 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle (oracle/), the golden
+fixtures generated from the unmodified reference (tests/golden/) and, where the prebuilt oracle/_ref travels, the
+unmodified reference itself.  Everything is integer work: the bar is bit-exact."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as O
+from psac_b200 import api
+from psac_b200 import textgen as G
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    e = api.Engine(0)
+    yield e
+    e.close()
+
+
+# ------------------------------------------------------------------------------------------- radix sort (a6)
+@pytest.mark.parametrize("kdt", [np.uint32, np.uint64])
+@pytest.mark.parametrize("vdt", [None, np.uint32, np.uint64])
+@pytest.mark.parametrize("n", [1, 2, 31, 33, 1000, 4608, 6144, 6145, 100003, (1 << 20) + 7])
+def test_sort_pairs_matches_stable_numpy(eng, kdt, vdt, n):
+    rng = np.random.default_rng(n * 7 + np.dtype(kdt).itemsize)
+    kb = np.dtype(kdt).itemsize * 8
+    for (b0, b1) in [(0, kb), (0, 8), (3, 21), (kb - 13, kb), (0, 1)]:
+        keys = rng.integers(0, 2 ** kb, size=n, dtype=kdt)
+        if b1 - b0 > 16:  # force ties so stability is tested
+            keys[rng.integers(0, n, size=n // 3)] = keys[0]
+        vals = None if vdt is None else np.arange(n, dtype=vdt)
+        mask = np.uint64(((1 << (b1 - b0)) - 1))
+        field = (keys.astype(np.uint64) >> np.uint64(b0)) & mask
+        order = np.argsort(field, kind="stable")
+        k2 = keys.copy()
+        v2 = None if vals is None else vals.copy()
+        eng.sort_pairs_host(k2, v2, b0, b1)
+        if vals is not None:
+            assert (v2 == vals[order]).all(), (n, b0, b1)
+            assert (k2 == keys[order]).all(), (n, b0, b1)
+        else:
+            assert (((k2.astype(np.uint64) >> np.uint64(b0)) & mask) == field[order]).all()
+            assert (np.sort(k2) == np.sort(keys)).all()
+
+
+def test_sort_pairs_skewed_digits(eng):
+    n = 300001
+    keys = np.zeros(n, np.uint64)
+    keys[::7] = 1 << 40
+    vals = np.arange(n, dtype=np.uint32)
+    order = np.argsort(keys, kind="stable")
+    k2, v2 = keys.copy(), vals.copy()
+    eng.sort_pairs_host(k2, v2, 0, 48)
+    assert (v2 == vals[order]).all() and (k2 == keys[order]).all()
+
+
+# ------------------------------------------------------------------------------------------- alphabet (a2)
+def test_alphabet_matches_oracle(eng):
+    for t in (b"mississippi", G.random_dna(10007, 3), np.arange(256, dtype=np.uint8).repeat(3), G.random_bytes(70001, 9)):
+        lut, sigma, bpc = eng.alphabet(t)
+        elut, esigma, ebpc = O.alphabet(t)
+        assert (lut == elut).all() and sigma == esigma and bpc == ebpc
+
+
+# ------------------------------------------------------------------------------------------- construct
+def _check(eng, text, index_bytes, want_lcp, k=0, exp=None):
+    text = np.ascontiguousarray(np.frombuffer(text, np.uint8) if isinstance(text, (bytes, bytearray)) else text, np.uint8)
+    r = eng.construct(text, index_bytes, want_lcp, k)
+    if exp is None:
+        exp = O.construct(text, index_bytes * 8, 0, want_lcp)
+        assert exp["rc"] == 0
+    assert (r["sa"].astype(np.uint64) == exp["sa"].astype(np.uint64)).all()
+    assert (r["isa"].astype(np.uint64) == exp["isa"].astype(np.uint64)).all()
+    if want_lcp:
+        assert (r["lcp"].astype(np.uint64) == exp["lcp"].astype(np.uint64)).all()
+    return r
+
+
+def test_mississippi_golden(eng):
+    # test/test_psac.cpp:105
+    for ib in (4, 8):
+        r = eng.construct(b"mississippi", ib, True)
+        assert r["sa"].tolist() == [10, 7, 4, 1, 0, 9, 8, 6, 3, 5, 2]
+        assert r["lcp"].tolist() == [0, 1, 1, 4, 0, 0, 1, 0, 2, 1, 3]
+        assert (r["sa"][r["isa"].astype(np.int64)] == np.arange(11)).all()
+
+
+def test_golden_fixtures_from_the_reference(eng, golden_dir):
+    seen = 0
+    for f in sorted(glob.glob(os.path.join(golden_dir, "*.npz"))):
+        d = np.load(f)
+        if "sa" not in d.files:
+            continue
+        want_lcp = "lcp" in d.files
+        exp = dict(sa=d["sa"], isa=d["isa"], lcp=d["lcp"] if want_lcp else None)
+        for k in {0, int(d["k"])}:
+            _check(eng, d["text"], int(d["index_bytes"]), want_lcp, k, exp)
+        seen += 1
+    assert seen >= 10
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 9, 31, 64, 65, 1000, 1024, 1025, 4097, 66763, 130370])
+def test_random_dna_vs_oracle(eng, n):
+    t = G.random_dna(n, 100 + n)
+    _check(eng, t, 4, False)
+    _check(eng, t, 8, True)
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 5])
+def test_forced_short_first_key_many_rounds(eng, k):
+    # the reference forces more doubling rounds / bucket chasing with small k (test_psac.cpp:148-171)
+    t = G.random_dna(20011, 5)
+    exp = O.construct(t, 64, 0, True)
+    r = _check(eng, t, 8, True, k, exp)
+    assert eng.stats()["rounds"] > 1
+
+
+def test_repetitive_and_periodic_texts(eng):
+    for t in (G.repeats_text(3000, 2), G.periodic_text(b"abc", 14681), G.periodic_text(b"a", 5000), G.periodic_text(b"ab", 4097),
+              np.zeros(1000, np.uint8)):
+        _check(eng, t, 8, True)
+        _check(eng, t, 4, True)
+
+
+def test_bytes_alphabets(eng):
+    t255 = np.minimum(G.random_bytes(50000, 4), 254).astype(np.uint8)
+    _check(eng, t255, 8, True)
+    t256 = G.random_bytes_config4(60000, 4)  # all 256 values: the reference's LUT wraps 0xFF to code 0
+    assert len(np.unique(t256)) == 256
+    _check(eng, t256, 8, False)
+    _check(eng, t256, 4, True)
+    _check(eng, G.random_bytes(777, 1) % 20 + 65, 8, True)  # protein-sized alphabet -> 8-bit packing
+    _check(eng, G.random_bytes(777, 1) % 13, 4, True)       # 4-bit packing, contains byte 0
+
+
+def test_user_alphabet_overload(eng):
+    t = G.random_dna(5000, 77)
+    lut, _, _ = O.alphabet(t)
+    r = eng.construct(t, 8, True, lut=lut)
+    exp = O.construct(t, 64, 0, True)
+    assert (r["sa"] == exp["sa"]).all() and (r["lcp"] == exp["lcp"]).all()
+
+
+@pytest.mark.skipif(not O.have_ref(), reason="oracle/_ref/libpsacref.so not built")
+def test_against_unmodified_reference(eng):
+    for n, ib, lcp in ((1 << 16, 4, False), (200003, 8, True)):
+        t = G.random_dna(n, 31 + n)
+        exp = O.ref_construct(t, ib, lcp)
+        _check(eng, t, ib, lcp, 0, exp)
+    t = G.random_bytes_config4(1 << 16, 8)
+    _check(eng, t, 8, False, 0, O.ref_construct(t, 8, False))
+
+
+def test_medium_size_properties(eng):
+    # 16 Mi random DNA (the size of the survey's CPU probe): exact ISA inverse + oracle order check
+    n = 1 << 24
+    t = G.random_dna(n, 2)
+    r = eng.construct(t, 4, True)
+    sa, isa, lcp = r["sa"], r["isa"], r["lcp"]
+    assert (sa[isa] == np.arange(n, dtype=np.uint32)).all()
+    assert O.check_sa(t, sa.astype(np.uint64), isa.astype(np.uint64)) == 0
+    # LCP spot check on a sample with the Kasai oracle restricted to a prefix of SA positions
+    idx = np.random.default_rng(1).integers(1, n, size=2000)
+    for p in idx:
+        a, b = int(sa[p - 1]), int(sa[p])
+        l = 0
+        while a + l < n and b + l < n and t[a + l] == t[b + l]:
+            l += 1
+        assert l == int(lcp[p])
+    assert lcp[0] == 0
+
+
+def test_sa_class_mirror(eng):
+    s = api.SuffixArray(index_bytes=8, construct_lcp=True, engine=eng).construct(b"mississippi")
+    assert s.n == 11 and s.local_size == 11 and s.p == 1
+    assert s.local_SA.tolist() == [10, 7, 4, 1, 0, 9, 8, 6, 3, 5, 2]
+    s2 = api.SuffixArray(index_bytes=4, engine=eng).construct_arr(G.random_dna(5000, 1), L=3)
+    exp = O.construct(G.random_dna(5000, 1), 32, 0, False)
+    assert (s2.local_SA == exp["sa"]).all() and (s2.local_B == exp["isa"]).all() and s2.local_LCP is None
+
+
+def test_errors(eng):
+    with pytest.raises(api.PsacError):
+        eng.construct(b"abc", 3)
+    r = eng.construct(b"", 8, True)
+    assert r["sa"].size == 0
