@@ -1,0 +1,266 @@
+#!/usr/bin/env python
+"""psac-b200 benchmark: suffixes/s of SA (+ISA) construction on synthetic random DNA.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--log2n 30] [--lcp]
+
+One "step" = one complete suffix-array construction (the hot path of BASELINE.json) over one synthetic text.
+N = 1 workload = BASELINE.json configs[1]: 1 GiB random DNA (|Sigma| = 4), SA-only, 32-bit index, one B200.
+  value     : suffixes/s with the text already resident in HBM and the outputs left in HBM (psacb200_construct_device)
+  e2e       : suffixes/s through the reference-facing C-ABI call with HOST (pinned) buffers -- H2D of the text and D2H
+              of SA and ISA inside the timed region (psacb200_construct)
+  roofline  : dominant kernel = one radix digit pass of the first sort; algorithmic bytes per launch =
+              n * 2 * (8-byte key + 4-byte suffix index), see DESIGN.md
+  cpu_baseline / --impl reference : the UNMODIFIED reference (oracle/_ref, MPI shim, np = 1 -> one core) on a bounded
+              prefix of the same text
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SEED = 2  # C2 = 2^30 uniform ACGT, seed 2
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.stop_flag = threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        self.stop_flag.set()
+        self.join(timeout=6)
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def reference_run(text_np, index_bytes, want_lcp, steps, warmup):
+    """Times the unmodified reference (oracle/_ref) -- or the plain-C port when _ref is absent -- on host cores."""
+    from oracle import pyoracle as O
+    kind = "reference" if O.have_ref() else "port"
+    fn = (lambda: O.ref_construct(text_np, index_bytes, want_lcp)) if kind == "reference" else (lambda: O.construct(text_np, index_bytes * 8, 0, want_lcp))
+    for _ in range(warmup):
+        fn()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        fn()
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return kind, text_np.size / dt, dt * 1e3
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--log2n", type=int, default=30, help="log2 of the characters per GPU")
+    ap.add_argument("--lcp", action="store_true", help="also build the LCP array")
+    ap.add_argument("--cpu-log2n", type=int, default=25, help="log2 of the CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    n = 1 << args.log2n
+    index_bytes = 4
+    workload = "random DNA (|Sigma|=4) 2^%d chars per GPU, SA%s, %d-bit index (BASELINE configs[1] shape)" % (
+        args.log2n, "+LCP" if args.lcp else "-only (+ISA)", index_bytes * 8)
+    from psac_b200 import textgen as G
+
+    # ------------------------------------------------------------------ reference arm (CPU, rank 0 only)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        m = 1 << min(args.cpu_log2n, args.log2n)
+        text = G.random_dna(m, SEED)
+        steps, warmup = max(1, args.steps), max(0, min(args.warmup, 1))
+        kind, sps, ms = reference_run(text, index_bytes, args.lcp, steps, warmup)
+        line = {"impl": "reference", "metric": "suffixes/sec SA build", "value": sps, "unit": "suffixes/s", "n_gpus": args.gpus, "steps": steps,
+                "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
+                "data": "synthetic", "config": {"workload": workload, "cpu_sample": "first 2^%d characters of the same text per step" % int(np.log2(m))},
+                "cpu_baseline": {"value": sps, "unit": "suffixes/s", "cores": 1, "kind": kind,
+                                 "sample": "first 2^%d characters of the text; unmodified psac at np=1 under the MPI shim (single core: the box has no MPI)" % int(np.log2(m))},
+                "e2e": {"value": sps, "unit": "suffixes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
+        return
+
+    # ------------------------------------------------------------------ B200 arm
+    import torch
+    import torch.distributed as dist
+    from psac_b200 import api
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- psac-b200 has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    eng = api.Engine(local_rank)
+    flags = (api.LCP if args.lcp else 0) | api.FAST_RESOLVAL
+    # every rank builds the SA of its own 2^log2n-character text (independent texts: seeds differ per rank)
+    text = G.random_dna_torch(n, SEED + rank, dev)
+    tdt = torch.int32  # raw 32-bit storage for uint32 outputs
+    d_sa = torch.empty(n, dtype=tdt, device=dev)
+    d_isa = torch.empty(n, dtype=tdt, device=dev)
+    d_lcp = torch.empty(n, dtype=tdt, device=dev) if args.lcp else None
+    eng.reserve(n, index_bytes, flags)
+    torch.cuda.synchronize()
+
+    def step_device():
+        eng.construct_ptr(text.data_ptr(), n, index_bytes, flags, 0, d_sa.data_ptr(), d_isa.data_ptr(), d_lcp.data_ptr() if d_lcp is not None else None,
+                          device=True)
+
+    ext = torch.cuda.ExternalStream(eng.stream_ptr, device=dev)
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = eng.launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pass_ms, phase = [], {}
+    ev0.record(ext)
+    for _ in range(args.steps):
+        step_device()
+        s = eng.stats()
+        pass_ms.append(s["ms_sort_pass_avg"])
+        for k, v in s.items():
+            if k.startswith("ms_"):
+                phase[k] = phase.get(k, 0.0) + v / args.steps
+    ev1.record(ext)
+    barrier()
+    ms_dev = ev0.elapsed_time(ev1) / args.steps
+    launches = eng.launches - launches0
+    clocks = sampler.summary()
+    stats = eng.stats()
+
+    # size-independent certificate of the last result (permutation + inverse), on the device
+    ar = torch.arange(n, dtype=torch.int64, device=dev)
+    ok = bool((d_isa.to(torch.int64).bitwise_and(0xFFFFFFFF)[d_sa.to(torch.int64).bitwise_and(0xFFFFFFFF)] == ar).all().item())
+    del ar
+    if not ok:
+        raise SystemExit("bench.py: ISA[SA[i]] != i -- result invalid")
+
+    # ------------------------------------------------------------------ end to end: pinned host buffers through the C ABI
+    e2e = None
+    if not args.no_e2e:
+        h_text = torch.empty(n, dtype=torch.uint8).pin_memory()
+        h_text.copy_(text)
+        h_sa = torch.empty(n, dtype=tdt).pin_memory()
+        h_isa = torch.empty(n, dtype=tdt).pin_memory()
+        h_lcp = torch.empty(n, dtype=tdt).pin_memory() if args.lcp else None
+        torch.cuda.synchronize()
+
+        def step_host():
+            eng.construct_ptr(h_text.data_ptr(), n, index_bytes, flags, 0, h_sa.data_ptr(), h_isa.data_ptr(), h_lcp.data_ptr() if h_lcp is not None else None)
+
+        step_host()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k_e2e = max(1, min(args.steps, 3))
+        e0.record(ext)
+        for _ in range(k_e2e):
+            step_host()
+        e1.record(ext)
+        barrier()
+        ms_e2e = e0.elapsed_time(e1) / k_e2e
+        outs = 2 + (1 if args.lcp else 0)
+        e2e = {"ms": ms_e2e, "h2d": n, "d2h": outs * n * index_bytes, "steps": k_e2e, "sa0": int(h_sa[0].item()) & 0xFFFFFFFF}
+
+    # ------------------------------------------------------------------ reduce over ranks (max time)
+    t = torch.tensor([ms_dev, e2e["ms"] if e2e else 0.0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_dev, ms_e2e = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peaks()
+    key_bytes, val_bytes = 8, stats["internal_index_bytes"]
+    pass_bytes = float(n) * 2 * (key_bytes + val_bytes)
+    pass_avg_ms = float(np.mean(pass_ms))
+    achieved = pass_bytes / (pass_avg_ms * 1e-3) / 1e9 if pass_avg_ms > 0 else 0.0
+    line = {
+        "metric": "suffixes/sec SA build", "value": world * n / (ms_dev * 1e-3), "unit": "suffixes/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
+        "data": "synthetic",
+        "config": {"workload": workload, "n_per_gpu": n, "parallelism": "1 text per GPU" if world > 1 else "single GPU", "seed": SEED,
+                   "l2": "inputs_exceed_l2 (every pass streams >= 12 GiB)", "key_chars": stats["key_chars"], "sort_passes": stats["sort_passes"],
+                   "rounds": stats["rounds"], "unresolved_after_first": stats["unresolved_after_first"], "verified": "ISA[SA[i]]==i on device"},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": "onesweep_pass_kernel<u64,u32> (one 8-bit digit pass of the first sort)", "achieved": achieved,
+                     "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "bytes_per_launch": pass_bytes, "ms_per_launch": pass_avg_ms},
+        "phases_ms": {k: round(v, 3) for k, v in sorted(phase.items())},
+    }
+    if e2e:
+        line["e2e"] = {"value": world * n / (ms_e2e * 1e-3), "unit": "suffixes/s", "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
+                       "ms_per_step": ms_e2e, "steps": e2e["steps"]}
+    if not args.no_cpu_baseline and world >= 1:
+        m = 1 << min(args.cpu_log2n, args.log2n)
+        kind, sps, ms = reference_run(G.random_dna(m, SEED), index_bytes, args.lcp, 1, 0)
+        line["cpu_baseline"] = {"value": sps, "unit": "suffixes/s", "cores": 1, "kind": kind, "ms": ms,
+                                "sample": "first 2^%d characters of the same text, one run; unmodified psac at np=1 under the MPI shim" % int(np.log2(m))}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -64,6 +64,8 @@ const char* psacb200_last_error(void);
 /* Number of CUDA kernel launches issued by this engine since creation (bench.py's gpu_launches). */
 uint64_t psacb200_launch_count(const psacb200_engine* e);
 int psacb200_get_stats(const psacb200_engine* e, psacb200_stats* out);
+/* The engine's cudaStream_t (as void*), so a caller can bracket calls with its own CUDA events on that stream. */
+void* psacb200_stream(const psacb200_engine* e);
 /* Pre-size the device buffers for texts up to n characters (optional; avoids cudaMalloc inside a timed call). */
 int psacb200_reserve(psacb200_engine* e, size_t n, int index_bytes, unsigned flags);
 

@@ -66,6 +66,8 @@ def lib():
         L.psacb200_launch_count.restype = C.c_uint64
         L.psacb200_launch_count.argtypes = [C.c_void_p]
         L.psacb200_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+        L.psacb200_stream.restype = C.c_void_p
+        L.psacb200_stream.argtypes = [C.c_void_p]
         L.psacb200_destroy.argtypes = [C.c_void_p]
         L.psacb200_destroy.restype = None
         L.psacb200_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
@@ -116,6 +118,11 @@ class Engine:
     @property
     def launches(self):
         return int(lib().psacb200_launch_count(self._h))
+
+    @property
+    def stream_ptr(self):
+        """cudaStream_t of the engine (for torch.cuda.ExternalStream / event timing)."""
+        return int(lib().psacb200_stream(self._h))
 
     def stats(self):
         s = Stats()

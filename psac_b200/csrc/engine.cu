@@ -128,6 +128,7 @@ struct Alphabet {
     unsigned sigma = 0;
     unsigned ref_bits = 0;
     int lbits = 1;
+    bool zero_code_used = false;  // sigma = 256 quirk: some character shares code 0 with the end-of-text padding
 };
 
 // reference alphabet<char>::init_mapping_table: codes 1..sigma in byte order, stored in an 8-bit table
@@ -151,6 +152,7 @@ void dense_codes(const u64* hist, Alphabet& a) {
     bool used[256] = {false};
     for (int c = 0; c < 256; ++c)
         if (hist[c]) used[a.lut[c]] = true;
+    a.zero_code_used = used[0];
     int rank[256];
     int d = 0;
     for (int v = 0; v < 256; ++v) rank[v] = used[v] ? d++ : 0;
@@ -313,6 +315,7 @@ void construct_core(psacb200_engine* e, const u8* d_text, u64 n, int index_bytes
     R.C = (int)C;
     R.kbits = 0;
     R.h = 0;
+    R.padded_lcp = alpha.zero_code_used ? 1 : 0;
     launch_resolve<IdxT>(e, true, R);
     e->end(PH_RESOLVE);
     u64 m = 0, nb = 0;
@@ -546,6 +549,8 @@ void psacb200_destroy(psacb200_engine* e) {
 }
 
 uint64_t psacb200_launch_count(const psacb200_engine* e) { return e ? e->launches : 0; }
+
+void* psacb200_stream(const psacb200_engine* e) { return e ? (void*)e->stream : nullptr; }
 
 int psacb200_get_stats(const psacb200_engine* e, psacb200_stats* out) {
     if (!e || !out) {

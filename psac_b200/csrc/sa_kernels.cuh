@@ -117,17 +117,26 @@ __global__ void __launch_bounds__(256) keygen_kernel(const u64* __restrict__ str
 
 // common characters of two suffixes starting at a+off / b+off in the packed text (used only for the few
 // boundaries that are split in rounds >= 1; all the others get their LCP from the sort keys)
-__device__ __forceinline__ u64 stream_lcp(const u64* __restrict__ stream, u64 n, int lbits, u64 a, u64 b, u64 off) {
+// `padded`: the reference's sigma = 256 quirk (include/alphabet.hpp:136,160: the 8-bit code table wraps 0xFF to code
+// 0, the code of "past the end"), where its LCP counts matches between 0xFF and the zero padding; then the
+// comparison runs over the zero-padded sequences instead of stopping at the end of the shorter suffix.
+__device__ __forceinline__ u64 stream_lcp(const u64* __restrict__ stream, u64 n, int lbits, u64 a, u64 b, u64 off, bool padded) {
     const int cpw = 64 / lbits;
     u64 l = off;
-    while (a + l < n && b + l < n) {
-        const u64 x = stream_extract(stream, a + l, lbits, 64) ^ stream_extract(stream, b + l, lbits, 64);
+    while (true) {
+        const bool ina = a + l < n, inb = b + l < n;
+        if (!ina && !inb) break;
+        if (!padded && !(ina && inb)) break;
+        const u64 wa = ina ? stream_extract(stream, a + l, lbits, 64) : 0;
+        const u64 wb = inb ? stream_extract(stream, b + l, lbits, 64) : 0;
+        const u64 x = wa ^ wb;
         if (x) {
             l += (u64)(__clzll((long long)x) / lbits);
             break;
         }
         l += cpw;
     }
+    if (padded) return l;
     const u64 la = n - a, lb = n - b;
     const u64 cap = la < lb ? la : lb;
     return l < cap ? l : cap;
@@ -162,6 +171,7 @@ struct ResolveArgs {
     int C;                // round 0: characters in the key
     int kbits;            // rounds >= 1: bits of the low key field (rank of suffix+h); the rest is the bucket
     u64 h;                // rounds >= 1: characters already known equal inside a bucket
+    int padded_lcp;       // reference quirk: a used character has code 0 and matches the padding (see stream_lcp)
 };
 
 constexpr int RES_THREADS = 256;
@@ -292,13 +302,17 @@ __global__ void __launch_bounds__(RES_THREADS) resolve_kernel(ResolveArgs A) {
                 const u64 sp = suf[i];
                 const u64 x = key[i] ^ key[i + 1];
                 u64 c = x ? (u64)(__clzll((long long)(x << (64 - nbits))) / A.lbits) : (u64)A.C;
-                const u64 la = n - sp, lb = n - s;
-                c = c < la ? c : la;
-                c = c < lb ? c : lb;
+                if (A.padded_lcp) {
+                    if (!x) c = stream_lcp(A.stream, n, A.lbits, sp, s, (u64)A.C, true);  // equal keys split by the end-of-text rule
+                } else {
+                    const u64 la = n - sp, lb = n - s;
+                    c = c < la ? c : la;
+                    c = c < lb ? c : lb;
+                }
                 lcp[q] = (IdxT)c;
             } else if ((key[i] >> A.kbits) == (key[i + 1] >> A.kbits)) {
                 // same old bucket, different rank of suffix+h: the first h characters agree
-                lcp[pos[i]] = (IdxT)stream_lcp(A.stream, n, A.lbits, suf[i], s, A.h);
+                lcp[pos[i]] = (IdxT)stream_lcp(A.stream, n, A.lbits, suf[i], s, A.h, A.padded_lcp != 0);
             }
         }
         const bool unresolved = !(head[i] && head[i + 1]);

@@ -75,3 +75,41 @@ def repeats_text(nwords, seed):
 def periodic_text(unit, reps):
     """(unit)^reps, e.g. (abc)^n of test/test_suffixtree.cpp:131-162."""
     return np.frombuffer(bytes(unit) * reps, np.uint8).copy()
+
+
+# ---------------------------------------------------------------- same generators as torch ops (any device)
+def _t_lsr(z, k):
+    """logical right shift of int64 tensors (torch's >> is arithmetic)"""
+    return (z >> k) & ((1 << (64 - k)) - 1)
+
+
+def _t_wrap(x):
+    x &= (1 << 64) - 1
+    return x - (1 << 64) if x >= (1 << 63) else x
+
+
+def splitmix64_torch(seed, idx):
+    """splitmix64 of psac_b200.textgen.splitmix64 on int64 tensors (two's complement wrap-around arithmetic)."""
+    z = (idx + 1) * _t_wrap(int(_GOLDEN)) + _t_wrap(int(seed) * int(_M1))
+    z = (z ^ _t_lsr(z, 30)) * _t_wrap(int(_M1))
+    z = (z ^ _t_lsr(z, 27)) * _t_wrap(int(_M2))
+    return z ^ _t_lsr(z, 31)
+
+
+def random_dna_torch(n, seed, device, start=0, chunk=1 << 26):
+    """Bit-identical to random_dna(n, seed, start) but generated with torch ops on `device`; returns a uint8 tensor."""
+    import torch
+    acgt = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=device)
+    out = torch.empty(n, dtype=torch.uint8, device=device)
+    shifts = (torch.arange(32, dtype=torch.int64, device=device) * 2)[None, :]
+    pos = 0
+    while pos < n:
+        m = min(chunk, n - pos)
+        g0 = start + pos
+        w0, w1 = g0 // 32, (g0 + m + 31) // 32
+        words = splitmix64_torch(seed, torch.arange(w0, w1, dtype=torch.int64, device=device))
+        codes = ((words[:, None] >> shifts) & 3).reshape(-1)
+        off = g0 - w0 * 32
+        out[pos:pos + m] = acgt[codes[off:off + m]]
+        pos += m
+    return out

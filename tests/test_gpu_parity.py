@@ -72,10 +72,14 @@ def _check(eng, text, index_bytes, want_lcp, k=0, exp=None):
     r = eng.construct(text, index_bytes, want_lcp, k)
     if exp is None:
         exp = O.construct(text, index_bytes * 8, 0, want_lcp)
-        assert exp["rc"] == 0
+        assert exp["rc"] == 0 or text.size == 1  # n == 1: the oracle's doubling loop never runs (rc 1), SA = {0}
     assert (r["sa"].astype(np.uint64) == exp["sa"].astype(np.uint64)).all()
     assert (r["isa"].astype(np.uint64) == exp["isa"].astype(np.uint64)).all()
     if want_lcp:
+        if text.size == 2:
+            # n == 2: the reference's k == 1 raw-character path (kmer.hpp:196-199) makes lcp_bitwise return garbage for
+            # LCP[1] (e.g. 2147483647); the engine returns the true LCP -- compare with Kasai (lcp.hpp:46-77) instead
+            exp = dict(exp, lcp=O.lcp_from_sa(text, exp["sa"], exp["isa"]))
         assert (r["lcp"].astype(np.uint64) == exp["lcp"].astype(np.uint64)).all()
     return r
 
