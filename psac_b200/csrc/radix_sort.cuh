@@ -102,6 +102,8 @@ __global__ void __launch_bounds__(RADIX) radix_scan_hist_kernel(const u64* __res
 }
 
 // ------------------------------------------------------------------ one digit pass
+// Shared memory layout of a pass CTA: [tile staging: TILE * max(sizeof key, sizeof value)] [per-warp rank table:
+// NW * 256 * {match mask, running position}] [bin_start 256 * u32] [goff 256 * u64] [misc].
 template <typename KeyT, typename ValT, int THREADS_, int ITEMS_>
 struct PassCfg {
     static constexpr int THREADS = THREADS_;
@@ -110,107 +112,127 @@ struct PassCfg {
     static constexpr int NW = THREADS / 32;
     static constexpr bool HAS_VALS = !std::is_same<ValT, NoVal>::value;
     static constexpr size_t ELT = (HAS_VALS && sizeof(ValT) > sizeof(KeyT)) ? sizeof(ValT) : sizeof(KeyT);
-    static constexpr size_t SMEM = (size_t)TILE * ELT + (size_t)NW * RADIX * 4 + RADIX * 4 + RADIX * 8 + 64;
+    static constexpr size_t OFF_TAB = (size_t)TILE * ELT;
+    static constexpr size_t OFF_BIN = OFF_TAB + (size_t)NW * RADIX * 8;
+    static constexpr size_t OFF_GOFF = OFF_BIN + RADIX * 4;
+    static constexpr size_t OFF_MISC = OFF_GOFF + RADIX * 8;
+    static constexpr size_t SMEM = OFF_MISC + 64;
 };
 
-template <typename KeyT, typename ValT, int THREADS, int ITEMS>
-__global__ void __launch_bounds__(THREADS) onesweep_pass_kernel(const KeyT* __restrict__ kin, KeyT* __restrict__ kout,
-                                                               const ValT* __restrict__ vin, ValT* __restrict__ vout, size_t n, int shift,
-                                                               int bits, const u64* __restrict__ gbase, u32* __restrict__ tile_counter,
-                                                               u64* __restrict__ lookback, u32 epoch) {
+// Stable ranking of the warp's keys by digit.  match.any costs ~50 cycles per warp instruction per SM on B200
+// (measured, tools/micro_rank.cu) -- more than the whole HBM budget of a key -- so peers are found through a
+// shared-memory table instead: every lane ORs its lane bit into mask[d]; one 64-bit read returns {peers, running
+// position}; the lowest peer clears the mask and advances the position (~13 cycles per warp instruction).
+template <typename KeyT, typename ValT, int THREADS, int ITEMS, bool FULL>
+__device__ __forceinline__ void onesweep_tile(unsigned char* smem_raw, const KeyT* __restrict__ kin, KeyT* __restrict__ kout,
+                                              const ValT* __restrict__ vin, ValT* __restrict__ vout, const size_t base, const int valid,
+                                              const int shift, const u32 mask, const u64* __restrict__ gbase, u64* __restrict__ lookback,
+                                              const size_t tile, const u32 epoch) {
     using Cfg = PassCfg<KeyT, ValT, THREADS, ITEMS>;
-    constexpr int TILE = Cfg::TILE;
     constexpr int NW = Cfg::NW;
-    static_assert(THREADS >= RADIX && THREADS % 32 == 0, "need one thread per digit");
-    static_assert(TILE < 65536, "tile positions are kept in 16 bits");
-
-    extern __shared__ __align__(16) unsigned char smem_raw[];
     KeyT* skeys = reinterpret_cast<KeyT*>(smem_raw);
-    u32(*wh)[RADIX] = reinterpret_cast<u32(*)[RADIX]>(smem_raw + (size_t)TILE * Cfg::ELT);
-    u32* bin_start = reinterpret_cast<u32*>(wh + NW);
-    u64* goff = reinterpret_cast<u64*>(bin_start + RADIX);
-    u32* misc = reinterpret_cast<u32*>(goff + RADIX);  // [0] tile id, [1..8] warp totals of the digit scan
+    uint2* tab = reinterpret_cast<uint2*>(smem_raw + Cfg::OFF_TAB);  // [NW][RADIX] {x: match mask, y: count / position}
+    u32* bin_start = reinterpret_cast<u32*>(smem_raw + Cfg::OFF_BIN);
+    u64* goff = reinterpret_cast<u64*>(smem_raw + Cfg::OFF_GOFF);
+    u32* misc = reinterpret_cast<u32*>(smem_raw + Cfg::OFF_MISC);  // [1..8] warp totals of the digit scan
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) misc[0] = atomicAdd(tile_counter, 1u);
-    for (int e = tid; e < NW * RADIX; e += THREADS) (&wh[0][0])[e] = 0;
-    __syncthreads();
-    const size_t tile = misc[0];
-    const size_t base = tile * (size_t)TILE;
-    const int valid = (n - base < (size_t)TILE) ? (int)(n - base) : TILE;
-    const u32 mask = (1u << bits) - 1u;
-
-    // ---- load keys, warp-striped: item j of lane l is tile element warp*32*ITEMS + j*32 + l
-    KeyT key[ITEMS];
     const int woff = warp * 32 * ITEMS + lane;
+    uint2* mytab = tab + warp * RADIX;
+    const u32 lane_bit = 1u << lane;
+    const u32 lt = lanemask_lt();
+
+    // ---- load keys (and values), warp-striped: item j of lane l is tile element warp*32*ITEMS + j*32 + l
+    KeyT key[ITEMS];
 #pragma unroll
     for (int j = 0; j < ITEMS; ++j) {
-        int o = woff + j * 32;
-        key[j] = (o < valid) ? ld_stream(kin + base + o) : (KeyT)0;
+        const int o = woff + j * 32;
+        key[j] = (FULL || o < valid) ? ld_stream(kin + base + o) : (KeyT)0;
     }
 
-    // ---- stable per-warp ranking with match_any; wh[warp][d] counts the digit inside this warp
-    u16 pos[ITEMS];
+    // ---- early counts: per-warp digit histogram with fire-and-forget shared atomics
 #pragma unroll
     for (int j = 0; j < ITEMS; ++j) {
-        const bool ok = (woff + j * 32) < valid;
-        const u32 d = (u32)(key[j] >> shift) & mask;
-        const u32 tag = ok ? d : (0x100u | (u32)lane);  // padding lanes match nobody
-        const unsigned peers = __match_any_sync(0xffffffffu, tag);
-        const int leader = __ffs(peers) - 1;
-        u32 before = 0;
-        if (ok && lane == leader) {
-            before = wh[warp][d];
-            wh[warp][d] = before + __popc(peers);
-        }
-        before = __shfl_sync(0xffffffffu, before, leader);
-        pos[j] = (u16)(before + __popc(peers & lanemask_lt()));
-        __syncwarp();
+        if (FULL || (woff + j * 32) < valid) atomicAdd(&mytab[(u32)(key[j] >> shift) & mask].y, 1u);
     }
     __syncthreads();
 
-    // ---- per digit: exclusive offsets of the warps inside the tile, tile count, tile-local bin start
+    // ---- per digit: exclusive offsets of the warps, tile count (published at once for the look-back), bin start
     u32 count = 0;
     if (tid < RADIX) {
 #pragma unroll
         for (int w = 0; w < NW; ++w) {
-            u32 c = wh[w][tid];
-            wh[w][tid] = count;
+            const u32 c = tab[w * RADIX + tid].y;
+            tab[w * RADIX + tid].y = count;
             count += c;
         }
+        if (tile > 0) st_relaxed(lookback + tile * RADIX + tid, lb_pack((u64)count, epoch, LB_AGGREGATE));
     }
-    u32 inc = warp_inclusive_sum_u32(count);
+    const u32 inc = warp_inclusive_sum_u32(count);
     if (tid < RADIX && lane == 31) misc[1 + warp] = inc;
     __syncthreads();
     if (tid < RADIX) {
         u32 pre = 0;
-        for (int w = 0; w < warp; ++w) pre += misc[1 + w];
+#pragma unroll
+        for (int w = 0; w < RADIX / 32; ++w) pre += (w < warp) ? misc[1 + w] : 0u;
         const u32 bstart = pre + inc - count;
         bin_start[tid] = bstart;
-        // ---- decoupled look-back, one channel per digit
-        const u64 excl = lookback_exclusive(lookback + tid, RADIX, tile, (u64)count, epoch, OpSum());
-        goff[tid] = gbase[tid] + excl - (u64)bstart;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) tab[w * RADIX + tid].y += bstart;  // position of the warp's first key of this digit
     }
     __syncthreads();
 
-    // ---- scatter keys into shared memory in bin order
+    // ---- stable ranking -> final position of every key inside the tile
+    u16 pos[ITEMS];
 #pragma unroll
     for (int j = 0; j < ITEMS; ++j) {
-        if ((woff + j * 32) < valid) {
-            const u32 d = (u32)(key[j] >> shift) & mask;
-            const u32 p = bin_start[d] + wh[warp][d] + pos[j];
-            pos[j] = (u16)p;
-            skeys[p] = key[j];
-        }
+        const bool ok = FULL || (woff + j * 32) < valid;
+        const u32 d = (u32)(key[j] >> shift) & mask;
+        if (ok) atomicOr(&mytab[d].x, lane_bit);
+        __syncwarp();
+        const uint2 e = mytab[d];
+        __syncwarp();
+        if (ok && (e.x & lt) == 0) mytab[d] = make_uint2(0u, e.y + __popc(e.x));
+        pos[j] = (u16)(e.y + __popc(e.x & lt));
+        __syncwarp();
     }
-    // values: issue the global loads now so they overlap the key write-out
+
+    // values: issue the global loads now, they overlap the key scatter, the look-back and the key write-out
     ValT val[Cfg::HAS_VALS ? ITEMS : 1];
     if constexpr (Cfg::HAS_VALS) {
 #pragma unroll
         for (int j = 0; j < ITEMS; ++j) {
-            int o = woff + j * 32;
-            if (o < valid) val[j] = ld_stream(vin + base + o);
+            const int o = woff + j * 32;
+            if (FULL || o < valid) val[j] = ld_stream(vin + base + o);
         }
+    }
+
+    // ---- scatter keys into shared memory in bin order (tile staging is free: keys live in registers)
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+        if (FULL || (woff + j * 32) < valid) skeys[pos[j]] = key[j];
+    }
+
+    // ---- decoupled look-back, one channel per digit; the predecessors published their counts long ago
+    if (tid < RADIX) {
+        u64 excl = 0;
+        if (tile == 0) {
+            st_relaxed(lookback + tid, lb_pack((u64)count, epoch, LB_INCLUSIVE));
+        } else {
+            size_t t = tile;
+            while (true) {
+                --t;
+                u64 w, st;
+                do {
+                    w = ld_relaxed(lookback + t * RADIX + tid);
+                    st = lb_state(w, epoch);
+                } while (st == LB_NONE);
+                excl += lb_payload(w);
+                if (st == LB_INCLUSIVE) break;
+            }
+            st_relaxed(lookback + tile * RADIX + tid, lb_pack(excl + count, epoch, LB_INCLUSIVE));
+        }
+        goff[tid] = gbase[tid] + excl - (u64)bin_start[tid];
     }
     __syncthreads();
 
@@ -219,7 +241,7 @@ __global__ void __launch_bounds__(THREADS) onesweep_pass_kernel(const KeyT* __re
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i) {
         const int s = i * THREADS + tid;
-        if (s < valid) {
+        if (FULL || s < valid) {
             const KeyT k = skeys[s];
             const u32 d = (u32)(k >> shift) & mask;
             dig[i] = (u8)d;
@@ -231,15 +253,40 @@ __global__ void __launch_bounds__(THREADS) onesweep_pass_kernel(const KeyT* __re
         __syncthreads();
 #pragma unroll
         for (int j = 0; j < ITEMS; ++j) {
-            if ((woff + j * 32) < valid) svals[pos[j]] = val[j];
+            if (FULL || (woff + j * 32) < valid) svals[pos[j]] = val[j];
         }
         __syncthreads();
 #pragma unroll
         for (int i = 0; i < ITEMS; ++i) {
             const int s = i * THREADS + tid;
-            if (s < valid) vout[goff[dig[i]] + (u64)s] = svals[s];
+            if (FULL || s < valid) vout[goff[dig[i]] + (u64)s] = svals[s];
         }
     }
+}
+
+template <typename KeyT, typename ValT, int THREADS, int ITEMS>
+__global__ void __launch_bounds__(THREADS, 2) onesweep_pass_kernel(const KeyT* __restrict__ kin, KeyT* __restrict__ kout,
+                                                               const ValT* __restrict__ vin, ValT* __restrict__ vout, size_t n, int shift,
+                                                               int bits, const u64* __restrict__ gbase, u32* __restrict__ tile_counter,
+                                                               u64* __restrict__ lookback, u32 epoch) {
+    using Cfg = PassCfg<KeyT, ValT, THREADS, ITEMS>;
+    constexpr int TILE = Cfg::TILE;
+    static_assert(THREADS >= RADIX && THREADS % 32 == 0, "need one thread per digit");
+    static_assert(TILE < 65536, "tile positions are kept in 16 bits");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    u32* misc = reinterpret_cast<u32*>(smem_raw + Cfg::OFF_MISC);
+    uint2* tab = reinterpret_cast<uint2*>(smem_raw + Cfg::OFF_TAB);
+    if (threadIdx.x == 0) misc[0] = atomicAdd(tile_counter, 1u);
+    for (int e = threadIdx.x; e < Cfg::NW * RADIX; e += THREADS) tab[e] = make_uint2(0u, 0u);
+    __syncthreads();
+    const size_t tile = misc[0];
+    const size_t base = tile * (size_t)TILE;
+    const u32 mask = (1u << bits) - 1u;
+    if (n - base >= (size_t)TILE)
+        onesweep_tile<KeyT, ValT, THREADS, ITEMS, true>(smem_raw, kin, kout, vin, vout, base, TILE, shift, mask, gbase, lookback, tile, epoch);
+    else
+        onesweep_tile<KeyT, ValT, THREADS, ITEMS, false>(smem_raw, kin, kout, vin, vout, base, (int)(n - base), shift, mask, gbase, lookback, tile,
+                                                       epoch);
 }
 
 // ------------------------------------------------------------------ host driver
