@@ -1,0 +1,159 @@
+// psacb200::suffix_array -- C++ host-side mirror of patflick/psac's suffix_array<char_t, index_t, LCP> for the
+// construct() / construct_arr<L>() path, forwarding to the C ABI in include/psacb200.h.
+//
+// Reference class surface mirrored here (reference include/suffix_array.hpp):
+//   class template + public members n, local_size, p, local_SA, local_B (= ISA), local_LCP   :169-212
+//   init_size(lsize)  -- throws std::runtime_error on a bad block decomposition              :217-228
+//   construct(begin, end, fast_resolval = true, k = 0)                                       :469-486
+//   construct(begin, end, fast_resolval, alphabet, k)                                        :365-366
+//   construct_arr<L>(begin, end, fast_resolval = true)   (SA / ISA only, no LCP :555-567)    :490-641
+// Differences, all outside the hot path: the communicator argument is psacb200::comm, a stand-in for an mxx::comm of
+// size 1 (the GPUs of one box are sharded INSIDE the engine, include/psacb200.h psacb200_construct_sharded, so the
+// host-facing object always holds the whole arrays); the alphabet is the 256-entry code table
+// of the reference's alphabet<char>::mapping_table (include/alphabet.hpp:136,157-164).
+// Errors surface as std::runtime_error carrying psacb200_last_error(), like the reference's own throw at :226-227.
+// There is no CPU fallback: without libpsacb200.so and a B200 every construct call throws.
+#ifndef PSACB200_SUFFIX_ARRAY_HPP
+#define PSACB200_SUFFIX_ARRAY_HPP
+
+#include <cstddef>
+#include <cstdint>
+#include <iterator>
+#include <stdexcept>
+#include <string>
+#include <type_traits>
+#include <vector>
+
+#include "../psacb200.h"
+
+namespace psacb200 {
+
+// stand-in for mxx::comm at p = 1 (reference ext/mxx/include/mxx/comm_fwd.hpp:44-); device = CUDA ordinal to use
+struct comm {
+    int device;
+    explicit comm(int device_ = 0) : device(device_) {}
+    int size() const { return 1; }
+    int rank() const { return 0; }
+    comm copy() const { return *this; }
+};
+
+// the reference's alphabet<char>: character -> code table (codes start at 1, 0 = end-of-text padding)
+struct alphabet {
+    uint8_t mapping_table[256];
+    unsigned sigma_;
+    unsigned bits_per_char_;
+    alphabet() : sigma_(0), bits_per_char_(0) {
+        for (int i = 0; i < 256; ++i) mapping_table[i] = 0;
+    }
+    unsigned sigma() const { return sigma_; }                  // alphabet.hpp:241
+    unsigned bits_per_char() const { return bits_per_char_; }  // alphabet.hpp:249
+    uint8_t encode(unsigned char c) const { return mapping_table[c]; }  // alphabet.hpp:266-269
+};
+
+template <typename char_t, typename index_t = std::size_t, bool _CONSTRUCT_LCP = false>
+class suffix_array {
+    static_assert(sizeof(char_t) == 1, "psacb200 handles 1-byte characters (the reference's alphabet<char> path)");
+    static_assert(sizeof(index_t) == 4 || sizeof(index_t) == 8, "index_t must be a 32- or 64-bit unsigned integer");
+    static_assert(std::is_unsigned<index_t>::value, "index_t must be unsigned");
+
+public:
+    explicit suffix_array(const psacb200::comm& c) : n(0), local_size(0), comm(c.copy()), p(1), engine_(nullptr) {}
+    virtual ~suffix_array() {
+        if (engine_) psacb200_destroy(engine_);
+    }
+    suffix_array(const suffix_array&) = delete;
+    suffix_array& operator=(const suffix_array&) = delete;
+
+    std::size_t n;
+    std::size_t local_size;
+    psacb200::comm comm;
+    int p;
+    using char_type = char_t;
+    using alphabet_type = psacb200::alphabet;
+    alphabet_type alpha;
+    std::vector<index_t> local_SA;
+    std::vector<index_t> local_B;  // inverse suffix array, 0-based (reference: local_B after :460-464)
+    std::vector<index_t> local_LCP;
+
+    // reference :217-228 -- at p = 1 every size is a valid block decomposition
+    void init_size(std::size_t lsize) {
+        local_size = lsize;
+        n = lsize;
+        p = comm.size();
+    }
+
+    // reference :469-486
+    template <typename Iterator>
+    void construct(Iterator begin, Iterator end, bool fast_resolval = true, unsigned int k = 0) {
+        init_size((std::size_t)std::distance(begin, end));
+        const uint8_t* text = contiguous(begin, end);
+        ensure_engine();
+        check(psacb200_alphabet(engine_, text, n, alpha.mapping_table, &alpha.sigma_, &alpha.bits_per_char_));
+        run(text, fast_resolval, k, nullptr, _CONSTRUCT_LCP);
+    }
+
+    // reference :365-366 (caller supplies the alphabet; only the ORDER of its codes matters)
+    template <typename Iterator>
+    void construct(Iterator begin, Iterator end, bool fast_resolval, const alphabet_type& alphabet, unsigned int k) {
+        init_size((std::size_t)std::distance(begin, end));
+        alpha = alphabet;
+        run(contiguous(begin, end), fast_resolval, k, alpha.mapping_table, _CONSTRUCT_LCP);
+    }
+
+    // reference :490-641 -- L-tuple doubling; the final SA / ISA are the same arrays, no LCP is built (:555-567)
+    template <std::size_t L, typename Iterator>
+    void construct_arr(Iterator begin, Iterator end, bool fast_resolval = true) {
+        static_assert(L >= 2, "construct_arr needs L >= 2");
+        init_size((std::size_t)std::distance(begin, end));
+        const uint8_t* text = contiguous(begin, end);
+        ensure_engine();
+        check(psacb200_alphabet(engine_, text, n, alpha.mapping_table, &alpha.sigma_, &alpha.bits_per_char_));
+        run(text, fast_resolval, 0, nullptr, false);
+    }
+
+    psacb200_stats stats() const {
+        psacb200_stats s{};
+        if (engine_) psacb200_get_stats(engine_, &s);
+        return s;
+    }
+
+private:
+    psacb200_engine* engine_;
+    std::vector<uint8_t> staging_;
+
+    static void check(int rc) {
+        if (rc != PSACB200_OK) throw std::runtime_error(std::string("psacb200: ") + psacb200_last_error());
+    }
+    void ensure_engine() {
+        if (!engine_) check(psacb200_create(comm.device, &engine_));
+    }
+    // the C ABI takes one contiguous byte buffer; pointers and vector/string iterators are passed through, anything
+    // else is copied once
+    template <typename Iterator>
+    const uint8_t* contiguous(Iterator begin, Iterator end) {
+        if (begin == end) return nullptr;
+        if (std::is_pointer<Iterator>::value ||
+            std::is_same<Iterator, typename std::vector<char_t>::iterator>::value ||
+            std::is_same<Iterator, typename std::vector<char_t>::const_iterator>::value ||
+            std::is_same<Iterator, std::string::iterator>::value || std::is_same<Iterator, std::string::const_iterator>::value)
+            return reinterpret_cast<const uint8_t*>(&*begin);
+        staging_.assign(begin, end);
+        return staging_.data();
+    }
+    void run(const uint8_t* text, bool fast_resolval, unsigned k, const uint8_t* lut, bool want_lcp) {
+        ensure_engine();
+        local_SA.resize(n);
+        local_B.resize(n);
+        local_LCP.clear();
+        if (want_lcp) local_LCP.resize(n);
+        const unsigned flags = (want_lcp ? PSACB200_LCP : 0u) | (fast_resolval ? PSACB200_FAST_RESOLVAL : 0u);
+        void* lcp = want_lcp ? (void*)local_LCP.data() : nullptr;
+        if (lut)
+            check(psacb200_construct_alphabet(engine_, text, n, (int)sizeof(index_t), flags, k, lut, local_SA.data(), local_B.data(), lcp));
+        else
+            check(psacb200_construct(engine_, text, n, (int)sizeof(index_t), flags, k, local_SA.data(), local_B.data(), lcp));
+    }
+};
+
+}  // namespace psacb200
+#endif

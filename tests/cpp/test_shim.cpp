@@ -1,0 +1,71 @@
+// Exercises include/psacb200/suffix_array.hpp the way the reference's own tests use its class
+// (reference test/test_psac.cpp:101-129 "Mississippi", :131-176 "RandAll" construct / construct_arr).
+// Exit codes: 0 = all checks passed on a GPU; 3 = no CUDA device and the shim threw std::runtime_error as it must
+// (there is no CPU fallback); anything else = failure.
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "psacb200/suffix_array.hpp"
+
+static int fail(const char* what) {
+    std::fprintf(stderr, "FAIL: %s\n", what);
+    return 1;
+}
+
+int main() {
+    const std::string s = "mississippi";
+    const size_t golden[11] = {10, 7, 4, 1, 0, 9, 8, 6, 3, 5, 2};  // test_psac.cpp:105
+    try {
+        psacb200::comm c(0);
+        psacb200::suffix_array<char, uint64_t, true> sa(c);
+        sa.construct(s.begin(), s.end());
+        if (sa.n != 11 || sa.local_size != 11 || sa.p != 1) return fail("sizes");
+        for (size_t i = 0; i < 11; ++i)
+            if (sa.local_SA[i] != golden[i]) return fail("mississippi SA");
+        for (size_t i = 0; i < 11; ++i)
+            if (sa.local_B[sa.local_SA[i]] != i) return fail("ISA is not the inverse of SA");
+        const uint64_t lcp[11] = {0, 1, 1, 4, 0, 0, 1, 0, 2, 1, 3};
+        for (size_t i = 0; i < 11; ++i)
+            if (sa.local_LCP[i] != lcp[i]) return fail("mississippi LCP");
+        if (sa.alpha.sigma() != 4 || sa.alpha.bits_per_char() != 3 || sa.alpha.encode('i') != 1 || sa.alpha.encode('s') != 4) return fail("alphabet");
+
+        // repeated construct on one object with different k, like test_psac.cpp:148-171
+        std::vector<char> t(20000);
+        uint64_t x = 88172645463325252ull;
+        for (auto& ch : t) {
+            x ^= x << 13, x ^= x >> 7, x ^= x << 17;
+            ch = "ACGT"[x & 3];
+        }
+        psacb200::suffix_array<char, uint32_t, false> sb(c);
+        sb.construct(t.begin(), t.end());
+        std::vector<uint32_t> ref_sa = sb.local_SA;
+        sb.construct(t.begin(), t.end(), true, 3);
+        if (sb.local_SA != ref_sa) return fail("k=3 differs");
+        sb.construct(t.begin(), t.end(), false, 2);
+        if (sb.local_SA != ref_sa) return fail("fast_resolval=false, k=2 differs");
+        sb.construct_arr<3>(t.begin(), t.end());
+        if (sb.local_SA != ref_sa || !sb.local_LCP.empty()) return fail("construct_arr<3> differs");
+        for (size_t i = 1; i < t.size(); ++i) {  // order check on the text itself
+            const uint32_t a = ref_sa[i - 1], b = ref_sa[i];
+            const size_t la = t.size() - a, lb = t.size() - b, m = la < lb ? la : lb;
+            const int cmp = std::memcmp(t.data() + a, t.data() + b, m);
+            if (cmp > 0 || (cmp == 0 && la > lb)) return fail("SA not sorted");
+        }
+        // user-supplied alphabet overload (suffix_array.hpp:365-366)
+        psacb200::suffix_array<char, uint64_t, true> sc(c);
+        sc.construct(s.begin(), s.end(), true, sa.alpha, 2);
+        for (size_t i = 0; i < 11; ++i)
+            if (sc.local_SA[i] != golden[i] || sc.local_LCP[i] != lcp[i]) return fail("alphabet overload");
+    } catch (const std::runtime_error& e) {
+        if (std::strstr(e.what(), "no CUDA device") || std::strstr(e.what(), "CUDA")) {
+            std::fprintf(stderr, "no GPU: %s\n", e.what());
+            return 3;
+        }
+        std::fprintf(stderr, "unexpected error: %s\n", e.what());
+        return 2;
+    }
+    std::puts("shim ok");
+    return 0;
+}

@@ -52,3 +52,31 @@ def test_null_engine_is_an_error_not_a_crash():
     sa = np.zeros(4, np.uint32)
     rc = L.psacb200_construct(None, None, 0, 4, 0, 0, sa.ctypes.data_as(C.c_void_p), None, None)
     assert rc < 0 and b"null" in L.psacb200_last_error()
+
+
+def _build_cpp_shim_test(tmp_path):
+    import subprocess
+    exe = str(tmp_path / "test_shim")
+    subprocess.check_call(["g++", "-std=c++11", "-O1", "-Wall", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", "test_shim.cpp"),
+                           "-L", os.path.join(ROOT, "psac_b200"), "-lpsacb200", "-Wl,-rpath," + os.path.join(ROOT, "psac_b200"), "-o", exe])
+    return exe
+
+
+def test_cpp_shim_compiles_and_fails_loudly_without_gpu(tmp_path):
+    # include/psacb200/suffix_array.hpp: the C++ mirror of the reference class (reference tests: test/test_psac.cpp:101-176)
+    import subprocess
+    import torch
+    api.lib()
+    exe = _build_cpp_shim_test(tmp_path)
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: the shim's results are checked by the gpu-marked test")
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 3, r.stderr  # std::runtime_error("... no CUDA device ...") -- no CPU fallback
+
+
+@pytest.mark.gpu
+def test_cpp_shim_matches_reference_goldens_on_gpu(tmp_path):
+    import subprocess
+    exe = _build_cpp_shim_test(tmp_path)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
