@@ -91,6 +91,36 @@ __global__ void k(unsigned* out, unsigned seed, long long* cycles) {
             if ((f.x & lanemask_lt()) == 0) tabB[d2] = make_uint2(0u, f.y + __popc(f.x));
             acc += e.y + __popc(e.x & lanemask_lt()) + f.y + __popc(f.x & lanemask_lt());
             __syncwarp();
+        } else if (MODE == 10) {  // split tables: atomicOr mask[d] + LDS mask + LDS count + leader STS x2
+            unsigned* mask = &cnt[0][0] + (warp & 15) * 512;
+            unsigned* cn = mask + 256;
+            atomicOr(&mask[d], 1u << lane);
+            __syncwarp();
+            unsigned m = mask[d];
+            unsigned c = cn[d];
+            __syncwarp();
+            if ((m & lanemask_lt()) == 0) { mask[d] = 0u; cn[d] = c + __popc(m); }
+            acc += c + __popc(m & lanemask_lt());
+            __syncwarp();
+        } else if (MODE == 11) {  // ballots on 8 bits, peers only, then count via per-warp table packed 2x16 (one LDS + leader STS)
+            unsigned peers = 0xffffffffu;
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+                unsigned m = __ballot_sync(0xffffffffu, (d >> b) & 1);
+                peers &= ((d >> b) & 1) ? m : ~m;
+            }
+            unsigned short* tab16 = reinterpret_cast<unsigned short*>(&cnt[0][0]) + warp * 256;
+            unsigned before = tab16[d];
+            __syncwarp();
+            if ((peers & lanemask_lt()) == 0) tab16[d] = (unsigned short)(before + __popc(peers));
+            acc += before + __popc(peers & lanemask_lt());
+            __syncwarp();
+        } else if (MODE == 12) {  // unstable: CTA-wide table, atomicAdd with return
+            acc += atomicAdd(&cnt[0][d], 1u);
+        } else if (MODE == 13) {  // plain LDS gather + STS scatter with random digit index (cost of one table lookup)
+            unsigned c = cnt[warp][d];
+            acc += c;
+            cnt[warp][(d + lane) & 255] = c + 1;
         }
     }
     long long t1 = clock64();
@@ -130,6 +160,10 @@ int main() {
         run<7>("smem atomicAdd no return", 384, c);
         run<8>("rank: atomicOr table + LDS64 + STS64", 384, c);
         run<9>("rank: 2 chains of the above (2 keys/iter)", 256, c);
+        run<10>("rank: atomicOr split tables", 384, c);
+        run<11>("rank: ballots + u16 table", 384, c);
+        run<12>("unstable: CTA atomicAdd w/ return", 384, c);
+        run<13>("LDS gather + STS scatter", 384, c);
     }
     return 0;
 }
