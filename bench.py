@@ -8,8 +8,8 @@ N = 1 workload = BASELINE.json configs[1]: 1 GiB random DNA (|Sigma| = 4), SA-on
   value     : suffixes/s with the text already resident in HBM and the outputs left in HBM (psacb200_construct_device)
   e2e       : suffixes/s through the reference-facing C-ABI call with HOST (pinned) buffers -- H2D of the text and D2H
               of SA and ISA inside the timed region (psacb200_construct)
-  roofline  : dominant kernel = one radix digit pass of the first sort; algorithmic bytes per launch =
-              n * 2 * (8-byte key + 4-byte suffix index), see DESIGN.md
+  roofline  : dominant kernel = one radix digit pass of the first sort over the carried keys; algorithmic bytes per
+              launch = n * 2 * (4-byte carried key + 4-byte suffix index), see DESIGN.md
   cpu_baseline / --impl reference : the UNMODIFIED reference (oracle/_ref, MPI shim, np = 1 -> one core) on a bounded
               prefix of the same text
 Prints ONE JSON line on rank 0.
@@ -231,7 +231,10 @@ def main():
         return
 
     peak, peak_src = measured_peaks()
-    key_bytes, val_bytes = 8, stats["internal_index_bytes"]
+    # dominant kernel: one 8-bit digit pass over the carried keys (passes 2..P of the first sort); algorithmic bytes
+    # per launch = read + write of one carried key and one suffix index per suffix (DESIGN.md section "Kernels")
+    key_bytes = 4 if stats["key_chars"] * stats["pack_bits"] - 8 <= 32 else 8
+    val_bytes = stats["internal_index_bytes"]
     pass_bytes = float(n) * 2 * (key_bytes + val_bytes)
     pass_avg_ms = float(np.mean(pass_ms))
     achieved = pass_bytes / (pass_avg_ms * 1e-3) / 1e9 if pass_avg_ms > 0 else 0.0
@@ -240,11 +243,11 @@ def main():
         "warmup": max(args.warmup, 3), "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
         "data": "synthetic",
         "config": {"workload": workload, "n_per_gpu": n, "parallelism": "1 text per GPU" if world > 1 else "single GPU", "seed": SEED,
-                   "l2": "inputs_exceed_l2 (every pass streams >= 12 GiB)", "key_chars": stats["key_chars"], "sort_passes": stats["sort_passes"],
+                   "l2": "inputs_exceed_l2 (every pass streams >= 8 GiB)", "key_chars": stats["key_chars"], "sort_passes": stats["sort_passes"],
                    "rounds": stats["rounds"], "unresolved_after_first": stats["unresolved_after_first"], "verified": "ISA[SA[i]]==i on device"},
         "gpu_launches": launches,
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "onesweep_pass_kernel<u64,u32> (one 8-bit digit pass of the first sort)", "achieved": achieved,
+        "roofline": {"bound": "hbm", "kernel": "onesweep_pass_kernel<ArraySrc<u%d,u%d>> (one 8-bit digit pass of the first sort over the carried keys)" % (key_bytes * 8, val_bytes * 8), "achieved": achieved,
                      "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                      "bytes_per_launch": pass_bytes, "ms_per_launch": pass_avg_ms},
         "phases_ms": {k: round(v, 3) for k, v in sorted(phase.items())},

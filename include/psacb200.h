@@ -51,9 +51,11 @@ typedef struct psacb200_stats {
     uint64_t unresolved_after_first; /* suffixes still sharing a bucket after the first sort */
     uint64_t device_bytes;    /* device memory held by the engine */
     float ms_total;           /* device time of the whole call (CUDA events) */
-    float ms_h2d, ms_alphabet, ms_pack, ms_keygen, ms_hist, ms_sort, ms_resolve, ms_rounds, ms_output, ms_d2h;
-    float ms_sort_pass_avg;   /* average duration of one radix digit pass of the first sort */
-    float reserved_f[3];
+    float ms_h2d, ms_alphabet, ms_pack, ms_keygen /* 0: fused into digit pass 1 */, ms_hist, ms_sort, ms_resolve, ms_rounds, ms_output, ms_d2h;
+    float ms_sort_pass_avg;   /* average duration of one radix digit pass of the first sort, pass 1 excluded */
+    float ms_isa;             /* SA -> ISA permutation of the first round (partition pass + windowed scatter) */
+    float ms_sort_pass1;      /* digit pass 1 of the first sort (keys read from the packed text) */
+    float reserved_f[1];
 } psacb200_stats;
 
 /* ---- lifetime ---------------------------------------------------------------------------------------------- */

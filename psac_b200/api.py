@@ -48,7 +48,9 @@ class Stats(C.Structure):
         ("ms_output", C.c_float),
         ("ms_d2h", C.c_float),
         ("ms_sort_pass_avg", C.c_float),
-        ("reserved_f", C.c_float * 3),
+        ("ms_isa", C.c_float),
+        ("ms_sort_pass1", C.c_float),
+        ("reserved_f", C.c_float * 1),
     ]
 
     def as_dict(self):

@@ -72,6 +72,27 @@ __host__ __device__ __forceinline__ unsigned bits_for(u64 x) {  // number of bit
 static inline size_t div_up(size_t a, size_t b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t a, size_t b) { return div_up(a, b) * b; }
 
+// ---------------------------------------------------------------- packed text
+// The text is stored as a big-endian bit stream of dense codes, lbits in {1,2,4,8} per character, character i
+// at stream bits [i*lbits, (i+1)*lbits).  Word w holds characters [w*cpw, (w+1)*cpw), first character in the
+// most significant bits, zero past the end; the stream has two zero words of padding.
+struct CodeTable {
+    u8 code[256];
+};
+
+// nbits (1..64) stream bits starting at stream bit position `bit`, right-aligned
+__device__ __forceinline__ u64 stream_bits(const u64* __restrict__ stream, u64 bit, int nbits) {
+    const u64 w = bit >> 6;
+    const unsigned o = (unsigned)(bit & 63);
+    const u64 hi = __ldg(stream + w), lo = __ldg(stream + w + 1);
+    const u64 v = o ? ((hi << o) | (lo >> (64 - o))) : hi;
+    return v >> (64 - nbits);
+}
+// nbits (<= 64) stream bits starting at character position i, right-aligned
+__device__ __forceinline__ u64 stream_extract(const u64* __restrict__ stream, u64 i, int lbits, int nbits) {
+    return stream_bits(stream, i * (u64)lbits, nbits);
+}
+
 // ---------------------------------------------------------------- decoupled look-back channel
 // One u64 per tile: [63:10] payload (54 bits), [9:2] epoch, [1:0] state.  The epoch makes entries of a
 // previous use of the same buffer read as "not yet written" without a memset between uses.

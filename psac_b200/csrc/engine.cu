@@ -65,7 +65,7 @@ struct DevBuf {
     }
 };
 
-enum Phase { PH_H2D, PH_ALPHABET, PH_PACK, PH_KEYGEN, PH_HIST, PH_SORT, PH_RESOLVE, PH_ROUNDS, PH_OUTPUT, PH_D2H, PH_TOTAL, PH_COUNT };
+enum Phase { PH_H2D, PH_ALPHABET, PH_PACK, PH_HIST, PH_SORT, PH_RESOLVE, PH_ISA, PH_PASS1, PH_ROUNDS, PH_OUTPUT, PH_D2H, PH_TOTAL, PH_COUNT };
 
 }  // namespace
 
@@ -160,16 +160,16 @@ void dense_codes(const u64* hist, Alphabet& a) {
     a.lbits = d <= 2 ? 1 : d <= 4 ? 2 : d <= 16 ? 4 : 8;
 }
 
-template <typename IdxT>
+template <typename IdxT, typename KeyC>
 void launch_resolve(psacb200_engine* e, bool first, const ResolveArgs& A) {
     const u64 ntiles = div_up(A.m, (size_t)RES_TILE);
     PSAC_CUDA(cudaMemsetAsync(A.lb_max, 0, 2 * ntiles * sizeof(u64), e->stream));  // lb_sum follows lb_max
     PSAC_CUDA(cudaMemsetAsync(A.counts, 0, 2 * sizeof(u64), e->stream));
     PSAC_CUDA(cudaMemsetAsync(A.tile_counter, 0, sizeof(u32), e->stream));
     if (first)
-        resolve_kernel<IdxT, true><<<(unsigned)ntiles, RES_THREADS, 0, e->stream>>>(A);
+        resolve_kernel<IdxT, KeyC, true><<<(unsigned)ntiles, RES_THREADS, 0, e->stream>>>(A);
     else
-        resolve_kernel<IdxT, false><<<(unsigned)ntiles, RES_THREADS, 0, e->stream>>>(A);
+        resolve_kernel<IdxT, u64, false><<<(unsigned)ntiles, RES_THREADS, 0, e->stream>>>(A);
     e->launches += 1;
     PSAC_CUDA(cudaGetLastError());
 }
@@ -181,9 +181,10 @@ void read_counts(psacb200_engine* e, u64* m, u64* nb) {
     *nb = e->h_pinned[1];
 }
 
+// Moves an internal result array (IdxT) to the caller's buffer (index_bytes wide, host or device).
 template <typename SrcT>
 void emit(psacb200_engine* e, const SrcT* src, void* dst, u64 n, int index_bytes, bool dst_is_host) {
-    if (dst == nullptr) return;
+    if (dst == nullptr || (const void*)src == dst) return;
     if ((int)sizeof(SrcT) == index_bytes) {
         PSAC_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(SrcT), dst_is_host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, e->stream));
         return;
@@ -204,6 +205,7 @@ void emit(psacb200_engine* e, const SrcT* src, void* dst, u64 n, int index_bytes
     if (dst_is_host) PSAC_CUDA(cudaMemcpyAsync(dst, target, n * (size_t)index_bytes, cudaMemcpyDeviceToHost, e->stream));
 }
 
+// Number of characters in the first sort key.
 unsigned choose_key_chars(u64 n, int lbits, unsigned k) {
     const unsigned maxC = 64u / (unsigned)lbits;
     if (k != 0) {
@@ -211,101 +213,84 @@ unsigned choose_key_chars(u64 n, int lbits, unsigned k) {
         u64 c = 2ull * k;
         return (unsigned)std::max<u64>(1, std::min<u64>(c, maxC));
     }
-    // enough characters that random text leaves well under 1 % of the suffixes unresolved, rounded so that every
-    // 8-bit digit pass is fully used
-    unsigned want = bits_for(n) + 8;
-    unsigned nbits = std::min(64u, (want + 7u) / 8u * 8u);
-    return std::max(1u, nbits / (unsigned)lbits);
+    // Enough characters that random text leaves well under 1 % of the suffixes in shared buckets (n / 2^bits of them),
+    // in whole 8-bit digit passes; 40 bits is preferred while it does so because the keys carried after the first
+    // digit pass then fit 32 bits (radix_sort.cuh).
+    unsigned want = bits_for(n) + 7;
+    unsigned nbits = want <= 40 ? 40u : std::min(64u, (want + 7u) / 8u * 8u);
+    if (bits_for(n) <= 16) nbits = std::min(nbits, 32u);
+    return std::max(1u, std::min(maxC, nbits / (unsigned)lbits));
 }
 
+size_t lookback_bytes(u64 n) {
+    return std::max(RadixWorkspace::lookback_bytes_for(n), (size_t)(2 * div_up(n, (size_t)RES_TILE) * sizeof(u64)));
+}
+
+// Device buffers of one construction.  When the caller's outputs are device buffers of the engine's internal index
+// width they are used in place (final SA = the value buffer the last digit pass writes, ISA and LCP directly).
 template <typename IdxT>
-void reserve_buffers(psacb200_engine* e, u64 n, bool want_lcp) {
+void reserve_buffers(psacb200_engine* e, u64 n, size_t key_bytes, bool want_lcp, bool ext_sa, bool ext_isa, bool ext_lcp) {
     size_t* tot = &e->device_bytes;
     e->small.reserve(psacb200_engine::small_bytes(), tot);
     e->packed.reserve((n / 8 + 4) * sizeof(u64) + 64, tot);  // worst case 8 bits per character
-    for (int b = 0; b < 2; ++b) {
-        e->keys[b].reserve(n * sizeof(u64), tot);
-        e->vals[b].reserve(n * sizeof(IdxT), tot);
-    }
-    e->isa.reserve(n * sizeof(IdxT), tot);
-    if (want_lcp) e->lcp.reserve(n * sizeof(IdxT), tot);
-    size_t lb = std::max(RadixWorkspace::lookback_bytes_for<u64, IdxT>(n), (size_t)(2 * div_up(n, (size_t)RES_TILE) * sizeof(u64)));
-    e->lookback.reserve(lb, tot);
+    for (int b = 0; b < 2; ++b) e->keys[b].reserve(n * key_bytes, tot);
+    e->vals[0].reserve(n * sizeof(IdxT), tot);
+    if (!ext_sa) e->vals[1].reserve(n * sizeof(IdxT), tot);
+    if (!ext_isa) e->isa.reserve(n * sizeof(IdxT), tot);
+    if (want_lcp && !ext_lcp) e->lcp.reserve(n * sizeof(IdxT), tot);
+    e->lookback.reserve(lookback_bytes(n), tot);
 }
 
-template <typename IdxT>
-void construct_core(psacb200_engine* e, const u8* d_text, u64 n, int index_bytes, unsigned flags, unsigned k, const uint8_t* user_lut, void* sa_out,
-                    void* isa_out, void* lcp_out, bool out_is_host) {
+template <typename IdxT, typename KeyC>
+void construct_core(psacb200_engine* e, u64 n, int index_bytes, unsigned flags, const Alphabet& alpha, unsigned C, void* sa_out, void* isa_out,
+                    void* lcp_out, bool out_is_host) {
+    static_assert(sizeof(KeyC) >= sizeof(IdxT), "bucket ids are staged in a key buffer");
     const bool want_lcp = (flags & PSACB200_LCP) != 0;
     cudaStream_t st = e->stream;
     psacb200_stats& S = e->stats;
     S.internal_index_bytes = sizeof(IdxT);
-    reserve_buffers<IdxT>(e, n, want_lcp);
-
-    // ---- alphabet (a2)
-    e->begin(PH_ALPHABET);
-    PSAC_CUDA(cudaMemsetAsync(e->byte_hist(), 0, 256 * sizeof(u64), st));
-    byte_hist_kernel<<<grid_for(e, n / 16 + 1, 512, 4), 512, 0, st>>>(d_text, n, e->byte_hist());
-    e->launches += 1;
-    PSAC_CUDA(cudaGetLastError());
-    PSAC_CUDA(cudaMemcpyAsync(e->h_pinned + 16, e->byte_hist(), 256 * sizeof(u64), cudaMemcpyDeviceToHost, st));
-    e->end(PH_ALPHABET);
-    PSAC_CUDA(cudaStreamSynchronize(st));
-    Alphabet alpha;
-    alphabet_from_hist(e->h_pinned + 16, alpha);
-    if (user_lut) memcpy(alpha.lut, user_lut, 256);
-    dense_codes(e->h_pinned + 16, alpha);
-    S.sigma = alpha.sigma;
-    S.bits_per_char = alpha.ref_bits;
-    S.pack_bits = alpha.lbits;
     const int lbits = alpha.lbits;
+    const bool inplace = !out_is_host && index_bytes == (int)sizeof(IdxT);
+    const bool ext_sa = inplace, ext_isa = inplace && isa_out != nullptr, ext_lcp = inplace && want_lcp;
+    reserve_buffers<IdxT>(e, n, sizeof(KeyC), want_lcp, ext_sa, ext_isa, ext_lcp);
 
-    // ---- packed text
-    e->begin(PH_PACK);
-    const int cpw = 64 / lbits;
-    const size_t nwords = div_up(n, (size_t)cpw) + 2;
-    pack_text_kernel<<<grid_for(e, nwords, 256, 8), 256, 0, st>>>(d_text, n, alpha.dense, lbits, e->packed.as<u64>(), nwords);
-    e->launches += 1;
-    PSAC_CUDA(cudaGetLastError());
-    e->end(PH_PACK);
-
-    // ---- first key (a4) + sort (a6)
-    const unsigned C = choose_key_chars(n, lbits, k);
-    S.key_chars = C;
-    e->begin(PH_KEYGEN);
-    keygen_kernel<IdxT><<<grid_for(e, n, 256, 16), 256, 0, st>>>(e->packed.as<u64>(), n, lbits, (int)C, e->keys[0].as<u64>(), e->vals[0].as<IdxT>());
-    e->launches += 1;
-    PSAC_CUDA(cudaGetLastError());
-    e->end(PH_KEYGEN);
-
-    RadixPlan plan;
+    // ---- first sort (a4 + a6): digit pass 1 reads the packed text, the others the carried keys
+    const RadixPlan plan = make_radix_plan(0, (int)C * lbits);
+    const int fin = (plan.npass - 1) & 1;  // buffer index the last pass writes
+    KeyC* kbuf[2] = {e->keys[0].as<KeyC>(), e->keys[1].as<KeyC>()};
+    IdxT* vbuf[2];
+    vbuf[fin] = ext_sa ? reinterpret_cast<IdxT*>(sa_out) : e->vals[1].as<IdxT>();
+    vbuf[1 - fin] = e->vals[0].as<IdxT>();
     uint64_t sort_launches = 0;
+    RadixPlan plan_used;
     e->begin(PH_HIST);
-    const bool in_alt = radix_sort_pairs<u64, IdxT>(e->radix_ws(), e->keys[0].as<u64>(), e->keys[1].as<u64>(), e->vals[0].as<IdxT>(),
-                                                   e->vals[1].as<IdxT>(), n, 0, (int)(C * lbits), st, e->sm_count, &plan, &sort_launches,
-                                                   e->ev_end[PH_HIST], e->ev_begin[PH_SORT]);
+    const int x = radix_sort_suffixes<KeyC, IdxT>(e->radix_ws(), e->packed.as<u64>(), n, lbits, (int)C, kbuf, vbuf, st, e->sm_count, &plan_used,
+                                                  &sort_launches, e->ev_end[PH_HIST], e->ev_begin[PH_SORT], e->ev_end[PH_PASS1]);
     e->ev_used[PH_SORT] = true;
     e->end(PH_SORT);
     e->launches += sort_launches;
-    S.sort_passes = plan.npass;
-    const int x = in_alt ? 1 : 0, y = 1 - x;
-    IdxT* SA = e->vals[x].as<IdxT>();
-    IdxT* ISA = e->isa.as<IdxT>();
-    IdxT* LCP = want_lcp ? e->lcp.as<IdxT>() : nullptr;
+    S.sort_passes = plan_used.npass;
+    const int y = 1 - x;
+    IdxT* SA = vbuf[x];
+    IdxT* ISA = ext_isa ? reinterpret_cast<IdxT*>(isa_out) : e->isa.as<IdxT>();
+    IdxT* LCP = want_lcp ? (ext_lcp ? reinterpret_cast<IdxT*>(lcp_out) : e->lcp.as<IdxT>()) : nullptr;
 
-    // ---- resolve round 0 (a7, a9, a10)
+    // ---- resolve round 0 (a7, a9): bucket ids, LCP, count of unresolved suffixes
+    const bool partitioned = n >= (1ull << 23);  // below that the ISA fits L2 many times over: scatter directly
+    IdxT* bucket = reinterpret_cast<IdxT*>(kbuf[y]);
     e->begin(PH_RESOLVE);
     ResolveArgs R{};
-    R.keys = e->keys[x].as<u64>();
+    R.keys = kbuf[x];
     R.vals = SA;
     R.pos_in = nullptr;
     R.m = n;
     R.n = n;
     R.sa = SA;
-    R.isa = ISA;
+    R.isa = partitioned ? nullptr : ISA;
+    R.bucket_out = bucket;
     R.lcp = LCP;
-    R.pos_out = e->vals[y].p;
-    R.head_out = e->keys[y].as<u8>();
+    R.pos_out = nullptr;
+    R.head_out = nullptr;
     R.counts = e->counts();
     R.lb_max = e->lookback.as<u64>();
     R.lb_sum = R.lb_max + div_up(n, (size_t)RES_TILE);
@@ -313,19 +298,19 @@ void construct_core(psacb200_engine* e, const u8* d_text, u64 n, int index_bytes
     R.stream = e->packed.as<u64>();
     R.lbits = lbits;
     R.C = (int)C;
+    R.drop = plan_used.bits[0];
     R.kbits = 0;
     R.h = 0;
     R.padded_lcp = alpha.zero_code_used ? 1 : 0;
-    launch_resolve<IdxT>(e, true, R);
+    launch_resolve<IdxT, KeyC>(e, true, R);
     e->end(PH_RESOLVE);
     u64 m = 0, nb = 0;
     read_counts(e, &m, &nb);
     S.unresolved_after_first = m;
     S.rounds = 1;
 
-    // ---- later rounds on the unresolved suffixes only (a5, a6, a8, a9, a10, a12)
+    // ---- list the unresolved suffixes (positions + head flags) for the later rounds
     if (m > 0) {
-        e->begin(PH_ROUNDS);
         size_t* tot = &e->device_bytes;
         for (int b = 0; b < 2; ++b) {
             e->rk[b].reserve(m * sizeof(u64), tot);
@@ -333,8 +318,41 @@ void construct_core(psacb200_engine* e, const u8* d_text, u64 n, int index_bytes
             e->rp[b].reserve(m * sizeof(IdxT), tot);
             e->rh[b].reserve(m, tot);
         }
-        const void* pos_in = e->vals[y].p;
-        const u8* head_in = e->keys[y].as<u8>();
+        const u64 ntiles = div_up(n, (size_t)RES_TILE);
+        PSAC_CUDA(cudaMemsetAsync(e->lookback.p, 0, ntiles * sizeof(u64), st));
+        PSAC_CUDA(cudaMemsetAsync(e->counters() + 18, 0, sizeof(u32), st));
+        compact_first_kernel<IdxT><<<(unsigned)ntiles, RES_THREADS, 0, st>>>(bucket, n, e->rp[1].as<IdxT>(), e->rh[1].as<u8>(), e->lookback.as<u64>(),
+                                                                             e->counters() + 18);
+        e->launches += 1;
+        PSAC_CUDA(cudaGetLastError());
+    }
+
+    // ---- SA -> ISA (a10): partition the (suffix, bucket) pairs by ISA window, then scatter window by window
+    e->begin(PH_ISA);
+    if (partitioned) {
+        const int nbits = (int)bits_for(n - 1);
+        const int shift = nbits > RADIX_BITS ? nbits - RADIX_BITS : 0;
+        RadixWorkspace ws = e->radix_ws();
+        u64* gb = ws.gbase + (MAX_PASSES - 1) * RADIX;
+        u32* ctr = ws.counters + (MAX_PASSES - 1);
+        perm_gbase_kernel<<<1, RADIX, 0, st>>>(n, shift, gb);
+        PSAC_CUDA(cudaMemsetAsync(ctr, 0, sizeof(u32), st));
+        PSAC_CUDA(cudaMemsetAsync(ws.lookback, 0, RadixWorkspace::lookback_bytes_for(n), st));
+        IdxT* part_suffix = vbuf[y];
+        IdxT* part_bucket = reinterpret_cast<IdxT*>(kbuf[x]);  // the sorted keys are dead after resolve
+        ArraySrc<IdxT, IdxT> src{SA, bucket, shift, (u32)(RADIX - 1)};
+        launch_pass<ArraySrc<IdxT, IdxT>, IdxT>(ws, src, part_suffix, part_bucket, n, gb, ctr, 1u, st);
+        isa_scatter_kernel<IdxT><<<(unsigned)div_up(n, (size_t)4096), 256, 0, st>>>(part_suffix, part_bucket, ISA, n);
+        e->launches += 3;
+        PSAC_CUDA(cudaGetLastError());
+    }
+    e->end(PH_ISA);
+
+    // ---- later rounds on the unresolved suffixes only (a5, a6, a8, a9, a10, a12)
+    if (m > 0) {
+        e->begin(PH_ROUNDS);
+        const void* pos_in = e->rp[1].p;
+        const u8* head_in = e->rh[1].as<u8>();
         const int kbits = (int)bits_for(n);
         u64 h = C;
         int t = 0;
@@ -365,16 +383,19 @@ void construct_core(psacb200_engine* e, const u8* d_text, u64 n, int index_bytes
                                                         e->rv[1].as<IdxT>(), m, 0, kbits + mbits, st, e->sm_count, nullptr, &sl);
             e->launches += sl;
             ResolveArgs Q = R;
-            Q.keys = e->rk[alt ? 1 : 0].as<u64>();
+            Q.keys = e->rk[alt ? 1 : 0].p;
             Q.vals = e->rv[alt ? 1 : 0].p;
             Q.pos_in = pos_in;
             Q.m = m;
+            Q.isa = ISA;
+            Q.bucket_out = nullptr;
             Q.pos_out = e->rp[t].p;
             Q.head_out = e->rh[t].as<u8>();
             Q.lb_sum = Q.lb_max + ntiles;
+            Q.drop = 0;
             Q.kbits = kbits;
             Q.h = h;
-            launch_resolve<IdxT>(e, false, Q);
+            launch_resolve<IdxT, u64>(e, false, Q);
             read_counts(e, &m, &nb);
             pos_in = e->rp[t].p;
             head_in = e->rh[t].as<u8>();
@@ -392,6 +413,35 @@ void construct_core(psacb200_engine* e, const u8* d_text, u64 n, int index_bytes
     emit<IdxT>(e, ISA, isa_out, n, index_bytes, out_is_host);
     if (want_lcp) emit<IdxT>(e, LCP, lcp_out, n, index_bytes, out_is_host);
     e->end(out_is_host ? PH_D2H : PH_OUTPUT);
+}
+
+// alphabet (a2) + packed text; synchronises once to read the 256-bin histogram
+void prepare_text(psacb200_engine* e, const u8* d_text, u64 n, const uint8_t* user_lut, Alphabet& alpha) {
+    cudaStream_t st = e->stream;
+    size_t* tot = &e->device_bytes;
+    e->small.reserve(psacb200_engine::small_bytes(), tot);
+    e->packed.reserve((n / 8 + 4) * sizeof(u64) + 64, tot);
+    e->begin(PH_ALPHABET);
+    PSAC_CUDA(cudaMemsetAsync(e->byte_hist(), 0, 256 * sizeof(u64), st));
+    byte_hist_kernel<<<grid_for(e, n / 16 + 1, 512, 4), 512, 0, st>>>(d_text, n, e->byte_hist());
+    e->launches += 1;
+    PSAC_CUDA(cudaGetLastError());
+    PSAC_CUDA(cudaMemcpyAsync(e->h_pinned + 16, e->byte_hist(), 256 * sizeof(u64), cudaMemcpyDeviceToHost, st));
+    e->end(PH_ALPHABET);
+    PSAC_CUDA(cudaStreamSynchronize(st));
+    alphabet_from_hist(e->h_pinned + 16, alpha);
+    if (user_lut) memcpy(alpha.lut, user_lut, 256);
+    dense_codes(e->h_pinned + 16, alpha);
+    e->stats.sigma = alpha.sigma;
+    e->stats.bits_per_char = alpha.ref_bits;
+    e->stats.pack_bits = alpha.lbits;
+    e->begin(PH_PACK);
+    const int cpw = 64 / alpha.lbits;
+    const size_t nwords = div_up(n, (size_t)cpw) + 2;
+    pack_text_kernel<<<grid_for(e, nwords, 256, 8), 256, 0, st>>>(d_text, n, alpha.dense, alpha.lbits, e->packed.as<u64>(), nwords);
+    e->launches += 1;
+    PSAC_CUDA(cudaGetLastError());
+    e->end(PH_PACK);
 }
 
 int construct_entry(psacb200_engine* e, const u8* text, bool text_is_host, size_t n, int index_bytes, unsigned flags, unsigned k, const uint8_t* lut,
@@ -420,10 +470,19 @@ int construct_entry(psacb200_engine* e, const u8* text, bool text_is_host, size_
             e->end(PH_H2D);
             d_text = e->text.as<u8>();
         }
-        if ((u64)n <= (1ull << 32))
-            construct_core<u32>(e, d_text, n, index_bytes, flags, k, lut, sa_out, isa_out, lcp_out, text_is_host);
-        else
-            construct_core<u64>(e, d_text, n, index_bytes, flags, k, lut, sa_out, isa_out, lcp_out, text_is_host);
+        Alphabet alpha;
+        prepare_text(e, d_text, n, lut, alpha);
+        const unsigned C = choose_key_chars(n, alpha.lbits, k);
+        e->stats.key_chars = C;
+        const int carried_bits = (int)C * alpha.lbits - make_radix_plan(0, (int)C * alpha.lbits).bits[0];
+        if ((u64)n <= (1ull << 32)) {
+            if (carried_bits <= 32)
+                construct_core<u32, u32>(e, n, index_bytes, flags, alpha, C, sa_out, isa_out, lcp_out, text_is_host);
+            else
+                construct_core<u32, u64>(e, n, index_bytes, flags, alpha, C, sa_out, isa_out, lcp_out, text_is_host);
+        } else {
+            construct_core<u64, u64>(e, n, index_bytes, flags, alpha, C, sa_out, isa_out, lcp_out, text_is_host);
+        }
         e->end(PH_TOTAL);
         PSAC_CUDA(cudaStreamSynchronize(e->stream));
         psacb200_stats& S = e->stats;
@@ -432,14 +491,20 @@ int construct_entry(psacb200_engine* e, const u8* text, bool text_is_host, size_
         S.ms_h2d = e->ms(PH_H2D);
         S.ms_alphabet = e->ms(PH_ALPHABET);
         S.ms_pack = e->ms(PH_PACK);
-        S.ms_keygen = e->ms(PH_KEYGEN);
+        S.ms_keygen = 0.f;  // the first key is generated inside digit pass 1
+        S.ms_isa = e->ms(PH_ISA);
+        {
+            float t1 = 0.f;  // digit pass 1 (reads the packed text) runs from the start of PH_SORT to ev_end[PH_PASS1]
+            if (e->ev_used[PH_SORT] && cudaEventElapsedTime(&t1, e->ev_begin[PH_SORT], e->ev_end[PH_PASS1]) == cudaSuccess) S.ms_sort_pass1 = t1;
+            else cudaGetLastError();
+        }
         S.ms_hist = e->ms(PH_HIST);
         S.ms_sort = e->ms(PH_SORT);
         S.ms_resolve = e->ms(PH_RESOLVE);
         S.ms_rounds = e->ms(PH_ROUNDS);
         S.ms_output = e->ms(PH_OUTPUT);
         S.ms_d2h = e->ms(PH_D2H);
-        S.ms_sort_pass_avg = S.sort_passes ? S.ms_sort / (float)S.sort_passes : 0.f;
+        S.ms_sort_pass_avg = S.sort_passes > 1 ? (S.ms_sort - S.ms_sort_pass1) / (float)(S.sort_passes - 1) : S.ms_sort;
         return PSACB200_OK;
     } catch (const cuda_failure& f) {
         set_last_error(std::string("CUDA error: ") + cudaGetErrorString(f.err) + " in " + f.what + " at " + f.file + ":" + std::to_string(f.line));
@@ -527,6 +592,20 @@ int psacb200_create(int device, psacb200_engine** out) {
         }
         memset(&e->stats, 0, sizeof(e->stats));
         e->small.reserve(psacb200_engine::small_bytes(), &e->device_bytes);
+        // hardware self-test of the ranking assumption of the radix passes (radix_sort.cuh): refuse to run if it fails
+        unsigned long long* bad = reinterpret_cast<unsigned long long*>(e->counts());
+        PSAC_CUDA(cudaMemsetAsync(bad, 0, sizeof(u64), e->stream));
+        atoms_order_selftest_kernel<16><<<e->sm_count, 384, 0, e->stream>>>(1u, 256u, bad);
+        atoms_order_selftest_kernel<16><<<e->sm_count, 384, 0, e->stream>>>(2u, 5u, bad);
+        e->launches += 2;
+        PSAC_CUDA(cudaMemcpyAsync(e->h_pinned, bad, sizeof(u64), cudaMemcpyDeviceToHost, e->stream));
+        PSAC_CUDA(cudaStreamSynchronize(e->stream));
+        if (e->h_pinned[0] != 0) {
+            const u64 nbad = e->h_pinned[0];
+            psacb200_destroy(e);
+            throw std::string("hardware self-test failed: shared-memory atomics of a warp are not applied in lane order (") + std::to_string(nbad) +
+                " mismatches); the radix ranking of this build is not valid on this device";
+        }
         *out = e;
         return PSACB200_OK;
     });
@@ -568,11 +647,12 @@ int psacb200_reserve(psacb200_engine* e, size_t n, int index_bytes, unsigned fla
     }
     return guarded([&]() -> int {
         PSAC_CUDA(cudaSetDevice(e->device));
+        // sized for the automatic key length (k = 0) and host outputs (the superset of the device-output case)
         const bool lcp = (flags & PSACB200_LCP) != 0;
         if ((u64)n <= (1ull << 32))
-            reserve_buffers<u32>(e, n, lcp);
+            reserve_buffers<u32>(e, n, sizeof(u32), lcp, false, false, false);
         else
-            reserve_buffers<u64>(e, n, lcp);
+            reserve_buffers<u64>(e, n, sizeof(u64), lcp, false, false, false);
         e->text.reserve(n + 64, &e->device_bytes);
         if ((u64)n <= (1ull << 32) && index_bytes == 8) e->scratch.reserve(n * 8, &e->device_bytes);
         return PSACB200_OK;

@@ -2,12 +2,24 @@
 // prefix-doubling loop (reference: include/idxsort.hpp:22-83 -> mxx::sort).
 //
 // Design (B200-first, not the reference's comparison sample sort):
-//   * one up-front histogram kernel counts every digit of every pass in a single read of the keys;
-//   * one kernel per 8-bit digit.  A CTA owns a tile, ranks its keys per digit with warp-level
-//     match_any multi-split (stable), resolves its global bin offsets with a decoupled look-back over
-//     256 per-digit channels (no second pass over the data, no grid-wide sync) and writes the tile
-//     out through shared memory so each bin's run leaves as one coalesced burst;
-//   * algorithmic HBM traffic per pass = read + write of every key and value once.
+//   * one up-front histogram kernel counts every digit of every pass in a single read of the keys (or, for the
+//     first sort of a construction, of the packed text: the keys are never materialised before the first pass);
+//   * one kernel per 8-bit digit.  A CTA owns a tile, ranks its keys with ONE shared-memory atomic per key
+//     (see "ranking" below), resolves its global bin offsets with a decoupled look-back over 256 per-digit
+//     channels (no second pass over the data, no grid-wide sync) and writes the tile out through shared
+//     memory so each bin's run leaves as one coalesced burst;
+//   * the first pass of a construction reads the packed text instead of a key array and drops the digit it
+//     consumed, so the keys carried through the remaining passes are 32 bits wide whenever the sort key has
+//     <= 40 bits (BASELINE configs[1]: 20 DNA characters);
+//   * algorithmic HBM traffic per pass = read + write of every carried key and value once.
+//
+// Ranking.  A stable rank needs, for every key, the number of earlier keys of the tile with the same digit.
+// On sm_100a the lanes of one ATOMS.ADD warp instruction that hit the same shared-memory word are applied in
+// ascending lane order, and successive ATOMS of a warp are applied in program order (profiles/r1_atoms_order.txt:
+// 0 mismatches in 3.2e9 atomics; re-verified by atoms_order_selftest at every engine creation).  So with one
+// 256-entry counter table per warp and warp-striped items, the value returned by atomicAdd(&tab[warp][digit], 1)
+// IS the key's stable rank inside its warp.  That is 2.6 cycles per warp instruction per SM against 13.4 for
+// the atomicOr match-table sequence it replaces and 47-62 for match.any (profiles/r1_micro_rank.txt).
 #pragma once
 #include <type_traits>
 
@@ -88,6 +100,29 @@ __global__ void __launch_bounds__(512) radix_hist_kernel(const KeyT* __restrict_
     hist_flush(sh, plan, ghist);
 }
 
+// Same histogram with the keys read straight from the packed text: key(i) = the kbits stream bits starting at
+// character i.  One thread walks the characters of one 64-bit stream word with a two-word window.
+__global__ void __launch_bounds__(512) text_hist_kernel(const u64* __restrict__ stream, size_t n, int lbits, int kbits, RadixPlan plan,
+                                                        u64* __restrict__ ghist) {
+    __shared__ u32 sh[MAX_PASSES][RADIX];
+    for (int e = threadIdx.x; e < MAX_PASSES * RADIX; e += blockDim.x) (&sh[0][0])[e] = 0;
+    __syncthreads();
+    const int cpw = 64 / lbits;
+    const size_t nwords = (n + cpw - 1) / cpw;
+    for (size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x; w < nwords; w += (size_t)gridDim.x * blockDim.x) {
+        const u64 hi = __ldg(stream + w), lo = __ldg(stream + w + 1);
+        const size_t c0 = w * (size_t)cpw;
+        const int cnt = (n - c0 < (size_t)cpw) ? (int)(n - c0) : cpw;
+        for (int c = 0; c < cnt; ++c) {
+            const int o = c * lbits;
+            const u64 v = o ? ((hi << o) | (lo >> (64 - o))) : hi;
+            hist_accumulate<u64>(sh, plan, v >> (64 - kbits));
+        }
+    }
+    __syncthreads();
+    hist_flush(sh, plan, ghist);
+}
+
 // exclusive scan of each pass's 256-bin histogram; one CTA of 256 threads per pass
 __global__ void __launch_bounds__(RADIX) radix_scan_hist_kernel(const u64* __restrict__ ghist, u64* __restrict__ gbase) {
     __shared__ u64 wtot[RADIX / 32];
@@ -101,59 +136,100 @@ __global__ void __launch_bounds__(RADIX) radix_scan_hist_kernel(const u64* __res
     gbase[p * RADIX + d] = pre + inc - c;
 }
 
+// bin bases of a pass over the digit bits [shift, shift+8) of a PERMUTATION of 0..n-1 (the SA -> ISA partition):
+// the histogram is known without reading anything
+__global__ void __launch_bounds__(RADIX) perm_gbase_kernel(u64 n, int shift, u64* __restrict__ gbase) {
+    const u64 lo = (u64)threadIdx.x << shift;
+    gbase[threadIdx.x] = lo < n ? lo : n;
+}
+
+// ------------------------------------------------------------------ key sources of a pass
+// A source provides the staged key of global element g, its digit, the key to write out, and the value.
+template <typename KeyT, typename ValT>
+struct ArraySrc {
+    using Stage = KeyT;
+    using Out = KeyT;
+    const KeyT* __restrict__ kin;
+    const ValT* __restrict__ vin;
+    int shift;
+    u32 mask;
+    __device__ __forceinline__ Stage load_key(size_t g) const { return ld_stream(kin + g); }
+    __device__ __forceinline__ u32 digit(Stage k) const { return (u32)(k >> shift) & mask; }
+    __device__ __forceinline__ Out out_key(Stage k) const { return k; }
+    __device__ __forceinline__ ValT load_val(size_t g) const { return ld_stream(vin + g); }
+};
+
+// First pass of a construction (reference a4 k-mer generation, include/kmer.hpp:119-224, fused into the sort):
+// element g is suffix idx(g); its key is the first kbits stream bits of that suffix; the digit is the low `drop` bits
+// and the key carried on is the rest.  Initial order: the T = min(n, C-1) suffixes that run past the end of the text
+// come FIRST, shortest first, then suffixes 0..n-T-1.  The sort is stable, so among equal keys the suffixes that hit
+// the end sort in front and by increasing length -- exactly the order the reference obtains from its 0 sentinel code
+// (include/alphabet.hpp:157-164: code 0 is reserved for "past the end").
+template <typename OutKeyT, typename IdxT>
+struct TextSrc {
+    using Stage = u64;
+    using Out = OutKeyT;
+    const u64* __restrict__ stream;
+    u64 n, T;
+    int lbits, kbits, drop;
+    u32 mask;
+    __device__ __forceinline__ u64 idx(size_t g) const { return (g < T) ? (n - 1 - g) : (g - T); }
+    __device__ __forceinline__ Stage load_key(size_t g) const { return stream_extract(stream, idx(g), lbits, kbits); }
+    __device__ __forceinline__ u32 digit(Stage k) const { return (u32)k & mask; }
+    __device__ __forceinline__ Out out_key(Stage k) const { return (Out)(k >> drop); }
+    __device__ __forceinline__ IdxT load_val(size_t g) const { return (IdxT)idx(g); }
+};
+
 // ------------------------------------------------------------------ one digit pass
-// Shared memory layout of a pass CTA: [tile staging: TILE * max(sizeof key, sizeof value)] [per-warp rank table:
-// NW * 256 * {match mask, running position}] [bin_start 256 * u32] [goff 256 * u64] [misc].
-template <typename KeyT, typename ValT, int THREADS_, int ITEMS_>
+// Shared memory layout of a pass CTA: [tile staging: TILE * max(sizeof staged key, sizeof value)] [per-warp counter
+// tables NW * 256 * u32] [bin_start 256 * u32] [goff 256 * u64] [misc].
+template <typename StageT, typename ValT, int THREADS_, int ITEMS_>
 struct PassCfg {
     static constexpr int THREADS = THREADS_;
     static constexpr int ITEMS = ITEMS_;
     static constexpr int TILE = THREADS * ITEMS;
     static constexpr int NW = THREADS / 32;
     static constexpr bool HAS_VALS = !std::is_same<ValT, NoVal>::value;
-    static constexpr size_t ELT = (HAS_VALS && sizeof(ValT) > sizeof(KeyT)) ? sizeof(ValT) : sizeof(KeyT);
+    static constexpr size_t ELT = (HAS_VALS && sizeof(ValT) > sizeof(StageT)) ? sizeof(ValT) : sizeof(StageT);
     static constexpr size_t OFF_TAB = (size_t)TILE * ELT;
-    static constexpr size_t OFF_BIN = OFF_TAB + (size_t)NW * RADIX * 8;
+    static constexpr size_t OFF_BIN = OFF_TAB + (size_t)NW * RADIX * 4;
     static constexpr size_t OFF_GOFF = OFF_BIN + RADIX * 4;
     static constexpr size_t OFF_MISC = OFF_GOFF + RADIX * 8;
     static constexpr size_t SMEM = OFF_MISC + 64;
 };
 
-// Stable ranking of the warp's keys by digit.  match.any costs ~50 cycles per warp instruction per SM on B200
-// (measured, tools/micro_rank.cu) -- more than the whole HBM budget of a key -- so peers are found through a
-// shared-memory table instead: every lane ORs its lane bit into mask[d]; one 64-bit read returns {peers, running
-// position}; the lowest peer clears the mask and advances the position (~13 cycles per warp instruction).
-template <typename KeyT, typename ValT, int THREADS, int ITEMS, bool FULL>
-__device__ __forceinline__ void onesweep_tile(unsigned char* smem_raw, const KeyT* __restrict__ kin, KeyT* __restrict__ kout,
-                                              const ValT* __restrict__ vin, ValT* __restrict__ vout, const size_t base, const int valid,
-                                              const int shift, const u32 mask, const u64* __restrict__ gbase, u64* __restrict__ lookback,
+template <class Src, typename ValT, int THREADS, int ITEMS, bool FULL>
+__device__ __forceinline__ void onesweep_tile(unsigned char* smem_raw, const Src& src, typename Src::Out* __restrict__ kout, ValT* __restrict__ vout,
+                                              const size_t base, const int valid, const u64* __restrict__ gbase, u64* __restrict__ lookback,
                                               const size_t tile, const u32 epoch) {
-    using Cfg = PassCfg<KeyT, ValT, THREADS, ITEMS>;
+    using Stage = typename Src::Stage;
+    using Cfg = PassCfg<Stage, ValT, THREADS, ITEMS>;
     constexpr int NW = Cfg::NW;
-    KeyT* skeys = reinterpret_cast<KeyT*>(smem_raw);
-    uint2* tab = reinterpret_cast<uint2*>(smem_raw + Cfg::OFF_TAB);  // [NW][RADIX] {x: match mask, y: count / position}
+    Stage* skeys = reinterpret_cast<Stage*>(smem_raw);
+    u32* tab = reinterpret_cast<u32*>(smem_raw + Cfg::OFF_TAB);  // [NW][RADIX] running counters, later warp bases
     u32* bin_start = reinterpret_cast<u32*>(smem_raw + Cfg::OFF_BIN);
     u64* goff = reinterpret_cast<u64*>(smem_raw + Cfg::OFF_GOFF);
     u32* misc = reinterpret_cast<u32*>(smem_raw + Cfg::OFF_MISC);  // [1..8] warp totals of the digit scan
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int woff = warp * 32 * ITEMS + lane;
-    uint2* mytab = tab + warp * RADIX;
-    const u32 lane_bit = 1u << lane;
-    const u32 lt = lanemask_lt();
+    u32* mytab = tab + warp * RADIX;
 
-    // ---- load keys (and values), warp-striped: item j of lane l is tile element warp*32*ITEMS + j*32 + l
-    KeyT key[ITEMS];
+    // ---- load keys, warp-striped: item j of lane l is tile element warp*32*ITEMS + j*32 + l
+    Stage key[ITEMS];
 #pragma unroll
     for (int j = 0; j < ITEMS; ++j) {
         const int o = woff + j * 32;
-        key[j] = (FULL || o < valid) ? ld_stream(kin + base + o) : (KeyT)0;
+        key[j] = (FULL || o < valid) ? src.load_key(base + o) : (Stage)0;
     }
 
-    // ---- early counts: per-warp digit histogram with fire-and-forget shared atomics
+    // ---- stable rank inside the warp: one ATOMS.ADD per key (lanes of one instruction apply in ascending lane order,
+    //      instructions of a warp in program order -- see the header comment)
+    u32 pos[ITEMS];
 #pragma unroll
     for (int j = 0; j < ITEMS; ++j) {
-        if (FULL || (woff + j * 32) < valid) atomicAdd(&mytab[(u32)(key[j] >> shift) & mask].y, 1u);
+        pos[j] = 0;
+        if (FULL || (woff + j * 32) < valid) pos[j] = atomicAdd(&mytab[src.digit(key[j])], 1u);
     }
     __syncthreads();
 
@@ -162,8 +238,8 @@ __device__ __forceinline__ void onesweep_tile(unsigned char* smem_raw, const Key
     if (tid < RADIX) {
 #pragma unroll
         for (int w = 0; w < NW; ++w) {
-            const u32 c = tab[w * RADIX + tid].y;
-            tab[w * RADIX + tid].y = count;
+            const u32 c = tab[w * RADIX + tid];
+            tab[w * RADIX + tid] = count;
             count += c;
         }
         if (tile > 0) st_relaxed(lookback + tile * RADIX + tid, lb_pack((u64)count, epoch, LB_AGGREGATE));
@@ -178,24 +254,9 @@ __device__ __forceinline__ void onesweep_tile(unsigned char* smem_raw, const Key
         const u32 bstart = pre + inc - count;
         bin_start[tid] = bstart;
 #pragma unroll
-        for (int w = 0; w < NW; ++w) tab[w * RADIX + tid].y += bstart;  // position of the warp's first key of this digit
+        for (int w = 0; w < NW; ++w) tab[w * RADIX + tid] += bstart;  // position of the warp's first key of this digit
     }
     __syncthreads();
-
-    // ---- stable ranking -> final position of every key inside the tile
-    u16 pos[ITEMS];
-#pragma unroll
-    for (int j = 0; j < ITEMS; ++j) {
-        const bool ok = FULL || (woff + j * 32) < valid;
-        const u32 d = (u32)(key[j] >> shift) & mask;
-        if (ok) atomicOr(&mytab[d].x, lane_bit);
-        __syncwarp();
-        const uint2 e = mytab[d];
-        __syncwarp();
-        if (ok && (e.x & lt) == 0) mytab[d] = make_uint2(0u, e.y + __popc(e.x));
-        pos[j] = (u16)(e.y + __popc(e.x & lt));
-        __syncwarp();
-    }
 
     // values: issue the global loads now, they overlap the key scatter, the look-back and the key write-out
     ValT val[Cfg::HAS_VALS ? ITEMS : 1];
@@ -203,14 +264,17 @@ __device__ __forceinline__ void onesweep_tile(unsigned char* smem_raw, const Key
 #pragma unroll
         for (int j = 0; j < ITEMS; ++j) {
             const int o = woff + j * 32;
-            if (FULL || o < valid) val[j] = ld_stream(vin + base + o);
+            if (FULL || o < valid) val[j] = src.load_val(base + o);
         }
     }
 
-    // ---- scatter keys into shared memory in bin order (tile staging is free: keys live in registers)
+    // ---- final position inside the tile, then scatter the keys into shared memory in bin order
 #pragma unroll
     for (int j = 0; j < ITEMS; ++j) {
-        if (FULL || (woff + j * 32) < valid) skeys[pos[j]] = key[j];
+        if (FULL || (woff + j * 32) < valid) {
+            pos[j] += mytab[src.digit(key[j])];
+            skeys[pos[j]] = key[j];
+        }
     }
 
     // ---- decoupled look-back, one channel per digit; the predecessors published their counts long ago
@@ -242,10 +306,10 @@ __device__ __forceinline__ void onesweep_tile(unsigned char* smem_raw, const Key
     for (int i = 0; i < ITEMS; ++i) {
         const int s = i * THREADS + tid;
         if (FULL || s < valid) {
-            const KeyT k = skeys[s];
-            const u32 d = (u32)(k >> shift) & mask;
+            const Stage k = skeys[s];
+            const u32 d = src.digit(k);
             dig[i] = (u8)d;
-            kout[goff[d] + (u64)s] = k;
+            st_stream(kout + goff[d] + (u64)s, src.out_key(k));
         }
     }
     if constexpr (Cfg::HAS_VALS) {
@@ -259,42 +323,92 @@ __device__ __forceinline__ void onesweep_tile(unsigned char* smem_raw, const Key
 #pragma unroll
         for (int i = 0; i < ITEMS; ++i) {
             const int s = i * THREADS + tid;
-            if (FULL || s < valid) vout[goff[dig[i]] + (u64)s] = svals[s];
+            if (FULL || s < valid) st_stream(vout + goff[dig[i]] + (u64)s, svals[s]);
         }
     }
 }
 
-template <typename KeyT, typename ValT, int THREADS, int ITEMS>
-__global__ void __launch_bounds__(THREADS, 2) onesweep_pass_kernel(const KeyT* __restrict__ kin, KeyT* __restrict__ kout,
-                                                               const ValT* __restrict__ vin, ValT* __restrict__ vout, size_t n, int shift,
-                                                               int bits, const u64* __restrict__ gbase, u32* __restrict__ tile_counter,
-                                                               u64* __restrict__ lookback, u32 epoch) {
-    using Cfg = PassCfg<KeyT, ValT, THREADS, ITEMS>;
+template <class Src, typename ValT, int THREADS, int ITEMS>
+__global__ void __launch_bounds__(THREADS, 2) onesweep_pass_kernel(const Src src, typename Src::Out* __restrict__ kout, ValT* __restrict__ vout,
+                                                                   size_t n, const u64* __restrict__ gbase, u32* __restrict__ tile_counter,
+                                                                   u64* __restrict__ lookback, u32 epoch) {
+    using Cfg = PassCfg<typename Src::Stage, ValT, THREADS, ITEMS>;
     constexpr int TILE = Cfg::TILE;
     static_assert(THREADS >= RADIX && THREADS % 32 == 0, "need one thread per digit");
-    static_assert(TILE < 65536, "tile positions are kept in 16 bits");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     u32* misc = reinterpret_cast<u32*>(smem_raw + Cfg::OFF_MISC);
-    uint2* tab = reinterpret_cast<uint2*>(smem_raw + Cfg::OFF_TAB);
+    u32* tab = reinterpret_cast<u32*>(smem_raw + Cfg::OFF_TAB);
     if (threadIdx.x == 0) misc[0] = atomicAdd(tile_counter, 1u);
-    for (int e = threadIdx.x; e < Cfg::NW * RADIX; e += THREADS) tab[e] = make_uint2(0u, 0u);
+    for (int e = threadIdx.x; e < Cfg::NW * RADIX; e += THREADS) tab[e] = 0u;
     __syncthreads();
     const size_t tile = misc[0];
     const size_t base = tile * (size_t)TILE;
-    const u32 mask = (1u << bits) - 1u;
     if (n - base >= (size_t)TILE)
-        onesweep_tile<KeyT, ValT, THREADS, ITEMS, true>(smem_raw, kin, kout, vin, vout, base, TILE, shift, mask, gbase, lookback, tile, epoch);
+        onesweep_tile<Src, ValT, THREADS, ITEMS, true>(smem_raw, src, kout, vout, base, TILE, gbase, lookback, tile, epoch);
     else
-        onesweep_tile<KeyT, ValT, THREADS, ITEMS, false>(smem_raw, kin, kout, vin, vout, base, (int)(n - base), shift, mask, gbase, lookback, tile,
-                                                       epoch);
+        onesweep_tile<Src, ValT, THREADS, ITEMS, false>(smem_raw, src, kout, vout, base, (int)(n - base), gbase, lookback, tile, epoch);
+}
+
+// ------------------------------------------------------------------ hardware self-test of the ranking assumption
+// Replays the ranking loop of onesweep_tile (ITEMS back-to-back ATOMS.ADD per lane on a per-warp table, some lanes
+// inactive) and compares every returned value with the stable rank computed from ballots.  Returns the number of
+// mismatches in *bad; the engine refuses to run when it is not zero.
+template <int ITEMS>
+__global__ void __launch_bounds__(384) atoms_order_selftest_kernel(u32 seed, u32 ndig, unsigned long long* bad) {
+    __shared__ u32 tab[12][RADIX];
+    __shared__ u32 ref[12][RADIX];
+    const u32 warp = threadIdx.x >> 5;
+    const u32 lt = lanemask_lt();
+    unsigned long long mism = 0;
+    u32 x = seed * 2654435761u + (blockIdx.x * blockDim.x + threadIdx.x) * 40503u + 977u;
+    for (int round = 0; round < 8; ++round) {
+        for (int e = threadIdx.x; e < 12 * RADIX; e += blockDim.x) {
+            (&tab[0][0])[e] = 0;
+            (&ref[0][0])[e] = 0;
+        }
+        __syncthreads();
+        u32 d[ITEMS], got[ITEMS];
+        bool act[ITEMS];
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) {
+            x = x * 1664525u + 1013904223u;
+            d[j] = (x >> 16) % ndig;
+            act[j] = ((x >> 8) & 7u) != 0u || (round & 1);
+        }
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) {
+            got[j] = 0;
+            if (act[j]) got[j] = atomicAdd(&tab[warp][d[j]], 1u);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) {
+            u32 peers = __ballot_sync(0xffffffffu, act[j]);
+#pragma unroll
+            for (int b = 0; b < RADIX_BITS; ++b) {
+                const u32 m = __ballot_sync(0xffffffffu, (d[j] >> b) & 1u);
+                peers &= ((d[j] >> b) & 1u) ? m : ~m;
+            }
+            const u32 before = ref[warp][d[j]];
+            __syncwarp();
+            if (act[j]) {
+                mism += (got[j] != before + __popc(peers & lt)) ? 1u : 0u;
+                if ((peers & lt) == 0) ref[warp][d[j]] = before + __popc(peers);
+            }
+            __syncwarp();
+        }
+        __syncthreads();
+    }
+    if (mism) atomicAdd(bad, mism);
 }
 
 // ------------------------------------------------------------------ host driver
-template <typename KeyT, typename ValT>
+template <typename StageT, typename ValT>
 struct SortTuning {
     static constexpr int THREADS = 384;
-    static constexpr int ITEMS = (sizeof(KeyT) + (std::is_same<ValT, NoVal>::value ? 0 : sizeof(ValT)) >= 16) ? 12 : 16;
+    static constexpr int ITEMS = (sizeof(StageT) + (std::is_same<ValT, NoVal>::value ? 0 : sizeof(ValT)) >= 16) ? 12 : 16;
 };
+constexpr int MIN_TILE = 384 * 12;
 
 struct RadixWorkspace {
     u64* ghist = nullptr;      // [MAX_PASSES][RADIX]
@@ -302,33 +416,33 @@ struct RadixWorkspace {
     u32* counters = nullptr;   // [MAX_PASSES]
     u64* lookback = nullptr;   // [max_tiles][RADIX]
     size_t lookback_bytes = 0;
-    static size_t small_bytes() { return 2 * MAX_PASSES * RADIX * sizeof(u64) + 64 * sizeof(u32); }
-    template <typename KeyT, typename ValT>
-    static size_t lookback_bytes_for(size_t n) {
-        using T = SortTuning<KeyT, ValT>;
-        return div_up(n ? n : 1, (size_t)T::THREADS * T::ITEMS) * RADIX * sizeof(u64);
-    }
+    static size_t lookback_bytes_for(size_t n) { return div_up(n ? n : 1, (size_t)MIN_TILE) * RADIX * sizeof(u64); }
 };
 
-// Sorts n pairs by key bits [begin_bit, end_bit).  Ping-pongs between (keys, vals) and (keys_alt, vals_alt);
-// returns true when the sorted data ended up in the *_alt buffers.
-template <typename KeyT, typename ValT>
-bool radix_sort_pairs(const RadixWorkspace& ws, KeyT* keys, KeyT* keys_alt, ValT* vals, ValT* vals_alt, size_t n, int begin_bit, int end_bit,
-                      cudaStream_t stream, int sm_count, RadixPlan* plan_out = nullptr, uint64_t* launches = nullptr,
-                      cudaEvent_t ev_hist_done = nullptr, cudaEvent_t ev_passes_begin = nullptr) {
-    using T = SortTuning<KeyT, ValT>;
-    using Cfg = PassCfg<KeyT, ValT, T::THREADS, T::ITEMS>;
-    RadixPlan plan = make_radix_plan(begin_bit, end_bit);
-    if (plan_out) *plan_out = plan;
-    if (n == 0 || plan.npass == 0) return false;
+template <class Src, typename ValT>
+void launch_pass(const RadixWorkspace& ws, const Src& src, typename Src::Out* kout, ValT* vout, size_t n, const u64* gbase, u32* tile_counter,
+                 u32 epoch, cudaStream_t stream) {
+    using T = SortTuning<typename Src::Stage, ValT>;
+    using Cfg = PassCfg<typename Src::Stage, ValT, T::THREADS, T::ITEMS>;
     const size_t tiles = div_up(n, (size_t)Cfg::TILE);
-    if (tiles * RADIX * sizeof(u64) > ws.lookback_bytes) throw std::string("radix_sort_pairs: look-back workspace too small");
-    auto kern = onesweep_pass_kernel<KeyT, ValT, T::THREADS, T::ITEMS>;
+    if (tiles * RADIX * sizeof(u64) > ws.lookback_bytes) throw std::string("radix pass: look-back workspace too small");
+    auto kern = onesweep_pass_kernel<Src, ValT, T::THREADS, T::ITEMS>;
     static bool attr_set = false;
     if (!attr_set) {
         PSAC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
         attr_set = true;
     }
+    kern<<<(unsigned)tiles, T::THREADS, Cfg::SMEM, stream>>>(src, kout, vout, n, gbase, tile_counter, ws.lookback, epoch);
+}
+
+// Sorts n pairs by key bits [begin_bit, end_bit).  Ping-pongs between (keys, vals) and (keys_alt, vals_alt);
+// returns true when the sorted data ended up in the *_alt buffers.
+template <typename KeyT, typename ValT>
+bool radix_sort_pairs(const RadixWorkspace& ws, KeyT* keys, KeyT* keys_alt, ValT* vals, ValT* vals_alt, size_t n, int begin_bit, int end_bit,
+                      cudaStream_t stream, int sm_count, RadixPlan* plan_out = nullptr, uint64_t* launches = nullptr) {
+    RadixPlan plan = make_radix_plan(begin_bit, end_bit);
+    if (plan_out) *plan_out = plan;
+    if (n == 0 || plan.npass == 0) return false;
     {
         PSAC_CUDA(cudaMemsetAsync(ws.ghist, 0, MAX_PASSES * RADIX * sizeof(u64), stream));
         size_t want = div_up(n, (size_t)512 * 32);
@@ -337,22 +451,58 @@ bool radix_sort_pairs(const RadixWorkspace& ws, KeyT* keys, KeyT* keys_alt, ValT
     }
     radix_scan_hist_kernel<<<plan.npass, RADIX, 0, stream>>>(ws.ghist, ws.gbase);
     if (launches) *launches = 2 + (uint64_t)plan.npass;
-    if (ev_hist_done) cudaEventRecord(ev_hist_done, stream);
-    if (ev_passes_begin) cudaEventRecord(ev_passes_begin, stream);
     PSAC_CUDA(cudaMemsetAsync(ws.counters, 0, MAX_PASSES * sizeof(u32), stream));
-    PSAC_CUDA(cudaMemsetAsync(ws.lookback, 0, tiles * RADIX * sizeof(u64), stream));
+    PSAC_CUDA(cudaMemsetAsync(ws.lookback, 0, RadixWorkspace::lookback_bytes_for(n), stream));
     bool in_alt = false;
     for (int p = 0; p < plan.npass; ++p) {
-        KeyT* ki = in_alt ? keys_alt : keys;
-        KeyT* ko = in_alt ? keys : keys_alt;
-        ValT* vi = in_alt ? vals_alt : vals;
-        ValT* vo = in_alt ? vals : vals_alt;
-        kern<<<(unsigned)tiles, T::THREADS, Cfg::SMEM, stream>>>(ki, ko, vi, vo, n, plan.shift[p], plan.bits[p], ws.gbase + p * RADIX,
-                                                                 ws.counters + p, ws.lookback, (u32)(p + 1));
+        ArraySrc<KeyT, ValT> src{in_alt ? keys_alt : keys, in_alt ? vals_alt : vals, plan.shift[p], (1u << plan.bits[p]) - 1u};
+        launch_pass<ArraySrc<KeyT, ValT>, ValT>(ws, src, in_alt ? keys : keys_alt, in_alt ? vals : vals_alt, n, ws.gbase + p * RADIX, ws.counters + p,
+                                                (u32)(p + 1), stream);
         in_alt = !in_alt;
     }
     PSAC_CUDA(cudaGetLastError());
     return in_alt;
+}
+
+// First sort of a construction: keys come from the packed text.  kbuf / vbuf are two ping-pong buffers each; pass 1
+// writes buffer 0; returns the index (0/1) of the buffers holding the sorted carried keys and suffix indices.
+// Carried key = key >> plan.bits[0].  Events (optional) bracket histogram and digit passes for the per-phase stats.
+template <typename KeyC, typename IdxT>
+int radix_sort_suffixes(const RadixWorkspace& ws, const u64* text_stream, size_t n, int lbits, int key_chars, KeyC* const kbuf[2], IdxT* const vbuf[2],
+                        cudaStream_t stream, int sm_count, RadixPlan* plan_out, uint64_t* launches, cudaEvent_t ev_hist_done = nullptr,
+                        cudaEvent_t ev_passes_begin = nullptr, cudaEvent_t ev_pass1_done = nullptr) {
+    const int kbits = key_chars * lbits;
+    RadixPlan plan = make_radix_plan(0, kbits);
+    if (plan_out) *plan_out = plan;
+    if (n == 0) return 0;
+    PSAC_CUDA(cudaMemsetAsync(ws.ghist, 0, MAX_PASSES * RADIX * sizeof(u64), stream));
+    {
+        const int cpw = 64 / lbits;
+        size_t want = div_up(div_up(n, (size_t)cpw), (size_t)512);
+        int grid = (int)(want < (size_t)sm_count * 4 ? (want ? want : 1) : (size_t)sm_count * 4);
+        text_hist_kernel<<<grid, 512, 0, stream>>>(text_stream, n, lbits, kbits, plan, ws.ghist);
+    }
+    radix_scan_hist_kernel<<<plan.npass, RADIX, 0, stream>>>(ws.ghist, ws.gbase);
+    if (launches) *launches = 2 + (uint64_t)plan.npass;
+    if (ev_hist_done) cudaEventRecord(ev_hist_done, stream);
+    if (ev_passes_begin) cudaEventRecord(ev_passes_begin, stream);
+    PSAC_CUDA(cudaMemsetAsync(ws.counters, 0, MAX_PASSES * sizeof(u32), stream));
+    PSAC_CUDA(cudaMemsetAsync(ws.lookback, 0, RadixWorkspace::lookback_bytes_for(n), stream));
+    const int drop = plan.bits[0];
+    {
+        const u64 C = (u64)key_chars;
+        TextSrc<KeyC, IdxT> src{text_stream, (u64)n, (n < C - 1) ? (u64)n : C - 1, lbits, kbits, drop, (1u << drop) - 1u};
+        launch_pass<TextSrc<KeyC, IdxT>, IdxT>(ws, src, kbuf[0], vbuf[0], n, ws.gbase, ws.counters, 1u, stream);
+    }
+    if (ev_pass1_done) cudaEventRecord(ev_pass1_done, stream);
+    int cur = 0;
+    for (int p = 1; p < plan.npass; ++p) {
+        ArraySrc<KeyC, IdxT> src{kbuf[cur], vbuf[cur], plan.shift[p] - drop, (1u << plan.bits[p]) - 1u};
+        launch_pass<ArraySrc<KeyC, IdxT>, IdxT>(ws, src, kbuf[1 - cur], vbuf[1 - cur], n, ws.gbase + p * RADIX, ws.counters + p, (u32)(p + 1), stream);
+        cur = 1 - cur;
+    }
+    PSAC_CUDA(cudaGetLastError());
+    return cur;
 }
 
 }  // namespace psacb200

@@ -2,14 +2,15 @@
 //
 // Reference stages restated here as kernels:
 //   a2  alphabet histogram            include/alphabet.hpp:48-59          -> byte_hist_kernel
-//   a4  k-mer generation              include/kmer.hpp:119-224            -> pack_text_kernel + keygen_kernel
+//   a4  k-mer generation              include/kmer.hpp:119-224            -> pack_text_kernel + TextSrc (radix_sort.cuh: fused into digit pass 1)
 //   a5  rank shift B2[i] = B[i+h]     include/shifting.hpp:32-122         -> fused into round_keys_kernel (gathers ISA[SA+h])
 //   a7  initial k-mer LCP             include/suffix_array.hpp:1353-1396  -> resolve_kernel<FIRST=true>
 //   a8  LCP of later rounds           include/suffix_array.hpp:1444-1508  -> resolve_kernel<FIRST=false> (direct compare on packed text)
 //   a9  rebucket (head flags + scan)  include/bucketing.hpp:57-123        -> resolve_kernel (warp-shuffle max-scan + look-back)
-//   a10 SA->ISA bulk permute          include/bulk_permute.hpp:14-73      -> resolve_kernel (ISA[SA[j]] = bucket)
+//   a10 SA->ISA bulk permute          include/bulk_permute.hpp:14-73      -> one radix partition pass by window + isa_scatter_kernel
+//                                                                             (direct scatter in resolve_kernel for small / later rounds)
 // The engine is not a port: text is packed densely (no sentinel code; suffixes that run past the end are
-// ordered by a stable-sort trick, see keygen_kernel), the first sort key is ONE word read from the packed
+// ordered by a stable-sort trick, see TextSrc in radix_sort.cuh), the first sort key is ONE word read from the packed
 // text instead of a materialised (B1,B2) pair, bucket ids are 0-based head positions (so the final ids ARE the
 // ISA and no fix-up pass exists) and later rounds touch only the suffixes that are still in a shared bucket.
 #pragma once
@@ -48,14 +49,7 @@ __global__ void __launch_bounds__(512) byte_hist_kernel(const u8* __restrict__ t
     }
 }
 
-// ------------------------------------------------------------------ packed text
-// The text is stored as a big-endian bit stream of dense codes, lbits in {1,2,4,8} per character, character i
-// at stream bits [i*lbits, (i+1)*lbits).  Word w holds characters [w*cpw, (w+1)*cpw), first character in the
-// most significant bits, zero past the end; the stream has two zero words of padding.
-struct CodeTable {
-    u8 code[256];
-};
-
+// ------------------------------------------------------------------ packed text (layout: common.cuh)
 __global__ void __launch_bounds__(256) pack_text_kernel(const u8* __restrict__ text, size_t n, CodeTable tab, int lbits, u64* __restrict__ stream,
                                                         size_t nwords) {
     __shared__ u8 lut[256];
@@ -84,34 +78,6 @@ __global__ void __launch_bounds__(256) pack_text_kernel(const u8* __restrict__ t
             }
         }
         stream[w] = acc;
-    }
-}
-
-// nbits (<= 64) stream bits starting at character position i, right-aligned
-__device__ __forceinline__ u64 stream_extract(const u64* __restrict__ stream, u64 i, int lbits, int nbits) {
-    const u64 bit = i * (u64)lbits;
-    const u64 w = bit >> 6;
-    const unsigned o = (unsigned)(bit & 63);
-    const u64 hi = __ldg(stream + w), lo = __ldg(stream + w + 1);
-    const u64 v = o ? ((hi << o) | (lo >> (64 - o))) : hi;
-    return v >> (64 - nbits);
-}
-
-// ------------------------------------------------------------------ a4: first sort key
-// keys[j] = the first C characters of suffix idx(j), packed; vals[j] = idx(j).
-// Initial order: the T = min(n, C-1) suffixes that run past the end of the text come FIRST, shortest first,
-// then suffixes 0..n-T-1.  The radix sort is stable, so among equal keys the suffixes that hit the end sort
-// in front and by increasing length -- exactly the order the reference obtains from its 0 sentinel code
-// (include/alphabet.hpp:157-164: code 0 is reserved for "past the end").
-template <typename IdxT>
-__global__ void __launch_bounds__(256) keygen_kernel(const u64* __restrict__ stream, u64 n, int lbits, int C, u64* __restrict__ keys,
-                                                     IdxT* __restrict__ vals) {
-    const u64 T = (n < (u64)(C - 1)) ? n : (u64)(C - 1);
-    const int nbits = C * lbits;
-    for (u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (u64)gridDim.x * blockDim.x) {
-        const u64 idx = (j < T) ? (n - 1 - j) : (j - T);
-        st_stream(keys + j, stream_extract(stream, idx, lbits, nbits));
-        st_stream(vals + j, (IdxT)idx);
     }
 }
 
@@ -147,20 +113,26 @@ __device__ __forceinline__ u64 stream_lcp(const u64* __restrict__ stream, u64 n,
 // unresolved ones, compacted, at SA positions pos[q]).
 //   head[q]   = first element of a bucket (sort key differs from the predecessor)
 //   bucket[q] = SA position of its head            (inclusive max-scan, warp shuffles + look-back)
-//   ISA[suffix[q]] = bucket[q]                      (SA -> ISA permute)
 //   LCP at every new bucket boundary
+// Round 0 (FIRST): the sorted keys are the CARRIED keys of the first sort (the low `drop` bits were consumed by the
+//   first digit pass, radix_sort.cuh); they are re-read from the packed text only where a neighbour has the same
+//   carried key.  bucket[q] is written sequentially to bucket_out (the SA -> ISA permutation is done afterwards by
+//   a partitioned scatter, see isa_scatter_kernel) and, for small inputs only (isa != null), also scattered directly:
+//   ISA[suffix[q]] = bucket[q].  Only the COUNT of unresolved elements is produced; compact_first_kernel lists them.
+// Later rounds: ISA[suffix[q]] = bucket[q], SA[pos[q]] = suffix[q] directly (few elements), and
 //   unresolved' = elements whose bucket still has >= 2 members; their positions and head flags are
-//                 compacted in order (exclusive sum-scan, look-back) for the next round.
+//   compacted in order (exclusive sum-scan, look-back) for the next round.
 struct ResolveArgs {
-    const u64* keys;      // sorted keys
+    const void* keys;     // sorted keys (KeyC)
     const void* vals;     // sorted suffix indices (IdxT)
     const void* pos_in;   // SA position of element q (rounds >= 1)
     u64 m;                // elements this round
     u64 n;                // text length
     void* sa;             // rounds >= 1: SA[pos[q]] = vals[q]
-    void* isa;
+    void* isa;            // null in round 0 when the partitioned permute follows
+    void* bucket_out;     // round 0: bucket id per sorted position (IdxT)
     void* lcp;            // may be null
-    void* pos_out;        // compacted positions of the still unresolved elements
+    void* pos_out;        // rounds >= 1: compacted positions of the still unresolved elements
     u8* head_out;         // their head flags
     u64* counts;          // [0] unresolved elements, [1] unresolved buckets (atomic)
     u64* lb_max;          // look-back channels, one u64 per tile each
@@ -169,6 +141,7 @@ struct ResolveArgs {
     const u64* stream;    // packed text
     int lbits;
     int C;                // round 0: characters in the key
+    int drop;             // round 0: low key bits missing from the carried keys
     int kbits;            // rounds >= 1: bits of the low key field (rank of suffix+h); the rest is the bucket
     u64 h;                // rounds >= 1: characters already known equal inside a bucket
     int padded_lcp;       // reference quirk: a used character has code 0 and matches the padding (see stream_lcp)
@@ -178,7 +151,7 @@ constexpr int RES_THREADS = 256;
 constexpr int RES_ITEMS = 4;
 constexpr int RES_TILE = RES_THREADS * RES_ITEMS;
 
-template <typename IdxT, bool FIRST>
+template <typename IdxT, typename KeyC, bool FIRST>
 __global__ void __launch_bounds__(RES_THREADS) resolve_kernel(ResolveArgs A) {
     __shared__ u64 s_wmax[RES_THREADS / 32];
     __shared__ u32 s_wsum[RES_THREADS / 32];
@@ -191,20 +164,38 @@ __global__ void __launch_bounds__(RES_THREADS) resolve_kernel(ResolveArgs A) {
     const u64 tile = s_tile;
     const u64 ntiles = (A.m + RES_TILE - 1) / RES_TILE;
     const u64 q0 = tile * RES_TILE + (u64)tid * RES_ITEMS;
+    const KeyC* keys = reinterpret_cast<const KeyC*>(A.keys);
     const IdxT* vals = reinterpret_cast<const IdxT*>(A.vals);
     const IdxT* pos_in = reinterpret_cast<const IdxT*>(A.pos_in);
     const u64 m = A.m, n = A.n;
+    const int nbits = A.C * A.lbits;
 
     // elements q0-1 .. q0+ITEMS (one neighbour on each side)
     u64 key[RES_ITEMS + 2];
     u64 suf[RES_ITEMS + 2];
     u64 pos[RES_ITEMS];
+    bool in[RES_ITEMS + 2];
 #pragma unroll
     for (int i = 0; i < RES_ITEMS + 2; ++i) {
         const u64 q = q0 + i - 1;
-        const bool in = (q0 + i >= 1) && q < m;
-        key[i] = in ? A.keys[q] : 0;
-        suf[i] = in ? (u64)vals[q] : 0;
+        in[i] = (q0 + i >= 1) && q < m;
+        key[i] = in[i] ? (u64)keys[q] : 0;
+        suf[i] = in[i] ? (u64)vals[q] : 0;
+    }
+    if (FIRST) {
+        // complete the carried keys with their dropped low bits where a neighbour ties
+        bool tie[RES_ITEMS + 2];
+#pragma unroll
+        for (int i = 0; i < RES_ITEMS + 2; ++i) {
+            tie[i] = false;
+            if (i > 0) tie[i] = tie[i] || (in[i] && in[i - 1] && key[i] == key[i - 1]);
+            if (i < RES_ITEMS + 1) tie[i] = tie[i] || (in[i] && in[i + 1] && key[i] == key[i + 1]);
+        }
+#pragma unroll
+        for (int i = 0; i < RES_ITEMS + 2; ++i) {
+            const u64 low = tie[i] ? stream_bits(A.stream, suf[i] * (u64)A.lbits + (u64)(nbits - A.drop), A.drop) : 0;
+            key[i] = (key[i] << A.drop) | low;
+        }
     }
 #pragma unroll
     for (int i = 0; i < RES_ITEMS; ++i) {
@@ -271,9 +262,14 @@ __global__ void __launch_bounds__(RES_THREADS) resolve_kernel(ResolveArgs A) {
     }
     if (tid == 0) s_excl_max = lookback_exclusive(A.lb_max, 1, tile, cta_max, 1u, OpMax());
     if (tid == 32) {
-        const u64 e = lookback_exclusive(A.lb_sum, 1, tile, (u64)cta_sum, 1u, OpSum());
-        s_excl_sum = e;
-        if (tile == ntiles - 1) atomicAdd((unsigned long long*)&A.counts[0], (unsigned long long)(e + cta_sum));
+        if (FIRST) {
+            if (cta_sum) atomicAdd((unsigned long long*)&A.counts[0], (unsigned long long)cta_sum);
+            s_excl_sum = 0;
+        } else {
+            const u64 e = lookback_exclusive(A.lb_sum, 1, tile, (u64)cta_sum, 1u, OpSum());
+            s_excl_sum = e;
+            if (tile == ntiles - 1) atomicAdd((unsigned long long*)&A.counts[0], (unsigned long long)(e + cta_sum));
+        }
     }
     if (lane == 0 && wb) atomicAdd((unsigned long long*)&A.counts[1], (unsigned long long)wb);
     __syncthreads();
@@ -286,14 +282,15 @@ __global__ void __launch_bounds__(RES_THREADS) resolve_kernel(ResolveArgs A) {
     IdxT* isa = reinterpret_cast<IdxT*>(A.isa);
     IdxT* lcp = reinterpret_cast<IdxT*>(A.lcp);
     IdxT* pos_out = reinterpret_cast<IdxT*>(A.pos_out);
-    const int nbits = A.C * A.lbits;
+    IdxT* bucket_out = reinterpret_cast<IdxT*>(A.bucket_out);
 #pragma unroll
     for (int i = 0; i < RES_ITEMS; ++i) {
         const u64 q = q0 + i;
         if (q >= m) break;
         const u64 bucket = mx[i] > pre_max ? mx[i] : pre_max;
         const u64 s = suf[i + 1];
-        isa[s] = (IdxT)bucket;
+        if (FIRST) st_stream(bucket_out + q, (IdxT)bucket);
+        if (isa != nullptr) isa[s] = (IdxT)bucket;
         if (!FIRST) sa[pos[i]] = (IdxT)s;
         if (lcp != nullptr && head[i]) {
             if (q == 0) {
@@ -315,12 +312,80 @@ __global__ void __launch_bounds__(RES_THREADS) resolve_kernel(ResolveArgs A) {
                 lcp[pos[i]] = (IdxT)stream_lcp(A.stream, n, A.lbits, suf[i], s, A.h, A.padded_lcp != 0);
             }
         }
-        const bool unresolved = !(head[i] && head[i + 1]);
-        if (unresolved) {
-            const u64 o = pre_sum + un[i];
-            pos_out[o] = (IdxT)pos[i];
-            A.head_out[o] = head[i] ? 1 : 0;
+        if (!FIRST) {
+            const bool unresolved = !(head[i] && head[i + 1]);
+            if (unresolved) {
+                const u64 o = pre_sum + un[i];
+                pos_out[o] = (IdxT)pos[i];
+                A.head_out[o] = head[i] ? 1 : 0;
+            }
         }
+    }
+}
+
+// ------------------------------------------------------------------ round 0: list the unresolved elements
+// From the bucket ids of round 0 (bucket[q] = position of q's bucket head): q is a head iff bucket[q] == q; it is
+// unresolved iff its bucket has >= 2 members.  Writes their positions and head flags in order (sum-scan + look-back).
+template <typename IdxT>
+__global__ void __launch_bounds__(RES_THREADS) compact_first_kernel(const IdxT* __restrict__ bucket, u64 n, IdxT* __restrict__ pos_out,
+                                                                    u8* __restrict__ head_out, u64* __restrict__ lb_sum, u32* __restrict__ tile_counter) {
+    __shared__ u32 s_wsum[RES_THREADS / 32];
+    __shared__ u64 s_excl_sum;
+    __shared__ u32 s_tile;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
+    __syncthreads();
+    const u64 tile = s_tile;
+    const u64 q0 = tile * RES_TILE + (u64)tid * RES_ITEMS;
+    bool head[RES_ITEMS + 1];
+#pragma unroll
+    for (int i = 0; i < RES_ITEMS + 1; ++i) {
+        const u64 q = q0 + i;
+        head[i] = (q >= n) || ((u64)bucket[q] == q);
+    }
+    u32 un[RES_ITEMS];
+    u32 run_sum = 0;
+#pragma unroll
+    for (int i = 0; i < RES_ITEMS; ++i) {
+        un[i] = run_sum;
+        run_sum += ((q0 + i) < n && !(head[i] && head[i + 1])) ? 1u : 0u;
+    }
+    const u32 wincl = warp_inclusive_sum_u32(run_sum);
+    if (lane == 31) s_wsum[warp] = wincl;
+    __syncthreads();
+    u32 cta_sum = 0, wpre = 0;
+#pragma unroll
+    for (int w = 0; w < RES_THREADS / 32; ++w) {
+        if (w == warp) wpre = cta_sum;
+        cta_sum += s_wsum[w];
+    }
+    if (tid == 0) s_excl_sum = lookback_exclusive(lb_sum, 1, tile, (u64)cta_sum, 1u, OpSum());
+    __syncthreads();
+    const u64 pre = s_excl_sum + wpre + (wincl - run_sum);
+#pragma unroll
+    for (int i = 0; i < RES_ITEMS; ++i) {
+        const u64 q = q0 + i;
+        if (q < n && !(head[i] && head[i + 1])) {
+            pos_out[pre + un[i]] = (IdxT)q;
+            head_out[pre + un[i]] = head[i] ? 1 : 0;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ a10: SA -> ISA, second half of the partitioned permute
+// (reference bulk_permute_inplace, include/bulk_permute.hpp:14-73, buckets the pairs by owner rank before scattering;
+// here the owner is an L2-sized window of the ISA).  Input: the (suffix, bucket id) pairs partitioned by the top
+// bits of the suffix index by one radix pass, so that the CTAs running at any moment scatter into one or two windows of
+// n/256 entries that stay resident in L2; every 32-byte sector is written out to HBM once, complete.
+template <typename IdxT>
+__global__ void __launch_bounds__(256) isa_scatter_kernel(const IdxT* __restrict__ suffix, const IdxT* __restrict__ bucket, IdxT* __restrict__ isa,
+                                                          u64 n) {
+    constexpr int PER = 16;
+    const u64 base = (u64)blockIdx.x * (256 * PER);
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        const u64 q = base + (u64)i * 256 + threadIdx.x;
+        if (q < n) isa[ld_stream(suffix + q)] = ld_stream(bucket + q);
     }
 }
 
