@@ -137,6 +137,34 @@ __device__ __forceinline__ u64 lookback_exclusive(u64* chan, size_t stride, size
     return excl;
 }
 
+// Sum look-back of ONE thread per channel with B loads in flight: on B200 a tile lives ~10 us, ~450 tiles are resident and
+// a dependent L2 load under full DRAM load costs several hundred ns, so a one-entry-at-a-time walk over the
+// predecessors that are still walking themselves never catches up (profiles/r1b: 40 % of the pass kernel's stall
+// samples sat on that load).  The caller has already published this tile's aggregate.  Returns the exclusive prefix.
+template <int B>
+__device__ __forceinline__ u64 lookback_sum_batched(const u64* chan, size_t stride, size_t tile, u32 epoch) {
+    u64 excl = 0;
+    size_t t = tile;  // predecessors t-1, t-2, ...
+    while (t > 0) {
+        u64 w[B];
+#pragma unroll
+        for (int b = 0; b < B; ++b) w[b] = (t > (size_t)b) ? ld_relaxed(chan + (t - 1 - b) * stride) : 0;
+#pragma unroll
+        for (int b = 0; b < B; ++b) {
+            if (t <= (size_t)b) return excl;  // walked past tile 0
+            u64 st = lb_state(w[b], epoch);
+            while (st == LB_NONE) {
+                w[b] = ld_relaxed(chan + (t - 1 - b) * stride);
+                st = lb_state(w[b], epoch);
+            }
+            excl += lb_payload(w[b]);
+            if (st == LB_INCLUSIVE) return excl;
+        }
+        t -= B;
+    }
+    return excl;
+}
+
 // ---------------------------------------------------------------- warp scans (shuffle based)
 template <typename Op>
 __device__ __forceinline__ u64 warp_inclusive_scan(u64 v, Op op) {
@@ -156,6 +184,43 @@ __device__ __forceinline__ u32 warp_inclusive_sum_u32(u32 v) {
         if (lane >= (unsigned)d) v += o;
     }
     return v;
+}
+
+// Look-back executed by ONE FULL WARP: 32 predecessors are examined per step (short-lived scan tiles are all in
+// the same phase, so a serial walk crosses hundreds of them).  Publishes the aggregate, returns the exclusive prefix in
+// every lane and publishes the inclusive one.  Op must be commutative (sum, max).
+template <typename Op>
+__device__ __forceinline__ u64 lookback_exclusive_warp(u64* chan, size_t tile, u64 aggregate, u32 epoch, Op op) {
+    const unsigned lane = lane_id();
+    if (tile == 0) {
+        if (lane == 0) st_relaxed(chan, lb_pack(aggregate, epoch, LB_INCLUSIVE));
+        return Op::identity();
+    }
+    if (lane == 0) st_relaxed(chan + tile, lb_pack(aggregate, epoch, LB_AGGREGATE));
+    u64 excl = Op::identity();
+    long long t = (long long)tile - 1;  // entry examined by lane 0
+    while (true) {
+        const long long mine = t - (long long)lane;
+        u64 st = LB_INCLUSIVE, payload = Op::identity();  // before tile 0: an inclusive identity
+        if (mine >= 0) {
+            u64 w;
+            do {
+                w = ld_relaxed(chan + mine);
+                st = lb_state(w, epoch);
+            } while (st == LB_NONE);
+            payload = lb_payload(w);
+        }
+        const unsigned incl = __ballot_sync(0xffffffffu, st == LB_INCLUSIVE);
+        const unsigned first = incl ? (unsigned)(__ffs(incl) - 1) : 31u;
+        u64 v = (lane <= first) ? payload : Op::identity();
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) v = op(v, __shfl_xor_sync(0xffffffffu, v, d));
+        excl = op(v, excl);
+        if (incl) break;
+        t -= 32;
+    }
+    if (lane == 0) st_relaxed(chan + tile, lb_pack(op(excl, aggregate), epoch, LB_INCLUSIVE));
+    return excl;
 }
 
 }  // namespace psacb200

@@ -75,7 +75,7 @@ struct psacb200_engine {
     cudaStream_t stream = nullptr;
     size_t device_bytes = 0;
     uint64_t launches = 0;
-    DevBuf text, packed, keys[2], vals[2], isa, lcp, small, lookback, rk[2], rv[2], rp[2], rh[2], scratch;
+    DevBuf text, packed, keys[2], vals[2], aux[2], isa, lcp, small, lookback, rk[2], rv[2], rp[2], rh[2], scratch;
     u64* h_pinned = nullptr;  // 512 u64 of pinned host memory for small read-backs
     cudaEvent_t ev_begin[PH_COUNT], ev_end[PH_COUNT];
     bool ev_used[PH_COUNT];
@@ -160,17 +160,21 @@ void dense_codes(const u64* hist, Alphabet& a) {
     a.lbits = d <= 2 ? 1 : d <= 4 ? 2 : d <= 16 ? 4 : 8;
 }
 
+// reduce -> scan -> apply (sa_kernels.cuh): per-tile aggregates, their exclusive scan, then the outputs
 template <typename IdxT, typename KeyC>
 void launch_resolve(psacb200_engine* e, bool first, const ResolveArgs& A) {
     const u64 ntiles = div_up(A.m, (size_t)RES_TILE);
-    PSAC_CUDA(cudaMemsetAsync(A.lb_max, 0, 2 * ntiles * sizeof(u64), e->stream));  // lb_sum follows lb_max
     PSAC_CUDA(cudaMemsetAsync(A.counts, 0, 2 * sizeof(u64), e->stream));
-    PSAC_CUDA(cudaMemsetAsync(A.tile_counter, 0, sizeof(u32), e->stream));
-    if (first)
-        resolve_kernel<IdxT, KeyC, true><<<(unsigned)ntiles, RES_THREADS, 0, e->stream>>>(A);
-    else
-        resolve_kernel<IdxT, u64, false><<<(unsigned)ntiles, RES_THREADS, 0, e->stream>>>(A);
-    e->launches += 1;
+    if (first) {
+        resolve_kernel<IdxT, KeyC, true, 0><<<(unsigned)ntiles, RES_THREADS, 0, e->stream>>>(A);
+        tile_scan_kernel<<<1, 1024, 0, e->stream>>>(A.lb_max, A.lb_sum, ntiles, A.counts);
+        resolve_kernel<IdxT, KeyC, true, 1><<<(unsigned)ntiles, RES_THREADS, 0, e->stream>>>(A);
+    } else {
+        resolve_kernel<IdxT, u64, false, 0><<<(unsigned)ntiles, RES_THREADS, 0, e->stream>>>(A);
+        tile_scan_kernel<<<1, 1024, 0, e->stream>>>(A.lb_max, A.lb_sum, ntiles, A.counts);
+        resolve_kernel<IdxT, u64, false, 1><<<(unsigned)ntiles, RES_THREADS, 0, e->stream>>>(A);
+    }
+    e->launches += 3;
     PSAC_CUDA(cudaGetLastError());
 }
 
@@ -228,17 +232,27 @@ size_t lookback_bytes(u64 n) {
 
 // Device buffers of one construction.  When the caller's outputs are device buffers of the engine's internal index
 // width they are used in place (final SA = the value buffer the last digit pass writes, ISA and LCP directly).
+// Unresolved-list capacity reserved up front: round 0 lists its unresolved suffixes inside the resolve kernel while
+// they fit (random text leaves n / 2^10 of them); a repetitive text that overflows it takes the compact_first_kernel path.
+u64 unresolved_cap(u64 n) { return n / 16 + 4096; }
+
 template <typename IdxT>
 void reserve_buffers(psacb200_engine* e, u64 n, size_t key_bytes, bool want_lcp, bool ext_sa, bool ext_isa, bool ext_lcp) {
     size_t* tot = &e->device_bytes;
     e->small.reserve(psacb200_engine::small_bytes(), tot);
     e->packed.reserve((n / 8 + 4) * sizeof(u64) + 64, tot);  // worst case 8 bits per character
-    for (int b = 0; b < 2; ++b) e->keys[b].reserve(n * key_bytes, tot);
+    for (int b = 0; b < 2; ++b) {
+        e->keys[b].reserve(n * key_bytes, tot);
+        if (key_bytes == 4) e->aux[b].reserve(n + 16, tot);
+    }
     e->vals[0].reserve(n * sizeof(IdxT), tot);
     if (!ext_sa) e->vals[1].reserve(n * sizeof(IdxT), tot);
     if (!ext_isa) e->isa.reserve(n * sizeof(IdxT), tot);
     if (want_lcp && !ext_lcp) e->lcp.reserve(n * sizeof(IdxT), tot);
     e->lookback.reserve(lookback_bytes(n), tot);
+    const u64 cap = unresolved_cap(n);
+    e->rp[1].reserve(cap * sizeof(IdxT), tot);
+    e->rh[1].reserve(cap, tot);
 }
 
 template <typename IdxT, typename KeyC>
@@ -261,10 +275,11 @@ void construct_core(psacb200_engine* e, u64 n, int index_bytes, unsigned flags, 
     IdxT* vbuf[2];
     vbuf[fin] = ext_sa ? reinterpret_cast<IdxT*>(sa_out) : e->vals[1].as<IdxT>();
     vbuf[1 - fin] = e->vals[0].as<IdxT>();
+    u8* abuf[2] = {e->aux[0].as<u8>(), e->aux[1].as<u8>()};
     uint64_t sort_launches = 0;
     RadixPlan plan_used;
     e->begin(PH_HIST);
-    const int x = radix_sort_suffixes<KeyC, IdxT>(e->radix_ws(), e->packed.as<u64>(), n, lbits, (int)C, kbuf, vbuf, st, e->sm_count, &plan_used,
+    const int x = radix_sort_suffixes<KeyC, IdxT>(e->radix_ws(), e->packed.as<u64>(), n, lbits, (int)C, kbuf, vbuf, abuf, st, e->sm_count, &plan_used,
                                                   &sort_launches, e->ev_end[PH_HIST], e->ev_begin[PH_SORT], e->ev_end[PH_PASS1]);
     e->ev_used[PH_SORT] = true;
     e->end(PH_SORT);
@@ -282,6 +297,7 @@ void construct_core(psacb200_engine* e, u64 n, int index_bytes, unsigned flags, 
     ResolveArgs R{};
     R.keys = kbuf[x];
     R.vals = SA;
+    R.aux = sizeof(KeyC) == 4 ? abuf[x] : nullptr;
     R.pos_in = nullptr;
     R.m = n;
     R.n = n;
@@ -289,16 +305,16 @@ void construct_core(psacb200_engine* e, u64 n, int index_bytes, unsigned flags, 
     R.isa = partitioned ? nullptr : ISA;
     R.bucket_out = bucket;
     R.lcp = LCP;
-    R.pos_out = nullptr;
-    R.head_out = nullptr;
+    R.pos_out = e->rp[1].p;
+    R.head_out = e->rh[1].as<u8>();
+    R.cap = std::min<u64>(unresolved_cap(n), e->rh[1].cap);
     R.counts = e->counts();
     R.lb_max = e->lookback.as<u64>();
     R.lb_sum = R.lb_max + div_up(n, (size_t)RES_TILE);
-    R.tile_counter = e->counters() + 16;
     R.stream = e->packed.as<u64>();
     R.lbits = lbits;
     R.C = (int)C;
-    R.drop = plan_used.bits[0];
+    R.drop = sizeof(KeyC) == 4 ? plan_used.bits[0] : 0;
     R.kbits = 0;
     R.h = 0;
     R.padded_lcp = alpha.zero_code_used ? 1 : 0;
@@ -309,22 +325,27 @@ void construct_core(psacb200_engine* e, u64 n, int index_bytes, unsigned flags, 
     S.unresolved_after_first = m;
     S.rounds = 1;
 
-    // ---- list the unresolved suffixes (positions + head flags) for the later rounds
+    // ---- unresolved suffixes (positions + head flags) for the later rounds: listed by the resolve kernel unless they
+    //      overflowed its capacity (repetitive text)
     if (m > 0) {
         size_t* tot = &e->device_bytes;
         for (int b = 0; b < 2; ++b) {
             e->rk[b].reserve(m * sizeof(u64), tot);
             e->rv[b].reserve(m * sizeof(IdxT), tot);
-            e->rp[b].reserve(m * sizeof(IdxT), tot);
-            e->rh[b].reserve(m, tot);
         }
-        const u64 ntiles = div_up(n, (size_t)RES_TILE);
-        PSAC_CUDA(cudaMemsetAsync(e->lookback.p, 0, ntiles * sizeof(u64), st));
-        PSAC_CUDA(cudaMemsetAsync(e->counters() + 18, 0, sizeof(u32), st));
-        compact_first_kernel<IdxT><<<(unsigned)ntiles, RES_THREADS, 0, st>>>(bucket, n, e->rp[1].as<IdxT>(), e->rh[1].as<u8>(), e->lookback.as<u64>(),
-                                                                             e->counters() + 18);
-        e->launches += 1;
-        PSAC_CUDA(cudaGetLastError());
+        e->rp[0].reserve(m * sizeof(IdxT), tot);
+        e->rh[0].reserve(m, tot);
+        if (m > R.cap) {
+            e->rp[1].reserve(m * sizeof(IdxT), tot);
+            e->rh[1].reserve(m, tot);
+            const u64 ntiles = div_up(n, (size_t)RES_TILE);
+            PSAC_CUDA(cudaMemsetAsync(e->lookback.p, 0, ntiles * sizeof(u64), st));
+            PSAC_CUDA(cudaMemsetAsync(e->counters() + 18, 0, sizeof(u32), st));
+            compact_first_kernel<IdxT><<<(unsigned)ntiles, RES_THREADS, 0, st>>>(bucket, n, e->rp[1].as<IdxT>(), e->rh[1].as<u8>(),
+                                                                                 e->lookback.as<u64>(), e->counters() + 18);
+            e->launches += 1;
+            PSAC_CUDA(cudaGetLastError());
+        }
     }
 
     // ---- SA -> ISA (a10): partition the (suffix, bucket) pairs by ISA window, then scatter window by window
@@ -340,8 +361,8 @@ void construct_core(psacb200_engine* e, u64 n, int index_bytes, unsigned flags, 
         PSAC_CUDA(cudaMemsetAsync(ws.lookback, 0, RadixWorkspace::lookback_bytes_for(n), st));
         IdxT* part_suffix = vbuf[y];
         IdxT* part_bucket = reinterpret_cast<IdxT*>(kbuf[x]);  // the sorted keys are dead after resolve
-        ArraySrc<IdxT, IdxT> src{SA, bucket, shift, (u32)(RADIX - 1)};
-        launch_pass<ArraySrc<IdxT, IdxT>, IdxT>(ws, src, part_suffix, part_bucket, n, gb, ctr, 1u, st);
+        ArraySrc<IdxT, IdxT> src{SA, bucket, nullptr, shift, (u32)(RADIX - 1)};
+        launch_pass<ArraySrc<IdxT, IdxT>, IdxT, false>(ws, src, part_suffix, part_bucket, nullptr, n, gb, ctr, 1u, st);
         isa_scatter_kernel<IdxT><<<(unsigned)div_up(n, (size_t)4096), 256, 0, st>>>(part_suffix, part_bucket, ISA, n);
         e->launches += 3;
         PSAC_CUDA(cudaGetLastError());
@@ -389,8 +410,10 @@ void construct_core(psacb200_engine* e, u64 n, int index_bytes, unsigned flags, 
             Q.m = m;
             Q.isa = ISA;
             Q.bucket_out = nullptr;
+            Q.aux = nullptr;
             Q.pos_out = e->rp[t].p;
             Q.head_out = e->rh[t].as<u8>();
+            Q.cap = m;
             Q.lb_sum = Q.lb_max + ntiles;
             Q.drop = 0;
             Q.kbits = kbits;
@@ -474,7 +497,7 @@ int construct_entry(psacb200_engine* e, const u8* text, bool text_is_host, size_
         prepare_text(e, d_text, n, lut, alpha);
         const unsigned C = choose_key_chars(n, alpha.lbits, k);
         e->stats.key_chars = C;
-        const int carried_bits = (int)C * alpha.lbits - make_radix_plan(0, (int)C * alpha.lbits).bits[0];
+        const int carried_bits = (int)C * alpha.lbits - make_radix_plan(0, (int)C * alpha.lbits).bits[0];  // see carried_drop_bits
         if ((u64)n <= (1ull << 32)) {
             if (carried_bits <= 32)
                 construct_core<u32, u32>(e, n, index_bytes, flags, alpha, C, sa_out, isa_out, lcp_out, text_is_host);
@@ -615,7 +638,7 @@ void psacb200_destroy(psacb200_engine* e) {
     if (!e) return;
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->stream);
-    DevBuf* all[] = {&e->text, &e->packed, &e->keys[0], &e->keys[1], &e->vals[0], &e->vals[1], &e->isa, &e->lcp, &e->small, &e->lookback,
+    DevBuf* all[] = {&e->text, &e->packed, &e->keys[0], &e->keys[1], &e->vals[0], &e->vals[1], &e->aux[0], &e->aux[1], &e->isa, &e->lcp, &e->small, &e->lookback,
                      &e->rk[0], &e->rk[1], &e->rv[0], &e->rv[1], &e->rp[0], &e->rp[1], &e->rh[0], &e->rh[1], &e->scratch};
     for (DevBuf* b : all) b->release(nullptr);
     for (int i = 0; i < PH_COUNT; ++i) {

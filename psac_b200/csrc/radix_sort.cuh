@@ -27,11 +27,29 @@
 
 namespace psacb200 {
 
+// optional per-phase cycle accounting of the pass kernel (tools/bench_pass.cu defines PSAC_PHASE_PROFILE)
+#ifdef PSAC_PHASE_PROFILE
+__device__ unsigned long long g_phase_cycles[16];
+#define PSAC_PHASE(i)                                                          \
+    do {                                                                       \
+        if (threadIdx.x == 0) {                                                \
+            const long long _c = clock64();                                    \
+            atomicAdd(&g_phase_cycles[i], (unsigned long long)(_c - _phase_t)); \
+            _phase_t = _c;                                                     \
+        }                                                                      \
+    } while (0)
+#define PSAC_PHASE_BEGIN() long long _phase_t = clock64()
+#else
+#define PSAC_PHASE(i) do { } while (0)
+#define PSAC_PHASE_BEGIN() do { } while (0)
+#endif
+
 struct NoVal {};  // keys-only sort
 
 constexpr int RADIX_BITS = 8;
 constexpr int RADIX = 1 << RADIX_BITS;
 constexpr int MAX_PASSES = 8;
+constexpr int LOOKBACK_BATCH = 8;  // look-back loads in flight per digit channel
 
 struct RadixPlan {
     int npass;
@@ -144,31 +162,38 @@ __global__ void __launch_bounds__(RADIX) perm_gbase_kernel(u64 n, int shift, u64
 }
 
 // ------------------------------------------------------------------ key sources of a pass
-// A source provides the staged key of global element g, its digit, the key to write out, and the value.
+// A source provides the staged key of global element g, its digit, the key to write out, the value and (optionally)
+// an auxiliary byte that travels with the pair.
 template <typename KeyT, typename ValT>
 struct ArraySrc {
     using Stage = KeyT;
     using Out = KeyT;
+    static constexpr bool FROM_TEXT = false;
     const KeyT* __restrict__ kin;
     const ValT* __restrict__ vin;
+    const u8* __restrict__ ain;  // auxiliary bytes (null when the pass carries none)
     int shift;
     u32 mask;
     __device__ __forceinline__ Stage load_key(size_t g) const { return ld_stream(kin + g); }
     __device__ __forceinline__ u32 digit(Stage k) const { return (u32)(k >> shift) & mask; }
     __device__ __forceinline__ Out out_key(Stage k) const { return k; }
     __device__ __forceinline__ ValT load_val(size_t g) const { return ld_stream(vin + g); }
+    __device__ __forceinline__ u8 load_aux(size_t g, Stage) const { return ld_stream(ain + g); }
 };
 
 // First pass of a construction (reference a4 k-mer generation, include/kmer.hpp:119-224, fused into the sort):
 // element g is suffix idx(g); its key is the first kbits stream bits of that suffix; the digit is the low `drop` bits
-// and the key carried on is the rest.  Initial order: the T = min(n, C-1) suffixes that run past the end of the text
-// come FIRST, shortest first, then suffixes 0..n-T-1.  The sort is stable, so among equal keys the suffixes that hit
-// the end sort in front and by increasing length -- exactly the order the reference obtains from its 0 sentinel code
-// (include/alphabet.hpp:157-164: code 0 is reserved for "past the end").
+// and the key carried on is the rest; the dropped digit travels on as the auxiliary byte (the resolve step needs the
+// complete key).  With drop == 0 the whole key is carried (64-bit carried keys) and there is no auxiliary byte.
+// Initial order: the T = min(n, C-1) suffixes that run past the end of the text come FIRST, shortest first, then
+// suffixes 0..n-T-1.  The sort is stable, so among equal keys the suffixes that hit the end sort in front and by
+// increasing length -- exactly the order the reference obtains from its 0 sentinel code (include/alphabet.hpp:157-164:
+// code 0 is reserved for "past the end").
 template <typename OutKeyT, typename IdxT>
 struct TextSrc {
     using Stage = u64;
     using Out = OutKeyT;
+    static constexpr bool FROM_TEXT = true;
     const u64* __restrict__ stream;
     u64 n, T;
     int lbits, kbits, drop;
@@ -178,35 +203,46 @@ struct TextSrc {
     __device__ __forceinline__ u32 digit(Stage k) const { return (u32)k & mask; }
     __device__ __forceinline__ Out out_key(Stage k) const { return (Out)(k >> drop); }
     __device__ __forceinline__ IdxT load_val(size_t g) const { return (IdxT)idx(g); }
+    __device__ __forceinline__ u8 load_aux(size_t, Stage k) const { return (u8)((u32)k & mask); }
 };
 
 // ------------------------------------------------------------------ one digit pass
-// Shared memory layout of a pass CTA: [tile staging: TILE * max(sizeof staged key, sizeof value)] [per-warp counter
-// tables NW * 256 * u32] [bin_start 256 * u32] [goff 256 * u64] [misc].
-template <typename StageT, typename ValT, int THREADS_, int ITEMS_>
+// Shared memory layout of a pass CTA: [tile staging] [aux staging TILE bytes, if any] [per-warp counter tables
+// NW * 256 * u32] [bin_start 256 * u32] [goff 256 * u64] [misc].  32-bit keys with 32-bit values are staged PACKED as
+// one 64-bit word per pair (one scatter, one read-back); other widths stage the keys, then the values.
+template <class Src, typename ValT, int THREADS_, int ITEMS_, bool HAS_AUX_>
 struct PassCfg {
+    using Stage = typename Src::Stage;
+    using Out = typename Src::Out;
     static constexpr int THREADS = THREADS_;
     static constexpr int ITEMS = ITEMS_;
     static constexpr int TILE = THREADS * ITEMS;
     static constexpr int NW = THREADS / 32;
     static constexpr bool HAS_VALS = !std::is_same<ValT, NoVal>::value;
-    static constexpr size_t ELT = (HAS_VALS && sizeof(ValT) > sizeof(StageT)) ? sizeof(ValT) : sizeof(StageT);
-    static constexpr size_t OFF_TAB = (size_t)TILE * ELT;
+    static constexpr bool HAS_AUX = HAS_AUX_;
+    static constexpr bool PACKED = HAS_VALS && sizeof(Out) == 4 && sizeof(ValT) == 4;
+    // a packed text pass no longer has the digit in the staged pair: it is read back from the aux byte
+    static_assert(!(PACKED && Src::FROM_TEXT) || HAS_AUX, "packed first pass needs the auxiliary byte");
+    static constexpr size_t KEYSZ = PACKED ? 8 : sizeof(Stage);
+    static constexpr size_t ELT = (!PACKED && HAS_VALS && sizeof(ValT) > KEYSZ) ? sizeof(ValT) : KEYSZ;
+    static constexpr size_t OFF_AUX = (size_t)TILE * ELT;
+    static constexpr size_t OFF_TAB = OFF_AUX + (HAS_AUX ? (size_t)TILE : 0);
     static constexpr size_t OFF_BIN = OFF_TAB + (size_t)NW * RADIX * 4;
     static constexpr size_t OFF_GOFF = OFF_BIN + RADIX * 4;
     static constexpr size_t OFF_MISC = OFF_GOFF + RADIX * 8;
     static constexpr size_t SMEM = OFF_MISC + 64;
+    static_assert(OFF_TAB % 8 == 0, "table alignment");
 };
 
-template <class Src, typename ValT, int THREADS, int ITEMS, bool FULL>
+template <class Cfg, class Src, typename ValT, bool FULL>
 __device__ __forceinline__ void onesweep_tile(unsigned char* smem_raw, const Src& src, typename Src::Out* __restrict__ kout, ValT* __restrict__ vout,
-                                              const size_t base, const int valid, const u64* __restrict__ gbase, u64* __restrict__ lookback,
-                                              const size_t tile, const u32 epoch) {
+                                              u8* __restrict__ aout, const size_t base, const int valid, const u64* __restrict__ gbase,
+                                              u64* __restrict__ lookback, const size_t tile, const u32 epoch) {
     using Stage = typename Src::Stage;
-    using Cfg = PassCfg<Stage, ValT, THREADS, ITEMS>;
-    constexpr int NW = Cfg::NW;
-    Stage* skeys = reinterpret_cast<Stage*>(smem_raw);
-    u32* tab = reinterpret_cast<u32*>(smem_raw + Cfg::OFF_TAB);  // [NW][RADIX] running counters, later warp bases
+    using Out = typename Src::Out;
+    constexpr int NW = Cfg::NW, ITEMS = Cfg::ITEMS, THREADS = Cfg::THREADS;
+    u8* saux = smem_raw + Cfg::OFF_AUX;
+    u32* tab = reinterpret_cast<u32*>(smem_raw + Cfg::OFF_TAB);  // [NW][RADIX] counts, then running positions
     u32* bin_start = reinterpret_cast<u32*>(smem_raw + Cfg::OFF_BIN);
     u64* goff = reinterpret_cast<u64*>(smem_raw + Cfg::OFF_GOFF);
     u32* misc = reinterpret_cast<u32*>(smem_raw + Cfg::OFF_MISC);  // [1..8] warp totals of the digit scan
@@ -215,6 +251,7 @@ __device__ __forceinline__ void onesweep_tile(unsigned char* smem_raw, const Src
     const int woff = warp * 32 * ITEMS + lane;
     u32* mytab = tab + warp * RADIX;
 
+    PSAC_PHASE_BEGIN();
     // ---- load keys, warp-striped: item j of lane l is tile element warp*32*ITEMS + j*32 + l
     Stage key[ITEMS];
 #pragma unroll
@@ -222,16 +259,31 @@ __device__ __forceinline__ void onesweep_tile(unsigned char* smem_raw, const Src
         const int o = woff + j * 32;
         key[j] = (FULL || o < valid) ? src.load_key(base + o) : (Stage)0;
     }
-
-    // ---- stable rank inside the warp: one ATOMS.ADD per key (lanes of one instruction apply in ascending lane order,
-    //      instructions of a warp in program order -- see the header comment)
-    u32 pos[ITEMS];
+    // ---- count the warp's digits (shared-memory reductions, no return value)
 #pragma unroll
     for (int j = 0; j < ITEMS; ++j) {
-        pos[j] = 0;
-        if (FULL || (woff + j * 32) < valid) pos[j] = atomicAdd(&mytab[src.digit(key[j])], 1u);
+        if (FULL || (woff + j * 32) < valid) atomicAdd(&mytab[src.digit(key[j])], 1u);
     }
+    // values / aux bytes: issue the global loads now, they land while the counts are scanned
+    ValT val[Cfg::HAS_VALS ? ITEMS : 1];
+    u8 aux[Cfg::HAS_AUX ? ITEMS : 1];
+    if constexpr (Cfg::HAS_VALS) {
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) {
+            const int o = woff + j * 32;
+            if (FULL || o < valid) val[j] = src.load_val(base + o);
+        }
+    }
+    if constexpr (Cfg::HAS_AUX) {
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) {
+            const int o = woff + j * 32;
+            if (FULL || o < valid) aux[j] = src.load_aux(base + o, key[j]);
+        }
+    }
+    PSAC_PHASE(0);  // key loads + counting
     __syncthreads();
+    PSAC_PHASE(1);  // barrier 1
 
     // ---- per digit: exclusive offsets of the warps, tile count (published at once for the look-back), bin start
     u32 count = 0;
@@ -257,82 +309,97 @@ __device__ __forceinline__ void onesweep_tile(unsigned char* smem_raw, const Src
         for (int w = 0; w < NW; ++w) tab[w * RADIX + tid] += bstart;  // position of the warp's first key of this digit
     }
     __syncthreads();
+    PSAC_PHASE(2);  // digit scan (2 barriers)
 
-    // values: issue the global loads now, they overlap the key scatter, the look-back and the key write-out
-    ValT val[Cfg::HAS_VALS ? ITEMS : 1];
-    if constexpr (Cfg::HAS_VALS) {
-#pragma unroll
-        for (int j = 0; j < ITEMS; ++j) {
-            const int o = woff + j * 32;
-            if (FULL || o < valid) val[j] = src.load_val(base + o);
-        }
-    }
-
-    // ---- final position inside the tile, then scatter the keys into shared memory in bin order
+    // ---- stable rank = one ATOMS.ADD with return per key on the warp's running positions (lanes of one instruction
+    //      apply in ascending lane order, instructions of a warp in program order -- see the header comment), then
+    //      scatter into shared memory in bin order
+    u32 pos[Cfg::PACKED ? 1 : ITEMS];
 #pragma unroll
     for (int j = 0; j < ITEMS; ++j) {
         if (FULL || (woff + j * 32) < valid) {
-            pos[j] += mytab[src.digit(key[j])];
-            skeys[pos[j]] = key[j];
+            const u32 p = atomicAdd(&mytab[src.digit(key[j])], 1u);
+            if constexpr (Cfg::PACKED) {
+                reinterpret_cast<u64*>(smem_raw)[p] = ((u64)src.out_key(key[j]) << 32) | (u64)val[j];
+            } else {
+                reinterpret_cast<Stage*>(smem_raw)[p] = key[j];
+                pos[j] = p;
+            }
+            if constexpr (Cfg::HAS_AUX) saux[p] = aux[j];
         }
     }
 
+    PSAC_PHASE(3);  // rank + scatter
     // ---- decoupled look-back, one channel per digit; the predecessors published their counts long ago
     if (tid < RADIX) {
         u64 excl = 0;
         if (tile == 0) {
             st_relaxed(lookback + tid, lb_pack((u64)count, epoch, LB_INCLUSIVE));
         } else {
-            size_t t = tile;
-            while (true) {
-                --t;
-                u64 w, st;
-                do {
-                    w = ld_relaxed(lookback + t * RADIX + tid);
-                    st = lb_state(w, epoch);
-                } while (st == LB_NONE);
-                excl += lb_payload(w);
-                if (st == LB_INCLUSIVE) break;
-            }
+            excl = lookback_sum_batched<LOOKBACK_BATCH>(lookback + tid, RADIX, tile, epoch);
             st_relaxed(lookback + tile * RADIX + tid, lb_pack(excl + count, epoch, LB_INCLUSIVE));
         }
         goff[tid] = gbase[tid] + excl - (u64)bin_start[tid];
     }
+    PSAC_PHASE(4);  // look-back
     __syncthreads();
+    PSAC_PHASE(5);  // barrier 3
 
     // ---- coalesced write-out: consecutive shared positions of one bin are consecutive in global memory
-    u8 dig[ITEMS];
-#pragma unroll
-    for (int i = 0; i < ITEMS; ++i) {
-        const int s = i * THREADS + tid;
-        if (FULL || s < valid) {
-            const Stage k = skeys[s];
-            const u32 d = src.digit(k);
-            dig[i] = (u8)d;
-            st_stream(kout + goff[d] + (u64)s, src.out_key(k));
-        }
-    }
-    if constexpr (Cfg::HAS_VALS) {
-        ValT* svals = reinterpret_cast<ValT*>(smem_raw);
-        __syncthreads();
-#pragma unroll
-        for (int j = 0; j < ITEMS; ++j) {
-            if (FULL || (woff + j * 32) < valid) svals[pos[j]] = val[j];
-        }
-        __syncthreads();
+    if constexpr (Cfg::PACKED) {
 #pragma unroll
         for (int i = 0; i < ITEMS; ++i) {
             const int s = i * THREADS + tid;
-            if (FULL || s < valid) st_stream(vout + goff[dig[i]] + (u64)s, svals[s]);
+            if (FULL || s < valid) {
+                const u64 e = reinterpret_cast<const u64*>(smem_raw)[s];
+                const Out k = (Out)(e >> 32);
+                u8 a = 0;
+                if constexpr (Cfg::HAS_AUX) a = saux[s];
+                const u32 d = Src::FROM_TEXT ? (u32)a : src.digit((Stage)k);
+                const u64 o = goff[d] + (u64)s;
+                st_stream(kout + o, k);
+                st_stream(vout + o, (ValT)(u32)e);
+                if constexpr (Cfg::HAS_AUX) aout[o] = a;
+            }
+        }
+    } else {
+        const Stage* skeys = reinterpret_cast<const Stage*>(smem_raw);
+        u8 dig[ITEMS];
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) {
+            const int s = i * THREADS + tid;
+            if (FULL || s < valid) {
+                const Stage k = skeys[s];
+                const u32 d = src.digit(k);
+                dig[i] = (u8)d;
+                const u64 o = goff[d] + (u64)s;
+                st_stream(kout + o, src.out_key(k));
+                if constexpr (Cfg::HAS_AUX) aout[o] = saux[s];
+            }
+        }
+        if constexpr (Cfg::HAS_VALS) {
+            ValT* svals = reinterpret_cast<ValT*>(smem_raw);
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < ITEMS; ++j) {
+                if (FULL || (woff + j * 32) < valid) svals[pos[j]] = val[j];
+            }
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < ITEMS; ++i) {
+                const int s = i * THREADS + tid;
+                if (FULL || s < valid) st_stream(vout + goff[dig[i]] + (u64)s, svals[s]);
+            }
         }
     }
+    PSAC_PHASE(6);  // write-out
 }
 
-template <class Src, typename ValT, int THREADS, int ITEMS>
-__global__ void __launch_bounds__(THREADS, 2) onesweep_pass_kernel(const Src src, typename Src::Out* __restrict__ kout, ValT* __restrict__ vout,
-                                                                   size_t n, const u64* __restrict__ gbase, u32* __restrict__ tile_counter,
-                                                                   u64* __restrict__ lookback, u32 epoch) {
-    using Cfg = PassCfg<typename Src::Stage, ValT, THREADS, ITEMS>;
+template <class Src, typename ValT, int THREADS, int ITEMS, bool HAS_AUX>
+__global__ void __launch_bounds__(THREADS, (sizeof(typename Src::Out) == 4 && sizeof(ValT) <= 4) ? 3 : 2)
+    onesweep_pass_kernel(const Src src, typename Src::Out* __restrict__ kout, ValT* __restrict__ vout, u8* __restrict__ aout, size_t n,
+                         const u64* __restrict__ gbase, u32* __restrict__ tile_counter, u64* __restrict__ lookback, u32 epoch) {
+    using Cfg = PassCfg<Src, ValT, THREADS, ITEMS, HAS_AUX>;
     constexpr int TILE = Cfg::TILE;
     static_assert(THREADS >= RADIX && THREADS % 32 == 0, "need one thread per digit");
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -344,9 +411,9 @@ __global__ void __launch_bounds__(THREADS, 2) onesweep_pass_kernel(const Src src
     const size_t tile = misc[0];
     const size_t base = tile * (size_t)TILE;
     if (n - base >= (size_t)TILE)
-        onesweep_tile<Src, ValT, THREADS, ITEMS, true>(smem_raw, src, kout, vout, base, TILE, gbase, lookback, tile, epoch);
+        onesweep_tile<Cfg, Src, ValT, true>(smem_raw, src, kout, vout, aout, base, TILE, gbase, lookback, tile, epoch);
     else
-        onesweep_tile<Src, ValT, THREADS, ITEMS, false>(smem_raw, src, kout, vout, base, (int)(n - base), gbase, lookback, tile, epoch);
+        onesweep_tile<Cfg, Src, ValT, false>(smem_raw, src, kout, vout, aout, base, (int)(n - base), gbase, lookback, tile, epoch);
 }
 
 // ------------------------------------------------------------------ hardware self-test of the ranking assumption
@@ -403,10 +470,11 @@ __global__ void __launch_bounds__(384) atoms_order_selftest_kernel(u32 seed, u32
 }
 
 // ------------------------------------------------------------------ host driver
-template <typename StageT, typename ValT>
+template <typename OutT, typename ValT>
 struct SortTuning {
     static constexpr int THREADS = 384;
-    static constexpr int ITEMS = (sizeof(StageT) + (std::is_same<ValT, NoVal>::value ? 0 : sizeof(ValT)) >= 16) ? 12 : 16;
+    // 32-bit pairs: 12 items keep the kernel under 56 registers -> 3 CTAs (36 warps) per SM; wider pairs: 2 CTAs per SM
+    static constexpr int ITEMS = (sizeof(OutT) == 4 && sizeof(ValT) <= 4) ? 12 : ((sizeof(OutT) + sizeof(ValT) >= 16) ? 12 : 16);
 };
 constexpr int MIN_TILE = 384 * 12;
 
@@ -419,20 +487,20 @@ struct RadixWorkspace {
     static size_t lookback_bytes_for(size_t n) { return div_up(n ? n : 1, (size_t)MIN_TILE) * RADIX * sizeof(u64); }
 };
 
-template <class Src, typename ValT>
-void launch_pass(const RadixWorkspace& ws, const Src& src, typename Src::Out* kout, ValT* vout, size_t n, const u64* gbase, u32* tile_counter,
+template <class Src, typename ValT, bool HAS_AUX>
+void launch_pass(const RadixWorkspace& ws, const Src& src, typename Src::Out* kout, ValT* vout, u8* aout, size_t n, const u64* gbase, u32* tile_counter,
                  u32 epoch, cudaStream_t stream) {
-    using T = SortTuning<typename Src::Stage, ValT>;
-    using Cfg = PassCfg<typename Src::Stage, ValT, T::THREADS, T::ITEMS>;
+    using T = SortTuning<typename Src::Out, ValT>;
+    using Cfg = PassCfg<Src, ValT, T::THREADS, T::ITEMS, HAS_AUX>;
     const size_t tiles = div_up(n, (size_t)Cfg::TILE);
     if (tiles * RADIX * sizeof(u64) > ws.lookback_bytes) throw std::string("radix pass: look-back workspace too small");
-    auto kern = onesweep_pass_kernel<Src, ValT, T::THREADS, T::ITEMS>;
+    auto kern = onesweep_pass_kernel<Src, ValT, T::THREADS, T::ITEMS, HAS_AUX>;
     static bool attr_set = false;
     if (!attr_set) {
         PSAC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
         attr_set = true;
     }
-    kern<<<(unsigned)tiles, T::THREADS, Cfg::SMEM, stream>>>(src, kout, vout, n, gbase, tile_counter, ws.lookback, epoch);
+    kern<<<(unsigned)tiles, T::THREADS, Cfg::SMEM, stream>>>(src, kout, vout, aout, n, gbase, tile_counter, ws.lookback, epoch);
 }
 
 // Sorts n pairs by key bits [begin_bit, end_bit).  Ping-pongs between (keys, vals) and (keys_alt, vals_alt);
@@ -455,22 +523,27 @@ bool radix_sort_pairs(const RadixWorkspace& ws, KeyT* keys, KeyT* keys_alt, ValT
     PSAC_CUDA(cudaMemsetAsync(ws.lookback, 0, RadixWorkspace::lookback_bytes_for(n), stream));
     bool in_alt = false;
     for (int p = 0; p < plan.npass; ++p) {
-        ArraySrc<KeyT, ValT> src{in_alt ? keys_alt : keys, in_alt ? vals_alt : vals, plan.shift[p], (1u << plan.bits[p]) - 1u};
-        launch_pass<ArraySrc<KeyT, ValT>, ValT>(ws, src, in_alt ? keys : keys_alt, in_alt ? vals : vals_alt, n, ws.gbase + p * RADIX, ws.counters + p,
-                                                (u32)(p + 1), stream);
+        ArraySrc<KeyT, ValT> src{in_alt ? keys_alt : keys, in_alt ? vals_alt : vals, nullptr, plan.shift[p], (1u << plan.bits[p]) - 1u};
+        launch_pass<ArraySrc<KeyT, ValT>, ValT, false>(ws, src, in_alt ? keys : keys_alt, in_alt ? vals : vals_alt, nullptr, n, ws.gbase + p * RADIX,
+                                                       ws.counters + p, (u32)(p + 1), stream);
         in_alt = !in_alt;
     }
     PSAC_CUDA(cudaGetLastError());
     return in_alt;
 }
 
-// First sort of a construction: keys come from the packed text.  kbuf / vbuf are two ping-pong buffers each; pass 1
-// writes buffer 0; returns the index (0/1) of the buffers holding the sorted carried keys and suffix indices.
-// Carried key = key >> plan.bits[0].  Events (optional) bracket histogram and digit passes for the per-phase stats.
+// Number of low key bits the first digit pass drops from the carried keys: its whole digit when the rest then fits
+// 32 bits (the digit travels on as the auxiliary byte), nothing otherwise (64-bit carried keys hold the whole key).
+static inline int carried_drop_bits(const RadixPlan& plan, int kbits) { return (kbits - plan.bits[0] <= 32) ? plan.bits[0] : 0; }
+
+// First sort of a construction: keys come from the packed text.  kbuf / vbuf / abuf are two ping-pong buffers each
+// (abuf only for 32-bit carried keys); pass 1 writes buffer 0; returns the index (0/1) of the buffers holding the
+// sorted carried keys, suffix indices and auxiliary bytes.  Events (optional) bracket histogram and digit passes.
 template <typename KeyC, typename IdxT>
 int radix_sort_suffixes(const RadixWorkspace& ws, const u64* text_stream, size_t n, int lbits, int key_chars, KeyC* const kbuf[2], IdxT* const vbuf[2],
-                        cudaStream_t stream, int sm_count, RadixPlan* plan_out, uint64_t* launches, cudaEvent_t ev_hist_done = nullptr,
+                        u8* const abuf[2], cudaStream_t stream, int sm_count, RadixPlan* plan_out, uint64_t* launches, cudaEvent_t ev_hist_done = nullptr,
                         cudaEvent_t ev_passes_begin = nullptr, cudaEvent_t ev_pass1_done = nullptr) {
+    constexpr bool AUX = sizeof(KeyC) == 4;
     const int kbits = key_chars * lbits;
     RadixPlan plan = make_radix_plan(0, kbits);
     if (plan_out) *plan_out = plan;
@@ -488,17 +561,19 @@ int radix_sort_suffixes(const RadixWorkspace& ws, const u64* text_stream, size_t
     if (ev_passes_begin) cudaEventRecord(ev_passes_begin, stream);
     PSAC_CUDA(cudaMemsetAsync(ws.counters, 0, MAX_PASSES * sizeof(u32), stream));
     PSAC_CUDA(cudaMemsetAsync(ws.lookback, 0, RadixWorkspace::lookback_bytes_for(n), stream));
-    const int drop = plan.bits[0];
+    const int drop = AUX ? plan.bits[0] : 0;
+    if (AUX && kbits - drop > 32) throw std::string("radix_sort_suffixes: carried key does not fit 32 bits");
     {
         const u64 C = (u64)key_chars;
-        TextSrc<KeyC, IdxT> src{text_stream, (u64)n, (n < C - 1) ? (u64)n : C - 1, lbits, kbits, drop, (1u << drop) - 1u};
-        launch_pass<TextSrc<KeyC, IdxT>, IdxT>(ws, src, kbuf[0], vbuf[0], n, ws.gbase, ws.counters, 1u, stream);
+        TextSrc<KeyC, IdxT> src{text_stream, (u64)n, (n < C - 1) ? (u64)n : C - 1, lbits, kbits, drop, (1u << plan.bits[0]) - 1u};
+        launch_pass<TextSrc<KeyC, IdxT>, IdxT, AUX>(ws, src, kbuf[0], vbuf[0], AUX ? abuf[0] : nullptr, n, ws.gbase, ws.counters, 1u, stream);
     }
     if (ev_pass1_done) cudaEventRecord(ev_pass1_done, stream);
     int cur = 0;
     for (int p = 1; p < plan.npass; ++p) {
-        ArraySrc<KeyC, IdxT> src{kbuf[cur], vbuf[cur], plan.shift[p] - drop, (1u << plan.bits[p]) - 1u};
-        launch_pass<ArraySrc<KeyC, IdxT>, IdxT>(ws, src, kbuf[1 - cur], vbuf[1 - cur], n, ws.gbase + p * RADIX, ws.counters + p, (u32)(p + 1), stream);
+        ArraySrc<KeyC, IdxT> src{kbuf[cur], vbuf[cur], AUX ? abuf[cur] : nullptr, plan.shift[p] - drop, (1u << plan.bits[p]) - 1u};
+        launch_pass<ArraySrc<KeyC, IdxT>, IdxT, AUX>(ws, src, kbuf[1 - cur], vbuf[1 - cur], AUX ? abuf[1 - cur] : nullptr, n, ws.gbase + p * RADIX,
+                                                     ws.counters + p, (u32)(p + 1), stream);
         cur = 1 - cur;
     }
     PSAC_CUDA(cudaGetLastError());

@@ -115,16 +115,17 @@ __device__ __forceinline__ u64 stream_lcp(const u64* __restrict__ stream, u64 n,
 //   bucket[q] = SA position of its head            (inclusive max-scan, warp shuffles + look-back)
 //   LCP at every new bucket boundary
 // Round 0 (FIRST): the sorted keys are the CARRIED keys of the first sort (the low `drop` bits were consumed by the
-//   first digit pass, radix_sort.cuh); they are re-read from the packed text only where a neighbour has the same
-//   carried key.  bucket[q] is written sequentially to bucket_out (the SA -> ISA permutation is done afterwards by
+//   first digit pass and travelled on as one auxiliary byte per suffix, radix_sort.cuh).  bucket[q] is written sequentially to bucket_out (the SA -> ISA permutation is done afterwards by
 //   a partitioned scatter, see isa_scatter_kernel) and, for small inputs only (isa != null), also scattered directly:
-//   ISA[suffix[q]] = bucket[q].  Only the COUNT of unresolved elements is produced; compact_first_kernel lists them.
+//   ISA[suffix[q]] = bucket[q].  The unresolved elements are listed up to a capacity; if more are found (repetitive
+//   text) compact_first_kernel lists them from the bucket ids once a large enough buffer exists.
 // Later rounds: ISA[suffix[q]] = bucket[q], SA[pos[q]] = suffix[q] directly (few elements), and
 //   unresolved' = elements whose bucket still has >= 2 members; their positions and head flags are
 //   compacted in order (exclusive sum-scan, look-back) for the next round.
 struct ResolveArgs {
     const void* keys;     // sorted keys (KeyC)
     const void* vals;     // sorted suffix indices (IdxT)
+    const u8* aux;        // round 0 with 32-bit carried keys: the key bits dropped by digit pass 1, else null
     const void* pos_in;   // SA position of element q (rounds >= 1)
     u64 m;                // elements this round
     u64 n;                // text length
@@ -132,40 +133,78 @@ struct ResolveArgs {
     void* isa;            // null in round 0 when the partitioned permute follows
     void* bucket_out;     // round 0: bucket id per sorted position (IdxT)
     void* lcp;            // may be null
-    void* pos_out;        // rounds >= 1: compacted positions of the still unresolved elements
+    void* pos_out;        // compacted positions of the still unresolved elements (first `cap` of them)
     u8* head_out;         // their head flags
+    u64 cap;              // capacity of pos_out / head_out (round 0: may be smaller than the number found)
     u64* counts;          // [0] unresolved elements, [1] unresolved buckets (atomic)
-    u64* lb_max;          // look-back channels, one u64 per tile each
+    u64* lb_max;          // per tile: aggregate after the reduce phase, exclusive prefix after tile_scan_kernel
     u64* lb_sum;
-    u32* tile_counter;
     const u64* stream;    // packed text
     int lbits;
     int C;                // round 0: characters in the key
-    int drop;             // round 0: low key bits missing from the carried keys
+    int drop;             // round 0: number of low key bits held in aux instead of the carried key
     int kbits;            // rounds >= 1: bits of the low key field (rank of suffix+h); the rest is the bucket
     u64 h;                // rounds >= 1: characters already known equal inside a bucket
     int padded_lcp;       // reference quirk: a used character has code 0 and matches the padding (see stream_lcp)
 };
 
 constexpr int RES_THREADS = 256;
-constexpr int RES_ITEMS = 4;
+constexpr int RES_ITEMS = 8;
 constexpr int RES_TILE = RES_THREADS * RES_ITEMS;
 
-template <typename IdxT, typename KeyC, bool FIRST>
+// out[i] = p[q0 - 1 + i] for i = 0 .. N+1 (0 outside [0, m)); the N inner elements come in as 128-bit loads when the
+// run is complete and 16-byte aligned
+template <typename T, int N>
+__device__ __forceinline__ void load_run(const T* __restrict__ p, u64 q0, u64 m, u64 (&out)[N + 2]) {
+    constexpr int PER = 16 / sizeof(T);
+    if (q0 + N <= m && ((reinterpret_cast<size_t>(p + q0) & 15) == 0) && (N % PER == 0)) {
+        const uint4* v = reinterpret_cast<const uint4*>(p + q0);
+#pragma unroll
+        for (int c = 0; c < N / PER; ++c) {
+            const uint4 t = __ldcs(v + c);
+            if (sizeof(T) == 4) {
+                out[1 + c * 4 + 0] = t.x;
+                out[1 + c * 4 + 1] = t.y;
+                out[1 + c * 4 + 2] = t.z;
+                out[1 + c * 4 + 3] = t.w;
+            } else {
+                out[1 + c * 2 + 0] = ((u64)t.y << 32) | t.x;
+                out[1 + c * 2 + 1] = ((u64)t.w << 32) | t.z;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; ++i) out[1 + i] = (q0 + i < m) ? (u64)p[q0 + i] : 0;
+    }
+    out[0] = (q0 >= 1 && q0 - 1 < m) ? (u64)p[q0 - 1] : 0;
+    out[N + 1] = (q0 + N < m) ? (u64)p[q0 + N] : 0;
+}
+template <int N>
+__device__ __forceinline__ void load_run_bytes(const u8* __restrict__ p, u64 q0, u64 m, u64 (&out)[N + 2]) {
+    static_assert(N == 8, "one 64-bit load per thread");
+    if (q0 + N <= m && ((reinterpret_cast<size_t>(p + q0) & 7) == 0)) {
+        const u64 t = __ldcs(reinterpret_cast<const u64*>(p + q0));
+#pragma unroll
+        for (int i = 0; i < N; ++i) out[1 + i] = (t >> (8 * i)) & 0xffu;
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; ++i) out[1 + i] = (q0 + i < m) ? (u64)p[q0 + i] : 0;
+    }
+    out[0] = (q0 >= 1 && q0 - 1 < m) ? (u64)p[q0 - 1] : 0;
+    out[N + 1] = (q0 + N < m) ? (u64)p[q0 + N] : 0;
+}
+
+// PHASE 0 = reduce: only the tile's aggregates (position of its last head, number of unresolved elements) are written;
+// PHASE 1 = apply: reads the tile's exclusive prefixes produced by tile_scan_kernel and writes the results.
+// (A single-pass chained scan was measured first: with ~500 k short tiles the look-back waits dominated, 14-17 ms
+// against ~5 ms for reduce / scan / apply, profiles/r1_notes.md.)
+template <typename IdxT, typename KeyC, bool FIRST, int PHASE>
 __global__ void __launch_bounds__(RES_THREADS) resolve_kernel(ResolveArgs A) {
     __shared__ u64 s_wmax[RES_THREADS / 32];
     __shared__ u32 s_wsum[RES_THREADS / 32];
-    __shared__ u64 s_excl_max;
-    __shared__ u64 s_excl_sum;
-    __shared__ u32 s_tile;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_tile = atomicAdd(A.tile_counter, 1u);
-    __syncthreads();
-    const u64 tile = s_tile;
-    const u64 ntiles = (A.m + RES_TILE - 1) / RES_TILE;
+    const u64 tile = blockIdx.x;
     const u64 q0 = tile * RES_TILE + (u64)tid * RES_ITEMS;
-    const KeyC* keys = reinterpret_cast<const KeyC*>(A.keys);
-    const IdxT* vals = reinterpret_cast<const IdxT*>(A.vals);
     const IdxT* pos_in = reinterpret_cast<const IdxT*>(A.pos_in);
     const u64 m = A.m, n = A.n;
     const int nbits = A.C * A.lbits;
@@ -173,30 +212,16 @@ __global__ void __launch_bounds__(RES_THREADS) resolve_kernel(ResolveArgs A) {
     // elements q0-1 .. q0+ITEMS (one neighbour on each side)
     u64 key[RES_ITEMS + 2];
     u64 suf[RES_ITEMS + 2];
+    load_run<KeyC, RES_ITEMS>(reinterpret_cast<const KeyC*>(A.keys), q0, m, key);
+    load_run<IdxT, RES_ITEMS>(reinterpret_cast<const IdxT*>(A.vals), q0, m, suf);
+    if (FIRST && A.drop > 0) {
+        // complete the carried keys with the bits digit pass 1 consumed
+        u64 low[RES_ITEMS + 2];
+        load_run_bytes<RES_ITEMS>(A.aux, q0, m, low);
+#pragma unroll
+        for (int i = 0; i < RES_ITEMS + 2; ++i) key[i] = (key[i] << A.drop) | low[i];
+    }
     u64 pos[RES_ITEMS];
-    bool in[RES_ITEMS + 2];
-#pragma unroll
-    for (int i = 0; i < RES_ITEMS + 2; ++i) {
-        const u64 q = q0 + i - 1;
-        in[i] = (q0 + i >= 1) && q < m;
-        key[i] = in[i] ? (u64)keys[q] : 0;
-        suf[i] = in[i] ? (u64)vals[q] : 0;
-    }
-    if (FIRST) {
-        // complete the carried keys with their dropped low bits where a neighbour ties
-        bool tie[RES_ITEMS + 2];
-#pragma unroll
-        for (int i = 0; i < RES_ITEMS + 2; ++i) {
-            tie[i] = false;
-            if (i > 0) tie[i] = tie[i] || (in[i] && in[i - 1] && key[i] == key[i - 1]);
-            if (i < RES_ITEMS + 1) tie[i] = tie[i] || (in[i] && in[i + 1] && key[i] == key[i + 1]);
-        }
-#pragma unroll
-        for (int i = 0; i < RES_ITEMS + 2; ++i) {
-            const u64 low = tie[i] ? stream_bits(A.stream, suf[i] * (u64)A.lbits + (u64)(nbits - A.drop), A.drop) : 0;
-            key[i] = (key[i] << A.drop) | low;
-        }
-    }
 #pragma unroll
     for (int i = 0; i < RES_ITEMS; ++i) {
         const u64 q = q0 + i;
@@ -260,37 +285,46 @@ __global__ void __launch_bounds__(RES_THREADS) resolve_kernel(ResolveArgs A) {
         cta_max = s_wmax[w] > cta_max ? s_wmax[w] : cta_max;
         cta_sum += s_wsum[w];
     }
-    if (tid == 0) s_excl_max = lookback_exclusive(A.lb_max, 1, tile, cta_max, 1u, OpMax());
-    if (tid == 32) {
-        if (FIRST) {
-            if (cta_sum) atomicAdd((unsigned long long*)&A.counts[0], (unsigned long long)cta_sum);
-            s_excl_sum = 0;
-        } else {
-            const u64 e = lookback_exclusive(A.lb_sum, 1, tile, (u64)cta_sum, 1u, OpSum());
-            s_excl_sum = e;
-            if (tile == ntiles - 1) atomicAdd((unsigned long long*)&A.counts[0], (unsigned long long)(e + cta_sum));
+    if (PHASE == 0) {
+        if (tid == 0) {
+            A.lb_max[tile] = cta_max;
+            A.lb_sum[tile] = cta_sum;
         }
+        if (lane == 0 && wb) atomicAdd((unsigned long long*)&A.counts[1], (unsigned long long)wb);
+        return;
     }
-    if (lane == 0 && wb) atomicAdd((unsigned long long*)&A.counts[1], (unsigned long long)wb);
-    __syncthreads();
-    u64 pre_max = s_excl_max;
+    u64 pre_max = A.lb_max[tile];  // exclusive prefixes over the preceding tiles (tile_scan_kernel)
     pre_max = wpre_max > pre_max ? wpre_max : pre_max;
     pre_max = texcl_max > pre_max ? texcl_max : pre_max;
-    const u64 pre_sum = s_excl_sum + wpre_sum + texcl_sum;
+    const u64 pre_sum = A.lb_sum[tile] + wpre_sum + texcl_sum;
 
     IdxT* sa = reinterpret_cast<IdxT*>(A.sa);
     IdxT* isa = reinterpret_cast<IdxT*>(A.isa);
     IdxT* lcp = reinterpret_cast<IdxT*>(A.lcp);
     IdxT* pos_out = reinterpret_cast<IdxT*>(A.pos_out);
     IdxT* bucket_out = reinterpret_cast<IdxT*>(A.bucket_out);
+    u64 bucket[RES_ITEMS];
+#pragma unroll
+    for (int i = 0; i < RES_ITEMS; ++i) bucket[i] = mx[i] > pre_max ? mx[i] : pre_max;
+    if (FIRST) {
+        // bucket ids leave sequentially: 128-bit stores where the run is complete
+        if (q0 + RES_ITEMS <= m && sizeof(IdxT) == 4 && ((reinterpret_cast<size_t>(bucket_out + q0) & 15) == 0)) {
+            uint4* o = reinterpret_cast<uint4*>(bucket_out + q0);
+#pragma unroll
+            for (int c = 0; c < RES_ITEMS / 4; ++c)
+                __stcs(o + c, make_uint4((u32)bucket[4 * c], (u32)bucket[4 * c + 1], (u32)bucket[4 * c + 2], (u32)bucket[4 * c + 3]));
+        } else {
+#pragma unroll
+            for (int i = 0; i < RES_ITEMS; ++i)
+                if (q0 + i < m) bucket_out[q0 + i] = (IdxT)bucket[i];
+        }
+    }
 #pragma unroll
     for (int i = 0; i < RES_ITEMS; ++i) {
         const u64 q = q0 + i;
         if (q >= m) break;
-        const u64 bucket = mx[i] > pre_max ? mx[i] : pre_max;
         const u64 s = suf[i + 1];
-        if (FIRST) st_stream(bucket_out + q, (IdxT)bucket);
-        if (isa != nullptr) isa[s] = (IdxT)bucket;
+        if (isa != nullptr) isa[s] = (IdxT)bucket[i];
         if (!FIRST) sa[pos[i]] = (IdxT)s;
         if (lcp != nullptr && head[i]) {
             if (q == 0) {
@@ -312,14 +346,54 @@ __global__ void __launch_bounds__(RES_THREADS) resolve_kernel(ResolveArgs A) {
                 lcp[pos[i]] = (IdxT)stream_lcp(A.stream, n, A.lbits, suf[i], s, A.h, A.padded_lcp != 0);
             }
         }
-        if (!FIRST) {
-            const bool unresolved = !(head[i] && head[i + 1]);
-            if (unresolved) {
-                const u64 o = pre_sum + un[i];
+        const bool unresolved = !(head[i] && head[i + 1]);
+        if (unresolved) {
+            const u64 o = pre_sum + un[i];
+            if (o < A.cap) {
                 pos_out[o] = (IdxT)pos[i];
                 A.head_out[o] = head[i] ? 1 : 0;
             }
         }
+    }
+}
+
+// Exclusive scan of the per-tile aggregates of a reduce phase, in place: mx[t] <- max of mx[0..t), sm[t] <- sum of
+// sm[0..t); the grand total of sm goes to *total.  One CTA; every thread owns a contiguous slice.
+__global__ void __launch_bounds__(1024) tile_scan_kernel(u64* __restrict__ mx, u64* __restrict__ sm, u64 ntiles, u64* __restrict__ total) {
+    __shared__ u64 w_max[32], w_sum[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u64 per = (ntiles + 1023) / 1024;
+    const u64 lo = (u64)tid * per, hi = (lo + per < ntiles) ? lo + per : ntiles;
+    u64 a_max = 0, a_sum = 0;
+    for (u64 t = lo; t < hi; ++t) {
+        a_max = mx[t] > a_max ? mx[t] : a_max;
+        a_sum += sm[t];
+    }
+    const u64 i_max = warp_inclusive_scan(a_max, OpMax());
+    const u64 i_sum = warp_inclusive_scan(a_sum, OpSum());
+    if (lane == 31) {
+        w_max[warp] = i_max;
+        w_sum[warp] = i_sum;
+    }
+    u64 e_max = __shfl_up_sync(0xffffffffu, i_max, 1);
+    if (lane == 0) e_max = 0;
+    u64 e_sum = i_sum - a_sum;
+    __syncthreads();
+    u64 tot = 0;
+    for (int w = 0; w < 32; ++w) {
+        if (w < warp) {
+            e_max = w_max[w] > e_max ? w_max[w] : e_max;
+            e_sum += w_sum[w];
+        }
+        tot += w_sum[w];
+    }
+    if (tid == 0 && total != nullptr) *total = tot;
+    for (u64 t = lo; t < hi; ++t) {
+        const u64 m = mx[t], c = sm[t];
+        mx[t] = e_max;
+        sm[t] = e_sum;
+        e_max = m > e_max ? m : e_max;
+        e_sum += c;
     }
 }
 
@@ -359,7 +433,10 @@ __global__ void __launch_bounds__(RES_THREADS) compact_first_kernel(const IdxT* 
         if (w == warp) wpre = cta_sum;
         cta_sum += s_wsum[w];
     }
-    if (tid == 0) s_excl_sum = lookback_exclusive(lb_sum, 1, tile, (u64)cta_sum, 1u, OpSum());
+    if (warp == 0) {
+        const u64 e = lookback_exclusive_warp(lb_sum, tile, (u64)cta_sum, 1u, OpSum());
+        if (lane == 0) s_excl_sum = e;
+    }
     __syncthreads();
     const u64 pre = s_excl_sum + wpre + (wincl - run_sum);
 #pragma unroll
@@ -447,7 +524,10 @@ __global__ void __launch_bounds__(RES_THREADS) round_keys_kernel(RoundKeyArgs A)
         if (w == warp) wpre = cta_max;
         cta_max = s_wmax[w] > cta_max ? s_wmax[w] : cta_max;
     }
-    if (tid == 0) s_excl_max = lookback_exclusive(A.lb_max, 1, tile, cta_max, 1u, OpMax());
+    if (warp == 0) {
+        const u64 e = lookback_exclusive_warp(A.lb_max, tile, cta_max, 1u, OpMax());
+        if (lane == 0) s_excl_max = e;
+    }
     __syncthreads();
     u64 pre = s_excl_max;
     pre = wpre > pre ? wpre : pre;
