@@ -152,6 +152,17 @@ constexpr int RES_THREADS = 256;
 constexpr int RES_ITEMS = 8;
 constexpr int RES_TILE = RES_THREADS * RES_ITEMS;
 
+// neighbours of a thread's run: the adjacent lanes hold them (all threads of a warp own consecutive runs); only the
+// first / last lane of a warp goes to memory.  Must be called by all 32 lanes.
+template <typename T, int N>
+__device__ __forceinline__ void load_halo(const T* __restrict__ p, u64 q0, u64 m, u64 (&out)[N + 2]) {
+    const unsigned lane = lane_id();
+    const u64 left = __shfl_up_sync(0xffffffffu, out[N], 1);
+    const u64 right = __shfl_down_sync(0xffffffffu, out[1], 1);
+    out[0] = (lane > 0) ? left : ((q0 >= 1 && q0 - 1 < m) ? (u64)p[q0 - 1] : 0);
+    out[N + 1] = (lane < 31) ? right : ((q0 + N < m) ? (u64)p[q0 + N] : 0);
+}
+
 // out[i] = p[q0 - 1 + i] for i = 0 .. N+1 (0 outside [0, m)); the N inner elements come in as 128-bit loads when the
 // run is complete and 16-byte aligned
 template <typename T, int N>
@@ -176,8 +187,7 @@ __device__ __forceinline__ void load_run(const T* __restrict__ p, u64 q0, u64 m,
 #pragma unroll
         for (int i = 0; i < N; ++i) out[1 + i] = (q0 + i < m) ? (u64)p[q0 + i] : 0;
     }
-    out[0] = (q0 >= 1 && q0 - 1 < m) ? (u64)p[q0 - 1] : 0;
-    out[N + 1] = (q0 + N < m) ? (u64)p[q0 + N] : 0;
+    load_halo<T, N>(p, q0, m, out);
 }
 template <int N>
 __device__ __forceinline__ void load_run_bytes(const u8* __restrict__ p, u64 q0, u64 m, u64 (&out)[N + 2]) {
@@ -190,8 +200,7 @@ __device__ __forceinline__ void load_run_bytes(const u8* __restrict__ p, u64 q0,
 #pragma unroll
         for (int i = 0; i < N; ++i) out[1 + i] = (q0 + i < m) ? (u64)p[q0 + i] : 0;
     }
-    out[0] = (q0 >= 1 && q0 - 1 < m) ? (u64)p[q0 - 1] : 0;
-    out[N + 1] = (q0 + N < m) ? (u64)p[q0 + N] : 0;
+    load_halo<u8, N>(p, q0, m, out);
 }
 
 // PHASE 0 = reduce: only the tile's aggregates (position of its last head, number of unresolved elements) are written;
