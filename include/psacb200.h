@@ -100,6 +100,24 @@ int psacb200_sort_pairs(psacb200_engine* e, void* d_keys, void* d_keys_alt, void
 /* Host-buffer wrapper of the above for tests. */
 int psacb200_sort_pairs_host(psacb200_engine* e, void* keys, void* vals, size_t n, int key_bytes, int val_bytes, int begin_bit, int end_bit);
 
+/* ---- sharded construction over the GPUs of one box: one process (rank) per GPU -------------------------------- */
+/* The reference is SPMD over an MPI communicator (suffix_array(const mxx::comm&), include/suffix_array.hpp:174): every
+ * rank calls construct() with its block of the text and ends up with its blocks of SA / ISA / LCP under mxx::blk_dist
+ * (ext/mxx/include/mxx/partition.hpp:283-331).  Here a rank is a process driving one GPU; the exchange steps run over
+ * NCCL on NVLink.  Rank 0 calls psacb200_comm_unique_id, the 128 bytes are handed to every rank by the caller's own
+ * channel (torch.distributed / MPI / a file), then every rank calls psacb200_comm_init on its engine (collective). */
+int psacb200_comm_unique_id(uint8_t id[128]);
+int psacb200_comm_init(psacb200_engine* e, const uint8_t id[128], int rank, int world);
+/* Collective.  d_text_local: this rank's block of the text (DEVICE), n_local = its size, which must be the blk_dist size
+ * for (n_global, world, rank) -- otherwise PSACB200_ERR_ARG, like the reference's std::runtime_error (suffix_array.hpp:226).
+ * Outputs (DEVICE, n_local elements of index_bytes each): this rank's blocks of SA, ISA (may be NULL) and LCP. */
+int psacb200_construct_sharded(psacb200_engine* e, const uint8_t* d_text_local, size_t n_local, size_t n_global, int index_bytes, unsigned flags,
+                               unsigned k, void* d_sa_local, void* d_isa_local, void* d_lcp_local);
+/* Host-side plans of the sharded construction (no GPU needed; used by the CPU tests): mxx::blk_dist, and the splitters
+ * over a key-prefix histogram (rank r sorts the bins [first[r], first[r+1]); first has p+1 entries, count p). */
+void psacb200_blk_dist(uint64_t n, int p, int r, uint64_t* start, uint64_t* size);
+int psacb200_choose_splitters(const uint64_t* hist, size_t nbins, uint64_t n, int p, uint64_t* first, uint64_t* count);
+
 #ifdef __cplusplus
 }
 #endif

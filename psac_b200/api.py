@@ -81,6 +81,13 @@ def lib():
         L.psacb200_construct_alphabet.argtypes = cargs[:6] + [C.c_void_p] + cargs[6:]
         L.psacb200_sort_pairs.argtypes = [C.c_void_p] * 5 + [C.c_size_t] + [C.c_int] * 4
         L.psacb200_sort_pairs_host.argtypes = [C.c_void_p] * 3 + [C.c_size_t] + [C.c_int] * 4
+        L.psacb200_comm_unique_id.argtypes = [C.c_void_p]
+        L.psacb200_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.psacb200_construct_sharded.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_uint, C.c_uint, C.c_void_p, C.c_void_p,
+                                                 C.c_void_p]
+        L.psacb200_blk_dist.argtypes = [C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.psacb200_blk_dist.restype = None
+        L.psacb200_choose_splitters.argtypes = [C.c_void_p, C.c_size_t, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -166,6 +173,24 @@ class Engine:
         f = lib().psacb200_construct_device if device else lib().psacb200_construct
         _check(f(self._h, _ptr(text_ptr), n, index_bytes, flags, k, _ptr(sa_ptr), _ptr(isa_ptr), _ptr(lcp_ptr)))
 
+    # ---- sharded construction (one rank per GPU)
+    @staticmethod
+    def comm_unique_id():
+        """128-byte NCCL id, to be created on rank 0 and handed to every rank (psacb200_comm_unique_id)."""
+        buf = np.zeros(128, np.uint8)
+        _check(lib().psacb200_comm_unique_id(_ptr(buf)))
+        return buf
+
+    def comm_init(self, unique_id, rank, world):
+        uid = np.ascontiguousarray(unique_id, np.uint8)
+        assert uid.size == 128
+        _check(lib().psacb200_comm_init(self._h, _ptr(uid), int(rank), int(world)))
+
+    def construct_sharded_ptr(self, text_ptr, n_local, n_global, index_bytes, flags, k, sa_ptr, isa_ptr, lcp_ptr):
+        """Collective; all pointers are DEVICE buffers of this rank's blocks."""
+        _check(lib().psacb200_construct_sharded(self._h, _ptr(text_ptr), n_local, n_global, index_bytes, flags, k, _ptr(sa_ptr), _ptr(isa_ptr),
+                                                _ptr(lcp_ptr)))
+
     def sort_pairs_host(self, keys, vals, begin_bit, end_bit):
         """In-place stable radix sort of numpy keys (uint32/uint64) and optional values by key bits [begin_bit, end_bit)."""
         assert keys.flags.c_contiguous and keys.dtype in (np.uint32, np.uint64)
@@ -224,3 +249,20 @@ class SuffixArray:
         self.n = self.local_size = t.size
         self.local_SA, self.local_B, self.local_LCP = r["sa"], r["isa"], None
         return self
+
+
+# ---------------------------------------------------------------------------------------------- host-side plans (no GPU)
+def blk_dist(n, p, r):
+    """(start, size) of rank r's block: mxx::blk_dist (reference ext/mxx/include/mxx/partition.hpp:283-331)."""
+    a, b = C.c_uint64(), C.c_uint64()
+    lib().psacb200_blk_dist(int(n), int(p), int(r), C.byref(a), C.byref(b))
+    return a.value, b.value
+
+
+def choose_splitters(hist, n, p):
+    """Key-range ownership over a key-prefix histogram: returns (first[p+1], count[p]); rank r sorts bins [first[r], first[r+1])."""
+    h = np.ascontiguousarray(hist, np.uint64)
+    first = np.zeros(p + 1, np.uint64)
+    count = np.zeros(p, np.uint64)
+    _check(lib().psacb200_choose_splitters(_ptr(h), h.size, int(n), int(p), _ptr(first), _ptr(count)))
+    return first, count

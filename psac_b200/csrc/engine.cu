@@ -75,7 +75,9 @@ struct psacb200_engine {
     cudaStream_t stream = nullptr;
     size_t device_bytes = 0;
     uint64_t launches = 0;
-    DevBuf text, packed, keys[2], vals[2], aux[2], isa, lcp, small, lookback, rk[2], rv[2], rp[2], rh[2], scratch;
+    DevBuf text, packed, keys[2], vals[2], aux[2], isa, lcp, small, lookback, rk[2], rv[2], rp[2], rh[2], scratch, rep[3];
+    void* nccl_comm = nullptr;  // ncclComm_t of the sharded construction (sharded.cuh), one rank per engine
+    int shard_rank = 0, shard_world = 1;
     u64* h_pinned = nullptr;  // 512 u64 of pinned host memory for small read-backs
     cudaEvent_t ev_begin[PH_COUNT], ev_end[PH_COUNT];
     bool ev_used[PH_COUNT];
@@ -87,7 +89,8 @@ struct psacb200_engine {
     u64* byte_hist() const { return small.as<u64>() + 2 * MAX_PASSES * RADIX; }
     u64* counts() const { return byte_hist() + 256; }
     u32* counters() const { return reinterpret_cast<u32*>(counts() + 8); }
-    static size_t small_bytes() { return (2 * MAX_PASSES * RADIX + 256 + 8) * sizeof(u64) + 64 * sizeof(u32); }
+    u64* shard_meta() const { return reinterpret_cast<u64*>(counters() + 64); }  // 64 u64 of small per-rank exchange data
+    static size_t small_bytes() { return (2 * MAX_PASSES * RADIX + 256 + 8) * sizeof(u64) + 64 * sizeof(u32) + 64 * sizeof(u64); }
 
     RadixWorkspace radix_ws() const {
         RadixWorkspace ws;
@@ -318,6 +321,13 @@ void construct_core(psacb200_engine* e, u64 n, int index_bytes, unsigned flags, 
     R.kbits = 0;
     R.h = 0;
     R.padded_lcp = alpha.zero_code_used ? 1 : 0;
+    R.pos_base = 0;
+    R.halo = nullptr;
+    R.sa_lo = 0;
+    R.sa_hi = n;
+    R.isa_lo = 0;
+    R.isa_hi = n;
+    R.suf_out = nullptr;
     launch_resolve<IdxT, KeyC>(e, true, R);
     e->end(PH_RESOLVE);
     u64 m = 0, nb = 0;
@@ -467,6 +477,29 @@ void prepare_text(psacb200_engine* e, const u8* d_text, u64 n, const uint8_t* us
     e->end(PH_PACK);
 }
 
+void fill_phase_stats(psacb200_engine* e) {
+    psacb200_stats& S = e->stats;
+    S.device_bytes = e->device_bytes;
+    S.ms_total = e->ms(PH_TOTAL);
+    S.ms_h2d = e->ms(PH_H2D);
+    S.ms_alphabet = e->ms(PH_ALPHABET);
+    S.ms_pack = e->ms(PH_PACK);
+    S.ms_keygen = 0.f;  // the first key is generated inside digit pass 1
+    S.ms_isa = e->ms(PH_ISA);
+    {
+        float t1 = 0.f;  // digit pass 1 (reads the packed text) runs from the start of PH_SORT to ev_end[PH_PASS1]
+        if (e->ev_used[PH_SORT] && cudaEventElapsedTime(&t1, e->ev_begin[PH_SORT], e->ev_end[PH_PASS1]) == cudaSuccess) S.ms_sort_pass1 = t1;
+        else cudaGetLastError();
+    }
+    S.ms_hist = e->ms(PH_HIST);
+    S.ms_sort = e->ms(PH_SORT);
+    S.ms_resolve = e->ms(PH_RESOLVE);
+    S.ms_rounds = e->ms(PH_ROUNDS);
+    S.ms_output = e->ms(PH_OUTPUT);
+    S.ms_d2h = e->ms(PH_D2H);
+    S.ms_sort_pass_avg = S.sort_passes > 1 ? (S.ms_sort - S.ms_sort_pass1) / (float)(S.sort_passes - 1) : S.ms_sort;
+}
+
 int construct_entry(psacb200_engine* e, const u8* text, bool text_is_host, size_t n, int index_bytes, unsigned flags, unsigned k, const uint8_t* lut,
                     void* sa_out, void* isa_out, void* lcp_out) {
     if (!e) {
@@ -508,26 +541,7 @@ int construct_entry(psacb200_engine* e, const u8* text, bool text_is_host, size_
         }
         e->end(PH_TOTAL);
         PSAC_CUDA(cudaStreamSynchronize(e->stream));
-        psacb200_stats& S = e->stats;
-        S.device_bytes = e->device_bytes;
-        S.ms_total = e->ms(PH_TOTAL);
-        S.ms_h2d = e->ms(PH_H2D);
-        S.ms_alphabet = e->ms(PH_ALPHABET);
-        S.ms_pack = e->ms(PH_PACK);
-        S.ms_keygen = 0.f;  // the first key is generated inside digit pass 1
-        S.ms_isa = e->ms(PH_ISA);
-        {
-            float t1 = 0.f;  // digit pass 1 (reads the packed text) runs from the start of PH_SORT to ev_end[PH_PASS1]
-            if (e->ev_used[PH_SORT] && cudaEventElapsedTime(&t1, e->ev_begin[PH_SORT], e->ev_end[PH_PASS1]) == cudaSuccess) S.ms_sort_pass1 = t1;
-            else cudaGetLastError();
-        }
-        S.ms_hist = e->ms(PH_HIST);
-        S.ms_sort = e->ms(PH_SORT);
-        S.ms_resolve = e->ms(PH_RESOLVE);
-        S.ms_rounds = e->ms(PH_ROUNDS);
-        S.ms_output = e->ms(PH_OUTPUT);
-        S.ms_d2h = e->ms(PH_D2H);
-        S.ms_sort_pass_avg = S.sort_passes > 1 ? (S.ms_sort - S.ms_sort_pass1) / (float)(S.sort_passes - 1) : S.ms_sort;
+        fill_phase_stats(e);
         return PSACB200_OK;
     } catch (const cuda_failure& f) {
         set_last_error(std::string("CUDA error: ") + cudaGetErrorString(f.err) + " in " + f.what + " at " + f.file + ":" + std::to_string(f.line));
@@ -578,6 +592,8 @@ bool sort_dispatch_val(psacb200_engine* e, void* k, void* ka, void* v, void* va,
 }
 
 }  // namespace
+
+#include "sharded.cuh"
 
 // ================================================================================================ C ABI
 extern "C" {
@@ -639,12 +655,13 @@ void psacb200_destroy(psacb200_engine* e) {
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->stream);
     DevBuf* all[] = {&e->text, &e->packed, &e->keys[0], &e->keys[1], &e->vals[0], &e->vals[1], &e->aux[0], &e->aux[1], &e->isa, &e->lcp, &e->small, &e->lookback,
-                     &e->rk[0], &e->rk[1], &e->rv[0], &e->rv[1], &e->rp[0], &e->rp[1], &e->rh[0], &e->rh[1], &e->scratch};
+                     &e->rk[0], &e->rk[1], &e->rv[0], &e->rv[1], &e->rp[0], &e->rp[1], &e->rh[0], &e->rh[1], &e->scratch, &e->rep[0], &e->rep[1], &e->rep[2]};
     for (DevBuf* b : all) b->release(nullptr);
     for (int i = 0; i < PH_COUNT; ++i) {
         cudaEventDestroy(e->ev_begin[i]);
         cudaEventDestroy(e->ev_end[i]);
     }
+    if (e->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(reinterpret_cast<ncclComm_t>(e->nccl_comm));
     if (e->h_pinned) cudaFreeHost(e->h_pinned);
     cudaStreamDestroy(e->stream);
     delete e;
@@ -772,6 +789,113 @@ int psacb200_sort_pairs_host(psacb200_engine* e, void* keys, void* vals, size_t 
         PSAC_CUDA(cudaStreamSynchronize(e->stream));
         return PSACB200_OK;
     });
+}
+
+
+// ---- sharded construction over the GPUs of one box (sharded.cuh)
+int psacb200_comm_unique_id(uint8_t id[128]) {
+    return guarded([&]() -> int {
+        static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+        g_nccl.load();
+        ncclUniqueId u;
+        PSAC_NCCL(g_nccl.GetUniqueId(&u));
+        memcpy(id, &u, 128);
+        return PSACB200_OK;
+    });
+}
+
+int psacb200_comm_init(psacb200_engine* e, const uint8_t id[128], int rank, int world) {
+    if (!e || !id) {
+        set_last_error("null argument");
+        return PSACB200_ERR_ARG;
+    }
+    return guarded([&]() -> int {
+        if (world < 1 || world > 16 || rank < 0 || rank >= world) throw arg_failure{"bad rank / world size (1..16 ranks of one box)"};
+        PSAC_CUDA(cudaSetDevice(e->device));
+        g_nccl.load();
+        if (e->nccl_comm) {
+            g_nccl.CommDestroy(reinterpret_cast<ncclComm_t>(e->nccl_comm));
+            e->nccl_comm = nullptr;
+        }
+        ncclUniqueId u;
+        memcpy(&u, id, 128);
+        ncclComm_t c;
+        PSAC_NCCL(g_nccl.CommInitRank(&c, world, u, rank));
+        e->nccl_comm = c;
+        e->shard_rank = rank;
+        e->shard_world = world;
+        return PSACB200_OK;
+    });
+}
+
+int psacb200_construct_sharded(psacb200_engine* e, const uint8_t* d_text_local, size_t n_local, size_t n_global, int index_bytes, unsigned flags, unsigned k,
+                               void* d_sa_local, void* d_isa_local, void* d_lcp_local) {
+    if (!e) {
+        set_last_error("null engine");
+        return PSACB200_ERR_ARG;
+    }
+    return guarded([&]() -> int {
+        if (!e->nccl_comm) throw arg_failure{"psacb200_comm_init has not been called on this engine"};
+        if (index_bytes != 4 && index_bytes != 8) throw arg_failure{"index_bytes must be 4 or 8"};
+        if (index_bytes == 4 && (u64)n_global >= (1ull << 32)) throw arg_failure{"32-bit index too small for this text (reference asserts the same)"};
+        if (n_local > 0 && (!d_text_local || !d_sa_local)) throw arg_failure{"null text / sa_out"};
+        if ((flags & PSACB200_LCP) && n_local > 0 && !d_lcp_local) throw arg_failure{"PSACB200_LCP set but lcp_out is null"};
+        PSAC_CUDA(cudaSetDevice(e->device));
+        ShardComm C{reinterpret_cast<ncclComm_t>(e->nccl_comm), e->shard_rank, e->shard_world};
+        const u64 n = n_global;
+        if (n == 0) return PSACB200_OK;
+        bool sharded = C.world > 1 && n >= (u64)C.world * (1ull << 16);
+        if (sharded) {
+            memset(&e->stats, 0, sizeof(e->stats));
+            memset(e->ev_used, 0, sizeof(e->ev_used));
+            e->stats.n = n;
+            e->begin(PH_TOTAL);
+            sharded = construct_sharded_core(e, C, d_text_local, n_local, n, index_bytes, flags, k, d_sa_local, d_isa_local, d_lcp_local);
+            e->end(PH_TOTAL);
+            PSAC_CUDA(cudaStreamSynchronize(e->stream));
+            if (sharded) {
+                fill_phase_stats(e);
+                return PSACB200_OK;
+            }
+            if (n > (1ull << 32)) throw arg_failure{"sharded construction: text too skewed / repetitive for this round's sharded scheme and too large to build replicated"};
+        }
+        {
+            // too small (or too skewed) to shard: every GPU builds the whole index from the all-gathered text and keeps its block
+            gather_text(e, C, d_text_local, n_local, n);
+            const BlkDist blk(n, C.world);
+            const bool lcp = (flags & PSACB200_LCP) != 0;
+            size_t* tot = &e->device_bytes;
+            for (int i = 0; i < 3; ++i)
+                if (i < 2 || lcp) e->rep[i].reserve(n * (size_t)index_bytes + 64, tot);
+            int rc = construct_entry(e, e->text.as<u8>(), false, n, index_bytes, flags, k, nullptr, e->rep[0].p, e->rep[1].p, lcp ? e->rep[2].p : nullptr);
+            if (rc != PSACB200_OK) return rc;
+            const size_t o = blk.start(C.rank) * (size_t)index_bytes, bytes = n_local * (size_t)index_bytes;
+            if (bytes) {
+                PSAC_CUDA(cudaMemcpyAsync(d_sa_local, e->rep[0].as<u8>() + o, bytes, cudaMemcpyDeviceToDevice, e->stream));
+                if (d_isa_local) PSAC_CUDA(cudaMemcpyAsync(d_isa_local, e->rep[1].as<u8>() + o, bytes, cudaMemcpyDeviceToDevice, e->stream));
+                if (lcp) PSAC_CUDA(cudaMemcpyAsync(d_lcp_local, e->rep[2].as<u8>() + o, bytes, cudaMemcpyDeviceToDevice, e->stream));
+            }
+            PSAC_CUDA(cudaStreamSynchronize(e->stream));
+            return PSACB200_OK;
+        }
+    });
+}
+
+// host-side plans of the sharded construction, exposed for the CPU tests (no GPU needed)
+void psacb200_blk_dist(uint64_t n, int p, int r, uint64_t* start, uint64_t* size) {
+    BlkDist b(n, p);
+    if (start) *start = b.start(r);
+    if (size) *size = b.size(r);
+}
+
+int psacb200_choose_splitters(const uint64_t* hist, size_t nbins, uint64_t n, int p, uint64_t* first_out, uint64_t* count_out) {
+    if (!hist || !first_out || !count_out || p < 1) return PSACB200_ERR_ARG;
+    std::vector<size_t> first;
+    std::vector<u64> count;
+    choose_splitters(hist, nbins, n, p, first, count);
+    for (int r = 0; r <= p; ++r) first_out[r] = first[r];
+    for (int r = 0; r < p; ++r) count_out[r] = count[r];
+    return PSACB200_OK;
 }
 
 }  // extern "C"

@@ -146,6 +146,12 @@ struct ResolveArgs {
     int kbits;            // rounds >= 1: bits of the low key field (rank of suffix+h); the rest is the bucket
     u64 h;                // rounds >= 1: characters already known equal inside a bucket
     int padded_lcp;       // reference quirk: a used character has code 0 and matches the padding (see stream_lcp)
+    // ---- sharded construction (sharded.cuh); single GPU: pos_base = 0, no halo, windows = [0, n), suf_out = null
+    u64 pos_base;         // round 0: global SA position of local element 0
+    const u64* halo;      // round 0: {key, suffix} of the last element of the previous shard, or null
+    u64 sa_lo, sa_hi;     // rounds >= 1: SA / LCP positions owned by this shard (sa, lcp point at position sa_lo)
+    u64 isa_lo, isa_hi;   // text positions whose ISA entries this shard owns (isa points at entry isa_lo)
+    void* suf_out;        // rounds >= 1: suffixes of the still unresolved elements (replicated rounds), or null
 };
 
 constexpr int RES_THREADS = 256;
@@ -230,11 +236,16 @@ __global__ void __launch_bounds__(RES_THREADS) resolve_kernel(ResolveArgs A) {
 #pragma unroll
         for (int i = 0; i < RES_ITEMS + 2; ++i) key[i] = (key[i] << A.drop) | low[i];
     }
+    const bool has_halo = FIRST && A.halo != nullptr;
+    if (has_halo && q0 == 0) {  // the element before local position 0 lives on the previous shard
+        key[0] = A.halo[0];
+        suf[0] = A.halo[1];
+    }
     u64 pos[RES_ITEMS];
 #pragma unroll
     for (int i = 0; i < RES_ITEMS; ++i) {
         const u64 q = q0 + i;
-        pos[i] = FIRST ? q : ((q < m) ? (u64)pos_in[q] : 0);
+        pos[i] = FIRST ? (q + A.pos_base) : ((q < m) ? (u64)pos_in[q] : 0);
     }
     // head flags for q0 .. q0+ITEMS (the last one only feeds the "unresolved" test); head[m] = true
     bool head[RES_ITEMS + 1];
@@ -244,7 +255,7 @@ __global__ void __launch_bounds__(RES_THREADS) resolve_kernel(ResolveArgs A) {
     for (int i = 0; i < RES_ITEMS + 1; ++i) {
         const u64 q = q0 + i;
         bool hd;
-        if (q >= m || q == 0) {
+        if (q >= m || (q == 0 && !has_halo)) {
             hd = true;
         } else {
             hd = key[i + 1] != key[i];
@@ -333,10 +344,11 @@ __global__ void __launch_bounds__(RES_THREADS) resolve_kernel(ResolveArgs A) {
         const u64 q = q0 + i;
         if (q >= m) break;
         const u64 s = suf[i + 1];
-        if (isa != nullptr) isa[s] = (IdxT)bucket[i];
-        if (!FIRST) sa[pos[i]] = (IdxT)s;
-        if (lcp != nullptr && head[i]) {
-            if (q == 0) {
+        if (isa != nullptr && s >= A.isa_lo && s < A.isa_hi) isa[s - A.isa_lo] = (IdxT)bucket[i];
+        const bool own_pos = FIRST || (pos[i] >= A.sa_lo && pos[i] < A.sa_hi);
+        if (!FIRST && own_pos) sa[pos[i] - A.sa_lo] = (IdxT)s;
+        if (lcp != nullptr && head[i] && own_pos) {
+            if (q == 0 && !has_halo) {
                 if (FIRST) lcp[0] = 0;
             } else if (FIRST) {
                 const u64 sp = suf[i];
@@ -352,7 +364,7 @@ __global__ void __launch_bounds__(RES_THREADS) resolve_kernel(ResolveArgs A) {
                 lcp[q] = (IdxT)c;
             } else if ((key[i] >> A.kbits) == (key[i + 1] >> A.kbits)) {
                 // same old bucket, different rank of suffix+h: the first h characters agree
-                lcp[pos[i]] = (IdxT)stream_lcp(A.stream, n, A.lbits, suf[i], s, A.h, A.padded_lcp != 0);
+                lcp[pos[i] - A.sa_lo] = (IdxT)stream_lcp(A.stream, n, A.lbits, suf[i], s, A.h, A.padded_lcp != 0);
             }
         }
         const bool unresolved = !(head[i] && head[i + 1]);
@@ -361,6 +373,7 @@ __global__ void __launch_bounds__(RES_THREADS) resolve_kernel(ResolveArgs A) {
             if (o < A.cap) {
                 pos_out[o] = (IdxT)pos[i];
                 A.head_out[o] = head[i] ? 1 : 0;
+                if (A.suf_out != nullptr) reinterpret_cast<IdxT*>(A.suf_out)[o] = (IdxT)s;
             }
         }
     }
@@ -491,6 +504,8 @@ struct RoundKeyArgs {
     void* vals;
     u64* lb_max;
     u32* tile_counter;
+    const void* suf_in;   // sharded rounds: suffix of element q (instead of sa[pos[q]]), or null
+    const u64* rank2;     // sharded rounds: ISA[suffix + h] + 1 (0 past the end) gathered across the shards, or null
 };
 
 template <typename IdxT>
@@ -516,9 +531,12 @@ __global__ void __launch_bounds__(RES_THREADS) round_keys_kernel(RoundKeyArgs A)
         k2[i] = 0;
         if (q < A.m) {
             if (A.head[q]) run_max = q;  // q increases, so "max" is simply the latest head
-            const u64 s = (u64)sa[pos[q]];
+            const u64 s = A.suf_in != nullptr ? (u64)reinterpret_cast<const IdxT*>(A.suf_in)[q] : (u64)sa[pos[q]];
             suf[i] = s;
-            k2[i] = (s + A.h < A.n) ? (u64)isa[s + A.h] + 1 : 0;
+            if (A.rank2 != nullptr)
+                k2[i] = A.rank2[q];
+            else
+                k2[i] = (s + A.h < A.n) ? (u64)isa[s + A.h] + 1 : 0;
         }
         mx[i] = run_max;
     }

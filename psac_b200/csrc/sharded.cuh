@@ -1,0 +1,681 @@
+// psac-b200: suffix-array construction sharded over the GPUs of one NVLink / NVSwitch box (one process per GPU).
+//
+// Reference behaviour restated: text, SA, ISA and LCP are block-distributed over p ranks exactly
+// like mxx::blk_dist (ext/mxx/include/mxx/partition.hpp:283-331: the first n % p ranks hold one element more); the
+// reference moves (B1, B2, index) tuples through a distributed sample sort (include/idxsort.hpp:22-83 ->
+// ext/mxx/include/mxx/samplesort.hpp:292-444) and (index, rank) pairs through bulk_permute_inplace
+// (include/bulk_permute.hpp:14-73) every round.
+//
+// B200-first design, not that schedule:
+//   * the PACKED text is replicated on every GPU (2 bits per DNA character: 8 Gi characters = 2 GiB of 180 GB HBM; one
+//     all-gather over NVLink).  Every rank can then form the sort key of ANY suffix locally, so the sample-sort tuple
+//     exchange disappears: rank r simply selects, from the whole text, the suffixes whose key prefix falls in its
+//     splitter range and sorts them locally.  Splitters are exact bin boundaries of a global 14-bit key-prefix
+//     histogram (all-gathered, 128 KiB per rank), so equal keys never straddle two ranks and round 0 needs no carry.
+//   * the only bulk exchange is the SA -> ISA permute: (suffix, bucket id) pairs partitioned by owner with one radix
+//     pass and moved with grouped ncclSend / ncclRecv (all-to-all-v on NVSwitch), then scattered locally; plus the
+//     final re-balancing of SA / LCP from key-range ownership to exact blocks (contiguous ranges to <= 2 neighbours).
+//   * later rounds touch only the unresolved suffixes (n / 2^10 of random text): their lists are all-gathered and the
+//     rounds run replicated on every GPU; the rank look-ups ISA[s + h] are answered by the owning shard and combined with
+//     one ncclAllReduce per round; every shard applies the updates that fall in its own SA / ISA windows.
+// Limits of this round (checked, reported as errors): the unresolved set must fit one GPU (replicated rounds) and the
+// key-prefix histogram must balance within the 2x capacity; inputs too small to shard run replicated on every GPU.
+#pragma once
+#include <dlfcn.h>
+#include <nccl.h>
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------ NCCL (dlopen)
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+
+    void load() {
+        if (handle) return;
+        // prefer the copy torch already loaded into this process, then the loader's search path
+        handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+        if (!handle) handle = dlopen("libnccl.so.2", RTLD_NOW);
+        if (!handle) handle = dlopen("libnccl.so", RTLD_NOW);
+        if (!handle) throw std::string("cannot load libnccl.so.2: ") + dlerror();
+#define PSAC_NCCL_SYM(field, name)                                                \
+    field = reinterpret_cast<decltype(field)>(dlsym(handle, name));               \
+    if (!field) throw std::string("libnccl is missing symbol ") + name
+        PSAC_NCCL_SYM(GetUniqueId, "ncclGetUniqueId");
+        PSAC_NCCL_SYM(CommInitRank, "ncclCommInitRank");
+        PSAC_NCCL_SYM(CommDestroy, "ncclCommDestroy");
+        PSAC_NCCL_SYM(AllReduce, "ncclAllReduce");
+        PSAC_NCCL_SYM(AllGather, "ncclAllGather");
+        PSAC_NCCL_SYM(Broadcast, "ncclBroadcast");
+        PSAC_NCCL_SYM(Send, "ncclSend");
+        PSAC_NCCL_SYM(Recv, "ncclRecv");
+        PSAC_NCCL_SYM(GroupStart, "ncclGroupStart");
+        PSAC_NCCL_SYM(GroupEnd, "ncclGroupEnd");
+        PSAC_NCCL_SYM(GetErrorString, "ncclGetErrorString");
+#undef PSAC_NCCL_SYM
+    }
+};
+NcclApi g_nccl;
+
+#define PSAC_NCCL(call)                                                                                          \
+    do {                                                                                                         \
+        ncclResult_t _r = (call);                                                                                \
+        if (_r != ncclSuccess) throw std::string("NCCL error: ") + g_nccl.GetErrorString(_r) + " in " + #call;   \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------ host-side plans
+// mxx::blk_dist (reference ext/mxx/include/mxx/partition.hpp:283-331)
+struct BlkDist {
+    u64 n = 0;
+    int p = 1;
+    u64 base = 0, rem = 0;
+    BlkDist() {}
+    BlkDist(u64 n_, int p_) : n(n_), p(p_), base(n_ / (u64)p_), rem(n_ % (u64)p_) {}
+    u64 size(int r) const { return base + ((u64)r < rem ? 1 : 0); }
+    u64 start(int r) const { return base * (u64)r + std::min<u64>((u64)r, rem); }
+    int owner(u64 g) const {
+        const u64 cut = rem * (base + 1);
+        return g < cut ? (int)(g / (base + 1)) : (int)(rem + (g - cut) / base);
+    }
+};
+
+// Splitters over a histogram of key-prefix bins: rank r owns bins [first[r], first[r+1]); greedy cut at the first bin
+// boundary where the running count reaches r * n / p, so that no bin (= no set of equal keys) is split.
+static void choose_splitters(const u64* hist, size_t nbins, u64 n, int p, std::vector<size_t>& first, std::vector<u64>& count) {
+    first.assign(p + 1, nbins);
+    count.assign(p, 0);
+    first[0] = 0;
+    u64 run = 0;
+    int r = 1;
+    for (size_t b = 0; b < nbins; ++b) {
+        while (r < p && run >= (n / (u64)p) * (u64)r + std::min<u64>((u64)r, n % (u64)p)) first[r++] = b;
+        run += hist[b];
+    }
+    while (r < p) first[r++] = nbins;
+    for (int q = 0; q < p; ++q)
+        for (size_t b = first[q]; b < first[q + 1]; ++b) count[q] += hist[b];
+}
+
+// ------------------------------------------------------------------------------------------------ kernels
+constexpr int PREFIX_BITS_MAX = 14;
+
+// histogram of the key-prefix bins of the suffixes [g0, g0 + cnt)
+__global__ void __launch_bounds__(512) prefix_hist_kernel(const u64* __restrict__ stream, u64 g0, u64 cnt, int lbits, int pbits, u64* __restrict__ hist) {
+    extern __shared__ u32 sh_hist[];
+    const u32 nb = 1u << pbits;
+    for (u32 e = threadIdx.x; e < nb; e += blockDim.x) sh_hist[e] = 0;
+    __syncthreads();
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += (u64)gridDim.x * blockDim.x)
+        atomicAdd(&sh_hist[(u32)stream_bits(stream, (g0 + i) * (u64)lbits, pbits)], 1u);
+    __syncthreads();
+    for (u32 e = threadIdx.x; e < nb; e += blockDim.x) {
+        const u32 c = sh_hist[e];
+        if (c) atomicAdd((unsigned long long*)&hist[e], (unsigned long long)c);
+    }
+}
+
+// Selection of the suffixes whose key-prefix bin lies in [bin_lo, bin_hi), in ascending suffix order (the suffixes that
+// run past the end of the text are handled by select_tails_kernel and come first: see TextSrc in radix_sort.cuh for why).
+// PHASE 0 counts per tile, PHASE 1 writes (key, suffix) at the tile's exclusive prefix (tile_scan_kernel) + *base.
+constexpr int SEL_THREADS = 256;
+constexpr int SEL_ITEMS = 32;
+constexpr int SEL_TILE = SEL_THREADS * SEL_ITEMS;
+
+template <int PHASE>
+__global__ void __launch_bounds__(SEL_THREADS) select_kernel(const u64* __restrict__ stream, u64 n_main, int lbits, int kbits, int pbits, u32 bin_lo,
+                                                             u32 bin_hi, u64* __restrict__ tile_sum, const u64* __restrict__ base,
+                                                             u64* __restrict__ keys_out, u64* __restrict__ suf_out) {
+    __shared__ u32 s_w[SEL_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u64 g0 = (u64)blockIdx.x * SEL_TILE + (u64)tid * SEL_ITEMS;
+    u32 mask = 0;
+    if (g0 < n_main) {
+#pragma unroll 4
+        for (int i = 0; i < SEL_ITEMS; ++i) {
+            const u64 g = g0 + i;
+            if (g < n_main) {
+                const u32 bin = (u32)stream_bits(stream, g * (u64)lbits, pbits);
+                if (bin >= bin_lo && bin < bin_hi) mask |= 1u << i;
+            }
+        }
+    }
+    const u32 cnt = __popc(mask);
+    const u32 incl = warp_inclusive_sum_u32(cnt);
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    u32 pre = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < SEL_THREADS / 32; ++w) {
+        if (w < warp) pre += s_w[w];
+        tot += s_w[w];
+    }
+    if (PHASE == 0) {
+        if (tid == 0) tile_sum[blockIdx.x] = tot;
+        return;
+    }
+    u64 o = *base + tile_sum[blockIdx.x] + pre + (incl - cnt);
+    while (mask) {
+        const int i = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const u64 g = g0 + i;
+        keys_out[o] = stream_extract(stream, g, lbits, kbits);
+        suf_out[o] = g;
+        ++o;
+    }
+}
+
+// the T <= 63 suffixes that run past the end of the text, shortest first; *count = how many fall in [bin_lo, bin_hi)
+__global__ void __launch_bounds__(64) select_tails_kernel(const u64* __restrict__ stream, u64 n, u64 T, int lbits, int kbits, int pbits, u32 bin_lo, u32 bin_hi,
+                                                          u64* __restrict__ count, u64* __restrict__ keys_out, u64* __restrict__ suf_out) {
+    __shared__ u32 s_cnt[2];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    bool sel = false;
+    u64 g = 0;
+    if ((u64)tid < T) {
+        g = n - 1 - (u64)tid;
+        const u32 bin = (u32)stream_bits(stream, g * (u64)lbits, pbits);
+        sel = bin >= bin_lo && bin < bin_hi;
+    }
+    const u32 b = __ballot_sync(0xffffffffu, sel);
+    if (lane == 0) s_cnt[warp] = __popc(b);
+    __syncthreads();
+    const u32 o = (warp ? s_cnt[0] : 0) + __popc(b & lanemask_lt());
+    if (sel) {
+        keys_out[o] = stream_extract(stream, g, lbits, kbits);
+        suf_out[o] = g;
+    }
+    if (tid == 0) *count = s_cnt[0] + s_cnt[1];
+}
+
+// key source of the SA -> ISA exchange partition: digit = owning rank of the suffix index under the block distribution
+struct OwnerSrc {
+    using Stage = u64;
+    using Out = u64;
+    static constexpr bool FROM_TEXT = false;
+    const u64* __restrict__ kin;
+    const u64* __restrict__ vin;
+    u64 cut, base1, base;  // cut = rem * (base + 1)
+    u32 rem;
+    double inv_base1, inv_base;
+    __device__ __forceinline__ static u64 divide(u64 x, u64 d, double inv) {
+        u64 q = (u64)__double2ull_rz((double)x * inv);
+        if (q * d > x) --q;
+        if ((q + 1) * d <= x) ++q;
+        return q;
+    }
+    __device__ __forceinline__ Stage load_key(size_t g) const { return ld_stream(kin + g); }
+    __device__ __forceinline__ u32 digit(Stage k) const { return k < cut ? (u32)divide(k, base1, inv_base1) : rem + (u32)divide(k - cut, base, inv_base); }
+    __device__ __forceinline__ Out out_key(Stage k) const { return k; }
+    __device__ __forceinline__ u64 load_val(size_t g) const { return ld_stream(vin + g); }
+    __device__ __forceinline__ u8 load_aux(size_t, Stage) const { return 0; }
+};
+
+// rank look-ups of one replicated round: ans[j] = ISA[suf[j] + h] + 1 if this shard owns that entry, else 0
+__global__ void __launch_bounds__(256) isa_answer_kernel(const u64* __restrict__ suf, u64 m, u64 h, u64 n, const u64* __restrict__ isa, u64 isa_lo,
+                                                         u64 isa_hi, u64* __restrict__ ans) {
+    for (u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x; j < m; j += (u64)gridDim.x * blockDim.x) {
+        const u64 g = suf[j] + h;
+        ans[j] = (g < n && g >= isa_lo && g < isa_hi) ? isa[g - isa_lo] + 1 : 0;
+    }
+}
+
+__global__ void __launch_bounds__(32) last_pair_kernel(const u64* __restrict__ keys, const u64* __restrict__ sufs, u64 cnt, u64* __restrict__ out) {
+    if (threadIdx.x == 0) {
+        out[0] = cnt ? keys[cnt - 1] : 0;
+        out[1] = cnt ? sufs[cnt - 1] : 0;
+    }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------ sharded engine state
+struct ShardComm {
+    ncclComm_t comm = nullptr;
+    int rank = 0, world = 1;
+};
+
+namespace {
+
+// all-to-all-v of `elt`-byte elements on the engine's stream (counts / displacements in elements)
+void all_to_all_v(psacb200_engine* e, const ShardComm& C, const void* send, const std::vector<u64>& scount, const std::vector<u64>& sdispl, void* recv,
+                  const std::vector<u64>& rcount, const std::vector<u64>& rdispl, size_t elt) {
+    const char* s = reinterpret_cast<const char*>(send);
+    char* r = reinterpret_cast<char*>(recv);
+    if (scount[C.rank])
+        PSAC_CUDA(cudaMemcpyAsync(r + rdispl[C.rank] * elt, s + sdispl[C.rank] * elt, scount[C.rank] * elt, cudaMemcpyDeviceToDevice, e->stream));
+    PSAC_NCCL(g_nccl.GroupStart());
+    for (int peer = 0; peer < C.world; ++peer) {
+        if (peer == C.rank) continue;
+        if (scount[peer]) PSAC_NCCL(g_nccl.Send(s + sdispl[peer] * elt, scount[peer] * elt, ncclUint8, peer, C.comm, e->stream));
+        if (rcount[peer]) PSAC_NCCL(g_nccl.Recv(r + rdispl[peer] * elt, rcount[peer] * elt, ncclUint8, peer, C.comm, e->stream));
+    }
+    PSAC_NCCL(g_nccl.GroupEnd());
+}
+
+// every rank contributes count[rank] elements at displ[rank] of the same replicated buffer (in place)
+void all_gather_v(psacb200_engine* e, const ShardComm& C, void* buf, const std::vector<u64>& count, const std::vector<u64>& displ, size_t elt) {
+    char* b = reinterpret_cast<char*>(buf);
+    PSAC_NCCL(g_nccl.GroupStart());
+    for (int root = 0; root < C.world; ++root)
+        if (count[root]) PSAC_NCCL(g_nccl.Broadcast(b + displ[root] * elt, b + displ[root] * elt, count[root] * elt, ncclUint8, root, C.comm, e->stream));
+    PSAC_NCCL(g_nccl.GroupEnd());
+}
+
+struct ShardedTimes {
+    cudaEvent_t ev[12];
+};
+
+// The sharded construction proper.  d_text_local: this rank's block of the text (device).  Outputs: this rank's blocks
+// of SA / ISA / LCP (device, index_bytes wide).
+// Returns false -- identically on every rank, from data all of them hold -- when this round's sharded scheme cannot take
+// the input (key prefixes too skewed to balance, or too many unresolved suffixes for the replicated rounds); the caller
+// then runs the replicated construction.
+bool construct_sharded_core(psacb200_engine* e, const ShardComm& C, const u8* d_text_local, u64 n_local, u64 n, int index_bytes, unsigned flags,
+                            unsigned k, void* sa_out, void* isa_out, void* lcp_out) {
+    const bool want_lcp = (flags & PSACB200_LCP) != 0;
+    const int p = C.world, me = C.rank;
+    cudaStream_t st = e->stream;
+    size_t* tot = &e->device_bytes;
+    psacb200_stats& S = e->stats;
+    const BlkDist blk(n, p);
+    if (blk.size(me) != n_local) throw arg_failure{"the input text must be equally block decomposed across all ranks (reference suffix_array.hpp:226)"};
+    S.internal_index_bytes = 8;
+    e->small.reserve(psacb200_engine::small_bytes(), tot);
+
+    // ---- S1 alphabet: local byte histogram, summed over the ranks (reference alphabet.hpp:94-100 allreduce)
+    e->begin(PH_ALPHABET);
+    PSAC_CUDA(cudaMemsetAsync(e->byte_hist(), 0, 256 * sizeof(u64), st));
+    if (n_local) {
+        byte_hist_kernel<<<grid_for(e, n_local / 16 + 1, 512, 4), 512, 0, st>>>(d_text_local, n_local, e->byte_hist());
+        e->launches += 1;
+    }
+    PSAC_NCCL(g_nccl.AllReduce(e->byte_hist(), e->byte_hist(), 256, ncclUint64, ncclSum, C.comm, st));
+    PSAC_CUDA(cudaMemcpyAsync(e->h_pinned + 16, e->byte_hist(), 256 * sizeof(u64), cudaMemcpyDeviceToHost, st));
+    e->end(PH_ALPHABET);
+    PSAC_CUDA(cudaStreamSynchronize(st));
+    Alphabet alpha;
+    alphabet_from_hist(e->h_pinned + 16, alpha);
+    dense_codes(e->h_pinned + 16, alpha);
+    S.sigma = alpha.sigma;
+    S.bits_per_char = alpha.ref_bits;
+    S.pack_bits = alpha.lbits;
+    const int lbits = alpha.lbits, cpw = 64 / lbits;
+
+    // ---- S2 replicated packed text
+    e->begin(PH_PACK);
+    const size_t nwords = div_up(n, (size_t)cpw) + 2;
+    e->packed.reserve(nwords * sizeof(u64) + 64, tot);
+    u64* stream = e->packed.as<u64>();
+    const bool aligned = (n % (u64)p == 0) && ((n / (u64)p) % (u64)cpw == 0);
+    if (aligned) {
+        // every block starts on a stream-word boundary: pack the local block in place, all-gather the words
+        const size_t wloc = n_local / cpw;
+        PSAC_CUDA(cudaMemsetAsync(stream + (size_t)p * wloc, 0, (nwords - (size_t)p * wloc) * sizeof(u64), st));
+        pack_text_kernel<<<grid_for(e, wloc, 256, 8), 256, 0, st>>>(d_text_local, n_local, alpha.dense, lbits, stream + (size_t)me * wloc, wloc);
+        e->launches += 1;
+        PSAC_NCCL(g_nccl.AllGather(stream + (size_t)me * wloc, stream, wloc, ncclUint64, C.comm, st));
+    } else {
+        // general block sizes: all-gather the raw characters, pack everything locally
+        e->text.reserve(n + 64, tot);
+        std::vector<u64> cnt(p), dsp(p);
+        for (int r = 0; r < p; ++r) {
+            cnt[r] = blk.size(r);
+            dsp[r] = blk.start(r);
+        }
+        if (n_local) PSAC_CUDA(cudaMemcpyAsync(e->text.as<u8>() + dsp[me], d_text_local, n_local, cudaMemcpyDeviceToDevice, st));
+        all_gather_v(e, C, e->text.p, cnt, dsp, 1);
+        pack_text_kernel<<<grid_for(e, nwords, 256, 8), 256, 0, st>>>(e->text.as<u8>(), n, alpha.dense, lbits, stream, nwords);
+        e->launches += 1;
+    }
+    PSAC_CUDA(cudaGetLastError());
+    e->end(PH_PACK);
+
+    // ---- S3 key length, key-prefix histogram of the local block, all-gathered
+    const unsigned Cc = choose_key_chars(n, lbits, k);
+    S.key_chars = Cc;
+    const int kbits = (int)Cc * lbits;
+    const int pbits = std::min(PREFIX_BITS_MAX, kbits);
+    const size_t nbins = (size_t)1 << pbits;
+    e->begin(PH_HIST);
+    e->scratch.reserve((size_t)p * nbins * sizeof(u64), tot);
+    u64* d_hist = e->scratch.as<u64>();
+    PSAC_CUDA(cudaMemsetAsync(d_hist + (size_t)me * nbins, 0, nbins * sizeof(u64), st));
+    if (n_local) {
+        PSAC_CUDA(cudaFuncSetAttribute(prefix_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(nbins * sizeof(u32))));
+        prefix_hist_kernel<<<grid_for(e, n_local, 512, 2), 512, nbins * sizeof(u32), st>>>(stream, blk.start(me), n_local, lbits, pbits, d_hist + (size_t)me * nbins);
+        e->launches += 1;
+        PSAC_CUDA(cudaGetLastError());
+    }
+    PSAC_NCCL(g_nccl.AllGather(d_hist + (size_t)me * nbins, d_hist, nbins, ncclUint64, C.comm, st));
+    std::vector<u64> h2d((size_t)p * nbins);
+    PSAC_CUDA(cudaMemcpyAsync(h2d.data(), d_hist, h2d.size() * sizeof(u64), cudaMemcpyDeviceToHost, st));
+    PSAC_CUDA(cudaStreamSynchronize(st));
+    e->end(PH_HIST);
+    std::vector<u64> hist(nbins, 0);
+    for (int b = 0; b < p; ++b)
+        for (size_t i = 0; i < nbins; ++i) hist[i] += h2d[(size_t)b * nbins + i];
+    std::vector<size_t> first;
+    std::vector<u64> cnt_key;  // suffixes per key range = SA positions owned after the sort
+    choose_splitters(hist.data(), nbins, n, p, first, cnt_key);
+    std::vector<u64> off_key(p + 1, 0);
+    for (int r = 0; r < p; ++r) off_key[r + 1] = off_key[r] + cnt_key[r];
+    const u64 cnt = cnt_key[me], off = off_key[me];
+    const u64 cap = 2 * div_up(n, (size_t)p) + 4096;
+    for (int r = 0; r < p; ++r)
+        if (cnt_key[r] > cap || cnt_key[r] == 0) return false;  // key prefixes too skewed for bin-boundary splitters
+    // send counts of the ISA exchange: [text block b][key range a] = suffixes of block b whose bin lies in range a
+    std::vector<u64> blk_in_range((size_t)p * p, 0);
+    for (int b = 0; b < p; ++b)
+        for (int a = 0; a < p; ++a)
+            for (size_t i = first[a]; i < first[a + 1]; ++i) blk_in_range[(size_t)b * p + a] += h2d[(size_t)b * nbins + i];
+
+    // ---- S5 select my key range from the whole text: (key, suffix) pairs, tails first
+    const u64 T = (n < (u64)Cc - 1) ? n : (u64)Cc - 1;
+    const u64 n_main = n - T;
+    for (int b = 0; b < 2; ++b) {
+        e->keys[b].reserve((cnt + 16) * sizeof(u64), tot);
+        e->vals[b].reserve((cnt + 16) * sizeof(u64), tot);
+    }
+    e->isa.reserve((n_local + 16) * sizeof(u64), tot);
+    if (want_lcp) e->lcp.reserve((cnt + 16) * sizeof(u64), tot);
+    const u64 sel_tiles = div_up(n_main ? n_main : 1, (size_t)SEL_TILE);
+    e->lookback.reserve(std::max<size_t>(lookback_bytes(cnt), 2 * (sel_tiles + 1) * sizeof(u64)), tot);
+    e->begin(PH_SORT);
+    u64* d_tcount = e->shard_meta() + 48;
+    u64* sel_sum = e->lookback.as<u64>();
+    u64* sel_max = sel_sum + sel_tiles;  // dummy channel for tile_scan_kernel
+    select_tails_kernel<<<1, 64, 0, st>>>(stream, n, T, lbits, kbits, pbits, (u32)first[me], (u32)first[me + 1], d_tcount, e->keys[0].as<u64>(),
+                                          e->vals[0].as<u64>());
+    PSAC_CUDA(cudaMemsetAsync(sel_max, 0, sel_tiles * sizeof(u64), st));
+    select_kernel<0><<<(unsigned)sel_tiles, SEL_THREADS, 0, st>>>(stream, n_main, lbits, kbits, pbits, (u32)first[me], (u32)first[me + 1], sel_sum, d_tcount,
+                                                                 nullptr, nullptr);
+    tile_scan_kernel<<<1, 1024, 0, st>>>(sel_max, sel_sum, sel_tiles, nullptr);
+    select_kernel<1><<<(unsigned)sel_tiles, SEL_THREADS, 0, st>>>(stream, n_main, lbits, kbits, pbits, (u32)first[me], (u32)first[me + 1], sel_sum, d_tcount,
+                                                                 e->keys[0].as<u64>(), e->vals[0].as<u64>());
+    e->launches += 4;
+    PSAC_CUDA(cudaGetLastError());
+
+    // ---- S6 local sort by the whole key (stable: tails stay in front of equal keys)
+    uint64_t sl = 0;
+    RadixPlan plan_used;
+    const bool alt = radix_sort_pairs<u64, u64>(e->radix_ws(), e->keys[0].as<u64>(), e->keys[1].as<u64>(), e->vals[0].as<u64>(), e->vals[1].as<u64>(), cnt, 0,
+                                                kbits, st, e->sm_count, &plan_used, &sl);
+    e->launches += sl;
+    S.sort_passes = plan_used.npass;
+    e->end(PH_SORT);
+    const int x = alt ? 1 : 0, y = 1 - x;
+    u64* SA = e->vals[x].as<u64>();     // SA positions [off, off + cnt)
+    u64* ISA = e->isa.as<u64>();        // ISA entries of my text block
+    u64* LCP = want_lcp ? e->lcp.as<u64>() : nullptr;
+    const u64 text_lo = blk.start(me), text_hi = text_lo + n_local;
+
+    // ---- S7 resolve round 0.  The element before my first one is the last element of the previous key range.
+    e->begin(PH_RESOLVE);
+    u64* d_last = e->shard_meta();                    // [2 * p] all-gathered {last key, last suffix}
+    last_pair_kernel<<<1, 32, 0, st>>>(e->keys[x].as<u64>(), SA, cnt, d_last + 2 * me);
+    PSAC_NCCL(g_nccl.AllGather(d_last + 2 * me, d_last, 2, ncclUint64, C.comm, st));
+    u64* bucket = e->keys[y].as<u64>();
+    const u64 ucap = std::max<u64>(unresolved_cap(cnt), 1);
+    e->rp[1].reserve(ucap * sizeof(u64), tot);
+    e->rh[1].reserve(ucap, tot);
+    e->rv[1].reserve(ucap * sizeof(u64), tot);
+    ResolveArgs R{};
+    R.keys = e->keys[x].p;
+    R.vals = SA;
+    R.aux = nullptr;
+    R.pos_in = nullptr;
+    R.m = cnt;
+    R.n = n;
+    R.sa = SA;
+    R.isa = nullptr;
+    R.bucket_out = bucket;
+    R.lcp = LCP;
+    R.pos_out = e->rp[1].p;
+    R.head_out = e->rh[1].as<u8>();
+    R.suf_out = e->rv[1].p;
+    R.cap = ucap;
+    R.counts = e->counts();
+    R.lb_max = e->lookback.as<u64>();
+    R.lb_sum = R.lb_max + div_up(cnt, (size_t)RES_TILE);
+    R.stream = stream;
+    R.lbits = lbits;
+    R.C = (int)Cc;
+    R.drop = 0;
+    R.kbits = 0;
+    R.h = 0;
+    R.padded_lcp = alpha.zero_code_used ? 1 : 0;
+    R.pos_base = off;
+    R.halo = me > 0 ? d_last + 2 * (me - 1) : nullptr;
+    R.sa_lo = off;
+    R.sa_hi = off + cnt;
+    R.isa_lo = text_lo;
+    R.isa_hi = text_hi;
+    launch_resolve<u64, u64>(e, true, R);
+    e->end(PH_RESOLVE);
+    // unresolved counts of all ranks
+    u64* d_m = e->shard_meta() + 32;  // [p]
+    PSAC_CUDA(cudaMemcpyAsync(d_m + me, e->counts(), sizeof(u64), cudaMemcpyDeviceToDevice, st));
+    PSAC_NCCL(g_nccl.AllGather(d_m + me, d_m, 1, ncclUint64, C.comm, st));
+    PSAC_CUDA(cudaMemcpyAsync(e->h_pinned, d_m, (size_t)p * sizeof(u64), cudaMemcpyDeviceToHost, st));
+    PSAC_CUDA(cudaStreamSynchronize(st));
+    std::vector<u64> m_r(p), m_dsp(p);
+    u64 M = 0;
+    for (int r = 0; r < p; ++r) {
+        m_r[r] = e->h_pinned[r];
+        m_dsp[r] = M;
+        M += m_r[r];
+    }
+    for (int r = 0; r < p; ++r)
+        if (m_r[r] > std::max<u64>(unresolved_cap(cnt_key[r]), 1)) return false;  // some rank's list overflowed (repetitive text)
+    if (M > (1ull << 28)) return false;                                          // too many for the replicated rounds
+    S.unresolved_after_first = M;
+    S.rounds = 1;
+
+    // ---- S9 SA -> ISA: partition (suffix, bucket) by owning rank, all-to-all-v, scatter into my ISA block
+    e->begin(PH_ISA);
+    {
+        RadixWorkspace ws = e->radix_ws();
+        u64* gb = ws.gbase + (MAX_PASSES - 1) * RADIX;
+        u32* ctr = ws.counters + (MAX_PASSES - 1);
+        std::vector<u64> scount(p), sdispl(p), rcount(p), rdispl(p);
+        u64 run = 0;
+        for (int b = 0; b < p; ++b) {
+            scount[b] = blk_in_range[(size_t)b * p + me];  // my key range, text block b
+            sdispl[b] = run;
+            run += scount[b];
+        }
+        if (run != cnt) throw std::string("sharded construction: exchange plan does not add up");
+        u64 rrun = 0;
+        for (int a = 0; a < p; ++a) {
+            rcount[a] = blk_in_range[(size_t)me * p + a];
+            rdispl[a] = rrun;
+            rrun += rcount[a];
+        }
+        if (rrun != n_local) throw std::string("sharded construction: exchange plan does not cover the block");
+        for (int d = 0; d < RADIX; ++d) e->h_pinned[64 + d] = d < p ? sdispl[d] : cnt;
+        PSAC_CUDA(cudaMemcpyAsync(gb, e->h_pinned + 64, RADIX * sizeof(u64), cudaMemcpyHostToDevice, st));
+        PSAC_CUDA(cudaMemsetAsync(ctr, 0, sizeof(u32), st));
+        PSAC_CUDA(cudaMemsetAsync(ws.lookback, 0, RadixWorkspace::lookback_bytes_for(cnt), st));
+        u64* part_suf = e->vals[y].as<u64>();
+        u64* part_bkt = e->keys[x].as<u64>();  // the sorted keys are dead after resolve
+        OwnerSrc src{SA, bucket, blk.rem * (blk.base + 1), blk.base + 1, blk.base ? blk.base : 1, (u32)blk.rem, 1.0 / (double)(blk.base + 1),
+                     1.0 / (double)(blk.base ? blk.base : 1)};
+        launch_pass<OwnerSrc, u64, false>(ws, src, part_suf, part_bkt, nullptr, cnt, gb, ctr, 1u, st);
+        e->launches += 1;
+        // receive buffers: the bucket array (dead after the partition) and a scratch of n_local entries
+        e->rk[0].reserve((n_local + 16) * sizeof(u64), tot);
+        e->rk[1].reserve((n_local + 16) * sizeof(u64), tot);
+        u64* recv_suf = e->rk[0].as<u64>();
+        u64* recv_bkt = e->rk[1].as<u64>();
+        all_to_all_v(e, C, part_suf, scount, sdispl, recv_suf, rcount, rdispl, sizeof(u64));
+        all_to_all_v(e, C, part_bkt, scount, sdispl, recv_bkt, rcount, rdispl, sizeof(u64));
+        if (n_local) {
+            isa_scatter_kernel<u64><<<(unsigned)div_up(n_local, (size_t)4096), 256, 0, st>>>(recv_suf, recv_bkt, ISA - text_lo, n_local);
+            e->launches += 1;
+        }
+        PSAC_CUDA(cudaGetLastError());
+    }
+    e->end(PH_ISA);
+
+    // ---- S8 later rounds, replicated on every rank over the all-gathered unresolved set
+    if (M > 0) {
+        e->begin(PH_ROUNDS);
+        // gathered lists first (rp/rh/rv[0]); the local lists live in rp/rh/rv[1], which may only be re-sized afterwards
+        e->rp[0].reserve(M * sizeof(u64), tot);
+        e->rh[0].reserve(M, tot);
+        e->rv[0].reserve(M * sizeof(u64), tot);
+        u64* pos_all = e->rp[0].as<u64>();
+        u8* head_all = e->rh[0].as<u8>();
+        u64* suf_all = e->rv[0].as<u64>();
+        if (m_r[me]) {
+            PSAC_CUDA(cudaMemcpyAsync(pos_all + m_dsp[me], e->rp[1].p, m_r[me] * sizeof(u64), cudaMemcpyDeviceToDevice, st));
+            PSAC_CUDA(cudaMemcpyAsync(head_all + m_dsp[me], e->rh[1].p, m_r[me], cudaMemcpyDeviceToDevice, st));
+            PSAC_CUDA(cudaMemcpyAsync(suf_all + m_dsp[me], e->rv[1].p, m_r[me] * sizeof(u64), cudaMemcpyDeviceToDevice, st));
+        }
+        PSAC_CUDA(cudaStreamSynchronize(st));  // the copies must have read the local lists before their buffers can move
+        e->rp[1].reserve(M * sizeof(u64), tot);
+        e->rh[1].reserve(M, tot);
+        e->rv[1].reserve(M * sizeof(u64), tot);
+        e->rk[0].reserve(M * sizeof(u64), tot);
+        e->rk[1].reserve(M * sizeof(u64), tot);
+        e->scratch.reserve(2 * M * sizeof(u64), tot);
+        all_gather_v(e, C, pos_all, m_r, m_dsp, sizeof(u64));
+        all_gather_v(e, C, head_all, m_r, m_dsp, 1);
+        all_gather_v(e, C, suf_all, m_r, m_dsp, sizeof(u64));
+        const int kb = (int)bits_for(n);
+        u64 h = Cc;
+        u64 m = M;
+        int t = 1;  // output lists of the next round
+        u64* ans = e->scratch.as<u64>();
+        u64* vals0 = ans + M;
+        e->lookback.reserve(std::max<size_t>(lookback_bytes(M), e->lookback.cap), tot);
+        while (m > 0) {
+            const int mbits = (int)bits_for(m - 1);
+            if (kb + mbits > 64) throw arg_failure{"text too repetitive for a 64-bit round key"};
+            const u64 ntiles = div_up(m, (size_t)RES_TILE);
+            isa_answer_kernel<<<grid_for(e, m, 256, 8), 256, 0, st>>>(suf_all, m, h, n, ISA, text_lo, text_hi, ans);
+            PSAC_NCCL(g_nccl.AllReduce(ans, ans, m, ncclUint64, ncclSum, C.comm, st));
+            RoundKeyArgs K{};
+            K.pos = pos_all;
+            K.head = head_all;
+            K.sa = nullptr;
+            K.isa = nullptr;
+            K.m = m;
+            K.n = n;
+            K.h = h;
+            K.kbits = kb;
+            K.keys = e->rk[0].as<u64>();
+            K.vals = vals0;
+            K.lb_max = e->lookback.as<u64>();
+            K.tile_counter = e->counters() + 17;
+            K.suf_in = suf_all;
+            K.rank2 = ans;
+            PSAC_CUDA(cudaMemsetAsync(K.lb_max, 0, ntiles * sizeof(u64), st));
+            PSAC_CUDA(cudaMemsetAsync(K.tile_counter, 0, sizeof(u32), st));
+            round_keys_kernel<u64><<<(unsigned)ntiles, RES_THREADS, 0, st>>>(K);
+            e->launches += 2;
+            PSAC_CUDA(cudaGetLastError());
+            uint64_t sl2 = 0;
+            // vals ping-pong: vals0 <-> suf_all is still needed by nothing after the keys are built, but keep it simple
+            u64* vals1 = e->rv[t].as<u64>();
+            const bool a2 = radix_sort_pairs<u64, u64>(e->radix_ws(), e->rk[0].as<u64>(), e->rk[1].as<u64>(), vals0, vals1, m, 0, kb + mbits, st, e->sm_count,
+                                                       nullptr, &sl2);
+            e->launches += sl2;
+            // sorted suffixes must not alias the output list suf_out (= rv[t]): move them to vals0 if they ended in vals1
+            const u64* sorted_keys = e->rk[a2 ? 1 : 0].as<u64>();
+            if (a2) PSAC_CUDA(cudaMemcpyAsync(vals0, vals1, m * sizeof(u64), cudaMemcpyDeviceToDevice, st));
+            ResolveArgs Q = R;
+            Q.keys = sorted_keys;
+            Q.vals = vals0;
+            Q.pos_in = pos_all;
+            Q.m = m;
+            Q.isa = ISA;
+            Q.bucket_out = nullptr;
+            Q.halo = nullptr;
+            Q.pos_base = 0;
+            Q.pos_out = e->rp[t].p;
+            Q.head_out = e->rh[t].as<u8>();
+            Q.suf_out = e->rv[t].p;
+            Q.cap = m;
+            Q.lb_sum = Q.lb_max + ntiles;
+            Q.drop = 0;
+            Q.kbits = kb;
+            Q.h = h;
+            launch_resolve<u64, u64>(e, false, Q);
+            u64 nb = 0;
+            read_counts(e, &m, &nb);
+            pos_all = e->rp[t].as<u64>();
+            head_all = e->rh[t].as<u8>();
+            suf_all = e->rv[t].as<u64>();
+            t ^= 1;
+            h *= 2;
+            S.rounds += 1;
+            if (h > 4 * n + 64 && m > 0) throw std::string("prefix doubling did not converge");
+        }
+        e->end(PH_ROUNDS);
+    }
+
+    // ---- S10 outputs: SA / LCP from key-range ownership [off, off + cnt) to exact blocks; ISA is already block-distributed
+    e->begin(PH_OUTPUT);
+    {
+        std::vector<u64> scount(p), sdispl(p), rcount(p), rdispl(p);
+        for (int b = 0; b < p; ++b) {
+            const u64 lo = std::max(off, blk.start(b)), hi = std::min(off + cnt, blk.start(b) + blk.size(b));
+            scount[b] = hi > lo ? hi - lo : 0;
+            sdispl[b] = hi > lo ? lo - off : 0;
+            const u64 rlo = std::max(off_key[b], text_lo), rhi = std::min(off_key[b + 1], text_hi);
+            rcount[b] = rhi > rlo ? rhi - rlo : 0;
+            rdispl[b] = rhi > rlo ? rlo - text_lo : 0;
+        }
+        const bool direct = index_bytes == 8;
+        u64* blk_buf = direct ? nullptr : e->rk[0].as<u64>();
+        if (!direct) e->rk[0].reserve((n_local + 16) * sizeof(u64), tot), blk_buf = e->rk[0].as<u64>();
+        auto deliver = [&](const u64* src, void* dst) {
+            u64* target = direct ? reinterpret_cast<u64*>(dst) : blk_buf;
+            all_to_all_v(e, C, src, scount, sdispl, target, rcount, rdispl, sizeof(u64));
+            if (!direct && n_local) {
+                convert_kernel<u64, u32><<<grid_for(e, n_local, 256, 16), 256, 0, st>>>(target, reinterpret_cast<u32*>(dst), n_local);
+                e->launches += 1;
+            }
+        };
+        deliver(SA, sa_out);
+        if (want_lcp) deliver(LCP, lcp_out);
+        if (isa_out && n_local) {
+            if (direct)
+                PSAC_CUDA(cudaMemcpyAsync(isa_out, ISA, n_local * sizeof(u64), cudaMemcpyDeviceToDevice, st));
+            else {
+                convert_kernel<u64, u32><<<grid_for(e, n_local, 256, 16), 256, 0, st>>>(ISA, reinterpret_cast<u32*>(isa_out), n_local);
+                e->launches += 1;
+            }
+        }
+        PSAC_CUDA(cudaGetLastError());
+    }
+    e->end(PH_OUTPUT);
+    return true;
+}
+
+// Inputs too small to shard: all-gather the text and let every GPU build the whole index; each keeps its block.
+void gather_text(psacb200_engine* e, const ShardComm& C, const u8* d_text_local, u64 n_local, u64 n) {
+    const BlkDist blk(n, C.world);
+    if (blk.size(C.rank) != n_local) throw arg_failure{"the input text must be equally block decomposed across all ranks (reference suffix_array.hpp:226)"};
+    e->text.reserve(n + 64, &e->device_bytes);
+    std::vector<u64> cnt(C.world), dsp(C.world);
+    for (int r = 0; r < C.world; ++r) {
+        cnt[r] = blk.size(r);
+        dsp[r] = blk.start(r);
+    }
+    if (n_local) PSAC_CUDA(cudaMemcpyAsync(e->text.as<u8>() + dsp[C.rank], d_text_local, n_local, cudaMemcpyDeviceToDevice, e->stream));
+    all_gather_v(e, C, e->text.p, cnt, dsp, 1);
+}
+
+}  // namespace

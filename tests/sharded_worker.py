@@ -1,0 +1,74 @@
+"""Worker of tests/test_gpu_sharded.py: run under torchrun with one rank per GPU.  Every rank builds its blocks of
+SA / ISA / LCP with ShardedSuffixArray; rank 0 gathers them and compares with the CPU oracle.  Exit code 0 = parity."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import pyoracle as O  # noqa: E402  (the checker)
+from psac_b200 import api, textgen as G  # noqa: E402
+from psac_b200.sharded import ShardedSuffixArray  # noqa: E402
+
+
+def gather_blocks(t, n, p, rank, dev):
+    """all ranks' blocks of a block-distributed int tensor -> one numpy array on rank 0"""
+    sizes = [api.blk_dist(n, p, r)[1] for r in range(p)]
+    mx = max(sizes)
+    pad = torch.zeros(mx, dtype=t.dtype, device=dev)
+    pad[: t.numel()] = t
+    out = [torch.zeros(mx, dtype=t.dtype, device=dev) for _ in range(p)]
+    dist.all_gather(out, pad)
+    return np.concatenate([o[:s].cpu().numpy() for o, s in zip(out, sizes)])
+
+
+def case(name, text, index_bytes, lcp, k=0):
+    rank, p = dist.get_rank(), dist.get_world_size()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    n = text.size
+    start, size = api.blk_dist(n, p, rank)
+    sa = ShardedSuffixArray(index_bytes, lcp).construct(text[start:start + size], k=k)
+    udt = np.uint32 if index_bytes == 4 else np.uint64
+    got_sa = gather_blocks(sa.local_SA, n, p, rank, dev).view(udt)
+    got_isa = gather_blocks(sa.local_B, n, p, rank, dev).view(udt)
+    got_lcp = gather_blocks(sa.local_LCP, n, p, rank, dev).view(udt) if lcp else None
+    ok = True
+    if rank == 0:
+        exp = O.construct(text, 64, 0, lcp)
+        ok = bool((got_sa.astype(np.uint64) == exp["sa"]).all() and (got_isa.astype(np.uint64) == exp["isa"]).all())
+        if lcp:
+            ok = ok and bool((got_lcp.astype(np.uint64) == exp["lcp"]).all())
+        st = sa.engine.stats()
+        print("%-34s n=%9d ib=%d lcp=%d k=%d rounds=%d unresolved=%d %s" % (name, n, index_bytes, int(lcp), k, st["rounds"], st["unresolved_after_first"],
+                                                                          "ok" if ok else "MISMATCH"), flush=True)
+    sa.engine.close()
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.broadcast(flag, 0)
+    return bool(flag.item())
+
+
+def main():
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    p = dist.get_world_size()
+    ok = True
+    ok &= case("random DNA, aligned blocks", G.random_dna(p << 20, 11), 8, True)
+    ok &= case("random DNA, ragged blocks", G.random_dna((p << 20) + 13, 12), 8, True)
+    ok &= case("random DNA, 32-bit index", G.random_dna((p << 19) + 5, 13), 4, False)
+    ok &= case("random DNA, short first key (k=4)", G.random_dna(p << 18, 14), 8, True, k=4)
+    ok &= case("random bytes (sigma=256 quirk)", G.random_bytes_config4(p << 18, 15), 8, False)
+    ok &= case("protein-like alphabet", (G.random_bytes(p << 18, 16) % 20 + 65).astype(np.uint8), 8, True)
+    ok &= case("small input (replicated path)", G.random_dna(1000 + p, 17), 8, True)
+    ok &= case("repetitive text (fallback path)", G.repeats_text(40000, 3), 8, True)
+    ok &= case("periodic text (fallback path)", G.periodic_text(b"abc", 60000), 4, True)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
