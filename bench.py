@@ -148,20 +148,36 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    eng = api.Engine(local_rank)
+    sharded = world > 1
     flags = (api.LCP if args.lcp else 0) | api.FAST_RESOLVAL
-    # every rank builds the SA of its own 2^log2n-character text (independent texts: seeds differ per rank)
+    n_total = n * world
+    if sharded:
+        # ONE text of world * 2^log2n characters, block-distributed over the ranks (BASELINE configs[2] shape: 64-bit index);
+        # SA / ISA / LCP come back block-distributed.  Rank r generates its own block (seed differs per rank).
+        from psac_b200.sharded import ShardedSuffixArray
+        index_bytes = 8
+        workload = "random DNA (|Sigma|=4), ONE text of %d x 2^%d chars sharded by block over %d GPUs, SA%s (+ISA), 64-bit index (BASELINE configs[2] shape)" % (
+            world, args.log2n, world, "+LCP" if args.lcp else "-only")
+        ssa = ShardedSuffixArray(index_bytes, args.lcp)
+        eng = ssa.engine
+    else:
+        eng = api.Engine(local_rank)
     text = G.random_dna_torch(n, SEED + rank, dev)
-    tdt = torch.int32  # raw 32-bit storage for uint32 outputs
+    tdt = torch.int32 if index_bytes == 4 else torch.int64  # raw storage for unsigned outputs
     d_sa = torch.empty(n, dtype=tdt, device=dev)
     d_isa = torch.empty(n, dtype=tdt, device=dev)
     d_lcp = torch.empty(n, dtype=tdt, device=dev) if args.lcp else None
-    eng.reserve(n, index_bytes, flags)
+    if not sharded:
+        eng.reserve(n, index_bytes, flags)
     torch.cuda.synchronize()
 
     def step_device():
-        eng.construct_ptr(text.data_ptr(), n, index_bytes, flags, 0, d_sa.data_ptr(), d_isa.data_ptr(), d_lcp.data_ptr() if d_lcp is not None else None,
-                          device=True)
+        if sharded:
+            eng.construct_sharded_ptr(text.data_ptr(), n, n_total, index_bytes, flags, 0, d_sa.data_ptr(), d_isa.data_ptr(),
+                                      d_lcp.data_ptr() if d_lcp is not None else None)
+        else:
+            eng.construct_ptr(text.data_ptr(), n, index_bytes, flags, 0, d_sa.data_ptr(), d_isa.data_ptr(), d_lcp.data_ptr() if d_lcp is not None else None,
+                              device=True)
 
     ext = torch.cuda.ExternalStream(eng.stream_ptr, device=dev)
     for _ in range(max(args.warmup, 3)):
@@ -187,14 +203,23 @@ def main():
     clocks = sampler.summary()
     stats = eng.stats()
 
-    # size-independent certificate of the last result (permutation + inverse), on the device
-    ar = torch.arange(n, dtype=torch.int64, device=dev)
-    ok = bool((d_isa.to(torch.int64).bitwise_and(0xFFFFFFFF)[d_sa.to(torch.int64).bitwise_and(0xFFFFFFFF)] == ar).all().item())
-    del ar
+    # size-independent certificate of the last result, on the device
+    if sharded:
+        # SA and ISA are permutations of 0..n-1: their sums over all ranks must be n(n-1)/2 (mod 2^64, int64 wrap-around)
+        sums = torch.stack([d_sa.sum(), d_isa.sum()])
+        dist.all_reduce(sums)
+        want = (n_total * (n_total - 1) // 2) % (1 << 64)
+        ok = all((int(v.item()) % (1 << 64)) == want for v in sums)
+        verified = "sum(SA) == sum(ISA) == n(n-1)/2 over all ranks (parity itself: tests/test_gpu_sharded.py)"
+    else:
+        ar = torch.arange(n, dtype=torch.int64, device=dev)
+        ok = bool((d_isa.to(torch.int64).bitwise_and(0xFFFFFFFF)[d_sa.to(torch.int64).bitwise_and(0xFFFFFFFF)] == ar).all().item())
+        del ar
+        verified = "ISA[SA[i]]==i on device"
     if not ok:
-        raise SystemExit("bench.py: ISA[SA[i]] != i -- result invalid")
+        raise SystemExit("bench.py: result certificate failed -- result invalid")
 
-    # ------------------------------------------------------------------ end to end: pinned host buffers through the C ABI
+    # ------------------------------------------------------------------ end to end: pinned host buffers through the public API
     e2e = None
     if not args.no_e2e:
         h_text = torch.empty(n, dtype=torch.uint8).pin_memory()
@@ -205,7 +230,20 @@ def main():
         torch.cuda.synchronize()
 
         def step_host():
-            eng.construct_ptr(h_text.data_ptr(), n, index_bytes, flags, 0, h_sa.data_ptr(), h_isa.data_ptr(), h_lcp.data_ptr() if h_lcp is not None else None)
+            if sharded:
+                # the sharded C ABI takes device blocks: the host block goes up and the result blocks come down on the
+                # engine's stream inside the timed region
+                with torch.cuda.stream(ext):
+                    text.copy_(h_text, non_blocking=True)
+                step_device()
+                with torch.cuda.stream(ext):
+                    h_sa.copy_(d_sa, non_blocking=True)
+                    h_isa.copy_(d_isa, non_blocking=True)
+                    if h_lcp is not None:
+                        h_lcp.copy_(d_lcp, non_blocking=True)
+                ext.synchronize()
+            else:
+                eng.construct_ptr(h_text.data_ptr(), n, index_bytes, flags, 0, h_sa.data_ptr(), h_isa.data_ptr(), h_lcp.data_ptr() if h_lcp is not None else None)
 
         step_host()
         barrier()
@@ -218,7 +256,7 @@ def main():
         barrier()
         ms_e2e = e0.elapsed_time(e1) / k_e2e
         outs = 2 + (1 if args.lcp else 0)
-        e2e = {"ms": ms_e2e, "h2d": n, "d2h": outs * n * index_bytes, "steps": k_e2e, "sa0": int(h_sa[0].item()) & 0xFFFFFFFF}
+        e2e = {"ms": ms_e2e, "h2d": n * world, "d2h": outs * n * index_bytes * world, "steps": k_e2e}
 
     # ------------------------------------------------------------------ reduce over ranks (max time)
     t = torch.tensor([ms_dev, e2e["ms"] if e2e else 0.0], dtype=torch.float64, device=dev)
@@ -232,30 +270,36 @@ def main():
 
     peak, peak_src = measured_peaks()
     # dominant kernel: one 8-bit digit pass over the carried keys (passes 2..P of the first sort); algorithmic bytes
-    # per launch = read + write of one carried key and one suffix index per suffix (DESIGN.md section "Kernels")
-    key_bytes = 4 if stats["key_chars"] * stats["pack_bits"] - 8 <= 32 else 8
-    val_bytes = stats["internal_index_bytes"]
-    pass_bytes = float(n) * 2 * (key_bytes + val_bytes)
+    # per launch = read + write of one carried key and one suffix index (+ one auxiliary byte with 32-bit carried keys)
+    # per suffix sorted on this GPU (DESIGN.md section "Kernels")
+    if sharded:
+        key_bytes, val_bytes, aux_bytes = 8, 8, 0
+    else:
+        key_bytes = 4 if stats["key_chars"] * stats["pack_bits"] - 8 <= 32 else 8
+        val_bytes, aux_bytes = stats["internal_index_bytes"], (1 if key_bytes == 4 else 0)
+    pass_bytes = float(n) * 2 * (key_bytes + val_bytes + aux_bytes)
     pass_avg_ms = float(np.mean(pass_ms))
     achieved = pass_bytes / (pass_avg_ms * 1e-3) / 1e9 if pass_avg_ms > 0 else 0.0
     line = {
-        "metric": "suffixes/sec SA build", "value": world * n / (ms_dev * 1e-3), "unit": "suffixes/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
-        "data": "synthetic",
-        "config": {"workload": workload, "n_per_gpu": n, "parallelism": "1 text per GPU" if world > 1 else "single GPU", "seed": SEED,
+        "metric": "suffixes/sec SA build", "value": n_total / (ms_dev * 1e-3), "unit": "suffixes/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u%d" % (index_bytes * 8), "data": "synthetic",
+        "config": {"workload": workload, "n_per_gpu": n, "n_total": n_total,
+                   "parallelism": ("block-sharded text/SA/ISA over %d GPUs, NCCL all-to-all-v" % world) if sharded else "single GPU", "seed": SEED,
                    "l2": "inputs_exceed_l2 (every pass streams >= 8 GiB)", "key_chars": stats["key_chars"], "sort_passes": stats["sort_passes"],
-                   "rounds": stats["rounds"], "unresolved_after_first": stats["unresolved_after_first"], "verified": "ISA[SA[i]]==i on device"},
+                   "rounds": stats["rounds"], "unresolved_after_first": stats["unresolved_after_first"], "verified": verified},
         "gpu_launches": launches,
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "onesweep_pass_kernel<ArraySrc<u%d,u%d>> (one 8-bit digit pass of the first sort over the carried keys)" % (key_bytes * 8, val_bytes * 8), "achieved": achieved,
-                     "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+        "roofline": {"bound": "hbm", "kernel": "onesweep_pass_kernel<ArraySrc<u%d,u%d>> (one 8-bit digit pass of the first sort over the carried keys; rank 0)" % (
+                         key_bytes * 8, val_bytes * 8),
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                      "bytes_per_launch": pass_bytes, "ms_per_launch": pass_avg_ms},
         "phases_ms": {k: round(v, 3) for k, v in sorted(phase.items())},
     }
     if e2e:
-        line["e2e"] = {"value": world * n / (ms_e2e * 1e-3), "unit": "suffixes/s", "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
+        line["e2e"] = {"value": n_total / (ms_e2e * 1e-3), "unit": "suffixes/s", "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
                        "ms_per_step": ms_e2e, "steps": e2e["steps"]}
-    if not args.no_cpu_baseline and world >= 1:
+    if not args.no_cpu_baseline and world == 1:
         m = 1 << min(args.cpu_log2n, args.log2n)
         kind, sps, ms = reference_run(G.random_dna(m, SEED), index_bytes, args.lcp, 1, 0)
         line["cpu_baseline"] = {"value": sps, "unit": "suffixes/s", "cores": 1, "kind": kind, "ms": ms,

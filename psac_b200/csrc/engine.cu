@@ -223,7 +223,7 @@ unsigned choose_key_chars(u64 n, int lbits, unsigned k) {
     // Enough characters that random text leaves well under 1 % of the suffixes in shared buckets (n / 2^bits of them),
     // in whole 8-bit digit passes; 40 bits is preferred while it does so because the keys carried after the first
     // digit pass then fit 32 bits (radix_sort.cuh).
-    unsigned want = bits_for(n) + 7;
+    unsigned want = bits_for(n) + 6;
     unsigned nbits = want <= 40 ? 40u : std::min(64u, (want + 7u) / 8u * 8u);
     if (bits_for(n) <= 16) nbits = std::min(nbits, 32u);
     return std::max(1u, std::min(maxC, nbits / (unsigned)lbits));
@@ -371,7 +371,7 @@ void construct_core(psacb200_engine* e, u64 n, int index_bytes, unsigned flags, 
         PSAC_CUDA(cudaMemsetAsync(ws.lookback, 0, RadixWorkspace::lookback_bytes_for(n), st));
         IdxT* part_suffix = vbuf[y];
         IdxT* part_bucket = reinterpret_cast<IdxT*>(kbuf[x]);  // the sorted keys are dead after resolve
-        ArraySrc<IdxT, IdxT> src{SA, bucket, nullptr, shift, (u32)(RADIX - 1)};
+        ArraySrc<IdxT, IdxT> src{SA, bucket, nullptr, shift, (u32)(RADIX - 1), (IdxT)0};
         launch_pass<ArraySrc<IdxT, IdxT>, IdxT, false>(ws, src, part_suffix, part_bucket, nullptr, n, gb, ctr, 1u, st);
         isa_scatter_kernel<IdxT><<<(unsigned)div_up(n, (size_t)4096), 256, 0, st>>>(part_suffix, part_bucket, ISA, n);
         e->launches += 3;
@@ -497,7 +497,10 @@ void fill_phase_stats(psacb200_engine* e) {
     S.ms_rounds = e->ms(PH_ROUNDS);
     S.ms_output = e->ms(PH_OUTPUT);
     S.ms_d2h = e->ms(PH_D2H);
-    S.ms_sort_pass_avg = S.sort_passes > 1 ? (S.ms_sort - S.ms_sort_pass1) / (float)(S.sort_passes - 1) : S.ms_sort;
+    if (e->nccl_comm && e->shard_world > 1 && S.internal_index_bytes == 8 && S.ms_sort_pass1 > 0.f)
+        S.ms_sort_pass_avg = S.sort_passes ? (S.ms_sort - S.ms_sort_pass1) / (float)S.sort_passes : 0.f;  // sharded: pass1 slot = selection
+    else
+        S.ms_sort_pass_avg = S.sort_passes > 1 ? (S.ms_sort - S.ms_sort_pass1) / (float)(S.sort_passes - 1) : S.ms_sort;
 }
 
 int construct_entry(psacb200_engine* e, const u8* text, bool text_is_host, size_t n, int index_bytes, unsigned flags, unsigned k, const uint8_t* lut,

@@ -174,8 +174,9 @@ struct ArraySrc {
     const u8* __restrict__ ain;  // auxiliary bytes (null when the pass carries none)
     int shift;
     u32 mask;
+    KeyT sub;                    // subtracted from the key before the digit is taken (window partitions of a shard's block)
     __device__ __forceinline__ Stage load_key(size_t g) const { return ld_stream(kin + g); }
-    __device__ __forceinline__ u32 digit(Stage k) const { return (u32)(k >> shift) & mask; }
+    __device__ __forceinline__ u32 digit(Stage k) const { return (u32)((k - sub) >> shift) & mask; }
     __device__ __forceinline__ Out out_key(Stage k) const { return k; }
     __device__ __forceinline__ ValT load_val(size_t g) const { return ld_stream(vin + g); }
     __device__ __forceinline__ u8 load_aux(size_t g, Stage) const { return ld_stream(ain + g); }
@@ -523,7 +524,7 @@ bool radix_sort_pairs(const RadixWorkspace& ws, KeyT* keys, KeyT* keys_alt, ValT
     PSAC_CUDA(cudaMemsetAsync(ws.lookback, 0, RadixWorkspace::lookback_bytes_for(n), stream));
     bool in_alt = false;
     for (int p = 0; p < plan.npass; ++p) {
-        ArraySrc<KeyT, ValT> src{in_alt ? keys_alt : keys, in_alt ? vals_alt : vals, nullptr, plan.shift[p], (1u << plan.bits[p]) - 1u};
+        ArraySrc<KeyT, ValT> src{in_alt ? keys_alt : keys, in_alt ? vals_alt : vals, nullptr, plan.shift[p], (1u << plan.bits[p]) - 1u, (KeyT)0};
         launch_pass<ArraySrc<KeyT, ValT>, ValT, false>(ws, src, in_alt ? keys : keys_alt, in_alt ? vals : vals_alt, nullptr, n, ws.gbase + p * RADIX,
                                                        ws.counters + p, (u32)(p + 1), stream);
         in_alt = !in_alt;
@@ -571,7 +572,7 @@ int radix_sort_suffixes(const RadixWorkspace& ws, const u64* text_stream, size_t
     if (ev_pass1_done) cudaEventRecord(ev_pass1_done, stream);
     int cur = 0;
     for (int p = 1; p < plan.npass; ++p) {
-        ArraySrc<KeyC, IdxT> src{kbuf[cur], vbuf[cur], AUX ? abuf[cur] : nullptr, plan.shift[p] - drop, (1u << plan.bits[p]) - 1u};
+        ArraySrc<KeyC, IdxT> src{kbuf[cur], vbuf[cur], AUX ? abuf[cur] : nullptr, plan.shift[p] - drop, (1u << plan.bits[p]) - 1u, (KeyC)0};
         launch_pass<ArraySrc<KeyC, IdxT>, IdxT, AUX>(ws, src, kbuf[1 - cur], vbuf[1 - cur], AUX ? abuf[1 - cur] : nullptr, n, ws.gbase + p * RADIX,
                                                      ws.counters + p, (u32)(p + 1), stream);
         cur = 1 - cur;

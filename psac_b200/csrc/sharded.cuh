@@ -124,53 +124,64 @@ __global__ void __launch_bounds__(512) prefix_hist_kernel(const u64* __restrict_
     }
 }
 
-// Selection of the suffixes whose key-prefix bin lies in [bin_lo, bin_hi), in ascending suffix order (the suffixes that
-// run past the end of the text are handled by select_tails_kernel and come first: see TextSrc in radix_sort.cuh for why).
-// PHASE 0 counts per tile, PHASE 1 writes (key, suffix) at the tile's exclusive prefix (tile_scan_kernel) + *base.
+// Selection of the suffixes whose key-prefix bin lies in [bin_lo, bin_hi) out of ALL suffixes [0, n_main) of the
+// replicated text: (key, suffix) pairs appended after the tails (select_tails_kernel: the suffixes that run past the end
+// of the text must come first, see TextSrc in radix_sort.cuh).  One thread walks the characters of one 64-bit stream word
+// with a two-word window; a CTA reserves its output range with one atomicAdd, so the order of the pairs between CTAs
+// is arbitrary -- equal keys of non-tail suffixes form an unresolved bucket whose internal order is settled by the later
+// rounds, and the final arrays are unique.
 constexpr int SEL_THREADS = 256;
-constexpr int SEL_ITEMS = 32;
-constexpr int SEL_TILE = SEL_THREADS * SEL_ITEMS;
 
-template <int PHASE>
 __global__ void __launch_bounds__(SEL_THREADS) select_kernel(const u64* __restrict__ stream, u64 n_main, int lbits, int kbits, int pbits, u32 bin_lo,
-                                                             u32 bin_hi, u64* __restrict__ tile_sum, const u64* __restrict__ base,
-                                                             u64* __restrict__ keys_out, u64* __restrict__ suf_out) {
+                                                             u32 bin_hi, u64* __restrict__ cursor, u64* __restrict__ keys_out, u64* __restrict__ suf_out) {
     __shared__ u32 s_w[SEL_THREADS / 32];
+    __shared__ u64 s_base;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const u64 g0 = (u64)blockIdx.x * SEL_TILE + (u64)tid * SEL_ITEMS;
-    u32 mask = 0;
+    const int cpw = 64 / lbits;
+    const u64 w = (u64)blockIdx.x * SEL_THREADS + tid;
+    const u64 g0 = w * (u64)cpw;
+    u64 mask = 0, hi = 0, lo = 0;
     if (g0 < n_main) {
-#pragma unroll 4
-        for (int i = 0; i < SEL_ITEMS; ++i) {
-            const u64 g = g0 + i;
-            if (g < n_main) {
-                const u32 bin = (u32)stream_bits(stream, g * (u64)lbits, pbits);
-                if (bin >= bin_lo && bin < bin_hi) mask |= 1u << i;
-            }
+        hi = __ldg(stream + w);
+        lo = __ldg(stream + w + 1);
+        const int cnt = (n_main - g0 < (u64)cpw) ? (int)(n_main - g0) : cpw;
+        for (int c = 0; c < cnt; ++c) {
+            const int o = c * lbits;
+            const u64 v = o ? ((hi << o) | (lo >> (64 - o))) : hi;
+            const u32 bin = (u32)(v >> (64 - pbits));
+            if (bin >= bin_lo && bin < bin_hi) mask |= 1ull << c;
         }
     }
-    const u32 cnt = __popc(mask);
+    const u32 cnt = __popcll(mask);
     const u32 incl = warp_inclusive_sum_u32(cnt);
     if (lane == 31) s_w[warp] = incl;
     __syncthreads();
     u32 pre = 0, tot = 0;
 #pragma unroll
-    for (int w = 0; w < SEL_THREADS / 32; ++w) {
-        if (w < warp) pre += s_w[w];
-        tot += s_w[w];
+    for (int i = 0; i < SEL_THREADS / 32; ++i) {
+        if (i < warp) pre += s_w[i];
+        tot += s_w[i];
     }
-    if (PHASE == 0) {
-        if (tid == 0) tile_sum[blockIdx.x] = tot;
-        return;
-    }
-    u64 o = *base + tile_sum[blockIdx.x] + pre + (incl - cnt);
-    while (mask) {
-        const int i = __ffs(mask) - 1;
-        mask &= mask - 1;
-        const u64 g = g0 + i;
-        keys_out[o] = stream_extract(stream, g, lbits, kbits);
-        suf_out[o] = g;
-        ++o;
+    if (tid == 0) s_base = tot ? atomicAdd((unsigned long long*)cursor, (unsigned long long)tot) : 0;
+    __syncthreads();
+    // write-out transposed: in step c every lane offers character c of ITS word, the selected lanes of the warp write
+    // consecutive pairs -> each store instruction covers one contiguous run instead of 32 separate sectors
+    u64 wbase = s_base + (u64)pre;  // `pre` = pairs of the warps before mine; lanes of one warp share it
+    const u32 lt = lanemask_lt();
+    const u64 any = __reduce_or_sync(0xffffffffu, (u32)(mask != 0));
+    if (any) {
+        for (int c = 0; c < cpw; ++c) {
+            const bool sel = (mask >> c) & 1ull;
+            const u32 b = __ballot_sync(0xffffffffu, sel);
+            if (sel) {
+                const int sh = c * lbits;
+                const u64 v = sh ? ((hi << sh) | (lo >> (64 - sh))) : hi;
+                const u64 dst = wbase + __popc(b & lt);
+                keys_out[dst] = v >> (64 - kbits);
+                suf_out[dst] = g0 + (u64)c;
+            }
+            wbase += __popc(b);
+        }
     }
 }
 
@@ -388,22 +399,19 @@ bool construct_sharded_core(psacb200_engine* e, const ShardComm& C, const u8* d_
     }
     e->isa.reserve((n_local + 16) * sizeof(u64), tot);
     if (want_lcp) e->lcp.reserve((cnt + 16) * sizeof(u64), tot);
-    const u64 sel_tiles = div_up(n_main ? n_main : 1, (size_t)SEL_TILE);
-    e->lookback.reserve(std::max<size_t>(lookback_bytes(cnt), 2 * (sel_tiles + 1) * sizeof(u64)), tot);
+    e->lookback.reserve(lookback_bytes(std::max(cnt, n_local)), tot);
     e->begin(PH_SORT);
-    u64* d_tcount = e->shard_meta() + 48;
-    u64* sel_sum = e->lookback.as<u64>();
-    u64* sel_max = sel_sum + sel_tiles;  // dummy channel for tile_scan_kernel
-    select_tails_kernel<<<1, 64, 0, st>>>(stream, n, T, lbits, kbits, pbits, (u32)first[me], (u32)first[me + 1], d_tcount, e->keys[0].as<u64>(),
+    u64* d_cursor = e->shard_meta() + 48;  // number of pairs written so far: the tails first, then the selection appends
+    select_tails_kernel<<<1, 64, 0, st>>>(stream, n, T, lbits, kbits, pbits, (u32)first[me], (u32)first[me + 1], d_cursor, e->keys[0].as<u64>(),
                                           e->vals[0].as<u64>());
-    PSAC_CUDA(cudaMemsetAsync(sel_max, 0, sel_tiles * sizeof(u64), st));
-    select_kernel<0><<<(unsigned)sel_tiles, SEL_THREADS, 0, st>>>(stream, n_main, lbits, kbits, pbits, (u32)first[me], (u32)first[me + 1], sel_sum, d_tcount,
-                                                                 nullptr, nullptr);
-    tile_scan_kernel<<<1, 1024, 0, st>>>(sel_max, sel_sum, sel_tiles, nullptr);
-    select_kernel<1><<<(unsigned)sel_tiles, SEL_THREADS, 0, st>>>(stream, n_main, lbits, kbits, pbits, (u32)first[me], (u32)first[me + 1], sel_sum, d_tcount,
-                                                                 e->keys[0].as<u64>(), e->vals[0].as<u64>());
-    e->launches += 4;
+    if (n_main) {
+        const u64 sel_ctas = div_up(div_up(n_main, (size_t)cpw), (size_t)SEL_THREADS);
+        select_kernel<<<(unsigned)sel_ctas, SEL_THREADS, 0, st>>>(stream, n_main, lbits, kbits, pbits, (u32)first[me], (u32)first[me + 1], d_cursor,
+                                                                  e->keys[0].as<u64>(), e->vals[0].as<u64>());
+    }
+    e->launches += 2;
     PSAC_CUDA(cudaGetLastError());
+    cudaEventRecord(e->ev_end[PH_PASS1], st);  // selection time is reported in the slot of "digit pass 1"
 
     // ---- S6 local sort by the whole key (stable: tails stay in front of equal keys)
     uint64_t sl = 0;
@@ -519,7 +527,23 @@ bool construct_sharded_core(psacb200_engine* e, const ShardComm& C, const u8* d_
         u64* recv_bkt = e->rk[1].as<u64>();
         all_to_all_v(e, C, part_suf, scount, sdispl, recv_suf, rcount, rdispl, sizeof(u64));
         all_to_all_v(e, C, part_bkt, scount, sdispl, recv_bkt, rcount, rdispl, sizeof(u64));
-        if (n_local) {
+        if (n_local >= (1ull << 22)) {
+            // as on one GPU: partition the received pairs by ISA window (top 8 bits of the index inside my block), then
+            // scatter window by window so the writes stay in L2 until their sectors are complete
+            const int nb2 = (int)bits_for(n_local - 1);
+            const int shift2 = nb2 > RADIX_BITS ? nb2 - RADIX_BITS : 0;
+            perm_gbase_kernel<<<1, RADIX, 0, st>>>(n_local, shift2, gb);
+            PSAC_CUDA(cudaMemsetAsync(ctr, 0, sizeof(u32), st));
+            PSAC_CUDA(cudaMemsetAsync(ws.lookback, 0, RadixWorkspace::lookback_bytes_for(n_local), st));
+            ArraySrc<u64, u64> wsrc{recv_suf, recv_bkt, nullptr, shift2, (u32)(RADIX - 1), text_lo};
+            e->vals[y].reserve((n_local + 16) * sizeof(u64), tot);
+            e->keys[x].reserve((n_local + 16) * sizeof(u64), tot);
+            u64* win_suf = e->vals[y].as<u64>();  // the partition buffers of the send side are free again
+            u64* win_bkt = e->keys[x].as<u64>();
+            launch_pass<ArraySrc<u64, u64>, u64, false>(ws, wsrc, win_suf, win_bkt, nullptr, n_local, gb, ctr, 2u, st);
+            isa_scatter_kernel<u64><<<(unsigned)div_up(n_local, (size_t)4096), 256, 0, st>>>(win_suf, win_bkt, ISA - text_lo, n_local);
+            e->launches += 3;
+        } else if (n_local) {
             isa_scatter_kernel<u64><<<(unsigned)div_up(n_local, (size_t)4096), 256, 0, st>>>(recv_suf, recv_bkt, ISA - text_lo, n_local);
             e->launches += 1;
         }

@@ -59,6 +59,7 @@ def main():
     ok &= case("random DNA, aligned blocks", G.random_dna(p << 20, 11), 8, True)
     ok &= case("random DNA, ragged blocks", G.random_dna((p << 20) + 13, 12), 8, True)
     ok &= case("random DNA, 32-bit index", G.random_dna((p << 19) + 5, 13), 4, False)
+    ok &= case("random DNA, k=7: replicated rounds", G.random_dna(p << 20, 18), 8, True, k=7)
     ok &= case("random DNA, short first key (k=4)", G.random_dna(p << 18, 14), 8, True, k=4)
     ok &= case("random bytes (sigma=256 quirk)", G.random_bytes_config4(p << 18, 15), 8, False)
     ok &= case("protein-like alphabet", (G.random_bytes(p << 18, 16) % 20 + 65).astype(np.uint8), 8, True)

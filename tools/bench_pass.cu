@@ -32,7 +32,7 @@ void run(size_t n, int reps) {
     for (int r = 0; r < reps; ++r) {
         cudaMemset(ws.counters, 0, 64 * 4); cudaMemset(ws.lookback, 0, ws.lookback_bytes);
         cudaMemcpyToSymbol(g_phase_cycles, zero, sizeof(zero));
-        ArraySrc<u32, u32> src{k[0], v[0], AUX ? a[0] : nullptr, 8, 255u};
+        ArraySrc<u32, u32> src{k[0], v[0], AUX ? a[0] : nullptr, 8, 255u, 0u};
         cudaEventRecord(e0);
         launch_pass<ArraySrc<u32, u32>, u32, AUX>(ws, src, k[1], v[1], AUX ? a[1] : nullptr, n, ws.gbase + RADIX, ws.counters, 1u, 0);
         cudaEventRecord(e1); cudaEventSynchronize(e1);
