@@ -94,11 +94,9 @@ struct psacb200_engine {
 
     RadixWorkspace radix_ws() const {
         RadixWorkspace ws;
-        ws.ghist = ghist();
         ws.gbase = gbase();
-        ws.counters = counters();
-        ws.lookback = lookback.as<u64>();
-        ws.lookback_bytes = lookback.cap;
+        ws.tiles = lookback.p;
+        ws.tiles_bytes = lookback.cap;
         return ws;
     }
     void begin(Phase p) {
@@ -230,7 +228,7 @@ unsigned choose_key_chars(u64 n, int lbits, unsigned k) {
 }
 
 size_t lookback_bytes(u64 n) {
-    return std::max(RadixWorkspace::lookback_bytes_for(n), (size_t)(2 * div_up(n, (size_t)RES_TILE) * sizeof(u64)));
+    return std::max(RadixWorkspace::tiles_bytes_for(n), (size_t)(2 * div_up(n, (size_t)RES_TILE) * sizeof(u64)));
 }
 
 // Device buffers of one construction.  When the caller's outputs are device buffers of the engine's internal index
@@ -281,10 +279,9 @@ void construct_core(psacb200_engine* e, u64 n, int index_bytes, unsigned flags, 
     u8* abuf[2] = {e->aux[0].as<u8>(), e->aux[1].as<u8>()};
     uint64_t sort_launches = 0;
     RadixPlan plan_used;
-    e->begin(PH_HIST);
+    e->begin(PH_SORT);
     const int x = radix_sort_suffixes<KeyC, IdxT>(e->radix_ws(), e->packed.as<u64>(), n, lbits, (int)C, kbuf, vbuf, abuf, st, e->sm_count, &plan_used,
-                                                  &sort_launches, e->ev_end[PH_HIST], e->ev_begin[PH_SORT], e->ev_end[PH_PASS1]);
-    e->ev_used[PH_SORT] = true;
+                                                  &sort_launches, e->ev_end[PH_PASS1]);
     e->end(PH_SORT);
     e->launches += sort_launches;
     S.sort_passes = plan_used.npass;
@@ -364,17 +361,12 @@ void construct_core(psacb200_engine* e, u64 n, int index_bytes, unsigned flags, 
         const int nbits = (int)bits_for(n - 1);
         const int shift = nbits > RADIX_BITS ? nbits - RADIX_BITS : 0;
         RadixWorkspace ws = e->radix_ws();
-        u64* gb = ws.gbase + (MAX_PASSES - 1) * RADIX;
-        u32* ctr = ws.counters + (MAX_PASSES - 1);
-        perm_gbase_kernel<<<1, RADIX, 0, st>>>(n, shift, gb);
-        PSAC_CUDA(cudaMemsetAsync(ctr, 0, sizeof(u32), st));
-        PSAC_CUDA(cudaMemsetAsync(ws.lookback, 0, RadixWorkspace::lookback_bytes_for(n), st));
         IdxT* part_suffix = vbuf[y];
         IdxT* part_bucket = reinterpret_cast<IdxT*>(kbuf[x]);  // the sorted keys are dead after resolve
         ArraySrc<IdxT, IdxT> src{SA, bucket, nullptr, shift, (u32)(RADIX - 1), (IdxT)0};
-        launch_pass<ArraySrc<IdxT, IdxT>, IdxT, false>(ws, src, part_suffix, part_bucket, nullptr, n, gb, ctr, 1u, st);
+        launch_pass<ArraySrc<IdxT, IdxT>, IdxT, false>(ws, src, part_suffix, part_bucket, nullptr, n, st);
         isa_scatter_kernel<IdxT><<<(unsigned)div_up(n, (size_t)4096), 256, 0, st>>>(part_suffix, part_bucket, ISA, n);
-        e->launches += 3;
+        e->launches += LAUNCHES_PER_PASS + 1;
         PSAC_CUDA(cudaGetLastError());
     }
     e->end(PH_ISA);
@@ -752,7 +744,7 @@ int psacb200_sort_pairs(psacb200_engine* e, void* d_keys, void* d_keys_alt, void
         if ((key_bytes != 4 && key_bytes != 8) || (val_bytes != 0 && val_bytes != 4 && val_bytes != 8)) throw arg_failure{"unsupported key/value width"};
         if (begin_bit < 0 || end_bit > key_bytes * 8 || begin_bit > end_bit) throw arg_failure{"bad bit range"};
         PSAC_CUDA(cudaSetDevice(e->device));
-        e->lookback.reserve(div_up(n ? n : 1, (size_t)2048) * RADIX * sizeof(u64), &e->device_bytes);
+        e->lookback.reserve(RadixWorkspace::tiles_bytes_for(n), &e->device_bytes);
         uint64_t sl = 0;
         bool alt = key_bytes == 8 ? sort_dispatch_val<u64>(e, d_keys, d_keys_alt, d_vals, d_vals_alt, n, val_bytes, begin_bit, end_bit, &sl)
                                   : sort_dispatch_val<u32>(e, d_keys, d_keys_alt, d_vals, d_vals_alt, n, val_bytes, begin_bit, end_bit, &sl);

@@ -2,16 +2,18 @@
 // prefix-doubling loop (reference: include/idxsort.hpp:22-83 -> mxx::sort).
 //
 // Design (B200-first, not the reference's comparison sample sort):
-//   * one up-front histogram kernel counts every digit of every pass in a single read of the keys (or, for the
-//     first sort of a construction, of the packed text: the keys are never materialised before the first pass);
-//   * one kernel per 8-bit digit.  A CTA owns a tile, ranks its keys with ONE shared-memory atomic per key
-//     (see "ranking" below), resolves its global bin offsets with a decoupled look-back over 256 per-digit
-//     channels (no second pass over the data, no grid-wide sync) and writes the tile out through shared
-//     memory so each bin's run leaves as one coalesced burst;
-//   * the first pass of a construction reads the packed text instead of a key array and drops the digit it
-//     consumed, so the keys carried through the remaining passes are 32 bits wide whenever the sort key has
-//     <= 40 bits (BASELINE configs[1]: 20 DNA characters);
-//   * algorithmic HBM traffic per pass = read + write of every carried key and value once.
+//   * LSD radix sort, one 8-bit digit per pass.  A pass is: per-tile digit histogram (reads the keys only) -> scan of
+//     the per-tile counts (two tiny kernels) -> scatter kernel.  A scatter CTA owns a tile, ranks its keys with ONE
+//     shared-memory atomic per key (see "ranking" below), adds the tile's global bin offsets and writes the tile out
+//     through shared memory so each bin's run leaves as one coalesced burst.
+//     (Measured first: the usual single-kernel "onesweep" with a decoupled look-back.  On B200 ~450 tiles are resident
+//     and a dependent L2 load under full DRAM load costs ~1 us, so 54 % of a tile's cycles were look-back waits
+//     (profiles/r1_bench_pass.txt); re-reading 4 bytes per key for the histogram is cheaper than that.)
+//   * the first pass of a construction reads the packed text instead of a key array (k-mer generation fused) and
+//     drops the digit it consumed, so the keys carried through the remaining passes are 32 bits wide whenever the
+//     sort key has <= 40 bits (BASELINE configs[1]: 20 DNA characters); the dropped digit travels on as one byte;
+//   * algorithmic HBM traffic per pass = read + write of every carried key, value and aux byte once (the histogram's
+//     re-read of the keys is overhead and counted as such in DESIGN.md).
 //
 // Ranking.  A stable rank needs, for every key, the number of earlier keys of the tile with the same digit.
 // On sm_100a the lanes of one ATOMS.ADD warp instruction that hit the same shared-memory word are applied in
@@ -49,7 +51,7 @@ struct NoVal {};  // keys-only sort
 constexpr int RADIX_BITS = 8;
 constexpr int RADIX = 1 << RADIX_BITS;
 constexpr int MAX_PASSES = 8;
-constexpr int LOOKBACK_BATCH = 8;  // look-back loads in flight per digit channel
+constexpr int SCAN_CHUNK = 256;  // tiles per chunk of the two-level scan of the per-tile digit counts
 
 struct RadixPlan {
     int npass;
@@ -73,92 +75,6 @@ static inline RadixPlan make_radix_plan(int begin_bit, int end_bit) {
         s += p.bits[i];
     }
     return p;
-}
-
-// ------------------------------------------------------------------ up-front digit histogram
-template <typename KeyT>
-__device__ __forceinline__ void hist_accumulate(u32 (*sh)[RADIX], const RadixPlan& plan, KeyT k) {
-#pragma unroll
-    for (int p = 0; p < MAX_PASSES; ++p) {
-        if (p < plan.npass) atomicAdd(&sh[p][(u32)(k >> plan.shift[p]) & ((1u << plan.bits[p]) - 1u)], 1u);
-    }
-}
-
-__device__ __forceinline__ void hist_flush(u32 (*sh)[RADIX], const RadixPlan& plan, u64* ghist) {
-    for (int e = threadIdx.x; e < plan.npass * RADIX; e += blockDim.x) {
-        u32 c = sh[e >> RADIX_BITS][e & (RADIX - 1)];
-        if (c) atomicAdd((unsigned long long*)&ghist[e], (unsigned long long)c);
-    }
-}
-
-template <typename KeyT>
-__global__ void __launch_bounds__(512) radix_hist_kernel(const KeyT* __restrict__ keys, size_t n, RadixPlan plan, u64* __restrict__ ghist) {
-    __shared__ u32 sh[MAX_PASSES][RADIX];
-    for (int e = threadIdx.x; e < MAX_PASSES * RADIX; e += blockDim.x) (&sh[0][0])[e] = 0;
-    __syncthreads();
-    constexpr int VEC = 16 / sizeof(KeyT);
-    const size_t nvec = n / VEC;
-    const uint4* kv = reinterpret_cast<const uint4*>(keys);
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
-        uint4 q = __ldcs(kv + i);
-        if (sizeof(KeyT) == 8) {
-            hist_accumulate<u64>(sh, plan, ((u64)q.y << 32) | q.x);
-            hist_accumulate<u64>(sh, plan, ((u64)q.w << 32) | q.z);
-        } else {
-            hist_accumulate<u32>(sh, plan, q.x);
-            hist_accumulate<u32>(sh, plan, q.y);
-            hist_accumulate<u32>(sh, plan, q.z);
-            hist_accumulate<u32>(sh, plan, q.w);
-        }
-    }
-    if (blockIdx.x == 0) {
-        for (size_t i = nvec * VEC + threadIdx.x; i < n; i += blockDim.x) hist_accumulate<KeyT>(sh, plan, keys[i]);
-    }
-    __syncthreads();
-    hist_flush(sh, plan, ghist);
-}
-
-// Same histogram with the keys read straight from the packed text: key(i) = the kbits stream bits starting at
-// character i.  One thread walks the characters of one 64-bit stream word with a two-word window.
-__global__ void __launch_bounds__(512) text_hist_kernel(const u64* __restrict__ stream, size_t n, int lbits, int kbits, RadixPlan plan,
-                                                        u64* __restrict__ ghist) {
-    __shared__ u32 sh[MAX_PASSES][RADIX];
-    for (int e = threadIdx.x; e < MAX_PASSES * RADIX; e += blockDim.x) (&sh[0][0])[e] = 0;
-    __syncthreads();
-    const int cpw = 64 / lbits;
-    const size_t nwords = (n + cpw - 1) / cpw;
-    for (size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x; w < nwords; w += (size_t)gridDim.x * blockDim.x) {
-        const u64 hi = __ldg(stream + w), lo = __ldg(stream + w + 1);
-        const size_t c0 = w * (size_t)cpw;
-        const int cnt = (n - c0 < (size_t)cpw) ? (int)(n - c0) : cpw;
-        for (int c = 0; c < cnt; ++c) {
-            const int o = c * lbits;
-            const u64 v = o ? ((hi << o) | (lo >> (64 - o))) : hi;
-            hist_accumulate<u64>(sh, plan, v >> (64 - kbits));
-        }
-    }
-    __syncthreads();
-    hist_flush(sh, plan, ghist);
-}
-
-// exclusive scan of each pass's 256-bin histogram; one CTA of 256 threads per pass
-__global__ void __launch_bounds__(RADIX) radix_scan_hist_kernel(const u64* __restrict__ ghist, u64* __restrict__ gbase) {
-    __shared__ u64 wtot[RADIX / 32];
-    const int p = blockIdx.x, d = threadIdx.x;
-    u64 c = ghist[p * RADIX + d];
-    u64 inc = warp_inclusive_scan(c, OpSum());
-    if ((d & 31) == 31) wtot[d >> 5] = inc;
-    __syncthreads();
-    u64 pre = 0;
-    for (int w = 0; w < (d >> 5); ++w) pre += wtot[w];
-    gbase[p * RADIX + d] = pre + inc - c;
-}
-
-// bin bases of a pass over the digit bits [shift, shift+8) of a PERMUTATION of 0..n-1 (the SA -> ISA partition):
-// the histogram is known without reading anything
-__global__ void __launch_bounds__(RADIX) perm_gbase_kernel(u64 n, int shift, u64* __restrict__ gbase) {
-    const u64 lo = (u64)threadIdx.x << shift;
-    gbase[threadIdx.x] = lo < n ? lo : n;
 }
 
 // ------------------------------------------------------------------ key sources of a pass
@@ -238,7 +154,7 @@ struct PassCfg {
 template <class Cfg, class Src, typename ValT, bool FULL>
 __device__ __forceinline__ void onesweep_tile(unsigned char* smem_raw, const Src& src, typename Src::Out* __restrict__ kout, ValT* __restrict__ vout,
                                               u8* __restrict__ aout, const size_t base, const int valid, const u64* __restrict__ gbase,
-                                              u64* __restrict__ lookback, const size_t tile, const u32 epoch) {
+                                              const u64* __restrict__ chunk_base, const u32* __restrict__ tile_excl) {
     using Stage = typename Src::Stage;
     using Out = typename Src::Out;
     constexpr int NW = Cfg::NW, ITEMS = Cfg::ITEMS, THREADS = Cfg::THREADS;
@@ -286,7 +202,7 @@ __device__ __forceinline__ void onesweep_tile(unsigned char* smem_raw, const Src
     __syncthreads();
     PSAC_PHASE(1);  // barrier 1
 
-    // ---- per digit: exclusive offsets of the warps, tile count (published at once for the look-back), bin start
+    // ---- per digit: exclusive offsets of the warps, tile count, bin start
     u32 count = 0;
     if (tid < RADIX) {
 #pragma unroll
@@ -295,7 +211,6 @@ __device__ __forceinline__ void onesweep_tile(unsigned char* smem_raw, const Src
             tab[w * RADIX + tid] = count;
             count += c;
         }
-        if (tile > 0) st_relaxed(lookback + tile * RADIX + tid, lb_pack((u64)count, epoch, LB_AGGREGATE));
     }
     const u32 inc = warp_inclusive_sum_u32(count);
     if (tid < RADIX && lane == 31) misc[1 + warp] = inc;
@@ -331,18 +246,9 @@ __device__ __forceinline__ void onesweep_tile(unsigned char* smem_raw, const Src
     }
 
     PSAC_PHASE(3);  // rank + scatter
-    // ---- decoupled look-back, one channel per digit; the predecessors published their counts long ago
-    if (tid < RADIX) {
-        u64 excl = 0;
-        if (tile == 0) {
-            st_relaxed(lookback + tid, lb_pack((u64)count, epoch, LB_INCLUSIVE));
-        } else {
-            excl = lookback_sum_batched<LOOKBACK_BATCH>(lookback + tid, RADIX, tile, epoch);
-            st_relaxed(lookback + tile * RADIX + tid, lb_pack(excl + count, epoch, LB_INCLUSIVE));
-        }
-        goff[tid] = gbase[tid] + excl - (u64)bin_start[tid];
-    }
-    PSAC_PHASE(4);  // look-back
+    // ---- global offset of each bin of this tile: digit base + chunks before mine + tiles of my chunk before me
+    if (tid < RADIX) goff[tid] = gbase[tid] + chunk_base[tid] + (u64)tile_excl[tid] - (u64)bin_start[tid];
+    PSAC_PHASE(4);  // offsets
     __syncthreads();
     PSAC_PHASE(5);  // barrier 3
 
@@ -398,23 +304,79 @@ __device__ __forceinline__ void onesweep_tile(unsigned char* smem_raw, const Src
 
 template <class Src, typename ValT, int THREADS, int ITEMS, bool HAS_AUX>
 __global__ void __launch_bounds__(THREADS, (sizeof(typename Src::Out) == 4 && sizeof(ValT) <= 4) ? 3 : 2)
-    onesweep_pass_kernel(const Src src, typename Src::Out* __restrict__ kout, ValT* __restrict__ vout, u8* __restrict__ aout, size_t n,
-                         const u64* __restrict__ gbase, u32* __restrict__ tile_counter, u64* __restrict__ lookback, u32 epoch) {
+    radix_scatter_kernel(const Src src, typename Src::Out* __restrict__ kout, ValT* __restrict__ vout, u8* __restrict__ aout, size_t n,
+                         const u64* __restrict__ gbase, const u64* __restrict__ chunk_base, const u32* __restrict__ tile_excl) {
     using Cfg = PassCfg<Src, ValT, THREADS, ITEMS, HAS_AUX>;
     constexpr int TILE = Cfg::TILE;
     static_assert(THREADS >= RADIX && THREADS % 32 == 0, "need one thread per digit");
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    u32* misc = reinterpret_cast<u32*>(smem_raw + Cfg::OFF_MISC);
     u32* tab = reinterpret_cast<u32*>(smem_raw + Cfg::OFF_TAB);
-    if (threadIdx.x == 0) misc[0] = atomicAdd(tile_counter, 1u);
     for (int e = threadIdx.x; e < Cfg::NW * RADIX; e += THREADS) tab[e] = 0u;
     __syncthreads();
-    const size_t tile = misc[0];
+    const size_t tile = blockIdx.x;
     const size_t base = tile * (size_t)TILE;
+    const u64* cb = chunk_base + (tile / SCAN_CHUNK) * RADIX;
+    const u32* te = tile_excl + tile * RADIX;
     if (n - base >= (size_t)TILE)
-        onesweep_tile<Cfg, Src, ValT, true>(smem_raw, src, kout, vout, aout, base, TILE, gbase, lookback, tile, epoch);
+        onesweep_tile<Cfg, Src, ValT, true>(smem_raw, src, kout, vout, aout, base, TILE, gbase, cb, te);
     else
-        onesweep_tile<Cfg, Src, ValT, false>(smem_raw, src, kout, vout, aout, base, (int)(n - base), gbase, lookback, tile, epoch);
+        onesweep_tile<Cfg, Src, ValT, false>(smem_raw, src, kout, vout, aout, base, (int)(n - base), gbase, cb, te);
+}
+
+// per-tile digit histogram of a pass (same tile geometry as the scatter kernel): counts[tile][256]
+template <class Src, int THREADS, int ITEMS>
+__global__ void __launch_bounds__(THREADS) tile_hist_kernel(const Src src, size_t n, u32* __restrict__ counts) {
+    __shared__ u32 sh[RADIX];
+    constexpr int TILE = THREADS * ITEMS;
+    if (threadIdx.x < RADIX) sh[threadIdx.x] = 0;
+    __syncthreads();
+    const size_t base = (size_t)blockIdx.x * TILE;
+    const int valid = (n - base >= (size_t)TILE) ? TILE : (int)(n - base);
+    typename Src::Stage key[ITEMS];
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+        const int o = j * THREADS + threadIdx.x;
+        if (o < valid) key[j] = src.load_key(base + o);
+    }
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+        if (j * THREADS + (int)threadIdx.x < valid) atomicAdd(&sh[src.digit(key[j])], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < RADIX) counts[(size_t)blockIdx.x * RADIX + threadIdx.x] = sh[threadIdx.x];
+}
+
+// scan level 1: inside every chunk of SCAN_CHUNK tiles the counts become exclusive prefixes; chunk totals go out
+__global__ void __launch_bounds__(RADIX) tile_scan_chunks_kernel(u32* __restrict__ counts, size_t tiles, u64* __restrict__ chunk_tot) {
+    const size_t c = blockIdx.x, t0 = c * SCAN_CHUNK, t1 = (t0 + SCAN_CHUNK < tiles) ? t0 + SCAN_CHUNK : tiles;
+    const int d = threadIdx.x;
+    u32 run = 0;
+#pragma unroll 8
+    for (size_t t = t0; t < t1; ++t) {
+        const u32 v = counts[t * RADIX + d];
+        counts[t * RADIX + d] = run;
+        run += v;
+    }
+    chunk_tot[c * RADIX + d] = run;
+}
+
+// scan level 2 (one CTA): chunk totals become exclusive prefixes over the chunks; digit totals -> exclusive digit bases
+__global__ void __launch_bounds__(RADIX) tile_scan_top_kernel(u64* __restrict__ chunk_tot, size_t chunks, u64* __restrict__ gbase) {
+    __shared__ u64 wtot[RADIX / 32];
+    const int d = threadIdx.x;
+    u64 run = 0;
+#pragma unroll 8
+    for (size_t c = 0; c < chunks; ++c) {
+        const u64 v = chunk_tot[c * RADIX + d];
+        chunk_tot[c * RADIX + d] = run;
+        run += v;
+    }
+    const u64 inc = warp_inclusive_scan(run, OpSum());
+    if ((d & 31) == 31) wtot[d >> 5] = inc;
+    __syncthreads();
+    u64 pre = 0;
+    for (int w = 0; w < (d >> 5); ++w) pre += wtot[w];
+    gbase[d] = pre + inc - run;
 }
 
 // ------------------------------------------------------------------ hardware self-test of the ranking assumption
@@ -480,53 +442,50 @@ struct SortTuning {
 constexpr int MIN_TILE = 384 * 12;
 
 struct RadixWorkspace {
-    u64* ghist = nullptr;      // [MAX_PASSES][RADIX]
-    u64* gbase = nullptr;      // [MAX_PASSES][RADIX]
-    u32* counters = nullptr;   // [MAX_PASSES]
-    u64* lookback = nullptr;   // [max_tiles][RADIX]
-    size_t lookback_bytes = 0;
-    static size_t lookback_bytes_for(size_t n) { return div_up(n ? n : 1, (size_t)MIN_TILE) * RADIX * sizeof(u64); }
+    u64* gbase = nullptr;      // [RADIX] digit bases of the pass in flight
+    void* tiles = nullptr;     // per-tile counts (u32 [tiles][RADIX]) followed by the chunk totals (u64 [chunks][RADIX])
+    size_t tiles_bytes = 0;
+    static size_t tiles_bytes_for(size_t n) { return (div_up(n ? n : 1, (size_t)MIN_TILE) + 2) * RADIX * sizeof(u64); }
 };
 
+// One digit pass: histogram, two-level scan, scatter.  4 launches.
 template <class Src, typename ValT, bool HAS_AUX>
-void launch_pass(const RadixWorkspace& ws, const Src& src, typename Src::Out* kout, ValT* vout, u8* aout, size_t n, const u64* gbase, u32* tile_counter,
-                 u32 epoch, cudaStream_t stream) {
+void launch_pass(const RadixWorkspace& ws, const Src& src, typename Src::Out* kout, ValT* vout, u8* aout, size_t n, cudaStream_t stream) {
     using T = SortTuning<typename Src::Out, ValT>;
     using Cfg = PassCfg<Src, ValT, T::THREADS, T::ITEMS, HAS_AUX>;
     const size_t tiles = div_up(n, (size_t)Cfg::TILE);
-    if (tiles * RADIX * sizeof(u64) > ws.lookback_bytes) throw std::string("radix pass: look-back workspace too small");
-    auto kern = onesweep_pass_kernel<Src, ValT, T::THREADS, T::ITEMS, HAS_AUX>;
+    const size_t chunks = div_up(tiles, (size_t)SCAN_CHUNK);
+    const size_t counts_bytes = align_up(tiles * RADIX * sizeof(u32), 256);
+    if (counts_bytes + chunks * RADIX * sizeof(u64) > ws.tiles_bytes) throw std::string("radix pass: tile workspace too small");
+    u32* counts = reinterpret_cast<u32*>(ws.tiles);
+    u64* chunk_tot = reinterpret_cast<u64*>(reinterpret_cast<char*>(ws.tiles) + counts_bytes);
+    auto kern = radix_scatter_kernel<Src, ValT, T::THREADS, T::ITEMS, HAS_AUX>;
     static bool attr_set = false;
     if (!attr_set) {
         PSAC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
         attr_set = true;
     }
-    kern<<<(unsigned)tiles, T::THREADS, Cfg::SMEM, stream>>>(src, kout, vout, aout, n, gbase, tile_counter, ws.lookback, epoch);
+    tile_hist_kernel<Src, T::THREADS, T::ITEMS><<<(unsigned)tiles, T::THREADS, 0, stream>>>(src, n, counts);
+    tile_scan_chunks_kernel<<<(unsigned)chunks, RADIX, 0, stream>>>(counts, tiles, chunk_tot);
+    tile_scan_top_kernel<<<1, RADIX, 0, stream>>>(chunk_tot, chunks, ws.gbase);
+    kern<<<(unsigned)tiles, T::THREADS, Cfg::SMEM, stream>>>(src, kout, vout, aout, n, ws.gbase, chunk_tot, counts);
 }
+constexpr int LAUNCHES_PER_PASS = 4;
 
 // Sorts n pairs by key bits [begin_bit, end_bit).  Ping-pongs between (keys, vals) and (keys_alt, vals_alt);
 // returns true when the sorted data ended up in the *_alt buffers.
 template <typename KeyT, typename ValT>
 bool radix_sort_pairs(const RadixWorkspace& ws, KeyT* keys, KeyT* keys_alt, ValT* vals, ValT* vals_alt, size_t n, int begin_bit, int end_bit,
                       cudaStream_t stream, int sm_count, RadixPlan* plan_out = nullptr, uint64_t* launches = nullptr) {
+    (void)sm_count;
     RadixPlan plan = make_radix_plan(begin_bit, end_bit);
     if (plan_out) *plan_out = plan;
     if (n == 0 || plan.npass == 0) return false;
-    {
-        PSAC_CUDA(cudaMemsetAsync(ws.ghist, 0, MAX_PASSES * RADIX * sizeof(u64), stream));
-        size_t want = div_up(n, (size_t)512 * 32);
-        int grid = (int)(want < (size_t)sm_count * 4 ? (want ? want : 1) : (size_t)sm_count * 4);
-        radix_hist_kernel<KeyT><<<grid, 512, 0, stream>>>(keys, n, plan, ws.ghist);
-    }
-    radix_scan_hist_kernel<<<plan.npass, RADIX, 0, stream>>>(ws.ghist, ws.gbase);
-    if (launches) *launches = 2 + (uint64_t)plan.npass;
-    PSAC_CUDA(cudaMemsetAsync(ws.counters, 0, MAX_PASSES * sizeof(u32), stream));
-    PSAC_CUDA(cudaMemsetAsync(ws.lookback, 0, RadixWorkspace::lookback_bytes_for(n), stream));
+    if (launches) *launches = (uint64_t)LAUNCHES_PER_PASS * plan.npass;
     bool in_alt = false;
     for (int p = 0; p < plan.npass; ++p) {
         ArraySrc<KeyT, ValT> src{in_alt ? keys_alt : keys, in_alt ? vals_alt : vals, nullptr, plan.shift[p], (1u << plan.bits[p]) - 1u, (KeyT)0};
-        launch_pass<ArraySrc<KeyT, ValT>, ValT, false>(ws, src, in_alt ? keys : keys_alt, in_alt ? vals : vals_alt, nullptr, n, ws.gbase + p * RADIX,
-                                                       ws.counters + p, (u32)(p + 1), stream);
+        launch_pass<ArraySrc<KeyT, ValT>, ValT, false>(ws, src, in_alt ? keys : keys_alt, in_alt ? vals : vals_alt, nullptr, n, stream);
         in_alt = !in_alt;
     }
     PSAC_CUDA(cudaGetLastError());
@@ -539,42 +498,30 @@ static inline int carried_drop_bits(const RadixPlan& plan, int kbits) { return (
 
 // First sort of a construction: keys come from the packed text.  kbuf / vbuf / abuf are two ping-pong buffers each
 // (abuf only for 32-bit carried keys); pass 1 writes buffer 0; returns the index (0/1) of the buffers holding the
-// sorted carried keys, suffix indices and auxiliary bytes.  Events (optional) bracket histogram and digit passes.
+// sorted carried keys, suffix indices and auxiliary bytes.  ev_pass1_done (optional) is recorded after digit pass 1.
 template <typename KeyC, typename IdxT>
 int radix_sort_suffixes(const RadixWorkspace& ws, const u64* text_stream, size_t n, int lbits, int key_chars, KeyC* const kbuf[2], IdxT* const vbuf[2],
-                        u8* const abuf[2], cudaStream_t stream, int sm_count, RadixPlan* plan_out, uint64_t* launches, cudaEvent_t ev_hist_done = nullptr,
-                        cudaEvent_t ev_passes_begin = nullptr, cudaEvent_t ev_pass1_done = nullptr) {
+                        u8* const abuf[2], cudaStream_t stream, int sm_count, RadixPlan* plan_out, uint64_t* launches,
+                        cudaEvent_t ev_pass1_done = nullptr) {
+    (void)sm_count;
     constexpr bool AUX = sizeof(KeyC) == 4;
     const int kbits = key_chars * lbits;
     RadixPlan plan = make_radix_plan(0, kbits);
     if (plan_out) *plan_out = plan;
     if (n == 0) return 0;
-    PSAC_CUDA(cudaMemsetAsync(ws.ghist, 0, MAX_PASSES * RADIX * sizeof(u64), stream));
-    {
-        const int cpw = 64 / lbits;
-        size_t want = div_up(div_up(n, (size_t)cpw), (size_t)512);
-        int grid = (int)(want < (size_t)sm_count * 4 ? (want ? want : 1) : (size_t)sm_count * 4);
-        text_hist_kernel<<<grid, 512, 0, stream>>>(text_stream, n, lbits, kbits, plan, ws.ghist);
-    }
-    radix_scan_hist_kernel<<<plan.npass, RADIX, 0, stream>>>(ws.ghist, ws.gbase);
-    if (launches) *launches = 2 + (uint64_t)plan.npass;
-    if (ev_hist_done) cudaEventRecord(ev_hist_done, stream);
-    if (ev_passes_begin) cudaEventRecord(ev_passes_begin, stream);
-    PSAC_CUDA(cudaMemsetAsync(ws.counters, 0, MAX_PASSES * sizeof(u32), stream));
-    PSAC_CUDA(cudaMemsetAsync(ws.lookback, 0, RadixWorkspace::lookback_bytes_for(n), stream));
+    if (launches) *launches = (uint64_t)LAUNCHES_PER_PASS * plan.npass;
     const int drop = AUX ? plan.bits[0] : 0;
     if (AUX && kbits - drop > 32) throw std::string("radix_sort_suffixes: carried key does not fit 32 bits");
     {
         const u64 C = (u64)key_chars;
         TextSrc<KeyC, IdxT> src{text_stream, (u64)n, (n < C - 1) ? (u64)n : C - 1, lbits, kbits, drop, (1u << plan.bits[0]) - 1u};
-        launch_pass<TextSrc<KeyC, IdxT>, IdxT, AUX>(ws, src, kbuf[0], vbuf[0], AUX ? abuf[0] : nullptr, n, ws.gbase, ws.counters, 1u, stream);
+        launch_pass<TextSrc<KeyC, IdxT>, IdxT, AUX>(ws, src, kbuf[0], vbuf[0], AUX ? abuf[0] : nullptr, n, stream);
     }
     if (ev_pass1_done) cudaEventRecord(ev_pass1_done, stream);
     int cur = 0;
     for (int p = 1; p < plan.npass; ++p) {
         ArraySrc<KeyC, IdxT> src{kbuf[cur], vbuf[cur], AUX ? abuf[cur] : nullptr, plan.shift[p] - drop, (1u << plan.bits[p]) - 1u, (KeyC)0};
-        launch_pass<ArraySrc<KeyC, IdxT>, IdxT, AUX>(ws, src, kbuf[1 - cur], vbuf[1 - cur], AUX ? abuf[1 - cur] : nullptr, n, ws.gbase + p * RADIX,
-                                                     ws.counters + p, (u32)(p + 1), stream);
+        launch_pass<ArraySrc<KeyC, IdxT>, IdxT, AUX>(ws, src, kbuf[1 - cur], vbuf[1 - cur], AUX ? abuf[1 - cur] : nullptr, n, stream);
         cur = 1 - cur;
     }
     PSAC_CUDA(cudaGetLastError());

@@ -493,8 +493,6 @@ bool construct_sharded_core(psacb200_engine* e, const ShardComm& C, const u8* d_
     e->begin(PH_ISA);
     {
         RadixWorkspace ws = e->radix_ws();
-        u64* gb = ws.gbase + (MAX_PASSES - 1) * RADIX;
-        u32* ctr = ws.counters + (MAX_PASSES - 1);
         std::vector<u64> scount(p), sdispl(p), rcount(p), rdispl(p);
         u64 run = 0;
         for (int b = 0; b < p; ++b) {
@@ -510,16 +508,12 @@ bool construct_sharded_core(psacb200_engine* e, const ShardComm& C, const u8* d_
             rrun += rcount[a];
         }
         if (rrun != n_local) throw std::string("sharded construction: exchange plan does not cover the block");
-        for (int d = 0; d < RADIX; ++d) e->h_pinned[64 + d] = d < p ? sdispl[d] : cnt;
-        PSAC_CUDA(cudaMemcpyAsync(gb, e->h_pinned + 64, RADIX * sizeof(u64), cudaMemcpyHostToDevice, st));
-        PSAC_CUDA(cudaMemsetAsync(ctr, 0, sizeof(u32), st));
-        PSAC_CUDA(cudaMemsetAsync(ws.lookback, 0, RadixWorkspace::lookback_bytes_for(cnt), st));
         u64* part_suf = e->vals[y].as<u64>();
         u64* part_bkt = e->keys[x].as<u64>();  // the sorted keys are dead after resolve
         OwnerSrc src{SA, bucket, blk.rem * (blk.base + 1), blk.base + 1, blk.base ? blk.base : 1, (u32)blk.rem, 1.0 / (double)(blk.base + 1),
                      1.0 / (double)(blk.base ? blk.base : 1)};
-        launch_pass<OwnerSrc, u64, false>(ws, src, part_suf, part_bkt, nullptr, cnt, gb, ctr, 1u, st);
-        e->launches += 1;
+        launch_pass<OwnerSrc, u64, false>(ws, src, part_suf, part_bkt, nullptr, cnt, st);
+        e->launches += LAUNCHES_PER_PASS;
         // receive buffers: the bucket array (dead after the partition) and a scratch of n_local entries
         e->rk[0].reserve((n_local + 16) * sizeof(u64), tot);
         e->rk[1].reserve((n_local + 16) * sizeof(u64), tot);
@@ -532,17 +526,14 @@ bool construct_sharded_core(psacb200_engine* e, const ShardComm& C, const u8* d_
             // scatter window by window so the writes stay in L2 until their sectors are complete
             const int nb2 = (int)bits_for(n_local - 1);
             const int shift2 = nb2 > RADIX_BITS ? nb2 - RADIX_BITS : 0;
-            perm_gbase_kernel<<<1, RADIX, 0, st>>>(n_local, shift2, gb);
-            PSAC_CUDA(cudaMemsetAsync(ctr, 0, sizeof(u32), st));
-            PSAC_CUDA(cudaMemsetAsync(ws.lookback, 0, RadixWorkspace::lookback_bytes_for(n_local), st));
             ArraySrc<u64, u64> wsrc{recv_suf, recv_bkt, nullptr, shift2, (u32)(RADIX - 1), text_lo};
             e->vals[y].reserve((n_local + 16) * sizeof(u64), tot);
             e->keys[x].reserve((n_local + 16) * sizeof(u64), tot);
             u64* win_suf = e->vals[y].as<u64>();  // the partition buffers of the send side are free again
             u64* win_bkt = e->keys[x].as<u64>();
-            launch_pass<ArraySrc<u64, u64>, u64, false>(ws, wsrc, win_suf, win_bkt, nullptr, n_local, gb, ctr, 2u, st);
+            launch_pass<ArraySrc<u64, u64>, u64, false>(ws, wsrc, win_suf, win_bkt, nullptr, n_local, st);
             isa_scatter_kernel<u64><<<(unsigned)div_up(n_local, (size_t)4096), 256, 0, st>>>(win_suf, win_bkt, ISA - text_lo, n_local);
-            e->launches += 3;
+            e->launches += LAUNCHES_PER_PASS + 1;
         } else if (n_local) {
             isa_scatter_kernel<u64><<<(unsigned)div_up(n_local, (size_t)4096), 256, 0, st>>>(recv_suf, recv_bkt, ISA - text_lo, n_local);
             e->launches += 1;

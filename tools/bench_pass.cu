@@ -1,4 +1,5 @@
-// Stand-alone timing of ONE radix digit pass (u32 keys, u32 values [, aux byte]) with per-phase cycle accounting.
+// Stand-alone timing of ONE radix digit pass (u32 keys, u32 values [, aux byte]: histogram + scan + scatter) with per-phase cycle
+// accounting of the scatter kernel.
 // nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -DPSAC_PHASE_PROFILE -o tools/bench_pass tools/bench_pass.cu
 #include <cstdio>
 #include <vector>
@@ -20,21 +21,16 @@ void run(size_t n, int reps) {
     for (int b = 0; b < 2; ++b) { cudaMalloc(&k[b], n * 4); cudaMalloc(&v[b], n * 4); cudaMalloc(&a[b], n); }
     fill<<<1184, 256>>>(k[0], v[0], a[0], n);
     RadixWorkspace ws;
-    cudaMalloc(&ws.ghist, MAX_PASSES * RADIX * 8); cudaMalloc(&ws.gbase, MAX_PASSES * RADIX * 8); cudaMalloc(&ws.counters, 64 * 4);
-    ws.lookback_bytes = RadixWorkspace::lookback_bytes_for(n); cudaMalloc(&ws.lookback, ws.lookback_bytes);
-    RadixPlan plan = make_radix_plan(0, 32);
-    cudaMemset(ws.ghist, 0, MAX_PASSES * RADIX * 8);
-    radix_hist_kernel<u32><<<592, 512>>>(k[0], n, plan, ws.ghist);
-    radix_scan_hist_kernel<<<plan.npass, RADIX>>>(ws.ghist, ws.gbase);
+    cudaMalloc(&ws.gbase, RADIX * 8);
+    ws.tiles_bytes = RadixWorkspace::tiles_bytes_for(n); cudaMalloc(&ws.tiles, ws.tiles_bytes);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     float best = 1e9f;
     unsigned long long zero[16] = {0};
     for (int r = 0; r < reps; ++r) {
-        cudaMemset(ws.counters, 0, 64 * 4); cudaMemset(ws.lookback, 0, ws.lookback_bytes);
         cudaMemcpyToSymbol(g_phase_cycles, zero, sizeof(zero));
         ArraySrc<u32, u32> src{k[0], v[0], AUX ? a[0] : nullptr, 8, 255u, 0u};
         cudaEventRecord(e0);
-        launch_pass<ArraySrc<u32, u32>, u32, AUX>(ws, src, k[1], v[1], AUX ? a[1] : nullptr, n, ws.gbase + RADIX, ws.counters, 1u, 0);
+        launch_pass<ArraySrc<u32, u32>, u32, AUX>(ws, src, k[1], v[1], AUX ? a[1] : nullptr, n, 0);
         cudaEventRecord(e1); cudaEventSynchronize(e1);
         float ms; cudaEventElapsedTime(&ms, e0, e1); if (ms < best) best = ms;
     }
@@ -42,12 +38,12 @@ void run(size_t n, int reps) {
     using T = SortTuning<u32, u32>;
     const double tiles = (double)((n + T::THREADS * T::ITEMS - 1) / (T::THREADS * T::ITEMS));
     printf("n=%zu aux=%d: %.3f ms  (%.1f GB/s algorithmic)  err=%s\n", n, (int)AUX, best, n * (AUX ? 18.0 : 16.0) / best * 1e-6, cudaGetErrorString(cudaGetLastError()));
-    const char* names[7] = {"key loads + count", "barrier 1", "digit scan", "rank + scatter", "look-back", "barrier 3", "write-out"};
+    const char* names[7] = {"key loads + count", "barrier 1", "digit scan", "rank + scatter", "offsets", "barrier 3", "write-out"};
     double tot = 0; for (int i = 0; i < 7; ++i) tot += ph[i];
     for (int i = 0; i < 7; ++i) printf("   %-18s %9.0f cycles/tile  %5.1f%%\n", names[i], ph[i] / tiles, 100.0 * ph[i] / tot);
     printf("   total %.0f cycles per tile (thread 0), tiles=%.0f\n", tot / tiles, tiles);
     for (int b = 0; b < 2; ++b) { cudaFree(k[b]); cudaFree(v[b]); cudaFree(a[b]); }
-    cudaFree(ws.ghist); cudaFree(ws.gbase); cudaFree(ws.counters); cudaFree(ws.lookback);
+    cudaFree(ws.gbase); cudaFree(ws.tiles);
 }
 
 int main() {
