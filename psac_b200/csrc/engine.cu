@@ -90,7 +90,8 @@ struct psacb200_engine {
     u64* counts() const { return byte_hist() + 256; }
     u32* counters() const { return reinterpret_cast<u32*>(counts() + 8); }
     u64* shard_meta() const { return reinterpret_cast<u64*>(counters() + 64); }  // 64 u64 of small per-rank exchange data
-    static size_t small_bytes() { return (2 * MAX_PASSES * RADIX + 256 + 8) * sizeof(u64) + 64 * sizeof(u32) + 64 * sizeof(u64); }
+    void* tail_list() const { return shard_meta() + 64; }                         // TailList (sa_kernels.cuh)
+    static size_t small_bytes() { return (2 * MAX_PASSES * RADIX + 256 + 8) * sizeof(u64) + 64 * sizeof(u32) + 64 * sizeof(u64) + 1024; }
 
     RadixWorkspace radix_ws() const {
         RadixWorkspace ws;
@@ -325,7 +326,41 @@ void construct_core(psacb200_engine* e, u64 n, int index_bytes, unsigned flags, 
     R.isa_lo = 0;
     R.isa_hi = n;
     R.suf_out = nullptr;
-    launch_resolve<IdxT, KeyC>(e, true, R);
+    if (sizeof(IdxT) == 4 && !alpha.zero_code_used) {
+        // lean path: heads from the keys alone (sa_kernels.cuh heads_kernel); the suffixes that run past the end of the
+        // text are located in the sorted order first
+        const u64 T = (n < (u64)C - 1) ? n : (u64)C - 1;
+        static_assert(sizeof(TailList) <= 1024, "TailList must fit its slot in the small buffer");
+        TailList* tails = reinterpret_cast<TailList*>(e->tail_list());
+        tail_positions_kernel<KeyC><<<1, 64, 0, st>>>(kbuf[x], R.aux, n, R.drop, e->packed.as<u64>(), n, T, lbits, (int)C * lbits, tails);
+        HeadsArgs H{};
+        H.keys = kbuf[x];
+        H.aux = R.aux;
+        H.vals = reinterpret_cast<const u32*>(SA);
+        H.m = n;
+        H.drop = R.drop;
+        H.lbits = lbits;
+        H.C = (int)C;
+        H.tails = tails;
+        H.bucket_out = reinterpret_cast<u32*>(bucket);
+        H.isa = partitioned ? nullptr : reinterpret_cast<u32*>(ISA);
+        H.lcp = reinterpret_cast<u32*>(LCP);
+        H.pos_out = reinterpret_cast<u32*>(R.pos_out);
+        H.head_out = R.head_out;
+        H.cap = R.cap;
+        H.counts = R.counts;
+        const u64 ntiles = div_up(n, (size_t)HD_TILE);
+        H.agg_max = e->lookback.as<u64>();
+        H.agg_sum = H.agg_max + ntiles;
+        PSAC_CUDA(cudaMemsetAsync(R.counts, 0, 2 * sizeof(u64), st));
+        heads_kernel<KeyC, 0><<<(unsigned)ntiles, HD_THREADS, 0, st>>>(H);
+        tile_scan_kernel<<<1, 1024, 0, st>>>(H.agg_max, H.agg_sum, ntiles, R.counts);
+        heads_kernel<KeyC, 1><<<(unsigned)ntiles, HD_THREADS, 0, st>>>(H);
+        e->launches += 4;
+        PSAC_CUDA(cudaGetLastError());
+    } else {
+        launch_resolve<IdxT, KeyC>(e, true, R);
+    }
     e->end(PH_RESOLVE);
     u64 m = 0, nb = 0;
     read_counts(e, &m, &nb);

@@ -419,6 +419,281 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(u64* __restrict__ mx, u
     }
 }
 
+// ------------------------------------------------------------------ round 0, lean path (a7 + a9)
+// Same results as resolve_kernel<FIRST> for 32-bit suffix indices without the padded-LCP quirk, at a fraction of the
+// instructions and bytes: heads come from the sorted keys alone.  The only place the suffix indices mattered was the
+// end-of-text rule (a suffix shorter than the key is a bucket of its own and caps the LCP), and those <= 63 suffixes
+// are located up front: the sort is stable and they were fed first, so tail j sits at lower_bound(its key) + (number
+// of shorter tails with the same key).  Reduce (PHASE 0) and apply (PHASE 1) around tile_scan_kernel as before.
+struct TailList {
+    u32 count;
+    u32 len[64];  // length of the suffix (< C)
+    u64 pos[64];  // position in the sorted order
+};
+
+template <typename KeyC>
+__global__ void __launch_bounds__(64) tail_positions_kernel(const KeyC* __restrict__ keys, const u8* __restrict__ aux, u64 m, int drop,
+                                                            const u64* __restrict__ stream, u64 n, u64 T, int lbits, int kbits, TailList* __restrict__ out) {
+    __shared__ u64 s_key[64];
+    const int j = threadIdx.x;
+    u64 full = 0;
+    if ((u64)j < T) full = stream_extract(stream, n - 1 - (u64)j, lbits, kbits);
+    s_key[j] = full;
+    __syncthreads();
+    if ((u64)j < T) {
+        u64 lo = 0, hi = m;  // first position whose complete key is >= full
+        while (lo < hi) {
+            const u64 mid = (lo + hi) >> 1;
+            u64 k = (u64)keys[mid];
+            if (drop > 0) k = (k << drop) | (u64)aux[mid];
+            if (k < full)
+                lo = mid + 1;
+            else
+                hi = mid;
+        }
+        u32 before = 0;
+        for (int i = 0; i < j; ++i) before += (s_key[i] == full) ? 1u : 0u;
+        out->pos[j] = lo + before;
+        out->len[j] = (u32)j + 1;
+    }
+    if (j == 0) out->count = (u32)T;
+}
+
+struct HeadsArgs {
+    const void* keys;      // sorted carried keys (KeyC)
+    const u8* aux;         // key bits dropped by digit pass 1 (drop > 0), else null
+    const u32* vals;       // sorted suffix indices; read only for the direct ISA scatter of small inputs
+    u64 m;                 // number of suffixes
+    int drop, lbits, C;
+    const TailList* tails;
+    u32* bucket_out;
+    u32* isa;              // direct scatter (small inputs) or null
+    u32* lcp;              // or null
+    u32* pos_out;          // unresolved list (first `cap` entries)
+    u8* head_out;
+    u64 cap;
+    u64* counts;           // [1] unresolved buckets (atomic); [0] is written by tile_scan_kernel
+    u64* agg_max;          // per tile: last head position / exclusive prefix after the scan
+    u64* agg_sum;          // per tile: unresolved elements / exclusive prefix
+};
+
+constexpr int HD_THREADS = 256;
+constexpr int HD_ITEMS = 16;
+constexpr int HD_TILE = HD_THREADS * HD_ITEMS;
+
+template <typename KeyC, int PHASE>
+__global__ void __launch_bounds__(HD_THREADS) heads_kernel(HeadsArgs A) {
+    __shared__ u32 s_wmax[HD_THREADS / 32];
+    __shared__ u32 s_wsum[HD_THREADS / 32];
+    __shared__ TailList s_tails;
+    __shared__ int s_has_tail;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u64 tile = blockIdx.x;
+    const u64 t0 = tile * HD_TILE;
+    const u64 q0 = t0 + (u64)tid * HD_ITEMS;
+    const u64 m = A.m;
+    const KeyC* keys = reinterpret_cast<const KeyC*>(A.keys);
+    if (tid == 0) s_has_tail = 0;
+    __syncthreads();
+    if (tid < 64 && (u32)tid < A.tails->count) {
+        const u64 p = A.tails->pos[tid];
+        if (p + 1 >= t0 && p <= t0 + HD_TILE) s_has_tail = 1;  // benign race: every writer stores 1
+    }
+    // ---- my 16 complete keys + one neighbour on each side
+    u64 key[HD_ITEMS + 2];
+    const bool full_run = q0 + HD_ITEMS <= m;
+    if (full_run) {
+        if (sizeof(KeyC) == 4) {
+            const uint4* v = reinterpret_cast<const uint4*>(keys + q0);
+#pragma unroll
+            for (int c = 0; c < HD_ITEMS / 4; ++c) {
+                const uint4 t = __ldcs(v + c);
+                key[1 + 4 * c] = t.x;
+                key[2 + 4 * c] = t.y;
+                key[3 + 4 * c] = t.z;
+                key[4 + 4 * c] = t.w;
+            }
+        } else {
+            const uint4* v = reinterpret_cast<const uint4*>(keys + q0);
+#pragma unroll
+            for (int c = 0; c < HD_ITEMS / 2; ++c) {
+                const uint4 t = __ldcs(v + c);
+                key[1 + 2 * c] = ((u64)t.y << 32) | t.x;
+                key[2 + 2 * c] = ((u64)t.w << 32) | t.z;
+            }
+        }
+        if (A.drop > 0) {
+            const uint4 t = __ldcs(reinterpret_cast<const uint4*>(A.aux + q0));
+            const u32 w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+            for (int i = 0; i < HD_ITEMS; ++i) key[1 + i] = (key[1 + i] << A.drop) | ((w[i >> 2] >> (8 * (i & 3))) & 0xffu);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < HD_ITEMS; ++i) {
+            const u64 q = q0 + i;
+            u64 k = 0;
+            if (q < m) {
+                k = (u64)keys[q];
+                if (A.drop > 0) k = (k << A.drop) | (u64)A.aux[q];
+            }
+            key[1 + i] = k;
+        }
+    }
+    {
+        const u64 left = __shfl_up_sync(0xffffffffu, key[HD_ITEMS], 1);
+        const u64 right = __shfl_down_sync(0xffffffffu, key[1], 1);
+        u64 l = left, r = right;
+        if (lane == 0) {
+            l = 0;
+            if (q0 >= 1 && q0 - 1 < m) {
+                l = (u64)keys[q0 - 1];
+                if (A.drop > 0) l = (l << A.drop) | (u64)A.aux[q0 - 1];
+            }
+        }
+        if (lane == 31) {
+            r = 0;
+            if (q0 + HD_ITEMS < m) {
+                r = (u64)keys[q0 + HD_ITEMS];
+                if (A.drop > 0) r = (r << A.drop) | (u64)A.aux[q0 + HD_ITEMS];
+            }
+        }
+        key[0] = l;
+        key[HD_ITEMS + 1] = r;
+    }
+    __syncthreads();
+    // ---- head bits of q0 .. q0+16 (bit 16 only feeds the "unresolved" test)
+    u32 head = 0;
+#pragma unroll
+    for (int i = 0; i <= HD_ITEMS; ++i) {
+        const u64 q = q0 + i;
+        if (q >= m || q == 0 || key[i + 1] != key[i]) head |= 1u << i;
+    }
+    if (s_has_tail) {
+        if (tid < 64) {
+            s_tails.pos[tid] = (u32)tid < A.tails->count ? A.tails->pos[tid] : ~0ull;
+            s_tails.len[tid] = (u32)tid < A.tails->count ? A.tails->len[tid] : 0u;
+        }
+        if (tid == 0) s_tails.count = A.tails->count;
+        __syncthreads();
+        for (u32 t = 0; t < s_tails.count; ++t) {
+            const u64 p = s_tails.pos[t];  // a suffix that runs past the end is a bucket of its own: heads at p and p + 1
+            if (p >= q0 && p <= q0 + HD_ITEMS) head |= 1u << (u32)(p - q0);
+            if (p + 1 >= q0 && p + 1 <= q0 + HD_ITEMS) head |= 1u << (u32)(p + 1 - q0);
+        }
+    }
+    const u32 valid = (q0 >= m) ? 0u : ((m - q0 >= HD_ITEMS) ? 0xffffu : ((1u << (u32)(m - q0)) - 1u));
+    const u32 hv = head & valid;                               // heads among my valid elements
+    const u32 unres = ~(head & (head >> 1)) & valid;           // element i is resolved iff it and its successor are heads
+    const u32 my_last = hv ? (u32)(q0 + (31 - __clz(hv))) : 0u;  // SA position of my last head (positions fit 32 bits here)
+    const u32 my_cnt = __popc(unres);
+    // ---- block scans: running max of head positions, running sum of unresolved counts
+    u32 imax = my_last, isum = my_cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const u32 om = __shfl_up_sync(0xffffffffu, imax, d);
+        const u32 os = __shfl_up_sync(0xffffffffu, isum, d);
+        if (lane >= d) {
+            imax = om > imax ? om : imax;
+            isum += os;
+        }
+    }
+    if (lane == 31) {
+        s_wmax[warp] = imax;
+        s_wsum[warp] = isum;
+    }
+    __syncthreads();
+    u32 cta_max = 0, cta_sum = 0, wpre_max = 0, wpre_sum = 0;
+#pragma unroll
+    for (int w = 0; w < HD_THREADS / 32; ++w) {
+        if (w == warp) {
+            wpre_max = cta_max;
+            wpre_sum = cta_sum;
+        }
+        cta_max = s_wmax[w] > cta_max ? s_wmax[w] : cta_max;
+        cta_sum += s_wsum[w];
+    }
+    if (PHASE == 0) {
+        if (tid == 0) {
+            A.agg_max[tile] = cta_max;
+            A.agg_sum[tile] = cta_sum;
+        }
+        const u32 nb = __popc(unres & head);  // unresolved buckets start at unresolved heads
+        u32 wb = nb;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) wb += __shfl_xor_sync(0xffffffffu, wb, d);
+        if (lane == 0 && wb) atomicAdd((unsigned long long*)&A.counts[1], (unsigned long long)wb);
+        return;
+    }
+    u32 tex_max = __shfl_up_sync(0xffffffffu, imax, 1);
+    if (lane == 0) tex_max = 0;
+    u32 run = (u32)A.agg_max[tile];
+    run = wpre_max > run ? wpre_max : run;
+    run = tex_max > run ? tex_max : run;
+    u64 o = A.agg_sum[tile] + wpre_sum + (isum - my_cnt);
+    if (q0 >= m) return;
+    // ---- bucket ids: position of the latest head
+    u32 bucket[HD_ITEMS];
+#pragma unroll
+    for (int i = 0; i < HD_ITEMS; ++i) {
+        if ((hv >> i) & 1u) run = (u32)(q0 + i);
+        bucket[i] = run;
+    }
+    if (full_run) {
+        uint4* ob = reinterpret_cast<uint4*>(A.bucket_out + q0);
+#pragma unroll
+        for (int c = 0; c < HD_ITEMS / 4; ++c) __stcs(ob + c, make_uint4(bucket[4 * c], bucket[4 * c + 1], bucket[4 * c + 2], bucket[4 * c + 3]));
+    } else {
+#pragma unroll
+        for (int i = 0; i < HD_ITEMS; ++i)
+            if (q0 + i < m) A.bucket_out[q0 + i] = bucket[i];
+    }
+    if (A.isa != nullptr) {
+#pragma unroll
+        for (int i = 0; i < HD_ITEMS; ++i)
+            if (q0 + i < m) A.isa[A.vals[q0 + i]] = bucket[i];
+    }
+    if (A.lcp != nullptr) {
+        const int nbits = A.C * A.lbits;
+        u32 l[HD_ITEMS];
+#pragma unroll
+        for (int i = 0; i < HD_ITEMS; ++i) {
+            const u64 x = key[i] ^ key[i + 1];
+            l[i] = x ? (u32)(__clzll((long long)(x << (64 - nbits))) / A.lbits) : (u32)A.C;
+        }
+        if (s_has_tail) {
+            for (u32 t = 0; t < s_tails.count; ++t) {
+                const u64 p = s_tails.pos[t];  // the boundaries on both sides of a short suffix are capped by its length
+#pragma unroll
+                for (int i = 0; i < HD_ITEMS; ++i)
+                    if (q0 + i == p || q0 + i == p + 1) l[i] = l[i] < s_tails.len[t] ? l[i] : s_tails.len[t];
+            }
+        }
+        if (q0 == 0) l[0] = 0;
+        // every position becomes a head in exactly one round and gets its LCP then: entries of non-heads written here
+        // are overwritten by the round that splits them, so the whole run can leave as 128-bit stores
+        if (full_run) {
+            uint4* ol = reinterpret_cast<uint4*>(A.lcp + q0);
+#pragma unroll
+            for (int c = 0; c < HD_ITEMS / 4; ++c) __stcs(ol + c, make_uint4(l[4 * c], l[4 * c + 1], l[4 * c + 2], l[4 * c + 3]));
+        } else {
+#pragma unroll
+            for (int i = 0; i < HD_ITEMS; ++i)
+                if (q0 + i < m) A.lcp[q0 + i] = l[i];
+        }
+    }
+    u32 u = unres;
+    while (u) {
+        const int i = __ffs(u) - 1;
+        u &= u - 1;
+        if (o < A.cap) {
+            A.pos_out[o] = (u32)(q0 + i);
+            A.head_out[o] = (head >> i) & 1u;
+        }
+        ++o;
+    }
+}
+
 // ------------------------------------------------------------------ round 0: list the unresolved elements
 // From the bucket ids of round 0 (bucket[q] = position of q's bucket head): q is a head iff bucket[q] == q; it is
 // unresolved iff its bucket has >= 2 members.  Writes their positions and head flags in order (sum-scan + look-back).
