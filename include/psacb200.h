@@ -118,6 +118,17 @@ int psacb200_construct_sharded(psacb200_engine* e, const uint8_t* d_text_local, 
 void psacb200_blk_dist(uint64_t n, int p, int r, uint64_t* start, uint64_t* size);
 int psacb200_choose_splitters(const uint64_t* hist, size_t nbins, uint64_t n, int p, uint64_t* first, uint64_t* count);
 
+/* ---- ANSV and suffix tree (reference include/ansv.hpp:2042-2051, include/suffix_tree.hpp:413-499) ------------------- */
+/* All nearest smaller values of n HOST values (val_bytes 4 or 8): left[i] / right[i] = index of the match on that side,
+ * or `nonsv` (global indexing at p = 1).  Modes: 0 nearest_sm, 1 nearest_eq, 2 furthest_eq (ansv.hpp:24-45). */
+int psacb200_ansv(psacb200_engine* e, const void* vals, size_t n, int val_bytes, int left_type, int right_type, uint64_t nonsv, uint64_t* left,
+                  uint64_t* right);
+/* Suffix tree from SA + LCP (HOST arrays of index_bytes each) and the text, as the reference's child table
+ * (construct_suffix_tree, suffix_tree.hpp:440-499): nodes[(sigma+1) * parent + code] = child, internal nodes are LCP
+ * indices, leaves are n + SA position, 0 = empty.  nodes_len >= (sigma+1) * n (sigma from psacb200_alphabet). */
+int psacb200_suffix_tree(psacb200_engine* e, const uint8_t* text, size_t n, int index_bytes, const void* sa, const void* lcp, uint64_t* nodes,
+                         size_t nodes_len);
+
 #ifdef __cplusplus
 }
 #endif

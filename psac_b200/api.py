@@ -85,6 +85,8 @@ def lib():
         L.psacb200_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.psacb200_construct_sharded.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_uint, C.c_uint, C.c_void_p, C.c_void_p,
                                                  C.c_void_p]
+        L.psacb200_ansv.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p]
+        L.psacb200_suffix_tree.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
         L.psacb200_blk_dist.argtypes = [C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.psacb200_blk_dist.restype = None
         L.psacb200_choose_splitters.argtypes = [C.c_void_p, C.c_size_t, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]
@@ -190,6 +192,29 @@ class Engine:
         """Collective; all pointers are DEVICE buffers of this rank's blocks."""
         _check(lib().psacb200_construct_sharded(self._h, _ptr(text_ptr), n_local, n_global, index_bytes, flags, k, _ptr(sa_ptr), _ptr(isa_ptr),
                                                 _ptr(lcp_ptr)))
+
+    # ---- ANSV / suffix tree
+    NEAREST_SM, NEAREST_EQ, FURTHEST_EQ = 0, 1, 2
+
+    def ansv(self, vals, left_type=0, right_type=0, nonsv=0):
+        """reference ansv<T, left_type, right_type, global_indexing>(in, left, right, comm, nonsv) at p = 1 (ansv.hpp:2042-2051)"""
+        v = np.ascontiguousarray(vals)
+        assert v.dtype in (np.uint32, np.uint64)
+        left = np.empty(v.size, np.uint64)
+        right = np.empty(v.size, np.uint64)
+        _check(lib().psacb200_ansv(self._h, _ptr(v), v.size, v.dtype.itemsize, left_type, right_type, nonsv, _ptr(left), _ptr(right)))
+        return left, right
+
+    def suffix_tree(self, text, sa, lcp):
+        """reference construct_suffix_tree(sa, begin, end, comm) at p = 1 (suffix_tree.hpp:413-499): (n, sigma+1) child table"""
+        t = _as_text(text)
+        sa = np.ascontiguousarray(sa)
+        lcp = np.ascontiguousarray(lcp, sa.dtype)
+        assert sa.dtype in (np.uint32, np.uint64) and sa.size == t.size == lcp.size
+        sigma = len(np.unique(t))
+        nodes = np.zeros((t.size, sigma + 1), np.uint64)
+        _check(lib().psacb200_suffix_tree(self._h, _ptr(t), t.size, sa.dtype.itemsize, _ptr(sa), _ptr(lcp), _ptr(nodes), nodes.size))
+        return nodes
 
     def sort_pairs_host(self, keys, vals, begin_bit, end_bit):
         """In-place stable radix sort of numpy keys (uint32/uint64) and optional values by key bits [begin_bit, end_bit)."""

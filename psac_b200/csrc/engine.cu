@@ -14,6 +14,7 @@
 #include "../../include/psacb200.h"
 #include "radix_sort.cuh"
 #include "sa_kernels.cuh"
+#include "tree_kernels.cuh"
 
 using namespace psacb200;
 
@@ -75,7 +76,7 @@ struct psacb200_engine {
     cudaStream_t stream = nullptr;
     size_t device_bytes = 0;
     uint64_t launches = 0;
-    DevBuf text, packed, keys[2], vals[2], aux[2], isa, lcp, small, lookback, rk[2], rv[2], rp[2], rh[2], scratch, rep[3];
+    DevBuf text, packed, keys[2], vals[2], aux[2], isa, lcp, small, lookback, rk[2], rv[2], rp[2], rh[2], scratch, rep[3], tb[6];
     void* nccl_comm = nullptr;  // ncclComm_t of the sharded construction (sharded.cuh), one rank per engine
     int shard_rank = 0, shard_world = 1;
     u64* h_pinned = nullptr;  // 512 u64 of pinned host memory for small read-backs
@@ -623,6 +624,38 @@ bool sort_dispatch_val(psacb200_engine* e, void* k, void* ka, void* v, void* va,
 
 }  // namespace
 
+// ---- ANSV: min-tree levels + search kernel (tree_kernels.cuh)
+namespace {
+template <typename T>
+void ansv_device(psacb200_engine* e, const T* d_vals, u64 n, int left_type, int right_type, u64 nonsv, u64* d_left, u64* d_right) {
+    MinTree<T> t{};
+    t.level[0] = d_vals;
+    t.size[0] = n;
+    t.levels = 1;
+    // upper levels: minima of blocks of 32, until one block is left
+    u64 total = 0;
+    for (u64 m = n; m > ANSV_FAN;) {
+        m = div_up(m, (size_t)ANSV_FAN);
+        total += m;
+    }
+    e->tb[0].reserve((total + 1) * sizeof(T), &e->device_bytes);
+    T* base = e->tb[0].as<T>();
+    while (t.size[t.levels - 1] > ANSV_FAN) {
+        if (t.levels >= ANSV_MAX_LEVELS) throw arg_failure{"ANSV input too large"};
+        const u64 m = div_up(t.size[t.levels - 1], (size_t)ANSV_FAN);
+        mintree_level_kernel<T><<<grid_for(e, m, 256, 8), 256, 0, e->stream>>>(t.level[t.levels - 1], t.size[t.levels - 1], base, m);
+        e->launches += 1;
+        t.level[t.levels] = base;
+        t.size[t.levels] = m;
+        base += m;
+        t.levels += 1;
+    }
+    ansv_kernel<T><<<grid_for(e, n, 256, 8), 256, 0, e->stream>>>(t, left_type, right_type, nonsv, d_left, d_right);
+    e->launches += 1;
+    PSAC_CUDA(cudaGetLastError());
+}
+}  // namespace
+
 #include "sharded.cuh"
 
 // ================================================================================================ C ABI
@@ -685,7 +718,7 @@ void psacb200_destroy(psacb200_engine* e) {
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->stream);
     DevBuf* all[] = {&e->text, &e->packed, &e->keys[0], &e->keys[1], &e->vals[0], &e->vals[1], &e->aux[0], &e->aux[1], &e->isa, &e->lcp, &e->small, &e->lookback,
-                     &e->rk[0], &e->rk[1], &e->rv[0], &e->rv[1], &e->rp[0], &e->rp[1], &e->rh[0], &e->rh[1], &e->scratch, &e->rep[0], &e->rep[1], &e->rep[2]};
+                     &e->rk[0], &e->rk[1], &e->rv[0], &e->rv[1], &e->rp[0], &e->rp[1], &e->rh[0], &e->rh[1], &e->scratch, &e->rep[0], &e->rep[1], &e->rep[2], &e->tb[0], &e->tb[1], &e->tb[2], &e->tb[3], &e->tb[4], &e->tb[5]};
     for (DevBuf* b : all) b->release(nullptr);
     for (int i = 0; i < PH_COUNT; ++i) {
         cudaEventDestroy(e->ev_begin[i]);
@@ -926,6 +959,97 @@ int psacb200_choose_splitters(const uint64_t* hist, size_t nbins, uint64_t n, in
     for (int r = 0; r <= p; ++r) first_out[r] = first[r];
     for (int r = 0; r < p; ++r) count_out[r] = count[r];
     return PSACB200_OK;
+}
+
+
+// ---- ANSV and suffix tree (tree_kernels.cuh)
+int psacb200_ansv(psacb200_engine* e, const void* vals, size_t n, int val_bytes, int left_type, int right_type, uint64_t nonsv, uint64_t* left,
+                  uint64_t* right) {
+    if (!e) {
+        set_last_error("null engine");
+        return PSACB200_ERR_ARG;
+    }
+    if (n == 0) return PSACB200_OK;
+    return guarded([&]() -> int {
+        if (!vals || !left || !right) throw arg_failure{"null argument"};
+        if (val_bytes != 4 && val_bytes != 8) throw arg_failure{"val_bytes must be 4 or 8"};
+        if (left_type < 0 || left_type > 2 || right_type < 0 || right_type > 2) throw arg_failure{"match mode must be 0 (nearest_sm), 1 (nearest_eq) or 2 (furthest_eq)"};
+        PSAC_CUDA(cudaSetDevice(e->device));
+        size_t* tot = &e->device_bytes;
+        e->tb[1].reserve(n * (size_t)val_bytes, tot);
+        e->tb[2].reserve(n * sizeof(u64), tot);
+        e->tb[3].reserve(n * sizeof(u64), tot);
+        PSAC_CUDA(cudaMemcpyAsync(e->tb[1].p, vals, n * (size_t)val_bytes, cudaMemcpyHostToDevice, e->stream));
+        if (val_bytes == 4)
+            ansv_device<u32>(e, e->tb[1].as<u32>(), n, left_type, right_type, nonsv, e->tb[2].as<u64>(), e->tb[3].as<u64>());
+        else
+            ansv_device<u64>(e, e->tb[1].as<u64>(), n, left_type, right_type, nonsv, e->tb[2].as<u64>(), e->tb[3].as<u64>());
+        PSAC_CUDA(cudaMemcpyAsync(left, e->tb[2].p, n * sizeof(u64), cudaMemcpyDeviceToHost, e->stream));
+        PSAC_CUDA(cudaMemcpyAsync(right, e->tb[3].p, n * sizeof(u64), cudaMemcpyDeviceToHost, e->stream));
+        PSAC_CUDA(cudaStreamSynchronize(e->stream));
+        return PSACB200_OK;
+    });
+}
+
+int psacb200_suffix_tree(psacb200_engine* e, const uint8_t* text, size_t n, int index_bytes, const void* sa, const void* lcp, uint64_t* nodes,
+                         size_t nodes_len) {
+    if (!e) {
+        set_last_error("null engine");
+        return PSACB200_ERR_ARG;
+    }
+    if (n == 0) return PSACB200_OK;
+    return guarded([&]() -> int {
+        if (!text || !sa || !lcp || !nodes) throw arg_failure{"null argument"};
+        if (index_bytes != 4 && index_bytes != 8) throw arg_failure{"index_bytes must be 4 or 8"};
+        PSAC_CUDA(cudaSetDevice(e->device));
+        cudaStream_t st = e->stream;
+        size_t* tot = &e->device_bytes;
+        e->text.reserve(n + 64, tot);
+        e->small.reserve(psacb200_engine::small_bytes(), tot);
+        PSAC_CUDA(cudaMemcpyAsync(e->text.p, text, n, cudaMemcpyHostToDevice, st));
+        // alphabet (reference codes)
+        PSAC_CUDA(cudaMemsetAsync(e->byte_hist(), 0, 256 * sizeof(u64), st));
+        byte_hist_kernel<<<grid_for(e, n / 16 + 1, 512, 4), 512, 0, st>>>(e->text.as<u8>(), n, e->byte_hist());
+        e->launches += 1;
+        PSAC_CUDA(cudaMemcpyAsync(e->h_pinned + 16, e->byte_hist(), 256 * sizeof(u64), cudaMemcpyDeviceToHost, st));
+        PSAC_CUDA(cudaStreamSynchronize(st));
+        Alphabet alpha;
+        alphabet_from_hist(e->h_pinned + 16, alpha);
+        const size_t width = (size_t)alpha.sigma + 1;
+        if (nodes_len < width * n) throw arg_failure{"nodes buffer too small: (sigma + 1) * n entries are needed"};
+        e->tb[1].reserve(n * (size_t)index_bytes, tot);  // LCP
+        e->tb[2].reserve(n * sizeof(u64), tot);          // left ANSV
+        e->tb[3].reserve(n * sizeof(u64), tot);          // right ANSV
+        e->tb[4].reserve(n * (size_t)index_bytes, tot);  // SA
+        e->tb[5].reserve(width * n * sizeof(u64), tot);  // child table
+        PSAC_CUDA(cudaMemcpyAsync(e->tb[1].p, lcp, n * (size_t)index_bytes, cudaMemcpyHostToDevice, st));
+        PSAC_CUDA(cudaMemcpyAsync(e->tb[4].p, sa, n * (size_t)index_bytes, cudaMemcpyHostToDevice, st));
+        PSAC_CUDA(cudaMemsetAsync(e->tb[5].p, 0, width * n * sizeof(u64), st));
+        // ansv<index_t, furthest_eq, nearest_sm>(LCP)  (suffix_tree.hpp:62)
+        if (index_bytes == 4)
+            ansv_device<u32>(e, e->tb[1].as<u32>(), n, 2, 0, ANSV_NONE, e->tb[2].as<u64>(), e->tb[3].as<u64>());
+        else
+            ansv_device<u64>(e, e->tb[1].as<u64>(), n, 2, 0, ANSV_NONE, e->tb[2].as<u64>(), e->tb[3].as<u64>());
+        TreeArgs A{};
+        A.sa = e->tb[4].p;
+        A.lcp = e->tb[1].p;
+        A.text = e->text.as<u8>();
+        A.n = n;
+        A.left = e->tb[2].as<u64>();
+        A.right = e->tb[3].as<u64>();
+        A.sigma = alpha.sigma;
+        memcpy(A.lut, alpha.lut, 256);
+        A.nodes = e->tb[5].as<u64>();
+        if (index_bytes == 4)
+            suffix_tree_kernel<u32><<<grid_for(e, n, 256, 8), 256, 0, st>>>(A);
+        else
+            suffix_tree_kernel<u64><<<grid_for(e, n, 256, 8), 256, 0, st>>>(A);
+        e->launches += 1;
+        PSAC_CUDA(cudaGetLastError());
+        PSAC_CUDA(cudaMemcpyAsync(nodes, e->tb[5].p, width * n * sizeof(u64), cudaMemcpyDeviceToHost, st));
+        PSAC_CUDA(cudaStreamSynchronize(st));
+        return PSACB200_OK;
+    });
 }
 
 }  // extern "C"
