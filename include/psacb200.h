@@ -47,7 +47,7 @@ typedef struct psacb200_stats {
     uint32_t rounds;          /* sorting rounds executed (1 = the first sort resolved everything) */
     uint32_t sort_passes;     /* radix digit passes of the first sort */
     uint32_t internal_index_bytes;
-    uint32_t reserved;
+    uint32_t reserved;        /* sharded construction: 1 = the SA->ISA exchange used peer stores over NVLink (fused kernel) */
     uint64_t unresolved_after_first; /* suffixes still sharing a bucket after the first sort */
     uint64_t device_bytes;    /* device memory held by the engine */
     float ms_total;           /* device time of the whole call (CUDA events) */

@@ -33,7 +33,7 @@ class Stats(C.Structure):
         ("rounds", C.c_uint32),
         ("sort_passes", C.c_uint32),
         ("internal_index_bytes", C.c_uint32),
-        ("reserved", C.c_uint32),
+        ("peer_exchange", C.c_uint32),
         ("unresolved_after_first", C.c_uint64),
         ("device_bytes", C.c_uint64),
         ("ms_total", C.c_float),

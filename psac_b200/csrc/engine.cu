@@ -7,6 +7,8 @@
 // Output SA / ISA / LCP are the unique arrays of the 0-padded suffix order, hence bit-identical to the reference's
 // (SURVEY.md section 0, items 1-2).
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
 #include <new>
 #include <string>
 #include <vector>
@@ -78,6 +80,7 @@ struct psacb200_engine {
     uint64_t launches = 0;
     DevBuf text, packed, keys[2], vals[2], aux[2], isa, lcp, small, lookback, rk[2], rv[2], rp[2], rh[2], scratch, rep[3], tb[6];
     void* nccl_comm = nullptr;  // ncclComm_t of the sharded construction (sharded.cuh), one rank per engine
+    void* peer_map = nullptr;   // PeerMap: CUDA-IPC mappings of the peers' exchange buffers (sharded.cuh)
     int shard_rank = 0, shard_world = 1;
     u64* h_pinned = nullptr;  // 512 u64 of pinned host memory for small read-backs
     cudaEvent_t ev_begin[PH_COUNT], ev_end[PH_COUNT];
@@ -724,6 +727,13 @@ void psacb200_destroy(psacb200_engine* e) {
         cudaEventDestroy(e->ev_begin[i]);
         cudaEventDestroy(e->ev_end[i]);
     }
+    if (e->peer_map) {
+        PeerMap* pm = reinterpret_cast<PeerMap*>(e->peer_map);
+        for (int r = 0; r < 16; ++r)
+            for (int b = 0; b < 2; ++b)
+                if (pm->open[r][b]) cudaIpcCloseMemHandle(pm->mapped[r][b]);
+        delete pm;
+    }
     if (e->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(reinterpret_cast<ncclComm_t>(e->nccl_comm));
     if (e->h_pinned) cudaFreeHost(e->h_pinned);
     cudaStreamDestroy(e->stream);
@@ -885,6 +895,7 @@ int psacb200_comm_init(psacb200_engine* e, const uint8_t id[128], int rank, int 
         ncclComm_t c;
         PSAC_NCCL(g_nccl.CommInitRank(&c, world, u, rank));
         e->nccl_comm = c;
+        if (!e->peer_map && !getenv("PSACB200_NO_PEER")) e->peer_map = new PeerMap();  // PSACB200_NO_PEER=1: NCCL all-to-all-v instead of peer stores
         e->shard_rank = rank;
         e->shard_world = world;
         return PSACB200_OK;

@@ -85,6 +85,7 @@ struct ArraySrc {
     using Stage = KeyT;
     using Out = KeyT;
     static constexpr bool FROM_TEXT = false;
+    static constexpr bool PEER = false;  // outputs go to one array pair (see OwnerSrc in sharded.cuh for per-digit outputs)
     const KeyT* __restrict__ kin;
     const ValT* __restrict__ vin;
     const u8* __restrict__ ain;  // auxiliary bytes (null when the pass carries none)
@@ -111,6 +112,7 @@ struct TextSrc {
     using Stage = u64;
     using Out = OutKeyT;
     static constexpr bool FROM_TEXT = true;
+    static constexpr bool PEER = false;
     const u64* __restrict__ stream;
     u64 n, T;
     int lbits, kbits, drop;
@@ -280,7 +282,10 @@ __device__ __forceinline__ void onesweep_tile(unsigned char* smem_raw, const Src
                 const u32 d = src.digit(k);
                 dig[i] = (u8)d;
                 const u64 o = goff[d] + (u64)s;
-                st_stream(kout + o, src.out_key(k));
+                if constexpr (Src::PEER)
+                    src.kpeer[d][o] = src.out_key(k);  // bin d lives in (peer) GPU d's receive buffer
+                else
+                    st_stream(kout + o, src.out_key(k));
                 if constexpr (Cfg::HAS_AUX) aout[o] = saux[s];
             }
         }
@@ -295,7 +300,12 @@ __device__ __forceinline__ void onesweep_tile(unsigned char* smem_raw, const Src
 #pragma unroll
             for (int i = 0; i < ITEMS; ++i) {
                 const int s = i * THREADS + tid;
-                if (FULL || s < valid) st_stream(vout + goff[dig[i]] + (u64)s, svals[s]);
+                if (FULL || s < valid) {
+                    if constexpr (Src::PEER)
+                        src.vpeer[dig[i]][goff[dig[i]] + (u64)s] = svals[s];
+                    else
+                        st_stream(vout + goff[dig[i]] + (u64)s, svals[s]);
+                }
             }
         }
     }

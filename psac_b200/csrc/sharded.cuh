@@ -209,12 +209,18 @@ __global__ void __launch_bounds__(64) select_tails_kernel(const u64* __restrict_
 }
 
 // key source of the SA -> ISA exchange partition: digit = owning rank of the suffix index under the block distribution
-struct OwnerSrc {
+template <bool PEER_>
+struct OwnerSrcT {
     using Stage = u64;
     using Out = u64;
     static constexpr bool FROM_TEXT = false;
+    static constexpr bool PEER = PEER_;
     const u64* __restrict__ kin;
     const u64* __restrict__ vin;
+    // PEER: bin d (= owning rank d) is written straight into rank d's receive buffers over NVLink; the pointers are
+    // pre-biased so that the bin-relative index the kernel computes (global bin offset + slot) lands at the right place
+    u64* kpeer[16];
+    u64* vpeer[16];
     u64 cut, base1, base;  // cut = rem * (base + 1)
     u32 rem;
     double inv_base1, inv_base;
@@ -230,6 +236,8 @@ struct OwnerSrc {
     __device__ __forceinline__ u64 load_val(size_t g) const { return ld_stream(vin + g); }
     __device__ __forceinline__ u8 load_aux(size_t, Stage) const { return 0; }
 };
+using OwnerSrc = OwnerSrcT<false>;
+using OwnerPeerSrc = OwnerSrcT<true>;
 
 // rank look-ups of one replicated round: ans[j] = ISA[suf[j] + h] + 1 if this shard owns that entry, else 0
 __global__ void __launch_bounds__(256) isa_answer_kernel(const u64* __restrict__ suf, u64 m, u64 h, u64 n, const u64* __restrict__ isa, u64 isa_lo,
@@ -256,6 +264,85 @@ struct ShardComm {
 };
 
 namespace {
+
+// CUDA-IPC mapping of every rank's two receive buffers of the SA -> ISA exchange, so that the owner partition kernel
+// can store straight into its peers' HBM over NVLink (kernel fused with its collective).  Handles are all-gathered on
+// every call (128 bytes per rank) and re-opened only when a buffer was re-allocated.  Returns false -- on every rank --
+// if any rank could not map its peers; the caller then uses the NCCL all-to-all-v path.
+struct PeerMap {
+    cudaIpcMemHandle_t handle[16][2];
+    void* mapped[16][2];
+    bool open[16][2];
+    PeerMap() {
+        memset(handle, 0, sizeof(handle));
+        memset(mapped, 0, sizeof(mapped));
+        memset(open, 0, sizeof(open));
+    }
+};
+
+bool map_peer_buffers(psacb200_engine* e, const ShardComm& C, void* mine0, void* mine1, PeerMap& pm, u64* out0[16], u64* out1[16]) {
+    cudaStream_t st = e->stream;
+    const int p = C.world, me = C.rank;
+    int ok = 1;
+    cudaIpcMemHandle_t hmine[2];
+    if (cudaIpcGetMemHandle(&hmine[0], mine0) != cudaSuccess || cudaIpcGetMemHandle(&hmine[1], mine1) != cudaSuccess) {
+        cudaGetLastError();
+        ok = 0;
+        memset(hmine, 0, sizeof(hmine));
+    }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    // all-gather the handles through a small device staging area
+    e->scratch.reserve((size_t)p * 128 + 64, &e->device_bytes);
+    u8* d_h = e->scratch.as<u8>();
+    PSAC_CUDA(cudaMemcpyAsync(d_h + (size_t)me * 128, hmine, 128, cudaMemcpyHostToDevice, st));
+    PSAC_NCCL(g_nccl.AllGather(d_h + (size_t)me * 128, d_h, 128, ncclUint8, C.comm, st));
+    std::vector<u8> all((size_t)p * 128);
+    PSAC_CUDA(cudaMemcpyAsync(all.data(), d_h, all.size(), cudaMemcpyDeviceToHost, st));
+    PSAC_CUDA(cudaStreamSynchronize(st));
+    for (int r = 0; r < p && ok; ++r) {
+        for (int b = 0; b < 2; ++b) {
+            if (r == me) {
+                pm.mapped[r][b] = b ? mine1 : mine0;
+                continue;
+            }
+            cudaIpcMemHandle_t h;
+            memcpy(&h, all.data() + (size_t)r * 128 + (size_t)b * 64, 64);
+            if (pm.open[r][b] && memcmp(&h, &pm.handle[r][b], 64) == 0) continue;
+            if (pm.open[r][b]) {
+                cudaIpcCloseMemHandle(pm.mapped[r][b]);
+                pm.open[r][b] = false;
+            }
+            void* ptr = nullptr;
+            if (cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                cudaGetLastError();
+                ok = 0;
+                break;
+            }
+            pm.handle[r][b] = h;
+            pm.mapped[r][b] = ptr;
+            pm.open[r][b] = true;
+        }
+    }
+    // agree: one failing rank sends everybody to the NCCL path
+    u64* d_ok = e->shard_meta() + 56;
+    e->h_pinned[40] = (u64)ok;
+    PSAC_CUDA(cudaMemcpyAsync(d_ok, e->h_pinned + 40, sizeof(u64), cudaMemcpyHostToDevice, st));
+    PSAC_NCCL(g_nccl.AllReduce(d_ok, d_ok, 1, ncclUint64, ncclMin, C.comm, st));
+    PSAC_CUDA(cudaMemcpyAsync(e->h_pinned + 40, d_ok, sizeof(u64), cudaMemcpyDeviceToHost, st));
+    PSAC_CUDA(cudaStreamSynchronize(st));
+    if (e->h_pinned[40] == 0) return false;
+    for (int r = 0; r < p; ++r) {
+        out0[r] = reinterpret_cast<u64*>(pm.mapped[r][0]);
+        out1[r] = reinterpret_cast<u64*>(pm.mapped[r][1]);
+    }
+    return true;
+}
+
+// stream-ordered barrier over the ranks (a one-word all-reduce)
+void rank_barrier(psacb200_engine* e, const ShardComm& C) {
+    u64* d = e->shard_meta() + 57;
+    PSAC_NCCL(g_nccl.AllReduce(d, d, 1, ncclUint64, ncclSum, C.comm, e->stream));
+}
 
 // all-to-all-v of `elt`-byte elements on the engine's stream (counts / displacements in elements)
 void all_to_all_v(psacb200_engine* e, const ShardComm& C, const void* send, const std::vector<u64>& scount, const std::vector<u64>& sdispl, void* recv,
@@ -508,19 +595,41 @@ bool construct_sharded_core(psacb200_engine* e, const ShardComm& C, const u8* d_
             rrun += rcount[a];
         }
         if (rrun != n_local) throw std::string("sharded construction: exchange plan does not cover the block");
-        u64* part_suf = e->vals[y].as<u64>();
-        u64* part_bkt = e->keys[x].as<u64>();  // the sorted keys are dead after resolve
-        OwnerSrc src{SA, bucket, blk.rem * (blk.base + 1), blk.base + 1, blk.base ? blk.base : 1, (u32)blk.rem, 1.0 / (double)(blk.base + 1),
-                     1.0 / (double)(blk.base ? blk.base : 1)};
-        launch_pass<OwnerSrc, u64, false>(ws, src, part_suf, part_bkt, nullptr, cnt, st);
-        e->launches += LAUNCHES_PER_PASS;
-        // receive buffers: the bucket array (dead after the partition) and a scratch of n_local entries
+        // receive buffers of n_local pairs
         e->rk[0].reserve((n_local + 16) * sizeof(u64), tot);
         e->rk[1].reserve((n_local + 16) * sizeof(u64), tot);
         u64* recv_suf = e->rk[0].as<u64>();
         u64* recv_bkt = e->rk[1].as<u64>();
-        all_to_all_v(e, C, part_suf, scount, sdispl, recv_suf, rcount, rdispl, sizeof(u64));
-        all_to_all_v(e, C, part_bkt, scount, sdispl, recv_bkt, rcount, rdispl, sizeof(u64));
+        u64* peer_suf[16];
+        u64* peer_bkt[16];
+        const bool fused = e->peer_map != nullptr && map_peer_buffers(e, C, recv_suf, recv_bkt, *reinterpret_cast<PeerMap*>(e->peer_map), peer_suf, peer_bkt);
+        S.reserved = fused ? 1u : 0u;  // reported as "exchange = peer stores" in the stats
+        const u64 cut = blk.rem * (blk.base + 1), base1 = blk.base + 1, base0 = blk.base ? blk.base : 1;
+        if (fused) {
+            // ONE kernel partitions by owner and stores each bin into its owner's receive buffer over NVLink (peer
+            // stores): the exchange overlaps the partition tile by tile.  Rank b receives my bin at its displacement
+            // for source `me`; barriers keep the receive buffers of a previous call / the next step apart.
+            OwnerPeerSrc src{SA, bucket, {}, {}, cut, base1, base0, (u32)blk.rem, 1.0 / (double)base1, 1.0 / (double)base0};
+            for (int b = 0; b < p; ++b) {
+                u64 rd = 0;  // displacement of source `me` in receiver b's buffer
+                for (int a = 0; a < me; ++a) rd += blk_in_range[(size_t)b * p + a];
+                src.kpeer[b] = peer_suf[b] + rd - sdispl[b];
+                src.vpeer[b] = peer_bkt[b] + rd - sdispl[b];
+            }
+            for (int b = p; b < 16; ++b) src.kpeer[b] = src.vpeer[b] = nullptr;
+            rank_barrier(e, C);
+            launch_pass<OwnerPeerSrc, u64, false>(ws, src, nullptr, nullptr, nullptr, cnt, st);
+            e->launches += LAUNCHES_PER_PASS;
+            rank_barrier(e, C);
+        } else {
+            u64* part_suf = e->vals[y].as<u64>();
+            u64* part_bkt = e->keys[x].as<u64>();  // the sorted keys are dead after resolve
+            OwnerSrc src{SA, bucket, {}, {}, cut, base1, base0, (u32)blk.rem, 1.0 / (double)base1, 1.0 / (double)base0};
+            launch_pass<OwnerSrc, u64, false>(ws, src, part_suf, part_bkt, nullptr, cnt, st);
+            e->launches += LAUNCHES_PER_PASS;
+            all_to_all_v(e, C, part_suf, scount, sdispl, recv_suf, rcount, rdispl, sizeof(u64));
+            all_to_all_v(e, C, part_bkt, scount, sdispl, recv_bkt, rcount, rdispl, sizeof(u64));
+        }
         if (n_local >= (1ull << 22)) {
             // as on one GPU: partition the received pairs by ISA window (top 8 bits of the index inside my block), then
             // scatter window by window so the writes stay in L2 until their sectors are complete
