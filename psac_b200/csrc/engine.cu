@@ -336,30 +336,34 @@ void construct_core(psacb200_engine* e, u64 n, int index_bytes, unsigned flags, 
         const u64 T = (n < (u64)C - 1) ? n : (u64)C - 1;
         static_assert(sizeof(TailList) <= 1024, "TailList must fit its slot in the small buffer");
         TailList* tails = reinterpret_cast<TailList*>(e->tail_list());
-        tail_positions_kernel<KeyC><<<1, 64, 0, st>>>(kbuf[x], R.aux, n, R.drop, e->packed.as<u64>(), n, T, lbits, (int)C * lbits, tails);
+        tail_positions_kernel<KeyC><<<1, 64, 0, st>>>(kbuf[x], R.aux, n, R.drop, e->packed.as<u64>(), n, T, lbits, (int)C * lbits, 0, 0u, 1u, tails);
         HeadsArgs H{};
         H.keys = kbuf[x];
         H.aux = R.aux;
-        H.vals = reinterpret_cast<const u32*>(SA);
+        H.vals = SA;
         H.m = n;
+        H.n = n;
         H.drop = R.drop;
         H.lbits = lbits;
         H.C = (int)C;
         H.tails = tails;
-        H.bucket_out = reinterpret_cast<u32*>(bucket);
-        H.isa = partitioned ? nullptr : reinterpret_cast<u32*>(ISA);
-        H.lcp = reinterpret_cast<u32*>(LCP);
-        H.pos_out = reinterpret_cast<u32*>(R.pos_out);
+        H.bucket_out = bucket;
+        H.isa = partitioned ? nullptr : ISA;
+        H.lcp = LCP;
+        H.pos_out = R.pos_out;
         H.head_out = R.head_out;
+        H.suf_out = nullptr;
         H.cap = R.cap;
         H.counts = R.counts;
+        H.pos_base = 0;
+        H.halo = nullptr;
         const u64 ntiles = div_up(n, (size_t)HD_TILE);
         H.agg_max = e->lookback.as<u64>();
         H.agg_sum = H.agg_max + ntiles;
         PSAC_CUDA(cudaMemsetAsync(R.counts, 0, 2 * sizeof(u64), st));
-        heads_kernel<KeyC, 0><<<(unsigned)ntiles, HD_THREADS, 0, st>>>(H);
+        heads_kernel<KeyC, u32, 0><<<(unsigned)ntiles, HD_THREADS, 0, st>>>(H);
         tile_scan_kernel<<<1, 1024, 0, st>>>(H.agg_max, H.agg_sum, ntiles, R.counts);
-        heads_kernel<KeyC, 1><<<(unsigned)ntiles, HD_THREADS, 0, st>>>(H);
+        heads_kernel<KeyC, u32, 1><<<(unsigned)ntiles, HD_THREADS, 0, st>>>(H);
         e->launches += 4;
         PSAC_CUDA(cudaGetLastError());
     } else {

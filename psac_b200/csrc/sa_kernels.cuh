@@ -431,9 +431,12 @@ struct TailList {
     u64 pos[64];  // position in the sorted order
 };
 
+// (sharded construction: only the tails whose key-prefix bin lies in [bin_lo, bin_hi) are in this shard's sorted range;
+//  the others get position ~0 and touch nothing)
 template <typename KeyC>
 __global__ void __launch_bounds__(64) tail_positions_kernel(const KeyC* __restrict__ keys, const u8* __restrict__ aux, u64 m, int drop,
-                                                            const u64* __restrict__ stream, u64 n, u64 T, int lbits, int kbits, TailList* __restrict__ out) {
+                                                            const u64* __restrict__ stream, u64 n, u64 T, int lbits, int kbits, int pbits, u32 bin_lo,
+                                                            u32 bin_hi, TailList* __restrict__ out) {
     __shared__ u64 s_key[64];
     const int j = threadIdx.x;
     u64 full = 0;
@@ -453,7 +456,9 @@ __global__ void __launch_bounds__(64) tail_positions_kernel(const KeyC* __restri
         }
         u32 before = 0;
         for (int i = 0; i < j; ++i) before += (s_key[i] == full) ? 1u : 0u;
-        out->pos[j] = lo + before;
+        const u32 bin = pbits > 0 ? (u32)(full >> (kbits - pbits)) : 0u;
+        const bool mine = pbits == 0 || (bin >= bin_lo && bin < bin_hi);
+        out->pos[j] = mine ? lo + before : ~0ull;
         out->len[j] = (u32)j + 1;
     }
     if (j == 0) out->count = (u32)T;
@@ -462,26 +467,30 @@ __global__ void __launch_bounds__(64) tail_positions_kernel(const KeyC* __restri
 struct HeadsArgs {
     const void* keys;      // sorted carried keys (KeyC)
     const u8* aux;         // key bits dropped by digit pass 1 (drop > 0), else null
-    const u32* vals;       // sorted suffix indices; read only for the direct ISA scatter of small inputs
-    u64 m;                 // number of suffixes
+    const void* vals;      // sorted suffix indices (PosT); read for the direct ISA scatter, the unresolved list and the halo LCP
+    u64 m;                 // number of suffixes sorted here
+    u64 n;                 // text length
     int drop, lbits, C;
     const TailList* tails;
-    u32* bucket_out;
-    u32* isa;              // direct scatter (small inputs) or null
-    u32* lcp;              // or null
-    u32* pos_out;          // unresolved list (first `cap` entries)
-    u8* head_out;
+    void* bucket_out;      // PosT
+    void* isa;             // direct scatter (small inputs) or null
+    void* lcp;             // or null
+    void* pos_out;         // unresolved list (first `cap` entries): SA positions, ...
+    u8* head_out;          // ... head flags ...
+    void* suf_out;         // ... and suffixes (sharded construction), or null
     u64 cap;
     u64* counts;           // [1] unresolved buckets (atomic); [0] is written by tile_scan_kernel
     u64* agg_max;          // per tile: last head position / exclusive prefix after the scan
     u64* agg_sum;          // per tile: unresolved elements / exclusive prefix
+    u64 pos_base;          // sharded construction: SA position of local element 0 (bucket ids and positions are global)
+    const u64* halo;       // sharded construction: {key, suffix} of the last element of the previous shard, or null
 };
 
 constexpr int HD_THREADS = 256;
 constexpr int HD_ITEMS = 16;
 constexpr int HD_TILE = HD_THREADS * HD_ITEMS;
 
-template <typename KeyC, int PHASE>
+template <typename KeyC, typename PosT, int PHASE>
 __global__ void __launch_bounds__(HD_THREADS) heads_kernel(HeadsArgs A) {
     __shared__ u32 s_wmax[HD_THREADS / 32];
     __shared__ u32 s_wsum[HD_THREADS / 32];
@@ -549,6 +558,8 @@ __global__ void __launch_bounds__(HD_THREADS) heads_kernel(HeadsArgs A) {
             if (q0 >= 1 && q0 - 1 < m) {
                 l = (u64)keys[q0 - 1];
                 if (A.drop > 0) l = (l << A.drop) | (u64)A.aux[q0 - 1];
+            } else if (q0 == 0 && A.halo != nullptr) {
+                l = A.halo[0];  // last key of the previous shard (only the LCP of position 0 uses it: position 0 is a head)
             }
         }
         if (lane == 31) {
@@ -633,6 +644,8 @@ __global__ void __launch_bounds__(HD_THREADS) heads_kernel(HeadsArgs A) {
     u64 o = A.agg_sum[tile] + wpre_sum + (isum - my_cnt);
     if (q0 >= m) return;
     // ---- bucket ids: position of the latest head
+    PosT* bucket_out = reinterpret_cast<PosT*>(A.bucket_out);
+    const PosT* vals = reinterpret_cast<const PosT*>(A.vals);
     u32 bucket[HD_ITEMS];
 #pragma unroll
     for (int i = 0; i < HD_ITEMS; ++i) {
@@ -640,18 +653,27 @@ __global__ void __launch_bounds__(HD_THREADS) heads_kernel(HeadsArgs A) {
         bucket[i] = run;
     }
     if (full_run) {
-        uint4* ob = reinterpret_cast<uint4*>(A.bucket_out + q0);
+        if (sizeof(PosT) == 4) {
+            uint4* ob = reinterpret_cast<uint4*>(bucket_out + q0);
 #pragma unroll
-        for (int c = 0; c < HD_ITEMS / 4; ++c) __stcs(ob + c, make_uint4(bucket[4 * c], bucket[4 * c + 1], bucket[4 * c + 2], bucket[4 * c + 3]));
+            for (int c = 0; c < HD_ITEMS / 4; ++c)
+                __stcs(ob + c, make_uint4(bucket[4 * c] + (u32)A.pos_base, bucket[4 * c + 1] + (u32)A.pos_base, bucket[4 * c + 2] + (u32)A.pos_base,
+                                          bucket[4 * c + 3] + (u32)A.pos_base));
+        } else {
+            ulonglong2* ob = reinterpret_cast<ulonglong2*>(bucket_out + q0);
+#pragma unroll
+            for (int c = 0; c < HD_ITEMS / 2; ++c) __stcs(ob + c, make_ulonglong2(A.pos_base + bucket[2 * c], A.pos_base + bucket[2 * c + 1]));
+        }
     } else {
 #pragma unroll
         for (int i = 0; i < HD_ITEMS; ++i)
-            if (q0 + i < m) A.bucket_out[q0 + i] = bucket[i];
+            if (q0 + i < m) bucket_out[q0 + i] = (PosT)(A.pos_base + bucket[i]);
     }
     if (A.isa != nullptr) {
+        PosT* isa = reinterpret_cast<PosT*>(A.isa);
 #pragma unroll
         for (int i = 0; i < HD_ITEMS; ++i)
-            if (q0 + i < m) A.isa[A.vals[q0 + i]] = bucket[i];
+            if (q0 + i < m) isa[vals[q0 + i]] = (PosT)(A.pos_base + bucket[i]);
     }
     if (A.lcp != nullptr) {
         const int nbits = A.C * A.lbits;
@@ -669,17 +691,31 @@ __global__ void __launch_bounds__(HD_THREADS) heads_kernel(HeadsArgs A) {
                     if (q0 + i == p || q0 + i == p + 1) l[i] = l[i] < s_tails.len[t] ? l[i] : s_tails.len[t];
             }
         }
-        if (q0 == 0) l[0] = 0;
+        if (q0 == 0) {
+            if (A.halo != nullptr) {
+                // boundary with the previous shard: cap by the lengths of both suffixes (either may run past the end)
+                const u64 la = A.n - A.halo[1], lb = A.n - (u64)vals[0];
+                l[0] = l[0] < la ? l[0] : (u32)la;
+                l[0] = l[0] < lb ? l[0] : (u32)lb;
+            } else {
+                l[0] = 0;
+            }
+        }
         // every position becomes a head in exactly one round and gets its LCP then: entries of non-heads written here
         // are overwritten by the round that splits them, so the whole run can leave as 128-bit stores
-        if (full_run) {
-            uint4* ol = reinterpret_cast<uint4*>(A.lcp + q0);
+        PosT* lcp = reinterpret_cast<PosT*>(A.lcp);
+        if (full_run && sizeof(PosT) == 4) {
+            uint4* ol = reinterpret_cast<uint4*>(lcp + q0);
 #pragma unroll
             for (int c = 0; c < HD_ITEMS / 4; ++c) __stcs(ol + c, make_uint4(l[4 * c], l[4 * c + 1], l[4 * c + 2], l[4 * c + 3]));
+        } else if (full_run) {
+            ulonglong2* ol = reinterpret_cast<ulonglong2*>(lcp + q0);
+#pragma unroll
+            for (int c = 0; c < HD_ITEMS / 2; ++c) __stcs(ol + c, make_ulonglong2((u64)l[2 * c], (u64)l[2 * c + 1]));
         } else {
 #pragma unroll
             for (int i = 0; i < HD_ITEMS; ++i)
-                if (q0 + i < m) A.lcp[q0 + i] = l[i];
+                if (q0 + i < m) lcp[q0 + i] = (PosT)l[i];
         }
     }
     u32 u = unres;
@@ -687,8 +723,9 @@ __global__ void __launch_bounds__(HD_THREADS) heads_kernel(HeadsArgs A) {
         const int i = __ffs(u) - 1;
         u &= u - 1;
         if (o < A.cap) {
-            A.pos_out[o] = (u32)(q0 + i);
+            reinterpret_cast<PosT*>(A.pos_out)[o] = (PosT)(A.pos_base + q0 + i);
             A.head_out[o] = (head >> i) & 1u;
+            if (A.suf_out != nullptr) reinterpret_cast<PosT*>(A.suf_out)[o] = vals[q0 + i];
         }
         ++o;
     }

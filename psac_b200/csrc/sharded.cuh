@@ -555,7 +555,43 @@ bool construct_sharded_core(psacb200_engine* e, const ShardComm& C, const u8* d_
     R.sa_hi = off + cnt;
     R.isa_lo = text_lo;
     R.isa_hi = text_hi;
-    launch_resolve<u64, u64>(e, true, R);
+    if (!alpha.zero_code_used) {
+        // lean round-0 resolve (sa_kernels.cuh heads_kernel) with global positions
+        TailList* tails = reinterpret_cast<TailList*>(e->tail_list());
+        tail_positions_kernel<u64><<<1, 64, 0, st>>>(e->keys[x].as<u64>(), nullptr, cnt, 0, stream, n, T, lbits, kbits, pbits, (u32)first[me],
+                                                     (u32)first[me + 1], tails);
+        HeadsArgs H{};
+        H.keys = e->keys[x].p;
+        H.aux = nullptr;
+        H.vals = SA;
+        H.m = cnt;
+        H.n = n;
+        H.drop = 0;
+        H.lbits = lbits;
+        H.C = (int)Cc;
+        H.tails = tails;
+        H.bucket_out = bucket;
+        H.isa = nullptr;
+        H.lcp = LCP;
+        H.pos_out = R.pos_out;
+        H.head_out = R.head_out;
+        H.suf_out = R.suf_out;
+        H.cap = R.cap;
+        H.counts = R.counts;
+        H.pos_base = off;
+        H.halo = R.halo;
+        const u64 ntiles = div_up(cnt, (size_t)HD_TILE);
+        H.agg_max = e->lookback.as<u64>();
+        H.agg_sum = H.agg_max + ntiles;
+        PSAC_CUDA(cudaMemsetAsync(R.counts, 0, 2 * sizeof(u64), st));
+        heads_kernel<u64, u64, 0><<<(unsigned)ntiles, HD_THREADS, 0, st>>>(H);
+        tile_scan_kernel<<<1, 1024, 0, st>>>(H.agg_max, H.agg_sum, ntiles, R.counts);
+        heads_kernel<u64, u64, 1><<<(unsigned)ntiles, HD_THREADS, 0, st>>>(H);
+        e->launches += 4;
+        PSAC_CUDA(cudaGetLastError());
+    } else {
+        launch_resolve<u64, u64>(e, true, R);
+    }
     e->end(PH_RESOLVE);
     // unresolved counts of all ranks
     u64* d_m = e->shard_meta() + 32;  // [p]
