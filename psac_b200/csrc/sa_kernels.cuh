@@ -506,7 +506,7 @@ __global__ void __launch_bounds__(HD_THREADS) heads_kernel(HeadsArgs A) {
     __syncthreads();
     if (tid < 64 && (u32)tid < A.tails->count) {
         const u64 p = A.tails->pos[tid];
-        if (p + 1 >= t0 && p <= t0 + HD_TILE) s_has_tail = 1;  // benign race: every writer stores 1
+        if (p != ~0ull && p + 1 >= t0 && p <= t0 + HD_TILE) s_has_tail = 1;  // benign race: every writer stores 1
     }
     // ---- my 16 complete keys + one neighbour on each side
     u64 key[HD_ITEMS + 2];
@@ -589,6 +589,7 @@ __global__ void __launch_bounds__(HD_THREADS) heads_kernel(HeadsArgs A) {
         __syncthreads();
         for (u32 t = 0; t < s_tails.count; ++t) {
             const u64 p = s_tails.pos[t];  // a suffix that runs past the end is a bucket of its own: heads at p and p + 1
+            if (p == ~0ull) continue;      // (a tail that sorts into another shard)
             if (p >= q0 && p <= q0 + HD_ITEMS) head |= 1u << (u32)(p - q0);
             if (p + 1 >= q0 && p + 1 <= q0 + HD_ITEMS) head |= 1u << (u32)(p + 1 - q0);
         }
@@ -686,6 +687,7 @@ __global__ void __launch_bounds__(HD_THREADS) heads_kernel(HeadsArgs A) {
         if (s_has_tail) {
             for (u32 t = 0; t < s_tails.count; ++t) {
                 const u64 p = s_tails.pos[t];  // the boundaries on both sides of a short suffix are capped by its length
+                if (p == ~0ull) continue;
 #pragma unroll
                 for (int i = 0; i < HD_ITEMS; ++i)
                     if (q0 + i == p || q0 + i == p + 1) l[i] = l[i] < s_tails.len[t] ? l[i] : s_tails.len[t];

@@ -38,9 +38,14 @@ def case(name, text, index_bytes, lcp, k=0):
     ok = True
     if rank == 0:
         exp = O.construct(text, 64, 0, lcp)
-        ok = bool((got_sa.astype(np.uint64) == exp["sa"]).all() and (got_isa.astype(np.uint64) == exp["isa"]).all())
-        if lcp:
-            ok = ok and bool((got_lcp.astype(np.uint64) == exp["lcp"]).all())
+        bad = []
+        for name_, got_, exp_ in (("SA", got_sa, exp["sa"]), ("ISA", got_isa, exp["isa"])) + ((("LCP", got_lcp, exp["lcp"]),) if lcp else ()):
+            neq = np.nonzero(got_.astype(np.uint64) != exp_)[0]
+            if neq.size:
+                bad.append("%s: %d mismatches, first at %d (got %d, want %d)" % (name_, neq.size, neq[0], int(got_[neq[0]]), int(exp_[neq[0]])))
+        ok = not bad
+        if bad:
+            print("   " + "; ".join(bad), flush=True)
         st = sa.engine.stats()
         print("%-34s n=%9d ib=%d lcp=%d k=%d rounds=%d unresolved=%d %s" % (name, n, index_bytes, int(lcp), k, st["rounds"], st["unresolved_after_first"],
                                                                           "ok" if ok else "MISMATCH"), flush=True)
