@@ -239,6 +239,70 @@ struct OwnerSrcT {
 using OwnerSrc = OwnerSrcT<false>;
 using OwnerPeerSrc = OwnerSrcT<true>;
 
+// Packed form of the same exchange: one 64-bit word per suffix instead of a (suffix, bucket) pair, halving the bytes that
+// cross NVLink and the bytes of the two receiver-side passes:
+//     [ index of the suffix inside its owner's block | rank field | bucket id relative to the sender's first SA position ]
+// The rank field holds the DESTINATION while the word is staged (it is the digit of the partition) and is replaced by the
+// SOURCE rank when the word is written out, so the receiver can turn the relative bucket id back into a global one.
+template <bool PEER_>
+struct OwnerPackSrcT {
+    using Stage = u64;
+    using Out = u64;
+    static constexpr bool FROM_TEXT = false;
+    static constexpr bool PEER = PEER_;
+    const u64* __restrict__ kin;  // suffix (global index)
+    const u64* __restrict__ vin;  // bucket id (global SA position)
+    u64* kpeer[16];
+    u64* vpeer[16];               // unused (keys only)
+    u64 cut, base1, base;         // block distribution: cut = rem * (base + 1)
+    u32 rem;
+    double inv_base1, inv_base;
+    u64 pos_base;                 // first SA position of the sender
+    int rank_shift, idx_shift;    // bit positions of the rank field and of the block-local index
+    u32 rank_mask;
+    u64 me;
+    __device__ __forceinline__ Stage load_key(size_t g) const {
+        const u64 s = ld_stream(kin + g), b = ld_stream(vin + g);
+        u64 owner, local;
+        if (s < cut) {
+            owner = OwnerSrcT<false>::divide(s, base1, inv_base1);
+            local = s - owner * base1;
+        } else {
+            const u64 q = OwnerSrcT<false>::divide(s - cut, base, inv_base);
+            owner = rem + q;
+            local = s - cut - q * base;
+        }
+        return (local << idx_shift) | (owner << rank_shift) | (b - pos_base);
+    }
+    __device__ __forceinline__ u32 digit(Stage k) const { return (u32)(k >> rank_shift) & rank_mask; }
+    __device__ __forceinline__ Out out_key(Stage k) const { return (k & ~((u64)rank_mask << rank_shift)) | (me << rank_shift); }
+    __device__ __forceinline__ NoVal load_val(size_t) const { return NoVal(); }
+    __device__ __forceinline__ u8 load_aux(size_t, Stage) const { return 0; }
+};
+
+// receiver side of the packed exchange: ISA[local index] = first SA position of the source rank + relative bucket id
+struct PackedScatterArgs {
+    const u64* words;
+    u64* isa;
+    u64 n;
+    int rank_shift, idx_shift;
+    u32 rank_mask;
+    u64 rel_mask;
+    u64 off_key[16];
+};
+__global__ void __launch_bounds__(256) isa_scatter_packed_kernel(PackedScatterArgs A) {
+    constexpr int PER = 16;
+    const u64 base = (u64)blockIdx.x * (256 * PER);
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        const u64 q = base + (u64)i * 256 + threadIdx.x;
+        if (q < A.n) {
+            const u64 w = ld_stream(A.words + q);
+            A.isa[w >> A.idx_shift] = A.off_key[(w >> A.rank_shift) & A.rank_mask] + (w & A.rel_mask);
+        }
+    }
+}
+
 // rank look-ups of one replicated round: ans[j] = ISA[suf[j] + h] + 1 if this shard owns that entry, else 0
 __global__ void __launch_bounds__(256) isa_answer_kernel(const u64* __restrict__ suf, u64 m, u64 h, u64 n, const u64* __restrict__ isa, u64 isa_lo,
                                                          u64 isa_hi, u64* __restrict__ ans) {
@@ -641,7 +705,55 @@ bool construct_sharded_core(psacb200_engine* e, const ShardComm& C, const u8* d_
         const bool fused = e->peer_map != nullptr && map_peer_buffers(e, C, recv_suf, recv_bkt, *reinterpret_cast<PeerMap*>(e->peer_map), peer_suf, peer_bkt);
         S.reserved = fused ? 1u : 0u;  // reported as "exchange = peer stores" in the stats
         const u64 cut = blk.rem * (blk.base + 1), base1 = blk.base + 1, base0 = blk.base ? blk.base : 1;
-        if (fused) {
+        // packed exchange: [local index | rank | relative bucket] in one word, when the three fields fit 64 bits
+        u64 max_cnt = 0;
+        for (int r = 0; r < p; ++r) max_cnt = std::max(max_cnt, cnt_key[r]);
+        const int rel_bits = (int)bits_for(max_cnt ? max_cnt - 1 : 0), rank_bits = std::max(1, (int)bits_for((u64)p - 1));
+        const int idx_bits = (int)bits_for(blk.size(0) ? blk.size(0) - 1 : 0);
+        const bool packed = rel_bits + rank_bits + idx_bits <= 64 && !getenv("PSACB200_NO_PACK");  // PSACB200_NO_PACK=1: (suffix, bucket) pairs
+        if (packed) {
+            const int rank_shift = rel_bits, idx_shift = rel_bits + rank_bits;
+            u64* recv_words = recv_suf;
+            if (fused) {
+                OwnerPackSrcT<true> src{SA, bucket, {}, {}, cut, base1, base0, (u32)blk.rem, 1.0 / (double)base1, 1.0 / (double)base0, off, rank_shift,
+                                        idx_shift, (1u << rank_bits) - 1u, (u64)me};
+                for (int b = 0; b < p; ++b) {
+                    u64 rd = 0;
+                    for (int a = 0; a < me; ++a) rd += blk_in_range[(size_t)b * p + a];
+                    src.kpeer[b] = peer_suf[b] + rd - sdispl[b];
+                    src.vpeer[b] = nullptr;
+                }
+                for (int b = p; b < 16; ++b) src.kpeer[b] = src.vpeer[b] = nullptr;
+                rank_barrier(e, C);
+                launch_pass<OwnerPackSrcT<true>, NoVal, false>(ws, src, nullptr, nullptr, nullptr, cnt, st);
+                e->launches += LAUNCHES_PER_PASS;
+                rank_barrier(e, C);
+            } else {
+                u64* part_words = e->vals[y].as<u64>();
+                OwnerPackSrcT<false> src{SA, bucket, {}, {}, cut, base1, base0, (u32)blk.rem, 1.0 / (double)base1, 1.0 / (double)base0, off, rank_shift,
+                                         idx_shift, (1u << rank_bits) - 1u, (u64)me};
+                launch_pass<OwnerPackSrcT<false>, NoVal, false>(ws, src, part_words, nullptr, nullptr, cnt, st);
+                e->launches += LAUNCHES_PER_PASS;
+                all_to_all_v(e, C, part_words, scount, sdispl, recv_words, rcount, rdispl, sizeof(u64));
+            }
+            // window partition by the top 8 bits of the local index, then the windowed scatter
+            const int shift2 = idx_shift + (idx_bits > RADIX_BITS ? idx_bits - RADIX_BITS : 0);
+            ArraySrc<u64, NoVal> wsrc{recv_words, nullptr, nullptr, shift2, (u32)(RADIX - 1), 0ull};
+            u64* win_words = recv_bkt;  // the second receive buffer is free in the packed exchange
+            launch_pass<ArraySrc<u64, NoVal>, NoVal, false>(ws, wsrc, win_words, nullptr, nullptr, n_local, st);
+            PackedScatterArgs PA{};
+            PA.words = win_words;
+            PA.isa = ISA;
+            PA.n = n_local;
+            PA.rank_shift = rank_shift;
+            PA.idx_shift = idx_shift;
+            PA.rank_mask = (1u << rank_bits) - 1u;
+            PA.rel_mask = rel_bits >= 64 ? ~0ull : ((1ull << rel_bits) - 1ull);
+            for (int r = 0; r < 16; ++r) PA.off_key[r] = r < p ? off_key[r] : 0;
+            isa_scatter_packed_kernel<<<(unsigned)div_up(n_local, (size_t)4096), 256, 0, st>>>(PA);
+            e->launches += LAUNCHES_PER_PASS + 1;
+            PSAC_CUDA(cudaGetLastError());
+        } else if (fused) {
             // ONE kernel partitions by owner and stores each bin into its owner's receive buffer over NVLink (peer
             // stores): the exchange overlaps the partition tile by tile.  Rank b receives my bin at its displacement
             // for source `me`; barriers keep the receive buffers of a previous call / the next step apart.
@@ -666,7 +778,9 @@ bool construct_sharded_core(psacb200_engine* e, const ShardComm& C, const u8* d_
             all_to_all_v(e, C, part_suf, scount, sdispl, recv_suf, rcount, rdispl, sizeof(u64));
             all_to_all_v(e, C, part_bkt, scount, sdispl, recv_bkt, rcount, rdispl, sizeof(u64));
         }
-        if (n_local >= (1ull << 22)) {
+        if (packed) {
+            // done above
+        } else if (n_local >= (1ull << 22)) {
             // as on one GPU: partition the received pairs by ISA window (top 8 bits of the index inside my block), then
             // scatter window by window so the writes stay in L2 until their sectors are complete
             const int nb2 = (int)bits_for(n_local - 1);

@@ -64,6 +64,13 @@ def main():
     ok &= case("random DNA, aligned blocks", G.random_dna(p << 20, 11), 8, True)
     ok &= case("random DNA, ragged blocks", G.random_dna((p << 20) + 13, 12), 8, True)
     ok &= case("random DNA, 32-bit index", G.random_dna((p << 19) + 5, 13), 4, False)
+    os.environ["PSACB200_NO_PACK"] = "1"  # the unpacked (suffix, bucket) exchange
+    ok &= case("random DNA, unpacked exchange", G.random_dna((p << 19) + 7, 19), 8, True)
+    os.environ["PSACB200_NO_PEER"] = "1"  # ... and over NCCL all-to-all-v instead of peer stores
+    ok &= case("random DNA, unpacked over NCCL", G.random_dna((p << 19) + 9, 20), 8, True)
+    del os.environ["PSACB200_NO_PACK"]
+    ok &= case("random DNA, packed over NCCL", G.random_dna((p << 19) + 11, 21), 8, True)
+    del os.environ["PSACB200_NO_PEER"]
     ok &= case("random DNA, k=7: replicated rounds", G.random_dna(p << 20, 18), 8, True, k=7)
     ok &= case("random DNA, short first key (k=4)", G.random_dna(p << 18, 14), 8, True, k=4)
     ok &= case("random bytes (sigma=256 quirk)", G.random_bytes_config4(p << 18, 15), 8, False)
