@@ -119,6 +119,15 @@ struct TextSrc {
     u32 mask;
     __device__ __forceinline__ u64 idx(size_t g) const { return (g < T) ? (n - 1 - g) : (g - T); }
     __device__ __forceinline__ Stage load_key(size_t g) const { return stream_extract(stream, idx(g), lbits, kbits); }
+    // key of element g from a shared-memory copy of the stream words [w0, w0 + nw) (elements g >= T only)
+    __device__ __forceinline__ Stage load_key_window(const u64* __restrict__ win, u64 w0, size_t g) const {
+        const u64 bit = (g - T) * (u64)lbits;
+        const u64 w = (bit >> 6) - w0;
+        const unsigned o = (unsigned)(bit & 63);
+        const u64 hi = win[w], lo = win[w + 1];
+        const u64 v = o ? ((hi << o) | (lo >> (64 - o))) : hi;
+        return v >> (64 - kbits);
+    }
     __device__ __forceinline__ u32 digit(Stage k) const { return (u32)k & mask; }
     __device__ __forceinline__ Out out_key(Stage k) const { return (Out)(k >> drop); }
     __device__ __forceinline__ IdxT load_val(size_t g) const { return (IdxT)idx(g); }
@@ -173,10 +182,31 @@ __device__ __forceinline__ void onesweep_tile(unsigned char* smem_raw, const Src
     PSAC_PHASE_BEGIN();
     // ---- load keys, warp-striped: item j of lane l is tile element warp*32*ITEMS + j*32 + l
     Stage key[ITEMS];
+    bool windowed = false;
+    if constexpr (Src::FROM_TEXT) {
+        // the tile's suffixes are consecutive: copy the stream words they touch into shared memory once (the staging
+        // area is free until the scatter) and cut the keys out of that window instead of two global loads per key
+        if (base >= src.T) {
+            windowed = true;
+            u64* win = reinterpret_cast<u64*>(smem_raw);
+            const u64 w0 = ((base - src.T) * (u64)src.lbits) >> 6;
+            const int nw = (int)((((u64)valid * src.lbits + src.kbits + 63) >> 6) + 2);
+            for (int e = tid; e < nw; e += THREADS) win[e] = __ldg(src.stream + w0 + e);
+            __syncthreads();
 #pragma unroll
-    for (int j = 0; j < ITEMS; ++j) {
-        const int o = woff + j * 32;
-        key[j] = (FULL || o < valid) ? src.load_key(base + o) : (Stage)0;
+            for (int j = 0; j < ITEMS; ++j) {
+                const int o = woff + j * 32;
+                key[j] = (FULL || o < valid) ? src.load_key_window(win, w0, base + o) : (Stage)0;
+            }
+            __syncthreads();  // the window is overwritten by the scatter later; all keys are in registers now
+        }
+    }
+    if (!windowed) {
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) {
+            const int o = woff + j * 32;
+            key[j] = (FULL || o < valid) ? src.load_key(base + o) : (Stage)0;
+        }
     }
     // ---- count the warp's digits (shared-memory reductions, no return value)
 #pragma unroll
@@ -312,8 +342,8 @@ __device__ __forceinline__ void onesweep_tile(unsigned char* smem_raw, const Src
     PSAC_PHASE(6);  // write-out
 }
 
-template <class Src, typename ValT, int THREADS, int ITEMS, bool HAS_AUX>
-__global__ void __launch_bounds__(THREADS, (sizeof(typename Src::Out) == 4 && sizeof(ValT) <= 4) ? 3 : 2)
+template <class Src, typename ValT, int THREADS, int ITEMS, bool HAS_AUX, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
     radix_scatter_kernel(const Src src, typename Src::Out* __restrict__ kout, ValT* __restrict__ vout, u8* __restrict__ aout, size_t n,
                          const u64* __restrict__ gbase, const u64* __restrict__ chunk_base, const u32* __restrict__ tile_excl) {
     using Cfg = PassCfg<Src, ValT, THREADS, ITEMS, HAS_AUX>;
@@ -351,6 +381,38 @@ __global__ void __launch_bounds__(THREADS) tile_hist_kernel(const Src src, size_
 #pragma unroll
     for (int j = 0; j < ITEMS; ++j) {
         if (j * THREADS + (int)threadIdx.x < valid) atomicAdd(&sh[src.digit(key[j])], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < RADIX) counts[(size_t)blockIdx.x * RADIX + threadIdx.x] = sh[threadIdx.x];
+}
+
+// the same for digit pass 1 of a construction (keys from the packed text): a thread takes ITEMS consecutive suffixes and
+// cuts their digits (the low `drop` key bits) out of a three-word window instead of loading two words per suffix
+template <class Src, int THREADS, int ITEMS>
+__global__ void __launch_bounds__(THREADS) text_tile_hist_kernel(const Src src, size_t n, u32* __restrict__ counts) {
+    __shared__ u32 sh[RADIX];
+    constexpr int TILE = THREADS * ITEMS;
+    if (threadIdx.x < RADIX) sh[threadIdx.x] = 0;
+    __syncthreads();
+    const size_t base = (size_t)blockIdx.x * TILE;
+    const int valid = (n - base >= (size_t)TILE) ? TILE : (int)(n - base);
+    const int o0 = (int)threadIdx.x * ITEMS;
+    const int dbits = __popc(src.mask);  // bits of the digit
+    if (base >= src.T && o0 + ITEMS <= valid && (ITEMS - 1) * src.lbits <= 64) {  // every digit starts inside the first two words
+        const u64 bit0 = (base + o0 - src.T) * (u64)src.lbits + (u64)(src.kbits - dbits);  // first digit's stream position
+        const u64 w0 = bit0 >> 6;
+        const u64 a = __ldg(src.stream + w0), b = __ldg(src.stream + w0 + 1), c = __ldg(src.stream + w0 + 2);
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) {
+            const unsigned bit = (unsigned)(bit0 & 63) + (unsigned)(j * src.lbits);
+            const u64 hi = bit < 64 ? a : b, lo = bit < 64 ? b : c;
+            const unsigned o = bit & 63;
+            const u64 v = o ? ((hi << o) | (lo >> (64 - o))) : hi;
+            atomicAdd(&sh[(u32)(v >> (64 - dbits))], 1u);
+        }
+    } else {
+        for (int j = 0; j < ITEMS; ++j)
+            if (o0 + j < valid) atomicAdd(&sh[src.digit(src.load_key(base + o0 + j))], 1u);
     }
     __syncthreads();
     if (threadIdx.x < RADIX) counts[(size_t)blockIdx.x * RADIX + threadIdx.x] = sh[threadIdx.x];
@@ -443,13 +505,17 @@ __global__ void __launch_bounds__(384) atoms_order_selftest_kernel(u32 seed, u32
 }
 
 // ------------------------------------------------------------------ host driver
-template <typename OutT, typename ValT>
+// Tile shape of a pass (swept with tools/bench_pass.cu, profiles/r1_bench_pass_sweep.txt): 32-bit pairs run best with
+// 512 threads and 2 CTAs per SM -- 12 keys per thread when the auxiliary byte travels along, 16 without it; wider pairs
+// keep 384 threads.
+template <typename OutT, typename ValT, bool HAS_AUX>
 struct SortTuning {
-    static constexpr int THREADS = 384;
-    // 32-bit pairs: 12 items keep the kernel under 56 registers -> 3 CTAs (36 warps) per SM; wider pairs: 2 CTAs per SM
-    static constexpr int ITEMS = (sizeof(OutT) == 4 && sizeof(ValT) <= 4) ? 12 : ((sizeof(OutT) + sizeof(ValT) >= 16) ? 12 : 16);
+    static constexpr bool NARROW = sizeof(OutT) == 4 && sizeof(ValT) <= 4;
+    static constexpr int THREADS = NARROW ? 512 : 384;
+    static constexpr int ITEMS = NARROW ? (HAS_AUX ? 12 : 16) : ((sizeof(OutT) + sizeof(ValT) >= 16) ? 12 : 16);
+    static constexpr int MINB = 2;
 };
-constexpr int MIN_TILE = 384 * 12;
+constexpr int MIN_TILE = 256 * 8;  // smallest tile any configuration uses (sizes the per-tile workspace)
 
 struct RadixWorkspace {
     u64* gbase = nullptr;      // [RADIX] digit bases of the pass in flight
@@ -458,27 +524,36 @@ struct RadixWorkspace {
     static size_t tiles_bytes_for(size_t n) { return (div_up(n ? n : 1, (size_t)MIN_TILE) + 2) * RADIX * sizeof(u64); }
 };
 
-// One digit pass: histogram, two-level scan, scatter.  4 launches.
-template <class Src, typename ValT, bool HAS_AUX>
-void launch_pass(const RadixWorkspace& ws, const Src& src, typename Src::Out* kout, ValT* vout, u8* aout, size_t n, cudaStream_t stream) {
-    using T = SortTuning<typename Src::Out, ValT>;
-    using Cfg = PassCfg<Src, ValT, T::THREADS, T::ITEMS, HAS_AUX>;
+// One digit pass: histogram, two-level scan, scatter.  4 launches.  (THREADS, ITEMS, MINB = CTAs per SM the scatter kernel
+// is compiled for; tools/bench_pass.cu sweeps them, SortTuning holds the choice.)
+template <class Src, typename ValT, bool HAS_AUX, int THREADS, int ITEMS, int MINB>
+void launch_pass_cfg(const RadixWorkspace& ws, const Src& src, typename Src::Out* kout, ValT* vout, u8* aout, size_t n, cudaStream_t stream) {
+    using Cfg = PassCfg<Src, ValT, THREADS, ITEMS, HAS_AUX>;
     const size_t tiles = div_up(n, (size_t)Cfg::TILE);
     const size_t chunks = div_up(tiles, (size_t)SCAN_CHUNK);
     const size_t counts_bytes = align_up(tiles * RADIX * sizeof(u32), 256);
     if (counts_bytes + chunks * RADIX * sizeof(u64) > ws.tiles_bytes) throw std::string("radix pass: tile workspace too small");
     u32* counts = reinterpret_cast<u32*>(ws.tiles);
     u64* chunk_tot = reinterpret_cast<u64*>(reinterpret_cast<char*>(ws.tiles) + counts_bytes);
-    auto kern = radix_scatter_kernel<Src, ValT, T::THREADS, T::ITEMS, HAS_AUX>;
+    auto kern = radix_scatter_kernel<Src, ValT, THREADS, ITEMS, HAS_AUX, MINB>;
     static bool attr_set = false;
     if (!attr_set) {
         PSAC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
         attr_set = true;
     }
-    tile_hist_kernel<Src, T::THREADS, T::ITEMS><<<(unsigned)tiles, T::THREADS, 0, stream>>>(src, n, counts);
+    if constexpr (Src::FROM_TEXT)
+        text_tile_hist_kernel<Src, THREADS, ITEMS><<<(unsigned)tiles, THREADS, 0, stream>>>(src, n, counts);
+    else
+        tile_hist_kernel<Src, THREADS, ITEMS><<<(unsigned)tiles, THREADS, 0, stream>>>(src, n, counts);
     tile_scan_chunks_kernel<<<(unsigned)chunks, RADIX, 0, stream>>>(counts, tiles, chunk_tot);
     tile_scan_top_kernel<<<1, RADIX, 0, stream>>>(chunk_tot, chunks, ws.gbase);
-    kern<<<(unsigned)tiles, T::THREADS, Cfg::SMEM, stream>>>(src, kout, vout, aout, n, ws.gbase, chunk_tot, counts);
+    kern<<<(unsigned)tiles, THREADS, Cfg::SMEM, stream>>>(src, kout, vout, aout, n, ws.gbase, chunk_tot, counts);
+}
+
+template <class Src, typename ValT, bool HAS_AUX>
+void launch_pass(const RadixWorkspace& ws, const Src& src, typename Src::Out* kout, ValT* vout, u8* aout, size_t n, cudaStream_t stream) {
+    using T = SortTuning<typename Src::Out, ValT, HAS_AUX>;
+    launch_pass_cfg<Src, ValT, HAS_AUX, T::THREADS, T::ITEMS, T::MINB>(ws, src, kout, vout, aout, n, stream);
 }
 constexpr int LAUNCHES_PER_PASS = 4;
 

@@ -15,7 +15,7 @@ __global__ void fill(u32* k, u32* v, u8* a, size_t n) {
     }
 }
 
-template <bool AUX>
+template <bool AUX, int THREADS, int ITEMS, int MINB>
 void run(size_t n, int reps) {
     u32 *k[2], *v[2]; u8* a[2];
     for (int b = 0; b < 2; ++b) { cudaMalloc(&k[b], n * 4); cudaMalloc(&v[b], n * 4); cudaMalloc(&a[b], n); }
@@ -30,14 +30,13 @@ void run(size_t n, int reps) {
         cudaMemcpyToSymbol(g_phase_cycles, zero, sizeof(zero));
         ArraySrc<u32, u32> src{k[0], v[0], AUX ? a[0] : nullptr, 8, 255u, 0u};
         cudaEventRecord(e0);
-        launch_pass<ArraySrc<u32, u32>, u32, AUX>(ws, src, k[1], v[1], AUX ? a[1] : nullptr, n, 0);
+        launch_pass_cfg<ArraySrc<u32, u32>, u32, AUX, THREADS, ITEMS, MINB>(ws, src, k[1], v[1], AUX ? a[1] : nullptr, n, 0);
         cudaEventRecord(e1); cudaEventSynchronize(e1);
         float ms; cudaEventElapsedTime(&ms, e0, e1); if (ms < best) best = ms;
     }
     unsigned long long ph[16]; cudaMemcpyFromSymbol(ph, g_phase_cycles, sizeof(ph));
-    using T = SortTuning<u32, u32>;
-    const double tiles = (double)((n + T::THREADS * T::ITEMS - 1) / (T::THREADS * T::ITEMS));
-    printf("n=%zu aux=%d: %.3f ms  (%.1f GB/s algorithmic)  err=%s\n", n, (int)AUX, best, n * (AUX ? 18.0 : 16.0) / best * 1e-6, cudaGetErrorString(cudaGetLastError()));
+    const double tiles = (double)((n + THREADS * ITEMS - 1) / (THREADS * ITEMS));
+    printf("n=%zu aux=%d threads=%d items=%d minb=%d: %.3f ms  (%.1f GB/s algorithmic)  err=%s\n", n, (int)AUX, THREADS, ITEMS, MINB, best, n * (AUX ? 18.0 : 16.0) / best * 1e-6, cudaGetErrorString(cudaGetLastError()));
     const char* names[7] = {"key loads + count", "barrier 1", "digit scan", "rank + scatter", "offsets", "barrier 3", "write-out"};
     double tot = 0; for (int i = 0; i < 7; ++i) tot += ph[i];
     for (int i = 0; i < 7; ++i) printf("   %-18s %9.0f cycles/tile  %5.1f%%\n", names[i], ph[i] / tiles, 100.0 * ph[i] / tot);
@@ -47,8 +46,18 @@ void run(size_t n, int reps) {
 }
 
 int main() {
-    run<false>((size_t)1 << 28, 3);
-    run<true>((size_t)1 << 28, 3);
-    run<false>((size_t)1 << 30, 3);
+    const size_t n = (size_t)1 << 28;
+    run<true, 384, 12, 3>(n, 3);
+    run<true, 384, 16, 2>(n, 3);
+    run<true, 512, 12, 2>(n, 3);
+    run<true, 512, 16, 2>(n, 3);
+    run<true, 384, 20, 2>(n, 3);
+    run<true, 640, 12, 1>(n, 3);
+    run<true, 768, 12, 1>(n, 3);
+    run<true, 1024, 12, 1>(n, 3);
+    run<false, 384, 12, 3>(n, 3);
+    run<false, 384, 16, 2>(n, 3);
+    run<false, 512, 12, 2>(n, 3);
+    run<false, 512, 16, 2>(n, 3);
     return 0;
 }
