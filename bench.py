@@ -109,9 +109,16 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     n = 1 << args.log2n
-    index_bytes = 4
-    workload = "random DNA (|Sigma|=4) 2^%d chars per GPU, SA%s, %d-bit index (BASELINE configs[1] shape)" % (
-        args.log2n, "+LCP" if args.lcp else "-only (+ISA)", index_bytes * 8)
+    ngpu = max(world, args.gpus)
+    if ngpu > 1:
+        # ONE text of ngpu * 2^log2n characters, block-distributed over the ranks (BASELINE configs[2] shape: 64-bit index)
+        index_bytes = 8
+        workload = "random DNA (|Sigma|=4), ONE text of %d x 2^%d chars sharded by block over %d GPUs, SA%s (+ISA), 64-bit index (BASELINE configs[2] shape)" % (
+            ngpu, args.log2n, ngpu, "+LCP" if args.lcp else "-only")
+    else:
+        index_bytes = 4
+        workload = "random DNA (|Sigma|=4) 2^%d chars per GPU, SA%s, %d-bit index (BASELINE configs[1] shape)" % (
+            args.log2n, "+LCP" if args.lcp else "-only (+ISA)", index_bytes * 8)
     from psac_b200 import textgen as G
 
     # ------------------------------------------------------------------ reference arm (CPU, rank 0 only)
@@ -123,8 +130,8 @@ def main():
         steps, warmup = max(1, args.steps), max(0, min(args.warmup, 1))
         kind, sps, ms = reference_run(text, index_bytes, args.lcp, steps, warmup)
         line = {"impl": "reference", "metric": "suffixes/sec SA build", "value": sps, "unit": "suffixes/s", "n_gpus": args.gpus, "steps": steps,
-                "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
-                "data": "synthetic", "config": {"workload": workload, "cpu_sample": "first 2^%d characters of the same text per step" % int(np.log2(m))},
+                "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u%d" % (index_bytes * 8),
+                "data": "synthetic", "config": {"workload": workload, "cpu_sample": "first 2^%d characters of the same text per step" % int(np.log2(m)), "n_per_gpu": n, "n_total": n * ngpu},
                 "cpu_baseline": {"value": sps, "unit": "suffixes/s", "cores": 1, "kind": kind,
                                  "sample": "first 2^%d characters of the text; unmodified psac at np=1 under the MPI shim (single core: the box has no MPI)" % int(np.log2(m))},
                 "e2e": {"value": sps, "unit": "suffixes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -152,12 +159,8 @@ def main():
     flags = (api.LCP if args.lcp else 0) | api.FAST_RESOLVAL
     n_total = n * world
     if sharded:
-        # ONE text of world * 2^log2n characters, block-distributed over the ranks (BASELINE configs[2] shape: 64-bit index);
-        # SA / ISA / LCP come back block-distributed.  Rank r generates its own block (seed differs per rank).
+        # SA / ISA / LCP come back block-distributed.  Rank r generates its own block of the text (seed differs per rank).
         from psac_b200.sharded import ShardedSuffixArray
-        index_bytes = 8
-        workload = "random DNA (|Sigma|=4), ONE text of %d x 2^%d chars sharded by block over %d GPUs, SA%s (+ISA), 64-bit index (BASELINE configs[2] shape)" % (
-            world, args.log2n, world, "+LCP" if args.lcp else "-only")
         ssa = ShardedSuffixArray(index_bytes, args.lcp)
         eng = ssa.engine
     else:
@@ -280,6 +283,14 @@ def main():
     pass_bytes = float(n) * 2 * (key_bytes + val_bytes + aux_bytes)
     pass_avg_ms = float(np.mean(pass_ms))
     achieved = pass_bytes / (pass_avg_ms * 1e-3) / 1e9 if pass_avg_ms > 0 else 0.0
+    traffic = None  # DRAM bytes of one pass from the committed ncu capture (same kernels, n = 2^30), scaled to this n
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+            tj = json.load(f)
+        if not sharded and key_bytes == 4:
+            traffic = float(tj["dram_bytes_per_pass"]) * n / float(tj["n"])
+    except Exception:
+        traffic = None
     line = {
         "metric": "suffixes/sec SA build", "value": n_total / (ms_dev * 1e-3), "unit": "suffixes/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -287,12 +298,14 @@ def main():
         "config": {"workload": workload, "n_per_gpu": n, "n_total": n_total,
                    "parallelism": ("block-sharded text/SA/ISA over %d GPUs, NCCL all-to-all-v" % world) if sharded else "single GPU", "seed": SEED,
                    "l2": "inputs_exceed_l2 (every pass streams >= 8 GiB)", "key_chars": stats["key_chars"], "sort_passes": stats["sort_passes"],
-                   "rounds": stats["rounds"], "unresolved_after_first": stats["unresolved_after_first"], "verified": verified},
+                   "rounds": stats["rounds"], "unresolved_after_first": stats["unresolved_after_first"], "verified": verified,
+                   "exchange": ("peer stores over NVLink fused into the owner partition kernel" if stats.get("peer_exchange") else "NCCL all-to-all-v") if sharded else None},
         "gpu_launches": launches,
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "onesweep_pass_kernel<ArraySrc<u%d,u%d>> (one 8-bit digit pass of the first sort over the carried keys; rank 0)" % (
-                         key_bytes * 8, val_bytes * 8),
-                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+        "roofline": {"bound": "hbm", "kernel": "one 8-bit digit pass over the carried keys = tile_hist_kernel + 2 scan kernels + radix_scatter_kernel<ArraySrc<u%d,u%d>> "
+                               "(4 launches timed as one unit, passes 2..P of the first sort; rank 0)" % (key_bytes * 8, val_bytes * 8),
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                     "traffic_source": "profiles/roofline_traffic.json (ncu dram bytes; the histogram pre-pass re-reads the keys: +4 B/suffix)" if traffic else None, "peak_source": peak_src,
                      "bytes_per_launch": pass_bytes, "ms_per_launch": pass_avg_ms},
         "phases_ms": {k: round(v, 3) for k, v in sorted(phase.items())},
     }
