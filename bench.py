@@ -278,8 +278,8 @@ def main():
     if sharded:
         key_bytes, val_bytes, aux_bytes = 8, 8, 0
     else:
-        key_bytes = 4 if stats["key_chars"] * stats["pack_bits"] - 8 <= 32 else 8
-        val_bytes, aux_bytes = stats["internal_index_bytes"], (1 if key_bytes == 4 else 0)
+        key_bytes = 4 if stats["key_chars"] * stats["pack_bits"] - 8 <= 32 else 8  # 32-bit carried keys: the top digit is implied by the segment
+        val_bytes, aux_bytes = stats["internal_index_bytes"], 0
     pass_bytes = float(n) * 2 * (key_bytes + val_bytes + aux_bytes)
     pass_avg_ms = float(np.mean(pass_ms))
     achieved = pass_bytes / (pass_avg_ms * 1e-3) / 1e9 if pass_avg_ms > 0 else 0.0
@@ -302,8 +302,8 @@ def main():
                    "exchange": ("peer stores over NVLink fused into the owner partition kernel" if stats.get("peer_exchange") else "NCCL all-to-all-v") if sharded else None},
         "gpu_launches": launches,
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "one 8-bit digit pass over the carried keys = tile_hist_kernel + 2 scan kernels + radix_scatter_kernel<ArraySrc<u%d,u%d>> "
-                               "(4 launches timed as one unit, passes 2..P of the first sort; rank 0)" % (key_bytes * 8, val_bytes * 8),
+        "roofline": {"bound": "hbm", "kernel": "one 8-bit digit pass over the carried keys = tile histogram + scan kernels + radix_scatter kernel <ArraySrc<u%d,u%d>> "
+                               "(timed as one unit, passes 2..P of the first sort; rank 0)" % (key_bytes * 8, val_bytes * 8),
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "traffic_source": "profiles/roofline_traffic.json (ncu dram bytes; the histogram pre-pass re-reads the keys: +4 B/suffix)" if traffic else None, "peak_source": peak_src,
                      "bytes_per_launch": pass_bytes, "ms_per_launch": pass_avg_ms},

@@ -78,7 +78,7 @@ struct psacb200_engine {
     cudaStream_t stream = nullptr;
     size_t device_bytes = 0;
     uint64_t launches = 0;
-    DevBuf text, packed, keys[2], vals[2], aux[2], isa, lcp, small, lookback, rk[2], rv[2], rp[2], rh[2], scratch, rep[3], tb[6];
+    DevBuf text, packed, keys[2], vals[2], vals2, segws, isa, lcp, small, lookback, rk[2], rv[2], rp[2], rh[2], scratch, rep[3], tb[6];
     void* nccl_comm = nullptr;  // ncclComm_t of the sharded construction (sharded.cuh), one rank per engine
     void* peer_map = nullptr;   // PeerMap: CUDA-IPC mappings of the peers' exchange buffers (sharded.cuh)
     int shard_rank = 0, shard_world = 1;
@@ -233,7 +233,9 @@ unsigned choose_key_chars(u64 n, int lbits, unsigned k) {
 }
 
 size_t lookback_bytes(u64 n) {
-    return std::max(RadixWorkspace::tiles_bytes_for(n), (size_t)(2 * div_up(n, (size_t)RES_TILE) * sizeof(u64)));
+    const size_t rows = suffix_sort_rows(n);  // padded tile rows of the top-digit-first suffix sort
+    const size_t seg = align_up(rows * RADIX * sizeof(u32), 256) + (div_up(rows, (size_t)SCAN_CHUNK) + 1) * RADIX * sizeof(u64);
+    return std::max(std::max(RadixWorkspace::tiles_bytes_for(n), seg), (size_t)(2 * div_up(n, (size_t)RES_TILE) * sizeof(u64)));
 }
 
 // Device buffers of one construction.  When the caller's outputs are device buffers of the engine's internal index
@@ -247,12 +249,20 @@ void reserve_buffers(psacb200_engine* e, u64 n, size_t key_bytes, bool want_lcp,
     size_t* tot = &e->device_bytes;
     e->small.reserve(psacb200_engine::small_bytes(), tot);
     e->packed.reserve((n / 8 + 4) * sizeof(u64) + 64, tot);  // worst case 8 bits per character
-    for (int b = 0; b < 2; ++b) {
-        e->keys[b].reserve(n * key_bytes, tot);
-        if (key_bytes == 4) e->aux[b].reserve(n + 16, tot);
+    if (key_bytes == 4) {
+        // top-digit-first sort: padded ping-pong buffers, segment tables, and a third suffix buffer for the dense result
+        const size_t pe = suffix_sort_padded_elems(n);
+        for (int b = 0; b < 2; ++b) {
+            e->keys[b].reserve(pe * sizeof(u32), tot);
+            e->vals[b].reserve(pe * sizeof(IdxT), tot);
+        }
+        if (!ext_sa) e->vals2.reserve(n * sizeof(IdxT), tot);
+        e->segws.reserve((2 * (RADIX + 1) + RADIX * RADIX) * sizeof(u64) + suffix_sort_rows(n) * sizeof(u32) + 256, tot);
+    } else {
+        for (int b = 0; b < 2; ++b) e->keys[b].reserve(n * key_bytes, tot);
+        e->vals[0].reserve(n * sizeof(IdxT), tot);
+        if (!ext_sa) e->vals[1].reserve(n * sizeof(IdxT), tot);
     }
-    e->vals[0].reserve(n * sizeof(IdxT), tot);
-    if (!ext_sa) e->vals[1].reserve(n * sizeof(IdxT), tot);
     if (!ext_isa) e->isa.reserve(n * sizeof(IdxT), tot);
     if (want_lcp && !ext_lcp) e->lcp.reserve(n * sizeof(IdxT), tot);
     e->lookback.reserve(lookback_bytes(n), tot);
@@ -276,22 +286,39 @@ void construct_core(psacb200_engine* e, u64 n, int index_bytes, unsigned flags, 
 
     // ---- first sort (a4 + a6): digit pass 1 reads the packed text, the others the carried keys
     const RadixPlan plan = make_radix_plan(0, (int)C * lbits);
-    const int fin = (plan.npass - 1) & 1;  // buffer index the last pass writes
     KeyC* kbuf[2] = {e->keys[0].as<KeyC>(), e->keys[1].as<KeyC>()};
-    IdxT* vbuf[2];
-    vbuf[fin] = ext_sa ? reinterpret_cast<IdxT*>(sa_out) : e->vals[1].as<IdxT>();
-    vbuf[1 - fin] = e->vals[0].as<IdxT>();
-    u8* abuf[2] = {e->aux[0].as<u8>(), e->aux[1].as<u8>()};
+    IdxT* vbuf[2] = {e->vals[0].as<IdxT>(), e->vals[1].as<IdxT>()};
+    IdxT* SA = nullptr;
+    const u64* seg_dense = nullptr;  // 32-bit carried keys: dense start of every top-digit segment
     uint64_t sort_launches = 0;
     RadixPlan plan_used;
+    int x;
     e->begin(PH_SORT);
-    const int x = radix_sort_suffixes<KeyC, IdxT>(e->radix_ws(), e->packed.as<u64>(), n, lbits, (int)C, kbuf, vbuf, abuf, st, e->sm_count, &plan_used,
-                                                  &sort_launches, e->ev_end[PH_PASS1]);
+    if constexpr (sizeof(KeyC) == 4) {
+        static_assert(sizeof(IdxT) == 4, "32-bit carried keys go with 32-bit suffix indices");
+        SegWorkspace sw;
+        sw.seg_dense = e->segws.as<u64>();
+        sw.seg_pad = sw.seg_dense + (RADIX + 1);
+        sw.segbase = sw.seg_pad + (RADIX + 1);
+        sw.tile_info = reinterpret_cast<u32*>(sw.segbase + RADIX * RADIX);
+        SA = ext_sa ? reinterpret_cast<IdxT*>(sa_out) : e->vals2.as<IdxT>();
+        x = radix_sort_suffixes_msd<IdxT>(e->radix_ws(), sw, e->packed.as<u64>(), n, lbits, (int)C, kbuf, vbuf, SA, st, &plan_used, &sort_launches,
+                                          e->ev_end[PH_PASS1]);
+        seg_dense = sw.seg_dense;
+    } else {
+        const int fin = (plan.npass - 1) & 1;  // buffer index the last pass writes
+        if (ext_sa) vbuf[fin] = reinterpret_cast<IdxT*>(sa_out), vbuf[1 - fin] = e->vals[0].as<IdxT>();
+        x = radix_sort_suffixes<IdxT>(e->radix_ws(), e->packed.as<u64>(), n, lbits, (int)C, kbuf, vbuf, st, &plan_used, &sort_launches, e->ev_end[PH_PASS1]);
+        SA = vbuf[x];
+    }
     e->end(PH_SORT);
     e->launches += sort_launches;
     S.sort_passes = plan_used.npass;
     const int y = 1 - x;
-    IdxT* SA = vbuf[x];
+    // scratch suffix buffer of n elements that is free from here on (window partition of the ISA step)
+    IdxT* vscratch = sizeof(KeyC) == 4 ? vbuf[0] : vbuf[y];
+    const int topbits = plan_used.bits[plan_used.npass - 1];
+    const int carried_bits = (int)C * lbits - topbits;  // 32-bit carried keys hold these low bits; the segment is the top digit
     IdxT* ISA = ext_isa ? reinterpret_cast<IdxT*>(isa_out) : e->isa.as<IdxT>();
     IdxT* LCP = want_lcp ? (ext_lcp ? reinterpret_cast<IdxT*>(lcp_out) : e->lcp.as<IdxT>()) : nullptr;
 
@@ -302,7 +329,7 @@ void construct_core(psacb200_engine* e, u64 n, int index_bytes, unsigned flags, 
     ResolveArgs R{};
     R.keys = kbuf[x];
     R.vals = SA;
-    R.aux = sizeof(KeyC) == 4 ? abuf[x] : nullptr;
+    R.aux = nullptr;
     R.pos_in = nullptr;
     R.m = n;
     R.n = n;
@@ -319,7 +346,7 @@ void construct_core(psacb200_engine* e, u64 n, int index_bytes, unsigned flags, 
     R.stream = e->packed.as<u64>();
     R.lbits = lbits;
     R.C = (int)C;
-    R.drop = sizeof(KeyC) == 4 ? plan_used.bits[0] : 0;
+    R.drop = 0;
     R.kbits = 0;
     R.h = 0;
     R.padded_lcp = alpha.zero_code_used ? 1 : 0;
@@ -330,20 +357,20 @@ void construct_core(psacb200_engine* e, u64 n, int index_bytes, unsigned flags, 
     R.isa_lo = 0;
     R.isa_hi = n;
     R.suf_out = nullptr;
-    if (sizeof(IdxT) == 4 && !alpha.zero_code_used) {
+    if (sizeof(KeyC) == 4 || (sizeof(IdxT) == 4 && !alpha.zero_code_used)) {
         // lean path: heads from the keys alone (sa_kernels.cuh heads_kernel); the suffixes that run past the end of the
         // text are located in the sorted order first
         const u64 T = (n < (u64)C - 1) ? n : (u64)C - 1;
         static_assert(sizeof(TailList) <= 1024, "TailList must fit its slot in the small buffer");
         TailList* tails = reinterpret_cast<TailList*>(e->tail_list());
-        tail_positions_kernel<KeyC><<<1, 64, 0, st>>>(kbuf[x], R.aux, n, R.drop, e->packed.as<u64>(), n, T, lbits, (int)C * lbits, 0, 0u, 1u, tails);
+        tail_positions_kernel<KeyC><<<1, 64, 0, st>>>(kbuf[x], n, seg_dense, carried_bits, e->packed.as<u64>(), n, T, lbits, (int)C * lbits, 0, 0u, 1u, tails);
         HeadsArgs H{};
         H.keys = kbuf[x];
-        H.aux = R.aux;
+        H.seg_dense = seg_dense;
+        H.seg_shift = carried_bits;
         H.vals = SA;
         H.m = n;
         H.n = n;
-        H.drop = R.drop;
         H.lbits = lbits;
         H.C = (int)C;
         H.tails = tails;
@@ -404,7 +431,7 @@ void construct_core(psacb200_engine* e, u64 n, int index_bytes, unsigned flags, 
         const int nbits = (int)bits_for(n - 1);
         const int shift = nbits > RADIX_BITS ? nbits - RADIX_BITS : 0;
         RadixWorkspace ws = e->radix_ws();
-        IdxT* part_suffix = vbuf[y];
+        IdxT* part_suffix = vscratch;
         IdxT* part_bucket = reinterpret_cast<IdxT*>(kbuf[x]);  // the sorted keys are dead after resolve
         ArraySrc<IdxT, IdxT> src{SA, bucket, nullptr, shift, (u32)(RADIX - 1), (IdxT)0};
         launch_pass<ArraySrc<IdxT, IdxT>, IdxT, false>(ws, src, part_suffix, part_bucket, nullptr, n, st);
@@ -568,9 +595,10 @@ int construct_entry(psacb200_engine* e, const u8* text, bool text_is_host, size_
         prepare_text(e, d_text, n, lut, alpha);
         const unsigned C = choose_key_chars(n, alpha.lbits, k);
         e->stats.key_chars = C;
-        const int carried_bits = (int)C * alpha.lbits - make_radix_plan(0, (int)C * alpha.lbits).bits[0];  // see carried_drop_bits
+        const RadixPlan plan0 = make_radix_plan(0, (int)C * alpha.lbits);
+        const int carried_bits = (int)C * alpha.lbits - plan0.bits[plan0.npass - 1];  // key bits below the top digit
         if ((u64)n <= (1ull << 32)) {
-            if (carried_bits <= 32)
+            if (carried_bits <= 32 && !alpha.zero_code_used)  // (the |Sigma| = 256 quirk takes the generic 64-bit-key path)
                 construct_core<u32, u32>(e, n, index_bytes, flags, alpha, C, sa_out, isa_out, lcp_out, text_is_host);
             else
                 construct_core<u32, u64>(e, n, index_bytes, flags, alpha, C, sa_out, isa_out, lcp_out, text_is_host);
@@ -724,7 +752,7 @@ void psacb200_destroy(psacb200_engine* e) {
     if (!e) return;
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->stream);
-    DevBuf* all[] = {&e->text, &e->packed, &e->keys[0], &e->keys[1], &e->vals[0], &e->vals[1], &e->aux[0], &e->aux[1], &e->isa, &e->lcp, &e->small, &e->lookback,
+    DevBuf* all[] = {&e->text, &e->packed, &e->keys[0], &e->keys[1], &e->vals[0], &e->vals[1], &e->vals2, &e->segws, &e->isa, &e->lcp, &e->small, &e->lookback,
                      &e->rk[0], &e->rk[1], &e->rv[0], &e->rv[1], &e->rp[0], &e->rp[1], &e->rh[0], &e->rh[1], &e->scratch, &e->rep[0], &e->rep[1], &e->rep[2], &e->tb[0], &e->tb[1], &e->tb[2], &e->tb[3], &e->tb[4], &e->tb[5]};
     for (DevBuf* b : all) b->release(nullptr);
     for (int i = 0; i < PH_COUNT; ++i) {
@@ -767,7 +795,7 @@ int psacb200_reserve(psacb200_engine* e, size_t n, int index_bytes, unsigned fla
         // sized for the automatic key length (k = 0) and host outputs (the superset of the device-output case)
         const bool lcp = (flags & PSACB200_LCP) != 0;
         if ((u64)n <= (1ull << 32))
-            reserve_buffers<u32>(e, n, sizeof(u32), lcp, false, false, false);
+            reserve_buffers<u32>(e, n, sizeof(u32), lcp, false, false, false);  // 32-bit carried keys (key <= 40 bits)
         else
             reserve_buffers<u64>(e, n, sizeof(u64), lcp, false, false, false);
         e->text.reserve(n + 64, &e->device_bytes);

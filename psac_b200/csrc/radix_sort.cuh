@@ -115,8 +115,9 @@ struct TextSrc {
     static constexpr bool PEER = false;
     const u64* __restrict__ stream;
     u64 n, T;
-    int lbits, kbits, drop;
+    int lbits, kbits, drop;  // drop: low key bits removed from the key that is written out
     u32 mask;
+    int dshift;              // the digit of this pass is (key >> dshift) & mask
     __device__ __forceinline__ u64 idx(size_t g) const { return (g < T) ? (n - 1 - g) : (g - T); }
     __device__ __forceinline__ Stage load_key(size_t g) const { return stream_extract(stream, idx(g), lbits, kbits); }
     // key of element g from a shared-memory copy of the stream words [w0, w0 + nw) (elements g >= T only)
@@ -128,10 +129,10 @@ struct TextSrc {
         const u64 v = o ? ((hi << o) | (lo >> (64 - o))) : hi;
         return v >> (64 - kbits);
     }
-    __device__ __forceinline__ u32 digit(Stage k) const { return (u32)k & mask; }
+    __device__ __forceinline__ u32 digit(Stage k) const { return (u32)(k >> dshift) & mask; }
     __device__ __forceinline__ Out out_key(Stage k) const { return (Out)(k >> drop); }
     __device__ __forceinline__ IdxT load_val(size_t g) const { return (IdxT)idx(g); }
-    __device__ __forceinline__ u8 load_aux(size_t, Stage k) const { return (u8)((u32)k & mask); }
+    __device__ __forceinline__ u8 load_aux(size_t, Stage k) const { return (u8)((u32)(k >> dshift) & mask); }
 };
 
 // ------------------------------------------------------------------ one digit pass
@@ -298,7 +299,9 @@ __device__ __forceinline__ void onesweep_tile(unsigned char* smem_raw, const Src
                 const u64 o = goff[d] + (u64)s;
                 st_stream(kout + o, k);
                 st_stream(vout + o, (ValT)(u32)e);
-                if constexpr (Cfg::HAS_AUX) aout[o] = a;
+                if constexpr (Cfg::HAS_AUX) {
+                    if (aout != nullptr) aout[o] = a;  // (pass 1 of the top-digit-first sort stages the digit only)
+                }
             }
         }
     } else {
@@ -399,7 +402,7 @@ __global__ void __launch_bounds__(THREADS) text_tile_hist_kernel(const Src src, 
     const int o0 = (int)threadIdx.x * ITEMS;
     const int dbits = __popc(src.mask);  // bits of the digit
     if (base >= src.T && o0 + ITEMS <= valid && (ITEMS - 1) * src.lbits <= 64) {  // every digit starts inside the first two words
-        const u64 bit0 = (base + o0 - src.T) * (u64)src.lbits + (u64)(src.kbits - dbits);  // first digit's stream position
+        const u64 bit0 = (base + o0 - src.T) * (u64)src.lbits + (u64)(src.kbits - src.dshift - dbits);  // first digit's stream position
         const u64 w0 = bit0 >> 6;
         const u64 a = __ldg(src.stream + w0), b = __ldg(src.stream + w0 + 1), c = __ldg(src.stream + w0 + 2);
 #pragma unroll
@@ -432,9 +435,12 @@ __global__ void __launch_bounds__(RADIX) tile_scan_chunks_kernel(u32* __restrict
     chunk_tot[c * RADIX + d] = run;
 }
 
-// scan level 2 (one CTA): chunk totals become exclusive prefixes over the chunks; digit totals -> exclusive digit bases
-__global__ void __launch_bounds__(RADIX) tile_scan_top_kernel(u64* __restrict__ chunk_tot, size_t chunks, u64* __restrict__ gbase) {
-    __shared__ u64 wtot[RADIX / 32];
+// scan level 2 (one CTA): chunk totals become exclusive prefixes over the chunks; digit totals -> exclusive digit bases.
+// With seg_dense / seg_pad (top-digit-first suffix sort) the digit bases are also published as the 257-entry segment
+// tables: dense starts, and starts padded to multiples of `pad_tile` elements -- gbase then holds the PADDED starts.
+__global__ void __launch_bounds__(RADIX) tile_scan_top_kernel(u64* __restrict__ chunk_tot, size_t chunks, u64* __restrict__ gbase,
+                                                              u64* __restrict__ seg_dense, u64* __restrict__ seg_pad, u64 pad_tile) {
+    __shared__ u64 wtot[RADIX / 32], wtot2[RADIX / 32];
     const int d = threadIdx.x;
     u64 run = 0;
 #pragma unroll 8
@@ -444,11 +450,126 @@ __global__ void __launch_bounds__(RADIX) tile_scan_top_kernel(u64* __restrict__ 
         run += v;
     }
     const u64 inc = warp_inclusive_scan(run, OpSum());
+    const u64 padded = seg_pad != nullptr ? (run + pad_tile - 1) / pad_tile * pad_tile : 0;
+    const u64 inc2 = warp_inclusive_scan(padded, OpSum());
+    if ((d & 31) == 31) {
+        wtot[d >> 5] = inc;
+        wtot2[d >> 5] = inc2;
+    }
+    __syncthreads();
+    u64 pre = 0, pre2 = 0;
+    for (int w = 0; w < (d >> 5); ++w) {
+        pre += wtot[w];
+        pre2 += wtot2[w];
+    }
+    const u64 dense = pre + inc - run, pad = pre2 + inc2 - padded;
+    if (gbase != nullptr) gbase[d] = seg_pad != nullptr ? pad : dense;
+    if (seg_pad != nullptr) {
+        seg_dense[d] = dense;
+        seg_pad[d] = pad;
+        if (d == RADIX - 1) {
+            seg_dense[RADIX] = dense + run;
+            seg_pad[RADIX] = pad + padded;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ top-digit-first sort of suffixes: segmented passes
+// After the first pass has partitioned the suffixes by the TOP digit of their key (256 segments), the remaining digits
+// are sorted LSD *inside each segment*, so the top digit never has to be stored: it is implied by the segment.  Segments
+// start on multiples of the tile size in the ping-pong buffers ("padded" layout), so a tile never straddles two
+// segments; the last pass writes the dense layout.  tile_info[t] = segment << 16 | valid elements of padded tile t.
+template <int TILE>
+__global__ void __launch_bounds__(256) seg_tiles_kernel(const u64* __restrict__ seg_dense, const u64* __restrict__ seg_pad, u32* __restrict__ tile_info,
+                                                        size_t rows) {
+    __shared__ u64 s_pad[RADIX + 1];
+    for (int e = threadIdx.x; e <= RADIX; e += blockDim.x) s_pad[e] = seg_pad[e];
+    __syncthreads();
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < rows; t += (size_t)gridDim.x * blockDim.x) {
+        const u64 pos = (u64)t * TILE;
+        int lo = 0, hi = RADIX;  // last segment whose padded start is <= pos
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (s_pad[mid] <= pos)
+                lo = mid;
+            else
+                hi = mid;
+        }
+        // empty segments share their start with the next one: move to the last segment starting here
+        while (lo + 1 < RADIX && s_pad[lo + 1] <= pos) ++lo;
+        const u64 len = seg_dense[lo + 1] - seg_dense[lo];
+        const u64 off = pos - s_pad[lo];
+        const u32 valid = off < len ? (u32)((len - off < (u64)TILE) ? len - off : (u64)TILE) : 0u;
+        tile_info[t] = ((u32)lo << 16) | valid;
+    }
+}
+
+template <class Src, int THREADS, int ITEMS>
+__global__ void __launch_bounds__(THREADS) tile_hist_seg_kernel(const Src src, const u32* __restrict__ tile_info, u32* __restrict__ counts) {
+    __shared__ u32 sh[RADIX];
+    constexpr int TILE = THREADS * ITEMS;
+    if (threadIdx.x < RADIX) sh[threadIdx.x] = 0;
+    __syncthreads();
+    const size_t base = (size_t)blockIdx.x * TILE;
+    const int valid = (int)(tile_info[blockIdx.x] & 0xffffu);
+    typename Src::Stage key[ITEMS];
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+        const int o = j * THREADS + threadIdx.x;
+        if (o < valid) key[j] = src.load_key(base + o);
+    }
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+        if (j * THREADS + (int)threadIdx.x < valid) atomicAdd(&sh[src.digit(key[j])], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < RADIX) counts[(size_t)blockIdx.x * RADIX + threadIdx.x] = sh[threadIdx.x];
+}
+
+// per segment: digit bases of this pass.  P(t, d) = number of digit-d elements in the padded tiles before t (from the
+// two-level scan).  Segment s covers tiles [a, b): segbase[s][d] = out_start[s] + sum_{d' < d} (P(b,d') - P(a,d')) - P(a,d),
+// so that an element's output position is segbase[s][d] + P(t, d) + its rank inside the tile.
+template <int TILE>
+__global__ void __launch_bounds__(RADIX) seg_base_kernel(const u32* __restrict__ tile_excl, const u64* __restrict__ chunk_base,
+                                                         const u64* __restrict__ seg_dense, const u64* __restrict__ seg_pad, int dense_out,
+                                                         u64* __restrict__ segbase) {
+    __shared__ u64 wtot[RADIX / 32];
+    const int s = blockIdx.x, d = threadIdx.x;
+    const u64 len = seg_dense[s + 1] - seg_dense[s];
+    const size_t a = (size_t)(seg_pad[s] / TILE), b = a + (size_t)((len + TILE - 1) / TILE);
+    const u64 pa = chunk_base[(a / SCAN_CHUNK) * RADIX + d] + (u64)tile_excl[a * RADIX + d];
+    const u64 pb = chunk_base[(b / SCAN_CHUNK) * RADIX + d] + (u64)tile_excl[b * RADIX + d];
+    const u64 tot = pb - pa;
+    const u64 inc = warp_inclusive_scan(tot, OpSum());
     if ((d & 31) == 31) wtot[d >> 5] = inc;
     __syncthreads();
     u64 pre = 0;
     for (int w = 0; w < (d >> 5); ++w) pre += wtot[w];
-    gbase[d] = pre + inc - run;
+    segbase[(size_t)s * RADIX + d] = (dense_out ? seg_dense[s] : seg_pad[s]) + (pre + inc - tot) - pa;
+}
+
+template <class Src, typename ValT, int THREADS, int ITEMS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+    radix_scatter_seg_kernel(const Src src, typename Src::Out* __restrict__ kout, ValT* __restrict__ vout, const u32* __restrict__ tile_info,
+                             const u64* __restrict__ segbase, const u64* __restrict__ chunk_base, const u32* __restrict__ tile_excl) {
+    using Cfg = PassCfg<Src, ValT, THREADS, ITEMS, false>;
+    constexpr int TILE = Cfg::TILE;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const u32 info = tile_info[blockIdx.x];
+    const int valid = (int)(info & 0xffffu);
+    if (valid == 0) return;
+    u32* tab = reinterpret_cast<u32*>(smem_raw + Cfg::OFF_TAB);
+    for (int e = threadIdx.x; e < Cfg::NW * RADIX; e += THREADS) tab[e] = 0u;
+    __syncthreads();
+    const size_t tile = blockIdx.x;
+    const size_t base = tile * (size_t)TILE;
+    const u64* gb = segbase + (size_t)(info >> 16) * RADIX;
+    const u64* cb = chunk_base + (tile / SCAN_CHUNK) * RADIX;
+    const u32* te = tile_excl + tile * RADIX;
+    if (valid == TILE)
+        onesweep_tile<Cfg, Src, ValT, true>(smem_raw, src, kout, vout, nullptr, base, TILE, gb, cb, te);
+    else
+        onesweep_tile<Cfg, Src, ValT, false>(smem_raw, src, kout, vout, nullptr, base, valid, gb, cb, te);
 }
 
 // ------------------------------------------------------------------ hardware self-test of the ranking assumption
@@ -546,7 +667,7 @@ void launch_pass_cfg(const RadixWorkspace& ws, const Src& src, typename Src::Out
     else
         tile_hist_kernel<Src, THREADS, ITEMS><<<(unsigned)tiles, THREADS, 0, stream>>>(src, n, counts);
     tile_scan_chunks_kernel<<<(unsigned)chunks, RADIX, 0, stream>>>(counts, tiles, chunk_tot);
-    tile_scan_top_kernel<<<1, RADIX, 0, stream>>>(chunk_tot, chunks, ws.gbase);
+    tile_scan_top_kernel<<<1, RADIX, 0, stream>>>(chunk_tot, chunks, ws.gbase, nullptr, nullptr, 1);
     kern<<<(unsigned)tiles, THREADS, Cfg::SMEM, stream>>>(src, kout, vout, aout, n, ws.gbase, chunk_tot, counts);
 }
 
@@ -577,38 +698,132 @@ bool radix_sort_pairs(const RadixWorkspace& ws, KeyT* keys, KeyT* keys_alt, ValT
     return in_alt;
 }
 
-// Number of low key bits the first digit pass drops from the carried keys: its whole digit when the rest then fits
-// 32 bits (the digit travels on as the auxiliary byte), nothing otherwise (64-bit carried keys hold the whole key).
-static inline int carried_drop_bits(const RadixPlan& plan, int kbits) { return (kbits - plan.bits[0] <= 32) ? plan.bits[0] : 0; }
-
-// First sort of a construction: keys come from the packed text.  kbuf / vbuf / abuf are two ping-pong buffers each
-// (abuf only for 32-bit carried keys); pass 1 writes buffer 0; returns the index (0/1) of the buffers holding the
-// sorted carried keys, suffix indices and auxiliary bytes.  ev_pass1_done (optional) is recorded after digit pass 1.
-template <typename KeyC, typename IdxT>
-int radix_sort_suffixes(const RadixWorkspace& ws, const u64* text_stream, size_t n, int lbits, int key_chars, KeyC* const kbuf[2], IdxT* const vbuf[2],
-                        u8* const abuf[2], cudaStream_t stream, int sm_count, RadixPlan* plan_out, uint64_t* launches,
-                        cudaEvent_t ev_pass1_done = nullptr) {
-    (void)sm_count;
-    constexpr bool AUX = sizeof(KeyC) == 4;
+// ---------------------------------------------------------------------------------------------------------------
+// First sort of a construction, 64-bit carried keys (more than 40 key bits, or the |Sigma| = 256 quirk): plain LSD, the
+// first pass reads the packed text and carries the whole key.  kbuf / vbuf are two ping-pong buffers; pass 1 writes
+// buffer 0; returns the index (0/1) of the buffers holding the sorted keys and suffix indices.
+template <typename IdxT>
+int radix_sort_suffixes(const RadixWorkspace& ws, const u64* text_stream, size_t n, int lbits, int key_chars, u64* const kbuf[2], IdxT* const vbuf[2],
+                        cudaStream_t stream, RadixPlan* plan_out, uint64_t* launches, cudaEvent_t ev_pass1_done = nullptr) {
     const int kbits = key_chars * lbits;
     RadixPlan plan = make_radix_plan(0, kbits);
     if (plan_out) *plan_out = plan;
     if (n == 0) return 0;
     if (launches) *launches = (uint64_t)LAUNCHES_PER_PASS * plan.npass;
-    const int drop = AUX ? plan.bits[0] : 0;
-    if (AUX && kbits - drop > 32) throw std::string("radix_sort_suffixes: carried key does not fit 32 bits");
     {
         const u64 C = (u64)key_chars;
-        TextSrc<KeyC, IdxT> src{text_stream, (u64)n, (n < C - 1) ? (u64)n : C - 1, lbits, kbits, drop, (1u << plan.bits[0]) - 1u};
-        launch_pass<TextSrc<KeyC, IdxT>, IdxT, AUX>(ws, src, kbuf[0], vbuf[0], AUX ? abuf[0] : nullptr, n, stream);
+        TextSrc<u64, IdxT> src{text_stream, (u64)n, (n < C - 1) ? (u64)n : C - 1, lbits, kbits, 0, (1u << plan.bits[0]) - 1u, 0};
+        launch_pass<TextSrc<u64, IdxT>, IdxT, false>(ws, src, kbuf[0], vbuf[0], nullptr, n, stream);
     }
     if (ev_pass1_done) cudaEventRecord(ev_pass1_done, stream);
     int cur = 0;
     for (int p = 1; p < plan.npass; ++p) {
-        ArraySrc<KeyC, IdxT> src{kbuf[cur], vbuf[cur], AUX ? abuf[cur] : nullptr, plan.shift[p] - drop, (1u << plan.bits[p]) - 1u, (KeyC)0};
-        launch_pass<ArraySrc<KeyC, IdxT>, IdxT, AUX>(ws, src, kbuf[1 - cur], vbuf[1 - cur], AUX ? abuf[1 - cur] : nullptr, n, stream);
+        ArraySrc<u64, IdxT> src{kbuf[cur], vbuf[cur], nullptr, plan.shift[p], (1u << plan.bits[p]) - 1u, 0ull};
+        launch_pass<ArraySrc<u64, IdxT>, IdxT, false>(ws, src, kbuf[1 - cur], vbuf[1 - cur], nullptr, n, stream);
         cur = 1 - cur;
     }
+    PSAC_CUDA(cudaGetLastError());
+    return cur;
+}
+
+// First sort of a construction, 32-bit carried keys (key bits minus the top digit <= 32: BASELINE configs[1]).
+// Top digit first: pass 1 reads the packed text and partitions the suffixes by the TOP digit of their key into 256
+// segments laid out on tile boundaries; the remaining digits are then sorted LSD inside the segments
+// (tile_hist_seg_kernel / seg_base_kernel / radix_scatter_seg_kernel), the last pass writing the dense layout.  The
+// keys carried between passes are the LOW bits only -- the top digit is implied by the segment (seg_dense[257] = dense
+// segment starts, returned for the resolve step), so a suffix moves as 4 + 4 bytes per pass and no byte array travels.
+// kbuf / vbuf: two ping-pong buffers of suffix_sort_padded_elems(n) elements; vfinal: n elements (may be the caller's
+// SA buffer).  Returns the index of the kbuf holding the sorted carried keys (dense).
+static inline size_t suffix_sort_tile() { return (size_t)SortTuning<u32, u32, false>::THREADS * SortTuning<u32, u32, false>::ITEMS; }
+static inline size_t suffix_sort_padded_elems(size_t n) { return n + (size_t)(RADIX + 1) * suffix_sort_tile(); }
+static inline size_t suffix_sort_rows(size_t n) { return div_up(suffix_sort_padded_elems(n), suffix_sort_tile()) + 1; }
+
+struct SegWorkspace {
+    u64* seg_dense;  // [257]
+    u64* seg_pad;    // [257]
+    u64* segbase;    // [256][256]
+    u32* tile_info;  // [suffix_sort_rows(n)]
+};
+
+template <typename IdxT>
+int radix_sort_suffixes_msd(const RadixWorkspace& ws, const SegWorkspace& sw, const u64* text_stream, size_t n, int lbits, int key_chars, u32* const kbuf[2],
+                            IdxT* const vbuf[2], IdxT* vfinal, cudaStream_t stream, RadixPlan* plan_out, uint64_t* launches,
+                            cudaEvent_t ev_pass1_done = nullptr) {
+    using T = SortTuning<u32, IdxT, false>;
+    constexpr int TILE = T::THREADS * T::ITEMS;
+    const int kbits = key_chars * lbits;
+    RadixPlan plan = make_radix_plan(0, kbits);
+    if (plan_out) *plan_out = plan;
+    if (n == 0) return 0;
+    const int top = plan.npass - 1;
+    if (kbits - plan.bits[top] > 32) throw std::string("radix_sort_suffixes_msd: carried key does not fit 32 bits");
+    const u64 C = (u64)key_chars;
+    const u64 T0 = (n < C - 1) ? (u64)n : C - 1;
+    uint64_t nl = 0;
+    // ---- pass 1: top digit, from the text.  A single-pass sort (<= 8 key bits) writes the dense layout at once.
+    {
+        // (the digit is staged as the aux byte in shared memory -- the packed pair no longer contains it -- but not written out)
+        using TT = SortTuning<u32, IdxT, true>;
+        using Src = TextSrc<u32, IdxT>;
+        using Cfg = PassCfg<Src, IdxT, TT::THREADS, TT::ITEMS, true>;
+        Src src{text_stream, (u64)n, T0, lbits, kbits, 0, (1u << plan.bits[top]) - 1u, plan.shift[top]};
+        const size_t tiles = div_up(n, (size_t)Cfg::TILE);
+        const size_t chunks = div_up(tiles, (size_t)SCAN_CHUNK);
+        const size_t counts_bytes = align_up(tiles * RADIX * sizeof(u32), 256);
+        if (counts_bytes + chunks * RADIX * sizeof(u64) > ws.tiles_bytes) throw std::string("radix pass: tile workspace too small");
+        u32* counts = reinterpret_cast<u32*>(ws.tiles);
+        u64* chunk_tot = reinterpret_cast<u64*>(reinterpret_cast<char*>(ws.tiles) + counts_bytes);
+        auto kern = radix_scatter_kernel<Src, IdxT, TT::THREADS, TT::ITEMS, true, TT::MINB>;
+        static bool attr_set = false;
+        if (!attr_set) {
+            PSAC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+            attr_set = true;
+        }
+        const bool single = plan.npass == 1;
+        text_tile_hist_kernel<Src, TT::THREADS, TT::ITEMS><<<(unsigned)tiles, TT::THREADS, 0, stream>>>(src, n, counts);
+        tile_scan_chunks_kernel<<<(unsigned)chunks, RADIX, 0, stream>>>(counts, tiles, chunk_tot);
+        // gbase = padded segment starts (dense ones for a single-pass sort: pad_tile = 1)
+        tile_scan_top_kernel<<<1, RADIX, 0, stream>>>(chunk_tot, chunks, ws.gbase, sw.seg_dense, sw.seg_pad, single ? 1 : (u64)TILE);
+        kern<<<(unsigned)tiles, TT::THREADS, Cfg::SMEM, stream>>>(src, kbuf[0], single ? vfinal : vbuf[0], nullptr, n, ws.gbase, chunk_tot, counts);
+        nl += 4;
+        if (ev_pass1_done) cudaEventRecord(ev_pass1_done, stream);
+        if (single) {
+            if (launches) *launches = nl;
+            PSAC_CUDA(cudaGetLastError());
+            return 0;
+        }
+    }
+    // ---- tile map of the padded layout
+    const size_t rows = suffix_sort_rows(n);
+    seg_tiles_kernel<TILE><<<(unsigned)div_up(rows, (size_t)256), 256, 0, stream>>>(sw.seg_dense, sw.seg_pad, sw.tile_info, rows);
+    nl += 1;
+    // ---- the remaining digits, least significant first, inside the segments
+    using Src = ArraySrc<u32, IdxT>;
+    using Cfg = PassCfg<Src, IdxT, T::THREADS, T::ITEMS, false>;
+    auto kern = radix_scatter_seg_kernel<Src, IdxT, T::THREADS, T::ITEMS, T::MINB>;
+    static bool attr_set2 = false;
+    if (!attr_set2) {
+        PSAC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+        attr_set2 = true;
+    }
+    const size_t chunks = div_up(rows, (size_t)SCAN_CHUNK);
+    const size_t counts_bytes = align_up(rows * RADIX * sizeof(u32), 256);
+    if (counts_bytes + chunks * RADIX * sizeof(u64) > ws.tiles_bytes) throw std::string("radix pass: tile workspace too small");
+    u32* counts = reinterpret_cast<u32*>(ws.tiles);
+    u64* chunk_tot = reinterpret_cast<u64*>(reinterpret_cast<char*>(ws.tiles) + counts_bytes);
+    int cur = 0;
+    for (int p = 0; p < top; ++p) {
+        const bool last = p == top - 1;
+        Src src{kbuf[cur], vbuf[cur], nullptr, plan.shift[p], (1u << plan.bits[p]) - 1u, 0u};
+        tile_hist_seg_kernel<Src, T::THREADS, T::ITEMS><<<(unsigned)rows, T::THREADS, 0, stream>>>(src, sw.tile_info, counts);
+        tile_scan_chunks_kernel<<<(unsigned)chunks, RADIX, 0, stream>>>(counts, rows, chunk_tot);
+        tile_scan_top_kernel<<<1, RADIX, 0, stream>>>(chunk_tot, chunks, nullptr, nullptr, nullptr, 1);
+        seg_base_kernel<TILE><<<RADIX, RADIX, 0, stream>>>(counts, chunk_tot, sw.seg_dense, sw.seg_pad, last ? 1 : 0, sw.segbase);
+        kern<<<(unsigned)rows, T::THREADS, Cfg::SMEM, stream>>>(src, kbuf[1 - cur], last ? vfinal : vbuf[1 - cur], sw.tile_info, sw.segbase, chunk_tot, counts);
+        nl += 5;
+        cur = 1 - cur;
+    }
+    if (launches) *launches = nl;
     PSAC_CUDA(cudaGetLastError());
     return cur;
 }

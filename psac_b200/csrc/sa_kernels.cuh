@@ -433,8 +433,9 @@ struct TailList {
 
 // (sharded construction: only the tails whose key-prefix bin lies in [bin_lo, bin_hi) are in this shard's sorted range;
 //  the others get position ~0 and touch nothing)
+// (32-bit carried keys hold the key bits below the top digit; the top digit of position q is its segment in seg_dense)
 template <typename KeyC>
-__global__ void __launch_bounds__(64) tail_positions_kernel(const KeyC* __restrict__ keys, const u8* __restrict__ aux, u64 m, int drop,
+__global__ void __launch_bounds__(64) tail_positions_kernel(const KeyC* __restrict__ keys, u64 m, const u64* __restrict__ seg_dense, int seg_shift,
                                                             const u64* __restrict__ stream, u64 n, u64 T, int lbits, int kbits, int pbits, u32 bin_lo,
                                                             u32 bin_hi, TailList* __restrict__ out) {
     __shared__ u64 s_key[64];
@@ -448,7 +449,17 @@ __global__ void __launch_bounds__(64) tail_positions_kernel(const KeyC* __restri
         while (lo < hi) {
             const u64 mid = (lo + hi) >> 1;
             u64 k = (u64)keys[mid];
-            if (drop > 0) k = (k << drop) | (u64)aux[mid];
+            if (seg_dense != nullptr) {
+                int a = 0, b = 256;  // last segment starting at or before mid
+                while (b - a > 1) {
+                    const int c = (a + b) >> 1;
+                    if (seg_dense[c] <= mid)
+                        a = c;
+                    else
+                        b = c;
+                }
+                k |= (u64)a << seg_shift;
+            }
             if (k < full)
                 lo = mid + 1;
             else
@@ -466,11 +477,12 @@ __global__ void __launch_bounds__(64) tail_positions_kernel(const KeyC* __restri
 
 struct HeadsArgs {
     const void* keys;      // sorted carried keys (KeyC)
-    const u8* aux;         // key bits dropped by digit pass 1 (drop > 0), else null
+    const u64* seg_dense;  // 32-bit carried keys: dense start of the 256 top-digit segments (the top digit of a position), else null
+    int seg_shift;         // ... and the number of carried bits below the top digit
     const void* vals;      // sorted suffix indices (PosT); read for the direct ISA scatter, the unresolved list and the halo LCP
     u64 m;                 // number of suffixes sorted here
     u64 n;                 // text length
-    int drop, lbits, C;
+    int lbits, C;
     const TailList* tails;
     void* bucket_out;      // PosT
     void* isa;             // direct scatter (small inputs) or null
@@ -496,6 +508,7 @@ __global__ void __launch_bounds__(HD_THREADS) heads_kernel(HeadsArgs A) {
     __shared__ u32 s_wsum[HD_THREADS / 32];
     __shared__ TailList s_tails;
     __shared__ int s_has_tail;
+    __shared__ u64 s_seg[257];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const u64 tile = blockIdx.x;
     const u64 t0 = tile * HD_TILE;
@@ -503,6 +516,8 @@ __global__ void __launch_bounds__(HD_THREADS) heads_kernel(HeadsArgs A) {
     const u64 m = A.m;
     const KeyC* keys = reinterpret_cast<const KeyC*>(A.keys);
     if (tid == 0) s_has_tail = 0;
+    if (A.seg_dense != nullptr)
+        for (int e = tid; e <= 256; e += HD_THREADS) s_seg[e] = A.seg_dense[e];
     __syncthreads();
     if (tid < 64 && (u32)tid < A.tails->count) {
         const u64 p = A.tails->pos[tid];
@@ -531,21 +546,12 @@ __global__ void __launch_bounds__(HD_THREADS) heads_kernel(HeadsArgs A) {
                 key[2 + 2 * c] = ((u64)t.w << 32) | t.z;
             }
         }
-        if (A.drop > 0) {
-            const uint4 t = __ldcs(reinterpret_cast<const uint4*>(A.aux + q0));
-            const u32 w[4] = {t.x, t.y, t.z, t.w};
-#pragma unroll
-            for (int i = 0; i < HD_ITEMS; ++i) key[1 + i] = (key[1 + i] << A.drop) | ((w[i >> 2] >> (8 * (i & 3))) & 0xffu);
-        }
     } else {
 #pragma unroll
         for (int i = 0; i < HD_ITEMS; ++i) {
             const u64 q = q0 + i;
             u64 k = 0;
-            if (q < m) {
-                k = (u64)keys[q];
-                if (A.drop > 0) k = (k << A.drop) | (u64)A.aux[q];
-            }
+            if (q < m) k = (u64)keys[q];
             key[1 + i] = k;
         }
     }
@@ -557,22 +563,39 @@ __global__ void __launch_bounds__(HD_THREADS) heads_kernel(HeadsArgs A) {
             l = 0;
             if (q0 >= 1 && q0 - 1 < m) {
                 l = (u64)keys[q0 - 1];
-                if (A.drop > 0) l = (l << A.drop) | (u64)A.aux[q0 - 1];
             } else if (q0 == 0 && A.halo != nullptr) {
                 l = A.halo[0];  // last key of the previous shard (only the LCP of position 0 uses it: position 0 is a head)
             }
         }
         if (lane == 31) {
             r = 0;
-            if (q0 + HD_ITEMS < m) {
-                r = (u64)keys[q0 + HD_ITEMS];
-                if (A.drop > 0) r = (r << A.drop) | (u64)A.aux[q0 + HD_ITEMS];
-            }
+            if (q0 + HD_ITEMS < m) r = (u64)keys[q0 + HD_ITEMS];
         }
         key[0] = l;
         key[HD_ITEMS + 1] = r;
     }
     __syncthreads();
+    if (A.seg_dense != nullptr) {
+        // 32-bit carried keys: the top digit of a position is the segment it lies in.  One binary search for the
+        // thread's first element, then a compare per element (a thread's 18 positions rarely cross a segment start).
+        const u64 qa = q0 >= 1 ? q0 - 1 : 0;
+        int sg = 0, hi = 256;
+        while (hi - sg > 1) {
+            const int c = (sg + hi) >> 1;
+            if (s_seg[c] <= qa)
+                sg = c;
+            else
+                hi = c;
+        }
+#pragma unroll
+        for (int i = 0; i < HD_ITEMS + 2; ++i) {
+            const u64 q = q0 + i - 1;  // (i = 0 with q0 = 0 is the halo / nothing: its key is not from this array)
+            if (q0 + i >= 1 && q < m) {
+                while (sg < 255 && s_seg[sg + 1] <= q) ++sg;
+                key[i] |= (u64)sg << A.seg_shift;
+            }
+        }
+    }
     // ---- head bits of q0 .. q0+16 (bit 16 only feeds the "unresolved" test)
     u32 head = 0;
 #pragma unroll

@@ -622,15 +622,15 @@ bool construct_sharded_core(psacb200_engine* e, const ShardComm& C, const u8* d_
     if (!alpha.zero_code_used) {
         // lean round-0 resolve (sa_kernels.cuh heads_kernel) with global positions
         TailList* tails = reinterpret_cast<TailList*>(e->tail_list());
-        tail_positions_kernel<u64><<<1, 64, 0, st>>>(e->keys[x].as<u64>(), nullptr, cnt, 0, stream, n, T, lbits, kbits, pbits, (u32)first[me],
+        tail_positions_kernel<u64><<<1, 64, 0, st>>>(e->keys[x].as<u64>(), cnt, nullptr, 0, stream, n, T, lbits, kbits, pbits, (u32)first[me],
                                                      (u32)first[me + 1], tails);
         HeadsArgs H{};
         H.keys = e->keys[x].p;
-        H.aux = nullptr;
+        H.seg_dense = nullptr;
+        H.seg_shift = 0;
         H.vals = SA;
         H.m = cnt;
         H.n = n;
-        H.drop = 0;
         H.lbits = lbits;
         H.C = (int)Cc;
         H.tails = tails;
