@@ -235,7 +235,7 @@ unsigned choose_key_chars(u64 n, int lbits, unsigned k) {
 size_t lookback_bytes(u64 n) {
     const size_t rows = suffix_sort_rows(n);  // padded tile rows of the top-digit-first suffix sort
     const size_t seg = align_up(rows * RADIX * sizeof(u32), 256) + (div_up(rows, (size_t)SCAN_CHUNK) + 1) * RADIX * sizeof(u64);
-    return std::max(std::max(RadixWorkspace::tiles_bytes_for(n), seg), (size_t)(2 * div_up(n, (size_t)RES_TILE) * sizeof(u64)));
+    return std::max(std::max(RadixWorkspace::tiles_bytes_for(n), seg), (size_t)(2 * div_up(n, (size_t)RES_TILE) * sizeof(u64) + div_up(n, (size_t)HD_TILE) + 64));
 }
 
 // Device buffers of one construction.  When the caller's outputs are device buffers of the engine's internal index
@@ -368,6 +368,14 @@ void construct_core(psacb200_engine* e, u64 n, int index_bytes, unsigned flags, 
         H.keys = kbuf[x];
         H.seg_dense = seg_dense;
         H.seg_shift = carried_bits;
+        H.seg_flags = nullptr;
+        if (seg_dense != nullptr) {
+            u8* flags = e->lookback.as<u8>() + 2 * div_up(n, (size_t)HD_TILE) * sizeof(u64);  // behind the tile aggregates
+            PSAC_CUDA(cudaMemsetAsync(flags, 0, div_up(n, (size_t)HD_TILE), st));
+            seg_flag_kernel<<<1, 256, 0, st>>>(seg_dense, n, (u64)HD_TILE, flags);
+            e->launches += 1;
+            H.seg_flags = flags;
+        }
         H.vals = SA;
         H.m = n;
         H.n = n;

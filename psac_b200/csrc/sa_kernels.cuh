@@ -475,10 +475,20 @@ __global__ void __launch_bounds__(64) tail_positions_kernel(const KeyC* __restri
     if (j == 0) out->count = (u32)T;
 }
 
+// marks the heads tiles that touch a segment start p (the tile of p and the tile of p - 1)
+__global__ void __launch_bounds__(256) seg_flag_kernel(const u64* __restrict__ seg_dense, u64 m, u64 tile_elems, u8* __restrict__ flags) {
+    const u64 p = seg_dense[threadIdx.x];
+    if (threadIdx.x > 0 && p > 0 && p < m) {
+        flags[p / tile_elems] = 1;
+        flags[(p - 1) / tile_elems] = 1;
+    }
+}
+
 struct HeadsArgs {
     const void* keys;      // sorted carried keys (KeyC)
     const u64* seg_dense;  // 32-bit carried keys: dense start of the 256 top-digit segments (the top digit of a position), else null
     int seg_shift;         // ... and the number of carried bits below the top digit
+    const u8* seg_flags;   // ... and per heads tile: 1 if a segment starts inside it or right after it
     const void* vals;      // sorted suffix indices (PosT); read for the direct ISA scatter, the unresolved list and the halo LCP
     u64 m;                 // number of suffixes sorted here
     u64 n;                 // text length
@@ -516,7 +526,9 @@ __global__ void __launch_bounds__(HD_THREADS) heads_kernel(HeadsArgs A) {
     const u64 m = A.m;
     const KeyC* keys = reinterpret_cast<const KeyC*>(A.keys);
     if (tid == 0) s_has_tail = 0;
-    if (A.seg_dense != nullptr)
+    // 32-bit carried keys: only the (at most 2 x 255) tiles that touch a segment start need the top digits
+    const bool has_seg = A.seg_dense != nullptr && A.seg_flags[tile] != 0;
+    if (has_seg)
         for (int e = tid; e <= 256; e += HD_THREADS) s_seg[e] = A.seg_dense[e];
     __syncthreads();
     if (tid < 64 && (u32)tid < A.tails->count) {
@@ -575,9 +587,10 @@ __global__ void __launch_bounds__(HD_THREADS) heads_kernel(HeadsArgs A) {
         key[HD_ITEMS + 1] = r;
     }
     __syncthreads();
-    if (A.seg_dense != nullptr) {
-        // 32-bit carried keys: the top digit of a position is the segment it lies in.  One binary search for the
-        // thread's first element, then a compare per element (a thread's 18 positions rarely cross a segment start).
+    if (has_seg) {
+        // the top digit of a position is the segment it lies in: inside one segment the carried keys alone decide heads
+        // and LCPs (the top digits cancel), so this runs only in tiles that contain a segment start.  One binary search
+        // for the thread's first element, then a compare per element.
         const u64 qa = q0 >= 1 ? q0 - 1 : 0;
         int sg = 0, hi = 256;
         while (hi - sg > 1) {

@@ -628,6 +628,7 @@ bool construct_sharded_core(psacb200_engine* e, const ShardComm& C, const u8* d_
         H.keys = e->keys[x].p;
         H.seg_dense = nullptr;
         H.seg_shift = 0;
+        H.seg_flags = nullptr;
         H.vals = SA;
         H.m = cnt;
         H.n = n;
