@@ -548,7 +548,8 @@ bool construct_sharded_core(psacb200_engine* e, const ShardComm& C, const u8* d_
         e->keys[b].reserve((cnt + 16) * sizeof(u64), tot);
         e->vals[b].reserve((cnt + 16) * sizeof(u64), tot);
     }
-    e->isa.reserve((n_local + 16) * sizeof(u64), tot);
+    const bool isa_inplace = index_bytes == 8 && isa_out != nullptr;  // 64-bit caller: scatter straight into the caller's ISA block
+    if (!isa_inplace) e->isa.reserve((n_local + 16) * sizeof(u64), tot);
     if (want_lcp) e->lcp.reserve((cnt + 16) * sizeof(u64), tot);
     e->lookback.reserve(lookback_bytes(std::max(cnt, n_local)), tot);
     e->begin(PH_SORT);
@@ -574,7 +575,7 @@ bool construct_sharded_core(psacb200_engine* e, const ShardComm& C, const u8* d_
     e->end(PH_SORT);
     const int x = alt ? 1 : 0, y = 1 - x;
     u64* SA = e->vals[x].as<u64>();     // SA positions [off, off + cnt)
-    u64* ISA = e->isa.as<u64>();        // ISA entries of my text block
+    u64* ISA = isa_inplace ? reinterpret_cast<u64*>(isa_out) : e->isa.as<u64>();  // ISA entries of my text block
     u64* LCP = want_lcp ? e->lcp.as<u64>() : nullptr;
     const u64 text_lo = blk.start(me), text_hi = text_lo + n_local;
 
@@ -926,7 +927,9 @@ bool construct_sharded_core(psacb200_engine* e, const ShardComm& C, const u8* d_
         deliver(SA, sa_out);
         if (want_lcp) deliver(LCP, lcp_out);
         if (isa_out && n_local) {
-            if (direct)
+            if (isa_inplace) {
+                // already there
+            } else if (direct)
                 PSAC_CUDA(cudaMemcpyAsync(isa_out, ISA, n_local * sizeof(u64), cudaMemcpyDeviceToDevice, st));
             else {
                 convert_kernel<u64, u32><<<grid_for(e, n_local, 256, 16), 256, 0, st>>>(ISA, reinterpret_cast<u32*>(isa_out), n_local);
