@@ -1,19 +1,21 @@
-// psac-b200: single-GPU LSD radix sort of (key, value) pairs -- the "(B1,B2) tuple sort" of the
+// psac-b200: single-GPU radix sort of (key, value) pairs -- the "(B1,B2) tuple sort" of the
 // prefix-doubling loop (reference: include/idxsort.hpp:22-83 -> mxx::sort).
 //
 // Design (B200-first, not the reference's comparison sample sort):
-//   * LSD radix sort, one 8-bit digit per pass.  A pass is: per-tile digit histogram (reads the keys only) -> scan of
-//     the per-tile counts (two tiny kernels) -> scatter kernel.  A scatter CTA owns a tile, ranks its keys with ONE
-//     shared-memory atomic per key (see "ranking" below), adds the tile's global bin offsets and writes the tile out
-//     through shared memory so each bin's run leaves as one coalesced burst.
+//   * one 8-bit digit per pass.  A pass is: per-tile digit histogram (reads the keys only) -> scan of the per-tile
+//     counts (tiny kernels) -> scatter kernel.  A scatter CTA owns a tile, ranks its keys with ONE shared-memory
+//     atomic per key (see "ranking" below), adds the tile's global bin offsets and writes the tile out through
+//     shared memory so each bin's run leaves as one coalesced burst.
 //     (Measured first: the usual single-kernel "onesweep" with a decoupled look-back.  On B200 ~450 tiles are resident
 //     and a dependent L2 load under full DRAM load costs ~1 us, so 54 % of a tile's cycles were look-back waits
 //     (profiles/r1_bench_pass.txt); re-reading 4 bytes per key for the histogram is cheaper than that.)
-//   * the first pass of a construction reads the packed text instead of a key array (k-mer generation fused) and
-//     drops the digit it consumed, so the keys carried through the remaining passes are 32 bits wide whenever the
-//     sort key has <= 40 bits (BASELINE configs[1]: 20 DNA characters); the dropped digit travels on as one byte;
-//   * algorithmic HBM traffic per pass = read + write of every carried key, value and aux byte once (the histogram's
-//     re-read of the keys is overhead and counted as such in DESIGN.md).
+//   * generic pairs (radix_sort_pairs) and 64-bit carried keys (radix_sort_suffixes) are sorted LSD;
+//   * the first sort of a construction with <= 40 key bits (BASELINE configs[1]: 20 DNA characters) goes TOP DIGIT FIRST
+//     (radix_sort_suffixes_msd): pass 1 reads the packed text instead of a key array (k-mer generation fused) and
+//     partitions by the top digit into 256 tile-aligned segments, the other digits are sorted LSD inside the segments,
+//     so only the low 32 key bits travel with the 32-bit suffix index -- the top digit is implied by the segment;
+//   * algorithmic HBM traffic per pass = read + write of every carried key and value once (the histogram's re-read of
+//     the keys is overhead and counted as such in DESIGN.md).
 //
 // Ranking.  A stable rank needs, for every key, the number of earlier keys of the tile with the same digit.
 // On sm_100a the lanes of one ATOMS.ADD warp instruction that hit the same shared-memory word are applied in
