@@ -111,60 +111,6 @@ struct OpMax {
     static __device__ __forceinline__ u64 identity() { return 0; }
 };
 
-// Called by ONE thread per channel.  Publishes this tile's aggregate, walks back over the predecessors
-// until an inclusive prefix is found, publishes this tile's inclusive prefix and returns the EXCLUSIVE one.
-// Tiles must be numbered in launch order (dynamic tile ids) so every predecessor is already running.
-template <typename Op>
-__device__ __forceinline__ u64 lookback_exclusive(u64* chan, size_t stride, size_t tile, u64 aggregate, u32 epoch, Op op) {
-    if (tile == 0) {
-        st_relaxed(chan, lb_pack(aggregate, epoch, LB_INCLUSIVE));
-        return Op::identity();
-    }
-    st_relaxed(chan + tile * stride, lb_pack(aggregate, epoch, LB_AGGREGATE));
-    u64 excl = Op::identity();
-    size_t t = tile;
-    while (true) {
-        --t;
-        u64 w, st;
-        do {
-            w = ld_relaxed(chan + t * stride);
-            st = lb_state(w, epoch);
-        } while (st == LB_NONE);
-        excl = op(lb_payload(w), excl);
-        if (st == LB_INCLUSIVE) break;
-    }
-    st_relaxed(chan + tile * stride, lb_pack(op(excl, aggregate), epoch, LB_INCLUSIVE));
-    return excl;
-}
-
-// Sum look-back of ONE thread per channel with B loads in flight: on B200 a tile lives ~10 us, ~450 tiles are resident and
-// a dependent L2 load under full DRAM load costs several hundred ns, so a one-entry-at-a-time walk over the
-// predecessors that are still walking themselves never catches up (profiles/r1b: 40 % of the pass kernel's stall
-// samples sat on that load).  The caller has already published this tile's aggregate.  Returns the exclusive prefix.
-template <int B>
-__device__ __forceinline__ u64 lookback_sum_batched(const u64* chan, size_t stride, size_t tile, u32 epoch) {
-    u64 excl = 0;
-    size_t t = tile;  // predecessors t-1, t-2, ...
-    while (t > 0) {
-        u64 w[B];
-#pragma unroll
-        for (int b = 0; b < B; ++b) w[b] = (t > (size_t)b) ? ld_relaxed(chan + (t - 1 - b) * stride) : 0;
-#pragma unroll
-        for (int b = 0; b < B; ++b) {
-            if (t <= (size_t)b) return excl;  // walked past tile 0
-            u64 st = lb_state(w[b], epoch);
-            while (st == LB_NONE) {
-                w[b] = ld_relaxed(chan + (t - 1 - b) * stride);
-                st = lb_state(w[b], epoch);
-            }
-            excl += lb_payload(w[b]);
-            if (st == LB_INCLUSIVE) return excl;
-        }
-        t -= B;
-    }
-    return excl;
-}
-
 // ---------------------------------------------------------------- warp scans (shuffle based)
 template <typename Op>
 __device__ __forceinline__ u64 warp_inclusive_scan(u64 v, Op op) {

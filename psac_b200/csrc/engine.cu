@@ -329,7 +329,6 @@ void construct_core(psacb200_engine* e, u64 n, int index_bytes, unsigned flags, 
     ResolveArgs R{};
     R.keys = kbuf[x];
     R.vals = SA;
-    R.aux = nullptr;
     R.pos_in = nullptr;
     R.m = n;
     R.n = n;
@@ -346,7 +345,6 @@ void construct_core(psacb200_engine* e, u64 n, int index_bytes, unsigned flags, 
     R.stream = e->packed.as<u64>();
     R.lbits = lbits;
     R.C = (int)C;
-    R.drop = 0;
     R.kbits = 0;
     R.h = 0;
     R.padded_lcp = alpha.zero_code_used ? 1 : 0;
@@ -490,12 +488,10 @@ void construct_core(psacb200_engine* e, u64 n, int index_bytes, unsigned flags, 
             Q.m = m;
             Q.isa = ISA;
             Q.bucket_out = nullptr;
-            Q.aux = nullptr;
             Q.pos_out = e->rp[t].p;
             Q.head_out = e->rh[t].as<u8>();
             Q.cap = m;
             Q.lb_sum = Q.lb_max + ntiles;
-            Q.drop = 0;
             Q.kbits = kbits;
             Q.h = h;
             launch_resolve<IdxT, u64>(e, false, Q);

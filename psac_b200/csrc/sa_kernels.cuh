@@ -125,7 +125,6 @@ __device__ __forceinline__ u64 stream_lcp(const u64* __restrict__ stream, u64 n,
 struct ResolveArgs {
     const void* keys;     // sorted keys (KeyC)
     const void* vals;     // sorted suffix indices (IdxT)
-    const u8* aux;        // round 0 with 32-bit carried keys: the key bits dropped by digit pass 1, else null
     const void* pos_in;   // SA position of element q (rounds >= 1)
     u64 m;                // elements this round
     u64 n;                // text length
@@ -142,7 +141,6 @@ struct ResolveArgs {
     const u64* stream;    // packed text
     int lbits;
     int C;                // round 0: characters in the key
-    int drop;             // round 0: number of low key bits held in aux instead of the carried key
     int kbits;            // rounds >= 1: bits of the low key field (rank of suffix+h); the rest is the bucket
     u64 h;                // rounds >= 1: characters already known equal inside a bucket
     int padded_lcp;       // reference quirk: a used character has code 0 and matches the padding (see stream_lcp)
@@ -195,20 +193,6 @@ __device__ __forceinline__ void load_run(const T* __restrict__ p, u64 q0, u64 m,
     }
     load_halo<T, N>(p, q0, m, out);
 }
-template <int N>
-__device__ __forceinline__ void load_run_bytes(const u8* __restrict__ p, u64 q0, u64 m, u64 (&out)[N + 2]) {
-    static_assert(N == 8, "one 64-bit load per thread");
-    if (q0 + N <= m && ((reinterpret_cast<size_t>(p + q0) & 7) == 0)) {
-        const u64 t = __ldcs(reinterpret_cast<const u64*>(p + q0));
-#pragma unroll
-        for (int i = 0; i < N; ++i) out[1 + i] = (t >> (8 * i)) & 0xffu;
-    } else {
-#pragma unroll
-        for (int i = 0; i < N; ++i) out[1 + i] = (q0 + i < m) ? (u64)p[q0 + i] : 0;
-    }
-    load_halo<u8, N>(p, q0, m, out);
-}
-
 // PHASE 0 = reduce: only the tile's aggregates (position of its last head, number of unresolved elements) are written;
 // PHASE 1 = apply: reads the tile's exclusive prefixes produced by tile_scan_kernel and writes the results.
 // (A single-pass chained scan was measured first: with ~500 k short tiles the look-back waits dominated, 14-17 ms
@@ -229,13 +213,6 @@ __global__ void __launch_bounds__(RES_THREADS) resolve_kernel(ResolveArgs A) {
     u64 suf[RES_ITEMS + 2];
     load_run<KeyC, RES_ITEMS>(reinterpret_cast<const KeyC*>(A.keys), q0, m, key);
     load_run<IdxT, RES_ITEMS>(reinterpret_cast<const IdxT*>(A.vals), q0, m, suf);
-    if (FIRST && A.drop > 0) {
-        // complete the carried keys with the bits digit pass 1 consumed
-        u64 low[RES_ITEMS + 2];
-        load_run_bytes<RES_ITEMS>(A.aux, q0, m, low);
-#pragma unroll
-        for (int i = 0; i < RES_ITEMS + 2; ++i) key[i] = (key[i] << A.drop) | low[i];
-    }
     const bool has_halo = FIRST && A.halo != nullptr;
     if (has_halo && q0 == 0) {  // the element before local position 0 lives on the previous shard
         key[0] = A.halo[0];

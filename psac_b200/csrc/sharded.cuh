@@ -592,7 +592,6 @@ bool construct_sharded_core(psacb200_engine* e, const ShardComm& C, const u8* d_
     ResolveArgs R{};
     R.keys = e->keys[x].p;
     R.vals = SA;
-    R.aux = nullptr;
     R.pos_in = nullptr;
     R.m = cnt;
     R.n = n;
@@ -610,7 +609,6 @@ bool construct_sharded_core(psacb200_engine* e, const ShardComm& C, const u8* d_
     R.stream = stream;
     R.lbits = lbits;
     R.C = (int)Cc;
-    R.drop = 0;
     R.kbits = 0;
     R.h = 0;
     R.padded_lcp = alpha.zero_code_used ? 1 : 0;
@@ -884,7 +882,6 @@ bool construct_sharded_core(psacb200_engine* e, const ShardComm& C, const u8* d_
             Q.suf_out = e->rv[t].p;
             Q.cap = m;
             Q.lb_sum = Q.lb_max + ntiles;
-            Q.drop = 0;
             Q.kbits = kb;
             Q.h = h;
             launch_resolve<u64, u64>(e, false, Q);

@@ -80,3 +80,13 @@ def test_cpp_shim_matches_reference_goldens_on_gpu(tmp_path):
     exe = _build_cpp_shim_test(tmp_path)
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+def test_header_is_valid_c99_and_links(tmp_path):
+    import subprocess
+    api.lib()
+    exe = str(tmp_path / "test_header")
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", "test_header.c"),
+                           "-L", os.path.join(ROOT, "psac_b200"), "-lpsacb200", "-Wl,-rpath," + os.path.join(ROOT, "psac_b200"), "-o", exe])
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
