@@ -7,6 +7,7 @@
 //   construct(begin, end, fast_resolval = true, k = 0)                                       :469-486
 //   construct(begin, end, fast_resolval, alphabet, k)                                        :365-366
 //   construct_arr<L>(begin, end, fast_resolval = true)   (SA / ISA only, no LCP :555-567)    :490-641
+//   write(basename) / read(basename)   (.sa / .lcp raw index_t arrays, .alpha)               :232-265
 // Differences, all outside the hot path: the communicator argument is psacb200::comm, a stand-in for an mxx::comm of
 // size 1 (the GPUs of one box are sharded INSIDE the engine, include/psacb200.h psacb200_construct_sharded, so the
 // host-facing object always holds the whole arrays); the alphabet is the 256-entry code table
@@ -18,6 +19,7 @@
 
 #include <cstddef>
 #include <cstdint>
+#include <fstream>
 #include <iterator>
 #include <stdexcept>
 #include <string>
@@ -111,6 +113,37 @@ public:
         run(text, fast_resolval, 0, nullptr, false);
     }
 
+    // reference :232-243 -- <basename>.sa, .lcp (if built): raw little-endian index_t; .alpha: the used characters
+    void write(const std::string& basename) const {
+        write_array(basename + ".sa", local_SA);
+        if (_CONSTRUCT_LCP) write_array(basename + ".lcp", local_LCP);
+        std::ofstream f(basename + ".alpha", std::ios::binary);
+        for (int c = 0; c < 256; ++c)
+            if (alpha.mapping_table[c] != 0 || (alpha.sigma_ == 256 && c == 255)) f.put((char)c);
+    }
+    // reference :245-265
+    void read(const std::string& basename) {
+        read_array(basename + ".sa", local_SA);
+        if (_CONSTRUCT_LCP) {
+            read_array(basename + ".lcp", local_LCP);
+            if (local_SA.size() != local_LCP.size()) throw std::runtime_error("SA and LCP have to have same size");
+        }
+        std::ifstream f(basename + ".alpha", std::ios::binary);
+        alpha = alphabet_type();
+        bool used[256] = {false};
+        char c;
+        while (f.get(c)) used[(unsigned char)c] = true;
+        unsigned code = 1;
+        for (int i = 0; i < 256; ++i)
+            if (used[i]) {
+                alpha.mapping_table[i] = (uint8_t)code++;  // 8-bit table like the reference (alphabet.hpp:136,160)
+                ++alpha.sigma_;
+            }
+        while ((1u << alpha.bits_per_char_) < alpha.sigma_ + 1) ++alpha.bits_per_char_;
+        local_B.clear();
+        init_size(local_SA.size());
+    }
+
     psacb200_stats stats() const {
         psacb200_stats s{};
         if (engine_) psacb200_get_stats(engine_, &s);
@@ -121,6 +154,19 @@ private:
     psacb200_engine* engine_;
     std::vector<uint8_t> staging_;
 
+    static void write_array(const std::string& filename, const std::vector<index_t>& v) {
+        std::ofstream f(filename, std::ios::binary | std::ios::trunc);
+        f.write(reinterpret_cast<const char*>(v.data()), (std::streamsize)(v.size() * sizeof(index_t)));
+        if (!f) throw std::runtime_error("cannot write " + filename);
+    }
+    static void read_array(const std::string& filename, std::vector<index_t>& v) {
+        std::ifstream f(filename, std::ios::binary | std::ios::ate);
+        if (!f) throw std::runtime_error("cannot read " + filename);
+        const std::size_t bytes = (std::size_t)f.tellg();
+        v.resize(bytes / sizeof(index_t));
+        f.seekg(0, std::ios::beg);
+        f.read(reinterpret_cast<char*>(v.data()), (std::streamsize)(v.size() * sizeof(index_t)));
+    }
     static void check(int rc) {
         if (rc != PSACB200_OK) throw std::runtime_error(std::string("psacb200: ") + psacb200_last_error());
     }

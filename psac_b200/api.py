@@ -253,6 +253,7 @@ class SuffixArray:
         self.local_B = None
         self.local_LCP = None
         self.alpha = None
+        self._text = None
 
     def _eng(self):
         return self.engine if self.engine is not None else default_engine()
@@ -261,8 +262,23 @@ class SuffixArray:
         """reference: construct(begin, end, fast_resolval = true, k = 0), suffix_array.hpp:469-486"""
         t = _as_text(text)
         r = self._eng().construct(t, self.index_bytes, self.construct_lcp, k, fast_resolval)
+        self._text = t
         self.n = self.local_size = t.size
         self.local_SA, self.local_B, self.local_LCP = r["sa"], r["isa"], r["lcp"]
+        return self
+
+    def write(self, basename, text=None):
+        """reference: write(basename), suffix_array.hpp:232-243 (.alpha needs the text or a previous construct)"""
+        from . import fileio
+        fileio.write_suffix_array(basename, self.local_SA, self.local_LCP if self.construct_lcp else None, text if text is not None else self._text)
+
+    def read(self, basename):
+        """reference: read(basename), suffix_array.hpp:245-265"""
+        from . import fileio
+        r = fileio.read_suffix_array(basename, self.index_bytes, with_lcp=self.construct_lcp)
+        self.local_SA, self.local_LCP, self.alpha = r["sa"], r["lcp"], r["lut"]
+        self.local_B = None
+        self.n = self.local_size = int(r["n"])
         return self
 
     def construct_arr(self, text, L=2, fast_resolval=True):

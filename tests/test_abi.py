@@ -90,3 +90,17 @@ def test_header_is_valid_c99_and_links(tmp_path):
                            "-L", os.path.join(ROOT, "psac_b200"), "-lpsacb200", "-Wl,-rpath," + os.path.join(ROOT, "psac_b200"), "-o", exe])
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+def test_cpp_shim_file_formats(tmp_path):
+    import subprocess
+    api.lib()
+    exe = str(tmp_path / "test_shim_io")
+    subprocess.check_call(["g++", "-std=c++11", "-O1", "-Wall", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", "test_shim_io.cpp"),
+                           "-L", os.path.join(ROOT, "psac_b200"), "-lpsacb200", "-Wl,-rpath," + os.path.join(ROOT, "psac_b200"), "-o", exe])
+    r = subprocess.run([exe, str(tmp_path / "idx")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    # the files are the reference's formats: the Python side reads them back
+    from psac_b200 import fileio
+    got = fileio.read_suffix_array(str(tmp_path / "idx"), 4, with_lcp=True)
+    assert got["sa"].tolist() == [10, 7, 4, 1, 0, 9, 8, 6, 3, 5, 2] and got["sigma"] == 4

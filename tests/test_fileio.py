@@ -1,0 +1,68 @@
+"""Host-side file formats of the reference (suffix_array::write/read, psac -o, alphabet files, block-decomposed text):
+round trips at p = 1 and across different numbers of ranks, like the reference's FileIO test (test/test_psac.cpp:306-347)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as O
+from psac_b200 import api, fileio
+from psac_b200 import textgen as G
+
+
+def test_write_read_roundtrip_and_raw_layout(tmp_path):
+    t = G.random_dna(5003, 9)
+    exp = O.construct(t, 64, 0, True)
+    base = str(tmp_path / "idx")
+    for dt, ib in ((np.uint32, 4), (np.uint64, 8)):
+        fileio.write_suffix_array(base, exp["sa"].astype(dt), exp["lcp"].astype(dt), text=t)
+        assert os.path.getsize(base + ".sa") == t.size * ib  # raw little-endian index_t, nothing else
+        assert (np.fromfile(base + ".sa", dtype="<u%d" % ib) == exp["sa"]).all()
+        r = fileio.read_suffix_array(base, ib, with_lcp=True)
+        assert r["n"] == t.size and (r["sa"] == exp["sa"]).all() and (r["lcp"] == exp["lcp"]).all()
+        lut, sigma, _ = O.alphabet(t)
+        assert r["sigma"] == sigma and (r["lut"] == lut).all()
+        assert open(base + ".alpha", "rb").read() == b"ACGT"
+
+
+@pytest.mark.parametrize("pw,pr", [(1, 3), (4, 1), (3, 5), (13, 4)])
+def test_written_by_p_ranks_read_by_q_ranks(tmp_path, pw, pr):
+    n = 1000 + pw
+    sa = np.random.default_rng(pw).permutation(n).astype(np.uint64)
+    f = str(tmp_path / "x.sa")
+    for r in range(pw):
+        s, m = api.blk_dist(n, pw, r)
+        fileio.write_dist_int_array(f, sa[s:s + m], r, pw, n)
+    got = np.concatenate([fileio.read_dist_int_array(f, np.uint64, r, pr)[0] for r in range(pr)])
+    assert (got == sa).all()
+
+
+def test_psac_cli_files_and_text_blocks(tmp_path):
+    t = G.random_bytes(777, 3)
+    p = str(tmp_path / "text.bin")
+    t.tofile(p)
+    blocks = [fileio.file_block_decompose(p, r, 4) for r in range(4)]
+    assert [b.size for b in blocks] == [api.blk_dist(777, 4, r)[1] for r in range(4)]
+    assert (np.concatenate(blocks) == t).all()
+    sa32 = np.arange(10, dtype=np.uint32)[::-1].copy()
+    fileio.write_psac_cli_output(str(tmp_path / "out"), sa32, lcp=np.zeros(10, np.uint32))
+    assert (np.fromfile(str(tmp_path / "out.sa64"), dtype="<u8") == sa32).all()
+    assert os.path.getsize(str(tmp_path / "out.lcp64")) == 80
+
+
+def test_alphabet_file_of_all_256_bytes(tmp_path):
+    t = G.random_bytes_config4(70000, 1)
+    f = str(tmp_path / "a.alpha")
+    fileio.write_alphabet(f, t)
+    assert os.path.getsize(f) == 256
+    lut, sigma = fileio.read_alphabet(f)
+    elut, esigma, _ = O.alphabet(t)
+    assert sigma == esigma == 256 and (lut == elut).all() and lut[255] == 0  # the reference's 8-bit overflow
+
+
+def test_size_mismatch_is_an_error(tmp_path):
+    base = str(tmp_path / "bad")
+    fileio.write_dist_int_array(base + ".sa", np.arange(5, dtype=np.uint64))
+    fileio.write_dist_int_array(base + ".lcp", np.arange(4, dtype=np.uint64))
+    with pytest.raises(api.PsacError):
+        fileio.read_suffix_array(base, 8, with_lcp=True)
