@@ -193,3 +193,43 @@ def test_port_matches_live_reference():
         ref = O.ref_construct(text, 4, False, 0, L != 4, L)
         r = O.construct_arr(text, L, 32)
         assert (r["sa"] == ref["sa"]).all() and (r["isa"] == ref["isa"]).all()
+
+
+# ------------------------------------------------------------------------------------------- randomised pinning of the port
+@pytest.mark.skipif(not O.have_ref(), reason="oracle/_ref/libpsacref.so not built")
+def test_port_vs_unmodified_reference_randomised():
+    """hypothesis-style sweep (own seeded generator, so the cases are reproducible): small alphabets force deep buckets,
+    tiny texts hit the k clamp (kmer.hpp:34-38), periodic texts hit every doubling round"""
+    rng = np.random.default_rng(20261017)
+    cases = 0
+    for _ in range(60):
+        n = int(rng.choice([1, 2, 3, 5, 17, 64, 257, 1000, 4099]))
+        sigma = int(rng.choice([1, 2, 3, 4, 20, 255]))
+        t = rng.integers(0, sigma, size=n).astype(np.uint8)
+        if rng.random() < 0.3 and n > 8:
+            period = int(rng.integers(1, 7))
+            t = np.resize(t[:period], n).astype(np.uint8)
+        if n < 3:
+            continue  # the reference's k == 1 raw-character path differs on LCP for n <= 2 (documented in tests/test_gpu_parity.py)
+        for ib in (4, 8):
+            ref = O.ref_construct(t, ib, True)
+            port = O.construct(t, ib * 8, 0, True)
+            assert (port["sa"] == ref["sa"].astype(np.uint64)).all(), (n, sigma, ib)
+            assert (port["isa"] == ref["isa"].astype(np.uint64)).all(), (n, sigma, ib)
+            assert (port["lcp"] == ref["lcp"].astype(np.uint64)).all(), (n, sigma, ib)
+            cases += 1
+    assert cases >= 80
+
+
+@pytest.mark.skipif(not O.have_ref(), reason="oracle/_ref/libpsacref.so not built")
+def test_ansv_port_vs_unmodified_reference_randomised():
+    rng = np.random.default_rng(7)
+    nonsv = 2 ** 64 - 1
+    for n in (1, 2, 13, 137, 1000):
+        for hi in (2, 5, 100):
+            v = rng.integers(0, hi, size=n).astype(np.uint64)
+            for lt in range(3):
+                for rt in range(3):
+                    l, r = O.ansv(v, lt, rt, nonsv)
+                    rl, rr = O.ref_ansv(v, lt, rt, nonsv)
+                    assert (l == rl).all() and (r == rr).all(), (n, hi, lt, rt)
