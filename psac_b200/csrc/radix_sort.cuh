@@ -640,6 +640,16 @@ struct SortTuning {
 };
 constexpr int MIN_TILE = 256 * 8;  // smallest tile any configuration uses (sizes the per-tile workspace)
 
+// function attributes are per device: true the first time a call site runs on the current device
+static inline bool first_use_on_device(bool (&seen)[64]) {
+    int d = 0;
+    cudaGetDevice(&d);
+    d &= 63;
+    if (seen[d]) return false;
+    seen[d] = true;
+    return true;
+}
+
 struct RadixWorkspace {
     u64* gbase = nullptr;      // [RADIX] digit bases of the pass in flight
     void* tiles = nullptr;     // per-tile counts (u32 [tiles][RADIX]) followed by the chunk totals (u64 [chunks][RADIX])
@@ -659,11 +669,8 @@ void launch_pass_cfg(const RadixWorkspace& ws, const Src& src, typename Src::Out
     u32* counts = reinterpret_cast<u32*>(ws.tiles);
     u64* chunk_tot = reinterpret_cast<u64*>(reinterpret_cast<char*>(ws.tiles) + counts_bytes);
     auto kern = radix_scatter_kernel<Src, ValT, THREADS, ITEMS, HAS_AUX, MINB>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        PSAC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
-        attr_set = true;
-    }
+    static bool seen[64] = {};
+    if (first_use_on_device(seen)) PSAC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
     if constexpr (Src::FROM_TEXT)
         text_tile_hist_kernel<Src, THREADS, ITEMS><<<(unsigned)tiles, THREADS, 0, stream>>>(src, n, counts);
     else
@@ -776,11 +783,8 @@ int radix_sort_suffixes_msd(const RadixWorkspace& ws, const SegWorkspace& sw, co
         u32* counts = reinterpret_cast<u32*>(ws.tiles);
         u64* chunk_tot = reinterpret_cast<u64*>(reinterpret_cast<char*>(ws.tiles) + counts_bytes);
         auto kern = radix_scatter_kernel<Src, IdxT, TT::THREADS, TT::ITEMS, true, TT::MINB>;
-        static bool attr_set = false;
-        if (!attr_set) {
-            PSAC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
-            attr_set = true;
-        }
+        static bool seen[64] = {};
+        if (first_use_on_device(seen)) PSAC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
         const bool single = plan.npass == 1;
         text_tile_hist_kernel<Src, TT::THREADS, TT::ITEMS><<<(unsigned)tiles, TT::THREADS, 0, stream>>>(src, n, counts);
         tile_scan_chunks_kernel<<<(unsigned)chunks, RADIX, 0, stream>>>(counts, tiles, chunk_tot);
@@ -803,11 +807,8 @@ int radix_sort_suffixes_msd(const RadixWorkspace& ws, const SegWorkspace& sw, co
     using Src = ArraySrc<u32, IdxT>;
     using Cfg = PassCfg<Src, IdxT, T::THREADS, T::ITEMS, false>;
     auto kern = radix_scatter_seg_kernel<Src, IdxT, T::THREADS, T::ITEMS, T::MINB>;
-    static bool attr_set2 = false;
-    if (!attr_set2) {
-        PSAC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
-        attr_set2 = true;
-    }
+    static bool seen2[64] = {};
+    if (first_use_on_device(seen2)) PSAC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
     const size_t chunks = div_up(rows, (size_t)SCAN_CHUNK);
     const size_t counts_bytes = align_up(rows * RADIX * sizeof(u32), 256);
     if (counts_bytes + chunks * RADIX * sizeof(u64) > ws.tiles_bytes) throw std::string("radix pass: tile workspace too small");
