@@ -55,7 +55,7 @@ typedef struct psacb200_stats {
     float ms_sort_pass_avg;   /* average duration of one radix digit pass of the first sort, pass 1 excluded */
     float ms_isa;             /* SA -> ISA permutation of the first round (partition pass + windowed scatter) */
     float ms_sort_pass1;      /* digit pass 1 of the first sort (keys read from the packed text) */
-    float reserved_f[1];
+    float ms_scatter_avg;     /* average duration of the scatter kernel of one segmented digit pass (32-bit carried keys) */
 } psacb200_stats;
 
 /* ---- lifetime ---------------------------------------------------------------------------------------------- */

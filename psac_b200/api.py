@@ -50,7 +50,7 @@ class Stats(C.Structure):
         ("ms_sort_pass_avg", C.c_float),
         ("ms_isa", C.c_float),
         ("ms_sort_pass1", C.c_float),
-        ("reserved_f", C.c_float * 1),
+        ("ms_scatter_avg", C.c_float),
     ]
 
     def as_dict(self):

@@ -85,6 +85,8 @@ struct psacb200_engine {
     u64* h_pinned = nullptr;  // 512 u64 of pinned host memory for small read-backs
     cudaEvent_t ev_begin[PH_COUNT], ev_end[PH_COUNT];
     bool ev_used[PH_COUNT];
+    cudaEvent_t ev_scatter[2 * MAX_PASSES];  // brackets of the scatter kernels of the segmented digit passes
+    int scatter_passes = 0;
     psacb200_stats stats;
 
     // layout of `small`
@@ -303,7 +305,8 @@ void construct_core(psacb200_engine* e, u64 n, int index_bytes, unsigned flags, 
         sw.tile_info = reinterpret_cast<u32*>(sw.segbase + RADIX * RADIX);
         SA = ext_sa ? reinterpret_cast<IdxT*>(sa_out) : e->vals2.as<IdxT>();
         x = radix_sort_suffixes_msd<IdxT>(e->radix_ws(), sw, e->packed.as<u64>(), n, lbits, (int)C, kbuf, vbuf, SA, st, &plan_used, &sort_launches,
-                                          e->ev_end[PH_PASS1]);
+                                          e->ev_end[PH_PASS1], e->ev_scatter);
+        e->scatter_passes = plan_used.npass - 1;
         seg_dense = sw.seg_dense;
     } else {
         const int fin = (plan.npass - 1) & 1;  // buffer index the last pass writes
@@ -557,6 +560,21 @@ void fill_phase_stats(psacb200_engine* e) {
         if (e->ev_used[PH_SORT] && cudaEventElapsedTime(&t1, e->ev_begin[PH_SORT], e->ev_end[PH_PASS1]) == cudaSuccess) S.ms_sort_pass1 = t1;
         else cudaGetLastError();
     }
+    S.ms_scatter_avg = 0.f;
+    if (e->scatter_passes > 0) {
+        float sum = 0.f;
+        int cnt = 0;
+        for (int p = 0; p < e->scatter_passes && p < MAX_PASSES; ++p) {
+            float t = 0.f;
+            if (cudaEventElapsedTime(&t, e->ev_scatter[2 * p], e->ev_scatter[2 * p + 1]) == cudaSuccess) {
+                sum += t;
+                ++cnt;
+            } else {
+                cudaGetLastError();
+            }
+        }
+        if (cnt) S.ms_scatter_avg = sum / (float)cnt;
+    }
     S.ms_hist = e->ms(PH_HIST);
     S.ms_sort = e->ms(PH_SORT);
     S.ms_resolve = e->ms(PH_RESOLVE);
@@ -584,6 +602,7 @@ int construct_entry(psacb200_engine* e, const u8* text, bool text_is_host, size_
         PSAC_CUDA(cudaSetDevice(e->device));
         memset(&e->stats, 0, sizeof(e->stats));
         memset(e->ev_used, 0, sizeof(e->ev_used));
+        e->scatter_passes = 0;
         e->stats.n = n;
         if (n == 0) return PSACB200_OK;
         e->begin(PH_TOTAL);
@@ -731,6 +750,7 @@ int psacb200_create(int device, psacb200_engine** out) {
             PSAC_CUDA(cudaEventCreate(&e->ev_end[i]));
             e->ev_used[i] = false;
         }
+        for (int i = 0; i < 2 * MAX_PASSES; ++i) PSAC_CUDA(cudaEventCreate(&e->ev_scatter[i]));
         memset(&e->stats, 0, sizeof(e->stats));
         e->small.reserve(psacb200_engine::small_bytes(), &e->device_bytes);
         // hardware self-test of the ranking assumption of the radix passes (radix_sort.cuh): refuse to run if it fails
@@ -763,6 +783,7 @@ void psacb200_destroy(psacb200_engine* e) {
         cudaEventDestroy(e->ev_begin[i]);
         cudaEventDestroy(e->ev_end[i]);
     }
+    for (int i = 0; i < 2 * MAX_PASSES; ++i) cudaEventDestroy(e->ev_scatter[i]);
     if (e->peer_map) {
         PeerMap* pm = reinterpret_cast<PeerMap*>(e->peer_map);
         for (int r = 0; r < 16; ++r)
@@ -958,6 +979,7 @@ int psacb200_construct_sharded(psacb200_engine* e, const uint8_t* d_text_local, 
         if (sharded) {
             memset(&e->stats, 0, sizeof(e->stats));
             memset(e->ev_used, 0, sizeof(e->ev_used));
+            e->scatter_passes = 0;
             e->stats.n = n;
             e->begin(PH_TOTAL);
             sharded = construct_sharded_core(e, C, d_text_local, n_local, n, index_bytes, flags, k, d_sa_local, d_isa_local, d_lcp_local);

@@ -757,7 +757,8 @@ struct SegWorkspace {
 template <typename IdxT>
 int radix_sort_suffixes_msd(const RadixWorkspace& ws, const SegWorkspace& sw, const u64* text_stream, size_t n, int lbits, int key_chars, u32* const kbuf[2],
                             IdxT* const vbuf[2], IdxT* vfinal, cudaStream_t stream, RadixPlan* plan_out, uint64_t* launches,
-                            cudaEvent_t ev_pass1_done = nullptr) {
+                            cudaEvent_t ev_pass1_done = nullptr, cudaEvent_t* ev_scatter = nullptr) {
+    // ev_scatter (optional, 2 * MAX_PASSES events): [2p] / [2p + 1] bracket the scatter kernel of segmented pass p
     using T = SortTuning<u32, IdxT, false>;
     constexpr int TILE = T::THREADS * T::ITEMS;
     const int kbits = key_chars * lbits;
@@ -822,7 +823,9 @@ int radix_sort_suffixes_msd(const RadixWorkspace& ws, const SegWorkspace& sw, co
         tile_scan_chunks_kernel<<<(unsigned)chunks, RADIX, 0, stream>>>(counts, rows, chunk_tot);
         tile_scan_top_kernel<<<1, RADIX, 0, stream>>>(chunk_tot, chunks, nullptr, nullptr, nullptr, 1);
         seg_base_kernel<TILE><<<RADIX, RADIX, 0, stream>>>(counts, chunk_tot, sw.seg_dense, sw.seg_pad, last ? 1 : 0, sw.segbase);
+        if (ev_scatter) cudaEventRecord(ev_scatter[2 * p], stream);
         kern<<<(unsigned)rows, T::THREADS, Cfg::SMEM, stream>>>(src, kbuf[1 - cur], last ? vfinal : vbuf[1 - cur], sw.tile_info, sw.segbase, chunk_tot, counts);
+        if (ev_scatter) cudaEventRecord(ev_scatter[2 * p + 1], stream);
         nl += 5;
         cur = 1 - cur;
     }
