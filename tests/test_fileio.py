@@ -66,3 +66,31 @@ def test_size_mismatch_is_an_error(tmp_path):
     fileio.write_dist_int_array(base + ".lcp", np.arange(4, dtype=np.uint64))
     with pytest.raises(api.PsacError):
         fileio.read_suffix_array(base, 8, with_lcp=True)
+
+
+def test_cli_fails_loudly_without_gpu(tmp_path):
+    # the psac-like command line tool (reference src/psac.cpp): flags parse, and without a GPU it reports the library's
+    # error instead of computing anything on the CPU
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "psac_b200.cli", "-r", "1000", "-s", "3", "-l", "-c", "-o", str(tmp_path / "o")], cwd=root,
+                       capture_output=True, text=True)
+    assert r.returncode == 2 and "no CUDA device" in r.stderr
+    assert not os.path.exists(str(tmp_path / "o.sa64"))
+
+
+def test_cli_check_function_detects_errors():
+    from psac_b200 import cli
+    t = G.random_dna(3000, 4)
+    exp = O.construct(t, 64, 0, True)
+    assert cli._check(t, exp["sa"], exp["isa"], exp["lcp"]) is None
+    bad = exp["sa"].copy()
+    bad[[5, 6]] = bad[[6, 5]]
+    assert cli._check(t, bad, exp["isa"], None) is not None
+    lcp = exp["lcp"].copy()
+    lcp[1:] += 1
+    assert "LCP" in cli._check(t, exp["sa"], exp["isa"], lcp)
