@@ -166,7 +166,7 @@ struct PassCfg {
 };
 
 template <class Cfg, class Src, typename ValT, bool FULL>
-__device__ __forceinline__ void onesweep_tile(unsigned char* smem_raw, const Src& src, typename Src::Out* __restrict__ kout, ValT* __restrict__ vout,
+__device__ __forceinline__ void scatter_tile(unsigned char* smem_raw, const Src& src, typename Src::Out* __restrict__ kout, ValT* __restrict__ vout,
                                               u8* __restrict__ aout, const size_t base, const int valid, const u64* __restrict__ gbase,
                                               const u64* __restrict__ chunk_base, const u32* __restrict__ tile_excl) {
     using Stage = typename Src::Stage;
@@ -363,9 +363,9 @@ __global__ void __launch_bounds__(THREADS, MINB)
     const u64* cb = chunk_base + (tile / SCAN_CHUNK) * RADIX;
     const u32* te = tile_excl + tile * RADIX;
     if (n - base >= (size_t)TILE)
-        onesweep_tile<Cfg, Src, ValT, true>(smem_raw, src, kout, vout, aout, base, TILE, gbase, cb, te);
+        scatter_tile<Cfg, Src, ValT, true>(smem_raw, src, kout, vout, aout, base, TILE, gbase, cb, te);
     else
-        onesweep_tile<Cfg, Src, ValT, false>(smem_raw, src, kout, vout, aout, base, (int)(n - base), gbase, cb, te);
+        scatter_tile<Cfg, Src, ValT, false>(smem_raw, src, kout, vout, aout, base, (int)(n - base), gbase, cb, te);
 }
 
 // per-tile digit histogram of a pass (same tile geometry as the scatter kernel): counts[tile][256]
@@ -569,13 +569,13 @@ __global__ void __launch_bounds__(THREADS, MINB)
     const u64* cb = chunk_base + (tile / SCAN_CHUNK) * RADIX;
     const u32* te = tile_excl + tile * RADIX;
     if (valid == TILE)
-        onesweep_tile<Cfg, Src, ValT, true>(smem_raw, src, kout, vout, nullptr, base, TILE, gb, cb, te);
+        scatter_tile<Cfg, Src, ValT, true>(smem_raw, src, kout, vout, nullptr, base, TILE, gb, cb, te);
     else
-        onesweep_tile<Cfg, Src, ValT, false>(smem_raw, src, kout, vout, nullptr, base, valid, gb, cb, te);
+        scatter_tile<Cfg, Src, ValT, false>(smem_raw, src, kout, vout, nullptr, base, valid, gb, cb, te);
 }
 
 // ------------------------------------------------------------------ hardware self-test of the ranking assumption
-// Replays the ranking loop of onesweep_tile (ITEMS back-to-back ATOMS.ADD per lane on a per-warp table, some lanes
+// Replays the ranking loop of scatter_tile (ITEMS back-to-back ATOMS.ADD per lane on a per-warp table, some lanes
 // inactive) and compares every returned value with the stable rank computed from ballots.  Returns the number of
 // mismatches in *bad; the engine refuses to run when it is not zero.
 template <int ITEMS>
