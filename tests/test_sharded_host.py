@@ -150,7 +150,7 @@ def _a2a_gloo(ins, outs, rank, world):
         r.wait()
 
 
-@pytest.mark.parametrize("world,n", [(2, 60000), (3, 50021)])
+@pytest.mark.parametrize("world,n", [(2, 60000), (3, 50021), (4, 40009)])
 def test_exchange_plans_over_gloo(world, n):
     port = 29650 + world
     mgr = mp.Manager()
