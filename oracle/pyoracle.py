@@ -4,6 +4,8 @@
 * ``_ref/libpsacref.so``: the UNMODIFIED reference compiled at np=1 against the MPI shim
                           (oracle/ref_driver.cpp, kind "reference").  Built only where
                           /root/reference exists; the prebuilt file travels to the GPU box.
+* ``_ref/libdivsufsort64.so``: the reference's vendored libdivsufsort (second, independent oracle for SA:
+                          induced sorting, orders by unsigned byte).
 
 All arrays are numpy; indices are uint64 in the port, uint32/uint64 (``index_bytes``) in the reference.
 """
@@ -16,6 +18,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 PORT_SO = os.path.join(HERE, "liboracle.so")
 REF_SO = os.path.join(HERE, "_ref", "libpsacref.so")
+DSS_SO = os.path.join(HERE, "_ref", "libdivsufsort64.so")
 
 _port = None
 _ref = None
@@ -26,7 +29,7 @@ def build(verbose=False):
     out = None if verbose else subprocess.DEVNULL
     subprocess.check_call(["make", "-s", "-f", os.path.join(HERE, "Makefile"), PORT_SO], stdout=out)
     if os.path.isdir("/root/reference/include"):
-        subprocess.check_call(["make", "-s", "-f", os.path.join(HERE, "Makefile"), REF_SO], stdout=out)
+        subprocess.check_call(["make", "-s", "-f", os.path.join(HERE, "Makefile"), REF_SO, DSS_SO], stdout=out)
 
 
 def _vp(a):
@@ -303,3 +306,37 @@ def ref_rand_dna(n, seed):
     out = np.zeros(n, np.uint8)
     ref().psacref_rand_dna(C.c_size_t(n), C.c_int(seed), _vp(out))
     return out
+
+
+# ------------------------------------------------------------- libdivsufsort (second, independent oracle)
+_dss = None
+
+
+def have_dss():
+    return os.path.exists(DSS_SO)
+
+
+def dss_sa(text):
+    """Suffix array by the reference's vendored libdivsufsort (divsufsort64; reference include/divsufsort_wrapper.hpp:54-71).
+    Byte order: equals psac's SA when at most 255 distinct byte values occur."""
+    global _dss
+    if _dss is None:
+        if not have_dss():
+            raise RuntimeError("oracle/_ref/libdivsufsort64.so missing (build it where /root/reference exists)")
+        _dss = C.CDLL(DSS_SO)
+    t = _text(text)
+    sa = np.zeros(t.size, np.int64)
+    rc = _dss.divsufsort64(_vp(t), _vp(sa), C.c_int64(t.size))
+    if rc != 0:
+        raise RuntimeError("divsufsort64 rc=%d" % rc)
+    return sa.astype(np.uint64)
+
+
+def dss_check(text, sa):
+    """libdivsufsort's own checker (sufcheck64; divsufsort_wrapper.hpp:90-109): 0 = valid suffix array"""
+    global _dss
+    if _dss is None:
+        dss_sa(b"a")
+    t = _text(text)
+    s = np.ascontiguousarray(sa, np.int64)
+    return int(_dss.sufcheck64(_vp(t), _vp(s), C.c_int64(t.size), C.c_int32(0)))

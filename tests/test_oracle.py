@@ -233,3 +233,25 @@ def test_ansv_port_vs_unmodified_reference_randomised():
                     l, r = O.ansv(v, lt, rt, nonsv)
                     rl, rr = O.ref_ansv(v, lt, rt, nonsv)
                     assert (l == rl).all() and (r == rr).all(), (n, hi, lt, rt)
+
+
+# ------------------------------------------------------------------------------------------- second, independent oracle
+@pytest.mark.skipif(not O.have_dss(), reason="oracle/_ref/libdivsufsort64.so not built")
+def test_port_and_reference_agree_with_libdivsufsort():
+    """The reference's own tests compare element-wise with divsufsort (test/test_psac.cpp:31-98, 131-176).  Induced sorting
+    shares nothing with prefix doubling, so agreement pins the SA of port and reference independently."""
+    texts = [np.frombuffer(b"mississippi", np.uint8), G.random_dna(130370, 7), G.random_dna(66763, 23), G.repeats_text(15000, 1),
+             G.periodic_text(b"abc", 14681), np.minimum(G.random_bytes(50000, 4), 254).astype(np.uint8), np.zeros(777, np.uint8)]
+    for t in texts:
+        dss = O.dss_sa(t)
+        assert O.dss_check(t, dss) == 0
+        port = O.construct(t, 64, 0, False)
+        assert (port["sa"] == dss).all(), t.size
+        if O.have_ref():
+            assert (O.ref_construct(t, 8, False)["sa"].astype(np.uint64) == dss).all(), t.size
+    # all 256 byte values: psac differs from divsufsort exactly by the 0xFF -> code 0 overflow (SURVEY section 0.3):
+    # it equals divsufsort of the text remapped 0xFF -> 0x00, c -> c + 1
+    t = G.random_bytes_config4(60000, 4)
+    remapped = (t.astype(np.uint16) + 1).astype(np.uint8)  # 0xFF + 1 wraps to 0
+    assert (O.construct(t, 64, 0, False)["sa"] == O.dss_sa(remapped)).all()
+    assert not (O.construct(t, 64, 0, False)["sa"] == O.dss_sa(t)).all()
