@@ -66,6 +66,10 @@ const char* psacb200_last_error(void);
 /* Number of CUDA kernel launches issued by this engine since creation (bench.py's gpu_launches). */
 uint64_t psacb200_launch_count(const psacb200_engine* e);
 int psacb200_get_stats(const psacb200_engine* e, psacb200_stats* out);
+/* Ranking mode of the radix digit passes: 0 = one shared-memory atomic per key (relies on the lanes of one ATOMS instruction
+ * being applied in lane order, verified on the device at every psacb200_create), 1 = match.any ranking (documented warp
+ * primitives only; selected automatically when that self-test fails, or with the environment variable PSACB200_SAFE_RANK=1). */
+int psacb200_rank_mode(const psacb200_engine* e, uint64_t* selftest_mismatches);
 /* The engine's cudaStream_t (as void*), so a caller can bracket calls with its own CUDA events on that stream. */
 void* psacb200_stream(const psacb200_engine* e);
 /* Pre-size the device buffers for texts up to n characters (optional; avoids cudaMalloc inside a timed call). */
@@ -113,6 +117,33 @@ int psacb200_comm_init(psacb200_engine* e, const uint8_t id[128], int rank, int 
  * Outputs (DEVICE, n_local elements of index_bytes each): this rank's blocks of SA, ISA (may be NULL) and LCP. */
 int psacb200_construct_sharded(psacb200_engine* e, const uint8_t* d_text_local, size_t n_local, size_t n_global, int index_bytes, unsigned flags,
                                unsigned k, void* d_sa_local, void* d_isa_local, void* d_lcp_local);
+/* Collective, optional: releases the peer-visible memory of the sharded construction in an ordered way (every rank closes its
+ * mappings of the peers' memory before any rank frees its own).  Call on every rank before psacb200_destroy. */
+int psacb200_comm_finalize(psacb200_engine* e);
+
+/* ---- device-side certificate of a result (reference d_check_sa, include/check_suffix_array.hpp:190-194, 206-267, plus the LCP
+ * part of gl_check_correct / check_lcp, :151-185) -------------------------------------------------------------------- */
+typedef struct psacb200_check_report {
+    uint64_t n;
+    uint64_t bad_range;   /* positions i with SA[i] >= n */
+    uint64_t bad_inverse; /* positions with ISA[SA[i]] != i          (conditions 1 + 2: SA is a permutation, ISA its inverse) */
+    uint64_t bad_order;   /* positions violating S[SA[i-1]] < S[SA[i]] or (equal and ISA[SA[i-1]+1] < ISA[SA[i]+1])   (3 + 4) */
+    uint64_t bad_lcp;     /* positions with LCP[i] != lcp(SA[i-1], SA[i]) (direct comparison on the text), LCP[0] != 0 */
+    uint64_t first_bad;   /* smallest failing SA position, ~0 when the result is correct */
+    float ms;             /* device time of the check */
+    uint32_t checked_lcp;
+} psacb200_check_report;
+/* All pointers are DEVICE buffers; d_lcp may be NULL (SA / ISA only).  Returns PSACB200_OK when the check RAN; the
+ * verdict is in the report (all four counters zero = correct). */
+int psacb200_check_device(psacb200_engine* e, const uint8_t* d_text, size_t n, int index_bytes, const void* d_sa, const void* d_isa, const void* d_lcp,
+                          psacb200_check_report* report);
+/* Same from HOST arrays (copies them to the device first). */
+int psacb200_check(psacb200_engine* e, const uint8_t* text, size_t n, int index_bytes, const void* sa, const void* isa, const void* lcp,
+                   psacb200_check_report* report);
+/* Collective over the ranks of psacb200_comm_init: every rank passes its blocks (DEVICE); the report is the same on all ranks. */
+int psacb200_check_sharded(psacb200_engine* e, const uint8_t* d_text_local, size_t n_local, size_t n_global, int index_bytes, const void* d_sa_local,
+                           const void* d_isa_local, const void* d_lcp_local, psacb200_check_report* report);
+
 /* Host-side plans of the sharded construction (no GPU needed; used by the CPU tests): mxx::blk_dist, and the splitters
  * over a key-prefix histogram (rank r sorts the bins [first[r], first[r+1]); first has p+1 entries, count p). */
 void psacb200_blk_dist(uint64_t n, int p, int r, uint64_t* start, uint64_t* size);

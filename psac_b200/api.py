@@ -57,6 +57,21 @@ class Stats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_ if not k.startswith("reserved")}
 
 
+class CheckReport(C.Structure):
+    """psacb200_check_report: verdict of the device-side certificate (reference d_check_sa + check_lcp)."""
+    _fields_ = [("n", C.c_uint64), ("bad_range", C.c_uint64), ("bad_inverse", C.c_uint64), ("bad_order", C.c_uint64), ("bad_lcp", C.c_uint64),
+                ("first_bad", C.c_uint64), ("ms", C.c_float), ("checked_lcp", C.c_uint32)]
+
+    def as_dict(self):
+        d = {k: getattr(self, k) for k, _ in self._fields_}
+        d["ok"] = self.ok
+        return d
+
+    @property
+    def ok(self):
+        return self.bad_range == 0 and self.bad_inverse == 0 and self.bad_order == 0 and self.bad_lcp == 0
+
+
 def lib():
     """Load libpsacb200.so (built in-tree by ``make`` / ``__graft_entry__.build``).  Raises if it is missing."""
     global _lib
@@ -87,6 +102,12 @@ def lib():
                                                  C.c_void_p]
         L.psacb200_ansv.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p]
         L.psacb200_suffix_tree.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+        L.psacb200_comm_finalize.argtypes = [C.c_void_p]
+        L.psacb200_rank_mode.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+        chk = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(CheckReport)]
+        L.psacb200_check_device.argtypes = chk
+        L.psacb200_check.argtypes = chk
+        L.psacb200_check_sharded.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(CheckReport)]
         L.psacb200_blk_dist.argtypes = [C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.psacb200_blk_dist.restype = None
         L.psacb200_choose_splitters.argtypes = [C.c_void_p, C.c_size_t, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]
@@ -192,6 +213,33 @@ class Engine:
         """Collective; all pointers are DEVICE buffers of this rank's blocks."""
         _check(lib().psacb200_construct_sharded(self._h, _ptr(text_ptr), n_local, n_global, index_bytes, flags, k, _ptr(sa_ptr), _ptr(isa_ptr),
                                                 _ptr(lcp_ptr)))
+
+    def comm_finalize(self):
+        """Collective: ordered release of the peer-visible memory (call on every rank before close())."""
+        _check(lib().psacb200_comm_finalize(self._h))
+
+    # ---- device-side certificate (reference d_check_sa, check_suffix_array.hpp:206-267, + check_lcp)
+    def check(self, text, sa, isa, lcp=None):
+        """Host arrays in; returns the report as a dict (``ok`` = all conditions hold)."""
+        t = _as_text(text)
+        sa = np.ascontiguousarray(sa)
+        assert sa.dtype in (np.uint32, np.uint64)
+        isa = np.ascontiguousarray(isa, sa.dtype)
+        lcp = None if lcp is None else np.ascontiguousarray(lcp, sa.dtype)
+        rep = CheckReport()
+        _check(lib().psacb200_check(self._h, _ptr(t), t.size, sa.dtype.itemsize, _ptr(sa), _ptr(isa), _ptr(lcp), C.byref(rep)))
+        return rep.as_dict()
+
+    def check_device_ptr(self, text_ptr, n, index_bytes, sa_ptr, isa_ptr, lcp_ptr=None):
+        rep = CheckReport()
+        _check(lib().psacb200_check_device(self._h, _ptr(text_ptr), n, index_bytes, _ptr(sa_ptr), _ptr(isa_ptr), _ptr(lcp_ptr), C.byref(rep)))
+        return rep.as_dict()
+
+    def check_sharded_ptr(self, text_ptr, n_local, n_global, index_bytes, sa_ptr, isa_ptr, lcp_ptr=None):
+        """Collective; DEVICE blocks of this rank."""
+        rep = CheckReport()
+        _check(lib().psacb200_check_sharded(self._h, _ptr(text_ptr), n_local, n_global, index_bytes, _ptr(sa_ptr), _ptr(isa_ptr), _ptr(lcp_ptr), C.byref(rep)))
+        return rep.as_dict()
 
     # ---- ANSV / suffix tree
     NEAREST_SM, NEAREST_EQ, FURTHEST_EQ = 0, 1, 2

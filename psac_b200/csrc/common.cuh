@@ -93,6 +93,43 @@ __device__ __forceinline__ u64 stream_extract(const u64* __restrict__ stream, u6
     return stream_bits(stream, i * (u64)lbits, nbits);
 }
 
+// ---------------------------------------------------------------- block distribution on the device
+// mxx::blk_dist (reference ext/mxx/include/mxx/partition.hpp:283-331): n elements over p ranks, the first n % p ranks
+// hold one element more.  owner() divides by multiplication with a double reciprocal plus one correction step (exact:
+// the quotient fits 4 bits, the operands 40).
+struct BlkDiv {
+    u64 cut, base1, base;  // cut = rem * (base + 1); base1 = base + 1; base >= 1
+    u32 rem;
+    double inv_base1, inv_base;
+    __host__ static BlkDiv make(u64 n, int p) {
+        BlkDiv d;
+        const u64 b = n / (u64)p;
+        d.rem = (u32)(n % (u64)p);
+        d.base = b ? b : 1;
+        d.base1 = b + 1;
+        d.cut = (u64)d.rem * (b + 1);
+        d.inv_base1 = 1.0 / (double)d.base1;
+        d.inv_base = 1.0 / (double)d.base;
+        return d;
+    }
+    __device__ __forceinline__ static u64 divide(u64 x, u64 d, double inv) {
+        u64 q = (u64)__double2ull_rz((double)x * inv);
+        if (q * d > x) --q;
+        if ((q + 1) * d <= x) ++q;
+        return q;
+    }
+    __device__ __forceinline__ u32 owner(u64 g, u64* local) const {
+        if (g < cut) {
+            const u64 q = divide(g, base1, inv_base1);
+            *local = g - q * base1;
+            return (u32)q;
+        }
+        const u64 q = divide(g - cut, base, inv_base);
+        *local = g - cut - q * base;
+        return rem + (u32)q;
+    }
+};
+
 // ---------------------------------------------------------------- decoupled look-back channel
 // One u64 per tile: [63:10] payload (54 bits), [9:2] epoch, [1:0] state.  The epoch makes entries of a
 // previous use of the same buffer read as "not yet written" without a memset between uses.

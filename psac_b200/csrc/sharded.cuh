@@ -23,6 +23,7 @@
 #pragma once
 #include <dlfcn.h>
 #include <nccl.h>
+#include <unistd.h>
 
 namespace {
 
@@ -329,77 +330,148 @@ struct ShardComm {
 
 namespace {
 
-// CUDA-IPC mapping of every rank's two receive buffers of the SA -> ISA exchange, so that the owner partition kernel
-// can store straight into its peers' HBM over NVLink (kernel fused with its collective).  Handles are all-gathered on
-// every call (128 bytes per rank) and re-opened only when a buffer was re-allocated.  Returns false -- on every rank --
-// if any rank could not map its peers; the caller then uses the NCCL all-to-all-v path.
-struct PeerMap {
-    cudaIpcMemHandle_t handle[16][2];
-    void* mapped[16][2];
-    bool open[16][2];
-    PeerMap() {
-        memset(handle, 0, sizeof(handle));
-        memset(mapped, 0, sizeof(mapped));
-        memset(open, 0, sizeof(open));
+// Peer-visible arena: ONE cudaMalloc'd region per rank, mapped into every peer (CUDA IPC between processes, plain peer
+// access between the engines of one process), so that kernels can load and store straight in their peers' HBM over
+// NVLink: the exchange steps are fused into the kernels that produce / consume the data.  Everything a peer may touch
+// (exchange receive buffers, the ISA block during the later rounds and the checker) is sub-allocated from it at offsets
+// that are identical on all ranks.  The region is never freed while a peer may hold a mapping: growing it is a
+// collective step (every rank closes its mappings, barrier, free + malloc, handles exchanged again), decided from
+// all-reduced sizes so that all ranks take it together; psacb200_comm_finalize releases it the same way.
+struct PeerArena {
+    u8* base = nullptr;
+    size_t bytes = 0;
+    u8* peer[16];
+    bool ipc_open[16];
+    int world = 0;
+    bool usable = false;
+    PeerArena() {
+        memset(peer, 0, sizeof(peer));
+        memset(ipc_open, 0, sizeof(ipc_open));
     }
 };
 
-bool map_peer_buffers(psacb200_engine* e, const ShardComm& C, void* mine0, void* mine1, PeerMap& pm, u64* out0[16], u64* out1[16]) {
+// host-visible barrier: a one-word all-reduce, then the stream is drained
+void host_barrier(psacb200_engine* e, const ShardComm& C) {
+    u64* d = e->shard_meta() + 57;
+    PSAC_NCCL(g_nccl.AllReduce(d, d, 1, ncclUint64, ncclSum, C.comm, e->stream));
+    PSAC_CUDA(cudaStreamSynchronize(e->stream));
+}
+
+void arena_close_peers(PeerArena& A) {
+    for (int r = 0; r < 16; ++r) {
+        if (A.ipc_open[r]) cudaIpcCloseMemHandle(A.peer[r]);
+        A.ipc_open[r] = false;
+        A.peer[r] = nullptr;
+    }
+    A.usable = false;
+}
+
+// Collective.  Makes sure every rank owns an arena of at least `need` bytes that all peers have mapped.  Returns false --
+// on every rank -- when peer mapping is unavailable (then the callers use their NCCL paths).
+bool arena_ensure(psacb200_engine* e, const ShardComm& C, size_t need) {
+    if (e->peer_map == nullptr) return false;  // PSACB200_NO_PEER
+    PeerArena& A = *reinterpret_cast<PeerArena*>(e->peer_map);
     cudaStream_t st = e->stream;
     const int p = C.world, me = C.rank;
+    // agree on max(need) and min(current size)
+    u64* d_w = e->shard_meta() + 58;  // 2 words
+    e->h_pinned[40] = (u64)need;
+    e->h_pinned[41] = ~(u64)((A.usable && A.world == p) ? A.bytes : 0);
+    PSAC_CUDA(cudaMemcpyAsync(d_w, e->h_pinned + 40, 2 * sizeof(u64), cudaMemcpyHostToDevice, st));
+    PSAC_NCCL(g_nccl.AllReduce(d_w, d_w, 2, ncclUint64, ncclMax, C.comm, st));
+    PSAC_CUDA(cudaMemcpyAsync(e->h_pinned + 40, d_w, 2 * sizeof(u64), cudaMemcpyDeviceToHost, st));
+    PSAC_CUDA(cudaStreamSynchronize(st));
+    const u64 need_all = e->h_pinned[40], have_min = ~e->h_pinned[41];
+    if (have_min >= need_all && have_min > 0) return true;
+    // ---- (re)allocate together
+    arena_close_peers(A);
+    host_barrier(e, C);  // nobody maps my old region any more
+    if (A.base) {
+        cudaFree(A.base);
+        e->device_bytes -= A.bytes;
+        A.base = nullptr;
+        A.bytes = 0;
+    }
+    const size_t bytes = align_up((size_t)need_all + (size_t)need_all / 16, (size_t)2 << 20);
     int ok = 1;
-    cudaIpcMemHandle_t hmine[2];
-    if (cudaIpcGetMemHandle(&hmine[0], mine0) != cudaSuccess || cudaIpcGetMemHandle(&hmine[1], mine1) != cudaSuccess) {
+    struct Info {
+        cudaIpcMemHandle_t handle;
+        u64 pid, ptr;
+        int dev, ok;
+        u8 pad[128 - 64 - 16 - 8];
+    } mine;
+    static_assert(sizeof(Info) == 128, "arena info record");
+    memset(&mine, 0, sizeof(mine));
+    void* ptr = nullptr;
+    if (cudaMalloc(&ptr, bytes) != cudaSuccess) {
         cudaGetLastError();
         ok = 0;
-        memset(hmine, 0, sizeof(hmine));
-    }
-    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
-    // all-gather the handles through a small device staging area
-    e->scratch.reserve((size_t)p * 128 + 64, &e->device_bytes);
-    u8* d_h = e->scratch.as<u8>();
-    PSAC_CUDA(cudaMemcpyAsync(d_h + (size_t)me * 128, hmine, 128, cudaMemcpyHostToDevice, st));
-    PSAC_NCCL(g_nccl.AllGather(d_h + (size_t)me * 128, d_h, 128, ncclUint8, C.comm, st));
-    std::vector<u8> all((size_t)p * 128);
-    PSAC_CUDA(cudaMemcpyAsync(all.data(), d_h, all.size(), cudaMemcpyDeviceToHost, st));
-    PSAC_CUDA(cudaStreamSynchronize(st));
-    for (int r = 0; r < p && ok; ++r) {
-        for (int b = 0; b < 2; ++b) {
-            if (r == me) {
-                pm.mapped[r][b] = b ? mine1 : mine0;
-                continue;
-            }
-            cudaIpcMemHandle_t h;
-            memcpy(&h, all.data() + (size_t)r * 128 + (size_t)b * 64, 64);
-            if (pm.open[r][b] && memcmp(&h, &pm.handle[r][b], 64) == 0) continue;
-            if (pm.open[r][b]) {
-                cudaIpcCloseMemHandle(pm.mapped[r][b]);
-                pm.open[r][b] = false;
-            }
-            void* ptr = nullptr;
-            if (cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
-                cudaGetLastError();
-                ok = 0;
-                break;
-            }
-            pm.handle[r][b] = h;
-            pm.mapped[r][b] = ptr;
-            pm.open[r][b] = true;
+    } else {
+        A.base = reinterpret_cast<u8*>(ptr);
+        A.bytes = bytes;
+        e->device_bytes += bytes;
+        if (cudaIpcGetMemHandle(&mine.handle, ptr) != cudaSuccess) {
+            cudaGetLastError();
+            ok = 0;
         }
     }
-    // agree: one failing rank sends everybody to the NCCL path
-    u64* d_ok = e->shard_meta() + 56;
-    e->h_pinned[40] = (u64)ok;
-    PSAC_CUDA(cudaMemcpyAsync(d_ok, e->h_pinned + 40, sizeof(u64), cudaMemcpyHostToDevice, st));
-    PSAC_NCCL(g_nccl.AllReduce(d_ok, d_ok, 1, ncclUint64, ncclMin, C.comm, st));
-    PSAC_CUDA(cudaMemcpyAsync(e->h_pinned + 40, d_ok, sizeof(u64), cudaMemcpyDeviceToHost, st));
+    mine.pid = (u64)getpid();
+    mine.ptr = (u64)(uintptr_t)ptr;
+    mine.dev = e->device;
+    mine.ok = ok;
+    e->scratch.reserve((size_t)p * 128 + 64, &e->device_bytes);
+    u8* d_h = e->scratch.as<u8>();
+    PSAC_CUDA(cudaMemcpyAsync(d_h + (size_t)me * 128, &mine, 128, cudaMemcpyHostToDevice, st));
+    PSAC_NCCL(g_nccl.AllGather(d_h + (size_t)me * 128, d_h, 128, ncclUint8, C.comm, st));
+    std::vector<Info> all(p);
+    PSAC_CUDA(cudaMemcpyAsync(all.data(), d_h, (size_t)p * 128, cudaMemcpyDeviceToHost, st));
     PSAC_CUDA(cudaStreamSynchronize(st));
-    if (e->h_pinned[40] == 0) return false;
-    for (int r = 0; r < p; ++r) {
-        out0[r] = reinterpret_cast<u64*>(pm.mapped[r][0]);
-        out1[r] = reinterpret_cast<u64*>(pm.mapped[r][1]);
+    for (int r = 0; r < p; ++r) ok &= all[r].ok;
+    for (int r = 0; r < p && ok; ++r) {
+        if (r == me) {
+            A.peer[r] = A.base;
+        } else if (all[r].pid == mine.pid) {
+            // another engine of this process: plain peer access
+            cudaError_t pe = all[r].dev == e->device ? cudaSuccess : cudaDeviceEnablePeerAccess(all[r].dev, 0);
+            if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) ok = 0;
+            cudaGetLastError();
+            A.peer[r] = reinterpret_cast<u8*>((uintptr_t)all[r].ptr);
+        } else {
+            void* q = nullptr;
+            if (cudaIpcOpenMemHandle(&q, all[r].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                cudaGetLastError();
+                ok = 0;
+            } else {
+                A.peer[r] = reinterpret_cast<u8*>(q);
+                A.ipc_open[r] = true;
+            }
+        }
     }
-    return true;
+    // agree: one failing rank sends everybody to the NCCL paths
+    e->h_pinned[40] = (u64)ok;
+    PSAC_CUDA(cudaMemcpyAsync(d_w, e->h_pinned + 40, sizeof(u64), cudaMemcpyHostToDevice, st));
+    PSAC_NCCL(g_nccl.AllReduce(d_w, d_w, 1, ncclUint64, ncclMin, C.comm, st));
+    PSAC_CUDA(cudaMemcpyAsync(e->h_pinned + 40, d_w, sizeof(u64), cudaMemcpyDeviceToHost, st));
+    PSAC_CUDA(cudaStreamSynchronize(st));
+    A.world = p;
+    A.usable = e->h_pinned[40] != 0;
+    if (!A.usable) arena_close_peers(A);
+    return A.usable;
+}
+
+// Collective release (psacb200_comm_finalize): mappings first, then the regions.
+void arena_release(psacb200_engine* e, const ShardComm* C) {
+    if (e->peer_map == nullptr) return;
+    PeerArena& A = *reinterpret_cast<PeerArena*>(e->peer_map);
+    cudaStreamSynchronize(e->stream);
+    arena_close_peers(A);
+    if (C != nullptr && C->comm != nullptr) host_barrier(e, *C);
+    if (A.base) {
+        cudaFree(A.base);
+        e->device_bytes -= A.bytes;
+    }
+    A.base = nullptr;
+    A.bytes = 0;
 }
 
 // stream-ordered barrier over the ranks (a one-word all-reduce)
@@ -433,28 +505,15 @@ void all_gather_v(psacb200_engine* e, const ShardComm& C, void* buf, const std::
     PSAC_NCCL(g_nccl.GroupEnd());
 }
 
-struct ShardedTimes {
-    cudaEvent_t ev[12];
-};
-
-// The sharded construction proper.  d_text_local: this rank's block of the text (device).  Outputs: this rank's blocks
-// of SA / ISA / LCP (device, index_bytes wide).
-// Returns false -- identically on every rank, from data all of them hold -- when this round's sharded scheme cannot take
-// the input (key prefixes too skewed to balance, or too many unresolved suffixes for the replicated rounds); the caller
-// then runs the replicated construction.
-bool construct_sharded_core(psacb200_engine* e, const ShardComm& C, const u8* d_text_local, u64 n_local, u64 n, int index_bytes, unsigned flags,
-                            unsigned k, void* sa_out, void* isa_out, void* lcp_out) {
-    const bool want_lcp = (flags & PSACB200_LCP) != 0;
+// S1 alphabet: local byte histogram, summed over the ranks (reference alphabet.hpp:94-100 allreduce);
+// S2 the packed text, replicated on every rank (e->packed)
+void prepare_text_sharded(psacb200_engine* e, const ShardComm& C, const u8* d_text_local, u64 n_local, u64 n, Alphabet& alpha) {
     const int p = C.world, me = C.rank;
     cudaStream_t st = e->stream;
     size_t* tot = &e->device_bytes;
     psacb200_stats& S = e->stats;
     const BlkDist blk(n, p);
-    if (blk.size(me) != n_local) throw arg_failure{"the input text must be equally block decomposed across all ranks (reference suffix_array.hpp:226)"};
-    S.internal_index_bytes = 8;
     e->small.reserve(psacb200_engine::small_bytes(), tot);
-
-    // ---- S1 alphabet: local byte histogram, summed over the ranks (reference alphabet.hpp:94-100 allreduce)
     e->begin(PH_ALPHABET);
     PSAC_CUDA(cudaMemsetAsync(e->byte_hist(), 0, 256 * sizeof(u64), st));
     if (n_local) {
@@ -465,7 +524,6 @@ bool construct_sharded_core(psacb200_engine* e, const ShardComm& C, const u8* d_
     PSAC_CUDA(cudaMemcpyAsync(e->h_pinned + 16, e->byte_hist(), 256 * sizeof(u64), cudaMemcpyDeviceToHost, st));
     e->end(PH_ALPHABET);
     PSAC_CUDA(cudaStreamSynchronize(st));
-    Alphabet alpha;
     alphabet_from_hist(e->h_pinned + 16, alpha);
     dense_codes(e->h_pinned + 16, alpha);
     S.sigma = alpha.sigma;
@@ -473,7 +531,6 @@ bool construct_sharded_core(psacb200_engine* e, const ShardComm& C, const u8* d_
     S.pack_bits = alpha.lbits;
     const int lbits = alpha.lbits, cpw = 64 / lbits;
 
-    // ---- S2 replicated packed text
     e->begin(PH_PACK);
     const size_t nwords = div_up(n, (size_t)cpw) + 2;
     e->packed.reserve(nwords * sizeof(u64) + 64, tot);
@@ -501,6 +558,34 @@ bool construct_sharded_core(psacb200_engine* e, const ShardComm& C, const u8* d_
     }
     PSAC_CUDA(cudaGetLastError());
     e->end(PH_PACK);
+}
+
+struct ShardedTimes {
+    cudaEvent_t ev[12];
+};
+
+// The sharded construction proper.  d_text_local: this rank's block of the text (device).  Outputs: this rank's blocks
+// of SA / ISA / LCP (device, index_bytes wide).
+// Returns false -- identically on every rank, from data all of them hold -- when this round's sharded scheme cannot take
+// the input (key prefixes too skewed to balance, or too many unresolved suffixes for the replicated rounds); the caller
+// then runs the replicated construction.
+bool construct_sharded_core(psacb200_engine* e, const ShardComm& C, const u8* d_text_local, u64 n_local, u64 n, int index_bytes, unsigned flags,
+                            unsigned k, void* sa_out, void* isa_out, void* lcp_out) {
+    const bool want_lcp = (flags & PSACB200_LCP) != 0;
+    const int p = C.world, me = C.rank;
+    cudaStream_t st = e->stream;
+    size_t* tot = &e->device_bytes;
+    psacb200_stats& S = e->stats;
+    const BlkDist blk(n, p);
+    if (blk.size(me) != n_local) throw arg_failure{"the input text must be equally block decomposed across all ranks (reference suffix_array.hpp:226)"};
+    S.internal_index_bytes = 8;
+    e->small.reserve(psacb200_engine::small_bytes(), tot);
+
+    // ---- S1 + S2 alphabet and replicated packed text
+    Alphabet alpha;
+    prepare_text_sharded(e, C, d_text_local, n_local, n, alpha);
+    const int lbits = alpha.lbits, cpw = 64 / lbits;
+    u64* stream = e->packed.as<u64>();
 
     // ---- S3 key length, key-prefix histogram of the local block, all-gathered
     const unsigned Cc = choose_key_chars(n, lbits, k);
@@ -696,13 +781,27 @@ bool construct_sharded_core(psacb200_engine* e, const ShardComm& C, const u8* d_
         }
         if (rrun != n_local) throw std::string("sharded construction: exchange plan does not cover the block");
         // receive buffers of n_local pairs
-        e->rk[0].reserve((n_local + 16) * sizeof(u64), tot);
-        e->rk[1].reserve((n_local + 16) * sizeof(u64), tot);
-        u64* recv_suf = e->rk[0].as<u64>();
-        u64* recv_bkt = e->rk[1].as<u64>();
+        // receive buffers of n_local pairs: in the peer-visible arena when it can be mapped, else private (NCCL path)
+        const size_t rbytes = align_up((blk.size(0) + 16) * sizeof(u64), 256);
+        const bool fused = arena_ensure(e, C, 2 * rbytes);
+        u64* recv_suf;
+        u64* recv_bkt;
         u64* peer_suf[16];
         u64* peer_bkt[16];
-        const bool fused = e->peer_map != nullptr && map_peer_buffers(e, C, recv_suf, recv_bkt, *reinterpret_cast<PeerMap*>(e->peer_map), peer_suf, peer_bkt);
+        if (fused) {
+            PeerArena& A = *reinterpret_cast<PeerArena*>(e->peer_map);
+            recv_suf = reinterpret_cast<u64*>(A.base);
+            recv_bkt = reinterpret_cast<u64*>(A.base + rbytes);
+            for (int r = 0; r < p; ++r) {
+                peer_suf[r] = reinterpret_cast<u64*>(A.peer[r]);
+                peer_bkt[r] = reinterpret_cast<u64*>(A.peer[r] + rbytes);
+            }
+        } else {
+            e->rk[0].reserve((n_local + 16) * sizeof(u64), tot);
+            e->rk[1].reserve((n_local + 16) * sizeof(u64), tot);
+            recv_suf = e->rk[0].as<u64>();
+            recv_bkt = e->rk[1].as<u64>();
+        }
         S.reserved = fused ? 1u : 0u;  // reported as "exchange = peer stores" in the stats
         const u64 cut = blk.rem * (blk.base + 1), base1 = blk.base + 1, base0 = blk.base ? blk.base : 1;
         // packed exchange: [local index | rank | relative bucket] in one word, when the three fields fit 64 bits
@@ -881,6 +980,7 @@ bool construct_sharded_core(psacb200_engine* e, const ShardComm& C, const u8* d_
             Q.head_out = e->rh[t].as<u8>();
             Q.suf_out = e->rv[t].p;
             Q.cap = m;
+            Q.lb_max = e->lookback.as<u64>();  // (the look-back buffer may have grown since R was filled in)
             Q.lb_sum = Q.lb_max + ntiles;
             Q.kbits = kb;
             Q.h = h;
@@ -951,6 +1051,77 @@ void gather_text(psacb200_engine* e, const ShardComm& C, const u8* d_text_local,
     }
     if (n_local) PSAC_CUDA(cudaMemcpyAsync(e->text.as<u8>() + dsp[C.rank], d_text_local, n_local, cudaMemcpyDeviceToDevice, e->stream));
     all_gather_v(e, C, e->text.p, cnt, dsp, 1);
+}
+
+// ------------------------------------------------------------------------------------------------ sharded certificate
+// d_check_sa over the ranks (check_kernels.cuh): every rank checks its block of SA positions; the ISA blocks are copied
+// into the peer arena and read by all ranks over NVLink; the element before a block comes from the previous non-empty
+// rank.  The failure counts are summed over the ranks, so every rank returns the same report.
+void check_sharded_core(psacb200_engine* e, const ShardComm& C, const u8* d_text_local, u64 n_local, u64 n, int index_bytes, const void* d_sa, const void* d_isa,
+                        const void* d_lcp, psacb200_check_report* rep) {
+    const int p = C.world, me = C.rank;
+    cudaStream_t st = e->stream;
+    const BlkDist blk(n, p);
+    if (blk.size(me) != n_local) throw arg_failure{"the arrays must be equally block decomposed across all ranks (reference suffix_array.hpp:226)"};
+    memset(rep, 0, sizeof(*rep));
+    rep->n = n;
+    rep->first_bad = ~0ull;
+    rep->checked_lcp = d_lcp != nullptr;
+    if (n == 0) return;
+    Alphabet alpha;
+    prepare_text_sharded(e, C, d_text_local, n_local, n, alpha);
+    const size_t blk_bytes = align_up((blk.size(0) + 16) * (size_t)index_bytes, 256);
+    if (!arena_ensure(e, C, blk_bytes)) throw std::string("sharded check needs peer access between the GPUs (CUDA IPC / P2P unavailable)");
+    PeerArena& A = *reinterpret_cast<PeerArena*>(e->peer_map);
+    cudaEvent_t e0 = e->ev_begin[PH_OUTPUT], e1 = e->ev_end[PH_OUTPUT];
+    PSAC_CUDA(cudaEventRecord(e0, st));
+    rank_barrier(e, C);  // nobody still reads the arena from a previous step
+    if (n_local) PSAC_CUDA(cudaMemcpyAsync(A.base, d_isa, n_local * (size_t)index_bytes, cudaMemcpyDeviceToDevice, st));
+    // last SA element of every rank
+    u64* d_last = e->shard_meta();  // [p]
+    PSAC_CUDA(cudaMemsetAsync(d_last + me, 0, sizeof(u64), st));
+    if (n_local)
+        PSAC_CUDA(cudaMemcpyAsync(d_last + me, reinterpret_cast<const u8*>(d_sa) + (n_local - 1) * (size_t)index_bytes, (size_t)index_bytes, cudaMemcpyDeviceToDevice, st));
+    PSAC_NCCL(g_nccl.AllGather(d_last + me, d_last, 1, ncclUint64, C.comm, st));  // (also orders the ISA copies before the peers' reads)
+    PSAC_CUDA(cudaMemcpyAsync(e->h_pinned, d_last, (size_t)p * sizeof(u64), cudaMemcpyDeviceToHost, st));
+    PSAC_CUDA(cudaStreamSynchronize(st));
+    u64 halo = 0;
+    for (int r = me - 1; r >= 0; --r)
+        if (blk.size(r)) {
+            halo = e->h_pinned[r];
+            break;
+        }
+    rank_barrier(e, C);
+    check_reset(e);
+    if (n_local) {
+        CheckArgs K{};
+        K.sa = d_sa;
+        K.lcp = d_lcp;
+        K.pos0 = blk.start(me);
+        K.m = n_local;
+        K.n = n;
+        K.halo_sa = halo;
+        K.stream = e->packed.as<u64>();
+        K.lbits = alpha.lbits;
+        K.padded = alpha.zero_code_used ? 1 : 0;
+        K.p = p;
+        for (int r = 0; r < p; ++r) K.isa_blk[r] = A.peer[r];
+        K.div = BlkDiv::make(n, p);
+        K.bad = check_counters(e);
+        check_launch(e, K, index_bytes);
+    }
+    unsigned long long* bad = check_counters(e);
+    PSAC_NCCL(g_nccl.AllReduce(bad, bad, 4, ncclUint64, ncclSum, C.comm, st));
+    PSAC_NCCL(g_nccl.AllReduce(bad + 4, bad + 4, 1, ncclUint64, ncclMin, C.comm, st));
+    PSAC_CUDA(cudaEventRecord(e1, st));
+    PSAC_CUDA(cudaMemcpyAsync(e->h_pinned + 48, bad, 5 * sizeof(u64), cudaMemcpyDeviceToHost, st));
+    PSAC_CUDA(cudaStreamSynchronize(st));
+    rep->bad_range = e->h_pinned[48];
+    rep->bad_inverse = e->h_pinned[49];
+    rep->bad_order = e->h_pinned[50];
+    rep->bad_lcp = e->h_pinned[51];
+    rep->first_bad = e->h_pinned[52];
+    cudaEventElapsedTime(&rep->ms, e0, e1);
 }
 
 }  // namespace

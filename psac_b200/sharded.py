@@ -59,6 +59,25 @@ class ShardedSuffixArray:
         self.local_B = torch.empty(m, dtype=dt, device=self.device)
         self.local_LCP = torch.empty(m, dtype=dt, device=self.device) if self.construct_lcp else None
         flags = (api.LCP if self.construct_lcp else 0) | (api.FAST_RESOLVAL if fast_resolval else 0)
+        self._text = text
+        # the engine works on its own stream: everything torch queued for the inputs (the copy above, the caller's
+        # producer kernels) must have completed before the engine reads them
+        torch.cuda.current_stream(self.device).synchronize()
         self.engine.construct_sharded_ptr(text.data_ptr() if m else None, m, self.n, self.index_bytes, flags, k, self.local_SA.data_ptr() if m else None,
                                           self.local_B.data_ptr() if m else None, self.local_LCP.data_ptr() if (m and self.construct_lcp) else None)
         return self
+
+    def check(self):
+        """Collective device-side certificate of the last construct (reference d_check_sa + check_lcp); dict, ``ok`` = correct."""
+        m = self.local_size
+        torch.cuda.current_stream(self.device).synchronize()
+        return self.engine.check_sharded_ptr(self._text.data_ptr() if m else None, m, self.n, self.index_bytes, self.local_SA.data_ptr() if m else None,
+                                             self.local_B.data_ptr() if m else None,
+                                             self.local_LCP.data_ptr() if (m and self.construct_lcp) else None)
+
+    def close(self):
+        """Collective: ordered release of the peer-visible memory, then the engine."""
+        if self.engine is not None:
+            self.engine.comm_finalize()
+            self.engine.close()
+            self.engine = None

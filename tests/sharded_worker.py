@@ -35,6 +35,7 @@ def case(name, text, index_bytes, lcp, k=0):
     got_sa = gather_blocks(sa.local_SA, n, p, rank, dev).view(udt)
     got_isa = gather_blocks(sa.local_B, n, p, rank, dev).view(udt)
     got_lcp = gather_blocks(sa.local_LCP, n, p, rank, dev).view(udt) if lcp else None
+    chk = sa.check()  # collective device-side certificate (same report on every rank)
     ok = True
     if rank == 0:
         exp = O.construct(text, 64, 0, lcp)
@@ -43,13 +44,26 @@ def case(name, text, index_bytes, lcp, k=0):
             neq = np.nonzero(got_.astype(np.uint64) != exp_)[0]
             if neq.size:
                 bad.append("%s: %d mismatches, first at %d (got %d, want %d)" % (name_, neq.size, neq[0], int(got_[neq[0]]), int(exp_[neq[0]])))
+        if not chk["ok"]:
+            bad.append("device check: %r" % (chk,))
         ok = not bad
         if bad:
             print("   " + "; ".join(bad), flush=True)
         st = sa.engine.stats()
         print("%-34s n=%9d ib=%d lcp=%d k=%d rounds=%d unresolved=%d %s" % (name, n, index_bytes, int(lcp), k, st["rounds"], st["unresolved_after_first"],
                                                                           "ok" if ok else "MISMATCH"), flush=True)
-    sa.engine.close()
+    if name.startswith("random DNA, aligned"):
+        # the certificate must also FAIL when it should: corrupt one LCP entry and one SA entry of the last rank's block
+        sa.local_LCP[3] += 1
+        c1 = sa.check()
+        sa.local_LCP[3] -= 1
+        a, b = int(sa.local_SA[5]), int(sa.local_SA[6])
+        sa.local_SA[5], sa.local_SA[6] = b, a
+        c2 = sa.check()
+        if rank == 0 and not (c1["bad_lcp"] == p and c1["bad_order"] == 0 and c2["bad_inverse"] == 2 * p and not c2["ok"]):
+            print("   device check did not flag the corruption: %r %r" % (c1, c2), flush=True)
+            ok = False
+    sa.close()
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.broadcast(flag, 0)
     return bool(flag.item())
