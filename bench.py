@@ -285,6 +285,7 @@ def main():
     barrier()
     ms_dev = ev0.elapsed_time(ev1) / args.steps
     launches = eng.launches - launches0
+    trace = eng.trace()  # device timeline of the last timed step (this rank)
     clocks = sampler.summary()
     stats = eng.stats()
 
@@ -419,6 +420,7 @@ def main():
                      "whole_pass": {"what": "histogram pre-pass + scans + scatter of one digit pass", "ms": pass_avg_ms, "achieved": pass_achieved,
                                     "frac": pass_achieved / peak}},
         "phases_ms": {k: round(v, 3) for k, v in sorted(phase.items())},
+        "trace_ms": [[k, round(v, 3)] for k, v in trace],
     }
     if e2e:
         line["e2e"] = {"value": n_total / (ms_e2e * 1e-3), "unit": "suffixes/s", "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],

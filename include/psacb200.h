@@ -69,6 +69,9 @@ const char* psacb200_last_error(void);
 /* Number of CUDA kernel launches issued by this engine since creation (bench.py's gpu_launches). */
 uint64_t psacb200_launch_count(const psacb200_engine* e);
 int psacb200_get_stats(const psacb200_engine* e, psacb200_stats* out);
+/* Fine-grained device timeline of the last construct call: "label=milliseconds;..." for consecutive marks on the engine's
+ * stream (CUDA events).  Synchronises the stream. */
+int psacb200_trace(psacb200_engine* e, char* buf, size_t buf_len);
 /* Ranking mode of the radix digit passes: 0 = one shared-memory atomic per key (relies on the lanes of one ATOMS instruction
  * being applied in lane order, verified on the device at every psacb200_create), 1 = match.any ranking (documented warp
  * primitives only; selected automatically when that self-test fails, or with the environment variable PSACB200_SAFE_RANK=1). */

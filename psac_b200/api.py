@@ -105,6 +105,7 @@ def lib():
         L.psacb200_ansv.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p]
         L.psacb200_suffix_tree.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
         L.psacb200_comm_finalize.argtypes = [C.c_void_p]
+        L.psacb200_trace.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
         L.psacb200_rank_mode.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
         chk = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(CheckReport)]
         L.psacb200_check_device.argtypes = chk
@@ -163,6 +164,17 @@ class Engine:
         s = Stats()
         _check(lib().psacb200_get_stats(self._h, C.byref(s)))
         return s.as_dict()
+
+    def trace(self):
+        """Device timeline of the last construct call: list of (label, ms) between consecutive marks."""
+        buf = C.create_string_buffer(8192)
+        _check(lib().psacb200_trace(self._h, buf, 8192))
+        out = []
+        for item in buf.value.decode().split(";"):
+            if "=" in item:
+                k, v = item.split("=")
+                out.append((k, float(v)))
+        return out
 
     def reserve(self, n, index_bytes=4, flags=0):
         _check(lib().psacb200_reserve(self._h, n, index_bytes, flags))

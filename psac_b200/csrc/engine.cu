@@ -81,15 +81,29 @@ struct psacb200_engine {
     uint64_t launches = 0;
     DevBuf text, packed, keys[2], vals[2], vals2, segws, isa, lcp, small, lookback, rk[2], rv[2], rp[2], rh[2], scratch, rep[3], tb[6];
     void* nccl_comm = nullptr;  // ncclComm_t of the sharded construction (sharded.cuh), one rank per engine
+    void* nccl_comm2 = nullptr; // a split of it for the copy stream (barrier of the SA -> ISA exchange), or null
+    cudaStream_t copy_stream = nullptr;  // peer copies of the SA -> ISA exchange (copy engines), overlapping the main stream
+    cudaEvent_t ev_x[2];
     void* peer_map = nullptr;   // PeerArena: peer-visible memory of the sharded construction (sharded.cuh)
     int shard_rank = 0, shard_world = 1;
-    u64* h_pinned = nullptr;  // 2048 u64 of pinned host memory for small read-backs and plan uploads
+    u64* h_pinned = nullptr;  // 8192 u64 of pinned host memory for small read-backs and plan uploads
     cudaEvent_t ev_begin[PH_COUNT], ev_end[PH_COUNT];
     bool ev_used[PH_COUNT];
     cudaEvent_t ev_scatter[2 * MAX_PASSES];  // brackets of the scatter kernels of the segmented digit passes
     int scatter_passes = 0;
     psacb200_stats stats;
     u64 selftest_mismatches = 0;
+    // fine-grained trace of the last call: consecutive marks on the engine's stream (psacb200_trace)
+    static constexpr int TRACE_MAX = 64;
+    cudaEvent_t tr_ev[TRACE_MAX];
+    const char* tr_name[TRACE_MAX];
+    int tr_n = 0;
+    void mark(const char* name) {
+        if (tr_n < TRACE_MAX) {
+            cudaEventRecord(tr_ev[tr_n], stream);
+            tr_name[tr_n++] = name;
+        }
+    }
     bool v1_stats = false;  // sharded v1: the slot of "digit pass 1" holds the key-range selection
 
     // layout of `small`
@@ -290,6 +304,7 @@ void construct_core(psacb200_engine* e, u64 n, int index_bytes, unsigned flags, 
     const bool ext_sa = inplace, ext_isa = inplace && isa_out != nullptr, ext_lcp = inplace && want_lcp;
     reserve_buffers<IdxT>(e, n, sizeof(KeyC), want_lcp, ext_sa, ext_isa, ext_lcp);
 
+    e->mark("text");
     // ---- first sort (a4 + a6): digit pass 1 reads the packed text, the others the carried keys
     const RadixPlan plan = make_radix_plan(0, (int)C * lbits);
     KeyC* kbuf[2] = {e->keys[0].as<KeyC>(), e->keys[1].as<KeyC>()};
@@ -318,6 +333,7 @@ void construct_core(psacb200_engine* e, u64 n, int index_bytes, unsigned flags, 
         x = radix_sort_suffixes<IdxT>(e->radix_ws(), e->packed.as<u64>(), n, lbits, (int)C, kbuf, vbuf, st, &plan_used, &sort_launches, e->ev_end[PH_PASS1]);
         SA = vbuf[x];
     }
+    e->mark("sort");
     e->end(PH_SORT);
     e->launches += sort_launches;
     S.sort_passes = plan_used.npass;
@@ -409,6 +425,7 @@ void construct_core(psacb200_engine* e, u64 n, int index_bytes, unsigned flags, 
     } else {
         launch_resolve<IdxT, KeyC>(e, true, R);
     }
+    e->mark("heads");
     e->end(PH_RESOLVE);
     u64 m = 0, nb = 0;
     read_counts(e, &m, &nb);
@@ -438,6 +455,7 @@ void construct_core(psacb200_engine* e, u64 n, int index_bytes, unsigned flags, 
         }
     }
 
+    e->mark("counts");
     // ---- SA -> ISA (a10): partition the (suffix, bucket) pairs by ISA window, then scatter window by window
     e->begin(PH_ISA);
     if (partitioned) {
@@ -448,10 +466,12 @@ void construct_core(psacb200_engine* e, u64 n, int index_bytes, unsigned flags, 
         IdxT* part_bucket = reinterpret_cast<IdxT*>(kbuf[x]);  // the sorted keys are dead after resolve
         ArraySrc<IdxT, IdxT> src{SA, bucket, nullptr, shift, (u32)(RADIX - 1), (IdxT)0};
         launch_pass<ArraySrc<IdxT, IdxT>, IdxT, false>(ws, src, part_suffix, part_bucket, nullptr, n, st);
+        e->mark("isa_window");
         isa_scatter_kernel<IdxT><<<(unsigned)div_up(n, (size_t)4096), 256, 0, st>>>(part_suffix, part_bucket, ISA, n);
         e->launches += LAUNCHES_PER_PASS + 1;
         PSAC_CUDA(cudaGetLastError());
     }
+    e->mark("isa_scatter");
     e->end(PH_ISA);
 
     // ---- later rounds on the unresolved suffixes only (a5, a6, a8, a9, a10, a12)
@@ -513,11 +533,13 @@ void construct_core(psacb200_engine* e, u64 n, int index_bytes, unsigned flags, 
         e->end(PH_ROUNDS);
     }
 
+    e->mark("rounds");
     // ---- outputs: SA and ISA (= final bucket ids, 0-based) and LCP in the caller's index width
     e->begin(out_is_host ? PH_D2H : PH_OUTPUT);
     emit<IdxT>(e, SA, sa_out, n, index_bytes, out_is_host);
     emit<IdxT>(e, ISA, isa_out, n, index_bytes, out_is_host);
     if (want_lcp) emit<IdxT>(e, LCP, lcp_out, n, index_bytes, out_is_host);
+    e->mark("output");
     e->end(out_is_host ? PH_D2H : PH_OUTPUT);
 }
 
@@ -664,9 +686,11 @@ int construct_entry(psacb200_engine* e, const u8* text, bool text_is_host, size_
         memset(&e->stats, 0, sizeof(e->stats));
         memset(e->ev_used, 0, sizeof(e->ev_used));
         e->scatter_passes = 0;
+        e->tr_n = 0;
         e->stats.n = n;
         if (n == 0) return PSACB200_OK;
         e->begin(PH_TOTAL);
+        e->mark("begin");
         const u8* d_text = text;
         if (text_is_host) {
             e->begin(PH_H2D);
@@ -805,13 +829,16 @@ int psacb200_create(int device, psacb200_engine** out) {
         e->device = device;
         e->sm_count = prop.multiProcessorCount;
         PSAC_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
-        PSAC_CUDA(cudaMallocHost((void**)&e->h_pinned, 2048 * sizeof(u64)));
+        PSAC_CUDA(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) PSAC_CUDA(cudaEventCreateWithFlags(&e->ev_x[i], cudaEventDisableTiming));
+        PSAC_CUDA(cudaMallocHost((void**)&e->h_pinned, 8192 * sizeof(u64)));
         for (int i = 0; i < PH_COUNT; ++i) {
             PSAC_CUDA(cudaEventCreate(&e->ev_begin[i]));
             PSAC_CUDA(cudaEventCreate(&e->ev_end[i]));
             e->ev_used[i] = false;
         }
         for (int i = 0; i < 2 * MAX_PASSES; ++i) PSAC_CUDA(cudaEventCreate(&e->ev_scatter[i]));
+        for (int i = 0; i < psacb200_engine::TRACE_MAX; ++i) PSAC_CUDA(cudaEventCreate(&e->tr_ev[i]));
         memset(&e->stats, 0, sizeof(e->stats));
         e->small.reserve(psacb200_engine::small_bytes(), &e->device_bytes);
         // hardware self-test of the ranking assumption of the radix passes (radix_sort.cuh): refuse to run if it fails
@@ -844,18 +871,41 @@ void psacb200_destroy(psacb200_engine* e) {
         cudaEventDestroy(e->ev_end[i]);
     }
     for (int i = 0; i < 2 * MAX_PASSES; ++i) cudaEventDestroy(e->ev_scatter[i]);
+    for (int i = 0; i < psacb200_engine::TRACE_MAX; ++i) cudaEventDestroy(e->tr_ev[i]);
     if (e->peer_map) {
         // (psacb200_comm_finalize is the collective, ordered release; this is the local last resort)
         arena_release(e, nullptr);
         delete reinterpret_cast<PeerArena*>(e->peer_map);
     }
+    if (e->nccl_comm2 && g_nccl.CommDestroy) g_nccl.CommDestroy(reinterpret_cast<ncclComm_t>(e->nccl_comm2));
     if (e->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(reinterpret_cast<ncclComm_t>(e->nccl_comm));
+    for (int i = 0; i < 2; ++i) cudaEventDestroy(e->ev_x[i]);
+    cudaStreamDestroy(e->copy_stream);
     if (e->h_pinned) cudaFreeHost(e->h_pinned);
     cudaStreamDestroy(e->stream);
     delete e;
 }
 
 uint64_t psacb200_launch_count(const psacb200_engine* e) { return e ? e->launches : 0; }
+
+int psacb200_trace(psacb200_engine* e, char* buf, size_t buf_len) {
+    if (!e || !buf || buf_len == 0) return PSACB200_ERR_ARG;
+    std::string out;
+    cudaSetDevice(e->device);
+    cudaStreamSynchronize(e->stream);
+    for (int i = 1; i < e->tr_n; ++i) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, e->tr_ev[i - 1], e->tr_ev[i]) != cudaSuccess) {
+            cudaGetLastError();
+            continue;
+        }
+        char tmp[96];
+        snprintf(tmp, sizeof(tmp), "%s=%.3f;", e->tr_name[i], t);
+        out += tmp;
+    }
+    snprintf(buf, buf_len, "%s", out.c_str());
+    return PSACB200_OK;
+}
 
 int psacb200_rank_mode(const psacb200_engine* e, uint64_t* selftest_mismatches) {
     if (e && selftest_mismatches) *selftest_mismatches = e->selftest_mismatches;
@@ -1006,6 +1056,10 @@ int psacb200_comm_init(psacb200_engine* e, const uint8_t id[128], int rank, int 
         if (world < 1 || world > 16 || rank < 0 || rank >= world) throw arg_failure{"bad rank / world size (1..16 ranks of one box)"};
         PSAC_CUDA(cudaSetDevice(e->device));
         g_nccl.load();
+        if (e->nccl_comm2) {
+            g_nccl.CommDestroy(reinterpret_cast<ncclComm_t>(e->nccl_comm2));
+            e->nccl_comm2 = nullptr;
+        }
         if (e->nccl_comm) {
             g_nccl.CommDestroy(reinterpret_cast<ncclComm_t>(e->nccl_comm));
             e->nccl_comm = nullptr;
@@ -1015,6 +1069,10 @@ int psacb200_comm_init(psacb200_engine* e, const uint8_t id[128], int rank, int 
         ncclComm_t c;
         PSAC_NCCL(g_nccl.CommInitRank(&c, world, u, rank));
         e->nccl_comm = c;
+        if (g_nccl.CommSplit && world > 1) {
+            ncclComm_t c2 = nullptr;
+            if (g_nccl.CommSplit(c, 0, rank, &c2, nullptr) == ncclSuccess) e->nccl_comm2 = c2;
+        }
         if (!e->peer_map && !getenv("PSACB200_NO_PEER")) e->peer_map = new PeerArena();  // PSACB200_NO_PEER=1: NCCL all-to-all-v instead of peer stores
         e->shard_rank = rank;
         e->shard_world = world;
@@ -1043,8 +1101,10 @@ int psacb200_construct_sharded(psacb200_engine* e, const uint8_t* d_text_local, 
             memset(&e->stats, 0, sizeof(e->stats));
             memset(e->ev_used, 0, sizeof(e->ev_used));
             e->scatter_passes = 0;
+            e->tr_n = 0;
             e->stats.n = n;
             e->begin(PH_TOTAL);
+            e->mark("begin");
             e->v1_stats = false;
             sharded = construct_sharded_v2(e, C, d_text_local, n_local, n, index_bytes, flags, k, d_sa_local, d_isa_local, d_lcp_local);
             e->stats.sharded_scheme = sharded ? 2u : 0u;

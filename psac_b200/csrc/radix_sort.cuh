@@ -88,8 +88,6 @@ struct ArraySrc {
     using Out = KeyT;
     static constexpr bool FROM_TEXT = false;
     static constexpr bool PEER = false;  // outputs go to one array pair (see OwnerSrc in sharded.cuh for per-digit outputs)
-    static constexpr bool WORD = false;  // (see TextWordSrc)
-    static constexpr bool ADDR = false;
     const KeyT* __restrict__ kin;
     const ValT* __restrict__ vin;
     const u8* __restrict__ ain;  // auxiliary bytes (null when the pass carries none)
@@ -117,14 +115,11 @@ struct TextSrc {
     using Out = OutKeyT;
     static constexpr bool FROM_TEXT = true;
     static constexpr bool PEER = false;
-    static constexpr bool WORD = false;
-    static constexpr bool ADDR = false;
     const u64* __restrict__ stream;
     u64 n, T;
     int lbits, kbits, drop;  // drop: low key bits removed from the key that is written out
     u32 mask;
     int dshift;              // the digit of this pass is (key >> dshift) & mask
-    static constexpr u64 g0 = 0;  // (single GPU: element T is suffix 0)
     __device__ __forceinline__ u64 idx(size_t g) const { return (g < T) ? (n - 1 - g) : (g - T); }
     __device__ __forceinline__ Stage load_key(size_t g) const { return stream_extract(stream, idx(g), lbits, kbits); }
     // key of element g from a shared-memory copy of the stream words [w0, w0 + nw) (elements g >= T only)
@@ -139,42 +134,6 @@ struct TextSrc {
     __device__ __forceinline__ u32 digit(Stage k) const { return (u32)(k >> dshift) & mask; }
     __device__ __forceinline__ Out out_key(Stage k) const { return (Out)(k >> drop); }
     __device__ __forceinline__ IdxT load_val(size_t g) const { return (IdxT)idx(g); }
-    __device__ __forceinline__ u8 load_aux(size_t, Stage k) const { return (u8)((u32)(k >> dshift) & mask); }
-};
-
-// First pass of a SHARDED construction (sharded.cuh): the same key cut from the (replicated) packed text, for the suffixes
-// of ONE rank's text block [g0, g0 + count) -- on the last rank the T suffixes that run past the end of the text come
-// first, as above.  The element that travels is ONE 64-bit word [carried key | global suffix index]: the carried key is the
-// key below the top digit (`dshift` bits), the index takes `ibits` = bits(n - 1) bits.  The digit (top key bits = the
-// segment, and through the splitters the rank that sorts it) is staged as the auxiliary byte only; every digit's run is
-// stored at a byte ADDRESS (gbase[d]), which lies in the HBM of the GPU that owns the digit: the first digit pass is fused
-// with the exchange of the sort (peer stores over NVLink).
-struct TextWordSrc {
-    using Stage = u64;
-    using Out = u64;
-    static constexpr bool FROM_TEXT = true;
-    static constexpr bool PEER = false;
-    static constexpr bool WORD = true;
-    static constexpr bool ADDR = true;
-    const u64* __restrict__ stream;
-    u64 n, T, g0;
-    int lbits, kbits, ibits;
-    u32 mask;
-    int dshift;
-    __device__ __forceinline__ u64 idx(size_t g) const { return (g < T) ? (n - 1 - g) : (g0 + (g - T)); }
-    __device__ __forceinline__ Stage load_key(size_t g) const { return stream_extract(stream, idx(g), lbits, kbits); }
-    __device__ __forceinline__ Stage load_key_window(const u64* __restrict__ win, u64 w0, size_t g) const {
-        const u64 bit = (g0 + (g - T)) * (u64)lbits;
-        const u64 w = (bit >> 6) - w0;
-        const unsigned o = (unsigned)(bit & 63);
-        const u64 hi = win[w], lo = win[w + 1];
-        const u64 v = o ? ((hi << o) | (lo >> (64 - o))) : hi;
-        return v >> (64 - kbits);
-    }
-    __device__ __forceinline__ u32 digit(Stage k) const { return (u32)(k >> dshift) & mask; }
-    __device__ __forceinline__ Out out_key(Stage k) const { return k; }
-    __device__ __forceinline__ u64 word(Stage k, size_t g) const { return ((k & ((1ull << dshift) - 1ull)) << ibits) | idx(g); }
-    __device__ __forceinline__ NoVal load_val(size_t) const { return NoVal(); }
     __device__ __forceinline__ u8 load_aux(size_t, Stage k) const { return (u8)((u32)(k >> dshift) & mask); }
 };
 
@@ -235,7 +194,7 @@ __device__ __forceinline__ void scatter_tile(unsigned char* smem_raw, const Src&
         if (base >= src.T) {
             windowed = true;
             u64* win = reinterpret_cast<u64*>(smem_raw);
-            const u64 w0 = ((src.g0 + (base - src.T)) * (u64)src.lbits) >> 6;
+            const u64 w0 = ((base - src.T) * (u64)src.lbits) >> 6;
             const int nw = (int)((((u64)valid * src.lbits + src.kbits + 63) >> 6) + 2);
             for (int e = tid; e < nw; e += THREADS) win[e] = __ldg(src.stream + w0 + e);
             __syncthreads();
@@ -308,7 +267,7 @@ __device__ __forceinline__ void scatter_tile(unsigned char* smem_raw, const Src&
     // ---- stable rank = one ATOMS.ADD with return per key on the warp's running positions (lanes of one instruction
     //      apply in ascending lane order, instructions of a warp in program order -- see the header comment), then
     //      scatter into shared memory in bin order
-    u32 pos[(Cfg::PACKED || Src::WORD) ? 1 : ITEMS];
+    u32 pos[Cfg::PACKED ? 1 : ITEMS];
 #pragma unroll
     for (int j = 0; j < ITEMS; ++j) {
         const bool act = FULL || (woff + j * 32) < valid;
@@ -327,13 +286,11 @@ __device__ __forceinline__ void scatter_tile(unsigned char* smem_raw, const Src&
             if (act) p = atomicAdd(&mytab[src.digit(key[j])], 1u);
         }
         if (act) {
-            if constexpr (Src::WORD) {
-                reinterpret_cast<u64*>(smem_raw)[p] = src.word(key[j], base + woff + j * 32);
-            } else if constexpr (Cfg::PACKED) {
+            if constexpr (Cfg::PACKED) {
                 reinterpret_cast<u64*>(smem_raw)[p] = ((u64)src.out_key(key[j]) << 32) | (u64)val[j];
             } else {
                 reinterpret_cast<Stage*>(smem_raw)[p] = key[j];
-                if constexpr (!Src::WORD) pos[j] = p;
+                pos[j] = p;
             }
             if constexpr (Cfg::HAS_AUX) saux[p] = aux[j];
         }
@@ -341,27 +298,13 @@ __device__ __forceinline__ void scatter_tile(unsigned char* smem_raw, const Src&
 
     PSAC_PHASE(3);  // rank + scatter
     // ---- global offset of each bin of this tile: digit base + chunks before mine + tiles of my chunk before me
-    if (tid < RADIX) {
-        const u64 rel = chunk_base[tid] + (u64)tile_excl[tid] - (u64)bin_start[tid];
-        goff[tid] = Src::ADDR ? gbase[tid] + rel * sizeof(typename Src::Out) : gbase[tid] + rel;  // ADDR: gbase holds byte addresses
-    }
+    if (tid < RADIX) goff[tid] = gbase[tid] + chunk_base[tid] + (u64)tile_excl[tid] - (u64)bin_start[tid];
     PSAC_PHASE(4);  // offsets
     __syncthreads();
     PSAC_PHASE(5);  // barrier 3
 
     // ---- coalesced write-out: consecutive shared positions of one bin are consecutive in global memory
-    if constexpr (Src::WORD) {
-        static_assert(!Src::WORD || (Cfg::HAS_AUX && Src::ADDR), "word sources stage the digit as the auxiliary byte and write to addresses");
-#pragma unroll
-        for (int i = 0; i < ITEMS; ++i) {
-            const int s = i * THREADS + tid;
-            if (FULL || s < valid) {
-                const u64 e = reinterpret_cast<const u64*>(smem_raw)[s];
-                const u32 d = saux[s];
-                *reinterpret_cast<u64*>(goff[d] + (u64)s * sizeof(u64)) = e;  // (possibly a peer GPU's HBM)
-            }
-        }
-    } else if constexpr (Cfg::PACKED) {
+    if constexpr (Cfg::PACKED) {
 #pragma unroll
         for (int i = 0; i < ITEMS; ++i) {
             const int s = i * THREADS + tid;
@@ -477,7 +420,7 @@ __global__ void __launch_bounds__(THREADS) text_tile_hist_kernel(const Src src, 
     const int o0 = (int)threadIdx.x * ITEMS;
     const int dbits = __popc(src.mask);  // bits of the digit
     if (base >= src.T && o0 + ITEMS <= valid && (ITEMS - 1) * src.lbits <= 64) {  // every digit starts inside the first two words
-        const u64 bit0 = (src.g0 + (base + o0 - src.T)) * (u64)src.lbits + (u64)(src.kbits - src.dshift - dbits);  // first digit's stream position
+        const u64 bit0 = (base + o0 - src.T) * (u64)src.lbits + (u64)(src.kbits - src.dshift - dbits);  // first digit's stream position
         const u64 w0 = bit0 >> 6;
         const u64 a = __ldg(src.stream + w0), b = __ldg(src.stream + w0 + 1), c = __ldg(src.stream + w0 + 2);
 #pragma unroll

@@ -41,6 +41,7 @@ struct NcclApi {
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    ncclResult_t (*CommSplit)(ncclComm_t, int, int, ncclComm_t*, void*) = nullptr;  // optional (NCCL >= 2.18)
 
     void load() {
         if (handle) return;
@@ -64,6 +65,7 @@ struct NcclApi {
         PSAC_NCCL_SYM(GroupEnd, "ncclGroupEnd");
         PSAC_NCCL_SYM(GetErrorString, "ncclGetErrorString");
 #undef PSAC_NCCL_SYM
+        CommSplit = reinterpret_cast<decltype(CommSplit)>(dlsym(handle, "ncclCommSplit"));
     }
 };
 NcclApi g_nccl;
@@ -216,8 +218,6 @@ struct OwnerSrcT {
     using Out = u64;
     static constexpr bool FROM_TEXT = false;
     static constexpr bool PEER = PEER_;
-    static constexpr bool WORD = false;
-    static constexpr bool ADDR = false;
     const u64* __restrict__ kin;
     const u64* __restrict__ vin;
     // PEER: bin d (= owning rank d) is written straight into rank d's receive buffers over NVLink; the pointers are
@@ -253,8 +253,6 @@ struct OwnerPackSrcT {
     using Out = u64;
     static constexpr bool FROM_TEXT = false;
     static constexpr bool PEER = PEER_;
-    static constexpr bool WORD = false;
-    static constexpr bool ADDR = false;
     const u64* __restrict__ kin;  // suffix (global index)
     const u64* __restrict__ vin;  // bucket id (global SA position)
     u64* kpeer[16];
@@ -537,7 +535,7 @@ void prepare_text_sharded(psacb200_engine* e, const ShardComm& C, const u8* d_te
 
     e->begin(PH_PACK);
     const size_t nwords = div_up(n, (size_t)cpw) + 2;
-    e->packed.reserve(nwords * sizeof(u64) + 64, tot);
+    e->packed.reserve(nwords * sizeof(u64) + 256, tot);
     u64* stream = e->packed.as<u64>();
     const bool aligned = (n % (u64)p == 0) && ((n / (u64)p) % (u64)cpw == 0);
     if (aligned) {
@@ -1118,29 +1116,235 @@ static void plan_word_exchange(const u64* cnt, int p, int nb, u64 n, u64 pad_til
     }
 }
 
-// key source of the SA -> ISA exchange of v2: element g of the sorted words is suffix (word & mask) at SA position
-// off + g; what travels is [index inside the owner's ISA block | rank field | g], see OwnerPackSrcT
-struct OwnerWordSrc {
+// ------------------------------------------------------------------------------------------------ v2, digit pass 1
+// The packed text is replicated, so a rank needs no exchange to collect the suffixes it sorts: it scans the whole text and
+// keeps the suffixes whose top key digit lies in its digit range [dlo, dhi) -- the selection IS the first (top-digit) pass
+// of the sort.  One kernel, no histogram pre-pass: a CTA takes 512 x 64 consecutive characters, marks the selected ones in a
+// 64-bit mask per thread, and in batches of <= SELW_CAP elements ranks them by digit in shared memory (order inside a
+// segment is free: equal keys are one bucket anyway), reserves every digit's run with ONE atomic on the segment's cursor
+// and writes the runs out coalesced as words [carried key | suffix index] into the tile-padded segment layout.  The
+// suffixes that run past the end of the text are placed first in their segments by select_tail_words_kernel (they must
+// precede equal keys, shortest first, and the LSD passes that follow are stable).
+// Cost per rank: reads n * lbits / 8 bytes of text, ~6 integer instructions per character, writes 8 bytes per selected
+// suffix; no NVLink traffic (measured alternative: the same pass with peer stores into the owners' HBM, 13.3 ms for
+// 2^30 suffixes on 2 GPUs against 716 GB/s of achievable NVLink store bandwidth, profiles/r2_peer_bw.txt).
+constexpr int SELW_THREADS = 512;
+constexpr int SELW_CPT = 64;      // characters per thread
+constexpr int SELW_CAP = 8192;    // staged words per batch
+
+struct SelectWordsArgs {
+    const u64* stream;
+    u64 n_main;                   // suffixes 0 .. n_main-1 (the others run past the end: select_tail_words_kernel)
+    int K, tb, cb, ib;            // key bits, top digit bits, carried bits, index bits
+    u32 dlo, dhi;
+    const u64* seg_pad;           // [257] padded segment starts of this rank
+    unsigned long long* cursor;   // [256] elements placed so far in every segment
+    u64* out;
+};
+
+template <int LBITS>
+__device__ __forceinline__ u64 selw_bits(const u64 (&wd)[LBITS + 1], int c) {
+    const int o = c * LBITS, j = o >> 6, off = o & 63;
+    u64 hi = wd[0], lo = wd[1];
+#pragma unroll
+    for (int q = 1; q < LBITS; ++q)
+        if (q == j) {
+            hi = wd[q];
+            lo = wd[q + 1];
+        }
+    return off ? ((hi << off) | (lo >> (64 - off))) : hi;
+}
+
+template <int LBITS>
+__global__ void __launch_bounds__(SELW_THREADS, 2) select_words_kernel(SelectWordsArgs A) {
+    extern __shared__ __align__(16) u64 sw_stage[];  // SELW_CAP words
+    __shared__ u8 s_dig[SELW_CAP];
+    __shared__ u32 s_hist[RADIX], s_pos[RADIX];
+    __shared__ u64 s_goff[RADIX];
+    __shared__ u32 s_wsum[SELW_THREADS / 32];
+    constexpr int WPT = LBITS;  // 64 characters = LBITS words
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u64 g0 = ((u64)blockIdx.x * SELW_THREADS + tid) * SELW_CPT;
+    u64 wd[WPT + 1];
+#pragma unroll
+    for (int j = 0; j <= WPT; ++j) wd[j] = 0;
+    u64 mask = 0;
+    if (g0 < A.n_main) {
+        const u64 w0 = (g0 * LBITS) >> 6;
+#pragma unroll
+        for (int j = 0; j <= WPT; ++j) wd[j] = __ldg(A.stream + w0 + j);  // (the stream carries two zero words of padding)
+        const u32 span = A.dhi - A.dlo;
+#pragma unroll
+        for (int c = 0; c < SELW_CPT; ++c) {
+            const int o = c * LBITS, j = o >> 6, off = o & 63;  // compile-time after unrolling
+            const u64 v = off ? ((wd[j] << off) | (wd[j + 1] >> (64 - off))) : wd[j];
+            const u32 d = (u32)(v >> (64 - A.tb));
+            if (d - A.dlo < span && g0 + c < A.n_main) mask |= 1ull << c;
+        }
+    }
+    // sequence numbers of the selected characters in thread order
+    const u32 mine = (u32)__popcll(mask);
+    const u32 incl = warp_inclusive_sum_u32(mine);
+    if (lane == 31) s_wsum[warp] = incl;
+    __syncthreads();
+    u32 tseq = incl - mine, total = 0;
+#pragma unroll
+    for (int w = 0; w < SELW_THREADS / 32; ++w) {
+        if (w < warp) tseq += s_wsum[w];
+        total += s_wsum[w];
+    }
+    const u64 keymask = A.cb >= 64 ? ~0ull : ((1ull << A.cb) - 1ull);
+    for (u32 lo = 0; lo < total; lo += SELW_CAP) {
+        const u32 hi = lo + SELW_CAP < total ? lo + SELW_CAP : total;
+        if (tid < RADIX) s_hist[tid] = 0;
+        __syncthreads();
+        {  // digit counts of this batch
+            u64 mm = mask;
+            u32 seq = tseq;
+            while (mm) {
+                const int c = __ffsll((long long)mm) - 1;
+                mm &= mm - 1;
+                if (seq >= lo && seq < hi) atomicAdd(&s_hist[(u32)(selw_bits<LBITS>(wd, c) >> (64 - A.tb))], 1u);
+                ++seq;
+            }
+        }
+        __syncthreads();
+        // exclusive scan over the digits; one global atomic per non-empty digit reserves its run
+        u32 cnt = 0, inc = 0;
+        if (tid < RADIX) {
+            cnt = s_hist[tid];
+            inc = warp_inclusive_sum_u32(cnt);
+            if (lane == 31) s_wsum[warp] = inc;
+        }
+        __syncthreads();
+        if (tid < RADIX) {
+            u32 pre = 0;
+#pragma unroll
+            for (int w = 0; w < RADIX / 32; ++w) pre += (w < warp) ? s_wsum[w] : 0u;
+            const u32 bstart = pre + inc - cnt;
+            s_pos[tid] = bstart;
+            if (cnt) s_goff[tid] = A.seg_pad[tid] + (u64)atomicAdd(&A.cursor[tid], (unsigned long long)cnt) - (u64)bstart;
+        }
+        __syncthreads();
+        {  // place: any order inside a digit
+            u64 mm = mask;
+            u32 seq = tseq;
+            while (mm) {
+                const int c = __ffsll((long long)mm) - 1;
+                mm &= mm - 1;
+                if (seq >= lo && seq < hi) {
+                    const u64 v = selw_bits<LBITS>(wd, c);
+                    const u32 d = (u32)(v >> (64 - A.tb));
+                    const u32 p = atomicAdd(&s_pos[d], 1u);
+                    sw_stage[p] = (((v >> (64 - A.K)) & keymask) << A.ib) | (g0 + (u64)c);
+                    s_dig[p] = (u8)d;
+                }
+                ++seq;
+            }
+        }
+        __syncthreads();
+        for (u32 s = tid; s < hi - lo; s += SELW_THREADS) st_stream(A.out + s_goff[s_dig[s]] + s, sw_stage[s]);
+        __syncthreads();
+    }
+}
+
+// the T <= 63 suffixes that run past the end of the text: first in their segments, shortest first; also initialises the cursors
+__global__ void __launch_bounds__(64) select_tail_words_kernel(SelectWordsArgs A, u64 n, u64 T, int lbits) {
+    __shared__ u32 s_d[64];
+    const int t = threadIdx.x;
+    u32 d = ~0u;
+    u64 key = 0;
+    const u64 g = n - 1 - (u64)t;
+    if ((u64)t < T) {
+        key = stream_extract(A.stream, g, lbits, A.K);
+        const u32 dd = (u32)(key >> A.cb);
+        if (dd - A.dlo < A.dhi - A.dlo) d = dd;
+    }
+    s_d[t] = d;
+    __syncthreads();
+    if (d != ~0u) {
+        u32 before = 0, all = 0;
+        for (int i = 0; i < 64; ++i) {
+            if (s_d[i] == d) {
+                all += 1;
+                if (i < t) before += 1;
+            }
+        }
+        const u64 keymask = A.cb >= 64 ? ~0ull : ((1ull << A.cb) - 1ull);
+        A.out[A.seg_pad[d] + before] = ((key & keymask) << A.ib) | g;
+        if (before == 0) A.cursor[d] = all;  // (the cursors were zeroed before)
+    }
+}
+
+// histogram of the top key digit of the suffixes [g_lo, g_lo + cnt) (one rank's text block)
+template <int LBITS>
+__global__ void __launch_bounds__(512) digit_hist_kernel(const u64* __restrict__ stream, u64 g_lo, u64 cnt, int tb, u64* __restrict__ hist) {
+    __shared__ u32 sh[4][RADIX];
+    for (int e = threadIdx.x; e < 4 * RADIX; e += blockDim.x) (&sh[0][0])[e] = 0;
+    __syncthreads();
+    u32* my = sh[(threadIdx.x >> 5) & 3];
+    constexpr int WPT = LBITS;
+    for (u64 t0 = ((u64)blockIdx.x * blockDim.x + threadIdx.x) * SELW_CPT; t0 < cnt; t0 += (u64)gridDim.x * blockDim.x * SELW_CPT) {
+        const u64 g0 = g_lo + t0;
+        const u64 bit0 = g0 * LBITS, w0 = bit0 >> 6;
+        const int sh0 = (int)(bit0 & 63);  // a block need not start on a word boundary
+        u64 wd[WPT + 2];
+#pragma unroll
+        for (int j = 0; j <= WPT + 1; ++j) wd[j] = __ldg(stream + w0 + j);
+        if (sh0) {
+#pragma unroll
+            for (int j = 0; j <= WPT; ++j) wd[j] = (wd[j] << sh0) | (wd[j + 1] >> (64 - sh0));
+        }
+#pragma unroll
+        for (int c = 0; c < SELW_CPT; ++c) {
+            const int o = c * LBITS, j = o >> 6, off = o & 63;
+            const u64 v = off ? ((wd[j] << off) | (wd[j + 1] >> (64 - off))) : wd[j];
+            if (t0 + c < cnt) atomicAdd(&my[(u32)(v >> (64 - tb))], 1u);
+        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < RADIX; c += blockDim.x) {
+        const u64 v = (u64)sh[0][c] + sh[1][c] + sh[2][c] + sh[3][c];
+        if (v) atomicAdd((unsigned long long*)&hist[c], (unsigned long long)v);
+    }
+}
+
+template <typename F>
+void dispatch_lbits(int lbits, F&& f) {
+    switch (lbits) {
+        case 1: f(std::integral_constant<int, 1>()); break;
+        case 2: f(std::integral_constant<int, 2>()); break;
+        case 4: f(std::integral_constant<int, 4>()); break;
+        default: f(std::integral_constant<int, 8>()); break;
+    }
+}
+
+// key source of the SA -> ISA step of v2: element g of the sorted words is suffix (word & mask) at SA position off + g; what
+// travels is [index inside the owner's ISA block | rank field | g] (see OwnerPackSrcT).  The pass partitions by
+// digit = (owning rank, middle bits of the block-local index): one run per (destination, ISA window group), so that the
+// receiver's single partition pass by the top index bits ends with windows of 2^-(8 + bshift) of the block -- small enough
+// to stay in L2 while the final scatter fills them.
+struct OwnerMidSrc {
     using Stage = u64;
     using Out = u64;
     static constexpr bool FROM_TEXT = false;
-    static constexpr bool PEER = true;
-    static constexpr bool WORD = false;
-    static constexpr bool ADDR = false;
+    static constexpr bool PEER = false;
     const u64* __restrict__ win;
     u64 word_mask;
-    u64* kpeer[16];
-    u64* vpeer[16];  // unused (keys only)
     BlkDiv div;
     int rank_shift, idx_shift;
     u32 rank_mask;
     u64 me;
+    int mshift, bshift;  // digit = owner << bshift | (local >> mshift) & ((1 << bshift) - 1)
     __device__ __forceinline__ Stage load_key(size_t g) const {
         u64 local;
         const u64 owner = div.owner(ld_stream(win + g) & word_mask, &local);
         return (local << idx_shift) | (owner << rank_shift) | (u64)g;
     }
-    __device__ __forceinline__ u32 digit(Stage k) const { return (u32)(k >> rank_shift) & rank_mask; }
+    __device__ __forceinline__ u32 digit(Stage k) const {
+        const u32 owner = (u32)(k >> rank_shift) & rank_mask;
+        return (owner << bshift) | ((u32)((k >> idx_shift) >> mshift) & ((1u << bshift) - 1u));
+    }
     __device__ __forceinline__ Out out_key(Stage k) const { return (k & ~((u64)rank_mask << rank_shift)) | (me << rank_shift); }
     __device__ __forceinline__ NoVal load_val(size_t) const { return NoVal(); }
     __device__ __forceinline__ u8 load_aux(size_t, Stage) const { return 0; }
@@ -1196,6 +1400,7 @@ bool construct_sharded_v2(psacb200_engine* e, const ShardComm& C, const u8* d_te
     const int lbits = alpha.lbits;
     u64* stream = e->packed.as<u64>();
 
+    e->mark("text");
     // ---- key shape: K = tb (top digit) + cb (carried) bits, cb + ib <= 64
     const int ib = std::max(1, (int)bits_for(n - 1));
     const u64 word_mask = (1ull << ib) - 1ull;
@@ -1209,40 +1414,28 @@ bool construct_sharded_v2(psacb200_engine* e, const ShardComm& C, const u8* d_te
     if (T > blk.size(p - 1)) return false;  // the suffixes that run past the end must all lie in the last block
     S.key_chars = Cc;
 
-    // ---- pass 1, first half: per-tile histogram of the top digit over my text block; digit totals all-gathered
-    using TT = SortTuning<u64, NoVal, true>;
-    using Src1 = TextWordSrc;
-    using Cfg1 = PassCfg<Src1, NoVal, TT::THREADS, TT::ITEMS, true>;
+    // ---- digit histogram of my text block, all-gathered: segment sizes and digit ownership (host plan)
     const size_t LTILE = word_sort_tile();
     e->begin(PH_SORT);
-    e->segws.reserve((2 * (RADIX + 1) + RADIX * RADIX) * sizeof(u64) + 256 + (size_t)(p + 1) * 257 * sizeof(u64) + 257 * sizeof(u64), tot);
-    e->lookback.reserve(lookback_bytes(n_local + 4 * LTILE), tot);
-    RadixWorkspace ws = e->radix_ws();
-    Src1 src1{stream, n, me == p - 1 ? T : 0, blk.start(me), lbits, K, ib, (u32)(nb - 1), cb};
-    const size_t tiles1 = div_up(n_local ? n_local : 1, (size_t)Cfg1::TILE), chunks1 = div_up(tiles1, (size_t)SCAN_CHUNK);
-    const size_t counts1_bytes = align_up(tiles1 * RADIX * sizeof(u32), 256);
-    if (counts1_bytes + chunks1 * RADIX * sizeof(u64) > ws.tiles_bytes) throw std::string("radix pass: tile workspace too small");
-    u32* counts1 = reinterpret_cast<u32*>(ws.tiles);
-    u64* chunk_tot1 = reinterpret_cast<u64*>(reinterpret_cast<char*>(ws.tiles) + counts1_bytes);
-    u64* d_segtab = e->segws.as<u64>();                                    // seg_dense[257], seg_pad[257], segbase[256][256]
-    u64* d_cnt = d_segtab + 2 * (RADIX + 1) + RADIX * RADIX + 32;          // [p][257] dense digit starts of every block
-    u64* d_dummy = d_cnt + (size_t)p * 257;                                // [257]
-    if (n_local) {
-        text_tile_hist_kernel<Src1, TT::THREADS, TT::ITEMS><<<(unsigned)tiles1, TT::THREADS, 0, st>>>(src1, n_local, counts1);
-        tile_scan_chunks_kernel<<<(unsigned)chunks1, RADIX, 0, st>>>(counts1, tiles1, chunk_tot1);
-        tile_scan_top_kernel<<<1, RADIX, 0, st>>>(chunk_tot1, chunks1, nullptr, d_cnt + (size_t)me * 257, d_dummy, 1);
-        e->launches += 3;
-        PSAC_CUDA(cudaGetLastError());
-    } else {
-        PSAC_CUDA(cudaMemsetAsync(d_cnt + (size_t)me * 257, 0, 257 * sizeof(u64), st));
-    }
-    PSAC_NCCL(g_nccl.AllGather(d_cnt + (size_t)me * 257, d_cnt, 257, ncclUint64, C.comm, st));
-    std::vector<u64> h_dense((size_t)p * 257);
-    PSAC_CUDA(cudaMemcpyAsync(h_dense.data(), d_cnt, h_dense.size() * sizeof(u64), cudaMemcpyDeviceToHost, st));
+    e->segws.reserve((2 * (RADIX + 1) + RADIX * RADIX) * sizeof(u64) + 256 + (size_t)(p + 2) * RADIX * sizeof(u64), tot);
+    u64* d_segtab = e->segws.as<u64>();                              // seg_dense[257], seg_pad[257], segbase[256][256]
+    u64* d_cnt = d_segtab + 2 * (RADIX + 1) + RADIX * RADIX + 32;    // [p][256] digit counts of every block
+    unsigned long long* d_cursor = reinterpret_cast<unsigned long long*>(d_cnt + (size_t)p * RADIX);  // [256]
+    PSAC_CUDA(cudaMemsetAsync(d_cnt + (size_t)me * RADIX, 0, RADIX * sizeof(u64), st));
+    PSAC_CUDA(cudaMemsetAsync(d_cursor, 0, RADIX * sizeof(u64), st));
+    dispatch_lbits(lbits, [&](auto LB) {
+        digit_hist_kernel<decltype(LB)::value><<<grid_for(e, n_local / SELW_CPT + 1, 512, 4), 512, 0, st>>>(stream, blk.start(me), n_local, tb, d_cnt + (size_t)me * RADIX);
+    });
+    e->launches += 1;
+    PSAC_CUDA(cudaGetLastError());
+    e->mark("p1_hist");
+    PSAC_NCCL(g_nccl.AllGather(d_cnt + (size_t)me * RADIX, d_cnt, RADIX, ncclUint64, C.comm, st));
+    std::vector<u64> h_cnt((size_t)p * RADIX);
+    PSAC_CUDA(cudaMemcpyAsync(h_cnt.data(), d_cnt, h_cnt.size() * sizeof(u64), cudaMemcpyDeviceToHost, st));
     PSAC_CUDA(cudaStreamSynchronize(st));
     std::vector<u64> cnt_sd((size_t)p * nb);
     for (int s = 0; s < p; ++s)
-        for (int d = 0; d < nb; ++d) cnt_sd[(size_t)s * nb + d] = h_dense[(size_t)s * 257 + d + 1] - h_dense[(size_t)s * 257 + d];
+        for (int d = 0; d < nb; ++d) cnt_sd[(size_t)s * nb + d] = h_cnt[(size_t)s * RADIX + d];
     WordExchangePlan P;
     plan_word_exchange(cnt_sd.data(), p, nb, n, cb > 0 ? (u64)LTILE : 1, P);
     if (!P.balanced) return false;  // top key digits too skewed for digit-boundary splitters
@@ -1263,16 +1456,7 @@ bool construct_sharded_v2(psacb200_engine* e, const ShardComm& C, const u8* d_te
     u64* ISA = at(me, oISA);
     S.reserved = 1u;
     e->lookback.reserve(lookback_bytes(std::max<u64>(PADE, n_local) + 4 * LTILE), tot);
-    ws = e->radix_ws();  // (the buffer may have moved; the tile counts of pass 1 are recomputed below in that case)
-    const bool moved = ws.tiles != (void*)counts1;
-    if (moved && n_local) {
-        counts1 = reinterpret_cast<u32*>(ws.tiles);
-        chunk_tot1 = reinterpret_cast<u64*>(reinterpret_cast<char*>(ws.tiles) + counts1_bytes);
-        text_tile_hist_kernel<Src1, TT::THREADS, TT::ITEMS><<<(unsigned)tiles1, TT::THREADS, 0, st>>>(src1, n_local, counts1);
-        tile_scan_chunks_kernel<<<(unsigned)chunks1, RADIX, 0, st>>>(counts1, tiles1, chunk_tot1);
-        tile_scan_top_kernel<<<1, RADIX, 0, st>>>(chunk_tot1, chunks1, nullptr, d_cnt + (size_t)me * 257, d_dummy, 1);
-        e->launches += 3;
-    }
+    RadixWorkspace ws = e->radix_ws();
     const size_t rows = (size_t)(P.seg_pad[(size_t)me * 257 + 256] / LTILE) + 1;
     SegWorkspace sw;
     sw.seg_dense = d_segtab;
@@ -1280,33 +1464,43 @@ bool construct_sharded_v2(psacb200_engine* e, const ShardComm& C, const u8* d_te
     sw.segbase = sw.seg_pad + (RADIX + 1);
     e->tb[0].reserve(rows * sizeof(u32) + 256, tot);
     sw.tile_info = e->tb[0].as<u32>();
-
-    // ---- upload my segment tables and the destination addresses of my runs
-    u64* hp = e->h_pinned + 512;  // [0..256] seg_dense, [257..513] seg_pad, [514..769] addresses
+    // my segment tables
+    u64* hp = e->h_pinned + 512;  // [0..256] seg_dense, [257..513] seg_pad
     for (int d = 0; d <= 256; ++d) {
         hp[d] = P.seg_dense[(size_t)me * 257 + d];
         hp[257 + d] = P.seg_pad[(size_t)me * 257 + d];
     }
-    for (int d = 0; d < 256; ++d) {
-        u64 a = 0;
-        if (d < nb) a = (u64)(uintptr_t)(at(P.owner[d], oW[0]) + P.run_off[(size_t)me * nb + d]);
-        hp[514 + d] = a;
-    }
     PSAC_CUDA(cudaMemcpyAsync(sw.seg_dense, hp, 2 * 257 * sizeof(u64), cudaMemcpyHostToDevice, st));
-    PSAC_CUDA(cudaMemcpyAsync(ws.gbase, hp + 514, 256 * sizeof(u64), cudaMemcpyHostToDevice, st));
+    e->mark("p1_plan");
 
-    // ---- pass 1, second half: the scatter kernel stores every digit's run into its owner's HBM (fused exchange)
-    rank_barrier(e, C);  // every rank is done with the word buffers of its previous call
-    if (n_local) {
-        auto kern1 = radix_scatter_kernel<Src1, NoVal, TT::THREADS, TT::ITEMS, true, TT::MINB, false>;
-        auto kern1_safe = radix_scatter_kernel<Src1, NoVal, TT::THREADS, TT::ITEMS, true, TT::MINB, true>;
-        PSAC_LAUNCH_RANKED(kern1, kern1_safe, Cfg1::SMEM, (unsigned)tiles1, TT::THREADS, st, src1, (u64*)nullptr, (NoVal*)nullptr, (u8*)nullptr, (size_t)n_local,
-                           ws.gbase, chunk_tot1, counts1);
-        e->launches += 1;
+    // ---- pass 1: select my digit range out of the whole (replicated) text, straight into the padded segment layout
+    rank_barrier(e, C);  // the peers have pulled their SA blocks out of my word buffers (previous call)
+    {
+        SelectWordsArgs SA_{};
+        SA_.stream = stream;
+        SA_.n_main = n - T;
+        SA_.K = K;
+        SA_.tb = tb;
+        SA_.cb = cb;
+        SA_.ib = ib;
+        SA_.dlo = (u32)P.first[me];
+        SA_.dhi = (u32)P.first[me + 1];
+        SA_.seg_pad = sw.seg_pad;
+        SA_.cursor = d_cursor;
+        SA_.out = W[0];
+        select_tail_words_kernel<<<1, 64, 0, st>>>(SA_, n, T, lbits);
+        const u64 ctas = div_up(SA_.n_main ? SA_.n_main : 1, (size_t)SELW_THREADS * SELW_CPT);
+        dispatch_lbits(lbits, [&](auto LB) {
+            auto kern = select_words_kernel<decltype(LB)::value>;
+            static bool seen[64] = {};
+            if (first_use_on_device(seen)) PSAC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SELW_CAP * sizeof(u64))));
+            kern<<<(unsigned)ctas, SELW_THREADS, SELW_CAP * sizeof(u64), st>>>(SA_);
+        });
+        e->launches += 2;
         PSAC_CUDA(cudaGetLastError());
     }
-    rank_barrier(e, C);  // all runs have landed
     cudaEventRecord(e->ev_end[PH_PASS1], st);
+    e->mark("p1_select");
 
     // ---- the remaining digits, LSD inside my segments
     int x = 0;
@@ -1319,7 +1513,30 @@ bool construct_sharded_v2(psacb200_engine* e, const ShardComm& C, const u8* d_te
     }
     S.sort_passes = 1 + plan_used.npass;
     e->end(PH_SORT);
+    e->mark("lsd");
     u64* Wx = W[x];  // sorted words, dense: SA positions [off, off + cnt)
+
+    // ---- SA -> ISA, part A (before the heads: it needs the sorted words only -- every suffix sends its POSITION, the
+    //      unresolved ones are fixed up to their bucket head afterwards).  Local partition of the exchange words by
+    //      (owner, window group) into the spare word buffer; the bin starts of all ranks are all-gathered.
+    e->begin(PH_ISA);
+    const int rank_shift = rel_bits, idx_shift = rel_bits + rank_bits;
+    const int bshift = RADIX_BITS - rank_bits;                       // window groups per owner = 1 << bshift
+    const int hshift = idx_bits > RADIX_BITS ? idx_bits - RADIX_BITS : 0;  // receiver's pass: top 8 bits of the local index
+    const int mshift = hshift > bshift ? hshift - bshift : 0;
+    u64* Sbuf = W[1 - x];
+    u64* h_bstart = e->h_pinned + 1024;  // [p][256] bin starts of every rank's partition (pinned)
+    {
+        OwnerMidSrc src{Wx, word_mask, BlkDiv::make(n, p), rank_shift, idx_shift, (1u << rank_bits) - 1u, (u64)me, mshift, bshift};
+        launch_pass<OwnerMidSrc, NoVal, false>(ws, src, Sbuf, nullptr, nullptr, cnt, st);
+        e->launches += LAUNCHES_PER_PASS;
+        PSAC_CUDA(cudaGetLastError());
+        PSAC_CUDA(cudaMemcpyAsync(d_cnt + (size_t)me * RADIX, ws.gbase, RADIX * sizeof(u64), cudaMemcpyDeviceToDevice, st));
+        PSAC_NCCL(g_nccl.AllGather(d_cnt + (size_t)me * RADIX, d_cnt, RADIX, ncclUint64, C.comm, st));
+        PSAC_CUDA(cudaMemcpyAsync(h_bstart, d_cnt, (size_t)p * RADIX * sizeof(u64), cudaMemcpyDeviceToHost, st));
+        PSAC_CUDA(cudaEventRecord(e->ev_x[0], st));
+    }
+    e->mark("isa_owner");
 
     // ---- resolve round 0 (heads, LCP, unresolved list) on the sorted words
     e->begin(PH_RESOLVE);
@@ -1379,6 +1596,37 @@ bool construct_sharded_v2(psacb200_engine* e, const ShardComm& C, const u8* d_te
     e->launches += 6;
     PSAC_CUDA(cudaGetLastError());
     e->end(PH_RESOLVE);
+    e->mark("heads");
+    // ---- SA -> ISA, part X (queued now, while the heads kernels run): every (destination, window group) run goes to the
+    //      destination's receive buffer with the copy engines (peer-mapped memory), group-major / source-minor
+    {
+        cudaStream_t cs = e->copy_stream;
+        PSAC_CUDA(cudaEventSynchronize(e->ev_x[0]));  // (the heads kernels are queued behind it and keep the GPU busy)
+        const int B = 1 << bshift;
+        auto count_of = [&](int s_, int bin) {
+            const u64 a0 = h_bstart[(size_t)s_ * RADIX + bin];
+            const u64 a1 = bin + 1 < RADIX ? h_bstart[(size_t)s_ * RADIX + bin + 1] : P.cnt_key[s_];
+            return a1 - a0;
+        };
+        PSAC_CUDA(cudaStreamWaitEvent(cs, e->ev_x[0], 0));
+        for (int b = 0; b < p; ++b) {
+            u64 run = 0;
+            for (int mgrp = 0; mgrp < B; ++mgrp)
+                for (int s_ = 0; s_ < p; ++s_) {
+                    const int bin = b * B + mgrp;
+                    const u64 len = count_of(s_, bin);
+                    if (s_ == me && len)
+                        PSAC_CUDA(cudaMemcpyAsync(at(b, oR0) + run, Sbuf + h_bstart[(size_t)me * RADIX + bin], len * sizeof(u64), cudaMemcpyDeviceToDevice, cs));
+                    run += len;
+                }
+            if (run != blk.size(b)) throw std::string("sharded construction: exchange plan does not cover the block");
+        }
+        // all pushes have landed everywhere: barrier on the copy stream, then the main stream may read the receive buffer
+        ShardComm C2{reinterpret_cast<ncclComm_t>(e->nccl_comm2 ? e->nccl_comm2 : e->nccl_comm), C.rank, C.world};
+        u64* d_b = e->shard_meta() + 60;
+        PSAC_NCCL(g_nccl.AllReduce(d_b, d_b, 1, ncclUint64, ncclSum, C2.comm, cs));
+        PSAC_CUDA(cudaEventRecord(e->ev_x[1], cs));
+    }
     // unresolved: mine and the total over the ranks
     u64* d_m = e->shard_meta() + 32;  // [0] mine, [1] sum
     auto read_unresolved = [&](u64* mine, u64* total) {
@@ -1406,38 +1654,20 @@ bool construct_sharded_v2(psacb200_engine* e, const ShardComm& C, const u8* d_te
         PSAC_CUDA(cudaGetLastError());
     }
 
-    // ---- SA -> ISA: positions to the owners of the ISA entries (fused owner partition + exchange), windowed scatter
-    e->begin(PH_ISA);
+    e->mark("counts");
+    // ---- SA -> ISA, parts B and S: once all runs have landed, the receiver's partition pass by the top index bits and the
+    //      windowed scatter into my ISA block
     {
-        // X[b][a] = suffixes of text block b in key range a (from the digit counts)
-        std::vector<u64> X((size_t)p * p, 0);
-        for (int b = 0; b < p; ++b)
-            for (int d = 0; d < nb; ++d) X[(size_t)b * p + P.owner[d]] += cnt_sd[(size_t)b * nb + d];
-        const int rank_shift = rel_bits, idx_shift = rel_bits + rank_bits;
-        OwnerWordSrc src{Wx, word_mask, {}, {}, BlkDiv::make(n, p), rank_shift, idx_shift, (1u << rank_bits) - 1u, (u64)me};
-        u64 sd = 0;
-        for (int b = 0; b < p; ++b) {
-            u64 rd = 0;  // displacement of source `me` in receiver b's buffer
-            for (int a = 0; a < me; ++a) rd += X[(size_t)b * p + a];
-            src.kpeer[b] = at(b, oR0) + rd - sd;
-            src.vpeer[b] = nullptr;
-            sd += X[(size_t)b * p + me];
-        }
-        if (sd != cnt) throw std::string("sharded construction: exchange plan does not add up");
-        for (int b = p; b < 16; ++b) src.kpeer[b] = src.vpeer[b] = nullptr;
-        rank_barrier(e, C);
-        launch_pass<OwnerWordSrc, NoVal, false>(ws, src, nullptr, nullptr, nullptr, cnt, st);
-        e->launches += LAUNCHES_PER_PASS;
-        rank_barrier(e, C);
+        PSAC_CUDA(cudaStreamWaitEvent(st, e->ev_x[1], 0));
+        e->mark("isa_landed");
         const u64* words = at(me, oR0);
         if (n_local >= (1ull << 22)) {
-            // window partition by the top 8 bits of the local index, so that the scattered writes merge in L2
-            const int shift2 = idx_shift + (idx_bits > RADIX_BITS ? idx_bits - RADIX_BITS : 0);
-            ArraySrc<u64, NoVal> wsrc{words, nullptr, nullptr, shift2, (u32)(RADIX - 1), 0ull};
+            ArraySrc<u64, NoVal> wsrc{words, nullptr, nullptr, idx_shift + hshift, (u32)(RADIX - 1), 0ull};
             launch_pass<ArraySrc<u64, NoVal>, NoVal, false>(ws, wsrc, at(me, oR1), nullptr, nullptr, n_local, st);
             e->launches += LAUNCHES_PER_PASS;
             words = at(me, oR1);
         }
+        e->mark("isa_window");
         PackedScatterArgs PA{};
         PA.words = words;
         PA.isa = ISA;
@@ -1453,6 +1683,7 @@ bool construct_sharded_v2(psacb200_engine* e, const ShardComm& C, const u8* d_te
         }
         PSAC_CUDA(cudaGetLastError());
     }
+    e->mark("isa_scatter");
     e->end(PH_ISA);
 
     // ---- later rounds, distributed: every rank sorts its own unresolved suffixes
@@ -1575,6 +1806,7 @@ bool construct_sharded_v2(psacb200_engine* e, const ShardComm& C, const u8* d_te
         e->end(PH_ROUNDS);
     }
 
+    e->mark("rounds");
     // ---- outputs: SA pulled from the key-range owners into exact blocks; LCP re-balanced; ISA is block-distributed already
     e->begin(PH_OUTPUT);
     {
@@ -1594,6 +1826,7 @@ bool construct_sharded_v2(psacb200_engine* e, const ShardComm& C, const u8* d_te
                 pull_sa_kernel<u32><<<grid_for(e, n_local, 256, 16), 256, 0, st>>>(PL);
             e->launches += 1;
         }
+        e->mark("out_sa");
         const u64 text_lo = blk.start(me), text_hi = text_lo + n_local;
         if (want_lcp) {
             std::vector<u64> scount(p), sdispl(p), rcount(p), rdispl(p);
@@ -1613,6 +1846,7 @@ bool construct_sharded_v2(psacb200_engine* e, const ShardComm& C, const u8* d_te
                 e->launches += 1;
             }
         }
+        e->mark("out_lcp");
         if (isa_out && n_local) {
             if (index_bytes == 8)
                 PSAC_CUDA(cudaMemcpyAsync(isa_out, ISA, n_local * sizeof(u64), cudaMemcpyDeviceToDevice, st));
@@ -1623,6 +1857,7 @@ bool construct_sharded_v2(psacb200_engine* e, const ShardComm& C, const u8* d_te
         }
         PSAC_CUDA(cudaGetLastError());
     }
+    e->mark("out_isa");
     e->end(PH_OUTPUT);
     return true;
 }
