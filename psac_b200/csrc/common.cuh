@@ -95,39 +95,69 @@ __device__ __forceinline__ u64 stream_extract(const u64* __restrict__ stream, u6
 
 // ---------------------------------------------------------------- block distribution on the device
 // mxx::blk_dist (reference ext/mxx/include/mxx/partition.hpp:283-331): n elements over p ranks, the first n % p ranks
-// hold one element more.  owner() divides by multiplication with a double reciprocal plus one correction step (exact:
-// the quotient fits 4 bits, the operands 40).
+// hold one element more.  owner() estimates the quotient with one 32-bit multiply-high and corrects it against the block starts.
 struct BlkDiv {
-    u64 cut, base1, base;  // cut = rem * (base + 1); base1 = base + 1; base >= 1
-    u32 rem;
-    double inv_base1, inv_base;
+    u64 cut, base1, base;  // cut = rem * (base + 1); base1 = base + 1
+    u32 rem, p;
+    u32 sh, magic32;       // quotient estimate: umulhi(g >> sh, magic32) <= g / block size, at most 2 below it
     __host__ static BlkDiv make(u64 n, int p) {
         BlkDiv d;
         const u64 b = n / (u64)p;
+        d.p = (u32)p;
         d.rem = (u32)(n % (u64)p);
-        d.base = b ? b : 1;
+        d.base = b;
         d.base1 = b + 1;
         d.cut = (u64)d.rem * (b + 1);
-        d.inv_base1 = 1.0 / (double)d.base1;
-        d.inv_base = 1.0 / (double)d.base;
+        d.sh = 0;
+        while ((n >> d.sh) >> 32) ++d.sh;
+        const u64 d32 = (d.base1 >> d.sh) + 1;  // over-estimates the divisor: the quotient estimate never overshoots
+        d.magic32 = d32 >= 2 ? (u32)((1ull << 32) / d32) : 0xffffffffu;
         return d;
     }
-    __device__ __forceinline__ static u64 divide(u64 x, u64 d, double inv) {
-        u64 q = (u64)__double2ull_rz((double)x * inv);
-        if (q * d > x) --q;
-        if ((q + 1) * d <= x) ++q;
+    __device__ __forceinline__ u64 start(u32 r) const { return (u64)r * base + (u64)(r < rem ? r : rem); }
+    // owner of global index g (g < n) and its index inside the owner's block; integer instructions only
+    __device__ __forceinline__ u32 owner(u64 g, u64* local) const {
+        u32 q = __umulhi((u32)(g >> sh), magic32);
+        q = q < p - 1 ? q : p - 1;
+        u64 st = start(q);
+        if (q + 1 < p) {
+            u64 nx = start(q + 1);
+            if (g >= nx) {
+                ++q;
+                st = nx;
+                if (q + 1 < p) {
+                    nx = start(q + 1);
+                    if (g >= nx) {
+                        ++q;
+                        st = nx;
+                        // (blocks smaller than 2^16 elements: the estimate may be further off)
+                        while (q + 1 < p && g >= start(q + 1)) st = start(++q);
+                    }
+                }
+            }
+        }
+        *local = g - st;
         return q;
     }
-    __device__ __forceinline__ u32 owner(u64 g, u64* local) const {
-        if (g < cut) {
-            const u64 q = divide(g, base1, inv_base1);
-            *local = g - q * base1;
-            return (u32)q;
-        }
-        const u64 q = divide(g - cut, base, inv_base);
-        *local = g - cut - q * base;
-        return rem + (u32)q;
+};
+
+// The suffix-index field of a sort word of the sharded construction: (owning rank of the suffix's ISA entry, index inside
+// that rank's text block) instead of the global index -- every later step that routes by owner (the SA -> ISA exchange)
+// reads it with two shifts, and the owner is computed once per 64 characters where the word is made.
+struct WordIdx {
+    BlkDiv div;
+    int lb;    // bits of the block-local index
+    u64 mask;  // mask of the whole field (lb + rank bits)
+    __device__ __forceinline__ u64 decode(u64 w) const {
+        const u64 f = w & mask;
+        return div.start((u32)(f >> lb)) + (f & ((1ull << lb) - 1ull));
     }
+    __device__ __forceinline__ u64 encode(u64 g) const {
+        u64 local;
+        const u64 o = div.owner(g, &local);
+        return (o << lb) | local;
+    }
+    __device__ __forceinline__ u64 block_size(u32 r) const { return div.base + (r < div.rem ? 1u : 0u); }
 };
 
 // ---------------------------------------------------------------- decoupled look-back channel

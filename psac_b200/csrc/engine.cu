@@ -82,8 +82,12 @@ struct psacb200_engine {
     DevBuf text, packed, keys[2], vals[2], vals2, segws, isa, lcp, small, lookback, rk[2], rv[2], rp[2], rh[2], scratch, rep[3], tb[6];
     void* nccl_comm = nullptr;  // ncclComm_t of the sharded construction (sharded.cuh), one rank per engine
     void* nccl_comm2 = nullptr; // a split of it for the copy stream (barrier of the SA -> ISA exchange), or null
-    cudaStream_t copy_stream = nullptr;  // peer copies of the SA -> ISA exchange (copy engines), overlapping the main stream
+    static constexpr int COPY_STREAMS = 4;
+    cudaStream_t copy_streams[COPY_STREAMS];  // peer copies of the SA -> ISA exchange (copy engines), overlapping the main stream
+    cudaEvent_t ev_cs[COPY_STREAMS];
     cudaEvent_t ev_x[2];
+    cudaEvent_t ev_xt[3];  // copy-stream timeline of the exchange: first copy, last copy, barrier
+    bool xt_used = false;
     void* peer_map = nullptr;   // PeerArena: peer-visible memory of the sharded construction (sharded.cuh)
     int shard_rank = 0, shard_world = 1;
     u64* h_pinned = nullptr;  // 8192 u64 of pinned host memory for small read-backs and plan uploads
@@ -829,8 +833,12 @@ int psacb200_create(int device, psacb200_engine** out) {
         e->device = device;
         e->sm_count = prop.multiProcessorCount;
         PSAC_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
-        PSAC_CUDA(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < psacb200_engine::COPY_STREAMS; ++i) {
+            PSAC_CUDA(cudaStreamCreateWithFlags(&e->copy_streams[i], cudaStreamNonBlocking));
+            PSAC_CUDA(cudaEventCreateWithFlags(&e->ev_cs[i], cudaEventDisableTiming));
+        }
         for (int i = 0; i < 2; ++i) PSAC_CUDA(cudaEventCreateWithFlags(&e->ev_x[i], cudaEventDisableTiming));
+        for (int i = 0; i < 3; ++i) PSAC_CUDA(cudaEventCreate(&e->ev_xt[i]));
         PSAC_CUDA(cudaMallocHost((void**)&e->h_pinned, 8192 * sizeof(u64)));
         for (int i = 0; i < PH_COUNT; ++i) {
             PSAC_CUDA(cudaEventCreate(&e->ev_begin[i]));
@@ -880,7 +888,11 @@ void psacb200_destroy(psacb200_engine* e) {
     if (e->nccl_comm2 && g_nccl.CommDestroy) g_nccl.CommDestroy(reinterpret_cast<ncclComm_t>(e->nccl_comm2));
     if (e->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(reinterpret_cast<ncclComm_t>(e->nccl_comm));
     for (int i = 0; i < 2; ++i) cudaEventDestroy(e->ev_x[i]);
-    cudaStreamDestroy(e->copy_stream);
+    for (int i = 0; i < 3; ++i) cudaEventDestroy(e->ev_xt[i]);
+    for (int i = 0; i < psacb200_engine::COPY_STREAMS; ++i) {
+        cudaStreamDestroy(e->copy_streams[i]);
+        cudaEventDestroy(e->ev_cs[i]);
+    }
     if (e->h_pinned) cudaFreeHost(e->h_pinned);
     cudaStreamDestroy(e->stream);
     delete e;
@@ -902,6 +914,18 @@ int psacb200_trace(psacb200_engine* e, char* buf, size_t buf_len) {
         char tmp[96];
         snprintf(tmp, sizeof(tmp), "%s=%.3f;", e->tr_name[i], t);
         out += tmp;
+    }
+    if (e->xt_used && e->tr_n > 0) {
+        cudaStreamSynchronize(e->copy_streams[0]);
+        float a = 0.f, b = 0.f, c = 0.f;
+        if (cudaEventElapsedTime(&a, e->tr_ev[0], e->ev_xt[0]) == cudaSuccess && cudaEventElapsedTime(&b, e->ev_xt[0], e->ev_xt[1]) == cudaSuccess &&
+            cudaEventElapsedTime(&c, e->ev_xt[1], e->ev_xt[2]) == cudaSuccess) {
+            char tmp[160];
+            snprintf(tmp, sizeof(tmp), "x_start_at=%.3f;x_copies=%.3f;x_barrier=%.3f;", a, b, c);
+            out += tmp;
+        } else {
+            cudaGetLastError();
+        }
     }
     snprintf(buf, buf_len, "%s", out.c_str());
     return PSACB200_OK;
@@ -1096,12 +1120,13 @@ int psacb200_construct_sharded(psacb200_engine* e, const uint8_t* d_text_local, 
         ShardComm C{reinterpret_cast<ncclComm_t>(e->nccl_comm), e->shard_rank, e->shard_world};
         const u64 n = n_global;
         if (n == 0) return PSACB200_OK;
-        bool sharded = C.world > 1 && n >= (u64)C.world * (1ull << 16);
+        bool sharded = (C.world > 1 || getenv("PSACB200_FORCE_SHARDED")) && n >= (u64)C.world * (1ull << 16);  // (forced at one rank: profiling)
         if (sharded) {
             memset(&e->stats, 0, sizeof(e->stats));
             memset(e->ev_used, 0, sizeof(e->ev_used));
             e->scatter_passes = 0;
             e->tr_n = 0;
+            e->xt_used = false;
             e->stats.n = n;
             e->begin(PH_TOTAL);
             e->mark("begin");

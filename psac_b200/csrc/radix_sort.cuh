@@ -50,6 +50,12 @@ __device__ unsigned long long g_phase_cycles[16];
 
 struct NoVal {};  // keys-only sort
 
+// sources may offer hist_digit(g): the digit of element g without building the complete staged key (histogram pre-pass)
+template <class Src, class = void>
+struct has_hist_digit : std::false_type {};
+template <class Src>
+struct has_hist_digit<Src, std::void_t<decltype(std::declval<const Src&>().hist_digit((size_t)0))>> : std::true_type {};
+
 constexpr int RADIX_BITS = 8;
 constexpr int RADIX = 1 << RADIX_BITS;
 constexpr int MAX_PASSES = 8;
@@ -393,15 +399,23 @@ __global__ void __launch_bounds__(THREADS) tile_hist_kernel(const Src src, size_
     __syncthreads();
     const size_t base = (size_t)blockIdx.x * TILE;
     const int valid = (n - base >= (size_t)TILE) ? TILE : (int)(n - base);
-    typename Src::Stage key[ITEMS];
+    if constexpr (has_hist_digit<Src>::value) {
 #pragma unroll
-    for (int j = 0; j < ITEMS; ++j) {
-        const int o = j * THREADS + threadIdx.x;
-        if (o < valid) key[j] = src.load_key(base + o);
-    }
+        for (int j = 0; j < ITEMS; ++j) {
+            const int o = j * THREADS + threadIdx.x;
+            if (o < valid) atomicAdd(&sh[src.hist_digit(base + o)], 1u);
+        }
+    } else {
+        typename Src::Stage key[ITEMS];
 #pragma unroll
-    for (int j = 0; j < ITEMS; ++j) {
-        if (j * THREADS + (int)threadIdx.x < valid) atomicAdd(&sh[src.digit(key[j])], 1u);
+        for (int j = 0; j < ITEMS; ++j) {
+            const int o = j * THREADS + threadIdx.x;
+            if (o < valid) key[j] = src.load_key(base + o);
+        }
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) {
+            if (j * THREADS + (int)threadIdx.x < valid) atomicAdd(&sh[src.digit(key[j])], 1u);
+        }
     }
     __syncthreads();
     if (threadIdx.x < RADIX) counts[(size_t)blockIdx.x * RADIX + threadIdx.x] = sh[threadIdx.x];

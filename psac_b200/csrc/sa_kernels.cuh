@@ -169,6 +169,7 @@ struct ResolveArgs {
     //      position) and puts the new bucket ids into the owners' ISA blocks through peer memory
     PeerIsa pisa;         // pisa.p > 0: ISA[s] = isa_add + bucket goes to pisa.at(s) instead of isa[]
     u64 isa_add;          // first SA position of this rank (bucket ids are global positions)
+    WordIdx widx;         // widx.lb > 0: sa[] holds sort words, the suffix is stored as its (owner, local index) field
 };
 
 constexpr int RES_THREADS = 256;
@@ -345,7 +346,7 @@ __global__ void __launch_bounds__(RES_THREADS) resolve_kernel(ResolveArgs A) {
         else if (isa != nullptr && s >= A.isa_lo && s < A.isa_hi)
             isa[s - A.isa_lo] = (IdxT)bucket[i];
         const bool own_pos = FIRST || (pos[i] >= A.sa_lo && pos[i] < A.sa_hi);
-        if (!FIRST && own_pos) sa[pos[i] - A.sa_lo] = (IdxT)s;
+        if (!FIRST && own_pos) sa[pos[i] - A.sa_lo] = (IdxT)(A.widx.lb > 0 ? A.widx.encode(s) : s);
         if (lcp != nullptr && head[i] && own_pos) {
             if (q == 0 && !has_halo) {
                 if (FIRST) lcp[0] = 0;
@@ -505,8 +506,8 @@ struct HeadsArgs {
     u64* agg_sum;          // per tile: unresolved elements / exclusive prefix
     u64 pos_base;          // sharded construction: SA position of local element 0 (bucket ids and positions are global)
     const u64* halo;       // sharded construction: {key, suffix} of the last element of the previous shard, or null
-    int word_shift;        // WORD: the keys are 64-bit words [carried key | suffix index]: the key is word >> word_shift,
-    u64 word_mask;         //       the suffix index word & word_mask (vals is not read)
+    int word_shift;        // WORD: the keys are 64-bit words [carried key | suffix index field]: the key is word >> word_shift,
+    WordIdx widx;          //       the suffix index widx.decode(word) (vals is not read)
 };
 
 constexpr int HD_THREADS = 256;
@@ -743,7 +744,7 @@ __global__ void __launch_bounds__(HD_THREADS) heads_kernel(HeadsArgs A) {
         if (q0 == 0) {
             if (A.halo != nullptr) {
                 // boundary with the previous shard: cap by the lengths of both suffixes (either may run past the end)
-                const u64 s0 = WORD ? ((u64)keys[0] & A.word_mask) : (u64)vals[0];
+                const u64 s0 = WORD ? A.widx.decode((u64)keys[0]) : (u64)vals[0];
                 const u64 la = A.n - A.halo[1], lb = A.n - s0;
                 l[0] = l[0] < la ? l[0] : (u32)la;
                 l[0] = l[0] < lb ? l[0] : (u32)lb;
@@ -777,7 +778,7 @@ __global__ void __launch_bounds__(HD_THREADS) heads_kernel(HeadsArgs A) {
             A.head_out[o] = (head >> i) & 1u;
             if (A.suf_out != nullptr) {
                 if (WORD)
-                    reinterpret_cast<u64*>(A.suf_out)[o] = (u64)keys[q0 + i] & A.word_mask;
+                    reinterpret_cast<u64*>(A.suf_out)[o] = A.widx.decode((u64)keys[q0 + i]);
                 else
                     reinterpret_cast<PosT*>(A.suf_out)[o] = vals[q0 + i];
             }

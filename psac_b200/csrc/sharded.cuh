@@ -224,17 +224,12 @@ struct OwnerSrcT {
     // pre-biased so that the bin-relative index the kernel computes (global bin offset + slot) lands at the right place
     u64* kpeer[16];
     u64* vpeer[16];
-    u64 cut, base1, base;  // cut = rem * (base + 1)
-    u32 rem;
-    double inv_base1, inv_base;
-    __device__ __forceinline__ static u64 divide(u64 x, u64 d, double inv) {
-        u64 q = (u64)__double2ull_rz((double)x * inv);
-        if (q * d > x) --q;
-        if ((q + 1) * d <= x) ++q;
-        return q;
-    }
+    BlkDiv div;
     __device__ __forceinline__ Stage load_key(size_t g) const { return ld_stream(kin + g); }
-    __device__ __forceinline__ u32 digit(Stage k) const { return k < cut ? (u32)divide(k, base1, inv_base1) : rem + (u32)divide(k - cut, base, inv_base); }
+    __device__ __forceinline__ u32 digit(Stage k) const {
+        u64 local;
+        return div.owner(k, &local);
+    }
     __device__ __forceinline__ Out out_key(Stage k) const { return k; }
     __device__ __forceinline__ u64 load_val(size_t g) const { return ld_stream(vin + g); }
     __device__ __forceinline__ u8 load_aux(size_t, Stage) const { return 0; }
@@ -257,24 +252,15 @@ struct OwnerPackSrcT {
     const u64* __restrict__ vin;  // bucket id (global SA position)
     u64* kpeer[16];
     u64* vpeer[16];               // unused (keys only)
-    u64 cut, base1, base;         // block distribution: cut = rem * (base + 1)
-    u32 rem;
-    double inv_base1, inv_base;
+    BlkDiv div;                   // block distribution
     u64 pos_base;                 // first SA position of the sender
     int rank_shift, idx_shift;    // bit positions of the rank field and of the block-local index
     u32 rank_mask;
     u64 me;
     __device__ __forceinline__ Stage load_key(size_t g) const {
         const u64 s = ld_stream(kin + g), b = ld_stream(vin + g);
-        u64 owner, local;
-        if (s < cut) {
-            owner = OwnerSrcT<false>::divide(s, base1, inv_base1);
-            local = s - owner * base1;
-        } else {
-            const u64 q = OwnerSrcT<false>::divide(s - cut, base, inv_base);
-            owner = rem + q;
-            local = s - cut - q * base;
-        }
+        u64 local;
+        const u64 owner = div.owner(s, &local);
         return (local << idx_shift) | (owner << rank_shift) | (b - pos_base);
     }
     __device__ __forceinline__ u32 digit(Stage k) const { return (u32)(k >> rank_shift) & rank_mask; }
@@ -807,7 +793,6 @@ bool construct_sharded_core(psacb200_engine* e, const ShardComm& C, const u8* d_
             recv_bkt = e->rk[1].as<u64>();
         }
         S.reserved = fused ? 1u : 0u;  // reported as "exchange = peer stores" in the stats
-        const u64 cut = blk.rem * (blk.base + 1), base1 = blk.base + 1, base0 = blk.base ? blk.base : 1;
         // packed exchange: [local index | rank | relative bucket] in one word, when the three fields fit 64 bits
         u64 max_cnt = 0;
         for (int r = 0; r < p; ++r) max_cnt = std::max(max_cnt, cnt_key[r]);
@@ -818,7 +803,7 @@ bool construct_sharded_core(psacb200_engine* e, const ShardComm& C, const u8* d_
             const int rank_shift = rel_bits, idx_shift = rel_bits + rank_bits;
             u64* recv_words = recv_suf;
             if (fused) {
-                OwnerPackSrcT<true> src{SA, bucket, {}, {}, cut, base1, base0, (u32)blk.rem, 1.0 / (double)base1, 1.0 / (double)base0, off, rank_shift,
+                OwnerPackSrcT<true> src{SA, bucket, {}, {}, BlkDiv::make(n, p), off, rank_shift,
                                         idx_shift, (1u << rank_bits) - 1u, (u64)me};
                 for (int b = 0; b < p; ++b) {
                     u64 rd = 0;
@@ -833,7 +818,7 @@ bool construct_sharded_core(psacb200_engine* e, const ShardComm& C, const u8* d_
                 rank_barrier(e, C);
             } else {
                 u64* part_words = e->vals[y].as<u64>();
-                OwnerPackSrcT<false> src{SA, bucket, {}, {}, cut, base1, base0, (u32)blk.rem, 1.0 / (double)base1, 1.0 / (double)base0, off, rank_shift,
+                OwnerPackSrcT<false> src{SA, bucket, {}, {}, BlkDiv::make(n, p), off, rank_shift,
                                          idx_shift, (1u << rank_bits) - 1u, (u64)me};
                 launch_pass<OwnerPackSrcT<false>, NoVal, false>(ws, src, part_words, nullptr, nullptr, cnt, st);
                 e->launches += LAUNCHES_PER_PASS;
@@ -860,7 +845,7 @@ bool construct_sharded_core(psacb200_engine* e, const ShardComm& C, const u8* d_
             // ONE kernel partitions by owner and stores each bin into its owner's receive buffer over NVLink (peer
             // stores): the exchange overlaps the partition tile by tile.  Rank b receives my bin at its displacement
             // for source `me`; barriers keep the receive buffers of a previous call / the next step apart.
-            OwnerPeerSrc src{SA, bucket, {}, {}, cut, base1, base0, (u32)blk.rem, 1.0 / (double)base1, 1.0 / (double)base0};
+            OwnerPeerSrc src{SA, bucket, {}, {}, BlkDiv::make(n, p)};
             for (int b = 0; b < p; ++b) {
                 u64 rd = 0;  // displacement of source `me` in receiver b's buffer
                 for (int a = 0; a < me; ++a) rd += blk_in_range[(size_t)b * p + a];
@@ -875,7 +860,7 @@ bool construct_sharded_core(psacb200_engine* e, const ShardComm& C, const u8* d_
         } else {
             u64* part_suf = e->vals[y].as<u64>();
             u64* part_bkt = e->keys[x].as<u64>();  // the sorted keys are dead after resolve
-            OwnerSrc src{SA, bucket, {}, {}, cut, base1, base0, (u32)blk.rem, 1.0 / (double)base1, 1.0 / (double)base0};
+            OwnerSrc src{SA, bucket, {}, {}, BlkDiv::make(n, p)};
             launch_pass<OwnerSrc, u64, false>(ws, src, part_suf, part_bkt, nullptr, cnt, st);
             e->launches += LAUNCHES_PER_PASS;
             all_to_all_v(e, C, part_suf, scount, sdispl, recv_suf, rcount, rdispl, sizeof(u64));
@@ -1129,25 +1114,27 @@ static void plan_word_exchange(const u64* cnt, int p, int nb, u64 n, u64 pad_til
 // suffix; no NVLink traffic (measured alternative: the same pass with peer stores into the owners' HBM, 13.3 ms for
 // 2^30 suffixes on 2 GPUs against 716 GB/s of achievable NVLink store bandwidth, profiles/r2_peer_bw.txt).
 constexpr int SELW_THREADS = 512;
-constexpr int SELW_CPT = 64;      // characters per thread
+constexpr int SELW_CPT = 64;      // characters per thread (32 when few ranks share the text: a CTA's selection then fits one batch)
 constexpr int SELW_CAP = 8192;    // staged words per batch
+constexpr size_t SELW_SMEM = SELW_CAP * sizeof(u64) + (SELW_THREADS / 32) * RADIX * sizeof(u32);
 
 struct SelectWordsArgs {
     const u64* stream;
     u64 n_main;                   // suffixes 0 .. n_main-1 (the others run past the end: select_tail_words_kernel)
-    int K, tb, cb, ib;            // key bits, top digit bits, carried bits, index bits
+    int K, tb, cb, ib;            // key bits, top digit bits, carried bits, bits of the index field
+    WordIdx widx;                 // the index field: (owner, block-local index)
     u32 dlo, dhi;
     const u64* seg_pad;           // [257] padded segment starts of this rank
     unsigned long long* cursor;   // [256] elements placed so far in every segment
     u64* out;
 };
 
-template <int LBITS>
-__device__ __forceinline__ u64 selw_bits(const u64 (&wd)[LBITS + 1], int c) {
+template <int WPT, int LBITS>
+__device__ __forceinline__ u64 selw_bits(const u64 (&wd)[WPT + 1], int c) {
     const int o = c * LBITS, j = o >> 6, off = o & 63;
     u64 hi = wd[0], lo = wd[1];
 #pragma unroll
-    for (int q = 1; q < LBITS; ++q)
+    for (int q = 1; q < WPT; ++q)
         if (q == j) {
             hi = wd[q];
             lo = wd[q + 1];
@@ -1155,31 +1142,45 @@ __device__ __forceinline__ u64 selw_bits(const u64 (&wd)[LBITS + 1], int c) {
     return off ? ((hi << off) | (lo >> (64 - off))) : hi;
 }
 
-template <int LBITS>
+template <int LBITS, int CPT>
 __global__ void __launch_bounds__(SELW_THREADS, 2) select_words_kernel(SelectWordsArgs A) {
-    extern __shared__ __align__(16) u64 sw_stage[];  // SELW_CAP words
+    static_assert(CPT == 64 || (CPT == 32 && LBITS >= 2), "a thread takes whole stream words");
+    extern __shared__ __align__(16) u64 sw_stage[];  // SELW_CAP words, then the per-warp digit tables
+    constexpr int NW = SELW_THREADS / 32;
+    u32* tab = reinterpret_cast<u32*>(sw_stage + SELW_CAP);  // [NW][RADIX]: counts, then running positions
     __shared__ u8 s_dig[SELW_CAP];
-    __shared__ u32 s_hist[RADIX], s_pos[RADIX];
     __shared__ u64 s_goff[RADIX];
-    __shared__ u32 s_wsum[SELW_THREADS / 32];
-    constexpr int WPT = LBITS;  // 64 characters = LBITS words
+    __shared__ u32 s_wsum[NW];
+    constexpr int WPT = LBITS * CPT / 64;  // CPT characters = WPT words
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const u64 g0 = ((u64)blockIdx.x * SELW_THREADS + tid) * SELW_CPT;
+    u32* mytab = tab + warp * RADIX;
+    const u64 g0 = ((u64)blockIdx.x * SELW_THREADS + tid) * CPT;
     u64 wd[WPT + 1];
 #pragma unroll
     for (int j = 0; j <= WPT; ++j) wd[j] = 0;
+    for (int e = tid; e < NW * RADIX; e += SELW_THREADS) tab[e] = 0u;
+    __syncthreads();
     u64 mask = 0;
     if (g0 < A.n_main) {
         const u64 w0 = (g0 * LBITS) >> 6;
 #pragma unroll
         for (int j = 0; j <= WPT; ++j) wd[j] = __ldg(A.stream + w0 + j);  // (the stream carries two zero words of padding)
         const u32 span = A.dhi - A.dlo;
+        const u64 left = A.n_main - g0;
+        const u64 vmask = left >= CPT ? (CPT == 64 ? ~0ull : ((1ull << (CPT & 63)) - 1ull)) : ((1ull << left) - 1ull);  // characters of this thread that are suffixes < n_main
+        const int dsh = 32 - A.tb;
 #pragma unroll
-        for (int c = 0; c < SELW_CPT; ++c) {
+        for (int c = 0; c < CPT; ++c) {
             const int o = c * LBITS, j = o >> 6, off = o & 63;  // compile-time after unrolling
-            const u64 v = off ? ((wd[j] << off) | (wd[j + 1] >> (64 - off))) : wd[j];
-            const u32 d = (u32)(v >> (64 - A.tb));
-            if (d - A.dlo < span && g0 + c < A.n_main) mask |= 1ull << c;
+            // the top 32 bits of the window at this character are enough for the digit
+            const u32 a = off < 32 ? (u32)(wd[j] >> 32) : (u32)wd[j];
+            const u32 b = off < 32 ? (u32)wd[j] : (u32)(wd[j + 1] >> 32);
+            const u32 v32 = __funnelshift_l(b, a, off & 31);
+            const u32 d = v32 >> dsh;
+            if (d - A.dlo < span && ((vmask >> c) & 1ull)) {
+                mask |= 1ull << c;
+                atomicAdd(&mytab[d], 1u);  // digit counts of the whole CTA (valid when everything fits one batch)
+            }
         }
     }
     // sequence numbers of the selected characters in thread order
@@ -1189,30 +1190,46 @@ __global__ void __launch_bounds__(SELW_THREADS, 2) select_words_kernel(SelectWor
     __syncthreads();
     u32 tseq = incl - mine, total = 0;
 #pragma unroll
-    for (int w = 0; w < SELW_THREADS / 32; ++w) {
+    for (int w = 0; w < NW; ++w) {
         if (w < warp) tseq += s_wsum[w];
         total += s_wsum[w];
     }
+    const bool single = total <= SELW_CAP;
     const u64 keymask = A.cb >= 64 ? ~0ull : ((1ull << A.cb) - 1ull);
+    // index field of my first character; my characters span at most two text blocks (blocks hold >= 2^16 characters)
+    u64 loc0 = 0, bsize = ~0ull;
+    u32 own0 = 0;
+    if (mask) {
+        own0 = A.widx.div.owner(g0, &loc0);
+        bsize = A.widx.block_size(own0);
+    }
     for (u32 lo = 0; lo < total; lo += SELW_CAP) {
         const u32 hi = lo + SELW_CAP < total ? lo + SELW_CAP : total;
-        if (tid < RADIX) s_hist[tid] = 0;
-        __syncthreads();
-        {  // digit counts of this batch
+        if (!single) {
+            // more than one batch (few ranks: a large share of the characters is mine): recount per batch
+            __syncthreads();
+            for (int e = tid; e < NW * RADIX; e += SELW_THREADS) tab[e] = 0u;
+            __syncthreads();
             u64 mm = mask;
             u32 seq = tseq;
             while (mm) {
                 const int c = __ffsll((long long)mm) - 1;
                 mm &= mm - 1;
-                if (seq >= lo && seq < hi) atomicAdd(&s_hist[(u32)(selw_bits<LBITS>(wd, c) >> (64 - A.tb))], 1u);
+                if (seq >= lo && seq < hi) atomicAdd(&mytab[(u32)(selw_bits<WPT, LBITS>(wd, c) >> (64 - A.tb))], 1u);
                 ++seq;
             }
         }
         __syncthreads();
-        // exclusive scan over the digits; one global atomic per non-empty digit reserves its run
+        // per digit: exclusive offsets of the warps, exclusive scan over the digits; ONE global atomic per non-empty digit
+        // reserves its run in the segment
         u32 cnt = 0, inc = 0;
         if (tid < RADIX) {
-            cnt = s_hist[tid];
+#pragma unroll
+            for (int w = 0; w < NW; ++w) {
+                const u32 cw = tab[w * RADIX + tid];
+                tab[w * RADIX + tid] = cnt;
+                cnt += cw;
+            }
             inc = warp_inclusive_sum_u32(cnt);
             if (lane == 31) s_wsum[warp] = inc;
         }
@@ -1222,7 +1239,8 @@ __global__ void __launch_bounds__(SELW_THREADS, 2) select_words_kernel(SelectWor
 #pragma unroll
             for (int w = 0; w < RADIX / 32; ++w) pre += (w < warp) ? s_wsum[w] : 0u;
             const u32 bstart = pre + inc - cnt;
-            s_pos[tid] = bstart;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) tab[w * RADIX + tid] += bstart;
             if (cnt) s_goff[tid] = A.seg_pad[tid] + (u64)atomicAdd(&A.cursor[tid], (unsigned long long)cnt) - (u64)bstart;
         }
         __syncthreads();
@@ -1233,10 +1251,12 @@ __global__ void __launch_bounds__(SELW_THREADS, 2) select_words_kernel(SelectWor
                 const int c = __ffsll((long long)mm) - 1;
                 mm &= mm - 1;
                 if (seq >= lo && seq < hi) {
-                    const u64 v = selw_bits<LBITS>(wd, c);
+                    const u64 v = selw_bits<WPT, LBITS>(wd, c);
                     const u32 d = (u32)(v >> (64 - A.tb));
-                    const u32 p = atomicAdd(&s_pos[d], 1u);
-                    sw_stage[p] = (((v >> (64 - A.K)) & keymask) << A.ib) | (g0 + (u64)c);
+                    const u32 p = atomicAdd(&mytab[d], 1u);
+                    const u64 loc = loc0 + (u64)c;
+                    const u64 fld = loc < bsize ? (((u64)own0 << A.widx.lb) | loc) : (((u64)(own0 + 1) << A.widx.lb) | (loc - bsize));
+                    sw_stage[p] = (((v >> (64 - A.K)) & keymask) << A.ib) | fld;
                     s_dig[p] = (u8)d;
                 }
                 ++seq;
@@ -1271,7 +1291,7 @@ __global__ void __launch_bounds__(64) select_tail_words_kernel(SelectWordsArgs A
             }
         }
         const u64 keymask = A.cb >= 64 ? ~0ull : ((1ull << A.cb) - 1ull);
-        A.out[A.seg_pad[d] + before] = ((key & keymask) << A.ib) | g;
+        A.out[A.seg_pad[d] + before] = ((key & keymask) << A.ib) | A.widx.encode(g);
         if (before == 0) A.cursor[d] = all;  // (the cursors were zeroed before)
     }
 }
@@ -1330,20 +1350,23 @@ struct OwnerMidSrc {
     static constexpr bool FROM_TEXT = false;
     static constexpr bool PEER = false;
     const u64* __restrict__ win;
-    u64 word_mask;
-    BlkDiv div;
+    u64 fmask, lmask;    // masks of the index field of a sort word and of its block-local part
+    int lb;
     int rank_shift, idx_shift;
     u32 rank_mask;
     u64 me;
     int mshift, bshift;  // digit = owner << bshift | (local >> mshift) & ((1 << bshift) - 1)
     __device__ __forceinline__ Stage load_key(size_t g) const {
-        u64 local;
-        const u64 owner = div.owner(ld_stream(win + g) & word_mask, &local);
-        return (local << idx_shift) | (owner << rank_shift) | (u64)g;
+        const u64 f = ld_stream(win + g) & fmask;
+        return ((f & lmask) << idx_shift) | ((f >> lb) << rank_shift) | (u64)g;
     }
     __device__ __forceinline__ u32 digit(Stage k) const {
         const u32 owner = (u32)(k >> rank_shift) & rank_mask;
         return (owner << bshift) | ((u32)((k >> idx_shift) >> mshift) & ((1u << bshift) - 1u));
+    }
+    __device__ __forceinline__ u32 hist_digit(size_t g) const {
+        const u64 f = ld_stream(win + g) & fmask;
+        return ((u32)(f >> lb) << bshift) | ((u32)((f & lmask) >> mshift) & ((1u << bshift) - 1u));
     }
     __device__ __forceinline__ Out out_key(Stage k) const { return (k & ~((u64)rank_mask << rank_shift)) | (me << rank_shift); }
     __device__ __forceinline__ NoVal load_val(size_t) const { return NoVal(); }
@@ -1351,11 +1374,11 @@ struct OwnerMidSrc {
 };
 
 // complete key and suffix of the last sorted word of a rank (the halo of the next rank's first boundary)
-__global__ void __launch_bounds__(32) last_word_kernel(const u64* __restrict__ words, u64 cnt, u64 top_digit, int cb, int ib, u64* __restrict__ out) {
+__global__ void __launch_bounds__(32) last_word_kernel(const u64* __restrict__ words, u64 cnt, u64 top_digit, int cb, int ib, WordIdx widx, u64* __restrict__ out) {
     if (threadIdx.x == 0) {
         const u64 w = cnt ? words[cnt - 1] : 0;
         out[0] = (top_digit << cb) | (w >> ib);
-        out[1] = ib >= 64 ? w : (w & ((1ull << ib) - 1ull));
+        out[1] = widx.decode(w);
     }
 }
 
@@ -1365,7 +1388,8 @@ struct PullArgs {
     const u64* src[16];
     u64 off_key[17];
     int p;
-    u64 dst_lo, m, mask;
+    u64 dst_lo, m;
+    WordIdx widx;
     void* dst;
 };
 template <typename OutT>
@@ -1375,7 +1399,7 @@ __global__ void __launch_bounds__(256) pull_sa_kernel(PullArgs A) {
         const u64 g = A.dst_lo + i;
         int a = 0;
         while (a + 1 < A.p && A.off_key[a + 1] <= g) ++a;
-        st_stream(dst + i, (OutT)(A.src[a][g - A.off_key[a]] & A.mask));
+        st_stream(dst + i, (OutT)A.widx.decode(A.src[a][g - A.off_key[a]]));
     }
 }
 
@@ -1402,8 +1426,13 @@ bool construct_sharded_v2(psacb200_engine* e, const ShardComm& C, const u8* d_te
 
     e->mark("text");
     // ---- key shape: K = tb (top digit) + cb (carried) bits, cb + ib <= 64
-    const int ib = std::max(1, (int)bits_for(n - 1));
-    const u64 word_mask = (1ull << ib) - 1ull;
+    // index field of a sort word: (owner of the suffix's ISA entry, index inside that rank's block)
+    const int idx_bits = std::max(1, (int)bits_for(blk.size(0) ? blk.size(0) - 1 : 0)), rank_bits = std::max(1, (int)bits_for((u64)p - 1));
+    const int ib = idx_bits + rank_bits;
+    WordIdx widx;
+    widx.div = BlkDiv::make(n, p);
+    widx.lb = idx_bits;
+    widx.mask = (1ull << ib) - 1ull;
     unsigned Cc = choose_key_chars(n, lbits, k);
     auto top_bits = [&](unsigned c) { return std::min(RADIX_BITS, (int)c * lbits); };
     while (Cc > 1 && (int)Cc * lbits - top_bits(Cc) > 64 - ib) --Cc;
@@ -1441,8 +1470,7 @@ bool construct_sharded_v2(psacb200_engine* e, const ShardComm& C, const u8* d_te
     if (!P.balanced) return false;  // top key digits too skewed for digit-boundary splitters
     const u64 cnt = P.cnt_key[me], off = P.off_key[me];
     // exchange word of the SA -> ISA step: [local index | rank | position relative to the sender]
-    const int rel_bits = std::max(1, (int)bits_for(P.max_cnt - 1)), rank_bits = std::max(1, (int)bits_for((u64)p - 1));
-    const int idx_bits = std::max(1, (int)bits_for(blk.size(0) ? blk.size(0) - 1 : 0));
+    const int rel_bits = std::max(1, (int)bits_for(P.max_cnt - 1));
     if (rel_bits + rank_bits + idx_bits > 64) return false;
 
     // ---- peer-visible buffers (identical offsets on all ranks)
@@ -1475,6 +1503,7 @@ bool construct_sharded_v2(psacb200_engine* e, const ShardComm& C, const u8* d_te
 
     // ---- pass 1: select my digit range out of the whole (replicated) text, straight into the padded segment layout
     rank_barrier(e, C);  // the peers have pulled their SA blocks out of my word buffers (previous call)
+    e->mark("p1_barrier");
     {
         SelectWordsArgs SA_{};
         SA_.stream = stream;
@@ -1483,18 +1512,33 @@ bool construct_sharded_v2(psacb200_engine* e, const ShardComm& C, const u8* d_te
         SA_.tb = tb;
         SA_.cb = cb;
         SA_.ib = ib;
+        SA_.widx = widx;
         SA_.dlo = (u32)P.first[me];
         SA_.dhi = (u32)P.first[me + 1];
         SA_.seg_pad = sw.seg_pad;
         SA_.cursor = d_cursor;
         SA_.out = W[0];
         select_tail_words_kernel<<<1, 64, 0, st>>>(SA_, n, T, lbits);
-        const u64 ctas = div_up(SA_.n_main ? SA_.n_main : 1, (size_t)SELW_THREADS * SELW_CPT);
+        // 64 characters per thread; 32 where a rank keeps a large share of the text (fewer than 4 ranks), so that the
+        // selection of a CTA still fits one batch of the staging buffer
+        const bool half = p < 4 && lbits >= 2;
+        const u64 ctas = div_up(SA_.n_main ? SA_.n_main : 1, (size_t)SELW_THREADS * (half ? 32 : 64));
         dispatch_lbits(lbits, [&](auto LB) {
-            auto kern = select_words_kernel<decltype(LB)::value>;
+            constexpr int L = decltype(LB)::value;
             static bool seen[64] = {};
-            if (first_use_on_device(seen)) PSAC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SELW_CAP * sizeof(u64))));
-            kern<<<(unsigned)ctas, SELW_THREADS, SELW_CAP * sizeof(u64), st>>>(SA_);
+            const bool first = first_use_on_device(seen);
+            auto launch = [&](auto kern) {
+                if (first) PSAC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SELW_SMEM));
+                kern<<<(unsigned)ctas, SELW_THREADS, SELW_SMEM, st>>>(SA_);
+            };
+            if constexpr (L >= 2) {
+                if (first) PSAC_CUDA(cudaFuncSetAttribute(select_words_kernel<L, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SELW_SMEM));
+                if (half) {
+                    select_words_kernel<L, 32><<<(unsigned)ctas, SELW_THREADS, SELW_SMEM, st>>>(SA_);
+                    return;
+                }
+            }
+            launch(select_words_kernel<L, 64>);
         });
         e->launches += 2;
         PSAC_CUDA(cudaGetLastError());
@@ -1527,10 +1571,11 @@ bool construct_sharded_v2(psacb200_engine* e, const ShardComm& C, const u8* d_te
     u64* Sbuf = W[1 - x];
     u64* h_bstart = e->h_pinned + 1024;  // [p][256] bin starts of every rank's partition (pinned)
     {
-        OwnerMidSrc src{Wx, word_mask, BlkDiv::make(n, p), rank_shift, idx_shift, (1u << rank_bits) - 1u, (u64)me, mshift, bshift};
+        OwnerMidSrc src{Wx, widx.mask, (1ull << idx_bits) - 1ull, idx_bits, rank_shift, idx_shift, (1u << rank_bits) - 1u, (u64)me, mshift, bshift};
         launch_pass<OwnerMidSrc, NoVal, false>(ws, src, Sbuf, nullptr, nullptr, cnt, st);
         e->launches += LAUNCHES_PER_PASS;
         PSAC_CUDA(cudaGetLastError());
+        e->mark("isa_partA");
         PSAC_CUDA(cudaMemcpyAsync(d_cnt + (size_t)me * RADIX, ws.gbase, RADIX * sizeof(u64), cudaMemcpyDeviceToDevice, st));
         PSAC_NCCL(g_nccl.AllGather(d_cnt + (size_t)me * RADIX, d_cnt, RADIX, ncclUint64, C.comm, st));
         PSAC_CUDA(cudaMemcpyAsync(h_bstart, d_cnt, (size_t)p * RADIX * sizeof(u64), cudaMemcpyDeviceToHost, st));
@@ -1544,7 +1589,7 @@ bool construct_sharded_v2(psacb200_engine* e, const ShardComm& C, const u8* d_te
     int last_digit = 0;
     for (int d = 0; d < nb; ++d)
         if (P.owner[d] == me && P.seg_dense[(size_t)me * 257 + d + 1] > P.seg_dense[(size_t)me * 257 + d]) last_digit = d;
-    last_word_kernel<<<1, 32, 0, st>>>(Wx, cnt, (u64)last_digit, cb, ib, d_last + 2 * me);
+    last_word_kernel<<<1, 32, 0, st>>>(Wx, cnt, (u64)last_digit, cb, ib, widx, d_last + 2 * me);
     PSAC_NCCL(g_nccl.AllGather(d_last + 2 * me, d_last, 2, ncclUint64, C.comm, st));
     if (want_lcp) e->lcp.reserve((cnt + 16) * sizeof(u64), tot);
     u64* LCP = want_lcp ? e->lcp.as<u64>() : nullptr;
@@ -1588,7 +1633,7 @@ bool construct_sharded_v2(psacb200_engine* e, const ShardComm& C, const u8* d_te
     H.agg_max = e->lookback.as<u64>();
     H.agg_sum = H.agg_max + htiles;
     H.word_shift = ib;
-    H.word_mask = word_mask;
+    H.widx = widx;
     PSAC_CUDA(cudaMemsetAsync(H.counts, 0, 2 * sizeof(u64), st));
     heads_kernel<u64, u64, 0, true><<<(unsigned)htiles, HD_THREADS, 0, st>>>(H);
     tile_scan_kernel<<<1, 1024, 0, st>>>(H.agg_max, H.agg_sum, htiles, H.counts);
@@ -1600,7 +1645,7 @@ bool construct_sharded_v2(psacb200_engine* e, const ShardComm& C, const u8* d_te
     // ---- SA -> ISA, part X (queued now, while the heads kernels run): every (destination, window group) run goes to the
     //      destination's receive buffer with the copy engines (peer-mapped memory), group-major / source-minor
     {
-        cudaStream_t cs = e->copy_stream;
+        cudaStream_t cs = e->copy_streams[0];
         PSAC_CUDA(cudaEventSynchronize(e->ev_x[0]));  // (the heads kernels are queued behind it and keep the GPU busy)
         const int B = 1 << bshift;
         auto count_of = [&](int s_, int bin) {
@@ -1608,24 +1653,44 @@ bool construct_sharded_v2(psacb200_engine* e, const ShardComm& C, const u8* d_te
             const u64 a1 = bin + 1 < RADIX ? h_bstart[(size_t)s_ * RADIX + bin + 1] : P.cnt_key[s_];
             return a1 - a0;
         };
-        PSAC_CUDA(cudaStreamWaitEvent(cs, e->ev_x[0], 0));
+        // several copy streams (= copy engines) side by side: the local share on one, the peers spread over the others,
+        // every rank starting with its right neighbour so that no destination is hit by all senders at once
+        constexpr int NCS = psacb200_engine::COPY_STREAMS;
+        for (int i = 0; i < NCS; ++i) PSAC_CUDA(cudaStreamWaitEvent(e->copy_streams[i], e->ev_x[0], 0));
+        PSAC_CUDA(cudaEventRecord(e->ev_xt[0], cs));
+        std::vector<u64> dst_off((size_t)p * B, 0);  // where my run of (destination b, group) starts in b's receive buffer
         for (int b = 0; b < p; ++b) {
             u64 run = 0;
             for (int mgrp = 0; mgrp < B; ++mgrp)
                 for (int s_ = 0; s_ < p; ++s_) {
-                    const int bin = b * B + mgrp;
-                    const u64 len = count_of(s_, bin);
-                    if (s_ == me && len)
-                        PSAC_CUDA(cudaMemcpyAsync(at(b, oR0) + run, Sbuf + h_bstart[(size_t)me * RADIX + bin], len * sizeof(u64), cudaMemcpyDeviceToDevice, cs));
-                    run += len;
+                    if (s_ == me) dst_off[(size_t)b * B + mgrp] = run;
+                    run += count_of(s_, b * B + mgrp);
                 }
             if (run != blk.size(b)) throw std::string("sharded construction: exchange plan does not cover the block");
         }
+        for (int kk = 0; kk < p; ++kk) {
+            const int b = (me + kk) % p;
+            cudaStream_t s2 = kk == 0 ? e->copy_streams[0] : e->copy_streams[NCS > 1 ? 1 + (kk - 1) % (NCS - 1) : 0];
+            for (int mgrp = 0; mgrp < B; ++mgrp) {
+                const int bin = b * B + mgrp;
+                const u64 len = count_of(me, bin);
+                if (len)
+                    PSAC_CUDA(cudaMemcpyAsync(at(b, oR0) + dst_off[(size_t)b * B + mgrp], Sbuf + h_bstart[(size_t)me * RADIX + bin], len * sizeof(u64),
+                                              cudaMemcpyDeviceToDevice, s2));
+            }
+        }
+        for (int i = 1; i < NCS; ++i) {
+            PSAC_CUDA(cudaEventRecord(e->ev_cs[i], e->copy_streams[i]));
+            PSAC_CUDA(cudaStreamWaitEvent(cs, e->ev_cs[i], 0));
+        }
+        PSAC_CUDA(cudaEventRecord(e->ev_xt[1], cs));
         // all pushes have landed everywhere: barrier on the copy stream, then the main stream may read the receive buffer
         ShardComm C2{reinterpret_cast<ncclComm_t>(e->nccl_comm2 ? e->nccl_comm2 : e->nccl_comm), C.rank, C.world};
         u64* d_b = e->shard_meta() + 60;
         PSAC_NCCL(g_nccl.AllReduce(d_b, d_b, 1, ncclUint64, ncclSum, C2.comm, cs));
         PSAC_CUDA(cudaEventRecord(e->ev_x[1], cs));
+        PSAC_CUDA(cudaEventRecord(e->ev_xt[2], cs));
+        e->xt_used = true;
     }
     // unresolved: mine and the total over the ranks
     u64* d_m = e->shard_meta() + 32;  // [0] mine, [1] sum
@@ -1790,6 +1855,7 @@ bool construct_sharded_v2(psacb200_engine* e, const ShardComm& C, const u8* d_te
                 Q.isa_hi = 0;
                 Q.pisa = pisa;
                 Q.isa_add = off;
+                Q.widx = widx;
                 launch_resolve<u64, u64>(e, false, Q);  // new bucket ids go to the owners' ISA blocks over peer memory
             } else {
                 PSAC_CUDA(cudaMemsetAsync(e->counts(), 0, 2 * sizeof(u64), st));
@@ -1818,7 +1884,7 @@ bool construct_sharded_v2(psacb200_engine* e, const ShardComm& C, const u8* d_te
             PL.p = p;
             PL.dst_lo = blk.start(me);
             PL.m = n_local;
-            PL.mask = word_mask;
+            PL.widx = widx;
             PL.dst = sa_out;
             if (index_bytes == 8)
                 pull_sa_kernel<u64><<<grid_for(e, n_local, 256, 16), 256, 0, st>>>(PL);
