@@ -173,6 +173,26 @@ int psacb200_ansv(psacb200_engine* e, const void* vals, size_t n, int val_bytes,
 int psacb200_suffix_tree(psacb200_engine* e, const uint8_t* text, size_t n, int index_bytes, const void* sa, const void* lcp, uint64_t* nodes,
                          size_t nodes_len);
 
+/* ---- the same on DEVICE arrays, on one GPU or block-sharded over the ranks of psacb200_comm_init (BASELINE configs[4]) ------- */
+/* ANSV of n DEVICE values; left / right: DEVICE arrays of n u64. */
+int psacb200_ansv_device(psacb200_engine* e, const void* d_vals, size_t n, int val_bytes, int left_type, int right_type, uint64_t nonsv, uint64_t* d_left,
+                         uint64_t* d_right);
+/* Collective: the values are block-distributed like mxx::blk_dist; every rank gets the matches of ITS block as GLOBAL indices
+ * (reference ansv<T, left, right, global_indexing>, include/ansv.hpp:2042-2051).  Elements whose match lies in another rank's block
+ * (the reference's unmatched prefix / suffix minima, ansv.hpp:1362-1442) are resolved through peer memory. */
+int psacb200_ansv_sharded(psacb200_engine* e, const void* d_vals_local, size_t n_local, size_t n_global, int val_bytes, int left_type, int right_type,
+                          uint64_t nonsv, uint64_t* d_left_local, uint64_t* d_right_local);
+/* Child table of the suffix tree from DEVICE SA + LCP (index_bytes each) and the text; the ANSV (furthest_eq left, nearest_sm
+ * right, reference suffix_tree.hpp:62) is searched on the fly, not materialised.  d_nodes: DEVICE, (sigma + 1) * n u64 (the rows of
+ * all LCP indices); *sigma_out receives sigma. */
+int psacb200_suffix_tree_device(psacb200_engine* e, const uint8_t* d_text, size_t n, int index_bytes, const void* d_sa, const void* d_lcp, uint64_t* d_nodes,
+                                size_t nodes_len, uint32_t* sigma_out);
+/* Collective: every rank passes its blocks of text / SA / LCP and receives the rows of the LCP indices of ITS block,
+ * (sigma + 1) * n_local u64 (reference construct_suffix_tree over a communicator, suffix_tree.hpp:440-499; edges whose parent row
+ * lives on another rank travel through peer memory instead of the reference's all-to-all). */
+int psacb200_suffix_tree_sharded(psacb200_engine* e, const uint8_t* d_text_local, size_t n_local, size_t n_global, int index_bytes, const void* d_sa_local,
+                                 const void* d_lcp_local, uint64_t* d_nodes_local, size_t nodes_len, uint32_t* sigma_out);
+
 #ifdef __cplusplus
 }
 #endif

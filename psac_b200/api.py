@@ -114,6 +114,11 @@ def lib():
         L.psacb200_blk_dist.argtypes = [C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.psacb200_blk_dist.restype = None
         L.psacb200_choose_splitters.argtypes = [C.c_void_p, C.c_size_t, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]
+        L.psacb200_ansv_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p]
+        L.psacb200_ansv_sharded.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p]
+        L.psacb200_suffix_tree_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_uint32)]
+        L.psacb200_suffix_tree_sharded.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                                   C.POINTER(C.c_uint32)]
         L.psacb200_plan_word_exchange.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_uint64] + [C.c_void_p] * 6 + [C.POINTER(C.c_int)]
         _lib = L
     return _lib
@@ -278,6 +283,24 @@ class Engine:
         nodes = np.zeros((t.size, sigma + 1), np.uint64)
         _check(lib().psacb200_suffix_tree(self._h, _ptr(t), t.size, sa.dtype.itemsize, _ptr(sa), _ptr(lcp), _ptr(nodes), nodes.size))
         return nodes
+
+    # ---- the same on device pointers (one GPU, or collective over the ranks of comm_init)
+    def ansv_device_ptr(self, vals_ptr, n, val_bytes, left_type, right_type, nonsv, left_ptr, right_ptr):
+        _check(lib().psacb200_ansv_device(self._h, _ptr(vals_ptr), n, val_bytes, left_type, right_type, nonsv, _ptr(left_ptr), _ptr(right_ptr)))
+
+    def ansv_sharded_ptr(self, vals_ptr, n_local, n_global, val_bytes, left_type, right_type, nonsv, left_ptr, right_ptr):
+        _check(lib().psacb200_ansv_sharded(self._h, _ptr(vals_ptr), n_local, n_global, val_bytes, left_type, right_type, nonsv, _ptr(left_ptr), _ptr(right_ptr)))
+
+    def suffix_tree_device_ptr(self, text_ptr, n, index_bytes, sa_ptr, lcp_ptr, nodes_ptr, nodes_len):
+        sigma = C.c_uint32()
+        _check(lib().psacb200_suffix_tree_device(self._h, _ptr(text_ptr), n, index_bytes, _ptr(sa_ptr), _ptr(lcp_ptr), _ptr(nodes_ptr), nodes_len, C.byref(sigma)))
+        return sigma.value
+
+    def suffix_tree_sharded_ptr(self, text_ptr, n_local, n_global, index_bytes, sa_ptr, lcp_ptr, nodes_ptr, nodes_len):
+        sigma = C.c_uint32()
+        _check(lib().psacb200_suffix_tree_sharded(self._h, _ptr(text_ptr), n_local, n_global, index_bytes, _ptr(sa_ptr), _ptr(lcp_ptr), _ptr(nodes_ptr), nodes_len,
+                                                  C.byref(sigma)))
+        return sigma.value
 
     def sort_pairs_host(self, keys, vals, begin_bit, end_bit):
         """In-place stable radix sort of numpy keys (uint32/uint64) and optional values by key bits [begin_bit, end_bit)."""

@@ -116,9 +116,9 @@ struct psacb200_engine {
     u64* byte_hist() const { return small.as<u64>() + 2 * MAX_PASSES * RADIX; }
     u64* counts() const { return byte_hist() + 256; }
     u32* counters() const { return reinterpret_cast<u32*>(counts() + 8); }
-    u64* shard_meta() const { return reinterpret_cast<u64*>(counters() + 64); }  // 256 u64 of small per-rank exchange data
-    void* tail_list() const { return shard_meta() + 256; }                        // TailList (sa_kernels.cuh)
-    static size_t small_bytes() { return (2 * MAX_PASSES * RADIX + 256 + 8) * sizeof(u64) + 64 * sizeof(u32) + 256 * sizeof(u64) + 1024; }
+    u64* shard_meta() const { return reinterpret_cast<u64*>(counters() + 64); }  // 512 u64 of small per-rank exchange data
+    void* tail_list() const { return shard_meta() + 512; }                        // TailList (sa_kernels.cuh)
+    static size_t small_bytes() { return (2 * MAX_PASSES * RADIX + 256 + 8) * sizeof(u64) + 64 * sizeof(u32) + 512 * sizeof(u64) + 1024; }
 
     RadixWorkspace radix_ws() const {
         RadixWorkspace ws;
@@ -797,7 +797,8 @@ void ansv_device(psacb200_engine* e, const T* d_vals, u64 n, int left_type, int 
         base += m;
         t.levels += 1;
     }
-    ansv_kernel<T><<<grid_for(e, n, 256, 8), 256, 0, e->stream>>>(t, left_type, right_type, nonsv, d_left, d_right);
+    LocalSearch<T> sr{t};
+    ansv_kernel<T, LocalSearch<T>><<<grid_for(e, n, 256, 8), 256, 0, e->stream>>>(sr, 0, n, left_type, right_type, nonsv, d_left, d_right);
     e->launches += 1;
     PSAC_CUDA(cudaGetLastError());
 }
@@ -1364,6 +1365,96 @@ int psacb200_suffix_tree(psacb200_engine* e, const uint8_t* text, size_t n, int 
         PSAC_CUDA(cudaGetLastError());
         PSAC_CUDA(cudaMemcpyAsync(nodes, e->tb[5].p, width * n * sizeof(u64), cudaMemcpyDeviceToHost, st));
         PSAC_CUDA(cudaStreamSynchronize(st));
+        return PSACB200_OK;
+    });
+}
+
+int psacb200_ansv_device(psacb200_engine* e, const void* d_vals, size_t n, int val_bytes, int left_type, int right_type, uint64_t nonsv, uint64_t* d_left,
+                         uint64_t* d_right) {
+    if (!e) {
+        set_last_error("null engine");
+        return PSACB200_ERR_ARG;
+    }
+    if (n == 0) return PSACB200_OK;
+    return guarded([&]() -> int {
+        if (!d_vals || !d_left || !d_right) throw arg_failure{"null argument"};
+        if (val_bytes != 4 && val_bytes != 8) throw arg_failure{"val_bytes must be 4 or 8"};
+        if (left_type < 0 || left_type > 2 || right_type < 0 || right_type > 2) throw arg_failure{"match mode must be 0 (nearest_sm), 1 (nearest_eq) or 2 (furthest_eq)"};
+        PSAC_CUDA(cudaSetDevice(e->device));
+        e->tr_n = 0;
+        e->mark("begin");
+        if (val_bytes == 4)
+            ansv_device<u32>(e, reinterpret_cast<const u32*>(d_vals), n, left_type, right_type, nonsv, d_left, d_right);
+        else
+            ansv_device<u64>(e, reinterpret_cast<const u64*>(d_vals), n, left_type, right_type, nonsv, d_left, d_right);
+        e->mark("ansv");
+        PSAC_CUDA(cudaStreamSynchronize(e->stream));
+        return PSACB200_OK;
+    });
+}
+
+int psacb200_ansv_sharded(psacb200_engine* e, const void* d_vals_local, size_t n_local, size_t n_global, int val_bytes, int left_type, int right_type,
+                          uint64_t nonsv, uint64_t* d_left_local, uint64_t* d_right_local) {
+    if (!e) {
+        set_last_error("null engine");
+        return PSACB200_ERR_ARG;
+    }
+    return guarded([&]() -> int {
+        if (!e->nccl_comm) throw arg_failure{"psacb200_comm_init has not been called on this engine"};
+        if (n_local && (!d_vals_local || !d_left_local || !d_right_local)) throw arg_failure{"null argument"};
+        if (val_bytes != 4 && val_bytes != 8) throw arg_failure{"val_bytes must be 4 or 8"};
+        if (left_type < 0 || left_type > 2 || right_type < 0 || right_type > 2) throw arg_failure{"match mode must be 0 (nearest_sm), 1 (nearest_eq) or 2 (furthest_eq)"};
+        PSAC_CUDA(cudaSetDevice(e->device));
+        if (n_global == 0) return PSACB200_OK;
+        ShardComm C{reinterpret_cast<ncclComm_t>(e->nccl_comm), e->shard_rank, e->shard_world};
+        e->tr_n = 0;
+        e->mark("begin");
+        if (val_bytes == 4)
+            ansv_sharded_core<u32>(e, C, reinterpret_cast<const u32*>(d_vals_local), n_local, n_global, left_type, right_type, nonsv, d_left_local, d_right_local);
+        else
+            ansv_sharded_core<u64>(e, C, reinterpret_cast<const u64*>(d_vals_local), n_local, n_global, left_type, right_type, nonsv, d_left_local, d_right_local);
+        return PSACB200_OK;
+    });
+}
+
+int psacb200_suffix_tree_device(psacb200_engine* e, const uint8_t* d_text, size_t n, int index_bytes, const void* d_sa, const void* d_lcp, uint64_t* d_nodes,
+                                size_t nodes_len, uint32_t* sigma_out) {
+    if (!e) {
+        set_last_error("null engine");
+        return PSACB200_ERR_ARG;
+    }
+    if (n == 0) return PSACB200_OK;
+    return guarded([&]() -> int {
+        if (!d_text || !d_sa || !d_lcp || !d_nodes) throw arg_failure{"null argument"};
+        if (index_bytes != 4 && index_bytes != 8) throw arg_failure{"index_bytes must be 4 or 8"};
+        PSAC_CUDA(cudaSetDevice(e->device));
+        if (index_bytes == 4)
+            suffix_tree_core<u32>(e, nullptr, d_text, n, n, reinterpret_cast<const u32*>(d_sa), reinterpret_cast<const u32*>(d_lcp), d_nodes, nodes_len, sigma_out);
+        else
+            suffix_tree_core<u64>(e, nullptr, d_text, n, n, reinterpret_cast<const u64*>(d_sa), reinterpret_cast<const u64*>(d_lcp), d_nodes, nodes_len, sigma_out);
+        return PSACB200_OK;
+    });
+}
+
+int psacb200_suffix_tree_sharded(psacb200_engine* e, const uint8_t* d_text_local, size_t n_local, size_t n_global, int index_bytes, const void* d_sa_local,
+                                 const void* d_lcp_local, uint64_t* d_nodes_local, size_t nodes_len, uint32_t* sigma_out) {
+    if (!e) {
+        set_last_error("null engine");
+        return PSACB200_ERR_ARG;
+    }
+    return guarded([&]() -> int {
+        if (!e->nccl_comm) throw arg_failure{"psacb200_comm_init has not been called on this engine"};
+        if (n_local && (!d_text_local || !d_sa_local || !d_lcp_local || !d_nodes_local)) throw arg_failure{"null argument"};
+        if (index_bytes != 4 && index_bytes != 8) throw arg_failure{"index_bytes must be 4 or 8"};
+        PSAC_CUDA(cudaSetDevice(e->device));
+        if (n_global == 0) return PSACB200_OK;
+        ShardComm C{reinterpret_cast<ncclComm_t>(e->nccl_comm), e->shard_rank, e->shard_world};
+        if (index_bytes == 4)
+            suffix_tree_core<u32>(e, &C, d_text_local, n_local, n_global, reinterpret_cast<const u32*>(d_sa_local), reinterpret_cast<const u32*>(d_lcp_local),
+                                  d_nodes_local, nodes_len, sigma_out);
+        else
+            suffix_tree_core<u64>(e, &C, d_text_local, n_local, n_global, reinterpret_cast<const u64*>(d_sa_local), reinterpret_cast<const u64*>(d_lcp_local),
+                                  d_nodes_local, nodes_len, sigma_out);
         return PSACB200_OK;
     });
 }

@@ -1569,7 +1569,7 @@ bool construct_sharded_v2(psacb200_engine* e, const ShardComm& C, const u8* d_te
     const int hshift = idx_bits > RADIX_BITS ? idx_bits - RADIX_BITS : 0;  // receiver's pass: top 8 bits of the local index
     const int mshift = hshift > bshift ? hshift - bshift : 0;
     u64* Sbuf = W[1 - x];
-    u64* h_bstart = e->h_pinned + 1024;  // [p][256] bin starts of every rank's partition (pinned)
+    u64* h_bstart = e->h_pinned + 2048;  // [p][256] bin starts of every rank's partition (pinned)
     {
         OwnerMidSrc src{Wx, widx.mask, (1ull << idx_bits) - 1ull, idx_bits, rank_shift, idx_shift, (1u << rank_bits) - 1u, (u64)me, mshift, bshift};
         launch_pass<OwnerMidSrc, NoVal, false>(ws, src, Sbuf, nullptr, nullptr, cnt, st);
@@ -2011,6 +2011,203 @@ void check_sharded_core(psacb200_engine* e, const ShardComm& C, const u8* d_text
     rep->bad_lcp = e->h_pinned[51];
     rep->first_bad = e->h_pinned[52];
     cudaEventElapsedTime(&rep->ms, e0, e1);
+}
+
+// ================================================================================================ ANSV / suffix tree, device resident
+// psacb200_ansv_device / _ansv_sharded and psacb200_suffix_tree_device / _suffix_tree_sharded (tree_kernels.cuh).  `C` may be
+// null (one GPU, no communicator): then the values are searched with LocalSearch and nothing leaves the GPU.
+struct TreeLayout {
+    size_t o_lvl0, o_upper, o_queue, total;
+    u64 qcap;
+};
+template <typename T>
+TreeLayout tree_layout(u64 n_loc_max, int p) {
+    TreeLayout L;
+    L.o_lvl0 = 0;
+    L.o_upper = align_up((n_loc_max + 64) * sizeof(T), 256);
+    const size_t upper = align_up((n_loc_max / (ANSV_FAN - 1) + 64 * ANSV_MAX_LEVELS) * sizeof(T), 256);
+    L.o_queue = L.o_upper + upper;
+    L.qcap = 1ull << 20;
+    L.total = L.o_queue + (size_t)p * L.qcap * 3 * sizeof(u64);
+    return L;
+}
+
+// levels of the min-tree over `m` values at `base + o_lvl0` (level 0 must be in place); returns the tree with pointers
+// relative to `base` (which may be a peer's mapping of the same layout)
+template <typename T>
+MinTree<T> mintree_describe(u8* base, const TreeLayout& L, u64 m) {
+    MinTree<T> t{};
+    t.level[0] = reinterpret_cast<const T*>(base + L.o_lvl0);
+    t.size[0] = m;
+    t.levels = 1;
+    T* up = reinterpret_cast<T*>(base + L.o_upper);
+    while (t.size[t.levels - 1] > (u64)ANSV_FAN) {
+        if (t.levels >= ANSV_MAX_LEVELS) throw arg_failure{"ANSV input too large"};
+        const u64 mm = div_up(t.size[t.levels - 1], (size_t)ANSV_FAN);
+        t.level[t.levels] = up;
+        t.size[t.levels] = mm;
+        up += mm;
+        t.levels += 1;
+    }
+    return t;
+}
+template <typename T>
+void mintree_build(psacb200_engine* e, const MinTree<T>& t) {
+    for (int lv = 1; lv < t.levels; ++lv) {
+        mintree_level_kernel<T><<<grid_for(e, t.size[lv], 256, 8), 256, 0, e->stream>>>(t.level[lv - 1], t.size[lv - 1], const_cast<T*>(t.level[lv]), t.size[lv]);
+        e->launches += 1;
+    }
+    PSAC_CUDA(cudaGetLastError());
+}
+
+// Distributed search structure over the values `d_vals_local` (this rank's block of a block-distributed array of n values):
+// copies the block into the peer arena, builds the min-tree, all-gathers the block minima, uploads the table of all
+// ranks' trees.  Returns the searcher.
+template <typename T>
+DistSearch<T> dist_search_setup(psacb200_engine* e, const ShardComm& C, const T* d_vals_local, u64 n_local, u64 n, TreeLayout& L) {
+    const int p = C.world, me = C.rank;
+    cudaStream_t st = e->stream;
+    const BlkDist blk(n, p);
+    L = tree_layout<T>(blk.size(0), p);
+    if (!arena_ensure(e, C, L.total)) throw std::string("sharded ANSV / suffix tree needs peer access between the GPUs (CUDA IPC / P2P unavailable)");
+    PeerArena& A = *reinterpret_cast<PeerArena*>(e->peer_map);
+    rank_barrier(e, C);  // nobody reads my arena any more (previous call)
+    if (n_local) PSAC_CUDA(cudaMemcpyAsync(A.base + L.o_lvl0, d_vals_local, n_local * sizeof(T), cudaMemcpyDeviceToDevice, st));
+    const MinTree<T> mine = mintree_describe<T>(A.base, L, n_local);
+    u64* d_min = e->shard_meta() + 96;  // [p] block minima (as u64)
+    PSAC_CUDA(cudaMemsetAsync(d_min + me, 0, sizeof(u64), st));
+    if (n_local) {
+        mintree_build<T>(e, mine);
+        array_min_kernel<T><<<1, 32, 0, st>>>(mine.level[mine.levels - 1], mine.size[mine.levels - 1], reinterpret_cast<T*>(d_min + me));
+        e->launches += 1;
+    }
+    PSAC_NCCL(g_nccl.AllGather(d_min + me, d_min, 1, ncclUint64, C.comm, st));  // (also: every rank's tree is complete before anybody searches it)
+    PSAC_CUDA(cudaMemcpyAsync(e->h_pinned + 64, d_min, (size_t)p * sizeof(u64), cudaMemcpyDeviceToHost, st));
+    PSAC_CUDA(cudaStreamSynchronize(st));
+    static_assert(sizeof(DistTreeTable<T>) <= 4096, "table size");
+    DistTreeTable<T> tab{};
+    tab.p = p;
+    for (int r = 0; r < p; ++r) {
+        tab.t[r] = mintree_describe<T>(A.peer[r], L, blk.size(r));
+        T v;
+        memcpy(&v, e->h_pinned + 64 + r, sizeof(T));
+        tab.blockmin[r] = v;
+        tab.start[r] = blk.start(r);
+    }
+    tab.start[p] = n;
+    e->tb[1].reserve(4096, &e->device_bytes);
+    memcpy(e->h_pinned + 6144, &tab, sizeof(tab));  // (pinned staging; at most 4096 bytes from word 6144)
+    PSAC_CUDA(cudaMemcpyAsync(e->tb[1].p, e->h_pinned + 6144, sizeof(tab), cudaMemcpyHostToDevice, st));
+    DistSearch<T> sr{};
+    sr.D = e->tb[1].as<DistTreeTable<T>>();
+    sr.div = BlkDiv::make(n, p);
+    sr.n_total = n;
+    return sr;
+}
+
+template <typename T>
+void ansv_sharded_core(psacb200_engine* e, const ShardComm& C, const T* d_vals_local, u64 n_local, u64 n, int left_type, int right_type, u64 nonsv,
+                       u64* d_left, u64* d_right) {
+    const BlkDist blk(n, C.world);
+    if (blk.size(C.rank) != n_local) throw arg_failure{"the values must be equally block decomposed across all ranks"};
+    TreeLayout L;
+    DistSearch<T> sr = dist_search_setup<T>(e, C, d_vals_local, n_local, n, L);
+    if (n_local) {
+        ansv_kernel<T, DistSearch<T>><<<grid_for(e, n_local, 256, 8), 256, 0, e->stream>>>(sr, blk.start(C.rank), n_local, left_type, right_type, nonsv, d_left, d_right);
+        e->launches += 1;
+        PSAC_CUDA(cudaGetLastError());
+    }
+    rank_barrier(e, C);  // my arena may be reused only after every rank is done searching it
+    PSAC_CUDA(cudaStreamSynchronize(e->stream));
+}
+
+// child table of the suffix tree from this rank's blocks of SA and LCP.  C == nullptr: one GPU.
+template <typename IdxT>
+void suffix_tree_core(psacb200_engine* e, const ShardComm* C, const u8* d_text_local, u64 n_local, u64 n, const IdxT* d_sa, const IdxT* d_lcp, u64* d_nodes,
+                      size_t nodes_len, uint32_t* sigma_out) {
+    const int p = C ? C->world : 1, me = C ? C->rank : 0;
+    cudaStream_t st = e->stream;
+    size_t* tot = &e->device_bytes;
+    const BlkDist blk(n, p);
+    if (blk.size(me) != n_local) throw arg_failure{"the arrays must be equally block decomposed across all ranks (reference suffix_array.hpp:226)"};
+    e->tr_n = 0;
+    e->mark("begin");
+    Alphabet alpha;
+    if (C)
+        prepare_text_sharded(e, *C, d_text_local, n_local, n, alpha);
+    else
+        prepare_text(e, d_text_local, n, nullptr, alpha);
+    if (sigma_out) *sigma_out = alpha.sigma;
+    const size_t width = (size_t)alpha.sigma + 1;
+    if (nodes_len < width * n_local) throw arg_failure{"nodes buffer too small: (sigma + 1) * n_local entries are needed"};
+    e->mark("text");
+    TreeFusedArgs<IdxT> A{};
+    A.sa = d_sa;
+    A.lcp = d_lcp;
+    A.g0 = blk.start(me);
+    A.m = n_local;
+    A.n = n;
+    A.stream = e->packed.as<u64>();
+    A.lbits = alpha.lbits;
+    A.sigma = alpha.sigma;
+    A.code_add = alpha.zero_code_used ? 0u : 1u;
+    A.nodes = d_nodes;
+    A.me = me;
+    A.div = BlkDiv::make(n, p);
+    unsigned long long* d_cur = reinterpret_cast<unsigned long long*>(e->shard_meta() + 128);  // [16] cursors, [16] overflow
+    PSAC_CUDA(cudaMemsetAsync(d_cur, 0, 17 * sizeof(u64), st));
+    A.q.cursor = d_cur;
+    A.q.overflow = d_cur + 16;
+    PSAC_CUDA(cudaMemsetAsync(d_nodes, 0, width * n_local * sizeof(u64), st));
+    if (C == nullptr) {
+        // one GPU: min-tree in a private buffer, nothing is queued
+        TreeLayout L = tree_layout<IdxT>(n, 1);
+        e->tb[0].reserve(L.o_queue + 64, tot);
+        PSAC_CUDA(cudaMemcpyAsync(e->tb[0].as<u8>() + L.o_lvl0, d_lcp, n * sizeof(IdxT), cudaMemcpyDeviceToDevice, st));
+        LocalSearch<IdxT> sr{mintree_describe<IdxT>(e->tb[0].as<u8>(), L, n)};
+        mintree_build<IdxT>(e, sr.t);
+        e->mark("mintree");
+        A.q.cap = 0;
+        suffix_tree_fused_kernel<IdxT, LocalSearch<IdxT>><<<grid_for(e, n, 256, 8), 256, 0, st>>>(A, sr);
+        e->launches += 1;
+        PSAC_CUDA(cudaGetLastError());
+        e->mark("tree");
+        PSAC_CUDA(cudaStreamSynchronize(st));
+        return;
+    }
+    TreeLayout L;
+    DistSearch<IdxT> sr = dist_search_setup<IdxT>(e, *C, d_lcp, n_local, n, L);
+    PeerArena& AR = *reinterpret_cast<PeerArena*>(e->peer_map);
+    e->mark("mintree");
+    A.q.cap = L.qcap;
+    for (int r = 0; r < 16; ++r) A.q.queue[r] = r < p ? reinterpret_cast<u64*>(AR.peer[r] + L.o_queue) + (size_t)me * L.qcap * 3 : nullptr;
+    if (n_local) {
+        suffix_tree_fused_kernel<IdxT, DistSearch<IdxT>><<<grid_for(e, n_local, 256, 8), 256, 0, st>>>(A, sr);
+        e->launches += 1;
+        PSAC_CUDA(cudaGetLastError());
+    }
+    e->mark("tree");
+    // edges queued for rows of other ranks: exchange the counts, apply mine
+    u64* d_all = e->shard_meta() + 160;  // [p][17]
+    PSAC_CUDA(cudaMemcpyAsync(d_all + (size_t)me * 17, d_cur, 17 * sizeof(u64), cudaMemcpyDeviceToDevice, st));
+    PSAC_NCCL(g_nccl.AllGather(d_all + (size_t)me * 17, d_all, 17, ncclUint64, C->comm, st));  // (orders every rank's queue writes before the apply)
+    PSAC_CUDA(cudaMemcpyAsync(e->h_pinned + 128, d_all, (size_t)p * 17 * sizeof(u64), cudaMemcpyDeviceToHost, st));
+    PSAC_CUDA(cudaStreamSynchronize(st));
+    u64 overflow = 0, applied = 0;
+    for (int s_ = 0; s_ < p; ++s_) {
+        overflow += e->h_pinned[128 + s_ * 17 + 16];
+        const u64 c = e->h_pinned[128 + s_ * 17 + me];
+        if (s_ == me || c == 0) continue;
+        tree_apply_edges_kernel<<<grid_for(e, c, 256, 8), 256, 0, st>>>(reinterpret_cast<const u64*>(AR.base + L.o_queue) + (size_t)s_ * L.qcap * 3, c, alpha.sigma, d_nodes);
+        e->launches += 1;
+        applied += c;
+    }
+    PSAC_CUDA(cudaGetLastError());
+    e->stats.unresolved_after_first = applied;  // (reported: edges that crossed ranks)
+    rank_barrier(e, *C);
+    e->mark("remote_edges");
+    PSAC_CUDA(cudaStreamSynchronize(st));
+    if (overflow) throw std::string("suffix tree: the cross-rank edge queue overflowed (") + std::to_string(overflow) + " edges)";
 }
 
 }  // namespace

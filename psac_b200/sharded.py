@@ -75,6 +75,38 @@ class ShardedSuffixArray:
                                              self.local_B.data_ptr() if m else None,
                                              self.local_LCP.data_ptr() if (m and self.construct_lcp) else None)
 
+    def construct_suffix_tree(self, sigma_plus_one=None):
+        """Collective; reference construct_suffix_tree(sa, begin, end, comm) (include/suffix_tree.hpp:413-499) on the blocks of the last
+        construct (needs construct_lcp): returns this rank's rows of the child table, an (local_size, sigma + 1) int64 CUDA tensor."""
+        if not self.construct_lcp:
+            raise api.PsacError("construct_suffix_tree needs the LCP array (construct_lcp=True)")
+        m = self.local_size
+        if sigma_plus_one is None:
+            # distinct characters of the whole text
+            h = torch.bincount(self._text.to(torch.int64), minlength=256)
+            if dist.get_backend() == "nccl":
+                dist.all_reduce(h)
+            else:
+                hc = h.cpu()
+                dist.all_reduce(hc)
+                h = hc
+            sigma_plus_one = int((h > 0).sum().item()) + 1
+        nodes = torch.empty((m, sigma_plus_one), dtype=torch.int64, device=self.device)
+        torch.cuda.current_stream(self.device).synchronize()
+        self.engine.suffix_tree_sharded_ptr(self._text.data_ptr() if m else None, m, self.n, self.index_bytes, self.local_SA.data_ptr() if m else None,
+                                            self.local_LCP.data_ptr() if m else None, nodes.data_ptr() if m else None, nodes.numel())
+        return nodes
+
+    def ansv(self, left_type=0, right_type=0, nonsv=0):
+        """Collective; reference ansv<index_t, left, right, global_indexing>(local_LCP, ...) (include/ansv.hpp:2042-2051): global indices."""
+        m = self.local_size
+        left = torch.empty(m, dtype=torch.int64, device=self.device)
+        right = torch.empty(m, dtype=torch.int64, device=self.device)
+        torch.cuda.current_stream(self.device).synchronize()
+        self.engine.ansv_sharded_ptr(self.local_LCP.data_ptr() if m else None, m, self.n, self.index_bytes, left_type, right_type, nonsv,
+                                     left.data_ptr() if m else None, right.data_ptr() if m else None)
+        return left, right
+
     def close(self):
         """Collective: ordered release of the peer-visible memory, then the engine."""
         if self.engine is not None:

@@ -14,9 +14,10 @@ from psac_b200 import api, textgen as G  # noqa: E402
 from psac_b200.sharded import ShardedSuffixArray  # noqa: E402
 
 
-def gather_blocks(t, n, p, rank, dev):
+def gather_blocks(t, n, p, rank, dev, sizes=None):
     """all ranks' blocks of a block-distributed int tensor -> one numpy array on rank 0"""
-    sizes = [api.blk_dist(n, p, r)[1] for r in range(p)]
+    if sizes is None:
+        sizes = [api.blk_dist(n, p, r)[1] for r in range(p)]
     mx = max(sizes)
     pad = torch.zeros(mx, dtype=t.dtype, device=dev)
     pad[: t.numel()] = t
@@ -25,7 +26,7 @@ def gather_blocks(t, n, p, rank, dev):
     return np.concatenate([o[:s].cpu().numpy() for o, s in zip(out, sizes)])
 
 
-def case(name, text, index_bytes, lcp, k=0, scheme=None):
+def case(name, text, index_bytes, lcp, k=0, scheme=None, tree=False):
     rank, p = dist.get_rank(), dist.get_world_size()
     dev = torch.device("cuda", torch.cuda.current_device())
     n = text.size
@@ -56,6 +57,33 @@ def case(name, text, index_bytes, lcp, k=0, scheme=None):
             ok = False
         print("%-38s n=%9d ib=%d lcp=%d k=%d scheme=%d rounds=%d unresolved=%d %s" % (name, n, index_bytes, int(lcp), k, st["sharded_scheme"], st["rounds"],
                                                                                     st["unresolved_after_first"], "ok" if ok else "MISMATCH"), flush=True)
+    if tree and lcp:
+        # suffix tree + ANSV from the blocks, sharded (psacb200_suffix_tree_sharded / _ansv_sharded)
+        nodes = sa.construct_suffix_tree()
+        width = nodes.shape[1]
+        got_nodes = gather_blocks(nodes.reshape(-1), n * width, p, rank, dev, sizes=[api.blk_dist(n, p, r)[1] * width for r in range(p)]).view(np.uint64)
+        l_, r_ = sa.ansv(2, 0, 2 ** 63 - 1)
+        got_l = gather_blocks(l_, n, p, rank, dev).view(np.uint64)
+        got_r = gather_blocks(r_, n, p, rank, dev).view(np.uint64)
+        if rank == 0:
+            want = O.ref_suffix_tree(text) if (O.have_ref() and index_bytes == 8) else None
+            if want is None:
+                e1 = api.Engine(torch.cuda.current_device())
+                want = e1.suffix_tree(text, exp["sa"].astype(udt), exp["lcp"].astype(udt))
+                e1.close()
+            if not (got_nodes.reshape(n, width) == want).all():
+                print("   suffix tree differs in %d cells" % int((got_nodes.reshape(n, width) != want).sum()), flush=True)
+                ok = False
+            wl = O.ansv_sequential  # nearest smaller on the right is what the sequential oracle gives directly
+            er = wl(exp["lcp"].astype(np.uint64), False, 2 ** 63 - 1)
+            if not (got_r == er).all():
+                print("   sharded ANSV (right, nearest_sm) differs in %d places" % int((got_r != er).sum()), flush=True)
+                ok = False
+            if n <= 300000:
+                el, _ = O.ansv(exp["lcp"].astype(np.uint64), 2, 0, 2 ** 63 - 1)
+                if not (got_l == el).all():
+                    print("   sharded ANSV (left, furthest_eq) differs in %d places" % int((got_l != el).sum()), flush=True)
+                    ok = False
     if name.startswith("random DNA, aligned") and lcp:
         # the certificate must also FAIL when it should: corrupt one LCP entry and one SA entry of the last rank's block
         sa.local_LCP[3] += 1
@@ -81,18 +109,18 @@ def main():
     ok = True
     # scheme 2: word exchange fused into digit pass 1, distributed later rounds (sharded.cuh construct_sharded_v2)
     ok &= case("random DNA, aligned blocks", G.random_dna(p << 20, 11), 8, True, scheme=2)
-    ok &= case("random DNA, ragged blocks", G.random_dna((p << 20) + 13, 12), 8, True, scheme=2)
-    ok &= case("random DNA, 32-bit index", G.random_dna((p << 19) + 5, 13), 4, True, scheme=2)
+    ok &= case("random DNA, ragged blocks + tree", G.random_dna((p << 20) + 13, 12), 8, True, scheme=2, tree=True)
+    ok &= case("random DNA, 32-bit index + tree", G.random_dna((p << 17) + 5, 13), 4, True, scheme=2, tree=True)
     ok &= case("random DNA, no LCP", G.random_dna((p << 19) + 3, 23), 8, False, scheme=2)
     ok &= case("random DNA, k=7: distributed rounds", G.random_dna(p << 20, 18), 8, True, k=7, scheme=2)
     ok &= case("random DNA, short first key (k=4)", G.random_dna(p << 18, 14), 8, True, k=4, scheme=2)
     ok &= case("random DNA, one-digit key (k=2)", G.random_dna(p << 17, 24), 8, True, k=2, scheme=2)
-    ok &= case("protein-like alphabet", (G.random_bytes(p << 18, 16) % 20 + 65).astype(np.uint8), 8, True, scheme=2)
-    ok &= case("repetitive text", G.repeats_text(40000 * p, 3), 8, True)
-    ok &= case("periodic text (abc)^k", G.periodic_text(b"abc", 60000 * p), 4, True)
+    ok &= case("protein-like alphabet + tree", (G.random_bytes(p << 18, 16) % 20 + 65).astype(np.uint8), 8, True, scheme=2, tree=True)
+    ok &= case("repetitive text + tree", G.repeats_text(40000 * p, 3), 8, True, tree=True)
+    ok &= case("periodic text (abc)^k + tree", G.periodic_text(b"abc", 60000 * p), 4, True, tree=True)
     ok &= case("two-symbol text", (G.random_bytes(p << 17, 25) % 2 + 97).astype(np.uint8), 8, True)
     ok &= case("random bytes (sigma=256 quirk)", G.random_bytes_config4(p << 18, 15), 8, False, scheme=1)
-    ok &= case("small input (replicated path)", G.random_dna(1000 + p, 17), 8, True, scheme=0)
+    ok &= case("small input (replicated path) + tree", G.random_dna(1000 + p, 17), 8, True, scheme=0, tree=True)
     # scheme 1 (the fallback): key-range selection + replicated rounds, all four exchange variants
     os.environ["PSACB200_SHARDED_V1"] = "1"
     ok &= case("v1: random DNA", G.random_dna((p << 19) + 1, 26), 8, True, scheme=1)

@@ -96,3 +96,50 @@ def test_suffix_tree_end_to_end_from_engine_outputs(eng):
     assert np.unique(inner).size == inner.size
     if O.have_ref():
         assert (nodes == O.ref_suffix_tree(t)).all()
+
+
+# ------------------------------------------------------------------------------------------- device-resident entry points
+def _dev(a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a).view(np.int64 if a.dtype.itemsize == 8 else (np.int32 if a.dtype.itemsize == 4 else np.uint8))).to("cuda:0")
+
+
+@pytest.mark.parametrize("ib", [4, 8])
+def test_device_suffix_tree_fused_matches_reference_table(eng, ib):
+    """psacb200_suffix_tree_device (ANSV searched on the fly, device arrays) against the host entry point, which is
+    pinned to the unmodified reference above, and against the reference itself where it travels."""
+    import torch
+    dt = np.uint32 if ib == 4 else np.uint64
+    texts = [G.random_dna(n, 31 + n) for n in (1, 2, 116, 23713, 300007)] + [G.periodic_text(b"abc", 151), np.frombuffer(b"mississippi", np.uint8),
+                                                                             (G.random_bytes(60000, 2) % 20 + 65).astype(np.uint8), G.repeats_text(2000, 5),
+                                                                             G.random_bytes_config4(1 << 16, 3)]
+    for t in texts:
+        t = np.ascontiguousarray(t, np.uint8)
+        r = eng.construct(t, ib, True)
+        want = eng.suffix_tree(t, r["sa"], r["lcp"])
+        d_t, d_sa, d_lcp = _dev(t), _dev(r["sa"].astype(dt)), _dev(r["lcp"].astype(dt))
+        width = want.shape[1]
+        d_nodes = torch.full((t.size, width), -1, dtype=torch.int64, device="cuda:0")
+        torch.cuda.synchronize()
+        sigma = eng.suffix_tree_device_ptr(d_t.data_ptr(), t.size, ib, d_sa.data_ptr(), d_lcp.data_ptr(), d_nodes.data_ptr(), d_nodes.numel())
+        assert sigma + 1 == width
+        got = d_nodes.cpu().numpy().view(np.uint64)
+        assert (got == want).all(), (t.size, ib)
+        if O.have_ref() and t.size > 1 and ib == 8:
+            assert (got == O.ref_suffix_tree(t)).all()
+
+
+def test_device_ansv_matches_host_api(eng):
+    import torch
+    rng = np.random.default_rng(11)
+    for n in (1, 33, 1000, 200003):
+        for dt in (np.uint32, np.uint64):
+            v = rng.integers(0, 50, size=n).astype(dt)
+            d_v = _dev(v)
+            d_l = torch.empty(n, dtype=torch.int64, device="cuda:0")
+            d_r = torch.empty(n, dtype=torch.int64, device="cuda:0")
+            torch.cuda.synchronize()
+            for lt, rt in ((0, 0), (2, 0), (1, 2)):
+                eng.ansv_device_ptr(d_v.data_ptr(), n, v.dtype.itemsize, lt, rt, int(NONSV), d_l.data_ptr(), d_r.data_ptr())
+                l, r = eng.ansv(v, lt, rt, int(NONSV))
+                assert (d_l.cpu().numpy().view(np.uint64) == l).all() and (d_r.cpu().numpy().view(np.uint64) == r).all(), (n, lt, rt)
