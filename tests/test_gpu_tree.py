@@ -112,7 +112,7 @@ def test_device_suffix_tree_fused_matches_reference_table(eng, ib):
     dt = np.uint32 if ib == 4 else np.uint64
     texts = [G.random_dna(n, 31 + n) for n in (1, 2, 116, 23713, 300007)] + [G.periodic_text(b"abc", 151), np.frombuffer(b"mississippi", np.uint8),
                                                                              (G.random_bytes(60000, 2) % 20 + 65).astype(np.uint8), G.repeats_text(2000, 5),
-                                                                             G.random_bytes_config4(1 << 16, 3)]
+                                                                             G.random_dna(70001, 77)]
     for t in texts:
         t = np.ascontiguousarray(t, np.uint8)
         r = eng.construct(t, ib, True)
@@ -125,7 +125,7 @@ def test_device_suffix_tree_fused_matches_reference_table(eng, ib):
         assert sigma + 1 == width
         got = d_nodes.cpu().numpy().view(np.uint64)
         assert (got == want).all(), (t.size, ib)
-        if O.have_ref() and t.size > 1 and ib == 8:
+        if O.have_ref() and t.size > 2 and ib == 8:  # (n <= 2: the reference's LCP[1] is uninitialised, tests/test_gpu_parity.py)
             assert (got == O.ref_suffix_tree(t)).all()
 
 
