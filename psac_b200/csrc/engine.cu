@@ -217,7 +217,27 @@ void read_counts(psacb200_engine* e, u64* m, u64* nb) {
 // Moves an internal result array (IdxT) to the caller's buffer (index_bytes wide, host or device).
 template <typename SrcT>
 void emit(psacb200_engine* e, const SrcT* src, void* dst, u64 n, int index_bytes, bool dst_is_host) {
-    if (dst == nullptr || (const void*)src == dst) return;
+    if (dst == nullptr) return;
+    if ((const void*)src == dst) {
+        if ((int)sizeof(SrcT) == index_bytes) return;  // the result was built in the caller's buffer
+        // The internal 32-bit array occupies the lower half of the caller's 64-bit buffer (reserve_buffers): widen in
+        // place from the top down.  Elements [c/2, c) are read at bytes [2c, 4c) and written to [4c, 8c): no overlap inside
+        // a launch, and everything a launch overwrites has been consumed by the launches before it.
+        u64* out = reinterpret_cast<u64*>(dst);
+        u64 c1 = n;
+        while (c1 > 1) {
+            const u64 c0 = (c1 + 1) / 2;  // 8 * c0 >= 4 * c1: the launch writes behind everything it reads
+            convert_kernel<SrcT, u64><<<grid_for(e, c1 - c0, 256, 16), 256, 0, e->stream>>>(src + c0, out + c0, c1 - c0);
+            e->launches += 1;
+            c1 = c0;
+        }
+        if (c1 == 1) {
+            convert_kernel<SrcT, u64><<<1, 32, 0, e->stream>>>(src, out, 1);  // element 0: one thread reads, then writes
+            e->launches += 1;
+        }
+        PSAC_CUDA(cudaGetLastError());
+        return;
+    }
     if ((int)sizeof(SrcT) == index_bytes) {
         PSAC_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(SrcT), dst_is_host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, e->stream));
         return;
@@ -304,7 +324,12 @@ void construct_core(psacb200_engine* e, u64 n, int index_bytes, unsigned flags, 
     S.internal_index_bytes = sizeof(IdxT);
     S.sort_elt_bytes = (uint32_t)(sizeof(KeyC) + sizeof(IdxT));
     const int lbits = alpha.lbits;
-    const bool inplace = !out_is_host && index_bytes == (int)sizeof(IdxT);
+    auto aligned16 = [](const void* q) { return (reinterpret_cast<size_t>(q) & 15) == 0; };  // (the kernels use 128-bit stores)
+    // Caller's DEVICE buffers double as the engine's result arrays: directly when the widths match, and as storage for the
+    // 32-bit internal array (widened in place at the end, see emit) when the caller's index is 64 bits wide -- at
+    // BASELINE configs[3] (2^32 characters) that keeps 48 GiB of device memory free.
+    const bool inplace = !out_is_host && (index_bytes == (int)sizeof(IdxT) || (index_bytes == 8 && sizeof(IdxT) == 4)) && aligned16(sa_out) &&
+                         aligned16(isa_out) && aligned16(lcp_out);
     const bool ext_sa = inplace, ext_isa = inplace && isa_out != nullptr, ext_lcp = inplace && want_lcp;
     reserve_buffers<IdxT>(e, n, sizeof(KeyC), want_lcp, ext_sa, ext_isa, ext_lcp);
 
@@ -382,7 +407,7 @@ void construct_core(psacb200_engine* e, u64 n, int index_bytes, unsigned flags, 
     R.isa_lo = 0;
     R.isa_hi = n;
     R.suf_out = nullptr;
-    if (sizeof(KeyC) == 4 || (sizeof(IdxT) == 4 && !alpha.zero_code_used)) {
+    if (sizeof(KeyC) == 4 || (sizeof(IdxT) == 4 && (!alpha.zero_code_used || !want_lcp))) {
         // lean path: heads from the keys alone (sa_kernels.cuh heads_kernel); the suffixes that run past the end of the
         // text are located in the sorted order first
         const u64 T = (n < (u64)C - 1) ? n : (u64)C - 1;
@@ -710,7 +735,10 @@ int construct_entry(psacb200_engine* e, const u8* text, bool text_is_host, size_
         const RadixPlan plan0 = make_radix_plan(0, (int)C * alpha.lbits);
         const int carried_bits = (int)C * alpha.lbits - plan0.bits[plan0.npass - 1];  // key bits below the top digit
         if ((u64)n <= (1ull << 32)) {
-            if (carried_bits <= 32 && !alpha.zero_code_used)  // (the |Sigma| = 256 quirk takes the generic 64-bit-key path)
+            // (the |Sigma| = 256 quirk changes only the LCP -- it counts matches against the zero padding -- so it needs the
+            //  generic 64-bit-key path only when the LCP array is wanted; SA / ISA come out of the lean path unchanged:
+            //  dense code 0 = 0xFF compares equal to the padding exactly as in the reference's zero-padded k-mers)
+            if (carried_bits <= 32 && (!alpha.zero_code_used || !(flags & PSACB200_LCP)))
                 construct_core<u32, u32>(e, n, index_bytes, flags, alpha, C, sa_out, isa_out, lcp_out, text_is_host);
             else
                 construct_core<u32, u64>(e, n, index_bytes, flags, alpha, C, sa_out, isa_out, lcp_out, text_is_host);

@@ -113,3 +113,20 @@ def random_dna_torch(n, seed, device, start=0, chunk=1 << 26):
         out[pos:pos + m] = acgt[codes[off:off + m]]
         pos += m
     return out
+
+
+def random_bytes_torch(n, seed, device, start=0, chunk=1 << 29):
+    """Bit-identical to random_bytes(n, seed, start), generated with torch ops on `device`; returns a uint8 tensor."""
+    import torch
+    out = torch.empty(n, dtype=torch.uint8, device=device)
+    pos = 0
+    while pos < n:
+        m = min(chunk, n - pos)
+        g0 = start + pos
+        w0, w1 = g0 // 8, (g0 + m + 7) // 8
+        words = splitmix64_torch(seed, torch.arange(w0, w1, dtype=torch.int64, device=device))
+        b = words.view(torch.uint8)  # little-endian bytes of every word, as in the numpy generator
+        off = g0 - w0 * 8
+        out[pos:pos + m] = b[off:off + m]
+        pos += m
+    return out

@@ -192,3 +192,48 @@ def test_errors(eng):
         eng.construct(b"abc", 3)
     r = eng.construct(b"", 8, True)
     assert r["sa"].size == 0
+
+
+# ------------------------------------------------------------------------------------------- device outputs wider than the internal index
+@pytest.mark.parametrize("n", [1, 2, 3, 7, 1000, 65537, (1 << 20) + 3])
+@pytest.mark.parametrize("lcp", [False, True])
+def test_device_outputs_64bit_hold_the_32bit_arrays_and_are_widened_in_place(eng, n, lcp):
+    """64-bit caller buffers on the device double as storage of the engine's 32-bit arrays and are widened in place
+    (engine.cu emit): every size parity, with and without LCP."""
+    import torch
+    t = G.random_dna(n, 900 + n)
+    dev = torch.device("cuda", 0)
+    d_t = torch.from_numpy(t).to(dev)
+    out = [torch.full((n,), -1, dtype=torch.int64, device=dev) for _ in range(3)]
+    torch.cuda.synchronize()
+    eng.construct_ptr(d_t.data_ptr(), n, 8, api.LCP if lcp else 0, 0, out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr() if lcp else None, device=True)
+    exp = O.construct(t, 64, 0, lcp)
+    assert (out[0].cpu().numpy().view(np.uint64) == exp["sa"]).all()
+    assert (out[1].cpu().numpy().view(np.uint64) == exp["isa"]).all()
+    if lcp and n > 2:
+        assert (out[2].cpu().numpy().view(np.uint64) == exp["lcp"]).all()
+
+
+def test_all_256_byte_values_without_lcp_take_the_lean_path(eng):
+    """BASELINE configs[3] shape at test size: every byte value occurs (reference LUT overflow: 0xFF gets code 0 = the
+    padding), SA / ISA only.  The lean 32-bit-key path must reproduce the reference's order exactly; with LCP the generic
+    path is taken and must agree as well."""
+    import torch
+    t = G.random_bytes_config4((1 << 19) + 5, 41)
+    assert len(np.unique(t)) == 256
+    exp = O.construct(t, 64, 0, True)
+    r = eng.construct(t, 8, False)
+    assert (r["sa"] == exp["sa"]).all() and (r["isa"] == exp["isa"]).all()
+    assert eng.stats()["sort_elt_bytes"] == 8  # 32-bit carried key + 32-bit suffix index
+    r = eng.construct(t, 8, True)
+    assert (r["sa"] == exp["sa"]).all() and (r["lcp"] == exp["lcp"]).all()
+    assert eng.stats()["sort_elt_bytes"] == 12  # generic path: 64-bit keys
+    # device buffers, 64-bit index, no LCP: the bench path of configs[3]
+    dev = torch.device("cuda", 0)
+    d_t = torch.from_numpy(t).to(dev)
+    d_sa = torch.empty(t.size, dtype=torch.int64, device=dev)
+    d_isa = torch.empty_like(d_sa)
+    torch.cuda.synchronize()
+    eng.construct_ptr(d_t.data_ptr(), t.size, 8, 0, 0, d_sa.data_ptr(), d_isa.data_ptr(), None, device=True)
+    assert (d_sa.cpu().numpy().view(np.uint64) == exp["sa"]).all() and (d_isa.cpu().numpy().view(np.uint64) == exp["isa"]).all()
+    assert eng.check_device_ptr(d_t.data_ptr(), t.size, 8, d_sa.data_ptr(), d_isa.data_ptr(), None)["ok"]
