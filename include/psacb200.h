@@ -173,6 +173,19 @@ int psacb200_ansv(psacb200_engine* e, const void* vals, size_t n, int val_bytes,
 int psacb200_suffix_tree(psacb200_engine* e, const uint8_t* text, size_t n, int index_bytes, const void* sa, const void* lcp, uint64_t* nodes,
                          size_t nodes_len);
 
+/* ---- several GPUs of one box behind ONE host call (the object a p = 1 caller of the reference class binds) -- */
+/* One engine per GPU, driven by one host thread each inside the call; text, SA, ISA and LCP are sharded by block over the GPUs
+ * internally (the same sharded construction as psacb200_construct_sharded; peer memory through plain peer access), the caller
+ * passes and receives WHOLE HOST arrays exactly as with psacb200_construct.  dev_ids may be NULL (devices 0 .. n_gpus-1). */
+typedef struct psacb200_multi psacb200_multi;
+int psacb200_multi_create(int n_gpus, const int* dev_ids, psacb200_multi** out);
+void psacb200_multi_destroy(psacb200_multi* m);
+int psacb200_multi_gpus(const psacb200_multi* m);
+psacb200_engine* psacb200_multi_engine(const psacb200_multi* m, int r); /* engine of GPU r (owned by the handle), e.g. for psacb200_alphabet */
+int psacb200_multi_construct(psacb200_multi* m, const uint8_t* text, size_t n, int index_bytes, unsigned flags, unsigned k, void* sa_out, void* isa_out,
+                             void* lcp_out);
+int psacb200_multi_get_stats(const psacb200_multi* m, psacb200_stats* out); /* statistics of GPU 0's share of the last call */
+
 /* ---- the same on DEVICE arrays, on one GPU or block-sharded over the ranks of psacb200_comm_init (BASELINE configs[4]) ------- */
 /* ANSV of n DEVICE values; left / right: DEVICE arrays of n u64. */
 int psacb200_ansv_device(psacb200_engine* e, const void* d_vals, size_t n, int val_bytes, int left_type, int right_type, uint64_t nonsv, uint64_t* d_left,

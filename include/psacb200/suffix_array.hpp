@@ -30,12 +30,16 @@
 
 namespace psacb200 {
 
-// stand-in for mxx::comm at p = 1 (reference ext/mxx/include/mxx/comm_fwd.hpp:44-); device = CUDA ordinal to use
+// stand-in for mxx::comm at p = 1 (reference ext/mxx/include/mxx/comm_fwd.hpp:44-).  device = first CUDA ordinal to use;
+// n_gpus > 1: the construction is sharded over the devices device .. device + n_gpus - 1 INSIDE the engine
+// (psacb200_multi_construct): the object still holds the whole arrays, size() stays 1.
 struct comm {
     int device;
-    explicit comm(int device_ = 0) : device(device_) {}
+    int n_gpus;
+    explicit comm(int device_ = 0, int n_gpus_ = 1) : device(device_), n_gpus(n_gpus_ < 1 ? 1 : n_gpus_) {}
     int size() const { return 1; }
     int rank() const { return 0; }
+    int gpus() const { return n_gpus; }
     comm copy() const { return *this; }
 };
 
@@ -59,9 +63,12 @@ class suffix_array {
     static_assert(std::is_unsigned<index_t>::value, "index_t must be unsigned");
 
 public:
-    explicit suffix_array(const psacb200::comm& c) : n(0), local_size(0), comm(c.copy()), p(1), engine_(nullptr) {}
+    explicit suffix_array(const psacb200::comm& c) : n(0), local_size(0), comm(c.copy()), p(1), engine_(nullptr), multi_(nullptr) {}
     virtual ~suffix_array() {
-        if (engine_) psacb200_destroy(engine_);
+        if (multi_)
+            psacb200_multi_destroy(multi_);  // (owns its engines)
+        else if (engine_)
+            psacb200_destroy(engine_);
     }
     suffix_array(const suffix_array&) = delete;
     suffix_array& operator=(const suffix_array&) = delete;
@@ -151,7 +158,8 @@ public:
     }
 
 private:
-    psacb200_engine* engine_;
+    psacb200_engine* engine_;  // the engine of the (first) GPU
+    psacb200_multi* multi_;    // several GPUs: the handle that owns all engines
     std::vector<uint8_t> staging_;
 
     static void write_array(const std::string& filename, const std::vector<index_t>& v) {
@@ -171,7 +179,15 @@ private:
         if (rc != PSACB200_OK) throw std::runtime_error(std::string("psacb200: ") + psacb200_last_error());
     }
     void ensure_engine() {
-        if (!engine_) check(psacb200_create(comm.device, &engine_));
+        if (engine_) return;
+        if (comm.gpus() > 1) {
+            std::vector<int> devs;
+            for (int i = 0; i < comm.gpus(); ++i) devs.push_back(comm.device + i);
+            check(psacb200_multi_create(comm.gpus(), devs.data(), &multi_));
+            engine_ = psacb200_multi_engine(multi_, 0);
+        } else {
+            check(psacb200_create(comm.device, &engine_));
+        }
     }
     // the C ABI takes one contiguous byte buffer; pointers and vector/string iterators are passed through, anything
     // else is copied once
@@ -194,8 +210,10 @@ private:
         if (want_lcp) local_LCP.resize(n);
         const unsigned flags = (want_lcp ? PSACB200_LCP : 0u) | (fast_resolval ? PSACB200_FAST_RESOLVAL : 0u);
         void* lcp = want_lcp ? (void*)local_LCP.data() : nullptr;
-        if (lut)
+        if (lut)  // (a caller-supplied code order runs on the first GPU)
             check(psacb200_construct_alphabet(engine_, text, n, (int)sizeof(index_t), flags, k, lut, local_SA.data(), local_B.data(), lcp));
+        else if (multi_)
+            check(psacb200_multi_construct(multi_, text, n, (int)sizeof(index_t), flags, k, local_SA.data(), local_B.data(), lcp));
         else
             check(psacb200_construct(engine_, text, n, (int)sizeof(index_t), flags, k, local_SA.data(), local_B.data(), lcp));
     }

@@ -119,6 +119,14 @@ def lib():
         L.psacb200_suffix_tree_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_uint32)]
         L.psacb200_suffix_tree_sharded.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
                                                    C.POINTER(C.c_uint32)]
+        L.psacb200_multi_create.argtypes = [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]
+        L.psacb200_multi_destroy.argtypes = [C.c_void_p]
+        L.psacb200_multi_destroy.restype = None
+        L.psacb200_multi_gpus.argtypes = [C.c_void_p]
+        L.psacb200_multi_engine.argtypes = [C.c_void_p, C.c_int]
+        L.psacb200_multi_engine.restype = C.c_void_p
+        L.psacb200_multi_construct.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_uint, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.psacb200_multi_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
         L.psacb200_plan_word_exchange.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_uint64] + [C.c_void_p] * 6 + [C.POINTER(C.c_int)]
         _lib = L
     return _lib
@@ -307,6 +315,48 @@ class Engine:
         assert keys.flags.c_contiguous and keys.dtype in (np.uint32, np.uint64)
         vb = 0 if vals is None else vals.dtype.itemsize
         _check(lib().psacb200_sort_pairs_host(self._h, _ptr(keys), _ptr(vals), keys.size, keys.dtype.itemsize, vb, begin_bit, end_bit))
+
+
+class MultiEngine:
+    """Several GPUs of one box behind one host call (psacb200_multi_*): whole host arrays in and out, sharded internally."""
+
+    def __init__(self, n_gpus, dev_ids=None):
+        self._h = C.c_void_p()
+        ids = None if dev_ids is None else np.ascontiguousarray(dev_ids, np.int32)
+        _check(lib().psacb200_multi_create(int(n_gpus), _ptr(ids), C.byref(self._h)))
+        self.n_gpus = int(n_gpus)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            lib().psacb200_multi_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def stats(self):
+        s = Stats()
+        _check(lib().psacb200_multi_get_stats(self._h, C.byref(s)))
+        return s.as_dict()
+
+    def construct(self, text, index_bytes=8, want_lcp=False, k=0, out=None):
+        t = _as_text(text)
+        n = t.size
+        dt = np.uint32 if index_bytes == 4 else np.uint64
+        if out is None:
+            sa, isa, lcp = np.empty(n, dt), np.empty(n, dt), (np.empty(n, dt) if want_lcp else None)
+        else:
+            sa, isa, lcp = out
+        flags = (LCP if want_lcp else 0) | FAST_RESOLVAL
+        _check(lib().psacb200_multi_construct(self._h, _ptr(t), n, index_bytes, flags, k, _ptr(sa), _ptr(isa), _ptr(lcp)))
+        return dict(sa=sa, isa=isa, lcp=lcp)
+
+    def construct_ptr(self, text_ptr, n, index_bytes, flags, k, sa_ptr, isa_ptr, lcp_ptr):
+        """Raw (pinned) host pointers."""
+        _check(lib().psacb200_multi_construct(self._h, _ptr(text_ptr), n, index_bytes, flags, k, _ptr(sa_ptr), _ptr(isa_ptr), _ptr(lcp_ptr)))
 
 
 def _as_text(t):

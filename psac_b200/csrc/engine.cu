@@ -11,6 +11,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/psacb200.h"
@@ -1484,6 +1485,141 @@ int psacb200_suffix_tree_sharded(psacb200_engine* e, const uint8_t* d_text_local
             suffix_tree_core<u64>(e, &C, d_text_local, n_local, n_global, reinterpret_cast<const u64*>(d_sa_local), reinterpret_cast<const u64*>(d_lcp_local),
                                   d_nodes_local, nodes_len, sigma_out);
         return PSACB200_OK;
+    });
+}
+
+}  // extern "C"
+
+// ================================================================================================ several GPUs behind ONE host call
+// psacb200_multi: the reference-facing object holds the whole arrays (p = 1 from the caller's point of view, SURVEY.md
+// section 8b) while the GPUs of the box are sharded inside the engine: one engine + one host thread per GPU, the same
+// sharded construction (sharded.cuh) over an NCCL communicator of the engines, peer memory between them through plain
+// peer access (one process: no IPC).
+struct psacb200_multi {
+    std::vector<psacb200_engine*> eng;
+    psacb200_stats stats;
+};
+
+namespace {
+template <typename F>
+int run_on_all(psacb200_multi* m, F&& f) {
+    const int p = (int)m->eng.size();
+    std::vector<int> rc(p, PSACB200_OK);
+    std::vector<std::string> err(p);
+    std::vector<std::thread> th;
+    for (int r = 0; r < p; ++r)
+        th.emplace_back([&, r]() {
+            rc[r] = f(r);
+            if (rc[r] != PSACB200_OK) err[r] = psacb200_last_error();  // (the message is thread-local)
+        });
+    for (auto& t : th) t.join();
+    for (int r = 0; r < p; ++r)
+        if (rc[r] != PSACB200_OK) {
+            set_last_error("GPU " + std::to_string(r) + ": " + err[r]);
+            return rc[r];
+        }
+    return PSACB200_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int psacb200_multi_create(int n_gpus, const int* dev_ids, psacb200_multi** out) {
+    if (!out || n_gpus < 1 || n_gpus > 16) {
+        set_last_error("psacb200_multi_create: 1..16 GPUs and a non-null out pointer");
+        return PSACB200_ERR_ARG;
+    }
+    *out = nullptr;
+    psacb200_multi* m = new psacb200_multi();
+    memset(&m->stats, 0, sizeof(m->stats));
+    for (int r = 0; r < n_gpus; ++r) {
+        psacb200_engine* e = nullptr;
+        const int rc = psacb200_create(dev_ids ? dev_ids[r] : r, &e);
+        if (rc != PSACB200_OK) {
+            psacb200_multi_destroy(m);
+            return rc;
+        }
+        m->eng.push_back(e);
+    }
+    if (n_gpus > 1) {
+        uint8_t id[128];
+        int rc = psacb200_comm_unique_id(id);
+        if (rc == PSACB200_OK) rc = run_on_all(m, [&](int r) { return psacb200_comm_init(m->eng[r], id, r, n_gpus); });
+        if (rc != PSACB200_OK) {
+            psacb200_multi_destroy(m);
+            return rc;
+        }
+    }
+    *out = m;
+    return PSACB200_OK;
+}
+
+void psacb200_multi_destroy(psacb200_multi* m) {
+    if (!m) return;
+    if (m->eng.size() > 1) run_on_all(m, [&](int r) { return m->eng[r]->nccl_comm ? psacb200_comm_finalize(m->eng[r]) : PSACB200_OK; });
+    for (psacb200_engine* e : m->eng) psacb200_destroy(e);
+    delete m;
+}
+
+int psacb200_multi_gpus(const psacb200_multi* m) { return m ? (int)m->eng.size() : 0; }
+
+psacb200_engine* psacb200_multi_engine(const psacb200_multi* m, int r) { return (m && r >= 0 && r < (int)m->eng.size()) ? m->eng[r] : nullptr; }
+
+int psacb200_multi_get_stats(const psacb200_multi* m, psacb200_stats* out) {
+    if (!m || !out || m->eng.empty()) {
+        set_last_error("null argument");
+        return PSACB200_ERR_ARG;
+    }
+    return psacb200_get_stats(m->eng[0], out);
+}
+
+int psacb200_multi_construct(psacb200_multi* m, const uint8_t* text, size_t n, int index_bytes, unsigned flags, unsigned k, void* sa_out, void* isa_out,
+                             void* lcp_out) {
+    if (!m || m->eng.empty()) {
+        set_last_error("null handle");
+        return PSACB200_ERR_ARG;
+    }
+    const int p = (int)m->eng.size();
+    if (p == 1) return psacb200_construct(m->eng[0], text, n, index_bytes, flags, k, sa_out, isa_out, lcp_out);
+    if (index_bytes != 4 && index_bytes != 8) {
+        set_last_error("index_bytes must be 4 or 8");
+        return PSACB200_ERR_ARG;
+    }
+    if (n > 0 && (!text || !sa_out)) {
+        set_last_error("null text / sa_out");
+        return PSACB200_ERR_ARG;
+    }
+    if ((flags & PSACB200_LCP) && n > 0 && !lcp_out) {
+        set_last_error("PSACB200_LCP set but lcp_out is null");
+        return PSACB200_ERR_ARG;
+    }
+    if (n == 0) return PSACB200_OK;
+    const bool want_lcp = (flags & PSACB200_LCP) != 0;
+    return run_on_all(m, [&](int r) -> int {
+        psacb200_engine* e = m->eng[r];
+        return guarded([&]() -> int {
+            PSAC_CUDA(cudaSetDevice(e->device));
+            const BlkDist blk(n, p);
+            const u64 lo = blk.start(r), nl = blk.size(r);
+            size_t* tot = &e->device_bytes;
+            const size_t ob = (nl + 16) * (size_t)index_bytes;
+            e->tb[2].reserve(nl + 64, tot);
+            e->tb[3].reserve(ob, tot);
+            e->tb[4].reserve(ob, tot);
+            if (want_lcp) e->tb[5].reserve(ob, tot);
+            if (nl) PSAC_CUDA(cudaMemcpyAsync(e->tb[2].p, text + lo, nl, cudaMemcpyHostToDevice, e->stream));
+            PSAC_CUDA(cudaStreamSynchronize(e->stream));
+            const int rc = psacb200_construct_sharded(e, e->tb[2].as<u8>(), nl, n, index_bytes, flags, k, e->tb[3].p, e->tb[4].p, want_lcp ? e->tb[5].p : nullptr);
+            if (rc != PSACB200_OK) return rc;
+            const size_t off = (size_t)lo * index_bytes, bytes = (size_t)nl * index_bytes;
+            if (bytes) {
+                PSAC_CUDA(cudaMemcpyAsync(reinterpret_cast<u8*>(sa_out) + off, e->tb[3].p, bytes, cudaMemcpyDeviceToHost, e->stream));
+                if (isa_out) PSAC_CUDA(cudaMemcpyAsync(reinterpret_cast<u8*>(isa_out) + off, e->tb[4].p, bytes, cudaMemcpyDeviceToHost, e->stream));
+                if (want_lcp) PSAC_CUDA(cudaMemcpyAsync(reinterpret_cast<u8*>(lcp_out) + off, e->tb[5].p, bytes, cudaMemcpyDeviceToHost, e->stream));
+            }
+            PSAC_CUDA(cudaStreamSynchronize(e->stream));
+            return PSACB200_OK;
+        });
     });
 }
 

@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_stats_struct_matches_header_size():
     # 4 u64-ish header words + floats; the C side memsets sizeof(psacb200_stats) -- keep the mirror in sync
-    assert C.sizeof(api.Stats) == 120  # static_assert'ed on the C side (engine.cu)
+    assert C.sizeof(api.Stats) == 128  # static_assert'ed on the C side (engine.cu)
 
 
 def test_no_cpu_fallback_without_gpu():
