@@ -302,6 +302,29 @@ def ref_suffix_tree(text):
     return nodes[: w * n].reshape(n, w).copy()
 
 
+def ref_write(text, index_bytes, basename):
+    """the UNMODIFIED reference builds SA + LCP of `text` and writes <basename>.sa / .lcp / .alpha with its own write()"""
+    t = _text(text)
+    rc = ref().psacref_write(_vp(t), C.c_size_t(t.size), C.c_int(index_bytes), str(basename).encode())
+    if rc != 0:
+        raise RuntimeError("psacref_write rc=%d" % rc)
+
+
+def ref_read(basename, index_bytes, cap):
+    """the UNMODIFIED reference reads <basename>.sa / .lcp / .alpha with its own read(): dict(n, sa, lcp, lut, sigma)"""
+    dt = np.uint32 if index_bytes == 4 else np.uint64
+    sa = np.zeros(cap, dt)
+    lcp = np.zeros(cap, dt)
+    lut = np.zeros(256, np.uint8)
+    sigma = C.c_uint()
+    f = ref().psacref_read
+    f.restype = C.c_long
+    n = f(str(basename).encode(), C.c_int(index_bytes), _vp(sa), _vp(lcp), C.c_size_t(cap), _vp(lut), C.byref(sigma))
+    if n < 0:
+        raise RuntimeError("psacref_read rc=%d" % n)
+    return dict(n=int(n), sa=sa[:n], lcp=lcp[:n], lut=lut, sigma=sigma.value)
+
+
 def ref_rand_dna(n, seed):
     out = np.zeros(n, np.uint8)
     ref().psacref_rand_dna(C.c_size_t(n), C.c_int(seed), _vp(out))

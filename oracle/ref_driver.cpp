@@ -183,6 +183,60 @@ long psacref_suffix_tree(const char* text, size_t n, uint64_t* nodes_out, size_t
     }
 }
 
+/* File formats of the reference's own suffix_array::write / read (include/suffix_array.hpp:232-265; .sa / .lcp raw index_t
+ * through mxx::coll_file, .alpha through alphabet::write): used by tests/test_fileio.py to cross-check psac_b200/fileio.py and the
+ * C++ mirror's write / read against files the UNMODIFIED reference wrote, and to let the reference read files written here. */
+int psacref_write(const char* text, size_t n, int index_bytes, const char* basename) {
+    try {
+        cerr_mute mute(!g_verbose);
+        mxx::comm c;
+        if (index_bytes == 4) {
+            suffix_array<char, uint32_t, true> sa(c);
+            sa.construct(text, text + n);
+            sa.write(basename);
+        } else {
+            suffix_array<char, uint64_t, true> sa(c);
+            sa.construct(text, text + n);
+            sa.write(basename);
+        }
+        return 0;
+    } catch (const std::exception& e) {
+        std::fprintf(stderr, "psacref_write: %s\n", e.what());
+        return -10;
+    }
+}
+
+/* reads <basename>.sa / .lcp / .alpha with the reference's read(); returns n (or < 0), fills sa / lcp (cap elements of
+ * index_bytes each) and lut256[c] = alpha.encode(c) */
+long psacref_read(const char* basename, int index_bytes, void* sa_out, void* lcp_out, size_t cap, uint8_t* lut256, unsigned* sigma) {
+    try {
+        cerr_mute mute(!g_verbose);
+        mxx::comm c;
+        if (index_bytes == 4) {
+            suffix_array<char, uint32_t, true> sa(c);
+            sa.read(basename);
+            if (sa.local_SA.size() > cap) return -2;
+            std::memcpy(sa_out, sa.local_SA.data(), sa.local_SA.size() * 4);
+            std::memcpy(lcp_out, sa.local_LCP.data(), sa.local_LCP.size() * 4);
+            for (int ch = 0; ch < 256; ++ch) lut256[ch] = sa.alpha.encode((char)ch);
+            *sigma = sa.alpha.sigma();
+            return (long)sa.n;
+        } else {
+            suffix_array<char, uint64_t, true> sa(c);
+            sa.read(basename);
+            if (sa.local_SA.size() > cap) return -2;
+            std::memcpy(sa_out, sa.local_SA.data(), sa.local_SA.size() * 8);
+            std::memcpy(lcp_out, sa.local_LCP.data(), sa.local_LCP.size() * 8);
+            for (int ch = 0; ch < 256; ++ch) lut256[ch] = sa.alpha.encode((char)ch);
+            *sigma = sa.alpha.sigma();
+            return (long)sa.n;
+        }
+    } catch (const std::exception& e) {
+        std::fprintf(stderr, "psacref_read: %s\n", e.what());
+        return -10;
+    }
+}
+
 /* rand_dna(size, seed) exactly as the reference's tests generate inputs (alphabet.hpp:37-45; glibc rand) */
 int psacref_rand_dna(size_t n, int seed, char* out) {
     std::string s = rand_dna(n, seed);

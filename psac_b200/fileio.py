@@ -28,6 +28,8 @@ def write_dist_int_array(filename, local_block, rank=0, world=1, n=None):
         raise api.PsacError("write_dist_int_array: the block is not this rank's blk_dist block")
     mode = "r+b" if os.path.exists(filename) else "w+b"
     with open(filename, mode) as f:
+        if rank == 0:
+            f.truncate(total * a.dtype.itemsize)  # a stale longer file would change the n that read() infers from the size
         f.seek(start * a.dtype.itemsize)
         f.write(a.tobytes())
 
@@ -47,14 +49,19 @@ def file_block_decompose(filename, rank=0, world=1):
     return np.fromfile(filename, dtype=np.uint8, count=size, offset=start)
 
 
-def write_alphabet(filename, text_or_lut):
-    """``alphabet::write``: the used characters in increasing code order (= increasing byte order, alphabet.hpp:157-164)"""
-    a = np.asarray(text_or_lut)
-    chars = np.unique(a.astype(np.uint8)) if a.size != 256 or a.dtype != np.uint8 or a.max(initial=0) > 255 else None
-    if chars is None:  # a 256-entry code table: characters with a non-zero code, plus 0xFF if the table wrapped (sigma = 256)
-        lut = a.astype(np.uint8)
-        used = np.nonzero(lut)[0]
-        if used.size == 255 and lut[255] == 0:
+def write_alphabet(filename, text=None, lut=None):
+    """``alphabet::write``: the used characters in increasing code order (= increasing byte order, alphabet.hpp:157-164).
+    Pass EITHER the text (its distinct characters are written) OR a 256-entry code table as produced by psacb200_alphabet."""
+    if (text is None) == (lut is None):
+        raise api.PsacError("write_alphabet: pass exactly one of text= / lut=")
+    if text is not None:
+        chars = np.unique(np.asarray(text).astype(np.uint8))
+    else:
+        table = np.asarray(lut).astype(np.uint8)
+        if table.size != 256:
+            raise api.PsacError("write_alphabet: a code table has 256 entries")
+        used = np.nonzero(table)[0]
+        if used.size == 255 and table[255] == 0:  # the 8-bit table wrapped: every byte value occurs (sigma = 256)
             used = np.arange(256)
         chars = used.astype(np.uint8)
     with open(filename, "wb") as f:
@@ -78,7 +85,7 @@ def write_suffix_array(basename, sa, lcp=None, text=None, rank=0, world=1, n=Non
     if lcp is not None:
         write_dist_int_array(basename + ".lcp", lcp, rank, world, n)
     if text is not None and rank == 0:
-        write_alphabet(basename + ".alpha", text)
+        write_alphabet(basename + ".alpha", text=text)
 
 
 def read_suffix_array(basename, index_bytes=8, with_lcp=False, rank=0, world=1):

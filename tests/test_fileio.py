@@ -53,7 +53,7 @@ def test_psac_cli_files_and_text_blocks(tmp_path):
 def test_alphabet_file_of_all_256_bytes(tmp_path):
     t = G.random_bytes_config4(70000, 1)
     f = str(tmp_path / "a.alpha")
-    fileio.write_alphabet(f, t)
+    fileio.write_alphabet(f, text=t)
     assert os.path.getsize(f) == 256
     lut, sigma = fileio.read_alphabet(f)
     elut, esigma, _ = O.alphabet(t)
@@ -94,3 +94,45 @@ def test_cli_check_function_detects_errors():
     lcp = exp["lcp"].copy()
     lcp[1:] += 1
     assert "LCP" in cli._check(t, exp["sa"], exp["isa"], lcp)
+
+
+# ------------------------------------------------------------------------------------------- against the reference's own write / read
+@pytest.mark.skipif(not O.have_ref(), reason="oracle/_ref/libpsacref.so not built")
+@pytest.mark.parametrize("ib", [4, 8])
+def test_files_written_by_the_unmodified_reference_are_read_here_and_vice_versa(tmp_path, ib):
+    """suffix_array::write / read of the UNMODIFIED reference (oracle/_ref; include/suffix_array.hpp:232-265 over the MPI shim's
+    stdio-backed MPI_File) against psac_b200/fileio.py: byte-identical files, and each side reads what the other wrote."""
+    dt = np.uint32 if ib == 4 else np.uint64
+    for t in (G.random_dna(4099, 5), G.repeats_text(300, 2), np.frombuffer(b"mississippi", np.uint8), ("ACGT" * 64).encode()):
+        t = np.frombuffer(bytes(t), np.uint8) if isinstance(t, bytes) else t
+        exp = O.construct(t, 64, 0, True)
+        ref_base, own_base = str(tmp_path / "ref"), str(tmp_path / "own")
+        O.ref_write(t, ib, ref_base)
+        fileio.write_suffix_array(own_base, exp["sa"].astype(dt), exp["lcp"].astype(dt), text=t)
+        for ext in (".sa", ".lcp", ".alpha"):
+            assert open(ref_base + ext, "rb").read() == open(own_base + ext, "rb").read(), ext
+        r = fileio.read_suffix_array(ref_base, ib, with_lcp=True)  # reference wrote, we read
+        assert r["n"] == t.size and (r["sa"] == exp["sa"]).all() and (r["lcp"] == exp["lcp"]).all()
+        assert (r["lut"] == O.alphabet(t)[0]).all()
+        rr = O.ref_read(own_base, ib, t.size + 8)  # we wrote, the reference reads
+        assert rr["n"] == t.size and (rr["sa"] == exp["sa"]).all() and (rr["lcp"] == exp["lcp"]).all()
+        assert (rr["lut"] == O.alphabet(t)[0]).all() and rr["sigma"] == O.alphabet(t)[1]
+
+
+def test_text_of_exactly_256_characters_writes_its_alphabet_not_a_table(tmp_path):
+    f = str(tmp_path / "a.alpha")
+    fileio.write_alphabet(f, text=np.frombuffer(b"ACGT" * 64, np.uint8))
+    assert open(f, "rb").read() == b"ACGT"
+    lut = np.zeros(256, np.uint8)
+    lut[[65, 67, 71, 84]] = [1, 2, 3, 4]
+    fileio.write_alphabet(f, lut=lut)
+    assert open(f, "rb").read() == b"ACGT"
+    with pytest.raises(api.PsacError):
+        fileio.write_alphabet(f, np.zeros(3, np.uint8), np.zeros(256, np.uint8))
+
+
+def test_rewriting_a_shorter_array_truncates_the_file(tmp_path):
+    f = str(tmp_path / "x.sa")
+    fileio.write_dist_int_array(f, np.arange(100, dtype=np.uint64))
+    fileio.write_dist_int_array(f, np.arange(10, dtype=np.uint64))
+    assert os.path.getsize(f) == 80 and fileio.read_dist_int_array(f, np.uint64)[1] == 10
