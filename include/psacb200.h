@@ -150,6 +150,15 @@ int psacb200_check(psacb200_engine* e, const uint8_t* text, size_t n, int index_
 int psacb200_check_sharded(psacb200_engine* e, const uint8_t* d_text_local, size_t n_local, size_t n_global, int index_bytes, const void* d_sa_local,
                            const void* d_isa_local, const void* d_lcp_local, psacb200_check_report* report);
 
+/* ---- left-branching characters (reference template parameter _CONSTRUCT_LC: local_Lc, include/suffix_array.hpp:212, 1365-1383,
+ * 1485-1495; consumed by the DESA index, include/desa.hpp:296-312) ------------------------------------------------------ */
+/* lc[i] = text[SA[i-1] + LCP[i]], '\0' where that position is past the end of the text, and for i = 0.  A by-product of SA + LCP:
+ * one gather per position.  DEVICE arrays / HOST arrays / collective over the ranks (blocks of SA and LCP in, block of Lc out). */
+int psacb200_lc_device(psacb200_engine* e, const uint8_t* d_text, size_t n, int index_bytes, const void* d_sa, const void* d_lcp, uint8_t* d_lc);
+int psacb200_lc(psacb200_engine* e, const uint8_t* text, size_t n, int index_bytes, const void* sa, const void* lcp, uint8_t* lc);
+int psacb200_lc_sharded(psacb200_engine* e, const uint8_t* d_text_local, size_t n_local, size_t n_global, int index_bytes, const void* d_sa_local,
+                        const void* d_lcp_local, uint8_t* d_lc_local);
+
 /* Host-side plans of the sharded construction (no GPU needed; used by the CPU tests): mxx::blk_dist, and the splitters
  * over a key-prefix histogram (rank r sorts the bins [first[r], first[r+1]); first has p+1 entries, count p). */
 void psacb200_blk_dist(uint64_t n, int p, int r, uint64_t* start, uint64_t* size);

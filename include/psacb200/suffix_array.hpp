@@ -56,8 +56,9 @@ struct alphabet {
     uint8_t encode(unsigned char c) const { return mapping_table[c]; }  // alphabet.hpp:266-269
 };
 
-template <typename char_t, typename index_t = std::size_t, bool _CONSTRUCT_LCP = false>
+template <typename char_t, typename index_t = std::size_t, bool _CONSTRUCT_LCP = false, bool _CONSTRUCT_LC = false>
 class suffix_array {
+    static_assert(!_CONSTRUCT_LC || _CONSTRUCT_LCP, "the left-branching characters need the LCP array (reference suffix_array.hpp:1365-1383)");
     static_assert(sizeof(char_t) == 1, "psacb200 handles 1-byte characters (the reference's alphabet<char> path)");
     static_assert(sizeof(index_t) == 4 || sizeof(index_t) == 8, "index_t must be a 32- or 64-bit unsigned integer");
     static_assert(std::is_unsigned<index_t>::value, "index_t must be unsigned");
@@ -83,6 +84,7 @@ public:
     std::vector<index_t> local_SA;
     std::vector<index_t> local_B;  // inverse suffix array, 0-based (reference: local_B after :460-464)
     std::vector<index_t> local_LCP;
+    std::vector<char_t> local_Lc;  // left-branching characters (reference :212; filled iff _CONSTRUCT_LC)
 
     // reference :217-228 -- at p = 1 every size is a valid block decomposition
     void init_size(std::size_t lsize) {
@@ -216,6 +218,11 @@ private:
             check(psacb200_multi_construct(multi_, text, n, (int)sizeof(index_t), flags, k, local_SA.data(), local_B.data(), lcp));
         else
             check(psacb200_construct(engine_, text, n, (int)sizeof(index_t), flags, k, local_SA.data(), local_B.data(), lcp));
+        local_Lc.clear();
+        if (_CONSTRUCT_LC && want_lcp && n > 0) {
+            local_Lc.resize(n);
+            check(psacb200_lc(engine_, text, n, (int)sizeof(index_t), local_SA.data(), local_LCP.data(), reinterpret_cast<uint8_t*>(local_Lc.data())));
+        }
     }
 };
 

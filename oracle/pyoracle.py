@@ -325,6 +325,29 @@ def ref_read(basename, index_bytes, cap):
     return dict(n=int(n), sa=sa[:n], lcp=lcp[:n], lut=lut, sigma=sigma.value)
 
 
+def lc_from_sa_lcp(text, sa, lcp):
+    """left-branching characters restated: Lc[i] = text[SA[i-1] + LCP[i]], 0 past the end and for i = 0
+    (reference include/desa.hpp:296-312 recomputes local_Lc exactly like this; suffix_array.hpp:1365-1383 by k-mer decoding)"""
+    t = _text(text)
+    n = t.size
+    out = np.zeros(n, np.uint8)
+    if n > 1:
+        g = np.asarray(sa[:-1]).astype(np.int64) + np.asarray(lcp[1:]).astype(np.int64)
+        ok = g < n
+        out[1:][ok] = t[g[ok]]
+    return out
+
+
+def ref_lc(text, k=0):
+    """local_Lc of the UNMODIFIED reference built with _CONSTRUCT_LC (oracle/_ref)"""
+    t = _text(text)
+    out = np.zeros(t.size, np.uint8)
+    rc = ref().psacref_lc(_vp(t), C.c_size_t(t.size), C.c_uint(k), _vp(out))
+    if rc != 0:
+        raise RuntimeError("psacref_lc rc=%d" % rc)
+    return out
+
+
 def ref_rand_dna(n, seed):
     out = np.zeros(n, np.uint8)
     ref().psacref_rand_dna(C.c_size_t(n), C.c_int(seed), _vp(out))

@@ -237,6 +237,22 @@ long psacref_read(const char* basename, int index_bytes, void* sa_out, void* lcp
     }
 }
 
+/* suffix_array<char, uint64_t, true, true>::local_Lc: the left-branching characters (suffix_array.hpp:212, 1365-1383, 1485-1495) */
+int psacref_lc(const char* text, size_t n, unsigned k, char* lc_out) {
+    try {
+        cerr_mute mute(!g_verbose);
+        mxx::comm c;
+        suffix_array<char, uint64_t, true, true> sa(c);
+        sa.construct(text, text + n, true, k);
+        if (sa.local_Lc.size() != n) return -3;
+        std::memcpy(lc_out, sa.local_Lc.data(), n);
+        return 0;
+    } catch (const std::exception& e) {
+        std::fprintf(stderr, "psacref_lc: %s\n", e.what());
+        return -10;
+    }
+}
+
 /* rand_dna(size, seed) exactly as the reference's tests generate inputs (alphabet.hpp:37-45; glibc rand) */
 int psacref_rand_dna(size_t n, int seed, char* out) {
     std::string s = rand_dna(n, seed);

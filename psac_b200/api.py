@@ -119,6 +119,9 @@ def lib():
         L.psacb200_suffix_tree_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_uint32)]
         L.psacb200_suffix_tree_sharded.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
                                                    C.POINTER(C.c_uint32)]
+        L.psacb200_lc.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.psacb200_lc_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.psacb200_lc_sharded.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.psacb200_multi_create.argtypes = [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]
         L.psacb200_multi_destroy.argtypes = [C.c_void_p]
         L.psacb200_multi_destroy.restype = None
@@ -292,6 +295,18 @@ class Engine:
         _check(lib().psacb200_suffix_tree(self._h, _ptr(t), t.size, sa.dtype.itemsize, _ptr(sa), _ptr(lcp), _ptr(nodes), nodes.size))
         return nodes
 
+    def lc(self, text, sa, lcp):
+        """left-branching characters local_Lc (reference _CONSTRUCT_LC, suffix_array.hpp:212): Lc[i] = text[SA[i-1] + LCP[i]]"""
+        t = _as_text(text)
+        sa = np.ascontiguousarray(sa)
+        lcp = np.ascontiguousarray(lcp, sa.dtype)
+        out = np.zeros(t.size, np.uint8)
+        _check(lib().psacb200_lc(self._h, _ptr(t), t.size, sa.dtype.itemsize, _ptr(sa), _ptr(lcp), _ptr(out)))
+        return out
+
+    def lc_sharded_ptr(self, text_ptr, n_local, n_global, index_bytes, sa_ptr, lcp_ptr, lc_ptr):
+        _check(lib().psacb200_lc_sharded(self._h, _ptr(text_ptr), n_local, n_global, index_bytes, _ptr(sa_ptr), _ptr(lcp_ptr), _ptr(lc_ptr)))
+
     # ---- the same on device pointers (one GPU, or collective over the ranks of comm_init)
     def ansv_device_ptr(self, vals_ptr, n, val_bytes, left_type, right_type, nonsv, left_ptr, right_ptr):
         _check(lib().psacb200_ansv_device(self._h, _ptr(vals_ptr), n, val_bytes, left_type, right_type, nonsv, _ptr(left_ptr), _ptr(right_ptr)))
@@ -378,9 +393,11 @@ def default_engine():
 class SuffixArray:
     """Python mirror of ``suffix_array<char, index_t, _CONSTRUCT_LCP>`` at p = 1 (reference suffix_array.hpp:170-213)."""
 
-    def __init__(self, index_bytes=8, construct_lcp=False, engine=None):
+    def __init__(self, index_bytes=8, construct_lcp=False, engine=None, construct_lc=False):
         self.index_bytes = index_bytes
-        self.construct_lcp = construct_lcp
+        self.construct_lcp = construct_lcp or construct_lc
+        self.construct_lc = construct_lc  # reference template parameter _CONSTRUCT_LC: also fill local_Lc
+        self.local_Lc = None
         self.engine = engine
         self.n = 0
         self.local_size = 0
@@ -401,6 +418,8 @@ class SuffixArray:
         self._text = t
         self.n = self.local_size = t.size
         self.local_SA, self.local_B, self.local_LCP = r["sa"], r["isa"], r["lcp"]
+        if self.construct_lc:
+            self.local_Lc = self._eng().lc(t, self.local_SA, self.local_LCP)
         return self
 
     def write(self, basename, text=None):

@@ -95,4 +95,25 @@ __global__ void __launch_bounds__(256) check_sa_kernel(CheckArgs A) {
     if (first_bad != ~0ull) atomicMin(&A.bad[4], (unsigned long long)first_bad);
 }
 
+// ------------------------------------------------------------------ left-branching characters (the Lc by-product)
+// Reference: suffix_array<..., _CONSTRUCT_LC = true>::local_Lc (include/suffix_array.hpp:212, 1365-1383, 1485-1495;
+// bulk_rmq_Lc, include/par_rmq.hpp:334-481), the array the DESA index consumes (include/desa.hpp:296-312, which recomputes it
+// the same way): Lc[i] = S[SA[i-1] + LCP[i]] -- the character of the LEFT neighbour at the first mismatch -- and '\0' where
+// that position lies past the end of the text or i = 0.  A pure function of (text, SA, LCP): one gather per position.
+template <typename IdxT>
+__global__ void __launch_bounds__(256) lc_kernel(const u64* __restrict__ stream, int lbits, const u8* __restrict__ inv, u64 n, const IdxT* __restrict__ sa,
+                                                 const IdxT* __restrict__ lcp, u64 pos0, u64 m, u64 halo_sa, u8* __restrict__ out) {
+    __shared__ u8 s_inv[256];
+    s_inv[threadIdx.x] = inv[threadIdx.x];
+    __syncthreads();
+    for (u64 q = (u64)blockIdx.x * blockDim.x + threadIdx.x; q < m; q += (u64)gridDim.x * blockDim.x) {
+        u8 c = 0;
+        if (pos0 + q > 0) {
+            const u64 g = (q ? (u64)sa[q - 1] : halo_sa) + (u64)lcp[q];
+            if (g < n) c = s_inv[(u32)stream_extract(stream, g, lbits, lbits)];
+        }
+        out[q] = c;
+    }
+}
+
 }  // namespace psacb200

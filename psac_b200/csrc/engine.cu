@@ -659,6 +659,27 @@ void check_device_core(psacb200_engine* e, const u8* d_text, u64 n, int index_by
     cudaEventElapsedTime(&rep->ms, e0, e1);
 }
 
+// inverse of the dense code table on the device (256 bytes at the end of `small`'s byte-histogram area is too tight: own slot)
+u8* upload_inverse_codes(psacb200_engine* e, const Alphabet& alpha, const u64* hist) {
+    u8* h = reinterpret_cast<u8*>(e->h_pinned + 7168);  // 256 bytes of the pinned staging area
+    memset(h, 0, 256);
+    for (int c = 255; c >= 0; --c)
+        if (hist[c]) h[alpha.dense.code[c]] = (u8)c;
+    e->tb[1].reserve(4096, &e->device_bytes);
+    u8* d = e->tb[1].as<u8>() + 3072;
+    PSAC_CUDA(cudaMemcpyAsync(d, h, 256, cudaMemcpyHostToDevice, e->stream));
+    return d;
+}
+
+template <typename IdxT>
+void lc_launch(psacb200_engine* e, const Alphabet& alpha, const u8* d_inv, u64 n, const void* d_sa, const void* d_lcp, u64 pos0, u64 m, u64 halo_sa, u8* d_lc) {
+    if (m == 0) return;
+    lc_kernel<IdxT><<<grid_for(e, m, 256, 16), 256, 0, e->stream>>>(e->packed.as<u64>(), alpha.lbits, d_inv, n, reinterpret_cast<const IdxT*>(d_sa),
+                                                                    reinterpret_cast<const IdxT*>(d_lcp), pos0, m, halo_sa, d_lc);
+    e->launches += 1;
+    PSAC_CUDA(cudaGetLastError());
+}
+
 void fill_phase_stats(psacb200_engine* e) {
     psacb200_stats& S = e->stats;
     S.device_bytes = e->device_bytes;
@@ -1271,6 +1292,98 @@ int psacb200_check_sharded(psacb200_engine* e, const uint8_t* d_text_local, size
             return PSACB200_OK;
         }
         check_sharded_core(e, C, d_text_local, n_local, n_global, index_bytes, d_sa_local, d_isa_local, d_lcp_local, report);
+        return PSACB200_OK;
+    });
+}
+
+// ---- left-branching characters Lc (check_kernels.cuh lc_kernel)
+int psacb200_lc_device(psacb200_engine* e, const uint8_t* d_text, size_t n, int index_bytes, const void* d_sa, const void* d_lcp, uint8_t* d_lc) {
+    if (!e) {
+        set_last_error("null engine");
+        return PSACB200_ERR_ARG;
+    }
+    if (n == 0) return PSACB200_OK;
+    return guarded([&]() -> int {
+        if (!d_text || !d_sa || !d_lcp || !d_lc) throw arg_failure{"null argument"};
+        if (index_bytes != 4 && index_bytes != 8) throw arg_failure{"index_bytes must be 4 or 8"};
+        PSAC_CUDA(cudaSetDevice(e->device));
+        Alphabet alpha;
+        prepare_text(e, d_text, n, nullptr, alpha);
+        const u8* d_inv = upload_inverse_codes(e, alpha, e->h_pinned + 16);
+        if (index_bytes == 4)
+            lc_launch<u32>(e, alpha, d_inv, n, d_sa, d_lcp, 0, n, 0, d_lc);
+        else
+            lc_launch<u64>(e, alpha, d_inv, n, d_sa, d_lcp, 0, n, 0, d_lc);
+        PSAC_CUDA(cudaStreamSynchronize(e->stream));
+        return PSACB200_OK;
+    });
+}
+
+int psacb200_lc(psacb200_engine* e, const uint8_t* text, size_t n, int index_bytes, const void* sa, const void* lcp, uint8_t* lc) {
+    if (!e) {
+        set_last_error("null engine");
+        return PSACB200_ERR_ARG;
+    }
+    if (n == 0) return PSACB200_OK;
+    return guarded([&]() -> int {
+        if (!text || !sa || !lcp || !lc) throw arg_failure{"null argument"};
+        if (index_bytes != 4 && index_bytes != 8) throw arg_failure{"index_bytes must be 4 or 8"};
+        PSAC_CUDA(cudaSetDevice(e->device));
+        size_t* tot = &e->device_bytes;
+        const size_t bytes = n * (size_t)index_bytes;
+        e->text.reserve(n + 64, tot);
+        e->rep[0].reserve(bytes + 64, tot);
+        e->rep[1].reserve(bytes + 64, tot);
+        e->rep[2].reserve(n + 64, tot);
+        PSAC_CUDA(cudaMemcpyAsync(e->text.p, text, n, cudaMemcpyHostToDevice, e->stream));
+        PSAC_CUDA(cudaMemcpyAsync(e->rep[0].p, sa, bytes, cudaMemcpyHostToDevice, e->stream));
+        PSAC_CUDA(cudaMemcpyAsync(e->rep[1].p, lcp, bytes, cudaMemcpyHostToDevice, e->stream));
+        const int rc = psacb200_lc_device(e, e->text.as<u8>(), n, index_bytes, e->rep[0].p, e->rep[1].p, e->rep[2].as<u8>());
+        if (rc != PSACB200_OK) return rc;
+        PSAC_CUDA(cudaMemcpyAsync(lc, e->rep[2].p, n, cudaMemcpyDeviceToHost, e->stream));
+        PSAC_CUDA(cudaStreamSynchronize(e->stream));
+        return PSACB200_OK;
+    });
+}
+
+int psacb200_lc_sharded(psacb200_engine* e, const uint8_t* d_text_local, size_t n_local, size_t n_global, int index_bytes, const void* d_sa_local,
+                        const void* d_lcp_local, uint8_t* d_lc_local) {
+    if (!e) {
+        set_last_error("null engine");
+        return PSACB200_ERR_ARG;
+    }
+    return guarded([&]() -> int {
+        if (!e->nccl_comm) throw arg_failure{"psacb200_comm_init has not been called on this engine"};
+        if (n_local && (!d_text_local || !d_sa_local || !d_lcp_local || !d_lc_local)) throw arg_failure{"null argument"};
+        if (index_bytes != 4 && index_bytes != 8) throw arg_failure{"index_bytes must be 4 or 8"};
+        PSAC_CUDA(cudaSetDevice(e->device));
+        if (n_global == 0) return PSACB200_OK;
+        ShardComm C{reinterpret_cast<ncclComm_t>(e->nccl_comm), e->shard_rank, e->shard_world};
+        const BlkDist blk(n_global, C.world);
+        if (blk.size(C.rank) != n_local) throw arg_failure{"the arrays must be equally block decomposed across all ranks (reference suffix_array.hpp:226)"};
+        Alphabet alpha;
+        prepare_text_sharded(e, C, d_text_local, n_local, n_global, alpha);
+        const u8* d_inv = upload_inverse_codes(e, alpha, e->h_pinned + 16);
+        // SA[pos0 - 1]: the last SA element of the previous non-empty rank
+        u64* d_last = e->shard_meta();
+        PSAC_CUDA(cudaMemsetAsync(d_last + C.rank, 0, sizeof(u64), e->stream));
+        if (n_local)
+            PSAC_CUDA(cudaMemcpyAsync(d_last + C.rank, reinterpret_cast<const u8*>(d_sa_local) + (n_local - 1) * (size_t)index_bytes, (size_t)index_bytes,
+                                      cudaMemcpyDeviceToDevice, e->stream));
+        PSAC_NCCL(g_nccl.AllGather(d_last + C.rank, d_last, 1, ncclUint64, C.comm, e->stream));
+        PSAC_CUDA(cudaMemcpyAsync(e->h_pinned + 64, d_last, (size_t)C.world * sizeof(u64), cudaMemcpyDeviceToHost, e->stream));
+        PSAC_CUDA(cudaStreamSynchronize(e->stream));
+        u64 halo = 0;
+        for (int r = C.rank - 1; r >= 0; --r)
+            if (blk.size(r)) {
+                halo = e->h_pinned[64 + r];
+                break;
+            }
+        if (index_bytes == 4)
+            lc_launch<u32>(e, alpha, d_inv, n_global, d_sa_local, d_lcp_local, blk.start(C.rank), n_local, halo, d_lc_local);
+        else
+            lc_launch<u64>(e, alpha, d_inv, n_global, d_sa_local, d_lcp_local, blk.start(C.rank), n_local, halo, d_lc_local);
+        PSAC_CUDA(cudaStreamSynchronize(e->stream));
         return PSACB200_OK;
     });
 }

@@ -107,6 +107,15 @@ class ShardedSuffixArray:
                                      left.data_ptr() if m else None, right.data_ptr() if m else None)
         return left, right
 
+    def left_branching_chars(self):
+        """Collective; the reference's local_Lc (_CONSTRUCT_LC, include/suffix_array.hpp:212): this rank's block, a uint8 CUDA tensor."""
+        m = self.local_size
+        lc = torch.empty(m, dtype=torch.uint8, device=self.device)
+        torch.cuda.current_stream(self.device).synchronize()
+        self.engine.lc_sharded_ptr(self._text.data_ptr() if m else None, m, self.n, self.index_bytes, self.local_SA.data_ptr() if m else None,
+                                   self.local_LCP.data_ptr() if m else None, lc.data_ptr() if m else None)
+        return lc
+
     def close(self):
         """Collective: ordered release of the peer-visible memory, then the engine."""
         if self.engine is not None:

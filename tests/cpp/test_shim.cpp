@@ -53,6 +53,15 @@ int main() {
             const int cmp = std::memcmp(t.data() + a, t.data() + b, m);
             if (cmp > 0 || (cmp == 0 && la > lb)) return fail("SA not sorted");
         }
+        // left-branching characters (_CONSTRUCT_LC, suffix_array.hpp:212): Lc[i] = S[SA[i-1] + LCP[i]], '\0' past the end
+        psacb200::suffix_array<char, uint64_t, true, true> sl(c);
+        sl.construct(s.begin(), s.end());
+        if (sl.local_Lc.size() != 11) return fail("Lc size");
+        for (size_t i = 0; i < 11; ++i) {
+            const size_t g = i ? sl.local_SA[i - 1] + sl.local_LCP[i] : 11;
+            const char want = g < 11 ? s[g] : '\0';
+            if (sl.local_Lc[i] != want) return fail("Lc");
+        }
         // user-supplied alphabet overload (suffix_array.hpp:365-366)
         psacb200::suffix_array<char, uint64_t, true> sc(c);
         sc.construct(s.begin(), s.end(), true, sa.alpha, 2);

@@ -62,6 +62,11 @@ def case(name, text, index_bytes, lcp, k=0, scheme=None, tree=False):
         nodes = sa.construct_suffix_tree()
         width = nodes.shape[1]
         got_nodes = gather_blocks(nodes.reshape(-1), n * width, p, rank, dev, sizes=[api.blk_dist(n, p, r)[1] * width for r in range(p)]).view(np.uint64)
+        lc_ = sa.left_branching_chars()
+        got_lc = gather_blocks(lc_, n, p, rank, dev)
+        if rank == 0 and not (got_lc == O.lc_from_sa_lcp(text, exp["sa"], exp["lcp"])).all():
+            print("   left-branching characters differ", flush=True)
+            ok = False
         l_, r_ = sa.ansv(2, 0, 2 ** 63 - 1)
         got_l = gather_blocks(l_, n, p, rank, dev).view(np.uint64)
         got_r = gather_blocks(r_, n, p, rank, dev).view(np.uint64)

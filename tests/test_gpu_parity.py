@@ -237,3 +237,15 @@ def test_all_256_byte_values_without_lcp_take_the_lean_path(eng):
     eng.construct_ptr(d_t.data_ptr(), t.size, 8, 0, 0, d_sa.data_ptr(), d_isa.data_ptr(), None, device=True)
     assert (d_sa.cpu().numpy().view(np.uint64) == exp["sa"]).all() and (d_isa.cpu().numpy().view(np.uint64) == exp["isa"]).all()
     assert eng.check_device_ptr(d_t.data_ptr(), t.size, 8, d_sa.data_ptr(), d_isa.data_ptr(), None)["ok"]
+
+
+# ------------------------------------------------------------------------------------------- left-branching characters (Lc)
+def test_left_branching_chars_match_oracle_and_reference(eng):
+    for t in (G.random_dna(100003, 3), G.repeats_text(3000, 2), np.frombuffer(b"mississippi", np.uint8), G.periodic_text(b"abc", 500),
+              (G.random_bytes(50000, 8) % 20 + 65).astype(np.uint8), np.frombuffer(b"a", np.uint8)):
+        for ib in (4, 8):
+            sa = api.SuffixArray(ib, construct_lc=True, engine=eng).construct(t)
+            want = O.lc_from_sa_lcp(t, sa.local_SA, sa.local_LCP)
+            assert (sa.local_Lc == want).all()
+            if O.have_ref() and t.size > 2:
+                assert (sa.local_Lc == O.ref_lc(t)).all()

@@ -255,3 +255,13 @@ def test_port_and_reference_agree_with_libdivsufsort():
     remapped = (t.astype(np.uint16) + 1).astype(np.uint8)  # 0xFF + 1 wraps to 0
     assert (O.construct(t, 64, 0, False)["sa"] == O.dss_sa(remapped)).all()
     assert not (O.construct(t, 64, 0, False)["sa"] == O.dss_sa(t)).all()
+
+
+@pytest.mark.skipif(not O.have_ref(), reason="oracle/_ref/libpsacref.so not built")
+def test_left_branching_chars_restatement_matches_reference_lc():
+    """local_Lc of suffix_array<char, uint64_t, true, true> (unmodified reference; k-mer decoding at :1365-1383 and bulk_rmq_Lc at
+    :1485-1495) equals the restatement Lc[i] = S[SA[i-1] + LCP[i]] (which is also how include/desa.hpp:296-312 recomputes it)."""
+    for t, k in [(G.random_dna(5003, 3), 0), (G.random_dna(3001, 4), 3), (G.repeats_text(300, 2), 0), (np.frombuffer(b"mississippi", np.uint8), 0),
+                 (G.periodic_text(b"abc", 97), 0), ((G.random_bytes(4000, 8) % 20 + 65).astype(np.uint8), 2)]:
+        e = O.construct(t, 64, k, True)
+        assert (O.lc_from_sa_lcp(t, e["sa"], e["lcp"]) == O.ref_lc(t, k)).all()
