@@ -848,7 +848,7 @@ void ansv_device(psacb200_engine* e, const T* d_vals, u64 n, int left_type, int 
         t.levels += 1;
     }
     LocalSearch<T> sr{t};
-    ansv_kernel<T, LocalSearch<T>><<<grid_for(e, n, 256, 8), 256, 0, e->stream>>>(sr, 0, n, left_type, right_type, nonsv, d_left, d_right);
+    launch_ansv_tile<T, LocalSearch<T>>(sr, d_vals, 0, n, left_type, right_type, nonsv, d_left, d_right, e->stream);
     e->launches += 1;
     PSAC_CUDA(cudaGetLastError());
 }

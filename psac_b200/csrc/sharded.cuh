@@ -2113,9 +2113,8 @@ void ansv_sharded_core(psacb200_engine* e, const ShardComm& C, const T* d_vals_l
     TreeLayout L;
     DistSearch<T> sr = dist_search_setup<T>(e, C, d_vals_local, n_local, n, L);
     if (n_local) {
-        ansv_kernel<T, DistSearch<T>><<<grid_for(e, n_local, 256, 8), 256, 0, e->stream>>>(sr, blk.start(C.rank), n_local, left_type, right_type, nonsv, d_left, d_right);
+        launch_ansv_tile<T, DistSearch<T>>(sr, d_vals_local, blk.start(C.rank), n_local, left_type, right_type, nonsv, d_left, d_right, e->stream);
         e->launches += 1;
-        PSAC_CUDA(cudaGetLastError());
     }
     rank_barrier(e, C);  // my arena may be reused only after every rank is done searching it
     PSAC_CUDA(cudaStreamSynchronize(e->stream));
@@ -2168,9 +2167,8 @@ void suffix_tree_core(psacb200_engine* e, const ShardComm* C, const u8* d_text_l
         mintree_build<IdxT>(e, sr.t);
         e->mark("mintree");
         A.q.cap = 0;
-        suffix_tree_fused_kernel<IdxT, LocalSearch<IdxT>><<<grid_for(e, n, 256, 8), 256, 0, st>>>(A, sr);
+        launch_tree_tile<IdxT, LocalSearch<IdxT>>(A, sr, st);
         e->launches += 1;
-        PSAC_CUDA(cudaGetLastError());
         e->mark("tree");
         PSAC_CUDA(cudaStreamSynchronize(st));
         return;
@@ -2182,9 +2180,8 @@ void suffix_tree_core(psacb200_engine* e, const ShardComm* C, const u8* d_text_l
     A.q.cap = L.qcap;
     for (int r = 0; r < 16; ++r) A.q.queue[r] = r < p ? reinterpret_cast<u64*>(AR.peer[r] + L.o_queue) + (size_t)me * L.qcap * 3 : nullptr;
     if (n_local) {
-        suffix_tree_fused_kernel<IdxT, DistSearch<IdxT>><<<grid_for(e, n_local, 256, 8), 256, 0, st>>>(A, sr);
+        launch_tree_tile<IdxT, DistSearch<IdxT>>(A, sr, st);
         e->launches += 1;
-        PSAC_CUDA(cudaGetLastError());
     }
     e->mark("tree");
     // edges queued for rows of other ranks: exchange the counts, apply mine

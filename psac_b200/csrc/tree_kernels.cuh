@@ -358,56 +358,243 @@ __device__ __forceinline__ void tree_emit_dist(const TreeFusedArgs<IdxT>& A, u64
     }
 }
 
+// one position: leaf edge and internal-node edge, every search through the searcher (exact, any distance)
 template <typename IdxT, class S>
-__global__ void __launch_bounds__(256) suffix_tree_fused_kernel(TreeFusedArgs<IdxT> A, S sr) {
+__device__ void tree_element_slow(const TreeFusedArgs<IdxT>& A, const S& sr, u64 i) {
     const u64 n = A.n;
-    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < A.m; i += (u64)gridDim.x * blockDim.x) {
-        const u64 gi = A.g0 + i;
-        const u64 lcp_i = A.lcp[i];
-        const u64 sa_i = A.sa[i];
-        // ---- leaf n + gi (suffix_tree.hpp:88-141)
-        u64 parent, lcp_val;
-        u64 lnsv = ANSV_NONE, left_val = 0;
-        const bool need_left = gi > 0;
-        if (need_left) {
-            lnsv = ansv_one<IdxT, -1>(sr, gi, 2);
-            left_val = sr.value(lnsv);
-        }
-        if (gi == 0) {
-            lcp_val = n > 1 ? (u64)sr.value(1) : 0;
-            parent = lcp_val > 0 ? 1 : 0;
-        } else {
-            const u64 next = gi + 1 < n ? (i + 1 < A.m ? (u64)A.lcp[i + 1] : (u64)sr.value(gi + 1)) : 0;
-            if (gi == n - 1 || lcp_i >= next) {
-                if (left_val == lcp_i) {
-                    parent = lnsv;
-                    lcp_val = left_val;
-                } else {
-                    parent = gi;
-                    lcp_val = lcp_i;
-                }
+    const u64 gi = A.g0 + i;
+    const u64 lcp_i = A.lcp[i];
+    const u64 sa_i = A.sa[i];
+    // ---- leaf n + gi (suffix_tree.hpp:88-141)
+    u64 parent, lcp_val;
+    u64 lnsv = ANSV_NONE, left_val = 0;
+    if (gi > 0) {
+        lnsv = ansv_one<IdxT, -1>(sr, gi, 2);
+        left_val = sr.value(lnsv);
+    }
+    if (gi == 0) {
+        lcp_val = n > 1 ? (u64)sr.value(1) : 0;
+        parent = lcp_val > 0 ? 1 : 0;
+    } else {
+        const u64 next = gi + 1 < n ? (i + 1 < A.m ? (u64)A.lcp[i + 1] : (u64)sr.value(gi + 1)) : 0;
+        if (gi == n - 1 || lcp_i >= next) {
+            if (left_val == lcp_i) {
+                parent = lnsv;
+                lcp_val = left_val;
             } else {
-                parent = gi + 1;
-                lcp_val = next;
+                parent = gi;
+                lcp_val = lcp_i;
             }
+        } else {
+            parent = gi + 1;
+            lcp_val = next;
         }
-        tree_emit_dist<IdxT>(A, parent, n + gi, sa_i, lcp_val);
-        // ---- internal node gi (suffix_tree.hpp:146-222): the root (0) and its duplicates (LCP = 0) have no parent
-        if (gi == 0 || lcp_i == 0) continue;
-        const u64 rnsv = ansv_one<IdxT, +1>(sr, gi, 0);
-        if (rnsv == ANSV_NONE) {
-            if (left_val == lcp_i) continue;  // duplicate of the node further left
+    }
+    tree_emit_dist<IdxT>(A, parent, n + gi, sa_i, lcp_val);
+    // ---- internal node gi (suffix_tree.hpp:146-222): the root (0) and its duplicates (LCP = 0) have no parent
+    if (gi == 0 || lcp_i == 0) return;
+    const u64 rnsv = ansv_one<IdxT, +1>(sr, gi, 0);
+    if (rnsv == ANSV_NONE) {
+        if (left_val == lcp_i) return;  // duplicate of the node further left
+        tree_emit_dist<IdxT>(A, lnsv, gi, sa_i, left_val);
+    } else {
+        const u64 right_val = sr.value(rnsv);
+        if (left_val >= right_val) {
+            if (left_val == lcp_i) return;
             tree_emit_dist<IdxT>(A, lnsv, gi, sa_i, left_val);
         } else {
-            const u64 right_val = sr.value(rnsv);
-            if (left_val >= right_val) {
-                if (left_val == lcp_i) continue;
-                tree_emit_dist<IdxT>(A, lnsv, gi, sa_i, left_val);
-            } else {
-                tree_emit_dist<IdxT>(A, rnsv, gi, sa_i, right_val);
+            tree_emit_dist<IdxT>(A, rnsv, gi, sa_i, right_val);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ tile kernels: sparse table in shared memory
+// A min-tree search costs one dependent probe per step and a warp waits for its slowest lane: on the LCP array of random DNA
+// a third of the positions need 20+ probes and a few per warp need hundreds (measured: 94 ms for the ANSV of 2^29 values,
+// 105 ms for the tree, profiles/r2_tree_notes.md).  The tile kernels take TILE consecutive values into shared memory, build
+// the sparse table M[k][j] = min(v[j .. j + 2^k)) there, and answer every nearest-smaller search INSIDE the tile by
+// binary lifting: log2(TILE) branch-free steps, the same for every lane.  Only positions whose match lies outside the tile
+// (a few per cent) are put on a list and finished by the exact min-tree search (ansv_one / tree_element_slow) with all
+// lanes busy.  The three match modes are the same compositions of directional searches as in ansv_one.
+template <typename T>
+struct AnsvTile {
+    static constexpr int TILE = sizeof(T) == 4 ? 2048 : 1024;
+    static constexpr int K = sizeof(T) == 4 ? 11 : 10;  // log2(TILE)
+    static constexpr size_t SMEM = (size_t)K * TILE * sizeof(T);
+    static constexpr int NOT_IN_TILE = -1;
+    const T* M;  // [K][TILE] in shared memory
+    __device__ __forceinline__ T at(int k, int j) const { return M[k * TILE + j]; }
+    // nearest j < i (DIR < 0) / j > i (DIR > 0) inside the tile with v[j] < x (STRICT) or v[j] <= x; NOT_IN_TILE if none
+    template <int DIR, bool STRICT>
+    __device__ __forceinline__ int search(int i, T x) const {
+        if (DIR < 0) {
+            int pos = i;
+#pragma unroll
+            for (int k = K - 1; k >= 0; --k) {
+                const int len = 1 << k;
+                if (pos >= len) {
+                    const T m = at(k, pos - len);
+                    if (STRICT ? (m >= x) : (m > x)) pos -= len;  // nothing in [pos - len, pos) qualifies: skip it
+                }
+            }
+            return pos > 0 ? pos - 1 : NOT_IN_TILE;
+        } else {
+            int pos = i + 1;
+#pragma unroll
+            for (int k = K - 1; k >= 0; --k) {
+                const int len = 1 << k;
+                if (pos + len <= TILE) {
+                    const T m = at(k, pos);
+                    if (STRICT ? (m >= x) : (m > x)) pos += len;
+                }
+            }
+            return pos < TILE ? pos : NOT_IN_TILE;
+        }
+    }
+    // one side of the ANSV of tile element i under the reference's match mode; NOT_IN_TILE = the exact search must decide
+    template <int DIR>
+    __device__ __forceinline__ int one(int i, int mode) const {
+        const T x = at(0, i);
+        if (mode == 1) return search<DIR, false>(i, x);
+        const int s = search<DIR, true>(i, x);
+        if (mode == 0 || s == NOT_IN_TILE) return s;
+        const int e = search<-DIR, false>(s, x);  // walking back from s towards i: the first element <= x (i itself at the latest)
+        if (e != i) return e;
+        const T m = at(0, s);  // no equal element before s: the far end of s's own run of equal values
+        const int s2 = search<DIR, true>(s, m);
+        if (s2 == NOT_IN_TILE) return NOT_IN_TILE;
+        return search<-DIR, false>(s2, m);
+    }
+};
+
+// loads the tile [t0, t0 + TILE) of vals (m values; past the end: the largest value, so that searches run off the tile) and
+// builds the sparse table
+template <typename T>
+__device__ __forceinline__ void ansv_tile_build(T* M, const T* __restrict__ vals, u64 t0, u64 m) {
+    constexpr int TILE = AnsvTile<T>::TILE, K = AnsvTile<T>::K;
+    for (int j = threadIdx.x; j < TILE; j += blockDim.x) M[j] = (t0 + j < m) ? vals[t0 + j] : (T)~(T)0;
+    __syncthreads();
+    for (int k = 1; k < K; ++k) {
+        const int half = 1 << (k - 1);
+        for (int j = threadIdx.x; j + 2 * half <= TILE; j += blockDim.x) {
+            const T a = M[(k - 1) * TILE + j], b = M[(k - 1) * TILE + j + half];
+            M[k * TILE + j] = a < b ? a : b;
+        }
+        __syncthreads();
+    }
+}
+
+constexpr int ANSV_LIST = 1024;  // positions per tile that may wait for the exact search (more are searched at once)
+
+template <typename T, class S>
+__global__ void __launch_bounds__(256, 2) ansv_tile_kernel(S sr, const T* __restrict__ vals, u64 g0, u64 m, int left_mode, int right_mode, u64 nonsv,
+                                                          u64* __restrict__ left, u64* __restrict__ right) {
+    extern __shared__ __align__(16) unsigned char ansv_smem[];
+    T* M = reinterpret_cast<T*>(ansv_smem);
+    __shared__ u32 s_list[ANSV_LIST];
+    __shared__ u32 s_cnt;
+    using Tile = AnsvTile<T>;
+    const u64 t0 = (u64)blockIdx.x * Tile::TILE;
+    if (threadIdx.x == 0) s_cnt = 0;
+    ansv_tile_build<T>(M, vals, t0, m);
+    const Tile tile{M};
+    for (int j = threadIdx.x; j < Tile::TILE && t0 + j < m; j += blockDim.x) {
+        const int l = tile.template one<-1>(j, left_mode), r = tile.template one<+1>(j, right_mode);
+        // a match that is the padding past the end of the array is no match: let the exact search decide
+        const bool lf = l == Tile::NOT_IN_TILE, rf = r == Tile::NOT_IN_TILE || t0 + (u64)r >= m;
+        if (!lf) left[t0 + j] = g0 + t0 + (u64)l;
+        if (!rf) right[t0 + j] = g0 + t0 + (u64)r;
+        if (lf || rf) {
+            const u32 slot = atomicAdd(&s_cnt, 1u);
+            const u32 entry = ((u32)j << 2) | (lf ? 1u : 0u) | (rf ? 2u : 0u);
+            if (slot < ANSV_LIST) {
+                s_list[slot] = entry;
+            } else {  // (list full: search right away)
+                if (lf) {
+                    const u64 v = ansv_one<T, -1>(sr, g0 + t0 + j, left_mode);
+                    left[t0 + j] = v == ANSV_NONE ? nonsv : v;
+                }
+                if (rf) {
+                    const u64 v = ansv_one<T, +1>(sr, g0 + t0 + j, right_mode);
+                    right[t0 + j] = v == ANSV_NONE ? nonsv : v;
+                }
             }
         }
     }
+    __syncthreads();
+    const u32 cnt = s_cnt < ANSV_LIST ? s_cnt : ANSV_LIST;
+    for (u32 e = threadIdx.x; e < cnt; e += blockDim.x) {
+        const u32 entry = s_list[e];
+        const u64 i = t0 + (entry >> 2);
+        if (entry & 1u) {
+            const u64 v = ansv_one<T, -1>(sr, g0 + i, left_mode);
+            left[i] = v == ANSV_NONE ? nonsv : v;
+        }
+        if (entry & 2u) {
+            const u64 v = ansv_one<T, +1>(sr, g0 + i, right_mode);
+            right[i] = v == ANSV_NONE ? nonsv : v;
+        }
+    }
+}
+
+// the fused child-table fill, tile version: positions whose left (furthest_eq) and right (nearest_sm) matches and whose
+// successor lie inside the tile are finished from shared memory; the others go through tree_element_slow
+template <typename IdxT, class S>
+__global__ void __launch_bounds__(256, 2) suffix_tree_tile_kernel(TreeFusedArgs<IdxT> A, S sr) {
+    extern __shared__ __align__(16) unsigned char ansv_smem[];
+    IdxT* M = reinterpret_cast<IdxT*>(ansv_smem);
+    __shared__ u32 s_list[ANSV_LIST];
+    __shared__ u32 s_cnt;
+    using Tile = AnsvTile<IdxT>;
+    const u64 t0 = (u64)blockIdx.x * Tile::TILE;
+    if (threadIdx.x == 0) s_cnt = 0;
+    ansv_tile_build<IdxT>(M, A.lcp, t0, A.m);
+    const Tile tile{M};
+    const u64 n = A.n;
+    for (int j = threadIdx.x; j < Tile::TILE && t0 + j < A.m; j += blockDim.x) {
+        const u64 i = t0 + j, gi = A.g0 + i;
+        const int l = gi > 0 ? tile.template one<-1>(j, 2) : 0;
+        const int r = tile.template one<+1>(j, 0);
+        const bool in_tile = l != Tile::NOT_IN_TILE && r != Tile::NOT_IN_TILE && t0 + (u64)r < A.m && j + 1 < Tile::TILE && i + 1 < A.m && gi > 0;
+        if (!in_tile) {
+            const u32 slot = atomicAdd(&s_cnt, 1u);
+            if (slot < ANSV_LIST)
+                s_list[slot] = (u32)j;
+            else
+                tree_element_slow<IdxT, S>(A, sr, i);
+            continue;
+        }
+        const u64 lcp_i = tile.at(0, j), sa_i = A.sa[i];
+        const u64 lnsv = A.g0 + t0 + (u64)l, left_val = tile.at(0, l);
+        const u64 rnsv = A.g0 + t0 + (u64)r, right_val = tile.at(0, r);
+        const u64 next = tile.at(0, j + 1);
+        // ---- leaf n + gi (suffix_tree.hpp:88-141; gi > 0 and gi + 1 < n here)
+        u64 parent, lcp_val;
+        if (lcp_i >= next) {
+            if (left_val == lcp_i) {
+                parent = lnsv;
+                lcp_val = left_val;
+            } else {
+                parent = gi;
+                lcp_val = lcp_i;
+            }
+        } else {
+            parent = gi + 1;
+            lcp_val = next;
+        }
+        tree_emit_dist<IdxT>(A, parent, n + gi, sa_i, lcp_val);
+        // ---- internal node gi (suffix_tree.hpp:146-222)
+        if (lcp_i == 0) continue;
+        if (left_val >= right_val) {
+            if (left_val == lcp_i) continue;
+            tree_emit_dist<IdxT>(A, lnsv, gi, sa_i, left_val);
+        } else {
+            tree_emit_dist<IdxT>(A, rnsv, gi, sa_i, right_val);
+        }
+    }
+    __syncthreads();
+    const u32 cnt = s_cnt < ANSV_LIST ? s_cnt : ANSV_LIST;
+    for (u32 e = threadIdx.x; e < cnt; e += blockDim.x) tree_element_slow<IdxT, S>(A, sr, t0 + s_list[e]);
 }
 
 // edges that other ranks queued for my rows: queue of source s holds counts[s] entries
@@ -426,6 +613,34 @@ __global__ void __launch_bounds__(32) array_min_kernel(const T* __restrict__ a, 
         m = o < m ? o : m;
     }
     if (threadIdx.x == 0) *out = m;
+}
+
+// ---- host launchers of the tile kernels (dynamic shared memory above 48 KB needs the attribute once per device)
+template <typename T, class S>
+void launch_ansv_tile(const S& sr, const T* vals, u64 g0, u64 m, int left_mode, int right_mode, u64 nonsv, u64* left, u64* right, cudaStream_t st) {
+    auto kern = ansv_tile_kernel<T, S>;
+    static bool seen[64] = {};
+    int d = 0;
+    cudaGetDevice(&d);
+    if (!seen[d & 63]) {
+        seen[d & 63] = true;
+        PSAC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AnsvTile<T>::SMEM));
+    }
+    kern<<<(unsigned)((m + AnsvTile<T>::TILE - 1) / AnsvTile<T>::TILE), 256, AnsvTile<T>::SMEM, st>>>(sr, vals, g0, m, left_mode, right_mode, nonsv, left, right);
+    PSAC_CUDA(cudaGetLastError());
+}
+template <typename IdxT, class S>
+void launch_tree_tile(const TreeFusedArgs<IdxT>& A, const S& sr, cudaStream_t st) {
+    auto kern = suffix_tree_tile_kernel<IdxT, S>;
+    static bool seen[64] = {};
+    int d = 0;
+    cudaGetDevice(&d);
+    if (!seen[d & 63]) {
+        seen[d & 63] = true;
+        PSAC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AnsvTile<IdxT>::SMEM));
+    }
+    kern<<<(unsigned)((A.m + AnsvTile<IdxT>::TILE - 1) / AnsvTile<IdxT>::TILE), 256, AnsvTile<IdxT>::SMEM, st>>>(A, sr);
+    PSAC_CUDA(cudaGetLastError());
 }
 
 }  // namespace psacb200
