@@ -823,6 +823,15 @@ bool sort_dispatch_val(psacb200_engine* e, void* k, void* ka, void* v, void* va,
 
 // ---- ANSV: min-tree levels + search kernel (tree_kernels.cuh)
 namespace {
+// list of the positions the tile kernels leave to the exact search: a quarter of the positions fit (random text: 3 %)
+AnsvList ansv_list(psacb200_engine* e, u64 m) {
+    AnsvList L;
+    L.cap = m / 4 + 4096;
+    e->tb[2].reserve(L.cap * sizeof(u64) + 64, &e->device_bytes);
+    L.entries = e->tb[2].as<u64>();
+    L.count = reinterpret_cast<unsigned long long*>(e->shard_meta() + 150);
+    return L;
+}
 template <typename T>
 void ansv_device(psacb200_engine* e, const T* d_vals, u64 n, int left_type, int right_type, u64 nonsv, u64* d_left, u64* d_right) {
     MinTree<T> t{};
@@ -848,7 +857,7 @@ void ansv_device(psacb200_engine* e, const T* d_vals, u64 n, int left_type, int 
         t.levels += 1;
     }
     LocalSearch<T> sr{t};
-    launch_ansv_tile<T, LocalSearch<T>>(sr, d_vals, 0, n, left_type, right_type, nonsv, d_left, d_right, e->stream);
+    launch_ansv_tile<T, LocalSearch<T>>(sr, d_vals, 0, n, left_type, right_type, nonsv, d_left, d_right, ansv_list(e, n), e->sm_count, e->stream);
     e->launches += 1;
     PSAC_CUDA(cudaGetLastError());
 }

@@ -2113,7 +2113,8 @@ void ansv_sharded_core(psacb200_engine* e, const ShardComm& C, const T* d_vals_l
     TreeLayout L;
     DistSearch<T> sr = dist_search_setup<T>(e, C, d_vals_local, n_local, n, L);
     if (n_local) {
-        launch_ansv_tile<T, DistSearch<T>>(sr, d_vals_local, blk.start(C.rank), n_local, left_type, right_type, nonsv, d_left, d_right, e->stream);
+        launch_ansv_tile<T, DistSearch<T>>(sr, d_vals_local, blk.start(C.rank), n_local, left_type, right_type, nonsv, d_left, d_right, ansv_list(e, n_local),
+                                           e->sm_count, e->stream);
         e->launches += 1;
     }
     rank_barrier(e, C);  // my arena may be reused only after every rank is done searching it
@@ -2167,7 +2168,7 @@ void suffix_tree_core(psacb200_engine* e, const ShardComm* C, const u8* d_text_l
         mintree_build<IdxT>(e, sr.t);
         e->mark("mintree");
         A.q.cap = 0;
-        launch_tree_tile<IdxT, LocalSearch<IdxT>>(A, sr, st);
+        launch_tree_tile<IdxT, LocalSearch<IdxT>>(A, sr, ansv_list(e, n), e->sm_count, st);
         e->launches += 1;
         e->mark("tree");
         PSAC_CUDA(cudaStreamSynchronize(st));
@@ -2180,7 +2181,7 @@ void suffix_tree_core(psacb200_engine* e, const ShardComm* C, const u8* d_text_l
     A.q.cap = L.qcap;
     for (int r = 0; r < 16; ++r) A.q.queue[r] = r < p ? reinterpret_cast<u64*>(AR.peer[r] + L.o_queue) + (size_t)me * L.qcap * 3 : nullptr;
     if (n_local) {
-        launch_tree_tile<IdxT, DistSearch<IdxT>>(A, sr, st);
+        launch_tree_tile<IdxT, DistSearch<IdxT>>(A, sr, ansv_list(e, n_local), e->sm_count, st);
         e->launches += 1;
     }
     e->mark("tree");

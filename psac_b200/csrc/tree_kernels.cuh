@@ -484,18 +484,23 @@ __device__ __forceinline__ void ansv_tile_build(T* M, const T* __restrict__ vals
     }
 }
 
-constexpr int ANSV_LIST = 1024;  // positions per tile that may wait for the exact search (more are searched at once)
+// Positions whose match lies outside their tile are appended to a GLOBAL list (entry = local index << 2 | left flag | right flag)
+// and finished by a second kernel, ansv_list_kernel / tree_list_kernel, where every thread has one of them: the exact search
+// is a chain of dependent loads, and only a full grid of such chains hides their latency (finishing them inside the tile
+// kernel, a few dozen per tile, left most of the CTA waiting: 170 ms for 2^29 positions, profiles/r2_tree_notes.md).
+struct AnsvList {
+    u64* entries;
+    unsigned long long* count;
+    u64 cap;
+};
 
 template <typename T, class S>
 __global__ void __launch_bounds__(256, 2) ansv_tile_kernel(S sr, const T* __restrict__ vals, u64 g0, u64 m, int left_mode, int right_mode, u64 nonsv,
-                                                          u64* __restrict__ left, u64* __restrict__ right) {
+                                                          u64* __restrict__ left, u64* __restrict__ right, AnsvList L) {
     extern __shared__ __align__(16) unsigned char ansv_smem[];
     T* M = reinterpret_cast<T*>(ansv_smem);
-    __shared__ u32 s_list[ANSV_LIST];
-    __shared__ u32 s_cnt;
     using Tile = AnsvTile<T>;
     const u64 t0 = (u64)blockIdx.x * Tile::TILE;
-    if (threadIdx.x == 0) s_cnt = 0;
     ansv_tile_build<T>(M, vals, t0, m);
     const Tile tile{M};
     for (int j = threadIdx.x; j < Tile::TILE && t0 + j < m; j += blockDim.x) {
@@ -505,10 +510,9 @@ __global__ void __launch_bounds__(256, 2) ansv_tile_kernel(S sr, const T* __rest
         if (!lf) left[t0 + j] = g0 + t0 + (u64)l;
         if (!rf) right[t0 + j] = g0 + t0 + (u64)r;
         if (lf || rf) {
-            const u32 slot = atomicAdd(&s_cnt, 1u);
-            const u32 entry = ((u32)j << 2) | (lf ? 1u : 0u) | (rf ? 2u : 0u);
-            if (slot < ANSV_LIST) {
-                s_list[slot] = entry;
+            const u64 slot = atomicAdd(L.count, 1ull);
+            if (slot < L.cap) {
+                L.entries[slot] = ((t0 + (u64)j) << 2) | (lf ? 1u : 0u) | (rf ? 2u : 0u);
             } else {  // (list full: search right away)
                 if (lf) {
                     const u64 v = ansv_one<T, -1>(sr, g0 + t0 + j, left_mode);
@@ -521,11 +525,14 @@ __global__ void __launch_bounds__(256, 2) ansv_tile_kernel(S sr, const T* __rest
             }
         }
     }
-    __syncthreads();
-    const u32 cnt = s_cnt < ANSV_LIST ? s_cnt : ANSV_LIST;
-    for (u32 e = threadIdx.x; e < cnt; e += blockDim.x) {
-        const u32 entry = s_list[e];
-        const u64 i = t0 + (entry >> 2);
+}
+
+template <typename T, class S>
+__global__ void __launch_bounds__(256) ansv_list_kernel(S sr, u64 g0, int left_mode, int right_mode, u64 nonsv, u64* __restrict__ left, u64* __restrict__ right,
+                                                        AnsvList L) {
+    const u64 cnt = *L.count < L.cap ? *L.count : L.cap;
+    for (u64 e = (u64)blockIdx.x * blockDim.x + threadIdx.x; e < cnt; e += (u64)gridDim.x * blockDim.x) {
+        const u64 entry = L.entries[e], i = entry >> 2;
         if (entry & 1u) {
             const u64 v = ansv_one<T, -1>(sr, g0 + i, left_mode);
             left[i] = v == ANSV_NONE ? nonsv : v;
@@ -538,16 +545,13 @@ __global__ void __launch_bounds__(256, 2) ansv_tile_kernel(S sr, const T* __rest
 }
 
 // the fused child-table fill, tile version: positions whose left (furthest_eq) and right (nearest_sm) matches and whose
-// successor lie inside the tile are finished from shared memory; the others go through tree_element_slow
+// successor lie inside the tile are finished from shared memory; the others go on the list (tree_list_kernel)
 template <typename IdxT, class S>
-__global__ void __launch_bounds__(256, 2) suffix_tree_tile_kernel(TreeFusedArgs<IdxT> A, S sr) {
+__global__ void __launch_bounds__(256, 2) suffix_tree_tile_kernel(TreeFusedArgs<IdxT> A, S sr, AnsvList L) {
     extern __shared__ __align__(16) unsigned char ansv_smem[];
     IdxT* M = reinterpret_cast<IdxT*>(ansv_smem);
-    __shared__ u32 s_list[ANSV_LIST];
-    __shared__ u32 s_cnt;
     using Tile = AnsvTile<IdxT>;
     const u64 t0 = (u64)blockIdx.x * Tile::TILE;
-    if (threadIdx.x == 0) s_cnt = 0;
     ansv_tile_build<IdxT>(M, A.lcp, t0, A.m);
     const Tile tile{M};
     const u64 n = A.n;
@@ -557,9 +561,9 @@ __global__ void __launch_bounds__(256, 2) suffix_tree_tile_kernel(TreeFusedArgs<
         const int r = tile.template one<+1>(j, 0);
         const bool in_tile = l != Tile::NOT_IN_TILE && r != Tile::NOT_IN_TILE && t0 + (u64)r < A.m && j + 1 < Tile::TILE && i + 1 < A.m && gi > 0;
         if (!in_tile) {
-            const u32 slot = atomicAdd(&s_cnt, 1u);
-            if (slot < ANSV_LIST)
-                s_list[slot] = (u32)j;
+            const u64 slot = atomicAdd(L.count, 1ull);
+            if (slot < L.cap)
+                L.entries[slot] = i;
             else
                 tree_element_slow<IdxT, S>(A, sr, i);
             continue;
@@ -592,9 +596,12 @@ __global__ void __launch_bounds__(256, 2) suffix_tree_tile_kernel(TreeFusedArgs<
             tree_emit_dist<IdxT>(A, rnsv, gi, sa_i, right_val);
         }
     }
-    __syncthreads();
-    const u32 cnt = s_cnt < ANSV_LIST ? s_cnt : ANSV_LIST;
-    for (u32 e = threadIdx.x; e < cnt; e += blockDim.x) tree_element_slow<IdxT, S>(A, sr, t0 + s_list[e]);
+}
+
+template <typename IdxT, class S>
+__global__ void __launch_bounds__(256) tree_list_kernel(TreeFusedArgs<IdxT> A, S sr, AnsvList L) {
+    const u64 cnt = *L.count < L.cap ? *L.count : L.cap;
+    for (u64 e = (u64)blockIdx.x * blockDim.x + threadIdx.x; e < cnt; e += (u64)gridDim.x * blockDim.x) tree_element_slow<IdxT, S>(A, sr, L.entries[e]);
 }
 
 // edges that other ranks queued for my rows: queue of source s holds counts[s] entries
@@ -615,9 +622,11 @@ __global__ void __launch_bounds__(32) array_min_kernel(const T* __restrict__ a, 
     if (threadIdx.x == 0) *out = m;
 }
 
-// ---- host launchers of the tile kernels (dynamic shared memory above 48 KB needs the attribute once per device)
+// ---- host launchers of the tile kernels (dynamic shared memory above 48 KB needs the attribute once per device); the
+// list kernel runs on a full grid: `sms` multiprocessors x 8 CTAs
 template <typename T, class S>
-void launch_ansv_tile(const S& sr, const T* vals, u64 g0, u64 m, int left_mode, int right_mode, u64 nonsv, u64* left, u64* right, cudaStream_t st) {
+void launch_ansv_tile(const S& sr, const T* vals, u64 g0, u64 m, int left_mode, int right_mode, u64 nonsv, u64* left, u64* right, AnsvList L, int sms,
+                      cudaStream_t st) {
     auto kern = ansv_tile_kernel<T, S>;
     static bool seen[64] = {};
     int d = 0;
@@ -626,11 +635,13 @@ void launch_ansv_tile(const S& sr, const T* vals, u64 g0, u64 m, int left_mode, 
         seen[d & 63] = true;
         PSAC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AnsvTile<T>::SMEM));
     }
-    kern<<<(unsigned)((m + AnsvTile<T>::TILE - 1) / AnsvTile<T>::TILE), 256, AnsvTile<T>::SMEM, st>>>(sr, vals, g0, m, left_mode, right_mode, nonsv, left, right);
+    PSAC_CUDA(cudaMemsetAsync(L.count, 0, sizeof(u64), st));
+    kern<<<(unsigned)((m + AnsvTile<T>::TILE - 1) / AnsvTile<T>::TILE), 256, AnsvTile<T>::SMEM, st>>>(sr, vals, g0, m, left_mode, right_mode, nonsv, left, right, L);
+    ansv_list_kernel<T, S><<<sms * 8, 256, 0, st>>>(sr, g0, left_mode, right_mode, nonsv, left, right, L);
     PSAC_CUDA(cudaGetLastError());
 }
 template <typename IdxT, class S>
-void launch_tree_tile(const TreeFusedArgs<IdxT>& A, const S& sr, cudaStream_t st) {
+void launch_tree_tile(const TreeFusedArgs<IdxT>& A, const S& sr, AnsvList L, int sms, cudaStream_t st) {
     auto kern = suffix_tree_tile_kernel<IdxT, S>;
     static bool seen[64] = {};
     int d = 0;
@@ -639,7 +650,9 @@ void launch_tree_tile(const TreeFusedArgs<IdxT>& A, const S& sr, cudaStream_t st
         seen[d & 63] = true;
         PSAC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AnsvTile<IdxT>::SMEM));
     }
-    kern<<<(unsigned)((A.m + AnsvTile<IdxT>::TILE - 1) / AnsvTile<IdxT>::TILE), 256, AnsvTile<IdxT>::SMEM, st>>>(A, sr);
+    PSAC_CUDA(cudaMemsetAsync(L.count, 0, sizeof(u64), st));
+    kern<<<(unsigned)((A.m + AnsvTile<IdxT>::TILE - 1) / AnsvTile<IdxT>::TILE), 256, AnsvTile<IdxT>::SMEM, st>>>(A, sr, L);
+    tree_list_kernel<IdxT, S><<<sms * 8, 256, 0, st>>>(A, sr, L);
     PSAC_CUDA(cudaGetLastError());
 }
 
