@@ -80,7 +80,7 @@ struct psacb200_engine {
     cudaStream_t stream = nullptr;
     size_t device_bytes = 0;
     uint64_t launches = 0;
-    DevBuf text, packed, keys[2], vals[2], vals2, segws, isa, lcp, small, lookback, rk[2], rv[2], rp[2], rh[2], scratch, rep[3], tb[6];
+    DevBuf text, packed, keys[2], vals[2], vals2, segws, isa, lcp, small, lookback, rk[2], rv[2], rp[2], rh[2], scratch, rep[3], tb[6], alist;
     void* nccl_comm = nullptr;  // ncclComm_t of the sharded construction (sharded.cuh), one rank per engine
     void* nccl_comm2 = nullptr; // a split of it for the copy stream (barrier of the SA -> ISA exchange), or null
     static constexpr int COPY_STREAMS = 4;
@@ -827,8 +827,8 @@ namespace {
 AnsvList ansv_list(psacb200_engine* e, u64 m) {
     AnsvList L;
     L.cap = m / 4 + 4096;
-    e->tb[2].reserve(L.cap * sizeof(u64) + 64, &e->device_bytes);
-    L.entries = e->tb[2].as<u64>();
+    e->alist.reserve(L.cap * sizeof(u64) + 64, &e->device_bytes);
+    L.entries = e->alist.as<u64>();
     L.count = reinterpret_cast<unsigned long long*>(e->shard_meta() + 150);
     return L;
 }
@@ -932,7 +932,7 @@ void psacb200_destroy(psacb200_engine* e) {
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->stream);
     DevBuf* all[] = {&e->text, &e->packed, &e->keys[0], &e->keys[1], &e->vals[0], &e->vals[1], &e->vals2, &e->segws, &e->isa, &e->lcp, &e->small, &e->lookback,
-                     &e->rk[0], &e->rk[1], &e->rv[0], &e->rv[1], &e->rp[0], &e->rp[1], &e->rh[0], &e->rh[1], &e->scratch, &e->rep[0], &e->rep[1], &e->rep[2], &e->tb[0], &e->tb[1], &e->tb[2], &e->tb[3], &e->tb[4], &e->tb[5]};
+                     &e->rk[0], &e->rk[1], &e->rv[0], &e->rv[1], &e->rp[0], &e->rp[1], &e->rh[0], &e->rh[1], &e->scratch, &e->rep[0], &e->rep[1], &e->rep[2], &e->tb[0], &e->tb[1], &e->tb[2], &e->tb[3], &e->tb[4], &e->tb[5], &e->alist};
     for (DevBuf* b : all) b->release(nullptr);
     for (int i = 0; i < PH_COUNT; ++i) {
         cudaEventDestroy(e->ev_begin[i]);

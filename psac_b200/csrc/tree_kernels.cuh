@@ -469,15 +469,15 @@ struct AnsvTile {
 
 // loads the tile [t0, t0 + TILE) of vals (m values; past the end: the largest value, so that searches run off the tile) and
 // builds the sparse table
-template <typename T>
-__device__ __forceinline__ void ansv_tile_build(T* M, const T* __restrict__ vals, u64 t0, u64 m) {
-    constexpr int TILE = AnsvTile<T>::TILE, K = AnsvTile<T>::K;
-    for (int j = threadIdx.x; j < TILE; j += blockDim.x) M[j] = (t0 + j < m) ? vals[t0 + j] : (T)~(T)0;
+template <typename T, typename V>
+__device__ __forceinline__ void ansv_tile_build(V* M, const T* __restrict__ vals, u64 t0, u64 m) {
+    constexpr int TILE = AnsvTile<V>::TILE, K = AnsvTile<V>::K;
+    for (int j = threadIdx.x; j < TILE; j += blockDim.x) M[j] = (t0 + j < m) ? (V)vals[t0 + j] : (V)~(V)0;
     __syncthreads();
     for (int k = 1; k < K; ++k) {
         const int half = 1 << (k - 1);
         for (int j = threadIdx.x; j + 2 * half <= TILE; j += blockDim.x) {
-            const T a = M[(k - 1) * TILE + j], b = M[(k - 1) * TILE + j + half];
+            const V a = M[(k - 1) * TILE + j], b = M[(k - 1) * TILE + j + half];
             M[k * TILE + j] = a < b ? a : b;
         }
         __syncthreads();
@@ -501,7 +501,7 @@ __global__ void __launch_bounds__(256, 2) ansv_tile_kernel(S sr, const T* __rest
     T* M = reinterpret_cast<T*>(ansv_smem);
     using Tile = AnsvTile<T>;
     const u64 t0 = (u64)blockIdx.x * Tile::TILE;
-    ansv_tile_build<T>(M, vals, t0, m);
+    ansv_tile_build<T, T>(M, vals, t0, m);
     const Tile tile{M};
     for (int j = threadIdx.x; j < Tile::TILE && t0 + j < m; j += blockDim.x) {
         const int l = tile.template one<-1>(j, left_mode), r = tile.template one<+1>(j, right_mode);
@@ -546,13 +546,15 @@ __global__ void __launch_bounds__(256) ansv_list_kernel(S sr, u64 g0, int left_m
 
 // the fused child-table fill, tile version: positions whose left (furthest_eq) and right (nearest_sm) matches and whose
 // successor lie inside the tile are finished from shared memory; the others go on the list (tree_list_kernel)
-template <typename IdxT, class S>
+// (V = type of the values in shared memory: 32 bits whenever the text is shorter than 2^32 -- LCP values are below n --, which
+//  doubles the tile)
+template <typename IdxT, typename V, class S>
 __global__ void __launch_bounds__(256, 2) suffix_tree_tile_kernel(TreeFusedArgs<IdxT> A, S sr, AnsvList L) {
     extern __shared__ __align__(16) unsigned char ansv_smem[];
-    IdxT* M = reinterpret_cast<IdxT*>(ansv_smem);
-    using Tile = AnsvTile<IdxT>;
+    V* M = reinterpret_cast<V*>(ansv_smem);
+    using Tile = AnsvTile<V>;
     const u64 t0 = (u64)blockIdx.x * Tile::TILE;
-    ansv_tile_build<IdxT>(M, A.lcp, t0, A.m);
+    ansv_tile_build<IdxT, V>(M, A.lcp, t0, A.m);
     const Tile tile{M};
     const u64 n = A.n;
     for (int j = threadIdx.x; j < Tile::TILE && t0 + j < A.m; j += blockDim.x) {
@@ -640,20 +642,27 @@ void launch_ansv_tile(const S& sr, const T* vals, u64 g0, u64 m, int left_mode, 
     ansv_list_kernel<T, S><<<sms * 8, 256, 0, st>>>(sr, g0, left_mode, right_mode, nonsv, left, right, L);
     PSAC_CUDA(cudaGetLastError());
 }
-template <typename IdxT, class S>
-void launch_tree_tile(const TreeFusedArgs<IdxT>& A, const S& sr, AnsvList L, int sms, cudaStream_t st) {
-    auto kern = suffix_tree_tile_kernel<IdxT, S>;
+template <typename IdxT, typename V, class S>
+void launch_tree_tile_v(const TreeFusedArgs<IdxT>& A, const S& sr, AnsvList L, int sms, cudaStream_t st) {
+    auto kern = suffix_tree_tile_kernel<IdxT, V, S>;
     static bool seen[64] = {};
     int d = 0;
     cudaGetDevice(&d);
     if (!seen[d & 63]) {
         seen[d & 63] = true;
-        PSAC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AnsvTile<IdxT>::SMEM));
+        PSAC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AnsvTile<V>::SMEM));
     }
     PSAC_CUDA(cudaMemsetAsync(L.count, 0, sizeof(u64), st));
-    kern<<<(unsigned)((A.m + AnsvTile<IdxT>::TILE - 1) / AnsvTile<IdxT>::TILE), 256, AnsvTile<IdxT>::SMEM, st>>>(A, sr, L);
+    kern<<<(unsigned)((A.m + AnsvTile<V>::TILE - 1) / AnsvTile<V>::TILE), 256, AnsvTile<V>::SMEM, st>>>(A, sr, L);
     tree_list_kernel<IdxT, S><<<sms * 8, 256, 0, st>>>(A, sr, L);
     PSAC_CUDA(cudaGetLastError());
+}
+template <typename IdxT, class S>
+void launch_tree_tile(const TreeFusedArgs<IdxT>& A, const S& sr, AnsvList L, int sms, cudaStream_t st) {
+    if (sizeof(IdxT) == 8 && A.n <= (1ull << 32))
+        launch_tree_tile_v<IdxT, u32, S>(A, sr, L, sms, st);  // LCP values are below n: 32 bits in shared memory
+    else
+        launch_tree_tile_v<IdxT, IdxT, S>(A, sr, L, sms, st);
 }
 
 }  // namespace psacb200
