@@ -823,10 +823,10 @@ bool sort_dispatch_val(psacb200_engine* e, void* k, void* ka, void* v, void* va,
 
 // ---- ANSV: min-tree levels + search kernel (tree_kernels.cuh)
 namespace {
-// list of the positions the tile kernels leave to the exact search: a quarter of the positions fit (random text: 3 %)
+// list of the positions the tile kernels leave to the exact search (random text: 3 % of them; room for all)
 AnsvList ansv_list(psacb200_engine* e, u64 m) {
     AnsvList L;
-    L.cap = m / 4 + 4096;
+    L.cap = m + 64;
     e->alist.reserve(L.cap * sizeof(u64) + 64, &e->device_bytes);
     L.entries = e->alist.as<u64>();
     L.count = reinterpret_cast<unsigned long long*>(e->shard_meta() + 150);

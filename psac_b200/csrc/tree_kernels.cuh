@@ -45,36 +45,55 @@ __device__ __forceinline__ bool ansv_hit(T v, T x) {
     return STRICT ? (v < x) : (v <= x);
 }
 
+// nearest hit inside a[lo, hi) seen from the near side (DIR < 0: the largest index, DIR > 0: the smallest), ANSV_NONE if there
+// is none.  The entries are fetched eight at a time with independent loads, so a block of 32 costs at most four memory round
+// trips instead of 31 dependent ones.
+template <typename T, int DIR, bool STRICT>
+__device__ __forceinline__ u64 ansv_scan(const T* __restrict__ a, u64 lo, u64 hi, T x) {
+    constexpr int G = 8;
+    if (DIR < 0) {
+        u64 j = hi;
+        while (j > lo) {
+            const int c = (j - lo) < (u64)G ? (int)(j - lo) : G;
+            T v[G];
+#pragma unroll
+            for (int q = 0; q < G; ++q)
+                if (q < c) v[q] = a[j - 1 - q];
+#pragma unroll
+            for (int q = 0; q < G; ++q)
+                if (q < c && ansv_hit<T, STRICT>(v[q], x)) return j - 1 - q;
+            j -= c;
+        }
+    } else {
+        u64 j = lo;
+        while (j < hi) {
+            const int c = (hi - j) < (u64)G ? (int)(hi - j) : G;
+            T v[G];
+#pragma unroll
+            for (int q = 0; q < G; ++q)
+                if (q < c) v[q] = a[j + q];
+#pragma unroll
+            for (int q = 0; q < G; ++q)
+                if (q < c && ansv_hit<T, STRICT>(v[q], x)) return j + q;
+            j += c;
+        }
+    }
+    return ANSV_NONE;
+}
+
 // Nearest position j on the LEFT (DIR = -1: j < i) or RIGHT (DIR = +1: j > i) of i with v[j] < x (STRICT) or <= x.
 // ANSV_NONE if there is none.
 template <typename T, int DIR, bool STRICT>
-__device__ u64 ansv_search(const MinTree<T>& t, u64 i, T x) {
+__device__ __noinline__ u64 ansv_search(const MinTree<T>& t, u64 i, T x) {
     int lv = 0;
     u64 p = i;  // current position at level lv; its block of 32 is [p & ~31, p | 31]
     // ---- climb: scan the rest of the current block away from p, then move to the parent
     while (true) {
         const u64 n = t.size[lv];
-        const T* a = t.level[lv];
-        u64 found = ANSV_NONE;
-        if (DIR < 0) {
-            const u64 lo = p & ~(u64)(ANSV_FAN - 1);
-            for (u64 j = p; j > lo;) {
-                --j;
-                if (ansv_hit<T, STRICT>(a[j], x)) {
-                    found = j;
-                    break;
-                }
-            }
-        } else {
-            u64 hi = (p | (u64)(ANSV_FAN - 1)) + 1;
-            hi = hi < n ? hi : n;
-            for (u64 j = p + 1; j < hi; ++j) {
-                if (ansv_hit<T, STRICT>(a[j], x)) {
-                    found = j;
-                    break;
-                }
-            }
-        }
+        const u64 blo = p & ~(u64)(ANSV_FAN - 1);
+        u64 bhi = blo + ANSV_FAN;
+        bhi = bhi < n ? bhi : n;
+        const u64 found = DIR < 0 ? ansv_scan<T, DIR, STRICT>(t.level[lv], blo, p, x) : ansv_scan<T, DIR, STRICT>(t.level[lv], p + 1, bhi, x);
         if (found != ANSV_NONE) {
             p = found;
             break;
@@ -83,26 +102,14 @@ __device__ u64 ansv_search(const MinTree<T>& t, u64 i, T x) {
         p >>= 5;
         ++lv;
     }
-    // ---- descend: inside block p of level lv take the child nearest to i that qualifies
+    // ---- descend: inside block p of level lv take the child nearest to i that qualifies (the block's minimum does)
     while (lv > 0) {
         --lv;
         const u64 n = t.size[lv];
-        const T* a = t.level[lv];
         const u64 lo = p * ANSV_FAN;
         u64 hi = lo + ANSV_FAN;
         hi = hi < n ? hi : n;
-        if (DIR < 0) {
-            u64 j = hi;
-            while (j > lo) {
-                --j;
-                if (ansv_hit<T, STRICT>(a[j], x)) break;
-            }
-            p = j;
-        } else {
-            u64 j = lo;
-            while (j < hi && !ansv_hit<T, STRICT>(a[j], x)) ++j;
-            p = j;
-        }
+        p = ansv_scan<T, DIR, STRICT>(t.level[lv], lo, hi, x);
     }
     return p;
 }
@@ -110,44 +117,16 @@ __device__ u64 ansv_search(const MinTree<T>& t, u64 i, T x) {
 // inside block-minimum tree t, the position nearest to the entry side (DIR < 0: we come from the right, so the LARGEST
 // qualifying index; DIR > 0: the smallest) -- the caller knows that the minimum of the whole array qualifies
 template <typename T, int DIR, bool STRICT>
-__device__ u64 ansv_descend_top(const MinTree<T>& t, T x) {
+__device__ __noinline__ u64 ansv_descend_top(const MinTree<T>& t, T x) {
     int lv = t.levels - 1;
-    u64 p = 0;
-    {
-        const T* a = t.level[lv];
-        const u64 n = t.size[lv];
-        if (DIR < 0) {
-            u64 j = n;
-            while (j > 0) {
-                --j;
-                if (ansv_hit<T, STRICT>(a[j], x)) break;
-            }
-            p = j;
-        } else {
-            u64 j = 0;
-            while (j + 1 < n && !ansv_hit<T, STRICT>(a[j], x)) ++j;
-            p = j;
-        }
-    }
+    u64 p = ansv_scan<T, DIR, STRICT>(t.level[lv], 0, t.size[lv], x);
     while (lv > 0) {
         --lv;
         const u64 n = t.size[lv];
-        const T* a = t.level[lv];
         const u64 lo = p * ANSV_FAN;
         u64 hi = lo + ANSV_FAN;
         hi = hi < n ? hi : n;
-        if (DIR < 0) {
-            u64 j = hi;
-            while (j > lo) {
-                --j;
-                if (ansv_hit<T, STRICT>(a[j], x)) break;
-            }
-            p = j;
-        } else {
-            u64 j = lo;
-            while (j < hi && !ansv_hit<T, STRICT>(a[j], x)) ++j;
-            p = j;
-        }
+        p = ansv_scan<T, DIR, STRICT>(t.level[lv], lo, hi, x);
     }
     return p;
 }
@@ -510,19 +489,8 @@ __global__ void __launch_bounds__(256, 2) ansv_tile_kernel(S sr, const T* __rest
         if (!lf) left[t0 + j] = g0 + t0 + (u64)l;
         if (!rf) right[t0 + j] = g0 + t0 + (u64)r;
         if (lf || rf) {
-            const u64 slot = atomicAdd(L.count, 1ull);
-            if (slot < L.cap) {
-                L.entries[slot] = ((t0 + (u64)j) << 2) | (lf ? 1u : 0u) | (rf ? 2u : 0u);
-            } else {  // (list full: search right away)
-                if (lf) {
-                    const u64 v = ansv_one<T, -1>(sr, g0 + t0 + j, left_mode);
-                    left[t0 + j] = v == ANSV_NONE ? nonsv : v;
-                }
-                if (rf) {
-                    const u64 v = ansv_one<T, +1>(sr, g0 + t0 + j, right_mode);
-                    right[t0 + j] = v == ANSV_NONE ? nonsv : v;
-                }
-            }
+            const u64 slot = atomicAdd(L.count, 1ull);  // (the list has room for every position)
+            if (slot < L.cap) L.entries[slot] = ((t0 + (u64)j) << 2) | (lf ? 1u : 0u) | (rf ? 2u : 0u);
         }
     }
 }
@@ -563,11 +531,8 @@ __global__ void __launch_bounds__(256, 2) suffix_tree_tile_kernel(TreeFusedArgs<
         const int r = tile.template one<+1>(j, 0);
         const bool in_tile = l != Tile::NOT_IN_TILE && r != Tile::NOT_IN_TILE && t0 + (u64)r < A.m && j + 1 < Tile::TILE && i + 1 < A.m && gi > 0;
         if (!in_tile) {
-            const u64 slot = atomicAdd(L.count, 1ull);
-            if (slot < L.cap)
-                L.entries[slot] = i;
-            else
-                tree_element_slow<IdxT, S>(A, sr, i);
+            const u64 slot = atomicAdd(L.count, 1ull);  // (the list has room for every position)
+            if (slot < L.cap) L.entries[slot] = i;
             continue;
         }
         const u64 lcp_i = tile.at(0, j), sa_i = A.sa[i];
