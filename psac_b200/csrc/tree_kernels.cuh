@@ -46,37 +46,18 @@ __device__ __forceinline__ bool ansv_hit(T v, T x) {
 }
 
 // nearest hit inside a[lo, hi) seen from the near side (DIR < 0: the largest index, DIR > 0: the smallest), ANSV_NONE if there
-// is none.  The entries are fetched eight at a time with independent loads, so a block of 32 costs at most four memory round
-// trips instead of 31 dependent ones.
+// is none.  (Fetching eight entries per round trip with independent loads was measured: the registers it takes cost the list
+// kernels more occupancy than the shorter dependency chains win, 46 -> 52 ms at 2^29, profiles/r2_tree_notes.md.)
 template <typename T, int DIR, bool STRICT>
 __device__ __forceinline__ u64 ansv_scan(const T* __restrict__ a, u64 lo, u64 hi, T x) {
-    constexpr int G = 8;
     if (DIR < 0) {
-        u64 j = hi;
-        while (j > lo) {
-            const int c = (j - lo) < (u64)G ? (int)(j - lo) : G;
-            T v[G];
-#pragma unroll
-            for (int q = 0; q < G; ++q)
-                if (q < c) v[q] = a[j - 1 - q];
-#pragma unroll
-            for (int q = 0; q < G; ++q)
-                if (q < c && ansv_hit<T, STRICT>(v[q], x)) return j - 1 - q;
-            j -= c;
+        for (u64 j = hi; j > lo;) {
+            --j;
+            if (ansv_hit<T, STRICT>(a[j], x)) return j;
         }
     } else {
-        u64 j = lo;
-        while (j < hi) {
-            const int c = (hi - j) < (u64)G ? (int)(hi - j) : G;
-            T v[G];
-#pragma unroll
-            for (int q = 0; q < G; ++q)
-                if (q < c) v[q] = a[j + q];
-#pragma unroll
-            for (int q = 0; q < G; ++q)
-                if (q < c && ansv_hit<T, STRICT>(v[q], x)) return j + q;
-            j += c;
-        }
+        for (u64 j = lo; j < hi; ++j)
+            if (ansv_hit<T, STRICT>(a[j], x)) return j;
     }
     return ANSV_NONE;
 }
@@ -407,6 +388,10 @@ struct AnsvTile {
     template <int DIR, bool STRICT>
     __device__ __forceinline__ int search(int i, T x) const {
         if (DIR < 0) {
+            // most matches are a few positions away: look at the three nearest entries before lifting
+            if (i >= 1 && (STRICT ? at(0, i - 1) < x : at(0, i - 1) <= x)) return i - 1;
+            if (i >= 2 && (STRICT ? at(0, i - 2) < x : at(0, i - 2) <= x)) return i - 2;
+            if (i >= 3 && (STRICT ? at(0, i - 3) < x : at(0, i - 3) <= x)) return i - 3;
             int pos = i;
 #pragma unroll
             for (int k = K - 1; k >= 0; --k) {
@@ -418,6 +403,9 @@ struct AnsvTile {
             }
             return pos > 0 ? pos - 1 : NOT_IN_TILE;
         } else {
+            if (i + 1 < TILE && (STRICT ? at(0, i + 1) < x : at(0, i + 1) <= x)) return i + 1;
+            if (i + 2 < TILE && (STRICT ? at(0, i + 2) < x : at(0, i + 2) <= x)) return i + 2;
+            if (i + 3 < TILE && (STRICT ? at(0, i + 3) < x : at(0, i + 3) <= x)) return i + 3;
             int pos = i + 1;
 #pragma unroll
             for (int k = K - 1; k >= 0; --k) {
