@@ -506,6 +506,7 @@ struct HeadsArgs {
     u64* agg_sum;          // per tile: unresolved elements / exclusive prefix
     u64 pos_base;          // sharded construction: SA position of local element 0 (bucket ids and positions are global)
     const u64* halo;       // sharded construction: {key, suffix} of the last element of the previous shard, or null
+    int kbits;             // bits of the complete key when it is not C whole characters (0: C * lbits)
     int word_shift;        // WORD: the keys are 64-bit words [carried key | suffix index field]: the key is word >> word_shift,
     WordIdx widx;          //       the suffix index widx.decode(word) (vals is not read)
 };
@@ -725,7 +726,7 @@ __global__ void __launch_bounds__(HD_THREADS) heads_kernel(HeadsArgs A) {
             if (q0 + i < m) isa[vals[q0 + i]] = (PosT)(A.pos_base + bucket[i]);
     }
     if (A.lcp != nullptr) {
-        const int nbits = A.C * A.lbits;
+        const int nbits = A.kbits ? A.kbits : A.C * A.lbits;
         u32 l[HD_ITEMS];
 #pragma unroll
         for (int i = 0; i < HD_ITEMS; ++i) {

@@ -1433,13 +1433,25 @@ bool construct_sharded_v2(psacb200_engine* e, const ShardComm& C, const u8* d_te
     widx.div = BlkDiv::make(n, p);
     widx.lb = idx_bits;
     widx.mask = (1ull << ib) - 1ull;
-    unsigned Cc = choose_key_chars(n, lbits, k);
-    auto top_bits = [&](unsigned c) { return std::min(RADIX_BITS, (int)c * lbits); };
-    while (Cc > 1 && (int)Cc * lbits - top_bits(Cc) > 64 - ib) --Cc;
-    const int K = (int)Cc * lbits, tb = top_bits(Cc), cb = K - tb;
-    if (cb > 64 - ib) return false;
+    // The key is the first K BITS of the suffix in the packed text -- not necessarily whole characters: with 2-bit DNA and a
+    // 33-bit index field 31 carried + 8 top bits = 39 bits = 19.5 characters, and the half character halves the number of
+    // suffixes that stay unresolved.  Cc = characters the key covers completely (what a shared bucket is known to agree on),
+    // Ct = characters it touches (suffixes shorter than that run past the end of the text inside the key).
+    const unsigned Cmax = choose_key_chars(n, lbits, k);
+    int K = (int)Cmax * lbits;
+    {
+        const int tb0 = std::min(RADIX_BITS, K);
+        K = std::min(K, tb0 + (64 - ib));
+        if (const char* force = getenv("PSACB200_V2_KEYBITS")) {  // test knob: a key that ends inside a character at small sizes
+            const int f = atoi(force);
+            if (f >= lbits && f <= K) K = f;
+        }
+    }
+    const int tb = std::min(RADIX_BITS, K), cb = K - tb;
+    if (K < lbits || cb > 64 - ib) return false;  // (less than one character of key: not worth a sharded sort)
+    const unsigned Cc = (unsigned)(K / lbits), Ct = (unsigned)((K + lbits - 1) / lbits);
     const int nb = 1 << tb;
-    const u64 T = (n < (u64)Cc - 1) ? n : (u64)Cc - 1;
+    const u64 T = (n < (u64)Ct - 1) ? n : (u64)Ct - 1;
     if (T > blk.size(p - 1)) return false;  // the suffixes that run past the end must all lie in the last block
     S.key_chars = Cc;
 
@@ -1619,6 +1631,7 @@ bool construct_sharded_v2(psacb200_engine* e, const ShardComm& C, const u8* d_te
     H.n = n;
     H.lbits = lbits;
     H.C = (int)Cc;
+    H.kbits = K;
     H.tails = tails;
     H.bucket_out = nullptr;
     H.isa = nullptr;

@@ -124,6 +124,14 @@ def main():
     ok &= case("repetitive text + tree", G.repeats_text(40000 * p, 3), 8, True, tree=True)
     ok &= case("periodic text (abc)^k + tree", G.periodic_text(b"abc", 60000 * p), 4, True, tree=True)
     ok &= case("two-symbol text", (G.random_bytes(p << 17, 25) % 2 + 97).astype(np.uint8), 8, True)
+    # keys that end inside a character (at full size: 39 key bits for 8 x 2^30 DNA characters); forced here at test size
+    for kb in ("39", "23", "9"):
+        os.environ["PSACB200_V2_KEYBITS"] = kb
+        ok &= case("random DNA, %s key bits" % kb, G.random_dna((p << 19) + 17, 30 + int(kb)), 8, True, scheme=2)
+    os.environ["PSACB200_V2_KEYBITS"] = "13"
+    ok &= case("16-symbol text, 13 key bits", (G.random_bytes(p << 18, 27) % 16 + 97).astype(np.uint8), 8, True, scheme=2)
+    ok &= case("repetitive text, 13 key bits", G.repeats_text(30000 * p, 5), 8, True, scheme=2)
+    del os.environ["PSACB200_V2_KEYBITS"]
     ok &= case("random bytes (sigma=256 quirk)", G.random_bytes_config4(p << 18, 15), 8, False, scheme=1)
     ok &= case("small input (replicated path) + tree", G.random_dna(1000 + p, 17), 8, True, scheme=0, tree=True)
     # scheme 1 (the fallback): key-range selection + replicated rounds, all four exchange variants
