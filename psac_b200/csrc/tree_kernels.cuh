@@ -388,10 +388,6 @@ struct AnsvTile {
     template <int DIR, bool STRICT>
     __device__ __forceinline__ int search(int i, T x) const {
         if (DIR < 0) {
-            // most matches are a few positions away: look at the three nearest entries before lifting
-            if (i >= 1 && (STRICT ? at(0, i - 1) < x : at(0, i - 1) <= x)) return i - 1;
-            if (i >= 2 && (STRICT ? at(0, i - 2) < x : at(0, i - 2) <= x)) return i - 2;
-            if (i >= 3 && (STRICT ? at(0, i - 3) < x : at(0, i - 3) <= x)) return i - 3;
             int pos = i;
 #pragma unroll
             for (int k = K - 1; k >= 0; --k) {
@@ -403,9 +399,6 @@ struct AnsvTile {
             }
             return pos > 0 ? pos - 1 : NOT_IN_TILE;
         } else {
-            if (i + 1 < TILE && (STRICT ? at(0, i + 1) < x : at(0, i + 1) <= x)) return i + 1;
-            if (i + 2 < TILE && (STRICT ? at(0, i + 2) < x : at(0, i + 2) <= x)) return i + 2;
-            if (i + 3 < TILE && (STRICT ? at(0, i + 3) < x : at(0, i + 3) <= x)) return i + 3;
             int pos = i + 1;
 #pragma unroll
             for (int k = K - 1; k >= 0; --k) {
@@ -513,9 +506,31 @@ __global__ void __launch_bounds__(256, 2) suffix_tree_tile_kernel(TreeFusedArgs<
     ansv_tile_build<IdxT, V>(M, A.lcp, t0, A.m);
     const Tile tile{M};
     const u64 n = A.n;
+    // left match (furthest_eq) in two steps, so that no position repeats the work of another: (1) s = nearest strictly smaller,
+    // e = first entry <= x walking back from s: an equal entry before j, or j itself; (2) where e is j itself the answer is the
+    // far end of s's run of equal values -- which is what step (1) of position s has found.
+    __shared__ int s_feq[Tile::TILE];
+    constexpr int SELF = 1 << 30;  // "no equal entry before me; my strictly smaller one is at (value & ~SELF)"
+    for (int j = threadIdx.x; j < Tile::TILE; j += blockDim.x) {
+        int f = Tile::NOT_IN_TILE;
+        if (t0 + j < A.m) {
+            const V x = tile.at(0, j);
+            const int s = tile.template search<-1, true>(j, x);
+            if (s != Tile::NOT_IN_TILE) {
+                const int e = tile.template search<+1, false>(s, x);
+                f = e != j ? e : (SELF | s);
+            }
+        }
+        s_feq[j] = f;
+    }
+    __syncthreads();
     for (int j = threadIdx.x; j < Tile::TILE && t0 + j < A.m; j += blockDim.x) {
         const u64 i = t0 + j, gi = A.g0 + i;
-        const int l = gi > 0 ? tile.template one<-1>(j, 2) : 0;
+        int l = s_feq[j];
+        if (l != Tile::NOT_IN_TILE && (l & SELF)) {
+            const int s = l & ~SELF, fs = s_feq[s];
+            l = fs == Tile::NOT_IN_TILE ? Tile::NOT_IN_TILE : ((fs & SELF) ? s : fs);
+        }
         const int r = tile.template one<+1>(j, 0);
         const bool in_tile = l != Tile::NOT_IN_TILE && r != Tile::NOT_IN_TILE && t0 + (u64)r < A.m && j + 1 < Tile::TILE && i + 1 < A.m && gi > 0;
         if (!in_tile) {
