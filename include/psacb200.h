@@ -97,7 +97,11 @@ int psacb200_construct(psacb200_engine* e, const uint8_t* text, size_t n, int in
  * produced by psacb200_alphabet; only their ORDER matters. */
 int psacb200_construct_alphabet(psacb200_engine* e, const uint8_t* text, size_t n, int index_bytes, unsigned flags, unsigned k,
                                 const uint8_t lut[256], void* sa_out, void* isa_out, void* lcp_out);
-/* DEVICE buffers in and out (text already resident in HBM; outputs stay there). */
+/* DEVICE buffers in and out (text already resident in HBM; outputs stay there).
+ * Stream contract of every *_device and *_sharded entry point: the engine reads its inputs and writes its outputs on ITS OWN
+ * stream (psacb200_stream) and returns after synchronising that stream; whatever produced the inputs on other streams must have
+ * completed before the call.  Output buffers that are 16-byte aligned are used in place as the engine's result arrays (also when
+ * the caller's index is 64 bits wide and the engine's 32: the narrow array lives in the lower half and is widened in place). */
 int psacb200_construct_device(psacb200_engine* e, const uint8_t* d_text, size_t n, int index_bytes, unsigned flags, unsigned k, void* d_sa,
                               void* d_isa, void* d_lcp);
 

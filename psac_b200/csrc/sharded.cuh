@@ -609,7 +609,7 @@ bool construct_sharded_core(psacb200_engine* e, const ShardComm& C, const u8* d_
     const u64 cnt = cnt_key[me], off = off_key[me];
     const u64 cap = 2 * div_up(n, (size_t)p) + 4096;
     for (int r = 0; r < p; ++r)
-        if (cnt_key[r] > cap || cnt_key[r] == 0) return false;  // key prefixes too skewed for bin-boundary splitters
+        if (cnt_key[r] > cap || cnt_key[r] == 0 || cnt_key[r] >= (1ull << 32)) return false;  // too skewed for bin-boundary splitters (or beyond the 32-bit local positions of the heads kernel)
     // send counts of the ISA exchange: [text block b][key range a] = suffixes of block b whose bin lies in range a
     std::vector<u64> blk_in_range((size_t)p * p, 0);
     for (int b = 0; b < p; ++b)
@@ -1480,6 +1480,7 @@ bool construct_sharded_v2(psacb200_engine* e, const ShardComm& C, const u8* d_te
     WordExchangePlan P;
     plan_word_exchange(cnt_sd.data(), p, nb, n, cb > 0 ? (u64)LTILE : 1, P);
     if (!P.balanced) return false;  // top key digits too skewed for digit-boundary splitters
+    if (P.max_cnt >= (1ull << 32)) return false;  // (the heads kernel keeps positions inside a rank's range in 32 bits)
     const u64 cnt = P.cnt_key[me], off = P.off_key[me];
     // exchange word of the SA -> ISA step: [local index | rank | position relative to the sender]
     const int rel_bits = std::max(1, (int)bits_for(P.max_cnt - 1));
