@@ -1606,6 +1606,12 @@ bool construct_sharded_v2(psacb200_engine* e, const ShardComm& C, const u8* d_te
     PSAC_NCCL(g_nccl.AllGather(d_last + 2 * me, d_last, 2, ncclUint64, C.comm, st));
     if (want_lcp) e->lcp.reserve((cnt + 16) * sizeof(u64), tot);
     u64* LCP = want_lcp ? e->lcp.as<u64>() : nullptr;
+    // 64-bit caller: the LCP of the positions of my key range that lie inside my own output block is written in place;
+    // only the slivers that belong to the neighbours' blocks go through the key-range buffer and the re-balancing step
+    const u64 blk_lo = blk.start(me), blk_hi = blk_lo + n_local;
+    const bool lcp_direct = want_lcp && index_bytes == 8 && std::min(off + cnt, blk_hi) > std::max(off, blk_lo);
+    const u64 main_lo = lcp_direct ? std::max(off, blk_lo) - off : 0, main_hi = lcp_direct ? std::min(off + cnt, blk_hi) - off : 0;
+    u64* lcp_main = lcp_direct ? reinterpret_cast<u64*>(lcp_out) + ((long long)off - (long long)blk_lo) : nullptr;
     u64 ucap = std::max<u64>(unresolved_cap(cnt), 1);
     auto reserve_lists = [&](int t, u64 cap_) {
         e->rp[t].reserve(cap_ * sizeof(u64), tot);
@@ -1637,6 +1643,9 @@ bool construct_sharded_v2(psacb200_engine* e, const ShardComm& C, const u8* d_te
     H.bucket_out = nullptr;
     H.isa = nullptr;
     H.lcp = LCP;
+    H.lcp_main = lcp_main;
+    H.main_lo = main_lo;
+    H.main_hi = main_hi;
     H.pos_out = e->rp[1].p;
     H.head_out = e->rh[1].as<u8>();
     H.suf_out = e->rv[1].p;
@@ -1870,6 +1879,9 @@ bool construct_sharded_v2(psacb200_engine* e, const ShardComm& C, const u8* d_te
                 Q.pisa = pisa;
                 Q.isa_add = off;
                 Q.widx = widx;
+                Q.lcp_main = lcp_main;
+                Q.main_lo = main_lo;
+                Q.main_hi = main_hi;
                 launch_resolve<u64, u64>(e, false, Q);  // new bucket ids go to the owners' ISA blocks over peer memory
             } else {
                 PSAC_CUDA(cudaMemsetAsync(e->counts(), 0, 2 * sizeof(u64), st));
@@ -1918,6 +1930,7 @@ bool construct_sharded_v2(psacb200_engine* e, const ShardComm& C, const u8* d_te
                 rcount[b] = rhi > rlo ? rhi - rlo : 0;
                 rdispl[b] = rhi > rlo ? rlo - text_lo : 0;
             }
+            if (lcp_direct) scount[me] = rcount[me] = 0;  // my own share is in place already
             const bool direct = index_bytes == 8;
             u64* target = direct ? reinterpret_cast<u64*>(lcp_out) : at(me, oR0);  // (the exchange buffer is free again)
             all_to_all_v(e, C, LCP, scount, sdispl, target, rcount, rdispl, sizeof(u64));
