@@ -105,6 +105,21 @@ int psacb200_construct_alphabet(psacb200_engine* e, const uint8_t* text, size_t 
 int psacb200_construct_device(psacb200_engine* e, const uint8_t* d_text, size_t n, int index_bytes, unsigned flags, unsigned k, void* d_sa,
                               void* d_isa, void* d_lcp);
 
+/* ---- generalized suffix array of a string set (reference suffix_array::construct_ss, include/suffix_array.hpp:269-363,
+ *      on a simple_dstringset, include/stringset.hpp:33-152; golden vectors test/test_gsa.cpp:97-98) ---------------- */
+/* flat = the strings separated by the byte `sep` (runs of separators, leading and trailing ones are allowed and skipped, as
+ * simple_dstringset::parse does).  The result indexes the concatenation of the strings WITHOUT separators: *n_out = number of
+ * non-separator characters (the reference's ss.sum_sizes), and sa_out / isa_out / lcp_out receive *n_out entries each (the
+ * caller provides room for len).  A suffix ends with its string; identical suffixes of different strings are ordered by
+ * position and their LCP is their length.  lut: NULL = alphabet of the characters that occur (alphabet<char>::from_string of
+ * all strings), or 256 codes whose ORDER defines the character order (codes of occurring characters must be non-zero).
+ * One GPU; isa_out may be NULL. */
+int psacb200_construct_ss(psacb200_engine* e, const uint8_t* flat, size_t len, uint8_t sep, int index_bytes, unsigned flags, const uint8_t* lut,
+                          void* sa_out, void* isa_out, void* lcp_out, uint64_t* n_out);
+/* Same on DEVICE buffers (stream contract as psacb200_construct_device). */
+int psacb200_construct_ss_device(psacb200_engine* e, const uint8_t* d_flat, size_t len, uint8_t sep, int index_bytes, unsigned flags,
+                                 const uint8_t* lut, void* d_sa, void* d_isa, void* d_lcp, uint64_t* n_out);
+
 /* ---- building blocks on DEVICE pointers (used by the parity tests and by the sharded multi-GPU driver) ------ */
 /* Stable LSD radix sort of n (key, value) pairs by key bits [begin_bit, end_bit); key_bytes in {4,8}, val_bytes in
  * {0,4,8}.  Sorted data is returned in keys/vals (keys_alt/vals_alt are scratch of the same size).

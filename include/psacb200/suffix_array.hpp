@@ -54,6 +54,33 @@ struct alphabet {
     unsigned sigma() const { return sigma_; }                  // alphabet.hpp:241
     unsigned bits_per_char() const { return bits_per_char_; }  // alphabet.hpp:249
     uint8_t encode(unsigned char c) const { return mapping_table[c]; }  // alphabet.hpp:266-269
+    // alphabet.hpp:220-225: the alphabet of the characters of a string (codes 1.. in byte order)
+    static alphabet from_string(const std::string& str, const comm& = comm()) {
+        alphabet a;
+        bool used[256] = {false};
+        for (unsigned char c : str) used[c] = true;
+        unsigned code = 1;
+        for (int i = 0; i < 256; ++i)
+            if (used[i]) {
+                a.mapping_table[i] = (uint8_t)code++;
+                ++a.sigma_;
+            }
+        while ((1u << a.bits_per_char_) < a.sigma_ + 1) ++a.bits_per_char_;
+        return a;
+    }
+};
+
+// stand-in for simple_dstringset at p = 1 (reference include/stringset.hpp:33-152): the strings are the maximal runs of
+// non-separator characters of a flat text, which is copied once (the reference borrows it)
+class simple_dstringset {
+public:
+    std::vector<uint8_t> flat;
+    char sep;
+    std::size_t sum_sizes;
+    template <typename Iterator>
+    simple_dstringset(Iterator begin, Iterator end, const comm& = comm(), char sep_ = '$') : flat(begin, end), sep(sep_), sum_sizes(0) {
+        for (uint8_t c : flat) sum_sizes += (c != (uint8_t)sep) ? 1 : 0;
+    }
 };
 
 template <typename char_t, typename index_t = std::size_t, bool _CONSTRUCT_LCP = false, bool _CONSTRUCT_LC = false>
@@ -120,6 +147,26 @@ public:
         ensure_engine();
         check(psacb200_alphabet(engine_, text, n, alpha.mapping_table, &alpha.sigma_, &alpha.bits_per_char_));
         run(text, fast_resolval, 0, nullptr, false);
+    }
+
+    // reference :269-363 -- generalized suffix array (+ LCP) of a string set: positions index the concatenation of the strings
+    // without separators; identical suffixes of different strings are ordered by position.  Runs on the first GPU.
+    void construct_ss(simple_dstringset& ss, const alphabet_type& alphabet) {
+        alpha = alphabet;
+        ensure_engine();
+        const std::size_t cap = ss.flat.size();
+        local_SA.resize(cap);
+        local_B.resize(cap);
+        local_LCP.clear();
+        if (_CONSTRUCT_LCP) local_LCP.resize(cap);
+        local_Lc.clear();
+        uint64_t m = 0;
+        check(psacb200_construct_ss(engine_, ss.flat.data(), cap, (uint8_t)ss.sep, (int)sizeof(index_t), _CONSTRUCT_LCP ? PSACB200_LCP : 0u,
+                                    alpha.mapping_table, local_SA.data(), local_B.data(), _CONSTRUCT_LCP ? (void*)local_LCP.data() : nullptr, &m));
+        local_SA.resize(m);
+        local_B.resize(m);
+        if (_CONSTRUCT_LCP) local_LCP.resize(m);
+        init_size(m);
     }
 
     // reference :232-243 -- <basename>.sa, .lcp (if built): raw little-endian index_t; .alpha: the used characters

@@ -17,6 +17,8 @@
  * halo exchanges of the reference (left/right shifts) degenerate to "0 past
  * the end" / "rank 0 has no left neighbour".
  *
+ * Also restated: construct_ss, the generalized suffix array of a string set (section 8 f2).
+ *
  * Not restated: construct_msgs (bucket chasing, suffix_array.hpp:1032-1285).
  * It is a schedule optimisation -- final SA/ISA/LCP do not depend on it
  * (0-padded suffixes are strictly totally ordered) -- and oracle/_ref runs the
@@ -267,6 +269,134 @@ int oracle_construct(const uint8_t* text, size_t n, unsigned index_bits, unsigne
     if (rounds_out) *rounds_out = rounds;
     free(b); free(b2);
     return ub == 0 ? 0 : 1; /* 1: loop ended with unfinished buckets (only with the sigma=256 code-0 quirk) */
+}
+
+/* ------------------------------------------- construct_ss: generalized SA (f2) */
+
+/* simple_dstringset::parse at np=1 (include/stringset.hpp:42-80): maximal runs of non-separator characters are the
+ * strings; str_end[i] (i = index in the concatenation WITHOUT separators) = exclusive end of i's string in that
+ * concatenation; cat[] = the concatenation.  Returns sum_sizes. */
+size_t oracle_parse_stringset(const uint8_t* flat, size_t len, uint8_t sep, uint8_t* cat, u64* str_end) {
+    size_t m = 0, i = 0;
+    while (i < len) {
+        while (i < len && flat[i] == sep) ++i;
+        size_t b = m;
+        while (i < len && flat[i] != sep) cat[m++] = flat[i++];
+        for (size_t j = b; j < m; ++j) str_end[j] = (u64)m;
+    }
+    return m;
+}
+
+/* kmer_gen_stringset at np=1 (include/kmer.hpp:269-355): k-mers never read past the end of their string (0 fill) */
+void oracle_kmer_gen_stringset(const uint8_t* cat, const u64* str_end, size_t n, const uint8_t lut[256], unsigned l, unsigned k, u64* out) {
+    for (size_t i = 0; i < n; ++i) {
+        u64 v = 0;
+        for (unsigned j = 0; j < k; ++j) {
+            v <<= l;
+            if (i + j < str_end[i]) v |= lut[cat[i + j]];
+        }
+        out[i] = v;
+    }
+}
+
+/* shift_buckets_ds at np=1 (include/shifting.hpp:374-418): B2[i] = B[i+h] inside i's string, else 0 */
+void oracle_shift_buckets_ds(const u64* b, const u64* str_end, size_t n, size_t h, u64* out) {
+    for (size_t i = 0; i < n; ++i) out[i] = (i + h < str_end[i]) ? b[i + h] : 0;
+}
+
+static unsigned ctz64(u64 x) { return x ? (unsigned)__builtin_ctzll(x) : 64; }
+
+/* initial_kmer_lcp_gsa at np=1 (include/suffix_array.hpp:1404-1441): as initial_kmer_lcp, but equal k-mers that end in
+ * 0 fill (a string ended inside them) have the length of the string's remainder as their LCP */
+void oracle_initial_kmer_lcp_gsa(const u64* b1, const u64* b2, size_t n, unsigned k, unsigned l, unsigned word_bits, u64* lcp) {
+    for (size_t i = 0; i < n; ++i) lcp[i] = (u64)n;
+    if (n) lcp[0] = 0;
+    for (size_t i = 1; i < n; ++i) {
+        u64 l1 = b1[i - 1], l2 = b2[i - 1], r1 = b1[i], r2 = b2[i];
+        if (l1 != r1) {
+            lcp[i] = oracle_lcp_bitwise(l1, r1, k, l, word_bits);
+        } else {
+            unsigned v = k - ctz64(l1) / l;
+            if (v == k) {
+                if (l2 != r2) {
+                    lcp[i] = v + oracle_lcp_bitwise(l2, r2, k, l, word_bits);
+                } else {
+                    if (l2 != 0) v += k - ctz64(l2) / l;
+                    if (v < 2 * k) lcp[i] = v;
+                }
+            } else {
+                lcp[i] = v;
+            }
+        }
+    }
+}
+
+/* rebucket_gsa_kmers / rebucket_gsa at np=1 (include/bucketing.hpp:130-143 on top of rebucket :57-123): two neighbours
+ * share a bucket only if their tuples are equal AND the string has not ended inside them (last character of the
+ * second k-mer non-zero in round 1 -- mask = low l bits --, second rank non-zero later -- mask = all ones). */
+void oracle_rebucket_gsa(u64* v1, const u64* v2, size_t n, u64 mask, u64* unfinished_buckets, u64* unfinished_elements) {
+    if (n == 0) { *unfinished_buckets = *unfinished_elements = 0; return; }
+    int next_diff = 1;
+    for (size_t i = 0; i + 1 < n; ++i) {
+        int set_one = next_diff;
+        next_diff = !(v1[i] == v1[i + 1] && v2[i] == v2[i + 1] && (v2[i] & mask) != 0);
+        v1[i] = set_one ? (u64)i + 1 : 0;
+    }
+    v1[n - 1] = next_diff ? (u64)(n - 1) + 1 : 0;
+    u64 ub = 0, ue = 0;
+    for (size_t i = 1; i < n; ++i) {
+        if (v1[i - 1] > 0 && v1[i] == 0) { ++ub; ++ue; }
+        if (v1[i] == 0) ++ue;
+    }
+    *unfinished_buckets = ub;
+    *unfinished_elements = ue;
+    u64 pre_max = 0;
+    for (size_t i = 0; i < n; ++i) {
+        if (v1[i] == 0) v1[i] = pre_max; else pre_max = v1[i];
+    }
+}
+
+/* suffix_array::construct_ss at np=1 (include/suffix_array.hpp:269-363): generalized suffix / LCP array of the strings
+ * of `flat` (separated by `sep`), alphabet = lut/l as given by the caller (alphabet<char>::from_string).  Positions index
+ * the concatenation without separators; identical suffixes of different strings are ordered by position (the sort is
+ * stable, idxsort_vectors<..., true> :297).  The reference switches to bucket chasing after its first round (:326-334,
+ * construct_msgs_gsa); this restatement keeps doubling with the same tuple / tie / LCP rules (rebucket_bucket_gsa :915-919
+ * and the LCP rule of rebucket_bucket :862-875 are those of rebucket_gsa and resolve_next_lcp), so the results are
+ * the same.  sa/isa/lcp receive sum_sizes entries (lcp may be NULL); returns sum_sizes or < 0. */
+long oracle_construct_ss(const uint8_t* flat, size_t len, uint8_t sep, const uint8_t lut[256], unsigned l, unsigned index_bits, u64* sa, u64* isa,
+                         u64* lcp, unsigned* rounds_out) {
+    uint8_t* cat = (uint8_t*)malloc(len ? len : 1);
+    u64* str_end = (u64*)malloc((len ? len : 1) * sizeof(u64));
+    if (!cat || !str_end) { free(cat); free(str_end); return -1; }
+    const size_t n = oracle_parse_stringset(flat, len, sep, cat, str_end);
+    if (n == 0) { free(cat); free(str_end); return 0; }
+    unsigned k = oracle_optimal_k(l, index_bits, n, 1, 0); /* :274 */
+    u64* b = (u64*)malloc(n * sizeof(u64));
+    u64* b2 = (u64*)malloc(n * sizeof(u64));
+    if (!b || !b2) { free(cat); free(str_end); free(b); free(b2); return -1; }
+    oracle_kmer_gen_stringset(cat, str_end, n, lut, l, k, b); /* :284 */
+    unsigned rounds = 0;
+    u64 ub = 1, ue = n;
+    int have_sa = 0;
+    for (size_t h = k; n > 1 && h < 4 * n + 64; h <<= 1) { /* :292; the chasing loop continues until nothing is active */
+        oracle_shift_buckets_ds(b, str_end, n, h, b2);            /* :296 */
+        if (oracle_idxsort(b, b2, n, sa)) { ub = 2; break; }       /* :300, stable */
+        have_sa = 1;
+        if (lcp) {                                                /* :304-315 */
+            if (h == k) oracle_initial_kmer_lcp_gsa(b, b2, n, k, l, index_bits, lcp);
+            else if (oracle_resolve_next_lcp(b, b2, n, (u64)h, lcp)) { ub = 2; break; }
+        }
+        oracle_rebucket_gsa(b, b2, n, h == k ? (((u64)1 << l) - 1) : ~(u64)0, &ub, &ue); /* :310, :316 */
+        oracle_bulk_permute(b, sa, n, b2);                         /* :325-333 */
+        memcpy(b, b2, n * sizeof(u64));
+        ++rounds;
+        if (ub == 0) break;
+    }
+    if (!have_sa) { sa[0] = 0; b[0] = 1; if (lcp) lcp[0] = 0; ub = 0; }
+    for (size_t i = 0; i < n; ++i) isa[i] = b[i] - 1; /* :358-362 */
+    if (rounds_out) *rounds_out = rounds;
+    free(cat); free(str_end); free(b); free(b2);
+    return ub == 0 ? (long)n : -2;
 }
 
 /* -------------------------------------------------- construct_arr<L> (a13) */

@@ -161,6 +161,57 @@ def construct(text, index_bits=64, k=0, want_lcp=False):
     return dict(sa=sa, isa=isa, lcp=lcp, rounds=rounds.value, rc=rc)
 
 
+def stringset_alphabet(flat, sep=ord("$")):
+    """lut / sigma / bits_per_char of alphabet<char>::from_string over the non-separator characters (test/test_gsa.cpp:86)"""
+    t = _text(flat)
+    return alphabet(t[t != sep])
+
+
+def construct_ss(flat, sep=ord("$"), index_bits=64, want_lcp=True, lut=None, bits_per_char=None):
+    """Port of suffix_array::construct_ss (generalized SA of the `sep`-separated strings) at np=1.
+    Positions index the concatenation without separators.  Returns dict(sa, isa, lcp|None, rounds, n)."""
+    t = _text(flat)
+    if lut is None:
+        lut, _, bits_per_char = stringset_alphabet(t, sep)
+    cap = max(t.size, 1)
+    sa = np.zeros(cap, np.uint64)
+    isa = np.zeros(cap, np.uint64)
+    lcp = np.zeros(cap, np.uint64) if want_lcp else None
+    rounds = C.c_uint()
+    f = port().oracle_construct_ss
+    f.restype = C.c_long
+    m = f(_vp(t), C.c_size_t(t.size), C.c_ubyte(sep), _vp(np.ascontiguousarray(lut, np.uint8)), C.c_uint(bits_per_char), C.c_uint(index_bits),
+          _vp(sa), _vp(isa), _vp(lcp), C.byref(rounds))
+    if m < 0:
+        raise RuntimeError("oracle_construct_ss failed: %d" % m)
+    return dict(sa=sa[:m], isa=isa[:m], lcp=None if lcp is None else lcp[:m], rounds=rounds.value, n=m)
+
+
+def gsa_naive(flat, sep=ord("$")):
+    """The definition the generalized SA must satisfy (test/test_gsa.cpp:97-98 and the closed forms :31-66): suffixes of
+    every string compared as strings (a proper prefix is smaller), ties by position; LCP = common prefix length."""
+    t = bytes(_text(flat))
+    suf = []
+    pos = 0
+    for s in t.split(bytes([sep])):
+        for i in range(len(s)):
+            suf.append((s[i:], pos + i))
+        pos += len(s)
+    suf.sort()
+    m = len(suf)
+    sa = np.array([p for _, p in suf], np.uint64).reshape(m)
+    lcp = np.zeros(m, np.uint64)
+    for q in range(1, m):
+        a, b = suf[q - 1][0], suf[q][0]
+        l = 0
+        while l < len(a) and l < len(b) and a[l] == b[l]:
+            l += 1
+        lcp[q] = l
+    isa = np.zeros(m, np.uint64)
+    isa[sa.astype(np.int64)] = np.arange(m, dtype=np.uint64)
+    return dict(sa=sa, isa=isa, lcp=lcp, n=m)
+
+
 def construct_arr(text, L, index_bits=64):
     t = _text(text)
     n = t.size
@@ -346,6 +397,25 @@ def ref_lc(text, k=0):
     if rc != 0:
         raise RuntimeError("psacref_lc rc=%d" % rc)
     return out
+
+
+def ref_construct_ss(flat, sep=ord("$"), index_bytes=8, alpha_chars=None):
+    """suffix_array<char,index_t,true>::construct_ss of the UNMODIFIED reference at np=1 (oracle/_ref)"""
+    t = _text(flat)
+    if alpha_chars is None:
+        alpha_chars = bytes(np.unique(t[t != sep]).tolist())
+    dt = np.uint32 if index_bytes == 4 else np.uint64
+    cap = max(t.size, 1)
+    sa = np.zeros(cap, dt)
+    isa = np.zeros(cap, dt)
+    lcp = np.zeros(cap, dt)
+    f = ref().psacref_construct_ss
+    f.restype = C.c_long
+    m = f(_vp(t), C.c_size_t(t.size), C.c_char(bytes([sep])), alpha_chars, C.c_size_t(len(alpha_chars)), C.c_int(index_bytes), _vp(sa), _vp(isa),
+          _vp(lcp), C.c_size_t(cap))
+    if m < 0:
+        raise RuntimeError("psacref_construct_ss rc=%d" % m)
+    return dict(sa=sa[:m], isa=isa[:m], lcp=lcp[:m], n=m)
 
 
 def ref_rand_dna(n, seed):

@@ -15,6 +15,7 @@
  *   lcp_from_sa (Kasai checker)                     include/lcp.hpp:46-77
  *   ansv / ansv_sequential                          include/ansv.hpp:47-65, 2042-2051
  *   construct_suffix_tree                           include/suffix_tree.hpp:413-499
+ *   suffix_array<...>::construct_ss (generalized SA) include/suffix_array.hpp:269-363, stringset.hpp:33-152
  */
 #include <mpi.h>
 
@@ -70,6 +71,29 @@ int run_construct(const char* text, size_t n, unsigned k, int fast, int arr_L, v
     }
     return 0;
 }
+
+/* Generalized suffix array of a string set (suffix_array.hpp:269-363): `flat` holds the strings separated by `sep`
+ * (simple_dstringset, stringset.hpp:33-152; runs of separators and leading / trailing ones are skipped); the alphabet is
+ * alphabet<char>::from_string(alpha_chars) as in test/test_gsa.cpp:86.  Outputs have sum_sizes entries (characters that
+ * are not separators); returns that count, or < 0. */
+template <typename index_t>
+long run_construct_ss(const char* flat, size_t len, char sep, const char* alpha_chars, size_t n_alpha, void* sa_out, void* isa_out, void* lcp_out,
+                      size_t cap) {
+    cerr_mute mute(!g_verbose);
+    mxx::comm c;
+    std::string f(flat, len);
+    simple_dstringset ss(f.begin(), f.end(), c, sep);
+    alphabet<char> a = alphabet<char>::from_string(std::string(alpha_chars, n_alpha), c);
+    suffix_array<char, index_t, true> sa(c);
+    sa.construct_ss(ss, a);
+    const size_t m = sa.local_SA.size();
+    if (m > cap) return -3;
+    if (sa_out) std::memcpy(sa_out, sa.local_SA.data(), m * sizeof(index_t));
+    if (isa_out && sa.local_B.size() == m) std::memcpy(isa_out, sa.local_B.data(), m * sizeof(index_t));
+    if (lcp_out && sa.local_LCP.size() == m) std::memcpy(lcp_out, sa.local_LCP.data(), m * sizeof(index_t));
+    return (long)m;
+}
+
 
 } // namespace
 
@@ -258,6 +282,18 @@ int psacref_rand_dna(size_t n, int seed, char* out) {
     std::string s = rand_dna(n, seed);
     std::memcpy(out, s.data(), n);
     return 0;
+}
+
+long psacref_construct_ss(const char* flat, size_t len, char sep, const char* alpha_chars, size_t n_alpha, int index_bytes, void* sa_out, void* isa_out,
+                          void* lcp_out, size_t cap) {
+    try {
+        if (index_bytes == 8) return run_construct_ss<uint64_t>(flat, len, sep, alpha_chars, n_alpha, sa_out, isa_out, lcp_out, cap);
+        if (index_bytes == 4) return run_construct_ss<uint32_t>(flat, len, sep, alpha_chars, n_alpha, sa_out, isa_out, lcp_out, cap);
+        return -1;
+    } catch (const std::exception& e) {
+        std::fprintf(stderr, "psacref_construct_ss: %s\n", e.what());
+        return -10;
+    }
 }
 
 } // extern "C"

@@ -97,6 +97,9 @@ def lib():
         L.psacb200_construct_device.argtypes = cargs
         L.psacb200_construct_alphabet.argtypes = cargs[:6] + [C.c_void_p] + cargs[6:]
         L.psacb200_sort_pairs.argtypes = [C.c_void_p] * 5 + [C.c_size_t] + [C.c_int] * 4
+        ssargs = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint8, C.c_int, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
+        L.psacb200_construct_ss.argtypes = ssargs
+        L.psacb200_construct_ss_device.argtypes = ssargs
         L.psacb200_sort_pairs_host.argtypes = [C.c_void_p] * 3 + [C.c_size_t] + [C.c_int] * 4
         L.psacb200_comm_unique_id.argtypes = [C.c_void_p]
         L.psacb200_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
@@ -221,6 +224,30 @@ class Engine:
             lut = np.ascontiguousarray(lut, np.uint8)
             _check(lib().psacb200_construct_alphabet(self._h, _ptr(t), n, index_bytes, flags, k, _ptr(lut), _ptr(sa), _ptr(isa), _ptr(lcp)))
         return dict(sa=sa, isa=isa, lcp=lcp)
+
+    def construct_ss(self, flat, sep=ord("$"), index_bytes=8, want_lcp=True, want_isa=True, lut=None):
+        """Generalized suffix array of the `sep`-separated strings of `flat` (reference construct_ss, suffix_array.hpp:269-363).
+        Host buffers in, numpy arrays out: dict(sa, isa, lcp, n); positions index the concatenation without separators."""
+        t = _as_text(flat)
+        dt = np.uint32 if index_bytes == 4 else np.uint64
+        cap = max(t.size, 1)
+        sa = np.empty(cap, dt)
+        isa = np.empty(cap, dt) if want_isa else None
+        lcp = np.empty(cap, dt) if want_lcp else None
+        n = C.c_uint64(0)
+        if lut is not None:
+            lut = np.ascontiguousarray(lut, np.uint8)
+        _check(lib().psacb200_construct_ss(self._h, _ptr(t), t.size, C.c_uint8(sep), index_bytes, LCP if want_lcp else 0, _ptr(lut), _ptr(sa),
+                                           _ptr(isa), _ptr(lcp), C.byref(n)))
+        m = n.value
+        return dict(sa=sa[:m], isa=None if isa is None else isa[:m], lcp=None if lcp is None else lcp[:m], n=m)
+
+    def construct_ss_ptr(self, flat_ptr, length, sep, index_bytes, flags, sa_ptr, isa_ptr, lcp_ptr, device=True):
+        """Raw-pointer form of construct_ss; returns the number of non-separator characters."""
+        n = C.c_uint64(0)
+        f = lib().psacb200_construct_ss_device if device else lib().psacb200_construct_ss
+        _check(f(self._h, _ptr(flat_ptr), length, C.c_uint8(sep), index_bytes, flags, None, _ptr(sa_ptr), _ptr(isa_ptr), _ptr(lcp_ptr), C.byref(n)))
+        return n.value
 
     def construct_ptr(self, text_ptr, n, index_bytes, flags, k, sa_ptr, isa_ptr, lcp_ptr, device=False):
         """Raw-pointer form (pinned host buffers or device buffers owned by the caller, e.g. torch tensors)."""
@@ -420,6 +447,16 @@ class SuffixArray:
         self.local_SA, self.local_B, self.local_LCP = r["sa"], r["isa"], r["lcp"]
         if self.construct_lc:
             self.local_Lc = self._eng().lc(t, self.local_SA, self.local_LCP)
+        return self
+
+    def construct_ss(self, flat, sep=ord("$"), lut=None):
+        """reference: construct_ss(simple_dstringset&, alphabet), suffix_array.hpp:269-363 -- generalized SA (+ LCP when the
+        object was created with construct_lcp) of the `sep`-separated strings; n = characters that are not separators"""
+        t = _as_text(flat)
+        r = self._eng().construct_ss(t, sep, self.index_bytes, self.construct_lcp, True, lut)
+        self._text = t[t != sep]
+        self.n = self.local_size = r["n"]
+        self.local_SA, self.local_B, self.local_LCP = r["sa"], r["isa"], r["lcp"]
         return self
 
     def write(self, basename, text=None):

@@ -93,6 +93,30 @@ __device__ __forceinline__ u64 stream_extract(const u64* __restrict__ stream, u6
     return stream_bits(stream, i * (u64)lbits, nbits);
 }
 
+// ---------------------------------------------------------------- generalized suffix array (string sets)
+// In a string-set construction code 0 is the separator: it ends its string, and no comparison runs past it
+// (reference kmer_gen_stringset, include/kmer.hpp:269-355: k-mers are 0-filled behind the end of their string).
+// lowest bit of every lbits-wide field of a word (lbits in {1,2,4,8})
+__host__ __device__ __forceinline__ u64 field_lsb(int lbits) {
+    return lbits == 1 ? ~0ull : lbits == 2 ? 0x5555555555555555ull : lbits == 4 ? 0x1111111111111111ull : 0x0101010101010101ull;
+}
+// the lowest bit of a field is set in the result iff the field of w is zero
+__host__ __device__ __forceinline__ u64 zero_fields(u64 w, int lbits) {
+    u64 nz = w;
+    if (lbits >= 2) nz |= nz >> 1;
+    if (lbits >= 4) nz |= nz >> 2;
+    if (lbits == 8) nz |= nz >> 4;
+    return ~nz & field_lsb(lbits);
+}
+// key of kbits bits (whole characters, right-aligned): everything behind its first zero character is cleared
+__device__ __forceinline__ u64 gsa_mask_key(u64 k, int lbits, int kbits) {
+    u64 z = zero_fields(k, lbits);
+    if (kbits < 64) z &= (1ull << kbits) - 1ull;
+    if (z == 0) return k;
+    const int p = 63 - __clzll((long long)z);  // lowest bit of the first zero character
+    return k & ~((1ull << p) - 1ull);
+}
+
 // ---------------------------------------------------------------- block distribution on the device
 // mxx::blk_dist (reference ext/mxx/include/mxx/partition.hpp:283-331): n elements over p ranks, the first n % p ranks
 // hold one element more.  owner() estimates the quotient with one 32-bit multiply-high and corrects it against the block starts.

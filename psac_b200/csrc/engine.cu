@@ -19,6 +19,7 @@
 #include "sa_kernels.cuh"
 #include "tree_kernels.cuh"
 #include "check_kernels.cuh"
+#include "gsa_kernels.cuh"
 
 using namespace psacb200;
 
@@ -80,7 +81,7 @@ struct psacb200_engine {
     cudaStream_t stream = nullptr;
     size_t device_bytes = 0;
     uint64_t launches = 0;
-    DevBuf text, packed, keys[2], vals[2], vals2, segws, isa, lcp, small, lookback, rk[2], rv[2], rp[2], rh[2], scratch, rep[3], tb[6], alist;
+    DevBuf text, packed, keys[2], vals[2], vals2, segws, isa, lcp, small, lookback, rk[2], rv[2], rp[2], rh[2], scratch, rep[3], tb[6], alist, gsa[5];
     void* nccl_comm = nullptr;  // ncclComm_t of the sharded construction (sharded.cuh), one rank per engine
     void* nccl_comm2 = nullptr; // a split of it for the copy stream (barrier of the SA -> ISA exchange), or null
     static constexpr int COPY_STREAMS = 4;
@@ -159,6 +160,7 @@ struct Alphabet {
     unsigned ref_bits = 0;
     int lbits = 1;
     bool zero_code_used = false;  // sigma = 256 quirk: some character shares code 0 with the end-of-text padding
+    bool gsa = false;             // string set: dense code 0 is the separator, the characters get 1..D (gsa_kernels.cuh)
 };
 
 // reference alphabet<char>::init_mapping_table: codes 1..sigma in byte order, stored in an 8-bit table
@@ -186,7 +188,15 @@ void dense_codes(const u64* hist, Alphabet& a) {
     int rank[256];
     int d = 0;
     for (int v = 0; v < 256; ++v) rank[v] = used[v] ? d++ : 0;
-    for (int c = 0; c < 256; ++c) a.dense.code[c] = hist[c] ? (u8)rank[a.lut[c]] : 0;
+    if (a.gsa) {
+        // (hist[separator] is 0 here: the separator keeps code 0 and matches nothing; a 0 of a caller's LUT cannot be told
+        //  from "unused", so the characters must have non-zero LUT codes)
+        if (used[0]) throw arg_failure{"string set: the alphabet maps a character that occurs to code 0"};
+        for (int c = 0; c < 256; ++c) a.dense.code[c] = hist[c] ? (u8)(rank[a.lut[c]] + 1) : 0;
+        d += 1;
+    } else {
+        for (int c = 0; c < 256; ++c) a.dense.code[c] = hist[c] ? (u8)rank[a.lut[c]] : 0;
+    }
     a.lbits = d <= 2 ? 1 : d <= 4 ? 2 : d <= 16 ? 4 : 8;
 }
 
@@ -317,7 +327,7 @@ void reserve_buffers(psacb200_engine* e, u64 n, size_t key_bytes, bool want_lcp,
 
 template <typename IdxT, typename KeyC>
 void construct_core(psacb200_engine* e, u64 n, int index_bytes, unsigned flags, const Alphabet& alpha, unsigned C, void* sa_out, void* isa_out,
-                    void* lcp_out, bool out_is_host) {
+                    void* lcp_out, bool out_is_host, bool gsa = false) {
     static_assert(sizeof(KeyC) >= sizeof(IdxT), "bucket ids are staged in a key buffer");
     const bool want_lcp = (flags & PSACB200_LCP) != 0;
     cudaStream_t st = e->stream;
@@ -357,6 +367,18 @@ void construct_core(psacb200_engine* e, u64 n, int index_bytes, unsigned flags, 
                                           e->ev_end[PH_PASS1], e->ev_scatter);
         e->scatter_passes = plan_used.npass - 1;
         seg_dense = sw.seg_dense;
+    } else if (gsa) {
+        // string set: keys cut behind the first separator, materialised in text order, then the generic stable LSD sort
+        const int fin = plan.npass & 1;
+        if (ext_sa) vbuf[fin] = reinterpret_cast<IdxT*>(sa_out), vbuf[1 - fin] = e->vals[0].as<IdxT>();
+        gsa_keys_kernel<IdxT><<<grid_for(e, n, 256, 16), 256, 0, st>>>(e->packed.as<u64>(), n, lbits, (int)C * lbits, kbuf[0], vbuf[0]);
+        PSAC_CUDA(cudaGetLastError());
+        cudaEventRecord(e->ev_end[PH_PASS1], st);
+        const bool alt = radix_sort_pairs<u64, IdxT>(e->radix_ws(), kbuf[0], kbuf[1], vbuf[0], vbuf[1], n, 0, (int)C * lbits, st, e->sm_count, &plan_used,
+                                                    &sort_launches);
+        sort_launches += 1;
+        x = alt ? 1 : 0;
+        SA = vbuf[x];
     } else {
         const int fin = (plan.npass - 1) & 1;  // buffer index the last pass writes
         if (ext_sa) vbuf[fin] = reinterpret_cast<IdxT*>(sa_out), vbuf[1 - fin] = e->vals[0].as<IdxT>();
@@ -408,7 +430,8 @@ void construct_core(psacb200_engine* e, u64 n, int index_bytes, unsigned flags, 
     R.isa_lo = 0;
     R.isa_hi = n;
     R.suf_out = nullptr;
-    if (sizeof(KeyC) == 4 || (sizeof(IdxT) == 4 && (!alpha.zero_code_used || !want_lcp))) {
+    R.gsa = gsa ? 1 : 0;
+    if (!gsa && (sizeof(KeyC) == 4 || (sizeof(IdxT) == 4 && (!alpha.zero_code_used || !want_lcp)))) {
         // lean path: heads from the keys alone (sa_kernels.cuh heads_kernel); the suffixes that run past the end of the
         // text are located in the sorted order first
         const u64 T = (n < (u64)C - 1) ? n : (u64)C - 1;
@@ -574,7 +597,7 @@ void construct_core(psacb200_engine* e, u64 n, int index_bytes, unsigned flags, 
 }
 
 // alphabet (a2) + packed text; synchronises once to read the 256-bin histogram
-void prepare_text(psacb200_engine* e, const u8* d_text, u64 n, const uint8_t* user_lut, Alphabet& alpha) {
+void prepare_text(psacb200_engine* e, const u8* d_text, u64 n, const uint8_t* user_lut, Alphabet& alpha, int gsa_sep = -1, u64* n_sep = nullptr) {
     cudaStream_t st = e->stream;
     size_t* tot = &e->device_bytes;
     e->small.reserve(psacb200_engine::small_bytes(), tot);
@@ -587,6 +610,11 @@ void prepare_text(psacb200_engine* e, const u8* d_text, u64 n, const uint8_t* us
     PSAC_CUDA(cudaMemcpyAsync(e->h_pinned + 16, e->byte_hist(), 256 * sizeof(u64), cudaMemcpyDeviceToHost, st));
     e->end(PH_ALPHABET);
     PSAC_CUDA(cudaStreamSynchronize(st));
+    if (gsa_sep >= 0) {  // string set: the separator is no character of the alphabet (alphabet<char>::from_string of the strings)
+        alpha.gsa = true;
+        if (n_sep) *n_sep = e->h_pinned[16 + gsa_sep];
+        e->h_pinned[16 + gsa_sep] = 0;
+    }
     alphabet_from_hist(e->h_pinned + 16, alpha);
     if (user_lut) memcpy(alpha.lut, user_lut, 256);
     dense_codes(e->h_pinned + 16, alpha);
@@ -810,6 +838,124 @@ int guarded(F&& f) {
     }
 }
 
+// ---- generalized suffix array of a string set (gsa_kernels.cuh; reference construct_ss, suffix_array.hpp:269-363)
+template <typename IdxT, typename OutT>
+void gsa_emit(psacb200_engine* e, u64 len, u64 m0, bool want_lcp, const u64* bits, const u64* pre, void* sa_out, void* isa_out, void* lcp_out,
+              bool out_is_host) {
+    cudaStream_t st = e->stream;
+    const u64 n = len - m0;
+    const IdxT* SA = e->gsa[0].as<IdxT>();
+    const IdxT* ISA = e->gsa[1].as<IdxT>();
+    const IdxT* LCP = want_lcp ? e->gsa[2].as<IdxT>() : nullptr;
+    OutT* sa_t = reinterpret_cast<OutT*>(sa_out);
+    OutT* lcp_t = want_lcp ? reinterpret_cast<OutT*>(lcp_out) : nullptr;
+    OutT* isa_t = reinterpret_cast<OutT*>(isa_out);
+    if (out_is_host) {
+        e->scratch.reserve(2 * n * sizeof(OutT) + 64, &e->device_bytes);
+        sa_t = e->scratch.as<OutT>();
+        lcp_t = want_lcp ? sa_t + n : nullptr;
+        isa_t = sa_t;
+    }
+    gsa_emit_sa_kernel<IdxT, OutT><<<grid_for(e, n, 256, 16), 256, 0, st>>>(SA, LCP, m0, len, bits, pre, sa_t, lcp_t);
+    e->launches += 1;
+    PSAC_CUDA(cudaGetLastError());
+    if (out_is_host) {
+        PSAC_CUDA(cudaMemcpyAsync(sa_out, sa_t, n * sizeof(OutT), cudaMemcpyDeviceToHost, st));
+        if (want_lcp) PSAC_CUDA(cudaMemcpyAsync(lcp_out, lcp_t, n * sizeof(OutT), cudaMemcpyDeviceToHost, st));
+    }
+    if (isa_out != nullptr) {
+        gsa_emit_isa_kernel<IdxT, OutT><<<grid_for(e, len, 256, 16), 256, 0, st>>>(ISA, m0, len, bits, pre, isa_t);
+        e->launches += 1;
+        PSAC_CUDA(cudaGetLastError());
+        if (out_is_host) PSAC_CUDA(cudaMemcpyAsync(isa_out, isa_t, n * sizeof(OutT), cudaMemcpyDeviceToHost, st));
+    }
+}
+
+template <typename IdxT>
+void gsa_core(psacb200_engine* e, const u8* d_text, u64 len, u64 m0, u8 sep, int index_bytes, unsigned flags, const Alphabet& alpha, unsigned C,
+              void* sa_out, void* isa_out, void* lcp_out, bool out_is_host) {
+    cudaStream_t st = e->stream;
+    size_t* tot = &e->device_bytes;
+    const bool want_lcp = (flags & PSACB200_LCP) != 0;
+    // SA / ISA / LCP of the flat text (separators included) in engine buffers of the internal index width
+    for (int b = 0; b < (want_lcp ? 3 : 2); ++b) e->gsa[b].reserve(len * sizeof(IdxT) + 64, tot);
+    construct_core<IdxT, u64>(e, len, (int)sizeof(IdxT), flags, alpha, C, e->gsa[0].p, e->gsa[1].p, want_lcp ? e->gsa[2].p : nullptr, false, true);
+    // separator bit vector + separators before every 64-character word
+    e->begin(out_is_host ? PH_D2H : PH_OUTPUT);
+    const u64 nwords = div_up(len, (size_t)64), ntiles = div_up(nwords, (size_t)GS_TILE);
+    e->gsa[3].reserve(nwords * sizeof(u64), tot);
+    e->gsa[4].reserve((nwords + 2 * ntiles + 8) * sizeof(u64), tot);
+    u64* bits = e->gsa[3].as<u64>();
+    u64* pre = e->gsa[4].as<u64>();
+    u64* tile_sum = pre + nwords;
+    u64* tile_dummy = tile_sum + ntiles;  // tile_scan_kernel scans a max array along with the sums
+    gsa_sepbits_kernel<<<grid_for(e, nwords * 32, 256, 16), 256, 0, st>>>(d_text, len, sep, bits, pre, nwords);
+    gsa_scan_reduce_kernel<<<(unsigned)ntiles, GS_THREADS, 0, st>>>(pre, nwords, tile_sum);
+    PSAC_CUDA(cudaMemsetAsync(tile_dummy, 0, ntiles * sizeof(u64), st));
+    tile_scan_kernel<<<1, 1024, 0, st>>>(tile_dummy, tile_sum, ntiles, nullptr);
+    gsa_scan_apply_kernel<<<(unsigned)ntiles, GS_THREADS, 0, st>>>(pre, nwords, tile_sum);
+    e->launches += 4;
+    PSAC_CUDA(cudaGetLastError());
+    if (index_bytes == 8)
+        gsa_emit<IdxT, u64>(e, len, m0, want_lcp, bits, pre, sa_out, isa_out, lcp_out, out_is_host);
+    else
+        gsa_emit<IdxT, u32>(e, len, m0, want_lcp, bits, pre, sa_out, isa_out, lcp_out, out_is_host);
+    e->mark("gsa_output");
+    e->end(out_is_host ? PH_D2H : PH_OUTPUT);
+}
+
+int gsa_entry(psacb200_engine* e, const u8* text, bool text_is_host, size_t len, uint8_t sep, int index_bytes, unsigned flags, const uint8_t* lut,
+              void* sa_out, void* isa_out, void* lcp_out, uint64_t* n_out) {
+    if (!e) {
+        set_last_error("null engine");
+        return PSACB200_ERR_ARG;
+    }
+    return guarded([&]() -> int {
+        if (index_bytes != 4 && index_bytes != 8) throw arg_failure{"index_bytes must be 4 or 8"};
+        if (!n_out) throw arg_failure{"null n_out"};
+        if (len > 0 && (!text || !sa_out)) throw arg_failure{"null text / sa_out"};
+        if ((flags & PSACB200_LCP) && len > 0 && !lcp_out) throw arg_failure{"PSACB200_LCP set but lcp_out is null"};
+        if (index_bytes == 4 && (u64)len >= (1ull << 32)) throw arg_failure{"32-bit index too small for this text"};
+        if ((u64)len >= (1ull << 40)) throw arg_failure{"n too large"};
+        PSAC_CUDA(cudaSetDevice(e->device));
+        memset(&e->stats, 0, sizeof(e->stats));
+        memset(e->ev_used, 0, sizeof(e->ev_used));
+        e->scatter_passes = 0;
+        e->tr_n = 0;
+        *n_out = 0;
+        if (len == 0) return PSACB200_OK;
+        e->begin(PH_TOTAL);
+        e->mark("begin");
+        const u8* d_text = text;
+        if (text_is_host) {
+            e->begin(PH_H2D);
+            e->text.reserve(len + 64, &e->device_bytes);
+            PSAC_CUDA(cudaMemcpyAsync(e->text.p, text, len, cudaMemcpyHostToDevice, e->stream));
+            e->end(PH_H2D);
+            d_text = e->text.as<u8>();
+        }
+        Alphabet alpha;
+        u64 m0 = 0;
+        prepare_text(e, d_text, len, lut, alpha, (int)sep, &m0);
+        const u64 n = (u64)len - m0;
+        *n_out = n;
+        e->stats.n = n;
+        if (n > 0) {
+            // separators use a code of their own, so only part of the code space occurs in a key: take the widest key
+            const unsigned C = std::max(1u, ((u64)len >= 65536 ? 64u : 32u) / (unsigned)alpha.lbits);
+            e->stats.key_chars = C;
+            if ((u64)len <= (1ull << 32))
+                gsa_core<u32>(e, d_text, len, m0, sep, index_bytes, flags, alpha, C, sa_out, isa_out, lcp_out, text_is_host);
+            else
+                gsa_core<u64>(e, d_text, len, m0, sep, index_bytes, flags, alpha, C, sa_out, isa_out, lcp_out, text_is_host);
+        }
+        e->end(PH_TOTAL);
+        PSAC_CUDA(cudaStreamSynchronize(e->stream));
+        fill_phase_stats(e);
+        return PSACB200_OK;
+    });
+}
+
 template <typename KeyT>
 bool sort_dispatch_val(psacb200_engine* e, void* k, void* ka, void* v, void* va, size_t n, int val_bytes, int b0, int b1, uint64_t* sl) {
     RadixWorkspace ws = e->radix_ws();
@@ -932,7 +1078,7 @@ void psacb200_destroy(psacb200_engine* e) {
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->stream);
     DevBuf* all[] = {&e->text, &e->packed, &e->keys[0], &e->keys[1], &e->vals[0], &e->vals[1], &e->vals2, &e->segws, &e->isa, &e->lcp, &e->small, &e->lookback,
-                     &e->rk[0], &e->rk[1], &e->rv[0], &e->rv[1], &e->rp[0], &e->rp[1], &e->rh[0], &e->rh[1], &e->scratch, &e->rep[0], &e->rep[1], &e->rep[2], &e->tb[0], &e->tb[1], &e->tb[2], &e->tb[3], &e->tb[4], &e->tb[5], &e->alist};
+                     &e->rk[0], &e->rk[1], &e->rv[0], &e->rv[1], &e->rp[0], &e->rp[1], &e->rh[0], &e->rh[1], &e->scratch, &e->rep[0], &e->rep[1], &e->rep[2], &e->tb[0], &e->tb[1], &e->tb[2], &e->tb[3], &e->tb[4], &e->tb[5], &e->alist, &e->gsa[0], &e->gsa[1], &e->gsa[2], &e->gsa[3], &e->gsa[4]};
     for (DevBuf* b : all) b->release(nullptr);
     for (int i = 0; i < PH_COUNT; ++i) {
         cudaEventDestroy(e->ev_begin[i]);
@@ -1064,6 +1210,16 @@ int psacb200_construct_alphabet(psacb200_engine* e, const uint8_t* text, size_t 
 int psacb200_construct_device(psacb200_engine* e, const uint8_t* d_text, size_t n, int index_bytes, unsigned flags, unsigned k, void* d_sa, void* d_isa,
                               void* d_lcp) {
     return construct_entry(e, d_text, false, n, index_bytes, flags, k, nullptr, d_sa, d_isa, d_lcp);
+}
+
+int psacb200_construct_ss(psacb200_engine* e, const uint8_t* flat, size_t len, uint8_t sep, int index_bytes, unsigned flags, const uint8_t* lut,
+                          void* sa_out, void* isa_out, void* lcp_out, uint64_t* n_out) {
+    return gsa_entry(e, flat, true, len, sep, index_bytes, flags, lut, sa_out, isa_out, lcp_out, n_out);
+}
+
+int psacb200_construct_ss_device(psacb200_engine* e, const uint8_t* d_flat, size_t len, uint8_t sep, int index_bytes, unsigned flags, const uint8_t* lut,
+                                 void* d_sa, void* d_isa, void* d_lcp, uint64_t* n_out) {
+    return gsa_entry(e, d_flat, false, len, sep, index_bytes, flags, lut, d_sa, d_isa, d_lcp, n_out);
 }
 
 int psacb200_sort_pairs(psacb200_engine* e, void* d_keys, void* d_keys_alt, void* d_vals, void* d_vals_alt, size_t n, int key_bytes, int val_bytes,

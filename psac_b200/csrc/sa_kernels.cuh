@@ -87,7 +87,8 @@ __global__ void __launch_bounds__(256) pack_text_kernel(const u8* __restrict__ t
 // 0, the code of "past the end"), where its LCP counts matches between 0xFF and the zero padding; then the
 // comparison runs over the zero-padded sequences instead of stopping at the end of the shorter suffix.
 __device__ __forceinline__ u64 stream_lcp(const u64* __restrict__ stream, u64 n, int lbits, u64 a, u64 b, u64 off, bool padded) {
-    const int cpw = 64 / lbits;
+    const int lsh = 31 - __clz(lbits);  // lbits is 1, 2, 4 or 8: divide by shifting
+    const int cpw = 64 >> lsh;
     u64 l = off;
     while (true) {
         const bool ina = a + l < n, inb = b + l < n;
@@ -97,7 +98,7 @@ __device__ __forceinline__ u64 stream_lcp(const u64* __restrict__ stream, u64 n,
         const u64 wb = inb ? stream_extract(stream, b + l, lbits, 64) : 0;
         const u64 x = wa ^ wb;
         if (x) {
-            l += (u64)(__clzll((long long)x) / lbits);
+            l += (u64)(__clzll((long long)x) >> lsh);
             break;
         }
         l += cpw;
@@ -106,6 +107,24 @@ __device__ __forceinline__ u64 stream_lcp(const u64* __restrict__ stream, u64 n,
     const u64 la = n - a, lb = n - b;
     const u64 cap = la < lb ? la : lb;
     return l < cap ? l : cap;
+}
+
+// string sets (generalized SA): code 0 is the separator and never matches, so the comparison stops at the first separator of
+// either suffix as well as at the first difference (the stream is zero behind the text)
+__device__ __forceinline__ u64 stream_lcp_gsa(const u64* __restrict__ stream, u64 n, int lbits, u64 a, u64 b, u64 off) {
+    const int lsh = 31 - __clz(lbits);
+    u64 l = off;
+    while (true) {
+        const u64 wa = a + l < n ? stream_extract(stream, a + l, lbits, 64) : 0;
+        const u64 wb = b + l < n ? stream_extract(stream, b + l, lbits, 64) : 0;
+        const u64 stop = (wa ^ wb) | zero_fields(wa, lbits);
+        if (stop) {
+            l += (u64)(__clzll((long long)stop) >> lsh);
+            break;
+        }
+        l += (u64)(64 >> lsh);
+    }
+    return l;
 }
 
 // ------------------------------------------------------------------ block-distributed ISA in peer-visible memory
@@ -170,6 +189,10 @@ struct ResolveArgs {
     PeerIsa pisa;         // pisa.p > 0: ISA[s] = isa_add + bucket goes to pisa.at(s) instead of isa[]
     u64 isa_add;          // first SA position of this rank (bucket ids are global positions)
     WordIdx widx;         // widx.lb > 0: sa[] holds sort words, the suffix is stored as its (owner, local index) field
+    void* lcp_main;       // as in HeadsArgs: LCP of positions [main_lo, main_hi) goes to lcp_main[pos], the rest to lcp[pos]
+    u64 main_lo, main_hi;
+    int gsa;              // string set (reference construct_ss): code 0 separates strings; round-0 keys are cut at their first
+                          // separator, equal keys that contain one are finished (rebucket_gsa_kmers, bucketing.hpp:137-143)
 };
 
 constexpr int RES_THREADS = 256;
@@ -257,6 +280,7 @@ __global__ void __launch_bounds__(RES_THREADS) resolve_kernel(ResolveArgs A) {
         } else {
             hd = key[i + 1] != key[i];
             if (FIRST) hd = hd || all_tail || suf[i + 1] > tail_from || suf[i] > tail_from;
+            if (FIRST && A.gsa) hd = hd || (key[i + 1] & ((1ull << A.lbits) - 1ull)) == 0;  // the string ended inside the key
         }
         head[i] = hd;
     }
@@ -353,8 +377,11 @@ __global__ void __launch_bounds__(RES_THREADS) resolve_kernel(ResolveArgs A) {
             } else if (FIRST) {
                 const u64 sp = suf[i];
                 const u64 x = key[i] ^ key[i + 1];
-                u64 c = x ? (u64)(__clzll((long long)(x << (64 - nbits))) / A.lbits) : (u64)A.C;
-                if (A.padded_lcp) {
+                u64 c = x ? (u64)(__clzll((long long)(x << (64 - nbits))) >> (31 - __clz(A.lbits))) : (u64)A.C;
+                if (A.gsa) {
+                    // equal keys: the common prefix ends where the string does (initial_kmer_lcp_gsa, suffix_array.hpp:1404-1441)
+                    if (!x) c = key[i] ? (u64)A.C - (u64)((__ffsll((long long)key[i]) - 1) >> (31 - __clz(A.lbits))) : 0;
+                } else if (A.padded_lcp) {
                     if (!x) c = stream_lcp(A.stream, n, A.lbits, sp, s, (u64)A.C, true);  // equal keys split by the end-of-text rule
                 } else {
                     const u64 la = n - sp, lb = n - s;
@@ -364,7 +391,10 @@ __global__ void __launch_bounds__(RES_THREADS) resolve_kernel(ResolveArgs A) {
                 lcp[q] = (IdxT)c;
             } else if ((key[i] >> A.kbits) == (key[i + 1] >> A.kbits)) {
                 // same old bucket, different rank of suffix+h: the first h characters agree
-                lcp[pos[i] - A.sa_lo] = (IdxT)stream_lcp(A.stream, n, A.lbits, suf[i], s, A.h, A.padded_lcp != 0);
+                const u64 pr = pos[i] - A.sa_lo;
+                IdxT* dst = (A.lcp_main != nullptr && pr >= A.main_lo && pr < A.main_hi) ? reinterpret_cast<IdxT*>(A.lcp_main) : lcp;
+                dst[pr] = (IdxT)(A.gsa ? stream_lcp_gsa(A.stream, n, A.lbits, suf[i], s, A.h)
+                                       : stream_lcp(A.stream, n, A.lbits, suf[i], s, A.h, A.padded_lcp != 0));
             }
         }
         const bool unresolved = !(head[i] && head[i + 1]);
@@ -506,6 +536,8 @@ struct HeadsArgs {
     u64* agg_sum;          // per tile: unresolved elements / exclusive prefix
     u64 pos_base;          // sharded construction: SA position of local element 0 (bucket ids and positions are global)
     const u64* halo;       // sharded construction: {key, suffix} of the last element of the previous shard, or null
+    void* lcp_main;        // sharded: positions [main_lo, main_hi) of this rank's range lie inside its OWN output block; their LCP
+    u64 main_lo, main_hi;  //          goes straight to lcp_main[q] (the caller's block, pre-offset), only the rest to lcp[q]
     int kbits;             // bits of the complete key when it is not C whole characters (0: C * lbits)
     int word_shift;        // WORD: the keys are 64-bit words [carried key | suffix index field]: the key is word >> word_shift,
     WordIdx widx;          //       the suffix index widx.decode(word) (vals is not read)
@@ -727,11 +759,12 @@ __global__ void __launch_bounds__(HD_THREADS) heads_kernel(HeadsArgs A) {
     }
     if (A.lcp != nullptr) {
         const int nbits = A.kbits ? A.kbits : A.C * A.lbits;
+        const int lsh = 31 - __clz(A.lbits);  // lbits is 1, 2, 4 or 8: divide by shifting
         u32 l[HD_ITEMS];
 #pragma unroll
         for (int i = 0; i < HD_ITEMS; ++i) {
             const u64 x = key[i] ^ key[i + 1];
-            l[i] = x ? (u32)(__clzll((long long)(x << (64 - nbits))) / A.lbits) : (u32)A.C;
+            l[i] = x ? (u32)(__clzll((long long)(x << (64 - nbits))) >> lsh) : (u32)A.C;
         }
         if (s_has_tail) {
             for (u32 t = 0; t < s_tails.count; ++t) {
@@ -756,11 +789,25 @@ __global__ void __launch_bounds__(HD_THREADS) heads_kernel(HeadsArgs A) {
         // every position becomes a head in exactly one round and gets its LCP then: entries of non-heads written here
         // are overwritten by the round that splits them, so the whole run can leave as 128-bit stores
         PosT* lcp = reinterpret_cast<PosT*>(A.lcp);
-        if (full_run && sizeof(PosT) == 4) {
+        bool routed = false;
+        if (A.lcp_main != nullptr) {
+            PosT* lm = reinterpret_cast<PosT*>(A.lcp_main);
+            if (q0 >= A.main_lo && q0 + HD_ITEMS <= A.main_hi) {
+                lcp = lm;  // the whole run lies in my own output block
+            } else if (q0 + HD_ITEMS > A.main_lo && q0 < A.main_hi) {
+                routed = true;  // the run straddles the edge of the block
+#pragma unroll
+                for (int i = 0; i < HD_ITEMS; ++i)
+                    if (q0 + i < m) ((q0 + i >= A.main_lo && q0 + i < A.main_hi) ? lm : lcp)[q0 + i] = (PosT)l[i];
+            }
+        }
+        const bool vec_ok = (reinterpret_cast<size_t>(lcp + q0) & 15) == 0;
+        if (routed) {
+        } else if (full_run && vec_ok && sizeof(PosT) == 4) {
             uint4* ol = reinterpret_cast<uint4*>(lcp + q0);
 #pragma unroll
             for (int c = 0; c < HD_ITEMS / 4; ++c) __stcs(ol + c, make_uint4(l[4 * c], l[4 * c + 1], l[4 * c + 2], l[4 * c + 3]));
-        } else if (full_run) {
+        } else if (full_run && vec_ok) {
             ulonglong2* ol = reinterpret_cast<ulonglong2*>(lcp + q0);
 #pragma unroll
             for (int c = 0; c < HD_ITEMS / 2; ++c) __stcs(ol + c, make_ulonglong2((u64)l[2 * c], (u64)l[2 * c + 1]));

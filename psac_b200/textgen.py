@@ -78,6 +78,26 @@ def periodic_text(unit, reps):
 
 
 # ---------------------------------------------------------------- same generators as torch ops (any device)
+def random_stringset(nstrings, max_len, seed, alphabet=b"ACGT", sep=b"$", repeat_unit=0):
+    """Flat text of `nstrings` strings (lengths 1..max_len, own PRNG) separated by `sep` -- the input of the reference's
+    simple_dstringset (include/stringset.hpp:33-152).  repeat_unit > 0: every string is a power of a short random unit
+    (many identical suffixes across strings, long common prefixes)."""
+    al = np.frombuffer(alphabet, np.uint8)
+    r = splitmix64(seed, np.arange(nstrings, dtype=np.uint64))
+    lens = (r % np.uint64(max_len)).astype(np.int64) + 1
+    out = []
+    for i in range(nstrings):
+        L = int(lens[i])
+        if repeat_unit > 0:
+            u = int(splitmix64(seed + 7, np.array([i], np.uint64))[0] % np.uint64(repeat_unit)) + 1
+            unit = al[(splitmix64(seed + 11 + i, np.arange(u, dtype=np.uint64)) % np.uint64(al.size)).astype(np.int64)]
+            s = np.tile(unit, L // u + 1)[:L]
+        else:
+            s = al[(splitmix64(seed + 13 + i, np.arange(L, dtype=np.uint64)) % np.uint64(al.size)).astype(np.int64)]
+        out.append(s.tobytes())
+    return np.frombuffer(sep.join(out), np.uint8).copy()
+
+
 def _t_lsr(z, k):
     """logical right shift of int64 tensors (torch's >> is arithmetic)"""
     return (z >> k) & ((1 << (64 - k)) - 1)

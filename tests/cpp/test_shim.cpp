@@ -67,6 +67,18 @@ int main() {
         sc.construct(s.begin(), s.end(), true, sa.alpha, 2);
         for (size_t i = 0; i < 11; ++i)
             if (sc.local_SA[i] != golden[i] || sc.local_LCP[i] != lcp[i]) return fail("alphabet overload");
+        // generalized suffix array of a string set (reference test/test_gsa.cpp:71-103 "SimpleTiny")
+        {
+            const std::string flat = "abab$baba";
+            psacb200::simple_dstringset ss(flat.begin(), flat.end(), c);
+            psacb200::alphabet a = psacb200::alphabet::from_string("ab", c);
+            psacb200::suffix_array<char, uint64_t, true> sg(c);
+            sg.construct_ss(ss, a);
+            const uint64_t ex_gsa[8] = {7, 2, 5, 0, 3, 6, 1, 4}, ex_lcp[8] = {0, 1, 2, 3, 0, 1, 2, 3};  // test_gsa.cpp:97-98
+            if (sg.n != 8 || sg.local_SA.size() != 8 || sg.local_LCP.size() != 8) return fail("GSA sizes");
+            for (size_t i = 0; i < 8; ++i)
+                if (sg.local_SA[i] != ex_gsa[i] || sg.local_LCP[i] != ex_lcp[i] || sg.local_B[sg.local_SA[i]] != i) return fail("GSA SimpleTiny");
+        }
     } catch (const std::runtime_error& e) {
         if (std::strstr(e.what(), "no CUDA device") || std::strstr(e.what(), "CUDA")) {
             std::fprintf(stderr, "no GPU: %s\n", e.what());

@@ -61,7 +61,28 @@ def main():
             d["l_%d_%d" % (lt, rt)] = l
             d["r_%d_%d" % (lt, rt)] = r
     np.savez_compressed(os.path.join(OUT, "ansv137.npz"), **d)
+    gsa_cases()
+
+
+def gsa_case(name, flat, index_bytes):
+    """generalized SA / LCP of a string set from the reference's construct_ss (suffix_array.hpp:269-363)"""
+    flat = np.ascontiguousarray(np.frombuffer(flat, np.uint8) if isinstance(flat, bytes) else flat, np.uint8)
+    r = O.ref_construct_ss(flat, ord("$"), index_bytes)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), flat=flat, sa=r["sa"], isa=r["isa"], lcp=r["lcp"], index_bytes=np.int32(index_bytes))
+    print(name, flat.size, r["n"], "ok")
+
+
+def gsa_cases():
+    gsa_case("gsa_tiny_u64", b"abab$baba", 8)                                                          # test_gsa.cpp:71-103
+    gsa_case("gsa_incabc10_u64", b"$".join(b"abc" * (i + 1) for i in range(10)), 8)                     # test_gsa.cpp:160-163
+    gsa_case("gsa_incaf50_u32", b"$".join(b"abcdef" * (i + 1) for i in range(50)), 4)                   # test_gsa.cpp:165-168
+    gsa_case("gsa_dna_reads_u64", G.random_stringset(300, 150, 31), 8)
+    gsa_case("gsa_dna_repeats_u32", G.random_stringset(200, 400, 32, repeat_unit=5), 4)
+    gsa_case("gsa_ragged_seps_u64", b"$$" + G.random_stringset(40, 30, 33, alphabet=b"ab").tobytes().replace(b"$", b"$$$") + b"$", 8)
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "gsa":
+        gsa_cases()
+    else:
+        main()

@@ -66,7 +66,7 @@ def test_optimal_k():
 def _golden_cases(golden_dir):
     for f in sorted(glob.glob(os.path.join(golden_dir, "*.npz"))):
         d = np.load(f)
-        if "sa" in d.files:
+        if "sa" in d.files and "text" in d.files:  # (gsa_*.npz: string sets, tests/test_gsa.py)
             yield os.path.basename(f), d
 
 
