@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """psac-b200 benchmark: suffixes/s of SA+LCP construction on synthetic text (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--config 2|1|3|5] [--log2n L]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--config 2|1|3|5|6] [--log2n L]
 
 One "step" = one complete construction (the hot path of BASELINE.json) over one synthetic text.
 
@@ -11,6 +11,7 @@ One "step" = one complete construction (the hot path of BASELINE.json) over one 
   --config 1: configs[1], 2^30 DNA, SA only, 32-bit index, one GPU (also reported as the extra key "configs1" of the default line)
   --config 3: configs[3], 2^32 random bytes (|Sigma| = 256, last byte != 0xFF), SA only, 64-bit index, one GPU
   --config 5: configs[4], DNA, SA+LCP + ANSV + suffix-tree child table, 2^29 characters per GPU
+  --config 6: generalized SA+LCP of a string set (reference construct_ss): 2^28 bytes of '$'-separated DNA reads, one GPU (bench_gsa.py)
 
   value     : suffixes/s, text resident in HBM, outputs left in HBM (psacb200_construct_device / _construct_sharded)
   e2e       : suffixes/s through the reference-facing C-ABI call with HOST (pinned) buffers: H2D of the text and D2H of
@@ -163,7 +164,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 5])
+    ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 5, 6])
     ap.add_argument("--log2n", type=int, default=0, help="log2 of the characters per GPU (default: the config's size)")
     ap.add_argument("--cpu-log2n", type=int, default=25, help="log2 of the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -179,6 +180,9 @@ def main():
     if cfg == 5:
         from bench_tree import main_tree  # configs[4]: SA + LCP + ANSV + suffix tree
         return main_tree(args, rank, world, local_rank)
+    if cfg == 6:
+        from bench_gsa import main_gsa  # generalized suffix array of a string set
+        return main_gsa(args, rank, world, local_rank)
     log2n = args.log2n or {1: 30, 2: 30, 3: 32}[cfg]
     n = 1 << log2n
     ngpu = max(world, args.gpus)

@@ -431,14 +431,21 @@ void construct_core(psacb200_engine* e, u64 n, int index_bytes, unsigned flags, 
     R.isa_hi = n;
     R.suf_out = nullptr;
     R.gsa = gsa ? 1 : 0;
-    if (!gsa && (sizeof(KeyC) == 4 || (sizeof(IdxT) == 4 && (!alpha.zero_code_used || !want_lcp)))) {
+    const bool lean = !gsa && (sizeof(KeyC) == 4 || (sizeof(IdxT) == 4 && (!alpha.zero_code_used || !want_lcp)));
+    // 64-bit caller, 32-bit engine: the LCP entries are written 64 bits wide where they are produced (no widening pass)
+    const bool lcp_wide = lean && ext_lcp && index_bytes == 8 && sizeof(IdxT) == 4 && !getenv("PSACB200_NO_WIDE_LCP");
+    // The SA -> ISA step scatters POSITIONS generated on the fly instead of a bucket-id array (a resolved suffix's bucket id
+    // is its position); the unresolved ones are fixed up from their list afterwards.  Saves one written and one read array.
+    bool implicit_pos = lean && partitioned && !getenv("PSACB200_NO_IMPLICIT_POS");
+    R.lcp_wide = lcp_wide ? 1 : 0;
+    HeadsArgs H{};
+    if (lean) {
         // lean path: heads from the keys alone (sa_kernels.cuh heads_kernel); the suffixes that run past the end of the
         // text are located in the sorted order first
         const u64 T = (n < (u64)C - 1) ? n : (u64)C - 1;
         static_assert(sizeof(TailList) <= 1024, "TailList must fit its slot in the small buffer");
         TailList* tails = reinterpret_cast<TailList*>(e->tail_list());
         tail_positions_kernel<KeyC><<<1, 64, 0, st>>>(kbuf[x], n, seg_dense, carried_bits, e->packed.as<u64>(), n, T, lbits, (int)C * lbits, 0, 0u, 1u, tails);
-        HeadsArgs H{};
         H.keys = kbuf[x];
         H.seg_dense = seg_dense;
         H.seg_shift = carried_bits;
@@ -456,9 +463,10 @@ void construct_core(psacb200_engine* e, u64 n, int index_bytes, unsigned flags, 
         H.lbits = lbits;
         H.C = (int)C;
         H.tails = tails;
-        H.bucket_out = bucket;
+        H.bucket_out = implicit_pos ? nullptr : bucket;
         H.isa = partitioned ? nullptr : ISA;
         H.lcp = LCP;
+        H.lcp_wide = lcp_wide ? 1 : 0;
         H.pos_out = R.pos_out;
         H.head_out = R.head_out;
         H.suf_out = nullptr;
@@ -496,6 +504,17 @@ void construct_core(psacb200_engine* e, u64 n, int index_bytes, unsigned flags, 
         e->rp[0].reserve(m * sizeof(IdxT), tot);
         e->rh[0].reserve(m, tot);
         if (m > R.cap) {
+            if (implicit_pos) {
+                // repetitive text: the list overflowed, so the bucket ids are needed after all -- apply phase once more
+                if constexpr (sizeof(IdxT) == 4) {
+                    H.bucket_out = bucket;
+                    H.lcp = nullptr;
+                    heads_kernel<KeyC, u32, 1><<<(unsigned)div_up(n, (size_t)HD_TILE), HD_THREADS, 0, st>>>(H);
+                    e->launches += 1;
+                    PSAC_CUDA(cudaGetLastError());
+                }
+                implicit_pos = false;
+            }
             e->rp[1].reserve(m * sizeof(IdxT), tot);
             e->rh[1].reserve(m, tot);
             const u64 ntiles = div_up(n, (size_t)RES_TILE);
@@ -517,12 +536,35 @@ void construct_core(psacb200_engine* e, u64 n, int index_bytes, unsigned flags, 
         RadixWorkspace ws = e->radix_ws();
         IdxT* part_suffix = vscratch;
         IdxT* part_bucket = reinterpret_cast<IdxT*>(kbuf[x]);  // the sorted keys are dead after resolve
-        ArraySrc<IdxT, IdxT> src{SA, bucket, nullptr, shift, (u32)(RADIX - 1), (IdxT)0};
-        launch_pass<ArraySrc<IdxT, IdxT>, IdxT, false>(ws, src, part_suffix, part_bucket, nullptr, n, st);
+        if (implicit_pos) {
+            PosSrc<IdxT, IdxT> src{SA, shift, (u32)(RADIX - 1)};
+            launch_pass<PosSrc<IdxT, IdxT>, IdxT, false>(ws, src, part_suffix, part_bucket, nullptr, n, st);
+        } else {
+            ArraySrc<IdxT, IdxT> src{SA, bucket, nullptr, shift, (u32)(RADIX - 1), (IdxT)0};
+            launch_pass<ArraySrc<IdxT, IdxT>, IdxT, false>(ws, src, part_suffix, part_bucket, nullptr, n, st);
+        }
         e->mark("isa_window");
         isa_scatter_kernel<IdxT><<<(unsigned)div_up(n, (size_t)4096), 256, 0, st>>>(part_suffix, part_bucket, ISA, n);
         e->launches += LAUNCHES_PER_PASS + 1;
         PSAC_CUDA(cudaGetLastError());
+        if (implicit_pos && m > 0) {
+            // ISA entries of the unresolved suffixes: the position of their bucket's head (round_keys_kernel FIXUP)
+            const u64 ntiles = div_up(m, (size_t)RES_TILE);
+            RoundKeyArgs K{};
+            K.pos = e->rp[1].p;
+            K.head = e->rh[1].as<u8>();
+            K.sa = SA;
+            K.isa = ISA;
+            K.m = m;
+            K.n = n;
+            K.lb_max = e->lookback.as<u64>();
+            K.tile_counter = e->counters() + 17;
+            PSAC_CUDA(cudaMemsetAsync(K.lb_max, 0, ntiles * sizeof(u64), st));
+            PSAC_CUDA(cudaMemsetAsync(K.tile_counter, 0, sizeof(u32), st));
+            round_keys_kernel<IdxT, true><<<(unsigned)ntiles, RES_THREADS, 0, st>>>(K);
+            e->launches += 1;
+            PSAC_CUDA(cudaGetLastError());
+        }
     }
     e->mark("isa_scatter");
     e->end(PH_ISA);
@@ -591,7 +633,7 @@ void construct_core(psacb200_engine* e, u64 n, int index_bytes, unsigned flags, 
     e->begin(out_is_host ? PH_D2H : PH_OUTPUT);
     emit<IdxT>(e, SA, sa_out, n, index_bytes, out_is_host);
     emit<IdxT>(e, ISA, isa_out, n, index_bytes, out_is_host);
-    if (want_lcp) emit<IdxT>(e, LCP, lcp_out, n, index_bytes, out_is_host);
+    if (want_lcp && !lcp_wide) emit<IdxT>(e, LCP, lcp_out, n, index_bytes, out_is_host);
     e->mark("output");
     e->end(out_is_host ? PH_D2H : PH_OUTPUT);
 }
@@ -915,7 +957,7 @@ int gsa_entry(psacb200_engine* e, const u8* text, bool text_is_host, size_t len,
         if (!n_out) throw arg_failure{"null n_out"};
         if (len > 0 && (!text || !sa_out)) throw arg_failure{"null text / sa_out"};
         if ((flags & PSACB200_LCP) && len > 0 && !lcp_out) throw arg_failure{"PSACB200_LCP set but lcp_out is null"};
-        if (index_bytes == 4 && (u64)len >= (1ull << 32)) throw arg_failure{"32-bit index too small for this text"};
+        if (index_bytes == 4 && (u64)len + 1 >= (1ull << 32)) throw arg_failure{"32-bit index too small for this text"};
         if ((u64)len >= (1ull << 40)) throw arg_failure{"n too large"};
         PSAC_CUDA(cudaSetDevice(e->device));
         memset(&e->stats, 0, sizeof(e->stats));
@@ -926,13 +968,31 @@ int gsa_entry(psacb200_engine* e, const u8* text, bool text_is_host, size_t len,
         if (len == 0) return PSACB200_OK;
         e->begin(PH_TOTAL);
         e->mark("begin");
+        // The flat text must END with a separator: the end of the text would otherwise rank before every separator in the
+        // doubling rounds, while the last string's suffixes belong behind their equals (ties are ordered by position).
         const u8* d_text = text;
+        bool append = false;
         if (text_is_host) {
+            append = text[len - 1] != sep;
             e->begin(PH_H2D);
             e->text.reserve(len + 64, &e->device_bytes);
             PSAC_CUDA(cudaMemcpyAsync(e->text.p, text, len, cudaMemcpyHostToDevice, e->stream));
             e->end(PH_H2D);
             d_text = e->text.as<u8>();
+        } else {
+            u8* last = reinterpret_cast<u8*>(e->h_pinned);
+            PSAC_CUDA(cudaMemcpyAsync(last, text + len - 1, 1, cudaMemcpyDeviceToHost, e->stream));
+            PSAC_CUDA(cudaStreamSynchronize(e->stream));
+            append = *last != sep;
+            if (append) {
+                e->text.reserve(len + 64, &e->device_bytes);
+                PSAC_CUDA(cudaMemcpyAsync(e->text.p, text, len, cudaMemcpyDeviceToDevice, e->stream));
+                d_text = e->text.as<u8>();
+            }
+        }
+        if (append) {
+            PSAC_CUDA(cudaMemsetAsync(e->text.as<u8>() + len, (int)sep, 1, e->stream));
+            len += 1;
         }
         Alphabet alpha;
         u64 m0 = 0;

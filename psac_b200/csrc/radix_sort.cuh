@@ -107,6 +107,24 @@ struct ArraySrc {
     __device__ __forceinline__ u8 load_aux(size_t g, Stage) const { return ld_stream(ain + g); }
 };
 
+// (suffix, position) pairs of the SA -> ISA step: the key is the suffix index read from the sorted array, the value its
+// position g in that array -- generated, not read
+template <typename KeyT, typename ValT>
+struct PosSrc {
+    using Stage = KeyT;
+    using Out = KeyT;
+    static constexpr bool FROM_TEXT = false;
+    static constexpr bool PEER = false;
+    const KeyT* __restrict__ kin;
+    int shift;
+    u32 mask;
+    __device__ __forceinline__ Stage load_key(size_t g) const { return ld_stream(kin + g); }
+    __device__ __forceinline__ u32 digit(Stage k) const { return (u32)(k >> shift) & mask; }
+    __device__ __forceinline__ Out out_key(Stage k) const { return k; }
+    __device__ __forceinline__ ValT load_val(size_t g) const { return (ValT)g; }
+    __device__ __forceinline__ u8 load_aux(size_t, Stage) const { return 0; }
+};
+
 // First pass of a construction (reference a4 k-mer generation, include/kmer.hpp:119-224, fused into the sort):
 // element g is suffix idx(g); its key is the first kbits stream bits of that suffix; the digit is the low `drop` bits
 // and the key carried on is the rest; the dropped digit travels on as the auxiliary byte (the resolve step needs the

@@ -191,6 +191,7 @@ struct ResolveArgs {
     WordIdx widx;         // widx.lb > 0: sa[] holds sort words, the suffix is stored as its (owner, local index) field
     void* lcp_main;       // as in HeadsArgs: LCP of positions [main_lo, main_hi) goes to lcp_main[pos], the rest to lcp[pos]
     u64 main_lo, main_hi;
+    int lcp_wide;         // rounds >= 1: lcp[] holds 64-bit entries although IdxT is 32 bits wide (see HeadsArgs)
     int gsa;              // string set (reference construct_ss): code 0 separates strings; round-0 keys are cut at their first
                           // separator, equal keys that contain one are finished (rebucket_gsa_kmers, bucketing.hpp:137-143)
 };
@@ -393,8 +394,11 @@ __global__ void __launch_bounds__(RES_THREADS) resolve_kernel(ResolveArgs A) {
                 // same old bucket, different rank of suffix+h: the first h characters agree
                 const u64 pr = pos[i] - A.sa_lo;
                 IdxT* dst = (A.lcp_main != nullptr && pr >= A.main_lo && pr < A.main_hi) ? reinterpret_cast<IdxT*>(A.lcp_main) : lcp;
-                dst[pr] = (IdxT)(A.gsa ? stream_lcp_gsa(A.stream, n, A.lbits, suf[i], s, A.h)
-                                       : stream_lcp(A.stream, n, A.lbits, suf[i], s, A.h, A.padded_lcp != 0));
+                const u64 v = A.gsa ? stream_lcp_gsa(A.stream, n, A.lbits, suf[i], s, A.h) : stream_lcp(A.stream, n, A.lbits, suf[i], s, A.h, A.padded_lcp != 0);
+                if (A.lcp_wide)
+                    reinterpret_cast<u64*>(dst)[pr] = v;
+                else
+                    dst[pr] = (IdxT)v;
             }
         }
         const bool unresolved = !(head[i] && head[i + 1]);
@@ -539,6 +543,7 @@ struct HeadsArgs {
     void* lcp_main;        // sharded: positions [main_lo, main_hi) of this rank's range lie inside its OWN output block; their LCP
     u64 main_lo, main_hi;  //          goes straight to lcp_main[q] (the caller's block, pre-offset), only the rest to lcp[q]
     int kbits;             // bits of the complete key when it is not C whole characters (0: C * lbits)
+    int lcp_wide;          // lcp[] is the caller's array of 64-bit entries although PosT is 32 bits wide (no widening pass later)
     int word_shift;        // WORD: the keys are 64-bit words [carried key | suffix index field]: the key is word >> word_shift,
     WordIdx widx;          //       the suffix index widx.decode(word) (vals is not read)
 };
@@ -802,7 +807,18 @@ __global__ void __launch_bounds__(HD_THREADS) heads_kernel(HeadsArgs A) {
             }
         }
         const bool vec_ok = (reinterpret_cast<size_t>(lcp + q0) & 15) == 0;
-        if (routed) {
+        if (A.lcp_wide) {
+            u64* lw = reinterpret_cast<u64*>(A.lcp);
+            if (full_run && (reinterpret_cast<size_t>(lw + q0) & 15) == 0) {
+                ulonglong2* ol = reinterpret_cast<ulonglong2*>(lw + q0);
+#pragma unroll
+                for (int c = 0; c < HD_ITEMS / 2; ++c) __stcs(ol + c, make_ulonglong2((u64)l[2 * c], (u64)l[2 * c + 1]));
+            } else {
+#pragma unroll
+                for (int i = 0; i < HD_ITEMS; ++i)
+                    if (q0 + i < m) lw[q0 + i] = (u64)l[i];
+            }
+        } else if (routed) {
         } else if (full_run && vec_ok && sizeof(PosT) == 4) {
             uint4* ol = reinterpret_cast<uint4*>(lcp + q0);
 #pragma unroll
@@ -926,8 +942,9 @@ struct RoundKeyArgs {
     u64 pos_add;          // FIXUP: first SA position of this rank
 };
 
-// FIXUP (distributed rounds, before the first of them): the SA -> ISA step wrote every suffix's own position; the
-// unresolved ones must carry the position of their bucket's head instead: ISA[suffix] = pos_add + pos[head index].
+// FIXUP (before the first later round, when the SA -> ISA step scattered POSITIONS instead of bucket ids): the step wrote
+// every suffix's own position; the unresolved ones must carry the position of their bucket's head instead:
+// ISA[suffix] = pos_add + pos[head index] (distributed rounds: through the peer-mapped ISA blocks).
 template <typename IdxT, bool FIXUP = false>
 __global__ void __launch_bounds__(RES_THREADS) round_keys_kernel(RoundKeyArgs A) {
     __shared__ u64 s_wmax[RES_THREADS / 32];
@@ -989,7 +1006,12 @@ __global__ void __launch_bounds__(RES_THREADS) round_keys_kernel(RoundKeyArgs A)
         if (q >= A.m) break;
         const u64 b = mx[i] > pre ? mx[i] : pre;
         if (FIXUP) {
-            if (!A.head[q]) *A.pisa.at(suf[i]) = A.pos_add + (u64)pos[b];  // (heads already carry their own position)
+            if (!A.head[q]) {  // (heads already carry their own position)
+                if (A.pisa.p > 0)
+                    *A.pisa.at(suf[i]) = A.pos_add + (u64)pos[b];
+                else
+                    const_cast<IdxT*>(isa)[suf[i]] = (IdxT)(A.pos_add + (u64)pos[b]);
+            }
         } else {
             A.keys[q] = (b << A.kbits) | k2[i];
             vals[q] = (IdxT)suf[i];

@@ -249,3 +249,46 @@ def test_left_branching_chars_match_oracle_and_reference(eng):
             assert (sa.local_Lc == want).all()
             if O.have_ref() and t.size > 2:
                 assert (sa.local_Lc == O.ref_lc(t)).all()
+
+
+# ------------------------------------------------------------------------------------------- the partitioned SA -> ISA step (n >= 2^23)
+def _device_case(eng, t, index_bytes, lcp, k=0):
+    """device buffers in and out (used in place by the engine); certified by the device checker, i.e. the reference's
+    d_check_sa conditions + LCP by direct comparison over all positions -- the certificate is exact, so a pass means the
+    arrays are THE suffix / inverse / LCP arrays"""
+    import torch
+    dev = torch.device("cuda", 0)
+    n = t.size
+    d_t = torch.from_numpy(t).to(dev)
+    tdt = torch.int64 if index_bytes == 8 else torch.int32
+    out = [torch.full((n,), -1, dtype=tdt, device=dev) for _ in range(3)]
+    torch.cuda.synchronize()
+    eng.construct_ptr(d_t.data_ptr(), n, index_bytes, api.LCP if lcp else 0, k, out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr() if lcp else None,
+                      device=True)
+    st = eng.stats()
+    chk = eng.check_device_ptr(d_t.data_ptr(), n, index_bytes, out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr() if lcp else None)
+    assert chk["ok"], chk
+    return st, [o.cpu().numpy().view(np.uint64 if index_bytes == 8 else np.uint32) for o in out]
+
+
+@pytest.mark.parametrize("index_bytes", [4, 8])
+def test_partitioned_isa_step_scatters_positions_and_fixes_up_the_unresolved(eng, index_bytes):
+    """n >= 2^23: the SA -> ISA step partitions (suffix, POSITION) pairs generated on the fly and the unresolved suffixes get
+    their bucket head afterwards; a 64-bit caller's LCP is written 64 bits wide by the heads kernel.  k = 7: ~3 % of the
+    suffixes stay unresolved after the first sort (inside the list capacity); k = 5: most do (the list overflows and the
+    bucket-id array is produced after all); k = 0: a handful."""
+    n = (1 << 23) + 5
+    t = G.random_dna(n, 41)
+    for k, lo, hi in ((7, n // 200, n // 16), (5, n // 4, n), (0, 1, 4096)):
+        st, out = _device_case(eng, t, index_bytes, True, k)
+        assert lo <= st["unresolved_after_first"] <= hi, (k, st["unresolved_after_first"])
+        if k == 7:  # element-wise against the CPU oracle once
+            exp = O.construct(t, 64, 0, True)
+            assert (out[0] == exp["sa"]).all() and (out[1] == exp["isa"]).all() and (out[2] == exp["lcp"]).all()
+
+
+def test_partitioned_isa_step_on_repetitive_and_periodic_texts(eng):
+    for t in (G.periodic_text(b"abc", (1 << 23) // 3 + 11), G.repeats_text(1 << 21, 5)[: (1 << 23) + 1]):
+        for ib, lcp in ((8, True), (4, False)):
+            st, _ = _device_case(eng, t, ib, lcp)
+            assert st["rounds"] > 2
