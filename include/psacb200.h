@@ -105,6 +105,21 @@ int psacb200_construct_alphabet(psacb200_engine* e, const uint8_t* text, size_t 
 int psacb200_construct_device(psacb200_engine* e, const uint8_t* d_text, size_t n, int index_bytes, unsigned flags, unsigned k, void* d_sa,
                               void* d_isa, void* d_lcp);
 
+/* ---- texts over wide characters (reference suffix_array<int, index_t, LCP>::construct with int_alphabet,
+ *      include/alphabet.hpp:355-513; test/test_psac.cpp:277-304 "IntAlphabetMiss") ------------------------------------ */
+/* text: n characters of char_bytes (2 or 4) bytes each, signed (char_signed != 0) or unsigned; the characters are ordered by
+ * VALUE.  At most 255 distinct values may occur (else PSACB200_ERR_ARG): the text is reduced on the device to one byte per
+ * character (1 + rank of its value) and the byte construction runs on that -- SA / ISA / LCP depend only on the order and
+ * equality of the characters.  distinct_out (optional, room for 255) receives the values that occur in ascending order,
+ * *n_distinct their number (min / max of the reference's int_alphabet = first / last).  Outputs as psacb200_construct.
+ * (Not reproduced: with a 32-bit index_t and more than 16 bits per character the reference falls to k = 1, copies the raw,
+ * sign-extended characters (include/kmer.hpp:196-199) and misorders negative values.) */
+int psacb200_construct_wide(psacb200_engine* e, const void* text, size_t n, int char_bytes, int char_signed, int index_bytes, unsigned flags,
+                            unsigned k, void* sa_out, void* isa_out, void* lcp_out, int64_t* distinct_out, uint32_t* n_distinct);
+/* Same on DEVICE buffers (distinct_out / n_distinct stay host pointers). */
+int psacb200_construct_wide_device(psacb200_engine* e, const void* d_text, size_t n, int char_bytes, int char_signed, int index_bytes,
+                                   unsigned flags, unsigned k, void* d_sa, void* d_isa, void* d_lcp, int64_t* distinct_out, uint32_t* n_distinct);
+
 /* ---- generalized suffix array of a string set (reference suffix_array::construct_ss, include/suffix_array.hpp:269-363,
  *      on a simple_dstringset, include/stringset.hpp:33-152; golden vectors test/test_gsa.cpp:97-98) ---------------- */
 /* flat = the strings separated by the byte `sep` (runs of separators, leading and trailing ones are allowed and skipped, as

@@ -70,6 +70,27 @@ struct alphabet {
     }
 };
 
+// the reference's int_alphabet<IntType> (include/alphabet.hpp:355-502): the characters of a wide-character text are ordered
+// by value; the alphabet is the value range [min_char, max_char] that occurs
+template <typename IntType>
+struct int_alphabet {
+    IntType min_char, max_char;
+    unsigned long long sigma_;
+    unsigned bits_per_char_;
+    int_alphabet() : min_char(0), max_char(0), sigma_(0), bits_per_char_(0) {}
+    int_alphabet(IntType mn, IntType mx) : min_char(mn), max_char(mx), sigma_((unsigned long long)((long long)mx - (long long)mn) + 1), bits_per_char_(0) {
+        while ((1ull << bits_per_char_) < sigma_ + 1) ++bits_per_char_;  // ceillog2(sigma + 1), alphabet.hpp:398
+    }
+    unsigned long long sigma() const { return sigma_; }
+    unsigned bits_per_char() const { return bits_per_char_; }
+};
+
+// reference alphabet_helper (alphabet.hpp:509-513); here every character type wider than a byte takes the value-ordered path
+template <typename CharType>
+struct alphabet_helper {
+    using alphabet_type = typename std::conditional<sizeof(CharType) == 1, alphabet, int_alphabet<CharType>>::type;
+};
+
 // stand-in for simple_dstringset at p = 1 (reference include/stringset.hpp:33-152): the strings are the maximal runs of
 // non-separator characters of a flat text, which is copied once (the reference borrows it)
 class simple_dstringset {
@@ -86,7 +107,9 @@ public:
 template <typename char_t, typename index_t = std::size_t, bool _CONSTRUCT_LCP = false, bool _CONSTRUCT_LC = false>
 class suffix_array {
     static_assert(!_CONSTRUCT_LC || _CONSTRUCT_LCP, "the left-branching characters need the LCP array (reference suffix_array.hpp:1365-1383)");
-    static_assert(sizeof(char_t) == 1, "psacb200 handles 1-byte characters (the reference's alphabet<char> path)");
+    static_assert(sizeof(char_t) == 1 || sizeof(char_t) == 2 || sizeof(char_t) == 4, "characters of 1, 2 or 4 bytes");
+    static_assert(sizeof(char_t) == 1 || !_CONSTRUCT_LC, "left-branching characters are built for 1-byte texts");
+    using byte_text = std::integral_constant<bool, sizeof(char_t) == 1>;
     static_assert(sizeof(index_t) == 4 || sizeof(index_t) == 8, "index_t must be a 32- or 64-bit unsigned integer");
     static_assert(std::is_unsigned<index_t>::value, "index_t must be unsigned");
 
@@ -106,7 +129,7 @@ public:
     psacb200::comm comm;
     int p;
     using char_type = char_t;
-    using alphabet_type = psacb200::alphabet;
+    using alphabet_type = typename psacb200::alphabet_helper<char_t>::alphabet_type;
     alphabet_type alpha;
     std::vector<index_t> local_SA;
     std::vector<index_t> local_B;  // inverse suffix array, 0-based (reference: local_B after :460-464)
@@ -124,18 +147,16 @@ public:
     template <typename Iterator>
     void construct(Iterator begin, Iterator end, bool fast_resolval = true, unsigned int k = 0) {
         init_size((std::size_t)std::distance(begin, end));
-        const uint8_t* text = contiguous(begin, end);
-        ensure_engine();
-        check(psacb200_alphabet(engine_, text, n, alpha.mapping_table, &alpha.sigma_, &alpha.bits_per_char_));
-        run(text, fast_resolval, k, nullptr, _CONSTRUCT_LCP);
+        construct_impl(begin, end, fast_resolval, k, _CONSTRUCT_LCP, byte_text());
     }
 
-    // reference :365-366 (caller supplies the alphabet; only the ORDER of its codes matters)
+    // reference :365-366 (caller supplies the alphabet; only the ORDER of its codes matters; a wide-character text is ordered
+    // by value whatever range the alphabet names)
     template <typename Iterator>
     void construct(Iterator begin, Iterator end, bool fast_resolval, const alphabet_type& alphabet, unsigned int k) {
         init_size((std::size_t)std::distance(begin, end));
         alpha = alphabet;
-        run(contiguous(begin, end), fast_resolval, k, alpha.mapping_table, _CONSTRUCT_LCP);
+        construct_alpha_impl(begin, end, fast_resolval, k, byte_text());
     }
 
     // reference :490-641 -- L-tuple doubling; the final SA / ISA are the same arrays, no LCP is built (:555-567)
@@ -143,15 +164,13 @@ public:
     void construct_arr(Iterator begin, Iterator end, bool fast_resolval = true) {
         static_assert(L >= 2, "construct_arr needs L >= 2");
         init_size((std::size_t)std::distance(begin, end));
-        const uint8_t* text = contiguous(begin, end);
-        ensure_engine();
-        check(psacb200_alphabet(engine_, text, n, alpha.mapping_table, &alpha.sigma_, &alpha.bits_per_char_));
-        run(text, fast_resolval, 0, nullptr, false);
+        construct_impl(begin, end, fast_resolval, 0, false, byte_text());
     }
 
     // reference :269-363 -- generalized suffix array (+ LCP) of a string set: positions index the concatenation of the strings
     // without separators; identical suffixes of different strings are ordered by position.  Runs on the first GPU.
     void construct_ss(simple_dstringset& ss, const alphabet_type& alphabet) {
+        static_assert(sizeof(char_t) == 1, "string sets are 1-byte texts");
         alpha = alphabet;
         ensure_engine();
         const std::size_t cap = ss.flat.size();
@@ -171,6 +190,7 @@ public:
 
     // reference :232-243 -- <basename>.sa, .lcp (if built): raw little-endian index_t; .alpha: the used characters
     void write(const std::string& basename) const {
+        static_assert(sizeof(char_t) == 1, "the .alpha file format lists 1-byte characters");
         write_array(basename + ".sa", local_SA);
         if (_CONSTRUCT_LCP) write_array(basename + ".lcp", local_LCP);
         std::ofstream f(basename + ".alpha", std::ios::binary);
@@ -179,6 +199,7 @@ public:
     }
     // reference :245-265
     void read(const std::string& basename) {
+        static_assert(sizeof(char_t) == 1, "the .alpha file format lists 1-byte characters");
         read_array(basename + ".sa", local_SA);
         if (_CONSTRUCT_LCP) {
             read_array(basename + ".lcp", local_LCP);
@@ -251,6 +272,45 @@ private:
         staging_.assign(begin, end);
         return staging_.data();
     }
+    // ---- 1-byte characters
+    template <typename Iterator>
+    void construct_impl(Iterator begin, Iterator end, bool fast_resolval, unsigned k, bool want_lcp, std::true_type) {
+        const uint8_t* text = contiguous(begin, end);
+        ensure_engine();
+        check(psacb200_alphabet(engine_, text, n, alpha.mapping_table, &alpha.sigma_, &alpha.bits_per_char_));
+        run(text, fast_resolval, k, nullptr, want_lcp);
+    }
+    template <typename Iterator>
+    void construct_alpha_impl(Iterator begin, Iterator end, bool fast_resolval, unsigned k, std::true_type) {
+        run(contiguous(begin, end), fast_resolval, k, alpha.mapping_table, _CONSTRUCT_LCP);
+    }
+    // ---- 2- and 4-byte characters, ordered by value (reference int_alphabet); runs on the first GPU
+    template <typename Iterator>
+    void construct_impl(Iterator begin, Iterator end, bool fast_resolval, unsigned k, bool want_lcp, std::false_type) {
+        run_wide(begin, end, fast_resolval, k, want_lcp, true);
+    }
+    template <typename Iterator>
+    void construct_alpha_impl(Iterator begin, Iterator end, bool fast_resolval, unsigned k, std::false_type) {
+        run_wide(begin, end, fast_resolval, k, _CONSTRUCT_LCP, false);
+    }
+    template <typename Iterator>
+    void run_wide(Iterator begin, Iterator end, bool fast_resolval, unsigned k, bool want_lcp, bool set_alpha) {
+        ensure_engine();
+        wide_staging_.assign(begin, end);
+        local_SA.resize(n);
+        local_B.resize(n);
+        local_LCP.clear();
+        if (want_lcp) local_LCP.resize(n);
+        local_Lc.clear();
+        int64_t distinct[255];
+        uint32_t nd = 0;
+        const unsigned flags = (want_lcp ? PSACB200_LCP : 0u) | (fast_resolval ? PSACB200_FAST_RESOLVAL : 0u);
+        check(psacb200_construct_wide(engine_, wide_staging_.data(), n, (int)sizeof(char_t), std::is_signed<char_t>::value ? 1 : 0, (int)sizeof(index_t), flags, k,
+                                      local_SA.data(), local_B.data(), want_lcp ? (void*)local_LCP.data() : nullptr, distinct, &nd));
+        if (set_alpha && nd > 0) alpha = alphabet_type((char_t)distinct[0], (char_t)distinct[nd - 1]);  // from_sequence: [min, max] (alphabet.hpp:404-436)
+    }
+    std::vector<char_t> wide_staging_;
+
     void run(const uint8_t* text, bool fast_resolval, unsigned k, const uint8_t* lut, bool want_lcp) {
         ensure_engine();
         local_SA.resize(n);

@@ -212,6 +212,18 @@ def gsa_naive(flat, sep=ord("$")):
     return dict(sa=sa, isa=isa, lcp=lcp, n=m)
 
 
+def construct_wide(text, index_bits=64, want_lcp=False):
+    """Texts over wide characters (reference suffix_array<int, ...> with int_alphabet, include/alphabet.hpp:355-513: the
+    characters are ordered by VALUE).  SA / ISA / LCP depend only on the order and equality of the characters, so the port
+    ranks the distinct values (<= 255 of them) into bytes and runs `construct`; pinned to the unmodified reference in
+    tests/test_wide.py."""
+    t = np.ascontiguousarray(text)
+    vals, inv = np.unique(t, return_inverse=True)
+    if vals.size > 255:
+        raise ValueError("more than 255 distinct characters")
+    return construct((inv + 1).astype(np.uint8), index_bits, 0, want_lcp)
+
+
 def construct_arr(text, L, index_bits=64):
     t = _text(text)
     n = t.size
@@ -416,6 +428,19 @@ def ref_construct_ss(flat, sep=ord("$"), index_bytes=8, alpha_chars=None):
     if m < 0:
         raise RuntimeError("psacref_construct_ss rc=%d" % m)
     return dict(sa=sa[:m], isa=isa[:m], lcp=lcp[:m], n=m)
+
+
+def ref_construct_int(text, index_bytes=8, want_lcp=False):
+    """suffix_array<int, index_t, LCP>::construct of the UNMODIFIED reference at np=1 (int_alphabet path)"""
+    t = np.ascontiguousarray(text, np.int32)
+    n = t.size
+    dt = np.uint32 if index_bytes == 4 else np.uint64
+    sa, isa = np.zeros(n, dt), np.zeros(n, dt)
+    lcp = np.zeros(n, dt) if want_lcp else None
+    rc = ref().psacref_construct_int(_vp(t), C.c_size_t(n), C.c_int(index_bytes), C.c_int(1 if want_lcp else 0), _vp(sa), _vp(isa), _vp(lcp))
+    if rc != 0:
+        raise RuntimeError("psacref_construct_int rc=%d" % rc)
+    return dict(sa=sa, isa=isa, lcp=lcp)
 
 
 def ref_rand_dna(n, seed):

@@ -15,6 +15,7 @@
  *   lcp_from_sa (Kasai checker)                     include/lcp.hpp:46-77
  *   ansv / ansv_sequential                          include/ansv.hpp:47-65, 2042-2051
  *   construct_suffix_tree                           include/suffix_tree.hpp:413-499
+ *   suffix_array<int,...>::construct (int_alphabet)  include/alphabet.hpp:355-513
  *   suffix_array<...>::construct_ss (generalized SA) include/suffix_array.hpp:269-363, stringset.hpp:33-152
  */
 #include <mpi.h>
@@ -94,6 +95,22 @@ long run_construct_ss(const char* flat, size_t len, char sep, const char* alpha_
     return (long)m;
 }
 
+
+/* suffix_array<int, index_t, LCP>::construct at np=1: texts over wide characters go through int_alphabet
+ * (include/alphabet.hpp:355-513; test/test_psac.cpp:277-304 "IntAlphabetMiss") */
+template <typename index_t, bool LCP>
+int run_construct_int(const int* text, size_t n, void* sa_out, void* isa_out, void* lcp_out) {
+    cerr_mute mute(!g_verbose);
+    mxx::comm c;
+    suffix_array<int, index_t, LCP> sa(c);
+    std::vector<int> t(text, text + n);
+    sa.construct(t.begin(), t.end());
+    if (sa.local_SA.size() != n || sa.local_B.size() != n) return -3;
+    if (sa_out) std::memcpy(sa_out, sa.local_SA.data(), n * sizeof(index_t));
+    if (isa_out) std::memcpy(isa_out, sa.local_B.data(), n * sizeof(index_t));
+    if (LCP && lcp_out) std::memcpy(lcp_out, sa.local_LCP.data(), n * sizeof(index_t));
+    return 0;
+}
 
 } // namespace
 
@@ -292,6 +309,17 @@ long psacref_construct_ss(const char* flat, size_t len, char sep, const char* al
         return -1;
     } catch (const std::exception& e) {
         std::fprintf(stderr, "psacref_construct_ss: %s\n", e.what());
+        return -10;
+    }
+}
+
+int psacref_construct_int(const int* text, size_t n, int index_bytes, int want_lcp, void* sa_out, void* isa_out, void* lcp_out) {
+    try {
+        if (index_bytes == 4) return want_lcp ? run_construct_int<uint32_t, true>(text, n, sa_out, isa_out, lcp_out) : run_construct_int<uint32_t, false>(text, n, sa_out, isa_out, lcp_out);
+        if (index_bytes == 8) return want_lcp ? run_construct_int<uint64_t, true>(text, n, sa_out, isa_out, lcp_out) : run_construct_int<uint64_t, false>(text, n, sa_out, isa_out, lcp_out);
+        return -1;
+    } catch (const std::exception& e) {
+        std::fprintf(stderr, "psacref_construct_int: %s\n", e.what());
         return -10;
     }
 }

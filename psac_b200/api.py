@@ -97,6 +97,10 @@ def lib():
         L.psacb200_construct_device.argtypes = cargs
         L.psacb200_construct_alphabet.argtypes = cargs[:6] + [C.c_void_p] + cargs[6:]
         L.psacb200_sort_pairs.argtypes = [C.c_void_p] * 5 + [C.c_size_t] + [C.c_int] * 4
+        wargs = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_uint, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                 C.POINTER(C.c_uint32)]
+        L.psacb200_construct_wide.argtypes = wargs
+        L.psacb200_construct_wide_device.argtypes = wargs
         ssargs = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint8, C.c_int, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
         L.psacb200_construct_ss.argtypes = ssargs
         L.psacb200_construct_ss_device.argtypes = ssargs
@@ -224,6 +228,22 @@ class Engine:
             lut = np.ascontiguousarray(lut, np.uint8)
             _check(lib().psacb200_construct_alphabet(self._h, _ptr(t), n, index_bytes, flags, k, _ptr(lut), _ptr(sa), _ptr(isa), _ptr(lcp)))
         return dict(sa=sa, isa=isa, lcp=lcp)
+
+    def construct_wide(self, text, index_bytes=8, want_lcp=False, k=0):
+        """Text over 2- or 4-byte characters (numpy int16 / uint16 / int32 / uint32), ordered by value -- reference
+        suffix_array<int, ...> (int_alphabet).  Returns dict(sa, isa, lcp, distinct)."""
+        t = np.ascontiguousarray(text)
+        if t.dtype not in (np.int16, np.uint16, np.int32, np.uint32):
+            raise PsacError("construct_wide: characters must be 16- or 32-bit integers")
+        n = t.size
+        dt = np.uint32 if index_bytes == 4 else np.uint64
+        sa, isa = np.empty(n, dt), np.empty(n, dt)
+        lcp = np.empty(n, dt) if want_lcp else None
+        distinct = np.zeros(255, np.int64)
+        nd = C.c_uint32(0)
+        _check(lib().psacb200_construct_wide(self._h, _ptr(t), n, t.dtype.itemsize, 1 if t.dtype.kind == "i" else 0, index_bytes,
+                                             (LCP if want_lcp else 0) | FAST_RESOLVAL, k, _ptr(sa), _ptr(isa), _ptr(lcp), _ptr(distinct), C.byref(nd)))
+        return dict(sa=sa, isa=isa, lcp=lcp, distinct=distinct[: nd.value])
 
     def construct_ss(self, flat, sep=ord("$"), index_bytes=8, want_lcp=True, want_isa=True, lut=None):
         """Generalized suffix array of the `sep`-separated strings of `flat` (reference construct_ss, suffix_array.hpp:269-363).

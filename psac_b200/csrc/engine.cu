@@ -20,6 +20,7 @@
 #include "tree_kernels.cuh"
 #include "check_kernels.cuh"
 #include "gsa_kernels.cuh"
+#include "wide_kernels.cuh"
 
 using namespace psacb200;
 
@@ -792,7 +793,8 @@ void fill_phase_stats(psacb200_engine* e) {
 }
 
 int construct_entry(psacb200_engine* e, const u8* text, bool text_is_host, size_t n, int index_bytes, unsigned flags, unsigned k, const uint8_t* lut,
-                    void* sa_out, void* isa_out, void* lcp_out) {
+                    void* sa_out, void* isa_out, void* lcp_out, int out_host = -1) {
+    const bool out_is_host = out_host < 0 ? text_is_host : out_host != 0;  // (wide characters: the byte text is on the device already)
     if (!e) {
         set_last_error("null engine");
         return PSACB200_ERR_ARG;
@@ -831,11 +833,11 @@ int construct_entry(psacb200_engine* e, const u8* text, bool text_is_host, size_
             //  generic 64-bit-key path only when the LCP array is wanted; SA / ISA come out of the lean path unchanged:
             //  dense code 0 = 0xFF compares equal to the padding exactly as in the reference's zero-padded k-mers)
             if (carried_bits <= 32 && (!alpha.zero_code_used || !(flags & PSACB200_LCP)))
-                construct_core<u32, u32>(e, n, index_bytes, flags, alpha, C, sa_out, isa_out, lcp_out, text_is_host);
+                construct_core<u32, u32>(e, n, index_bytes, flags, alpha, C, sa_out, isa_out, lcp_out, out_is_host);
             else
-                construct_core<u32, u64>(e, n, index_bytes, flags, alpha, C, sa_out, isa_out, lcp_out, text_is_host);
+                construct_core<u32, u64>(e, n, index_bytes, flags, alpha, C, sa_out, isa_out, lcp_out, out_is_host);
         } else {
-            construct_core<u64, u64>(e, n, index_bytes, flags, alpha, C, sa_out, isa_out, lcp_out, text_is_host);
+            construct_core<u64, u64>(e, n, index_bytes, flags, alpha, C, sa_out, isa_out, lcp_out, out_is_host);
         }
         e->end(PH_TOTAL);
         PSAC_CUDA(cudaStreamSynchronize(e->stream));
@@ -878,6 +880,77 @@ int guarded(F&& f) {
         set_last_error(s);
         return PSACB200_ERR_INTERNAL;
     }
+}
+
+// ---- texts over wide characters (wide_kernels.cuh; reference suffix_array<int, ...> with int_alphabet)
+template <typename T>
+int wide_core(psacb200_engine* e, const void* text, bool text_is_host, size_t n, u32 flip, int index_bytes, unsigned flags, unsigned k, void* sa_out,
+              void* isa_out, void* lcp_out, int64_t* distinct_out, uint32_t* n_distinct, bool is_signed) {
+    cudaStream_t st = e->stream;
+    size_t* tot = &e->device_bytes;
+    const T* d_wide = reinterpret_cast<const T*>(text);
+    if (text_is_host) {
+        e->gsa[0].reserve(n * sizeof(T) + 64, tot);
+        PSAC_CUDA(cudaMemcpyAsync(e->gsa[0].p, text, n * sizeof(T), cudaMemcpyHostToDevice, st));
+        d_wide = e->gsa[0].as<T>();
+    }
+    e->gsa[3].reserve((WIDE_SLOTS + 2 + 256) * sizeof(u64), tot);
+    unsigned long long* gtab = e->gsa[3].as<unsigned long long>();
+    unsigned int* meta = reinterpret_cast<unsigned int*>(gtab + WIDE_SLOTS);
+    u32* d_table = reinterpret_cast<u32*>(gtab + WIDE_SLOTS + 2);
+    PSAC_CUDA(cudaMemsetAsync(gtab, 0, (WIDE_SLOTS + 2) * sizeof(u64), st));
+    wide_distinct_kernel<T><<<grid_for(e, n, 256, 8), 256, 0, st>>>(d_wide, n, flip, gtab, meta);
+    e->launches += 1;
+    PSAC_CUDA(cudaGetLastError());
+    u64* h = e->h_pinned;
+    PSAC_CUDA(cudaMemcpyAsync(h, gtab, (WIDE_SLOTS + 2) * sizeof(u64), cudaMemcpyDeviceToHost, st));
+    PSAC_CUDA(cudaStreamSynchronize(st));
+    const unsigned int* hm = reinterpret_cast<const unsigned int*>(h + WIDE_SLOTS);
+    std::vector<u32> keys;
+    for (int i = 0; i < WIDE_SLOTS; ++i)
+        if (h[i]) keys.push_back((u32)h[i]);
+    if (hm[1] != 0 || keys.size() > (size_t)WIDE_MAX_DISTINCT)
+        throw arg_failure{"more than 255 distinct characters: wide-character texts are reduced to one byte per character"};
+    std::sort(keys.begin(), keys.end());
+    if (n_distinct) *n_distinct = (uint32_t)keys.size();
+    if (distinct_out)
+        for (size_t i = 0; i < keys.size(); ++i) {
+            const u32 raw = keys[i] ^ flip;
+            distinct_out[i] = is_signed ? (sizeof(T) == 2 ? (int64_t)(int16_t)raw : (int64_t)(int32_t)raw) : (int64_t)raw;
+        }
+    u32* hk = reinterpret_cast<u32*>(h);
+    for (size_t i = 0; i < keys.size(); ++i) hk[i] = keys[i];
+    PSAC_CUDA(cudaMemcpyAsync(d_table, hk, keys.size() * sizeof(u32), cudaMemcpyHostToDevice, st));
+    e->text.reserve(n + 64, tot);
+    wide_map_kernel<T><<<grid_for(e, n, 256, 8), 256, 0, st>>>(d_wide, n, flip, d_table, (int)keys.size(), e->text.as<u8>());
+    e->launches += 1;
+    PSAC_CUDA(cudaGetLastError());
+    PSAC_CUDA(cudaStreamSynchronize(st));  // (h_pinned is reused by the construction)
+    uint8_t lut[256];
+    for (int c = 0; c < 256; ++c) lut[c] = (c >= 1 && c <= (int)keys.size()) ? (uint8_t)c : 0;
+    const uint64_t launches = e->launches;
+    const int rc = construct_entry(e, e->text.as<u8>(), false, n, index_bytes, flags, k, lut, sa_out, isa_out, lcp_out, text_is_host ? 1 : 0);
+    (void)launches;
+    return rc;
+}
+
+int wide_entry(psacb200_engine* e, const void* text, bool text_is_host, size_t n, int char_bytes, int char_signed, int index_bytes, unsigned flags,
+               unsigned k, void* sa_out, void* isa_out, void* lcp_out, int64_t* distinct_out, uint32_t* n_distinct) {
+    if (!e) {
+        set_last_error("null engine");
+        return PSACB200_ERR_ARG;
+    }
+    return guarded([&]() -> int {
+        if (char_bytes != 2 && char_bytes != 4) throw arg_failure{"char_bytes must be 2 or 4 (1-byte texts: psacb200_construct)"};
+        if (n_distinct) *n_distinct = 0;
+        if (n == 0) return PSACB200_OK;
+        if (!text || !sa_out) throw arg_failure{"null text / sa_out"};
+        PSAC_CUDA(cudaSetDevice(e->device));
+        const bool sg = char_signed != 0;
+        if (char_bytes == 2)
+            return wide_core<uint16_t>(e, text, text_is_host, n, sg ? 0x8000u : 0u, index_bytes, flags, k, sa_out, isa_out, lcp_out, distinct_out, n_distinct, sg);
+        return wide_core<uint32_t>(e, text, text_is_host, n, sg ? 0x80000000u : 0u, index_bytes, flags, k, sa_out, isa_out, lcp_out, distinct_out, n_distinct, sg);
+    });
 }
 
 // ---- generalized suffix array of a string set (gsa_kernels.cuh; reference construct_ss, suffix_array.hpp:269-363)
@@ -1270,6 +1343,16 @@ int psacb200_construct_alphabet(psacb200_engine* e, const uint8_t* text, size_t 
 int psacb200_construct_device(psacb200_engine* e, const uint8_t* d_text, size_t n, int index_bytes, unsigned flags, unsigned k, void* d_sa, void* d_isa,
                               void* d_lcp) {
     return construct_entry(e, d_text, false, n, index_bytes, flags, k, nullptr, d_sa, d_isa, d_lcp);
+}
+
+int psacb200_construct_wide(psacb200_engine* e, const void* text, size_t n, int char_bytes, int char_signed, int index_bytes, unsigned flags, unsigned k,
+                            void* sa_out, void* isa_out, void* lcp_out, int64_t* distinct_out, uint32_t* n_distinct) {
+    return wide_entry(e, text, true, n, char_bytes, char_signed, index_bytes, flags, k, sa_out, isa_out, lcp_out, distinct_out, n_distinct);
+}
+
+int psacb200_construct_wide_device(psacb200_engine* e, const void* d_text, size_t n, int char_bytes, int char_signed, int index_bytes, unsigned flags,
+                                   unsigned k, void* d_sa, void* d_isa, void* d_lcp, int64_t* distinct_out, uint32_t* n_distinct) {
+    return wide_entry(e, d_text, false, n, char_bytes, char_signed, index_bytes, flags, k, d_sa, d_isa, d_lcp, distinct_out, n_distinct);
 }
 
 int psacb200_construct_ss(psacb200_engine* e, const uint8_t* flat, size_t len, uint8_t sep, int index_bytes, unsigned flags, const uint8_t* lut,

@@ -79,6 +79,15 @@ int main() {
             for (size_t i = 0; i < 8; ++i)
                 if (sg.local_SA[i] != ex_gsa[i] || sg.local_LCP[i] != ex_lcp[i] || sg.local_B[sg.local_SA[i]] != i) return fail("GSA SimpleTiny");
         }
+        // wide characters ordered by value (reference test/test_psac.cpp:277-304 "IntAlphabetMiss")
+        {
+            const std::vector<int> str = {128, 3, 12345678, 12345678, 3, 12345678, 12345678, 3, 66000, 66000, 3};
+            psacb200::suffix_array<int, unsigned int, true> si(c);
+            si.construct(str.begin(), str.end());
+            for (size_t i = 0; i < 11; ++i)
+                if (si.local_SA[i] != golden[i] || si.local_LCP[i] != lcp[i]) return fail("IntAlphabetMiss");
+            if (si.alpha.min_char != 3 || si.alpha.max_char != 12345678 || si.alpha.bits_per_char() != 24) return fail("int_alphabet");
+        }
     } catch (const std::runtime_error& e) {
         if (std::strstr(e.what(), "no CUDA device") || std::strstr(e.what(), "CUDA")) {
             std::fprintf(stderr, "no GPU: %s\n", e.what());
