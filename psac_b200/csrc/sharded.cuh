@@ -2185,7 +2185,8 @@ void suffix_tree_core(psacb200_engine* e, const ShardComm* C, const u8* d_text_l
     PSAC_CUDA(cudaMemsetAsync(d_cur, 0, 17 * sizeof(u64), st));
     A.q.cursor = d_cur;
     A.q.overflow = d_cur + 16;
-    PSAC_CUDA(cudaMemsetAsync(d_nodes, 0, width * n_local * sizeof(u64), st));
+    // (small alphabets: the tile kernel assembles its rows in shared memory and writes every row of the table itself)
+    if (!tree_tile_writes_all_rows<IdxT>(n, alpha.sigma)) PSAC_CUDA(cudaMemsetAsync(d_nodes, 0, width * n_local * sizeof(u64), st));
     if (C == nullptr) {
         // one GPU: min-tree in a private buffer, nothing is queued
         TreeLayout L = tree_layout<IdxT>(n, 1);

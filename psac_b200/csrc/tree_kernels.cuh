@@ -497,12 +497,22 @@ __global__ void __launch_bounds__(256) ansv_list_kernel(S sr, u64 g0, int left_m
 // successor lie inside the tile are finished from shared memory; the others go on the list (tree_list_kernel)
 // (V = type of the values in shared memory: 32 bits whenever the text is shorter than 2^32 -- LCP values are below n --, which
 //  doubles the tile)
-template <typename IdxT, typename V, class S>
-__global__ void __launch_bounds__(256, 2) suffix_tree_tile_kernel(TreeFusedArgs<IdxT> A, S sr, AnsvList L) {
+// STAGE: the child-table rows of the tile are assembled in shared memory and leave as one coalesced stream.  A position that
+// is finished here has its matches -- hence its parent -- inside the tile, so every edge the tile kernel emits lands in the
+// tile's own rows; the table needs no clearing pass, and the scattered 8-byte stores into 40-byte rows (a read-modify-write of
+// a DRAM sector each) disappear.  Needs (sigma + 1) * TILE * 8 bytes next to the sparse table: small alphabets (DNA).
+template <typename IdxT, typename V, class S, bool STAGE>
+__global__ void __launch_bounds__(STAGE ? 1024 : 256, STAGE ? 1 : 2) suffix_tree_tile_kernel(TreeFusedArgs<IdxT> A, S sr, AnsvList L) {
     extern __shared__ __align__(16) unsigned char ansv_smem[];
     V* M = reinterpret_cast<V*>(ansv_smem);
     using Tile = AnsvTile<V>;
     const u64 t0 = (u64)blockIdx.x * Tile::TILE;
+    u64* rows = reinterpret_cast<u64*>(ansv_smem + Tile::SMEM);  // [TILE][sigma + 1] (STAGE)
+    const u32 width = A.sigma + 1;
+    if (STAGE) {
+        ulonglong2* rz = reinterpret_cast<ulonglong2*>(rows);
+        for (u32 e = threadIdx.x; e < (u32)Tile::TILE * width / 2; e += blockDim.x) rz[e] = make_ulonglong2(0ull, 0ull);
+    }
     ansv_tile_build<IdxT, V>(M, A.lcp, t0, A.m);
     const Tile tile{M};
     const u64 n = A.n;
@@ -556,14 +566,38 @@ __global__ void __launch_bounds__(256, 2) suffix_tree_tile_kernel(TreeFusedArgs<
             parent = gi + 1;
             lcp_val = next;
         }
-        tree_emit_dist<IdxT>(A, parent, n + gi, sa_i, lcp_val);
+        // (STAGE: parent - (g0 + t0) is the parent's row inside the tile: l, j, j + 1 or r)
+        auto emit = [&](u64 par, u64 child, u64 lv) {
+            if (STAGE) {
+                const u64 ci = sa_i + lv;
+                const u64 col = ci < n ? stream_extract(A.stream, ci, A.lbits, A.lbits) + A.code_add : 0;
+                rows[(par - (A.g0 + t0)) * width + col] = child;
+            } else {
+                tree_emit_dist<IdxT>(A, par, child, sa_i, lv);
+            }
+        };
+        emit(parent, n + gi, lcp_val);
         // ---- internal node gi (suffix_tree.hpp:146-222)
         if (lcp_i == 0) continue;
         if (left_val >= right_val) {
             if (left_val == lcp_i) continue;
-            tree_emit_dist<IdxT>(A, lnsv, gi, sa_i, left_val);
+            emit(lnsv, gi, left_val);
         } else {
-            tree_emit_dist<IdxT>(A, rnsv, gi, sa_i, right_val);
+            emit(rnsv, gi, right_val);
+        }
+    }
+    if (STAGE) {
+        __syncthreads();
+        const u64 valid_rows = A.m - t0 < (u64)Tile::TILE ? A.m - t0 : (u64)Tile::TILE;
+        const u64 cells = valid_rows * width;
+        u64* out = A.nodes + t0 * (u64)width;  // (t0 is a multiple of the tile: 16-byte aligned whenever the table is)
+        if ((reinterpret_cast<size_t>(out) & 15) == 0) {
+            const ulonglong2* src2 = reinterpret_cast<const ulonglong2*>(rows);
+            ulonglong2* out2 = reinterpret_cast<ulonglong2*>(out);
+            for (u64 e = threadIdx.x; e < cells / 2; e += blockDim.x) __stcs(out2 + e, src2[e]);
+            if ((cells & 1) && threadIdx.x == 0) out[cells - 1] = rows[cells - 1];
+        } else {
+            for (u64 e = threadIdx.x; e < cells; e += blockDim.x) out[e] = rows[e];
         }
     }
 }
@@ -610,18 +644,39 @@ void launch_ansv_tile(const S& sr, const T* vals, u64 g0, u64 m, int left_mode, 
     ansv_list_kernel<T, S><<<sms * 8, 256, 0, st>>>(sr, g0, left_mode, right_mode, nonsv, left, right, L);
     PSAC_CUDA(cudaGetLastError());
 }
+// shared memory the staged rows may take next to the sparse table (the static s_feq array is on top of both)
+constexpr size_t TREE_STAGE_BUDGET = 200 * 1024;
+template <typename V>
+static inline bool tree_rows_staged(u32 sigma) {
+    return AnsvTile<V>::SMEM + (size_t)(sigma + 1) * AnsvTile<V>::TILE * sizeof(u64) <= TREE_STAGE_BUDGET && !getenv("PSACB200_NO_TREE_STAGE");
+}
+// does the tile kernel write every row of the table itself (no clearing pass needed)?
+template <typename IdxT>
+static inline bool tree_tile_writes_all_rows(u64 n, u32 sigma) {
+    return (sizeof(IdxT) == 8 && n <= (1ull << 32)) ? tree_rows_staged<u32>(sigma) : tree_rows_staged<IdxT>(sigma);
+}
+
 template <typename IdxT, typename V, class S>
 void launch_tree_tile_v(const TreeFusedArgs<IdxT>& A, const S& sr, AnsvList L, int sms, cudaStream_t st) {
-    auto kern = suffix_tree_tile_kernel<IdxT, V, S>;
+    const bool stage = tree_rows_staged<V>(A.sigma);
+    auto kern = suffix_tree_tile_kernel<IdxT, V, S, false>;
+    auto kern_stage = suffix_tree_tile_kernel<IdxT, V, S, true>;
     static bool seen[64] = {};
     int d = 0;
     cudaGetDevice(&d);
     if (!seen[d & 63]) {
         seen[d & 63] = true;
         PSAC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AnsvTile<V>::SMEM));
+        PSAC_CUDA(cudaFuncSetAttribute(kern_stage, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TREE_STAGE_BUDGET));
     }
     PSAC_CUDA(cudaMemsetAsync(L.count, 0, sizeof(u64), st));
-    kern<<<(unsigned)((A.m + AnsvTile<V>::TILE - 1) / AnsvTile<V>::TILE), 256, AnsvTile<V>::SMEM, st>>>(A, sr, L);
+    const unsigned tiles = (unsigned)((A.m + AnsvTile<V>::TILE - 1) / AnsvTile<V>::TILE);
+    // one CTA per SM (the shared memory is full): 1024 threads -- measured at 2^29: 512 threads 40.6 ms, 1024 threads 35.0 ms
+    static const int stage_threads = getenv("PSACB200_TREE_THREADS") ? atoi(getenv("PSACB200_TREE_THREADS")) : 1024;
+    if (stage)
+        kern_stage<<<tiles, stage_threads, AnsvTile<V>::SMEM + (size_t)(A.sigma + 1) * AnsvTile<V>::TILE * sizeof(u64), st>>>(A, sr, L);
+    else
+        kern<<<tiles, 256, AnsvTile<V>::SMEM, st>>>(A, sr, L);
     tree_list_kernel<IdxT, S><<<sms * 8, 256, 0, st>>>(A, sr, L);
     PSAC_CUDA(cudaGetLastError());
 }
