@@ -736,8 +736,8 @@ u8* upload_inverse_codes(psacb200_engine* e, const Alphabet& alpha, const u64* h
     memset(h, 0, 256);
     for (int c = 255; c >= 0; --c)
         if (hist[c]) h[alpha.dense.code[c]] = (u8)c;
-    e->tb[1].reserve(4096, &e->device_bytes);
-    u8* d = e->tb[1].as<u8>() + 3072;
+    e->tb[1].reserve(8192 + 256, &e->device_bytes);
+    u8* d = e->tb[1].as<u8>() + 8192;  // (behind the slot of the sharded searcher's table, sharded.cuh dist_search_setup)
     PSAC_CUDA(cudaMemcpyAsync(d, h, 256, cudaMemcpyHostToDevice, e->stream));
     return d;
 }

@@ -2111,7 +2111,7 @@ DistSearch<T> dist_search_setup(psacb200_engine* e, const ShardComm& C, const T*
     PSAC_NCCL(g_nccl.AllGather(d_min + me, d_min, 1, ncclUint64, C.comm, st));  // (also: every rank's tree is complete before anybody searches it)
     PSAC_CUDA(cudaMemcpyAsync(e->h_pinned + 64, d_min, (size_t)p * sizeof(u64), cudaMemcpyDeviceToHost, st));
     PSAC_CUDA(cudaStreamSynchronize(st));
-    static_assert(sizeof(DistTreeTable<T>) <= 4096, "table size");
+    static_assert(sizeof(DistTreeTable<T>) <= 8192, "table size");
     DistTreeTable<T> tab{};
     tab.p = p;
     for (int r = 0; r < p; ++r) {
@@ -2122,8 +2122,8 @@ DistSearch<T> dist_search_setup(psacb200_engine* e, const ShardComm& C, const T*
         tab.start[r] = blk.start(r);
     }
     tab.start[p] = n;
-    e->tb[1].reserve(4096, &e->device_bytes);
-    memcpy(e->h_pinned + 6144, &tab, sizeof(tab));  // (pinned staging; at most 4096 bytes from word 6144)
+    e->tb[1].reserve(8192 + 256, &e->device_bytes);
+    memcpy(e->h_pinned + 6144, &tab, sizeof(tab));  // (pinned staging; at most 8192 bytes from word 6144 of 8192)
     PSAC_CUDA(cudaMemcpyAsync(e->tb[1].p, e->h_pinned + 6144, sizeof(tab), cudaMemcpyHostToDevice, st));
     DistSearch<T> sr{};
     sr.D = e->tb[1].as<DistTreeTable<T>>();

@@ -19,8 +19,13 @@
 
 namespace psacb200 {
 
-constexpr int ANSV_FAN = 32;
-constexpr int ANSV_MAX_LEVELS = 9;
+// Fan-out of the block-minimum tree.  An exact search scans the rest of its block at every level it climbs and one block at
+// every level it descends, one dependent load per entry: ~ FAN / 2 * 2 * log_FAN(distance) loads.  8 instead of 32 cuts that
+// chain for the far matches the list kernels are left with (the tree takes n / 7 instead of n / 31 extra entries).  Measured at
+// 2^29 (tree / standalone ANSV): fan-out 32: 35.0 / 36.0 ms, 8: 32.9 / 31.9 ms, 4: 33.4 / 32.6 ms.
+constexpr int ANSV_FAN_LOG = 3;
+constexpr int ANSV_FAN = 1 << ANSV_FAN_LOG;
+constexpr int ANSV_MAX_LEVELS = 14;
 constexpr u64 ANSV_NONE = ~0ull;
 
 template <typename T>
@@ -80,7 +85,7 @@ __device__ __noinline__ u64 ansv_search(const MinTree<T>& t, u64 i, T x) {
             break;
         }
         if (lv + 1 >= t.levels) return ANSV_NONE;
-        p >>= 5;
+        p >>= ANSV_FAN_LOG;
         ++lv;
     }
     // ---- descend: inside block p of level lv take the child nearest to i that qualifies (the block's minimum does)
