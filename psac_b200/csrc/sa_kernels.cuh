@@ -806,8 +806,46 @@ __global__ void __launch_bounds__(HD_THREADS) heads_kernel(HeadsArgs A) {
                     if (q0 + i < m) ((q0 + i >= A.main_lo && q0 + i < A.main_hi) ? lm : lcp)[q0 + i] = (PosT)l[i];
             }
         }
+        // A thread's run of 16 entries is 64 or 128 contiguous bytes: written thread by thread, one store instruction of a warp
+        // touches 32 different lines, half a sector in each, and the L2 request rate (not DRAM) bounds the kernel.  So a warp
+        // whose 512 entries are complete and go to one array transposes them through shared memory (rows padded by 16 bytes:
+        // conflict-free both ways) and stores 512 contiguous bytes per instruction.
+        bool transposed = false;
+        {
+            constexpr int HD_ROW_MAX = HD_ITEMS * 8 + 16;
+            __shared__ __align__(16) unsigned char s_tr[HD_THREADS / 32][32 * HD_ROW_MAX];
+            const int es = (A.lcp_wide || sizeof(PosT) == 8) ? 8 : 4;  // bytes per entry of the destination array
+            const u64 w0 = q0 - (u64)lane * HD_ITEMS, w1 = w0 + 32 * HD_ITEMS;
+            unsigned char* base = reinterpret_cast<unsigned char*>(A.lcp);
+            if (A.lcp_main != nullptr) {
+                if (w0 >= A.main_lo && w1 <= A.main_hi)
+                    base = reinterpret_cast<unsigned char*>(A.lcp_main);
+                else if (!(w1 <= A.main_lo || w0 >= A.main_hi))
+                    base = nullptr;  // the warp straddles the edge of the block: thread by thread below
+            }
+            if (w1 <= m && base != nullptr && ((reinterpret_cast<size_t>(base) + w0 * es) & 15) == 0) {  // (warp-uniform)
+                const int row = HD_ITEMS * es + 16;
+                unsigned char* mine = s_tr[warp] + lane * row;
+                if (es == 8) {
+#pragma unroll
+                    for (int c = 0; c < HD_ITEMS / 2; ++c) reinterpret_cast<ulonglong2*>(mine)[c] = make_ulonglong2((u64)l[2 * c], (u64)l[2 * c + 1]);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < HD_ITEMS / 4; ++c) reinterpret_cast<uint4*>(mine)[c] = make_uint4(l[4 * c], l[4 * c + 1], l[4 * c + 2], l[4 * c + 3]);
+                }
+                __syncwarp();
+                const int cpt = es;  // 16-byte chunks per thread row (HD_ITEMS * es / 16)
+                uint4* dst = reinterpret_cast<uint4*>(base + w0 * es);
+                for (int g = lane; g < 32 * cpt; g += 32) {
+                    const int t = g / cpt, c = g - t * cpt;
+                    __stcs(dst + g, *reinterpret_cast<const uint4*>(s_tr[warp] + t * row + c * 16));
+                }
+                transposed = true;
+            }
+        }
         const bool vec_ok = (reinterpret_cast<size_t>(lcp + q0) & 15) == 0;
-        if (A.lcp_wide) {
+        if (transposed) {
+        } else if (A.lcp_wide) {
             u64* lw = reinterpret_cast<u64*>(A.lcp);
             if (full_run && (reinterpret_cast<size_t>(lw + q0) & 15) == 0) {
                 ulonglong2* ol = reinterpret_cast<ulonglong2*>(lw + q0);
