@@ -167,7 +167,7 @@ def main_tree(args, rank, world, local_rank):
                 n_total, int(cnt[1].item())),
             "cross_rank_edges_rank0": stats["unresolved_after_first"] if sharded else 0},
         "gpu_launches": launches, "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "suffix_tree_fused_kernel + table memset (child table fill with on-the-fly ANSV)", "achieved": fill_bytes / (tree_kernel_ms * 1e-3) / 1e9,
+        "roofline": {"bound": "hbm", "kernel": "suffix_tree_tile_kernel + tree_list_kernel (child table fill with on-the-fly ANSV; DNA: rows assembled in shared memory, no clearing pass)", "achieved": fill_bytes / (tree_kernel_ms * 1e-3) / 1e9,
                      "peak": peak, "unit": "GB/s", "frac": fill_bytes / (tree_kernel_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
                      "bytes_per_launch": fill_bytes, "ms_per_launch": tree_kernel_ms},
         "phases_ms": {"construct_sa_isa_lcp": round(ms_c, 3), "suffix_tree": round(ms_t, 3), "ansv_standalone_left_furthest_eq_right_nearest_sm": round(ms_ansv, 3)},
