@@ -18,8 +18,6 @@ def main_tree(args, rank, world, local_rank):
     from bench import ClockSampler, measured_peaks, reference_run, SEEDS, METRIC
     from psac_b200 import api, textgen as G
 
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device -- psac-b200 has no CPU path")
     log2n = args.log2n or 29
     n = 1 << log2n
     seed = SEEDS[5]
@@ -45,6 +43,8 @@ def main_tree(args, rank, world, local_rank):
         print(json.dumps(line), flush=True)
         return
 
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- psac-b200 has no CPU path")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     sharded = world > 1
