@@ -54,6 +54,17 @@ def test_null_engine_is_an_error_not_a_crash():
     assert rc < 0 and b"null" in L.psacb200_last_error()
 
 
+def test_new_entry_points_reject_a_null_engine():
+    L = api.lib()
+    buf = np.zeros(8, np.uint64)
+    n_out = C.c_uint64(7)
+    rc = L.psacb200_construct_ss(None, None, 0, C.c_uint8(36), 8, 0, None, buf.ctypes.data_as(C.c_void_p), None, None, C.byref(n_out))
+    assert rc < 0 and b"null" in L.psacb200_last_error()
+    nd = C.c_uint32(0)
+    rc = L.psacb200_construct_wide(None, None, 0, 4, 1, 8, 0, 0, buf.ctypes.data_as(C.c_void_p), None, None, None, C.byref(nd))
+    assert rc < 0 and b"null" in L.psacb200_last_error()
+
+
 def _build_cpp_shim_test(tmp_path):
     import subprocess
     exe = str(tmp_path / "test_shim")
