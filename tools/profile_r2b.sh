@@ -1,5 +1,8 @@
 #!/bin/bash
 # Final round-2 measurements behind profiles/r2b_* (run from the repo root on a B200 box through gpurun; one GPU).
+# Of this script the bench commands and the ncu LAUNCH LIST were run for the committed r2b files (each in its own gpurun call);
+# the three `--set full` captures below were NOT run any more (the round's GPU budget was spent): the full captures under
+# profiles/r2_* are of kernels that did not change afterwards (segmented scatter, pass-1 scatter, ISA scatter).
 # Numbers printed by a run under ncu are never bench values.
 set -u
 mkdir -p gpurun_out
